@@ -1,0 +1,262 @@
+/*
+ * mms_b200.h -- C ABI of libmms_b200.so: hand-written sm_100a kernels for the hot path of
+ * 17LiQi/MultimodalSignal (CnnGruAttentionModel training step + resample/windowing).
+ *
+ * The reference has no FFI of its own (pure Python / torch.nn); the boundary
+ * it offers is its Python API.  Every entry point below therefore replaces a *library call
+ * site* of the reference, cited as file:line into /root/reference.  The Python host side
+ * (the multimodalsignal_b200 package) binds these with ctypes and keeps the reference's class and
+ * function signatures.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative MMS_E_* code; mms_last_error()
+ *     returns a thread-local description of the most recent failure;
+ *   - all pointers are DEVICE pointers unless the parameter name ends in _host;
+ *   - nothing here allocates, frees or synchronises: workspaces are caller-provided (sizes
+ *     from the *_workspace_bytes functions) and every launch goes to the cudaStream_t given
+ *     (passed as void* so that this header needs no CUDA headers);
+ *   - there is no CPU fallback: mms_init() fails unless the device is compute capability 10.x.
+ *   - tensors are contiguous float32 unless stated otherwise.
+ */
+#ifndef MMS_B200_H
+#define MMS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMS_OK 0
+#define MMS_E_INVALID (-1)      /* bad argument / unsupported shape            */
+#define MMS_E_CUDA (-2)         /* a CUDA runtime call or launch failed        */
+#define MMS_E_ARCH (-3)         /* device is not sm_100 (no fallback exists)   */
+#define MMS_E_WORKSPACE (-4)    /* workspace too small                         */
+
+typedef void* mms_stream_t;     /* cudaStream_t */
+
+int mms_version(void);
+const char* mms_last_error(void);
+/* Select `device`, verify it is sm_100 (B200) and raise the dynamic shared-memory limits of
+ * the kernels that need it.  Must be called once per process before any other function. */
+int mms_init(int device);
+
+/* ------------------------------------------------------------------------------------------
+ * Model description (reference models.py:39-40 constructor arguments + call-time facts).
+ * Conv widths 16 / k7 / k5 and the 64-wide classifier hidden layer are hard-coded in the
+ * reference (models.py:46,50,67) and therefore here.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t batch;          /* B                                                        */
+    int32_t in_channels;    /* C  = len(CHANNELS_TO_USE), main.py:47,116                */
+    int32_t seq_len;        /* T  = window samples (3840 @64 Hz, 7680 @128 Hz)          */
+    int32_t num_classes;    /* 2 (stress_binary) or 3 (ternary), <= 8                   */
+    int32_t cnn_out;        /* cnn_out_channels, models.py:39 (32)                      */
+    int32_t hidden;         /* gru_hidden_size (64 or 32)                               */
+    int32_t layers;         /* gru_num_layers (>= 1)                                    */
+    int32_t training;       /* 1: batch-stat BN + dropout (model.train()), 0: eval      */
+    int32_t attention;      /* 1: ChannelAttention gate, 0: cnn_gru baseline*/
+    int32_t need_grad;      /* 1: keep activations for mms_cnngru_backward              */
+    float dropout_p;        /* models.py:40; applied between GRU layers and in the head */
+    uint64_t rng_seed;      /* dropout stream seed                                      */
+    uint64_t rng_offset;    /* dropout stream offset used when rng_offset_dev == NULL   */
+    const int64_t* rng_offset_dev; /* optional device counter read by the kernels
+                                      (the fused train step passes its Adam step count) */
+} mms_cnngru_desc;
+
+/* Flat parameter buffer.  The model's parameters live in ONE float32 buffer so that Adam and
+ * the gradient all-reduce are single launches.  Segment order (each segment 16-byte aligned):
+ *   0 ca_w1   [C/4, C]      channel_attention.fc.0.weight      models.py:18
+ *   1 ca_w2   [C, C/4]      channel_attention.fc.2.weight      models.py:20
+ *   2 conv1_w [16, C, 7]    cnn_encoder.0.weight               models.py:46
+ *   3 bn1_g [16]  4 bn1_b [16]                                  models.py:47
+ *   5 conv2_w [O, 16, 5]    cnn_encoder.4.weight               models.py:50
+ *   6 bn2_g [O]   7 bn2_b [O]                                   models.py:51
+ *   then for each GRU layer l (models.py:56-63), both directions adjacent (forward first):
+ *   8+4l w_ih [2][3H, I_l]   9+4l w_hh [2][3H, H]   10+4l b_ih [2][3H]   11+4l b_hh [2][3H]
+ *   then fc0_w [64, 2H], fc0_b [64], fc3_w [nc, 64], fc3_b [nc]  models.py:66-71
+ * offsets/sizes are in floats.  Returns the number of segments (or < 0). */
+#define MMS_MAX_SEGMENTS 64
+int mms_cnngru_param_layout(const mms_cnngru_desc* d, int64_t* offsets_host, int64_t* sizes_host,
+                            int32_t max_segments, int64_t* total_floats_host);
+
+/* BatchNorm buffers: bn_buffers = [running_mean1[16] | running_var1[16] | running_mean2[O] |
+ * running_var2[O]] float32, num_batches_tracked = int64[2] (state_dict entries
+ * cnn_encoder.{1,5}.running_mean/.running_var/.num_batches_tracked). */
+
+int64_t mms_cnngru_workspace_bytes(const mms_cnngru_desc* d);
+
+/* models.py:73-81 forward.  x [B,C,T] -> logits [B,nc].  In training mode the workspace keeps
+ * every activation the backward needs and the BN running statistics are updated. */
+int mms_cnngru_forward(const mms_cnngru_desc* d, const float* x, const float* params,
+                       float* bn_buffers, int64_t* num_batches_tracked, void* workspace,
+                       float* logits, mms_stream_t stream);
+
+/* trainer.py:148 loss.backward() from dlogits [B,nc]: adds every parameter gradient into
+ * grads (same flat layout as params; the caller zeroes it, trainer.py:144 zero_grad).
+ * dx may be NULL (inputs do not require grad in the reference, trainer.py:140). */
+int mms_cnngru_backward(const mms_cnngru_desc* d, const float* x, const float* params,
+                        const float* bn_buffers, void* workspace, const float* dlogits,
+                        float* grads, float* dx, mms_stream_t stream);
+
+/* trainer.py:69,147 CrossEntropyLoss() (mean): loss_out[0] = mean_b(lse - logit[y]),
+ * dlogits = (softmax - onehot)/B (NULL to skip).  If loss_sum_accum != NULL it receives
+ * += loss * B in float64 (trainer.py:152 accumulates loss.item()*batch_size on the host;
+ * this keeps the sum on the device so that a step needs no sync). */
+int mms_cross_entropy(const float* logits, const int64_t* labels, int32_t batch, int32_t num_classes,
+                      float* loss_out, float* dlogits, double* loss_sum_accum, mms_stream_t stream);
+
+/* trainer.py:68,149 torch.optim.Adam (coupled L2 weight decay) over the flat buffer.
+ * step_dev holds the number of steps already taken; the kernel uses step_dev+1 for the bias
+ * corrections and increments it.  lr_dev is a device scalar (ReduceLROnPlateau writes it,
+ * trainer.py:72-77,160).  scratch_dev: one int32, zero-initialised. */
+int mms_adam_flat_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                       int64_t n, const float* lr_dev, float beta1, float beta2, float eps,
+                       float weight_decay, int64_t* step_dev, int32_t* scratch_dev, mms_stream_t stream);
+
+/* One whole training step, trainer.py:144-149: zero_grad, forward, CE, backward, Adam.
+ * (With world_size > 1 the host calls forward/backward/adam separately around its NCCL
+ * all-reduce instead.) */
+int mms_cnngru_train_step(const mms_cnngru_desc* d, const float* x, const int64_t* labels,
+                          float* params, float* grads, float* exp_avg, float* exp_avg_sq,
+                          float* bn_buffers, int64_t* num_batches_tracked, void* workspace,
+                          float* logits, float* loss_out, double* loss_sum_accum,
+                          const float* lr_dev, float beta1, float beta2, float eps, float weight_decay,
+                          int64_t* step_dev, int32_t* scratch_dev, mms_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Operator-level entry points (the same kernels the composed calls launch), for unit parity
+ * tests and for callers that use one layer on its own.
+ * ---------------------------------------------------------------------------------------- */
+
+/* models.py:24-31 ChannelAttention.forward.  hidden = C/4 may be 0 (gate == 0.5).
+ * mean_out/gate_out [B,C]; y may be NULL (gate only; the model folds the gate into conv1). */
+int mms_chan_attn_fwd(const float* x, const float* w1, const float* w2, int32_t B, int32_t C, int32_t T,
+                      float* mean_out, float* gate_out, float* y, mms_stream_t stream);
+/* Backward of the above: dy [B,C,T] -> dx [B,C,T] (may be NULL), dw1, dw2 (+=). scratch: 4*B*C floats. */
+int mms_chan_attn_bwd(const float* x, const float* dy, const float* w1, const float* w2,
+                      const float* mean, const float* gate, int32_t B, int32_t C, int32_t T,
+                      float* dx, float* dw1, float* dw2, float* scratch, mms_stream_t stream);
+
+/* models.py:46 / :50  Conv1d(bias=False).  which = 1: k7 s2 p3 (C_in = any <= 16, C_out 16);
+ * which = 2: k5 s2 p2 (C_in 16, C_out = cnn_out).  gate [B,C_in] optional (x*gate fused).
+ * stats (float64 [2][C_out]: sum, sum of squares over (B,L_out)) optional, accumulated (+=). */
+int mms_conv1d_fwd(int32_t which, const float* x, const float* w, const float* gate, int32_t B,
+                   int32_t c_in, int32_t c_out, int32_t l_in, float* y, double* stats, mms_stream_t stream);
+/* dgrad: dy [B,C_out,L_out] -> dx [B,C_in,L_in] (may be NULL) and, if xdot != NULL,
+ * dgate[b,c] += sum_t dx[b,c,t]*xdot[b,c,t] (the only part of conv1's dgrad training needs). */
+int mms_conv1d_dgrad(int32_t which, const float* dy, const float* w, int32_t B, int32_t c_in, int32_t c_out,
+                     int32_t l_in, float* dx, const float* xdot, float* dgate, mms_stream_t stream);
+/* wgrad: dw[o,c,k] += sum_{b,l} dy[b,o,l] * gate[b,c] * x[b,c,s*l+k-p]. */
+int mms_conv1d_wgrad(int32_t which, const float* x, const float* dy, const float* gate, int32_t B,
+                     int32_t c_in, int32_t c_out, int32_t l_in, float* dw, mms_stream_t stream);
+
+/* models.py:47-49 / :51-53  BatchNorm1d + ReLU + MaxPool1d(3,2,1) fused.
+ * training: batch statistics from `stats` (as produced by mms_conv1d_fwd), running buffers
+ * updated (momentum 0.1, unbiased variance), nbt incremented; eval: running buffers.
+ * time_major = 1 writes out[b, l, c] (models.py:77 permute(0,2,1) for free). */
+int mms_bn_relu_pool_fwd(const float* y, const double* stats, const float* gamma, const float* beta,
+                         float* running_mean, float* running_var, int64_t* nbt, int32_t B, int32_t C,
+                         int32_t l_in, int32_t training, int32_t time_major, float* out, mms_stream_t stream);
+/* Backward: dout (layout per time_major) -> dy [B,C,L_in] (in-place capable scratch), dgamma/dbeta (+=).
+ * red: float64 [2][C] zero-initialised scratch. */
+int mms_bn_relu_pool_bwd(const float* y, const double* stats, const float* gamma, const float* beta,
+                         const float* running_mean, const float* running_var, const float* dout,
+                         int32_t B, int32_t C, int32_t l_in, int32_t training, int32_t time_major,
+                         float* dy, float* dgamma, float* dbeta, double* red, mms_stream_t stream);
+
+/* GEMMs used for the GRU input projections and their gradients (models.py:78, the
+ * x @ W_ih^T + b_ih part of nn.GRU):
+ *   nt : C[m,n]  = sum_k A[m*lda+k] * W[n*ldw+k] + bias[n]
+ *   nn : C[m,n] (+)= sum_k A[m*lda+k] * W[k*ldw+n]
+ *   tn : C[i,j] += sum_m A[m*lda+acol(i)] * Bm[row(m)*ldb+j], bias_grad[i] += sum_m A[m*lda+acol(i)]
+ *        acol(i) = i < a_split ? i : i + a_skip;  row(m) = m + shift within each block of
+ *        `seq` rows (rows shifted outside their block read as zero) -- this is h_{t-1}. */
+int mms_gemm_nt_bias(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
+                     float* C, int64_t ldc, int32_t M, int32_t N, int32_t K, mms_stream_t stream);
+int mms_gemm_nn(const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc,
+                int32_t M, int32_t N, int32_t K, int32_t accumulate, mms_stream_t stream);
+int mms_gemm_tn_acc(const float* A, int64_t lda, int32_t a_split, int32_t a_skip, const float* Bm, int64_t ldb,
+                    int32_t shift, int32_t seq, float* C, int64_t ldc, float* bias_grad,
+                    int32_t M, int32_t N1, int32_t N2, mms_stream_t stream);
+
+/* The GRU recurrence of one direction (models.py:56-63; gate order r,z,n; h0 = 0).
+ * gi[(b*gi_bs + t*gi_ts) + 0..3H) are the input projections (incl. b_ih).  Runs `nsteps` steps
+ * starting at t0 and moving by dt (+1 forward, -1 reverse).  Writes h to hs[b*hs_bs + t*hs_ts + j],
+ * optionally a dropped copy to hs_drop (same indexing; element id for the RNG is
+ * drop_base + b*hs_bs + t*hs_ts + j), and, if stash != NULL, (r,z,n,W_hn h + b_hn) to
+ * stash[(b*st_bs + t*st_ts) + 0..4H). */
+typedef struct {
+    const float* gi; int64_t gi_bs, gi_ts;
+    const float* w_hh; const float* b_hh;
+    float* hs; int64_t hs_bs, hs_ts;
+    float* hs_drop; int64_t drop_base;
+    float* stash; int64_t st_bs, st_ts;
+    int32_t t0, dt, nsteps;
+} mms_gru_dir_fwd;
+int mms_gru_recur_fwd(const mms_gru_dir_fwd* dirs_host, int32_t ndirs, int32_t B, int32_t H,
+                      float dropout_p, uint64_t rng_seed, uint64_t rng_offset, const int64_t* rng_offset_dev,
+                      mms_stream_t stream);
+
+/* Reverse-time pass of one direction.  dout (optional) is the gradient w.r.t. the emitted h,
+ * indexed like hs; dout_last [B, dl_ld] (optional) is added at the forward-order LAST step
+ * only; dh_head/W0 (optional): initial dh[b,k] += sum_i dh_head[b*64+i] * w0[i*w0_ld + w0_col + k].
+ * If drop_mask != 0 the incoming dout is multiplied by the same dropout multiplier the forward
+ * applied to hs_drop.  Writes D[(b*d_bs + t*d_ts) + 0..4H) = (d r_pre, d z_pre, d n_pre, d q). */
+typedef struct {
+    const float* w_hh;
+    const float* stash; int64_t st_bs, st_ts;
+    const float* hs; int64_t hs_bs, hs_ts;
+    const float* dout; int64_t do_bs, do_ts; int64_t drop_base; int32_t drop_mask;
+    const float* dout_last; int64_t dl_ld;
+    const float* dh_head; const float* w0; int64_t w0_ld; int32_t w0_col;
+    float* D; int64_t d_bs, d_ts;
+    int32_t t0, dt, nsteps;
+} mms_gru_dir_bwd;
+int mms_gru_recur_bwd(const mms_gru_dir_bwd* dirs_host, int32_t ndirs, int32_t B, int32_t H,
+                      float dropout_p, uint64_t rng_seed, uint64_t rng_offset, const int64_t* rng_offset_dev,
+                      mms_stream_t stream);
+
+/* models.py:79-80 classifier head on last [B,2H]: Linear(2H,64)+ReLU+Dropout+Linear(64,nc).
+ * hid_out [B,64] keeps the post-ReLU activations for the backward. */
+int mms_head_fwd(const float* last, const float* w0, const float* b0, const float* w3, const float* b3,
+                 int32_t B, int32_t H2, int32_t nc, float dropout_p, uint64_t rng_seed, uint64_t rng_offset,
+                 const int64_t* rng_offset_dev, float* hid_out, float* logits, mms_stream_t stream);
+int mms_head_bwd(const float* last, const float* hid, const float* dlogits, const float* w3,
+                 int32_t B, int32_t H2, int32_t nc, float dropout_p, uint64_t rng_seed, uint64_t rng_offset,
+                 const int64_t* rng_offset_dev, float* dhid, float* dw0, float* db0, float* dw3, float* db3,
+                 mms_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Preprocess path (reference preprocess.py:70-75 resample_signal -> scipy.signal.resample,
+ * preprocess.py:189-200 window stacking, dataset.py:37-48 normalisation).
+ * ---------------------------------------------------------------------------------------- */
+
+/* FFT resampling of `n_sig` real float64 signals of length n_in to length n_out
+ * (scipy.signal.resample semantics, Fourier method, no window).  x [n_sig][n_in] ->
+ * y [n_sig][n_out], both float64, rows contiguous. */
+int64_t mms_resample_workspace_bytes(int64_t n_in, int64_t n_out, int32_t n_sig);
+int mms_resample_f64(const double* x, int64_t n_in, int64_t n_out, int32_t n_sig, double* y,
+                     void* workspace, int64_t workspace_bytes, mms_stream_t stream);
+
+/* preprocess.py:189-200: out[w, i, c] = streams[c][starts[w] + i] for w < n_win, i < win, c < n_ch.
+ * streams: HOST array of n_ch device pointers (float64 rows of length stream_len); out float64 [n_win, win, n_ch]
+ * (out_f32 = 0) or float32 [n_win, n_ch, win] already permuted as dataset.py:63 does (out_f32 = 1,
+ * in which case (x - shift[c]) * scale[c] is applied, log1p first where log_flag[c] != 0). */
+int mms_window_gather(const double* const* streams, int32_t n_ch, int64_t stream_len,
+                      const int64_t* starts, int32_t n_win, int32_t win, int32_t out_f32,
+                      const double* shift, const double* scale, const int32_t* log_flag,
+                      void* out, mms_stream_t stream);
+
+/* dataset.py:37-48 statistics over the WINDOWED array without materialising it: for each
+ * channel, sum and sum of squares (of log1p(x) where log_flag) over all (window, sample)
+ * pairs, i.e. each stream sample weighted by the number of windows covering it.
+ * sums float64 [n_ch][2], zero-initialised by the caller. */
+int mms_window_stats(const double* const* streams, int32_t n_ch, int64_t stream_len,
+                     const int64_t* starts, int32_t n_win, int32_t win, const int32_t* log_flag,
+                     double* sums, mms_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMS_B200_H */

@@ -1,0 +1,531 @@
+// CNN encoder of the reference (models.py:45-54): Conv1d(bias=False) -> BatchNorm1d -> ReLU ->
+// MaxPool1d(3,2,1), twice.  fp32 SIMT kernels staged through shared memory:
+//   conv1d_fwd    : x tile + (gate-scaled) weights in smem, one output position per thread, all
+//                   C_out accumulators in registers, BN batch statistics reduced in the epilogue
+//                   (float64 atomics -> order-independent to ~1e-16);
+//   bn_relu_pool  : one streaming pass, optional time-major store so the permute(0,2,1) of
+//                   models.py:77 costs nothing;
+//   backward      : pool/ReLU/BN-reduction pass, BN apply pass, dgrad (optionally reduced against x
+//                   for the attention gate) and wgrad.
+#include "mms_common.cuh"
+
+namespace mms {
+
+constexpr int CONV_CI_PAD = 16;
+
+// ------------------------------------------------------------------------------------------
+template <int CO, int KW, int S, int P, int TL>
+__global__ void __launch_bounds__(TL) conv1d_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ gate, float* __restrict__ y,
+                                                        double* __restrict__ stats, int CI, int Lin, int Lout) {
+    constexpr int SPAN = (TL - 1) * S + KW;
+    extern __shared__ __align__(16) float smem[];
+    float* ws = smem;                       // [CI*KW][CO]
+    float* xs = smem + CI * KW * CO;        // [CI][SPAN]
+    __shared__ double red[TL / 32][2 * CO];
+
+    const int b = blockIdx.y, l0 = blockIdx.x * TL, tid = threadIdx.x;
+    const int in0 = l0 * S - P;
+    const float* xb = x + (size_t)b * CI * Lin;
+    for (int idx = tid; idx < CI * SPAN; idx += TL) {
+        const int c = idx / SPAN, i = idx - c * SPAN, gi = in0 + i;
+        xs[idx] = (gi >= 0 && gi < Lin) ? __ldg(xb + (size_t)c * Lin + gi) : 0.f;
+    }
+    for (int idx = tid; idx < CO * CI * KW; idx += TL) {
+        const int o = idx / (CI * KW), ck = idx - o * (CI * KW), c = ck / KW;
+        const float g = gate ? gate[b * CI + c] : 1.f;
+        ws[ck * CO + o] = w[idx] * g;
+    }
+    __syncthreads();
+
+    float acc[CO];
+#pragma unroll
+    for (int o = 0; o < CO; ++o) acc[o] = 0.f;
+    const float* xr = xs + tid * S;
+    for (int c = 0; c < CI; ++c) {
+#pragma unroll
+        for (int k = 0; k < KW; ++k) {
+            const float xv = xr[c * SPAN + k];
+            const float4* wv = reinterpret_cast<const float4*>(ws + (c * KW + k) * CO);
+#pragma unroll
+            for (int o4 = 0; o4 < CO / 4; ++o4) {
+                const float4 wq = wv[o4];
+                acc[4 * o4 + 0] += wq.x * xv;
+                acc[4 * o4 + 1] += wq.y * xv;
+                acc[4 * o4 + 2] += wq.z * xv;
+                acc[4 * o4 + 3] += wq.w * xv;
+            }
+        }
+    }
+    const int l = l0 + tid;
+    const bool valid = l < Lout;
+    if (valid) {
+        float* yb = y + (size_t)b * CO * Lout + l;
+#pragma unroll
+        for (int o = 0; o < CO; ++o) yb[(size_t)o * Lout] = acc[o];
+    }
+    if (stats) {
+        const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+        for (int o = 0; o < CO; ++o) {
+            const float v = valid ? acc[o] : 0.f;
+            const float s = warp_sum(v), q = warp_sum(v * v);
+            if (lane == 0) { red[warp][o] = (double)s; red[warp][CO + o] = (double)q; }
+        }
+        __syncthreads();
+        if (tid < 2 * CO) {
+            double t = 0.0;
+#pragma unroll
+            for (int wq = 0; wq < TL / 32; ++wq) t += red[wq][tid];
+            atomicAdd(stats + tid, t);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+struct BnAffine { float a, b, mean, inv; };
+
+__device__ __forceinline__ BnAffine bn_affine(int training, const double* stats, const float* gamma, const float* beta,
+                                              const float* rm, const float* rv, int c, int C, double n) {
+    double mean, var;
+    if (training) {
+        mean = stats[c] / n;
+        var = stats[C + c] / n - mean * mean;
+        if (var < 0.0) var = 0.0;
+    } else {
+        mean = (double)rm[c];
+        var = (double)rv[c];
+    }
+    const double inv = 1.0 / sqrt(var + (double)BN_EPS);
+    BnAffine r;
+    r.inv = (float)inv;
+    r.mean = (float)mean;
+    r.a = gamma[c] * r.inv;
+    r.b = beta[c] - r.mean * r.a;
+    return r;
+}
+
+__device__ __forceinline__ void bn_running_update(const double* stats, float* rm, float* rv, int64_t* nbt, int C,
+                                                  double n, int tid) {
+    if (tid < C) {
+        const double mean = stats[tid] / n;
+        double var = stats[C + tid] / n - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const double unbiased = n > 1.0 ? var * (n / (n - 1.0)) : var;
+        rm[tid] = (1.f - BN_MOMENTUM) * rm[tid] + BN_MOMENTUM * (float)mean;
+        rv[tid] = (1.f - BN_MOMENTUM) * rv[tid] + BN_MOMENTUM * (float)unbiased;
+    }
+    if (tid == 0 && nbt) *nbt += 1;
+}
+
+__device__ __forceinline__ float pooled_value(const float* __restrict__ row, int j, int Lin, float a, float bsh) {
+    float m = -INFINITY;
+#pragma unroll
+    for (int e = 0; e < 3; ++e) {
+        const int i = 2 * j - 1 + e;
+        if (i >= 0 && i < Lin) m = fmaxf(m, fmaxf(fmaf(a, __ldg(row + i), bsh), 0.f));
+    }
+    return m;
+}
+
+// out[b,c,j] (channel-major)       grid = (ceil(Lout/256), C, B), block = 256
+__global__ void __launch_bounds__(256) bn_relu_pool_fwd_ncl_kernel(const float* __restrict__ y, const double* __restrict__ stats,
+                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                   float* rm, float* rv, int64_t* nbt, int B, int C, int Lin,
+                                                                   int Lout, int training, float* __restrict__ out) {
+    const int c = blockIdx.y, b = blockIdx.z;
+    const double n = (double)B * (double)Lin;
+    const BnAffine af = bn_affine(training, stats, gamma, beta, rm, rv, c, C, n);
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < Lout) {
+        const float* row = y + ((size_t)b * C + c) * Lin;
+        out[((size_t)b * C + c) * Lout + j] = pooled_value(row, j, Lin, af.a, af.b);
+    }
+    if (training && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+        __syncthreads();
+        bn_running_update(stats, rm, rv, nbt, C, n, threadIdx.x);
+    }
+}
+
+// out[b,j,c] (time-major)          grid = (ceil(Lout/32), B), block = 256, C <= 64
+__global__ void __launch_bounds__(256) bn_relu_pool_fwd_tm_kernel(const float* __restrict__ y, const double* __restrict__ stats,
+                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                  float* rm, float* rv, int64_t* nbt, int B, int C, int Lin,
+                                                                  int Lout, int training, float* __restrict__ out) {
+    __shared__ float tile[32][65];
+    __shared__ float sa[64], sb[64];
+    const int b = blockIdx.y, j0 = blockIdx.x * 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const double n = (double)B * (double)Lin;
+    if (threadIdx.x < C) {
+        const BnAffine af = bn_affine(training, stats, gamma, beta, rm, rv, threadIdx.x, C, n);
+        sa[threadIdx.x] = af.a;
+        sb[threadIdx.x] = af.b;
+    }
+    __syncthreads();
+    for (int c = warp; c < C; c += 8) {
+        const int j = j0 + lane;
+        if (j < Lout) tile[lane][c] = pooled_value(y + ((size_t)b * C + c) * Lin, j, Lin, sa[c], sb[c]);
+    }
+    __syncthreads();
+    for (int jj = warp; jj < 32; jj += 8) {
+        const int j = j0 + jj;
+        if (j < Lout)
+            for (int c = lane; c < C; c += 32) out[((size_t)b * Lout + j) * C + c] = tile[jj][c];
+    }
+    if (training && blockIdx.x == 0 && blockIdx.y == 0) {
+        __syncthreads();
+        bn_running_update(stats, rm, rv, nbt, C, n, threadIdx.x);
+    }
+}
+
+// ---- backward pass A: d(pool) -> d(relu) -> dyn, plus the two BN reductions --------------------
+// grid = (ceil(Lin/256), C, B), block = 256.  dyn is written to dy.
+__global__ void __launch_bounds__(256) pool_relu_bwd_kernel(const float* __restrict__ y, const double* __restrict__ stats,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            const float* __restrict__ rm, const float* __restrict__ rv,
+                                                            const float* __restrict__ dout, int B, int C, int Lin, int Lout,
+                                                            int training, int time_major, float* __restrict__ dy,
+                                                            double* __restrict__ red) {
+    __shared__ double part[8][2];
+    const int c = blockIdx.y, b = blockIdx.z;
+    const double n = (double)B * (double)Lin;
+    const BnAffine af = bn_affine(training, stats, gamma, beta, rm, rv, c, C, n);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float dyn = 0.f, xhat = 0.f;
+    if (i < Lin) {
+        const float* row = y + ((size_t)b * C + c) * Lin;
+        float z[5];
+#pragma unroll
+        for (int e = 0; e < 5; ++e) {
+            const int ii = i - 2 + e;
+            z[e] = (ii >= 0 && ii < Lin) ? fmaxf(fmaf(af.a, __ldg(row + ii), af.b), 0.f) : -INFINITY;
+        }
+        // windows that contain i: centre j=i/2 for even i; j=(i+1)/2 (i is element 0) and
+        // j=(i-1)/2 (i is element 2) for odd i.  First maximal element wins (ATen: val > maxval).
+        float dsum = 0.f;
+        int js[2], nj = 0;
+        if ((i & 1) == 0) { js[nj++] = i >> 1; }
+        else { js[nj++] = (i + 1) >> 1; js[nj++] = (i - 1) >> 1; }
+        for (int q = 0; q < nj; ++q) {
+            const int j = js[q];
+            if (j < 0 || j >= Lout) continue;
+            float best = -INFINITY;
+            int arg = -1;
+#pragma unroll
+            for (int e = 0; e < 3; ++e) {
+                const int ii = 2 * j - 1 + e;
+                if (ii < 0 || ii >= Lin) continue;
+                const float v = z[ii - i + 2];
+                if (v > best || arg < 0) { if (v > best || arg < 0) { best = v; arg = ii; } }
+            }
+            if (arg == i) {
+                const size_t di = time_major ? ((size_t)b * Lout + j) * C + c : ((size_t)b * C + c) * Lout + j;
+                dsum += __ldg(dout + di);
+            }
+        }
+        dyn = z[2] > 0.f ? dsum : 0.f;
+        xhat = (__ldg(row + i) - af.mean) * af.inv;
+        dy[((size_t)b * C + c) * Lin + i] = dyn;
+    }
+    const float s1 = warp_sum(dyn), s2 = warp_sum(dyn * xhat);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { part[warp][0] = (double)s1; part[warp][1] = (double)s2; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        double t = 0.0;
+        for (int wq = 0; wq < 8; ++wq) t += part[wq][threadIdx.x];
+        atomicAdd(red + threadIdx.x * C + c, t);      // red[0][c] = sum dyn, red[1][c] = sum dyn*xhat
+    }
+}
+
+// ---- backward pass B: BN input gradient in place, dgamma / dbeta ---------------------------
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restrict__ y, const double* __restrict__ stats,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           const float* __restrict__ rm, const float* __restrict__ rv,
+                                                           const double* __restrict__ red, int B, int C, int Lin, int training,
+                                                           float* __restrict__ dy, float* __restrict__ dgamma,
+                                                           float* __restrict__ dbeta) {
+    const int c = blockIdx.y, b = blockIdx.z;
+    const double n = (double)B * (double)Lin;
+    const BnAffine af = bn_affine(training, stats, gamma, beta, rm, rv, c, C, n);
+    const float m1 = training ? (float)(red[c] / n) : 0.f;
+    const float m2 = training ? (float)(red[C + c] / n) : 0.f;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < Lin) {
+        const size_t idx = ((size_t)b * C + c) * Lin + i;
+        const float xhat = (__ldg(y + idx) - af.mean) * af.inv;
+        dy[idx] = af.a * (dy[idx] - m1 - xhat * m2);
+    }
+    if (blockIdx.x == 0 && b == 0 && threadIdx.x == 0) {
+        dgamma[c] += (float)red[C + c];
+        dbeta[c] += (float)red[c];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int floor_div2(int a) { return a >= 0 ? a / 2 : -((-a + 1) / 2); }
+
+// dx[b,c,i] = sum_{o,k : S*l + k - P == i} w[o,c,k] * dy[b,o,l];   optional dot with xdot -> dgate
+template <int CO, int KW, int S, int P, int TI>
+__global__ void __launch_bounds__(TI) conv1d_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+                                                          float* __restrict__ dx, const float* __restrict__ xdot,
+                                                          float* __restrict__ dgate, int CI, int Lin, int Lout) {
+    static_assert(S == 2, "stride-2 convolutions only");
+    constexpr int NL = (TI - 1 + KW - 1) / S + 2;
+    extern __shared__ __align__(16) float smem[];
+    float* ws = smem;                           // [KW][CO][16]
+    float* dys = smem + KW * CO * CONV_CI_PAD;  // [CO][NL]
+    __shared__ float red[TI / 32][CONV_CI_PAD];
+
+    const int b = blockIdx.y, i0 = blockIdx.x * TI, tid = threadIdx.x;
+    const int lbase = floor_div2(i0 + P - (KW - 1));
+    const float* dyb = dy + (size_t)b * CO * Lout;
+    for (int idx = tid; idx < CO * NL; idx += TI) {
+        const int o = idx / NL, ll = idx - o * NL, l = lbase + ll;
+        dys[idx] = (l >= 0 && l < Lout) ? __ldg(dyb + (size_t)o * Lout + l) : 0.f;
+    }
+    for (int idx = tid; idx < KW * CO * CONV_CI_PAD; idx += TI) {
+        const int c = idx % CONV_CI_PAD, ko = idx / CONV_CI_PAD, o = ko % CO, k = ko / CO;
+        ws[idx] = c < CI ? w[((size_t)o * CI + c) * KW + k] : 0.f;
+    }
+    __syncthreads();
+
+    const int i = i0 + tid;
+    float acc[CONV_CI_PAD];
+#pragma unroll
+    for (int c = 0; c < CONV_CI_PAD; ++c) acc[c] = 0.f;
+    for (int k = (i + P) & 1; k < KW; k += S) {
+        const int ll = (i + P - k) / S - lbase;     // i + P - k is even; may be negative -> staged as zero
+        if (ll < 0 || ll >= NL) continue;
+        for (int o = 0; o < CO; ++o) {
+            const float d = dys[o * NL + ll];
+            const float4* wv = reinterpret_cast<const float4*>(ws + (k * CO + o) * CONV_CI_PAD);
+#pragma unroll
+            for (int c4 = 0; c4 < CONV_CI_PAD / 4; ++c4) {
+                const float4 wq = wv[c4];
+                acc[4 * c4 + 0] += wq.x * d;
+                acc[4 * c4 + 1] += wq.y * d;
+                acc[4 * c4 + 2] += wq.z * d;
+                acc[4 * c4 + 3] += wq.w * d;
+            }
+        }
+    }
+    const bool valid = i < Lin;
+    if (dx && valid) {
+#pragma unroll
+        for (int c = 0; c < CONV_CI_PAD; ++c)
+            if (c < CI) dx[((size_t)b * CI + c) * Lin + i] = acc[c];
+    }
+    if (xdot) {
+        const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+        for (int c = 0; c < CONV_CI_PAD; ++c) {
+            float v = 0.f;
+            if (valid && c < CI) v = acc[c] * __ldg(xdot + ((size_t)b * CI + c) * Lin + i);
+            v = warp_sum(v);
+            if (lane == 0) red[warp][c] = v;
+        }
+        __syncthreads();
+        if (tid < CI) {
+            float t = 0.f;
+#pragma unroll
+            for (int wq = 0; wq < TI / 32; ++wq) t += red[wq][tid];
+            atomicAdd(dgate + b * CI + tid, t);
+        }
+    }
+}
+
+// dw[o,c,k] += gate[b,c] * sum_l dy[b,o,l] * x[b,c,S*l+k-P]     grid = (ceil(Lout/TL), B), block 256
+template <int CO, int KW, int S, int P, int TL>
+__global__ void __launch_bounds__(256) conv1d_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                           const float* __restrict__ gate, float* __restrict__ dw, int CI,
+                                                           int Lin, int Lout) {
+    constexpr int SPAN = (TL - 1) * S + KW;
+    constexpr int TLP = TL + 1;
+    extern __shared__ __align__(16) float smem[];
+    float* dys = smem;                 // [CO][TLP]
+    float* xs = smem + CO * TLP;       // [CI][SPAN]
+    const int b = blockIdx.y, l0 = blockIdx.x * TL, tid = threadIdx.x;
+    const int in0 = l0 * S - P;
+    const float* xb = x + (size_t)b * CI * Lin;
+    const float* dyb = dy + (size_t)b * CO * Lout;
+    for (int idx = tid; idx < CI * SPAN; idx += 256) {
+        const int c = idx / SPAN, i = idx - c * SPAN, gi = in0 + i;
+        xs[idx] = (gi >= 0 && gi < Lin) ? __ldg(xb + (size_t)c * Lin + gi) : 0.f;
+    }
+    for (int idx = tid; idx < CO * TL; idx += 256) {
+        const int o = idx / TL, ll = idx - o * TL, l = l0 + ll;
+        dys[o * TLP + ll] = l < Lout ? __ldg(dyb + (size_t)o * Lout + l) : 0.f;
+    }
+    __syncthreads();
+    for (int p = tid; p < CO * CI; p += 256) {
+        const int o = p / CI, c = p - o * CI;
+        float acc[KW];
+#pragma unroll
+        for (int k = 0; k < KW; ++k) acc[k] = 0.f;
+        const float* dr = dys + o * TLP;
+        const float* xr = xs + c * SPAN;
+        for (int l = 0; l < TL; ++l) {
+            const float d = dr[l];
+#pragma unroll
+            for (int k = 0; k < KW; ++k) acc[k] += d * xr[l * S + k];
+        }
+        const float g = gate ? gate[b * CI + c] : 1.f;
+#pragma unroll
+        for (int k = 0; k < KW; ++k) atomicAdd(dw + ((size_t)o * CI + c) * KW + k, acc[k] * g);
+    }
+}
+
+// ---- launchers -------------------------------------------------------------------------------
+template <int CO, int KW, int S, int P, int TL>
+static int conv_fwd_launch(const float* x, const float* w, const float* gate, int B, int CI, int Lin, float* y,
+                           double* stats, cudaStream_t st) {
+    const int Lout = conv_out_len(Lin, KW, S, P);
+    constexpr int SPAN = (TL - 1) * S + KW;
+    const size_t smem = (size_t)(CI * KW * CO + CI * SPAN) * sizeof(float);
+    auto kern = conv1d_fwd_kernel<CO, KW, S, P, TL>;
+    static bool attr_done = false;
+    if (!attr_done) { MMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr_done = true; }
+    MMS_REQUIRE(smem <= 96 * 1024, "conv1d_fwd: shared memory %zu too large", smem);
+    dim3 grid(cdiv(Lout, TL), B);
+    kern<<<grid, TL, smem, st>>>(x, w, gate, y, stats, CI, Lin, Lout);
+    MMS_LAUNCH_CHECK("conv1d_fwd_kernel");
+    return MMS_OK;
+}
+
+template <int CO, int KW, int S, int P, int TI>
+static int conv_dgrad_launch(const float* dy, const float* w, int B, int CI, int Lin, float* dx, const float* xdot,
+                             float* dgate, cudaStream_t st) {
+    const int Lout = conv_out_len(Lin, KW, S, P);
+    constexpr int NL = (TI - 1 + KW - 1) / S + 2;
+    const size_t smem = (size_t)(KW * CO * CONV_CI_PAD + CO * NL) * sizeof(float);
+    auto kern = conv1d_dgrad_kernel<CO, KW, S, P, TI>;
+    static bool attr_done = false;
+    if (!attr_done) { MMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr_done = true; }
+    dim3 grid(cdiv(Lin, TI), B);
+    kern<<<grid, TI, smem, st>>>(dy, w, dx, xdot, dgate, CI, Lin, Lout);
+    MMS_LAUNCH_CHECK("conv1d_dgrad_kernel");
+    return MMS_OK;
+}
+
+template <int CO, int KW, int S, int P, int TL>
+static int conv_wgrad_launch(const float* x, const float* dy, const float* gate, int B, int CI, int Lin, float* dw,
+                             cudaStream_t st) {
+    const int Lout = conv_out_len(Lin, KW, S, P);
+    constexpr int SPAN = (TL - 1) * S + KW;
+    const size_t smem = (size_t)(CO * (TL + 1) + CI * SPAN) * sizeof(float);
+    auto kern = conv1d_wgrad_kernel<CO, KW, S, P, TL>;
+    static bool attr_done = false;
+    if (!attr_done) { MMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr_done = true; }
+    dim3 grid(cdiv(Lout, TL), B);
+    kern<<<grid, 256, smem, st>>>(x, dy, gate, dw, CI, Lin, Lout);
+    MMS_LAUNCH_CHECK("conv1d_wgrad_kernel");
+    return MMS_OK;
+}
+
+static int check_conv(int which, int c_in, int c_out) {
+    if (which == 1) {
+        MMS_REQUIRE(c_out == CONV1_CO && c_in >= 1 && c_in <= CONV_CI_PAD, "conv1: need C_out=16 and 1<=C_in<=16 (got %d,%d)", c_out, c_in);
+    } else if (which == 2) {
+        MMS_REQUIRE(c_in == CONV2_CI && (c_out == 16 || c_out == 32 || c_out == 64), "conv2: need C_in=16 and C_out in {16,32,64} (got %d,%d)", c_in, c_out);
+    } else {
+        MMS_REQUIRE(false, "conv: which must be 1 or 2");
+    }
+    return MMS_OK;
+}
+
+int launch_conv_fwd(int which, const float* x, const float* w, const float* gate, int B, int c_in, int c_out, int l_in,
+                    float* y, double* stats, cudaStream_t st) {
+    int rc = check_conv(which, c_in, c_out);
+    if (rc) return rc;
+    if (which == 1) return conv_fwd_launch<16, CONV1_K, CONV1_S, CONV1_P, 256>(x, w, gate, B, c_in, l_in, y, stats, st);
+    if (c_out == 16) return conv_fwd_launch<16, CONV2_K, CONV2_S, CONV2_P, 128>(x, w, gate, B, c_in, l_in, y, stats, st);
+    if (c_out == 32) return conv_fwd_launch<32, CONV2_K, CONV2_S, CONV2_P, 128>(x, w, gate, B, c_in, l_in, y, stats, st);
+    return conv_fwd_launch<64, CONV2_K, CONV2_S, CONV2_P, 128>(x, w, gate, B, c_in, l_in, y, stats, st);
+}
+
+int launch_conv_dgrad(int which, const float* dy, const float* w, int B, int c_in, int c_out, int l_in, float* dx,
+                      const float* xdot, float* dgate, cudaStream_t st) {
+    int rc = check_conv(which, c_in, c_out);
+    if (rc) return rc;
+    if (which == 1) return conv_dgrad_launch<16, CONV1_K, CONV1_S, CONV1_P, 256>(dy, w, B, c_in, l_in, dx, xdot, dgate, st);
+    if (c_out == 16) return conv_dgrad_launch<16, CONV2_K, CONV2_S, CONV2_P, 128>(dy, w, B, c_in, l_in, dx, xdot, dgate, st);
+    if (c_out == 32) return conv_dgrad_launch<32, CONV2_K, CONV2_S, CONV2_P, 128>(dy, w, B, c_in, l_in, dx, xdot, dgate, st);
+    return conv_dgrad_launch<64, CONV2_K, CONV2_S, CONV2_P, 128>(dy, w, B, c_in, l_in, dx, xdot, dgate, st);
+}
+
+int launch_conv_wgrad(int which, const float* x, const float* dy, const float* gate, int B, int c_in, int c_out,
+                      int l_in, float* dw, cudaStream_t st) {
+    int rc = check_conv(which, c_in, c_out);
+    if (rc) return rc;
+    if (which == 1) return conv_wgrad_launch<16, CONV1_K, CONV1_S, CONV1_P, 128>(x, dy, gate, B, c_in, l_in, dw, st);
+    if (c_out == 16) return conv_wgrad_launch<16, CONV2_K, CONV2_S, CONV2_P, 128>(x, dy, gate, B, c_in, l_in, dw, st);
+    if (c_out == 32) return conv_wgrad_launch<32, CONV2_K, CONV2_S, CONV2_P, 128>(x, dy, gate, B, c_in, l_in, dw, st);
+    return conv_wgrad_launch<64, CONV2_K, CONV2_S, CONV2_P, 128>(x, dy, gate, B, c_in, l_in, dw, st);
+}
+
+int launch_bn_relu_pool_fwd(const float* y, const double* stats, const float* gamma, const float* beta, float* rm,
+                            float* rv, int64_t* nbt, int B, int C, int l_in, int training, int time_major, float* out,
+                            cudaStream_t st) {
+    const int Lout = pool_out_len(l_in);
+    MMS_REQUIRE(C >= 1 && C <= 64, "bn_relu_pool: channels %d outside [1,64]", C);
+    MMS_REQUIRE(!training || stats, "bn_relu_pool: training mode needs batch statistics");
+    if (time_major) {
+        dim3 grid(cdiv(Lout, 32), B);
+        bn_relu_pool_fwd_tm_kernel<<<grid, 256, 0, st>>>(y, stats, gamma, beta, rm, rv, nbt, B, C, l_in, Lout, training, out);
+    } else {
+        dim3 grid(cdiv(Lout, 256), C, B);
+        bn_relu_pool_fwd_ncl_kernel<<<grid, 256, 0, st>>>(y, stats, gamma, beta, rm, rv, nbt, B, C, l_in, Lout, training, out);
+    }
+    MMS_LAUNCH_CHECK("bn_relu_pool_fwd");
+    return MMS_OK;
+}
+
+int launch_bn_relu_pool_bwd(const float* y, const double* stats, const float* gamma, const float* beta, const float* rm,
+                            const float* rv, const float* dout, int B, int C, int l_in, int training, int time_major,
+                            float* dy, float* dgamma, float* dbeta, double* red, cudaStream_t st) {
+    const int Lout = pool_out_len(l_in);
+    MMS_REQUIRE(C >= 1 && C <= 64, "bn_relu_pool_bwd: channels %d outside [1,64]", C);
+    dim3 grid(cdiv(l_in, 256), C, B);
+    pool_relu_bwd_kernel<<<grid, 256, 0, st>>>(y, stats, gamma, beta, rm, rv, dout, B, C, l_in, Lout, training, time_major, dy, red);
+    MMS_LAUNCH_CHECK("pool_relu_bwd_kernel");
+    bn_bwd_apply_kernel<<<grid, 256, 0, st>>>(y, stats, gamma, beta, rm, rv, red, B, C, l_in, training, dy, dgamma, dbeta);
+    MMS_LAUNCH_CHECK("bn_bwd_apply_kernel");
+    return MMS_OK;
+}
+
+}  // namespace mms
+
+using namespace mms;
+
+extern "C" int mms_conv1d_fwd(int32_t which, const float* x, const float* w, const float* gate, int32_t B, int32_t c_in,
+                              int32_t c_out, int32_t l_in, float* y, double* stats, mms_stream_t stream) {
+    MMS_REQUIRE(x && w && y && B > 0 && l_in > 0, "conv1d_fwd: bad arguments");
+    return launch_conv_fwd(which, x, w, gate, B, c_in, c_out, l_in, y, stats, (cudaStream_t)stream);
+}
+extern "C" int mms_conv1d_dgrad(int32_t which, const float* dy, const float* w, int32_t B, int32_t c_in, int32_t c_out,
+                                int32_t l_in, float* dx, const float* xdot, float* dgate, mms_stream_t stream) {
+    MMS_REQUIRE(dy && w && B > 0 && l_in > 0 && (dx || (xdot && dgate)), "conv1d_dgrad: bad arguments");
+    return launch_conv_dgrad(which, dy, w, B, c_in, c_out, l_in, dx, xdot, dgate, (cudaStream_t)stream);
+}
+extern "C" int mms_conv1d_wgrad(int32_t which, const float* x, const float* dy, const float* gate, int32_t B, int32_t c_in,
+                                int32_t c_out, int32_t l_in, float* dw, mms_stream_t stream) {
+    MMS_REQUIRE(x && dy && dw && B > 0 && l_in > 0, "conv1d_wgrad: bad arguments");
+    return launch_conv_wgrad(which, x, dy, gate, B, c_in, c_out, l_in, dw, (cudaStream_t)stream);
+}
+extern "C" int mms_bn_relu_pool_fwd(const float* y, const double* stats, const float* gamma, const float* beta,
+                                    float* running_mean, float* running_var, int64_t* nbt, int32_t B, int32_t C, int32_t l_in,
+                                    int32_t training, int32_t time_major, float* out, mms_stream_t stream) {
+    MMS_REQUIRE(y && gamma && beta && running_mean && running_var && out, "bn_relu_pool_fwd: bad arguments");
+    return launch_bn_relu_pool_fwd(y, stats, gamma, beta, running_mean, running_var, nbt, B, C, l_in, training, time_major, out,
+                                   (cudaStream_t)stream);
+}
+extern "C" int mms_bn_relu_pool_bwd(const float* y, const double* stats, const float* gamma, const float* beta,
+                                    const float* running_mean, const float* running_var, const float* dout, int32_t B, int32_t C,
+                                    int32_t l_in, int32_t training, int32_t time_major, float* dy, float* dgamma, float* dbeta,
+                                    double* red, mms_stream_t stream) {
+    MMS_REQUIRE(y && gamma && beta && dout && dy && dgamma && dbeta && red, "bn_relu_pool_bwd: bad arguments");
+    return launch_bn_relu_pool_bwd(y, stats, gamma, beta, running_mean, running_var, dout, B, C, l_in, training, time_major, dy,
+                                   dgamma, dbeta, red, (cudaStream_t)stream);
+}

@@ -1,0 +1,92 @@
+// Shared device/host helpers for libmms_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/mms_b200.h"
+
+namespace mms {
+
+// ---- error plumbing ------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define MMS_CUDA(call)                                                              \
+    do {                                                                            \
+        cudaError_t _e = (call);                                                    \
+        if (_e != cudaSuccess) return ::mms::cuda_fail(_e, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define MMS_LAUNCH_CHECK(name)                                                      \
+    do {                                                                            \
+        cudaError_t _e = cudaPeekAtLastError();                                     \
+        if (_e != cudaSuccess) return ::mms::cuda_fail(_e, name, __FILE__, __LINE__);  \
+    } while (0)
+
+#define MMS_REQUIRE(cond, ...)                                                      \
+    do {                                                                            \
+        if (!(cond)) { ::mms::set_error(__VA_ARGS__); return MMS_E_INVALID; }       \
+    } while (0)
+
+static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- shapes of the reference CNN stack (models.py:46-53) ------------------------------
+static inline int conv_out_len(int l_in, int k, int s, int p) { return (l_in + 2 * p - k) / s + 1; }
+static inline int pool_out_len(int l_in) { return (l_in + 2 - 3) / 2 + 1; }
+
+constexpr int CONV1_CO = 16, CONV1_K = 7, CONV1_S = 2, CONV1_P = 3;
+constexpr int CONV2_CI = 16, CONV2_K = 5, CONV2_S = 2, CONV2_P = 2;
+constexpr int HEAD_HID = 64;
+constexpr float BN_EPS = 1e-5f;
+constexpr float BN_MOMENTUM = 0.1f;
+
+// ---- device helpers -----------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Counter-based dropout stream: murmur3 finaliser over (seed, offset, element index).
+// Not bit-compatible with torch's Philox stream (nothing outside torch can be); parity
+// tests run with p = 0 or in eval mode, exactly as SURVEY.md §7 hard part 4 prescribes.
+__device__ __forceinline__ uint32_t fmix32(uint32_t h) {
+    h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+    return h;
+}
+struct DropRng {
+    uint32_t k0, k1;
+    float p, scale;
+    __device__ __forceinline__ void init(uint64_t seed, uint64_t offset, float p_) {
+        k0 = fmix32((uint32_t)seed ^ 0x9e3779b9u) ^ fmix32((uint32_t)(offset) + 0x7f4a7c15u);
+        k1 = fmix32((uint32_t)(seed >> 32) ^ 0x85ebca6bu) + fmix32((uint32_t)(offset >> 32) ^ 0xc2b2ae35u);
+        p = p_;
+        scale = p_ < 1.f ? 1.f / (1.f - p_) : 0.f;
+    }
+    // multiplier applied to element `idx`: 0 (dropped) or 1/(1-p)
+    __device__ __forceinline__ float mult(uint64_t idx) const {
+        uint32_t h = fmix32((uint32_t)idx ^ k0);
+        h = fmix32(h + k1 + (uint32_t)(idx >> 32) * 0x27d4eb2fu);
+        float u = (float)(h >> 8) * (1.0f / 16777216.0f);
+        return u >= p ? scale : 0.f;
+    }
+};
+
+__device__ __forceinline__ uint64_t resolve_offset(uint64_t host_off, const int64_t* dev_off) {
+    return dev_off ? (uint64_t)(*dev_off) : host_off;
+}
+
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+
+#endif  // __CUDACC__
+
+}  // namespace mms

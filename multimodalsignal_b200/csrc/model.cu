@@ -1,0 +1,453 @@
+// CnnGruAttentionModel (reference models.py:34-81) as a chain of hand-written kernels:
+// parameter layout, workspace carving and the forward / backward / train-step launch sequences.
+// Nothing here allocates or synchronises; one call enqueues the whole chain on the caller's stream
+// (so a Python caller pays one ctypes call per pass and the chain can be captured in a CUDA graph).
+#include "mms_common.cuh"
+#include <string.h>
+
+namespace mms {
+
+// launchers defined in the other translation units
+int launch_chan_gate(const float*, const float*, const float*, int, int, int, float*, float*, cudaStream_t);
+int launch_chan_param_bwd(const float*, const float*, const float*, const float*, const float*, int, int, float*, float*, float*,
+                          float*, cudaStream_t);
+int launch_conv_fwd(int, const float*, const float*, const float*, int, int, int, int, float*, double*, cudaStream_t);
+int launch_conv_dgrad(int, const float*, const float*, int, int, int, int, float*, const float*, float*, cudaStream_t);
+int launch_conv_wgrad(int, const float*, const float*, const float*, int, int, int, int, float*, cudaStream_t);
+int launch_bn_relu_pool_fwd(const float*, const double*, const float*, const float*, float*, float*, int64_t*, int, int, int, int,
+                            int, float*, cudaStream_t);
+int launch_bn_relu_pool_bwd(const float*, const double*, const float*, const float*, const float*, const float*, const float*, int,
+                            int, int, int, int, float*, float*, float*, double*, cudaStream_t);
+int launch_gemm_nt_bias(const float*, int64_t, const float*, int64_t, const float*, float*, int64_t, int, int, int, cudaStream_t);
+int launch_gemm_nn(const float*, int64_t, const float*, int64_t, float*, int64_t, int, int, int, int, cudaStream_t);
+int launch_gemm_tn_acc(const float*, int64_t, int, int, const float*, int64_t, int, int, float*, int64_t, float*, int, int, int,
+                       cudaStream_t);
+int launch_gru_fwd(const mms_gru_dir_fwd*, int, int, int, float, uint64_t, uint64_t, const int64_t*, cudaStream_t);
+int launch_gru_bwd(const mms_gru_dir_bwd*, int, int, int, float, uint64_t, uint64_t, const int64_t*, cudaStream_t);
+int launch_head_fwd2(const float*, int64_t, const float*, int64_t, int, const float*, const float*, const float*, const float*, int,
+                     int, int, float, uint64_t, uint64_t, const int64_t*, float*, float*, float*, cudaStream_t);
+int launch_head_bwd(const float*, const float*, const float*, const float*, int, int, int, float, uint64_t, uint64_t,
+                    const int64_t*, float*, float*, float*, float*, float*, cudaStream_t);
+int launch_cross_entropy(const float*, const int64_t*, int, int, float*, float*, double*, cudaStream_t);
+int launch_adam(float*, const float*, float*, float*, int64_t, const float*, float, float, float, float, int64_t*, int32_t*,
+                cudaStream_t);
+int launch_chan_dx(const float*, const float*, const float*, int, int, int, float*, cudaStream_t);
+
+constexpr int MAX_LAYERS = 8;
+constexpr int64_t DROP_LAYER_STRIDE = 1ll << 40;
+
+struct Dims {
+    int B, C, T, nc, O, H, layers, A;
+    int L1c, P1, L2c, L;   // conv1 out, pool1 out, conv2 out, pool2 out (= GRU sequence length)
+    bool training, attention, need_grad, drop_gru, drop_head;
+    float p;
+};
+
+static int make_dims(const mms_cnngru_desc* d, Dims* o) {
+    MMS_REQUIRE(d, "null descriptor");
+    o->B = d->batch; o->C = d->in_channels; o->T = d->seq_len; o->nc = d->num_classes; o->O = d->cnn_out;
+    o->H = d->hidden; o->layers = d->layers; o->A = d->in_channels / 4;
+    MMS_REQUIRE(o->B >= 1, "batch must be >= 1 (got %d)", o->B);
+    MMS_REQUIRE(o->C >= 1 && o->C <= 16, "in_channels %d outside [1,16]", o->C);
+    MMS_REQUIRE(o->nc >= 1 && o->nc <= 8, "num_classes %d outside [1,8]", o->nc);
+    MMS_REQUIRE(o->O == 16 || o->O == 32 || o->O == 64, "cnn_out_channels %d not in {16,32,64}", o->O);
+    MMS_REQUIRE(o->H == 32 || o->H == 64, "gru_hidden_size %d not in {32,64}", o->H);
+    MMS_REQUIRE(o->layers >= 1 && o->layers <= MAX_LAYERS, "gru_num_layers %d outside [1,%d]", o->layers, MAX_LAYERS);
+    o->L1c = conv_out_len(o->T, CONV1_K, CONV1_S, CONV1_P);
+    MMS_REQUIRE(o->T >= 1 && o->L1c >= 1, "seq_len %d too short", o->T);
+    o->P1 = pool_out_len(o->L1c);
+    o->L2c = conv_out_len(o->P1, CONV2_K, CONV2_S, CONV2_P);
+    MMS_REQUIRE(o->L2c >= 1, "seq_len %d too short", o->T);
+    o->L = pool_out_len(o->L2c);
+    o->training = d->training != 0;
+    o->attention = d->attention != 0;
+    o->need_grad = d->need_grad != 0;
+    o->p = d->dropout_p;
+    MMS_REQUIRE(o->p >= 0.f && o->p < 1.f, "dropout %f outside [0,1)", (double)o->p);
+    o->drop_gru = o->training && o->p > 0.f && o->layers > 1;   // nn.GRU applies dropout only between layers
+    o->drop_head = o->training && o->p > 0.f;
+    return MMS_OK;
+}
+
+struct ParamOff {
+    int64_t ca_w1, ca_w2, conv1_w, bn1_g, bn1_b, conv2_w, bn2_g, bn2_b;
+    int64_t w_ih[MAX_LAYERS], w_hh[MAX_LAYERS], b_ih[MAX_LAYERS], b_hh[MAX_LAYERS];
+    int64_t fc0_w, fc0_b, fc3_w, fc3_b, total;
+    int nseg;
+    int64_t off[MMS_MAX_SEGMENTS], size[MMS_MAX_SEGMENTS];
+};
+
+static void make_params(const Dims& m, ParamOff* p) {
+    int64_t cur = 0;
+    int n = 0;
+    auto seg = [&](int64_t count) {
+        const int64_t o = cur;
+        p->off[n] = o; p->size[n] = count; ++n;
+        cur = align_up(cur + count, 4);
+        return o;
+    };
+    p->ca_w1 = seg((int64_t)m.A * m.C);
+    p->ca_w2 = seg((int64_t)m.C * m.A);
+    p->conv1_w = seg((int64_t)CONV1_CO * m.C * CONV1_K);
+    p->bn1_g = seg(CONV1_CO);
+    p->bn1_b = seg(CONV1_CO);
+    p->conv2_w = seg((int64_t)m.O * CONV2_CI * CONV2_K);
+    p->bn2_g = seg(m.O);
+    p->bn2_b = seg(m.O);
+    for (int l = 0; l < m.layers; ++l) {
+        const int I = l == 0 ? m.O : 2 * m.H;
+        p->w_ih[l] = seg((int64_t)2 * 3 * m.H * I);
+        p->w_hh[l] = seg((int64_t)2 * 3 * m.H * m.H);
+        p->b_ih[l] = seg((int64_t)2 * 3 * m.H);
+        p->b_hh[l] = seg((int64_t)2 * 3 * m.H);
+    }
+    p->fc0_w = seg((int64_t)HEAD_HID * 2 * m.H);
+    p->fc0_b = seg(HEAD_HID);
+    p->fc3_w = seg((int64_t)m.nc * HEAD_HID);
+    p->fc3_b = seg(m.nc);
+    p->total = cur;
+    p->nseg = n;
+}
+
+struct Workspace {
+    // zeroed at the start of every forward
+    double* stats1; double* stats2;
+    // zeroed at the start of every backward
+    double* red1; double* red2; float* dgate;
+    size_t fwd_zero_bytes, bwd_zero_bytes;
+    char* fwd_zero; char* bwd_zero;
+    float *mean, *gate, *y1, *p1, *y2, *seq;
+    float *gi[MAX_LAYERS], *hs[MAX_LAYERS], *outd[MAX_LAYERS], *stash[MAX_LAYERS];   // bottom layers
+    float *gi_tf, *gi_tr, *hs_tf, *h_tr, *stash_tf, *stash_tr, *last, *hid;
+    float *dhid, *dlogits, *D_tf, *D_tr, *D[MAX_LAYERS], *dxa, *dxb, *dy2, *dp1, *dy1, *ca_scratch;
+    int64_t total;
+};
+
+static void carve(const Dims& m, char* base, Workspace* w) {
+    int64_t cur = 0;
+    auto take = [&](int64_t bytes) {
+        char* p = base ? base + cur : nullptr;
+        cur = align_up(cur + bytes, 256);
+        return p;
+    };
+    const int64_t B = m.B, L = m.L, H = m.H, M = B * L;
+    const int64_t f = sizeof(float);
+    w->fwd_zero = take((int64_t)sizeof(double) * 2 * (CONV1_CO + m.O));
+    w->stats1 = (double*)w->fwd_zero;
+    w->stats2 = w->stats1 ? w->stats1 + 2 * CONV1_CO : nullptr;
+    w->fwd_zero_bytes = sizeof(double) * 2 * (CONV1_CO + m.O);
+    const int64_t bz = (int64_t)sizeof(double) * 2 * (CONV1_CO + m.O) + align_up(B * m.C, 4) * f;
+    w->bwd_zero = take(bz);
+    w->red1 = (double*)w->bwd_zero;
+    w->red2 = w->red1 ? w->red1 + 2 * CONV1_CO : nullptr;
+    w->dgate = w->red1 ? (float*)(w->red2 + 2 * m.O) : nullptr;
+    w->bwd_zero_bytes = bz;
+    w->mean = (float*)take(B * m.C * f);
+    w->gate = (float*)take(B * m.C * f);
+    w->y1 = (float*)take(B * CONV1_CO * m.L1c * f);
+    w->p1 = (float*)take(B * CONV1_CO * m.P1 * f);
+    w->y2 = (float*)take(B * m.O * m.L2c * f);
+    w->seq = (float*)take(M * m.O * f);
+    for (int l = 0; l < m.layers - 1; ++l) {
+        w->gi[l] = (float*)take(M * 6 * H * f);
+        w->hs[l] = (float*)take(M * 2 * H * f);
+        w->outd[l] = m.drop_gru ? (float*)take(M * 2 * H * f) : w->hs[l];
+        w->stash[l] = m.need_grad ? (float*)take(2 * M * 4 * H * f) : nullptr;
+    }
+    w->gi_tf = (float*)take(M * 3 * H * f);
+    w->gi_tr = (float*)take(B * 3 * H * f);
+    w->hs_tf = (float*)take(M * H * f);
+    w->h_tr = (float*)take(B * H * f);
+    w->stash_tf = m.need_grad ? (float*)take(M * 4 * H * f) : nullptr;
+    w->stash_tr = m.need_grad ? (float*)take(B * 4 * H * f) : nullptr;
+    w->last = (float*)take(B * 2 * H * f);
+    w->hid = (float*)take(B * HEAD_HID * f);
+    if (m.need_grad) {
+        w->dhid = (float*)take(B * HEAD_HID * f);
+        w->dlogits = (float*)take(B * 8 * f);
+        w->D_tf = (float*)take(M * 4 * H * f);
+        w->D_tr = (float*)take(B * 4 * H * f);
+        for (int l = 0; l < m.layers - 1; ++l) w->D[l] = (float*)take(M * 8 * H * f);
+        const int64_t widest = 2 * H > m.O ? 2 * H : m.O;
+        w->dxa = (float*)take(M * widest * f);
+        w->dxb = (float*)take(M * widest * f);
+        w->dy2 = (float*)take(B * m.O * m.L2c * f);
+        w->dp1 = (float*)take(B * CONV1_CO * m.P1 * f);
+        w->dy1 = (float*)take(B * CONV1_CO * m.L1c * f);
+        w->ca_scratch = (float*)take(4 * B * m.C * f);
+    }
+    w->total = cur;
+}
+
+static int model_forward(const mms_cnngru_desc* d, const float* x, const float* P, float* bn, int64_t* nbt, void* ws,
+                         float* logits, cudaStream_t st) {
+    Dims m;
+    int rc = make_dims(d, &m);
+    if (rc) return rc;
+    MMS_REQUIRE(x && P && bn && ws && logits, "cnngru_forward: null pointer");
+    MMS_REQUIRE(!m.training || nbt, "cnngru_forward: training mode needs num_batches_tracked");
+    ParamOff po;
+    make_params(m, &po);
+    Workspace w;
+    carve(m, (char*)ws, &w);
+    const int B = m.B, H = m.H, L = m.L;
+    const int64_t M = (int64_t)B * L;
+    float *rm1 = bn, *rv1 = bn + CONV1_CO, *rm2 = bn + 2 * CONV1_CO, *rv2 = bn + 2 * CONV1_CO + m.O;
+
+    MMS_CUDA(cudaMemsetAsync(w.fwd_zero, 0, w.fwd_zero_bytes, st));
+    const float* gate = nullptr;
+    if (m.attention) {
+        rc = launch_chan_gate(x, P + po.ca_w1, P + po.ca_w2, B, m.C, m.T, w.mean, w.gate, st);
+        if (rc) return rc;
+        gate = w.gate;
+    }
+    rc = launch_conv_fwd(1, x, P + po.conv1_w, gate, B, m.C, CONV1_CO, m.T, w.y1, m.training ? w.stats1 : nullptr, st);
+    if (rc) return rc;
+    rc = launch_bn_relu_pool_fwd(w.y1, w.stats1, P + po.bn1_g, P + po.bn1_b, rm1, rv1, nbt, B, CONV1_CO, m.L1c, m.training, 0, w.p1, st);
+    if (rc) return rc;
+    rc = launch_conv_fwd(2, w.p1, P + po.conv2_w, nullptr, B, CONV2_CI, m.O, m.P1, w.y2, m.training ? w.stats2 : nullptr, st);
+    if (rc) return rc;
+    rc = launch_bn_relu_pool_fwd(w.y2, w.stats2, P + po.bn2_g, P + po.bn2_b, rm2, rv2, nbt ? nbt + 1 : nullptr, B, m.O, m.L2c,
+                                 m.training, 1, w.seq, st);
+    if (rc) return rc;
+
+    const float* in = w.seq;
+    int I = m.O;
+    for (int l = 0; l < m.layers - 1; ++l) {
+        rc = launch_gemm_nt_bias(in, I, P + po.w_ih[l], I, P + po.b_ih[l], w.gi[l], 6 * H, (int)M, 6 * H, I, st);
+        if (rc) return rc;
+        mms_gru_dir_fwd dirs[2];
+        for (int dd = 0; dd < 2; ++dd) {
+            mms_gru_dir_fwd& g = dirs[dd];
+            memset(&g, 0, sizeof(g));
+            g.gi = w.gi[l] + dd * 3 * H; g.gi_bs = (int64_t)L * 6 * H; g.gi_ts = 6 * H;
+            g.w_hh = P + po.w_hh[l] + (int64_t)dd * 3 * H * H;
+            g.b_hh = P + po.b_hh[l] + dd * 3 * H;
+            g.hs = w.hs[l] + dd * H; g.hs_bs = (int64_t)L * 2 * H; g.hs_ts = 2 * H;
+            g.hs_drop = m.drop_gru ? w.outd[l] + dd * H : nullptr;
+            g.drop_base = (int64_t)l * DROP_LAYER_STRIDE + dd * H;
+            g.stash = m.need_grad ? w.stash[l] + (int64_t)dd * M * 4 * H : nullptr;
+            g.st_bs = (int64_t)L * 4 * H; g.st_ts = 4 * H;
+            g.t0 = dd ? L - 1 : 0; g.dt = dd ? -1 : 1; g.nsteps = L;
+        }
+        rc = launch_gru_fwd(dirs, 2, B, H, m.p, d->rng_seed, d->rng_offset, d->rng_offset_dev, st);
+        if (rc) return rc;
+        in = w.outd[l];
+        I = 2 * H;
+    }
+    {   // top layer: forward direction over the whole sequence, reverse direction for its first step only
+        const int l = m.layers - 1;
+        rc = launch_gemm_nt_bias(in, I, P + po.w_ih[l], I, P + po.b_ih[l], w.gi_tf, 3 * H, (int)M, 3 * H, I, st);
+        if (rc) return rc;
+        rc = launch_gemm_nt_bias(in + (int64_t)(L - 1) * I, (int64_t)L * I, P + po.w_ih[l] + (int64_t)3 * H * I, I,
+                                 P + po.b_ih[l] + 3 * H, w.gi_tr, 3 * H, B, 3 * H, I, st);
+        if (rc) return rc;
+        mms_gru_dir_fwd dirs[2];
+        memset(dirs, 0, sizeof(dirs));
+        dirs[0].gi = w.gi_tf; dirs[0].gi_bs = (int64_t)L * 3 * H; dirs[0].gi_ts = 3 * H;
+        dirs[0].w_hh = P + po.w_hh[l]; dirs[0].b_hh = P + po.b_hh[l];
+        dirs[0].hs = w.hs_tf; dirs[0].hs_bs = (int64_t)L * H; dirs[0].hs_ts = H;
+        dirs[0].stash = w.stash_tf; dirs[0].st_bs = (int64_t)L * 4 * H; dirs[0].st_ts = 4 * H;
+        dirs[0].t0 = 0; dirs[0].dt = 1; dirs[0].nsteps = L;
+        dirs[1].gi = w.gi_tr; dirs[1].gi_bs = 3 * H; dirs[1].gi_ts = 0;
+        dirs[1].w_hh = P + po.w_hh[l] + (int64_t)3 * H * H; dirs[1].b_hh = P + po.b_hh[l] + 3 * H;
+        dirs[1].hs = w.h_tr; dirs[1].hs_bs = H; dirs[1].hs_ts = 0;
+        dirs[1].stash = w.stash_tr; dirs[1].st_bs = 4 * H; dirs[1].st_ts = 0;
+        dirs[1].t0 = L - 1; dirs[1].dt = -1; dirs[1].nsteps = 1;
+        rc = launch_gru_fwd(dirs, 2, B, H, 0.f, d->rng_seed, d->rng_offset, d->rng_offset_dev, st);
+        if (rc) return rc;
+    }
+    return launch_head_fwd2(w.hs_tf + (int64_t)(L - 1) * H, (int64_t)L * H, w.h_tr, H, H, P + po.fc0_w, P + po.fc0_b, P + po.fc3_w,
+                            P + po.fc3_b, B, 2 * H, m.nc, m.drop_head ? m.p : 0.f, d->rng_seed, d->rng_offset, d->rng_offset_dev,
+                            w.last, w.hid, logits, st);
+}
+
+static int model_backward(const mms_cnngru_desc* d, const float* x, const float* P, const float* bn, void* ws,
+                          const float* dlogits, float* G, float* dx, cudaStream_t st) {
+    Dims m;
+    int rc = make_dims(d, &m);
+    if (rc) return rc;
+    MMS_REQUIRE(m.need_grad, "cnngru_backward: the forward pass was run with need_grad = 0");
+    MMS_REQUIRE(x && P && bn && ws && dlogits && G, "cnngru_backward: null pointer");
+    ParamOff po;
+    make_params(m, &po);
+    Workspace w;
+    carve(m, (char*)ws, &w);
+    const int B = m.B, H = m.H, L = m.L;
+    const int M = B * L;
+    const float *rm1 = bn, *rv1 = bn + CONV1_CO, *rm2 = bn + 2 * CONV1_CO, *rv2 = bn + 2 * CONV1_CO + m.O;
+    const float p = m.p;
+
+    MMS_CUDA(cudaMemsetAsync(w.bwd_zero, 0, w.bwd_zero_bytes, st));
+    rc = launch_head_bwd(w.last, w.hid, dlogits, P + po.fc3_w, B, 2 * H, m.nc, m.drop_head ? p : 0.f, d->rng_seed, d->rng_offset,
+                         d->rng_offset_dev, w.dhid, G + po.fc0_w, G + po.fc0_b, G + po.fc3_w, G + po.fc3_b, st);
+    if (rc) return rc;
+
+    const int top = m.layers - 1;
+    const float* in_top = top == 0 ? w.seq : w.outd[top - 1];
+    const int I_top = top == 0 ? m.O : 2 * H;
+    float* dxcur = w.dxa;
+    float* dxnext = w.dxb;
+    {
+        mms_gru_dir_bwd dirs[2];
+        memset(dirs, 0, sizeof(dirs));
+        dirs[0].w_hh = P + po.w_hh[top];
+        dirs[0].stash = w.stash_tf; dirs[0].st_bs = (int64_t)L * 4 * H; dirs[0].st_ts = 4 * H;
+        dirs[0].hs = w.hs_tf; dirs[0].hs_bs = (int64_t)L * H; dirs[0].hs_ts = H;
+        dirs[0].dh_head = w.dhid; dirs[0].w0 = P + po.fc0_w; dirs[0].w0_ld = 2 * H; dirs[0].w0_col = 0;
+        dirs[0].D = w.D_tf; dirs[0].d_bs = (int64_t)L * 4 * H; dirs[0].d_ts = 4 * H;
+        dirs[0].t0 = 0; dirs[0].dt = 1; dirs[0].nsteps = L;
+        dirs[1].w_hh = P + po.w_hh[top] + (int64_t)3 * H * H;
+        dirs[1].stash = w.stash_tr; dirs[1].st_bs = 4 * H; dirs[1].st_ts = 0;
+        dirs[1].hs = w.h_tr; dirs[1].hs_bs = H; dirs[1].hs_ts = 0;
+        dirs[1].dh_head = w.dhid; dirs[1].w0 = P + po.fc0_w; dirs[1].w0_ld = 2 * H; dirs[1].w0_col = H;
+        dirs[1].D = w.D_tr; dirs[1].d_bs = 4 * H; dirs[1].d_ts = 0;
+        dirs[1].t0 = L - 1; dirs[1].dt = -1; dirs[1].nsteps = 1;
+        rc = launch_gru_bwd(dirs, 2, B, H, p, d->rng_seed, d->rng_offset, d->rng_offset_dev, st);
+        if (rc) return rc;
+        // weight gradients of the top layer
+        rc = launch_gemm_tn_acc(w.D_tf, 4 * H, 3 * H, 0, in_top, I_top, 0, L, G + po.w_ih[top], I_top, G + po.b_ih[top], M, 3 * H, I_top, st);
+        if (rc) return rc;
+        rc = launch_gemm_tn_acc(w.D_tf, 4 * H, 2 * H, H, w.hs_tf, H, -1, L, G + po.w_hh[top], H, G + po.b_hh[top], M, 3 * H, H, st);
+        if (rc) return rc;
+        rc = launch_gemm_tn_acc(w.D_tr, 4 * H, 3 * H, 0, in_top + (int64_t)(L - 1) * I_top, (int64_t)L * I_top, 0, 1,
+                                G + po.w_ih[top] + (int64_t)3 * H * I_top, I_top, G + po.b_ih[top] + 3 * H, B, 3 * H, I_top, st);
+        if (rc) return rc;
+        // h_prev = 0 for the single reverse step: dW_hh(reverse) = 0, only the bias gradient remains
+        rc = launch_gemm_tn_acc(w.D_tr, 4 * H, 2 * H, H, nullptr, 0, 0, 1, nullptr, 0, G + po.b_hh[top] + 3 * H, B, 3 * H, 0, st);
+        if (rc) return rc;
+        // gradient w.r.t. the top layer's input
+        rc = launch_gemm_nn(w.D_tf, 4 * H, P + po.w_ih[top], I_top, dxcur, I_top, M, I_top, 3 * H, 0, st);
+        if (rc) return rc;
+        rc = launch_gemm_nn(w.D_tr, 4 * H, P + po.w_ih[top] + (int64_t)3 * H * I_top, I_top, dxcur + (int64_t)(L - 1) * I_top,
+                            (int64_t)L * I_top, B, I_top, 3 * H, 1, st);
+        if (rc) return rc;
+    }
+    for (int l = top - 1; l >= 0; --l) {
+        const float* in_l = l == 0 ? w.seq : w.outd[l - 1];
+        const int I_l = l == 0 ? m.O : 2 * H;
+        mms_gru_dir_bwd dirs[2];
+        memset(dirs, 0, sizeof(dirs));
+        for (int dd = 0; dd < 2; ++dd) {
+            mms_gru_dir_bwd& g = dirs[dd];
+            g.w_hh = P + po.w_hh[l] + (int64_t)dd * 3 * H * H;
+            g.stash = w.stash[l] + (int64_t)dd * M * 4 * H; g.st_bs = (int64_t)L * 4 * H; g.st_ts = 4 * H;
+            g.hs = w.hs[l] + dd * H; g.hs_bs = (int64_t)L * 2 * H; g.hs_ts = 2 * H;
+            g.dout = dxcur + dd * H; g.do_bs = (int64_t)L * 2 * H; g.do_ts = 2 * H;
+            g.drop_base = (int64_t)l * DROP_LAYER_STRIDE + dd * H;
+            g.drop_mask = m.drop_gru ? 1 : 0;
+            g.D = w.D[l] + dd * 4 * H; g.d_bs = (int64_t)L * 8 * H; g.d_ts = 8 * H;
+            g.t0 = dd ? L - 1 : 0; g.dt = dd ? -1 : 1; g.nsteps = L;
+        }
+        rc = launch_gru_bwd(dirs, 2, B, H, p, d->rng_seed, d->rng_offset, d->rng_offset_dev, st);
+        if (rc) return rc;
+        for (int dd = 0; dd < 2; ++dd) {
+            const float* Dd = w.D[l] + dd * 4 * H;
+            rc = launch_gemm_tn_acc(Dd, 8 * H, 3 * H, 0, in_l, I_l, 0, L, G + po.w_ih[l] + (int64_t)dd * 3 * H * I_l, I_l,
+                                    G + po.b_ih[l] + dd * 3 * H, M, 3 * H, I_l, st);
+            if (rc) return rc;
+            rc = launch_gemm_tn_acc(Dd, 8 * H, 2 * H, H, w.hs[l] + dd * H, 2 * H, dd ? 1 : -1, L,
+                                    G + po.w_hh[l] + (int64_t)dd * 3 * H * H, H, G + po.b_hh[l] + dd * 3 * H, M, 3 * H, H, st);
+            if (rc) return rc;
+            rc = launch_gemm_nn(Dd, 8 * H, P + po.w_ih[l] + (int64_t)dd * 3 * H * I_l, I_l, dxnext, I_l, M, I_l, 3 * H, dd, st);
+            if (rc) return rc;
+        }
+        float* t = dxcur; dxcur = dxnext; dxnext = t;
+    }
+    // dxcur = d(seq) [B, L, O] time-major
+    rc = launch_bn_relu_pool_bwd(w.y2, w.stats2, P + po.bn2_g, P + po.bn2_b, rm2, rv2, dxcur, B, m.O, m.L2c, m.training, 1, w.dy2,
+                                 G + po.bn2_g, G + po.bn2_b, w.red2, st);
+    if (rc) return rc;
+    rc = launch_conv_wgrad(2, w.p1, w.dy2, nullptr, B, CONV2_CI, m.O, m.P1, G + po.conv2_w, st);
+    if (rc) return rc;
+    rc = launch_conv_dgrad(2, w.dy2, P + po.conv2_w, B, CONV2_CI, m.O, m.P1, w.dp1, nullptr, nullptr, st);
+    if (rc) return rc;
+    rc = launch_bn_relu_pool_bwd(w.y1, w.stats1, P + po.bn1_g, P + po.bn1_b, rm1, rv1, w.dp1, B, CONV1_CO, m.L1c, m.training, 0,
+                                 w.dy1, G + po.bn1_g, G + po.bn1_b, w.red1, st);
+    if (rc) return rc;
+    rc = launch_conv_wgrad(1, x, w.dy1, m.attention ? w.gate : nullptr, B, m.C, CONV1_CO, m.T, G + po.conv1_w, st);
+    if (rc) return rc;
+    if (m.attention) {
+        if (m.A > 0 || dx) {
+            // dx (if requested) first receives d(x*gate); dgate[b,c] = sum_t d(x*gate) * x
+            rc = launch_conv_dgrad(1, w.dy1, P + po.conv1_w, B, m.C, CONV1_CO, m.T, dx, x, w.dgate, st);
+            if (rc) return rc;
+            float* ds = dx && m.A > 0 ? w.ca_scratch : nullptr;
+            rc = launch_chan_param_bwd(w.dgate, w.mean, w.gate, P + po.ca_w1, P + po.ca_w2, B, m.C, w.ca_scratch + (int64_t)B * m.C, ds,
+                                       G + po.ca_w1, G + po.ca_w2, st);
+            if (rc) return rc;
+            if (dx) {
+                rc = launch_chan_dx(dx, w.gate, ds, B, m.C, m.T, dx, st);
+                if (rc) return rc;
+            }
+        }
+    } else if (dx) {
+        rc = launch_conv_dgrad(1, w.dy1, P + po.conv1_w, B, m.C, CONV1_CO, m.T, dx, nullptr, nullptr, st);
+        if (rc) return rc;
+    }
+    return MMS_OK;
+}
+
+}  // namespace mms
+
+using namespace mms;
+
+extern "C" int mms_cnngru_param_layout(const mms_cnngru_desc* d, int64_t* offsets_host, int64_t* sizes_host, int32_t max_segments,
+                                       int64_t* total_floats_host) {
+    Dims m;
+    int rc = make_dims(d, &m);
+    if (rc) return rc;
+    ParamOff po;
+    make_params(m, &po);
+    MMS_REQUIRE(po.nseg <= max_segments, "param_layout: need room for %d segments", po.nseg);
+    for (int i = 0; i < po.nseg; ++i) {
+        if (offsets_host) offsets_host[i] = po.off[i];
+        if (sizes_host) sizes_host[i] = po.size[i];
+    }
+    if (total_floats_host) *total_floats_host = po.total;
+    return po.nseg;
+}
+
+extern "C" int64_t mms_cnngru_workspace_bytes(const mms_cnngru_desc* d) {
+    Dims m;
+    if (make_dims(d, &m)) return -1;
+    Workspace w;
+    carve(m, nullptr, &w);
+    return w.total;
+}
+
+extern "C" int mms_cnngru_forward(const mms_cnngru_desc* d, const float* x, const float* params, float* bn_buffers,
+                                  int64_t* num_batches_tracked, void* workspace, float* logits, mms_stream_t stream) {
+    return model_forward(d, x, params, bn_buffers, num_batches_tracked, workspace, logits, (cudaStream_t)stream);
+}
+
+extern "C" int mms_cnngru_backward(const mms_cnngru_desc* d, const float* x, const float* params, const float* bn_buffers,
+                                   void* workspace, const float* dlogits, float* grads, float* dx, mms_stream_t stream) {
+    return model_backward(d, x, params, bn_buffers, workspace, dlogits, grads, dx, (cudaStream_t)stream);
+}
+
+extern "C" int mms_cnngru_train_step(const mms_cnngru_desc* d, const float* x, const int64_t* labels, float* params, float* grads,
+                                     float* exp_avg, float* exp_avg_sq, float* bn_buffers, int64_t* num_batches_tracked,
+                                     void* workspace, float* logits, float* loss_out, double* loss_sum_accum, const float* lr_dev,
+                                     float beta1, float beta2, float eps, float weight_decay, int64_t* step_dev,
+                                     int32_t* scratch_dev, mms_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    Dims m;
+    int rc = make_dims(d, &m);
+    if (rc) return rc;
+    MMS_REQUIRE(m.training && m.need_grad, "train_step: descriptor must have training = need_grad = 1");
+    MMS_REQUIRE(labels && grads && exp_avg && exp_avg_sq && loss_out && lr_dev && step_dev && scratch_dev, "train_step: null pointer");
+    ParamOff po;
+    make_params(m, &po);
+    Workspace w;
+    carve(m, (char*)workspace, &w);
+    MMS_CUDA(cudaMemsetAsync(grads, 0, po.total * sizeof(float), st));                      // trainer.py:144
+    rc = model_forward(d, x, params, bn_buffers, num_batches_tracked, workspace, logits, st);  // trainer.py:146
+    if (rc) return rc;
+    rc = launch_cross_entropy(logits, labels, m.B, m.nc, loss_out, w.dlogits, loss_sum_accum, st);  // trainer.py:147
+    if (rc) return rc;
+    rc = model_backward(d, x, params, bn_buffers, workspace, w.dlogits, grads, nullptr, st);        // trainer.py:148
+    if (rc) return rc;
+    return launch_adam(params, grads, exp_avg, exp_avg_sq, po.total, lr_dev, beta1, beta2, eps, weight_decay, step_dev,
+                       scratch_dev, st);                                                          // trainer.py:149
+}

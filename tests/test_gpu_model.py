@@ -1,0 +1,188 @@
+"""Whole-model parity on a B200: the drop-in ``CnnGruAttentionModel`` (CUDA kernels through the
+C ABI) against fixtures produced by the unmodified reference ``models.py`` (tests/golden) and
+against the float64 oracle.
+
+Stated tolerances (north star / SURVEY §7): fp32 path, dropout disabled --
+|logit error| <= 1e-4 absolute; gradients <= 1e-3 of the tensor's max magnitude."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import MODEL_CASES, golden_state, load_golden
+from oracle import model_oracle as mo
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_ATOL = 1e-4
+GRAD_RTOL = 1e-3
+
+
+def build(meta, sd, dropout=0.0, attention=True):
+    from multimodalsignal_b200.models import CnnGruAttentionModel
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = CnnGruAttentionModel(meta["C"], meta["num_classes"], dropout=dropout, attention=attention, **meta["kwargs"])
+    missing = m.load_state_dict(sd, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    return m.cuda()
+
+
+@pytest.mark.parametrize("case", MODEL_CASES)
+def test_state_dict_layout_matches_reference(case):
+    z, meta = load_golden(f"model_{case}.npz")
+    sd = golden_state(z, "sd")
+    m = build(meta, sd)
+    mine = m.state_dict()
+    assert list(mine.keys()) == list(sd.keys())
+    for k in sd:
+        assert tuple(mine[k].shape) == tuple(sd[k].shape), k
+        assert mine[k].dtype == sd[k].dtype, k
+    # after the first CUDA forward every parameter is a view of the flat buffer and still round-trips
+    x = torch.from_numpy(z["x"]).cuda()
+    m.eval()
+    with torch.no_grad():
+        m(x)
+    for k, v in m.state_dict().items():
+        assert torch.equal(v.cpu(), sd[k]), k
+
+
+@pytest.mark.parametrize("case", MODEL_CASES)
+def test_train_forward_backward_vs_reference(case):
+    z, meta = load_golden(f"model_{case}.npz")
+    sd = golden_state(z, "sd")
+    m = build(meta, sd)
+    m.train()
+    x, y = torch.from_numpy(z["x"]).cuda(), torch.from_numpy(z["y"]).cuda()
+    logits = m(x)
+    np.testing.assert_allclose(logits.detach().cpu().numpy(), z["train_logits"], atol=LOGIT_ATOL)
+    loss = torch.nn.functional.cross_entropy(logits, y)
+    assert abs(loss.item() - float(z["train_loss"])) < 1e-4
+    loss.backward()
+    for k, p in m.named_parameters():
+        ref = z[f"grad/{k}"]
+        if ref.size == 0:
+            continue
+        got = p.grad.detach().cpu().numpy()
+        scale = max(np.abs(ref).max(), 1e-6)
+        assert np.abs(got - ref).max() <= GRAD_RTOL * scale, (k, np.abs(got - ref).max(), scale)
+    for k, v in m.state_dict().items():
+        if "running" in k:
+            np.testing.assert_allclose(v.cpu().numpy(), z[f"sd_after_fwd/{k}"], atol=2e-6, rtol=1e-5, err_msg=k)
+        if "num_batches" in k:
+            assert int(v.item()) == 1
+    m.eval()
+    with torch.no_grad():
+        ev = m(x)
+    np.testing.assert_allclose(ev.cpu().numpy(), z["eval_logits"], atol=LOGIT_ATOL)
+
+
+@pytest.mark.parametrize("case", MODEL_CASES)
+def test_gradients_vs_float64_oracle(case):
+    """Tighter than the float32 reference allows: compare with the oracle evaluated in float64."""
+    z, meta = load_golden(f"model_{case}.npz")
+    sd = golden_state(z, "sd")
+    params = {k: v.double() for k, v in sd.items() if "running" not in k and "num_batches" not in k}
+    x, y = torch.from_numpy(z["x"]), torch.from_numpy(z["y"])
+    loss, logits, grads, _ = mo.loss_and_grads(params, x.double(), y, training=True,
+                                               gru_layers=meta["kwargs"].get("gru_num_layers", 2), prune=True)
+    m = build(meta, sd)
+    m.train()
+    out = m(x.cuda())
+    np.testing.assert_allclose(out.detach().cpu().numpy(), logits.numpy(), atol=5e-5)
+    torch.nn.functional.cross_entropy(out, y.cuda()).backward()
+    for k, p in m.named_parameters():
+        ref = grads[k].numpy()
+        if ref.size == 0:
+            continue
+        got = p.grad.detach().cpu().numpy()
+        scale = max(np.abs(ref).max(), 1e-6)
+        assert np.abs(got - ref).max() <= 3e-4 * scale, (k, np.abs(got - ref).max(), scale)
+
+
+def test_input_gradient_matches_oracle():
+    z, meta = load_golden("model_c6_t640.npz")
+    sd = golden_state(z, "sd")
+    params = {k: v.double() for k, v in sd.items() if "running" not in k and "num_batches" not in k}
+    x, y = torch.from_numpy(z["x"]), torch.from_numpy(z["y"])
+    xr = x.double().requires_grad_()
+    logits, _ = mo.forward(params, xr, training=True)
+    mo.cross_entropy_mean(logits, y).backward()
+    m = build(meta, sd)
+    m.train()
+    xc = x.cuda().requires_grad_()
+    torch.nn.functional.cross_entropy(m(xc), y.cuda()).backward()
+    ref = xr.grad.numpy()
+    assert np.abs(xc.grad.cpu().numpy() - ref).max() <= 3e-4 * np.abs(ref).max()
+
+
+def test_cnn_gru_baseline_variant():
+    """configs[0]: ``cnn_gru`` = the stack without attention, vs the oracle."""
+    z, meta = load_golden("model_c6_t640.npz")
+    sd = golden_state(z, "sd")
+    params = {k: v.double() for k, v in sd.items() if "running" not in k and "num_batches" not in k}
+    x, y = torch.from_numpy(z["x"]), torch.from_numpy(z["y"])
+    loss, logits, grads, _ = mo.loss_and_grads(params, x.double(), y, training=True, attention=False, prune=True)
+    m = build(meta, sd, attention=False)
+    m.train()
+    out = m(x.cuda())
+    np.testing.assert_allclose(out.detach().cpu().numpy(), logits.numpy(), atol=5e-5)
+    torch.nn.functional.cross_entropy(out, y.cuda()).backward()
+    for k, p in m.named_parameters():
+        ref = grads[k].numpy()
+        got = p.grad.detach().cpu().numpy()
+        scale = max(np.abs(ref).max(), 1e-6)
+        assert np.abs(got - ref).max() <= 3e-4 * scale + 1e-9, k
+
+
+@pytest.mark.parametrize("case", ["c6_t640", "c8_h32_l1"])
+def test_fused_train_step_follows_reference_adam_trajectory(case):
+    """mms_cnngru_train_step (zero_grad+forward+CE+backward+Adam in one call, CUDA-graph replayed)
+    against the reference's torch.optim.Adam trajectory (trainer.py:68,144-149)."""
+    from multimodalsignal_b200.trainer import FusedTrainStep, FlatAdam
+    z, meta = load_golden(f"model_{case}.npz")
+    sd = golden_state(z, "sd")
+    m = build(meta, sd)
+    m.train()
+    x, y = torch.from_numpy(z["x"]).cuda(), torch.from_numpy(z["y"]).cuda()
+    opt = FlatAdam(m, lr=1e-3, weight_decay=1e-4)
+    step = FusedTrainStep(m, opt, batch=x.shape[0], seq_len=x.shape[2])
+    losses = []
+    for _ in range(int(z["adam_steps"])):
+        step(x, y)
+        losses.append(step.last_loss())
+    np.testing.assert_allclose(losses, z["adam_losses"], atol=1e-4)
+    mine = m.state_dict()
+    for k in sd:
+        ref = z[f"sd_adam/{k}"]
+        if ref.size == 0 or "num_batches" in k:
+            continue
+        np.testing.assert_allclose(mine[k].cpu().numpy(), ref, atol=5e-5, err_msg=k)
+    assert int(mine["cnn_encoder.1.num_batches_tracked"].item()) == int(z["adam_steps"])
+
+
+def test_dropout_training_runs_and_is_stochastic():
+    z, meta = load_golden("model_c6_t640.npz")
+    sd = golden_state(z, "sd")
+    m = build(meta, sd, dropout=0.5)
+    m.train()
+    x = torch.from_numpy(z["x"]).cuda()
+    a = m(x).detach().clone()
+    b = m(x).detach().clone()
+    assert torch.isfinite(a).all() and not torch.allclose(a, b)
+    y = torch.from_numpy(z["y"]).cuda()
+    out = m(x)
+    torch.nn.functional.cross_entropy(out, y).backward()
+    assert all(torch.isfinite(p.grad).all() for p in m.parameters() if p.numel())
+    m.eval()
+    with torch.no_grad():
+        np.testing.assert_allclose(m(x).cpu().numpy(), m(x).cpu().numpy())
+
+
+def test_cpu_input_is_refused():
+    """No CPU fallback: the product path fails loudly."""
+    from multimodalsignal_b200.models import CnnGruAttentionModel
+    from multimodalsignal_b200._ext import MmsError
+    m = CnnGruAttentionModel(6, 2)
+    with pytest.raises(MmsError):
+        m(torch.zeros(2, 6, 640))
