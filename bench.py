@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""Headline benchmark: CnnGruAttention training throughput (windows/s, fwd+bwd+Adam).
+
+``python bench.py --gpus N --steps K --warmup W`` -- one process per GPU (torchrun for N > 1).
+Workload = BASELINE.json configs[1]: cnn_gru_attention, 6 channels, B=64 windows of T=3840
+(64 Hz x 60 s), one LOSO fold per GPU, dropout 0.5 as the reference trains, synthetic data.
+With N > 1 every rank trains its own fold (LOSO folds are independent: weak scaling, no
+collective on the data path).
+
+One JSON line on rank 0:
+  value        windows/s, inputs resident in HBM (a pool larger than L2 is cycled);
+  e2e          the same step driven the way reference trainer.py:140-153 drives it: pinned HOST
+               batch -> H2D copy -> step -> loss read back (D2H + sync) every step;
+  roofline     the dominant kernel of the step, timed live with CUDA events (eager replay of the
+               same step through the library's event hooks);
+  cpu_baseline oracle/cpu_port.py (the reference's step through the same ATen CPU kernels) on the
+               host cores, bounded sample, rank 0 at N=1 only.
+``--impl reference`` times that CPU port alone (the reference is Python and cannot travel to the
+GPU box).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+FLOP_PER_WINDOW = {(6, 3840): 121.6e6, (14, 3840): 131.9e6, (6, 7680): 242.8e6}   # SURVEY §8d (minimal count)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--channels", type=int, default=6)
+    ap.add_argument("--seq-len", type=int, default=3840)
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the measured region (B200_PROFILING.md)."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc, self.thread = index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            return
+        def pump():
+            for line in self.proc.stdout:
+                self.rows.append(line.strip())
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            parts = [x.strip() for x in r.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(args, steps, warmup, budget_s):
+    """Time oracle/cpu_port.py (bounded by ``budget_s`` seconds of CPU work)."""
+    import torch
+    from oracle import cpu_port
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    p, bufs = cpu_port.make_state(C=args.channels, seed=0)
+    step = cpu_port.CpuTrainStep(p, bufs)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(args.batch, args.channels, args.seq_len, generator=g)
+    y = torch.randint(0, 2, (args.batch,), generator=g)
+    t0 = time.perf_counter()
+    step(x, y)
+    first = time.perf_counter() - t0
+    warm = max(0, min(warmup - 1, int(0.25 * budget_s / max(first, 1e-3))))
+    for _ in range(warm):
+        step(x, y)
+    n = max(1, min(steps, int(budget_s / max(first, 1e-3))))
+    t0 = time.perf_counter()
+    for _ in range(n):
+        step(x, y)
+    dt = time.perf_counter() - t0
+    return {"value": args.batch * n / dt, "unit": "windows/s", "cores": threads, "kind": "port",
+            "ms_per_step": 1e3 * dt / n, "timed_steps": n,
+            "sample": f"{n} full training steps (B={args.batch}, C={args.channels}, T={args.seq_len}, dropout 0.5, Adam) of "
+                      f"oracle/cpu_port.py = the reference step through the same ATen CPU kernels, {threads} threads"}
+
+
+def config_dict(args, n_gpus):
+    return {"workload": "cnn_gru_attention single LOSO fold per GPU (BASELINE.json configs[1])",
+            "batch": args.batch, "channels": args.channels, "seq_len": args.seq_len, "num_classes": 2,
+            "hidden": 64, "gru_layers": 2, "dropout": 0.5, "optimizer": "Adam lr=1e-3 wd=1e-4",
+            "global_batch": args.batch * n_gpus, "parallelism": f"fold-sharded x{n_gpus} (no collective)",
+            "l2_policy": "device-resident input pool of 48 batches (283 MB > 126 MB L2) cycled; activations ~170 MB/step"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_run(args, args.steps, args.warmup, budget_s=120.0)
+    line = {"impl": "reference", "metric": "train windows/sec (fwd+bwd+Adam) CnnGruAttention", "value": r["value"],
+            "unit": "windows/s", "n_gpus": args.gpus, "steps": r["timed_steps"], "requested_steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(args, args.gpus),
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from multimodalsignal_b200 import _ext
+    from multimodalsignal_b200.models import CnnGruAttentionModel
+    from multimodalsignal_b200.trainer import FlatAdam, FusedTrainStep
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _ext.lib()
+
+    B, Cc, T = args.batch, args.channels, args.seq_len
+    torch.manual_seed(42 + rank)                          # per-fold seeding (SURVEY §7 hard part 5)
+    model = CnnGruAttentionModel(Cc, 2, dropout=0.5).to(dev).train()
+    opt = FlatAdam(model, lr=1e-3, weight_decay=1e-4)
+    step = FusedTrainStep(model, opt, B, T, use_graph=not args.no_graph)
+
+    NB = 48
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    pool_x = torch.randn(NB, B, Cc, T, device=dev, generator=gen)
+    pool_y = torch.randint(0, 2, (NB, B), device=dev, generator=gen)
+    pool_x[:, :, 0, :] += pool_y[:, :, None].float() * 0.5
+    NH = 8
+    host_x = torch.randn(NH, B, Cc, T).pin_memory()
+    host_y = torch.randint(0, 2, (NH, B)).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    l0 = lib.mms_launch_count()
+    step(pool_x[0], pool_y[0])                            # eager: counts the kernels of one step
+    torch.cuda.synchronize()
+    kernels_per_step = int(lib.mms_launch_count() - l0)
+    for i in range(1, max(args.warmup, 3)):
+        step(pool_x[i % NB], pool_y[i % NB])
+    barrier()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+
+    # ---- value: device-resident inputs -------------------------------------------------------
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        step(pool_x[i % NB], pool_y[i % NB])
+    ev1.record()
+    barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    loss_after = step.last_loss()
+
+    # ---- e2e: pinned host batch -> H2D -> step -> loss.item() every step ----------------------
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    sink = 0.0
+    for i in range(args.steps):
+        step.load(host_x[i % NH], host_y[i % NH])
+        step.run()
+        sink += step.last_loss()                          # D2H read + sync, as trainer.py:152 does
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_ms = torch.tensor([max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0))], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_total = float(e2e_ms.item())
+
+    # keep the sampler under the same load until it has a few samples
+    if rank == 0:
+        t_end = time.perf_counter() + 1.5
+        while len(sampler.rows) < 5 and time.perf_counter() < t_end + 3.0:
+            for i in range(50):
+                step(pool_x[i % NB], pool_y[i % NB])
+            torch.cuda.synchronize()
+        clocks = sampler.stop()
+    barrier()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- live per-kernel times of the same step (eager, event-bracketed launches) -------------
+    PROF_STEPS = 20
+    lib.mms_profile_enable(1)
+    for i in range(PROF_STEPS):
+        step.load(pool_x[i % NB], pool_y[i % NB])
+        step._enqueue()
+    buf = (__import__("ctypes").c_char * 16384)()
+    lib.mms_profile_report(buf, 16384)
+    lib.mms_profile_enable(0)
+    kern = {}
+    for line in buf.value.decode().strip().splitlines():
+        name, cnt, tot = line.rsplit(" ", 2)
+        kern[name] = {"launches_per_step": int(cnt) / PROF_STEPS, "ms_per_step": float(tot) / PROF_STEPS,
+                      "avg_us": 1e3 * float(tot) / int(cnt)}
+    kern_total = sum(k["ms_per_step"] for k in kern.values())
+    top = max(kern, key=lambda k: kern[k]["ms_per_step"])
+
+    pk = peaks()
+    H, L = 64, model_seq_len(T)
+    # recurrent mat-vec FLOPs inside the GRU kernels per step: layer 0 both directions (2L steps),
+    # top layer forward direction (L steps) + its single reverse step; 3H x H MACs per step and row
+    gru_flops = 2.0 * 3 * H * H * B * (2 * L + L + 1)
+    flops_by_kernel = {"gru_fwd_kernel": gru_flops, "gru_bwd_kernel": gru_flops}
+    roof = {"kernel": top, "bound": "tensor", "unit": "TFLOP/s", "peak": pk["bf16_tflops_sustained"],
+            "peak_source": f"{pk['source']} bf16 sustained (kernel timed inside a long step)", "traffic": None,
+            "avg_us": kern[top]["avg_us"], "share_of_step_kernel_time": kern[top]["ms_per_step"] / kern_total}
+    if top in flops_by_kernel:
+        per_launch = flops_by_kernel[top] / kern[top]["launches_per_step"]
+        roof["achieved"] = per_launch / (kern[top]["avg_us"] * 1e-6) / 1e12
+        roof["frac"] = roof["achieved"] / roof["peak"]
+        roof["note"] = "fp32 SIMT recurrence, latency-bound by design (one block barrier per time step)"
+    else:
+        roof["achieved"], roof["frac"] = None, None
+
+    value = world * B * args.steps / (ms_total * 1e-3)
+    e2e_value = world * B * args.steps / (e2e_total * 1e-3)
+    fpw = FLOP_PER_WINDOW.get((Cc, T))
+    line = {
+        "metric": "train windows/sec (fwd+bwd+Adam) CnnGruAttention",
+        "value": value, "unit": "windows/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": config_dict(args, world),
+        "e2e": {"value": e2e_value, "unit": "windows/s", "ms_per_step": e2e_total / args.steps,
+                "h2d_bytes_per_step": B * Cc * T * 4 + B * 8, "d2h_bytes_per_step": 4},
+        "gpu_launches": kernels_per_step * args.steps, "kernels_per_step": kernels_per_step,
+        "cuda_graph": not args.no_graph, "clocks": clocks, "roofline": roof,
+        "step_roofline": {"flop_per_window": fpw, "achieved_tflops": (value / world) * fpw / 1e12 if fpw else None,
+                          "frac_of_bf16_sustained": (value / world) * fpw / 1e12 / pk["bf16_tflops_sustained"] if fpw else None},
+        "kernel_breakdown_ms_per_step": {k: round(v["ms_per_step"], 5) for k, v in kern.items()},
+        "eager_kernel_ms_per_step": kern_total, "final_loss": loss_after,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        r = cpu_reference_run(args, steps=10 ** 6, warmup=2, budget_s=args.cpu_seconds)
+        line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def model_seq_len(T):
+    l1 = (T + 6 - 7) // 2 + 1
+    p1 = (l1 - 1) // 2 + 1
+    l2 = (p1 + 4 - 5) // 2 + 1
+    return (l2 - 1) // 2 + 1
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -41,6 +41,15 @@ const char* mms_last_error(void);
  * the kernels that need it.  Must be called once per process before any other function. */
 int mms_init(int device);
 
+/* Diagnostics.  mms_launch_count(): kernels launched by this library since it was loaded
+ * (launches recorded into a CUDA graph count once, at capture).  mms_profile_enable(1) makes
+ * every subsequent eager launch record a CUDA-event pair on its stream (and clears earlier
+ * records); mms_profile_report() synchronises the device and writes one line per kernel name,
+ * "name launches total_ms", in first-launch order, into a host buffer. */
+int64_t mms_launch_count(void);
+int mms_profile_enable(int32_t on);
+int mms_profile_report(char* buf_host, int64_t buf_bytes);
+
 /* ------------------------------------------------------------------------------------------
  * Model description (reference models.py:39-40 constructor arguments + call-time facts).
  * Conv widths 16 / k7 / k5 and the 64-wide classifier hidden layer are hard-coded in the

@@ -44,3 +44,73 @@ extern "C" int mms_init(int device) {
     MMS_CUDA(cudaSetDevice(device));
     return MMS_OK;
 }
+
+// ---- launch counter + opt-in per-kernel event timer -------------------------------------------
+#include <atomic>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace mms {
+
+static std::atomic<long long> g_launches{0};
+static bool g_prof_on = false;
+struct ProfRec { const char* name; cudaEvent_t a, b; };
+static std::vector<ProfRec> g_recs;
+static thread_local cudaStream_t tl_stream = nullptr;
+static thread_local cudaEvent_t tl_begin = nullptr;
+
+void prof_begin(cudaStream_t st) {
+    tl_stream = st;
+    if (!g_prof_on) return;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return;
+    if (cudaEventCreate(&tl_begin) != cudaSuccess) { tl_begin = nullptr; return; }
+    cudaEventRecord(tl_begin, st);
+}
+
+void prof_end(const char* name) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (!g_prof_on || !tl_begin) return;
+    ProfRec r;
+    r.name = name;
+    r.a = tl_begin;
+    tl_begin = nullptr;
+    if (cudaEventCreate(&r.b) != cudaSuccess) { cudaEventDestroy(r.a); return; }
+    cudaEventRecord(r.b, tl_stream);
+    g_recs.push_back(r);
+}
+
+}  // namespace mms
+
+extern "C" int64_t mms_launch_count(void) { return (int64_t)g_launches.load(); }
+
+extern "C" int mms_profile_enable(int32_t on) {
+    for (auto& r : g_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    g_recs.clear();
+    g_prof_on = on != 0;
+    return MMS_OK;
+}
+
+extern "C" int mms_profile_report(char* buf_host, int64_t buf_bytes) {
+    MMS_REQUIRE(buf_host && buf_bytes > 0, "profile_report: bad buffer");
+    MMS_CUDA(cudaDeviceSynchronize());
+    std::map<std::string, std::pair<long long, double>> agg;
+    std::vector<std::string> order;
+    for (auto& r : g_recs) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) continue;
+        auto it = agg.find(r.name);
+        if (it == agg.end()) { agg[r.name] = {1, (double)ms}; order.push_back(r.name); }
+        else { it->second.first += 1; it->second.second += ms; }
+    }
+    std::string out;
+    char line[256];
+    for (auto& n : order) {
+        snprintf(line, sizeof(line), "%s %lld %.6f\n", n.c_str(), agg[n].first, agg[n].second);
+        out += line;
+    }
+    if ((int64_t)out.size() + 1 > buf_bytes) out.resize(buf_bytes - 1);
+    memcpy(buf_host, out.c_str(), out.size() + 1);
+    return MMS_OK;
+}

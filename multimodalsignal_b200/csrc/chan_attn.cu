@@ -153,6 +153,7 @@ int launch_chan_gate(const float* x, const float* w1, const float* w2, int B, in
                      float* gate_out, cudaStream_t st) {
     MMS_REQUIRE(C >= 1 && C <= CA_MAX_C, "chan_attn: in_channels %d outside [1,%d]", C, CA_MAX_C);
     const int A = C / 4;
+    MMS_PROF_BEGIN(st);
     chan_gate_kernel<<<B, 256, 0, st>>>(x, w1, w2, C, A, T, mean_out, gate_out);
     MMS_LAUNCH_CHECK("chan_gate_kernel");
     return MMS_OK;
@@ -162,6 +163,7 @@ int launch_chan_param_bwd(const float* dg, const float* mean, const float* gate,
                           int B, int C, float* scratch, float* ds, float* dw1, float* dw2, cudaStream_t st) {
     const int A = C / 4;
     if (A == 0) return MMS_OK;          // no parameters
+    MMS_PROF_BEGIN(st);
     chan_param_bwd_kernel<<<1, 256, 0, st>>>(dg, mean, gate, w1, w2, B, C, A, scratch, ds, dw1, dw2);
     MMS_LAUNCH_CHECK("chan_param_bwd_kernel");
     return MMS_OK;
@@ -169,6 +171,7 @@ int launch_chan_param_bwd(const float* dg, const float* mean, const float* gate,
 
 int launch_chan_dx(const float* dy, const float* gate, const float* ds, int B, int C, int T, float* dx, cudaStream_t st) {
     dim3 grid(cdiv(T, 1024), B * C);
+    MMS_PROF_BEGIN(st);
     chan_dx_kernel<<<grid, 256, 0, st>>>(dy, gate, ds, T, dx);
     MMS_LAUNCH_CHECK("chan_dx_kernel");
     return MMS_OK;
@@ -186,6 +189,7 @@ extern "C" int mms_chan_attn_fwd(const float* x, const float* w1, const float* w
     if (rc) return rc;
     if (y) {
         dim3 grid(cdiv(T, 1024), B * C);
+        MMS_PROF_BEGIN(st);
         chan_scale_kernel<<<grid, 256, 0, st>>>(x, gate_out, T, y);
         MMS_LAUNCH_CHECK("chan_scale_kernel");
     }
@@ -202,6 +206,7 @@ extern "C" int mms_chan_attn_bwd(const float* x, const float* dy, const float* w
     float* ds = scratch + (size_t)B * C;
     float* rest = ds + (size_t)B * C;
     const int A = C / 4;
+    MMS_PROF_BEGIN(st);
     chan_dot_kernel<<<B * C, 256, 0, st>>>(x, dy, T, dg);
     MMS_LAUNCH_CHECK("chan_dot_kernel");
     int rc = launch_chan_param_bwd(dg, mean, gate, w1, w2, B, C, rest, ds, dw1, dw2, st);

@@ -389,6 +389,7 @@ static int conv_fwd_launch(const float* x, const float* w, const float* gate, in
     if (!attr_done) { MMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr_done = true; }
     MMS_REQUIRE(smem <= 96 * 1024, "conv1d_fwd: shared memory %zu too large", smem);
     dim3 grid(cdiv(Lout, TL), B);
+    MMS_PROF_BEGIN(st);
     kern<<<grid, TL, smem, st>>>(x, w, gate, y, stats, CI, Lin, Lout);
     MMS_LAUNCH_CHECK("conv1d_fwd_kernel");
     return MMS_OK;
@@ -404,6 +405,7 @@ static int conv_dgrad_launch(const float* dy, const float* w, int B, int CI, int
     static bool attr_done = false;
     if (!attr_done) { MMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr_done = true; }
     dim3 grid(cdiv(Lin, TI), B);
+    MMS_PROF_BEGIN(st);
     kern<<<grid, TI, smem, st>>>(dy, w, dx, xdot, dgate, CI, Lin, Lout);
     MMS_LAUNCH_CHECK("conv1d_dgrad_kernel");
     return MMS_OK;
@@ -419,6 +421,7 @@ static int conv_wgrad_launch(const float* x, const float* dy, const float* gate,
     static bool attr_done = false;
     if (!attr_done) { MMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr_done = true; }
     dim3 grid(cdiv(Lout, TL), B);
+    MMS_PROF_BEGIN(st);
     kern<<<grid, 256, smem, st>>>(x, dy, gate, dw, CI, Lin, Lout);
     MMS_LAUNCH_CHECK("conv1d_wgrad_kernel");
     return MMS_OK;
@@ -473,9 +476,11 @@ int launch_bn_relu_pool_fwd(const float* y, const double* stats, const float* ga
     MMS_REQUIRE(!training || stats, "bn_relu_pool: training mode needs batch statistics");
     if (time_major) {
         dim3 grid(cdiv(Lout, 32), B);
+        MMS_PROF_BEGIN(st);
         bn_relu_pool_fwd_tm_kernel<<<grid, 256, 0, st>>>(y, stats, gamma, beta, rm, rv, nbt, B, C, l_in, Lout, training, out);
     } else {
         dim3 grid(cdiv(Lout, 256), C, B);
+        MMS_PROF_BEGIN(st);
         bn_relu_pool_fwd_ncl_kernel<<<grid, 256, 0, st>>>(y, stats, gamma, beta, rm, rv, nbt, B, C, l_in, Lout, training, out);
     }
     MMS_LAUNCH_CHECK("bn_relu_pool_fwd");
@@ -488,8 +493,10 @@ int launch_bn_relu_pool_bwd(const float* y, const double* stats, const float* ga
     const int Lout = pool_out_len(l_in);
     MMS_REQUIRE(C >= 1 && C <= 64, "bn_relu_pool_bwd: channels %d outside [1,64]", C);
     dim3 grid(cdiv(l_in, 256), C, B);
+    MMS_PROF_BEGIN(st);
     pool_relu_bwd_kernel<<<grid, 256, 0, st>>>(y, stats, gamma, beta, rm, rv, dout, B, C, l_in, Lout, training, time_major, dy, red);
     MMS_LAUNCH_CHECK("pool_relu_bwd_kernel");
+    MMS_PROF_BEGIN(st);
     bn_bwd_apply_kernel<<<grid, 256, 0, st>>>(y, stats, gamma, beta, rm, rv, red, B, C, l_in, training, dy, dgamma, dbeta);
     MMS_LAUNCH_CHECK("bn_bwd_apply_kernel");
     return MMS_OK;

@@ -190,6 +190,7 @@ int launch_gemm_nt_bias(const float* A, int64_t lda, const float* W, int64_t ldw
                         int M, int N, int K, cudaStream_t st) {
     if (M <= 0 || N <= 0) return MMS_OK;
     dim3 grid(cdiv(N, BN), cdiv(M, BM));
+    MMS_PROF_BEGIN(st);
     gemm_nt_bias_kernel<<<grid, 256, 0, st>>>(A, lda, W, ldw, bias, C, ldc, M, N, K, aligned16(A) && lda % 4 == 0,
                                               aligned16(W) && ldw % 4 == 0);
     MMS_LAUNCH_CHECK("gemm_nt_bias_kernel");
@@ -200,6 +201,7 @@ int launch_gemm_nn(const float* A, int64_t lda, const float* W, int64_t ldw, flo
                    int accumulate, cudaStream_t st) {
     if (M <= 0 || N <= 0) return MMS_OK;
     dim3 grid(cdiv(N, BN), cdiv(M, BM));
+    MMS_PROF_BEGIN(st);
     gemm_nn_kernel<<<grid, 256, 0, st>>>(A, lda, W, ldw, C, ldc, M, N, K, accumulate, aligned16(A) && lda % 4 == 0,
                                          aligned16(W) && ldw % 4 == 0);
     MMS_LAUNCH_CHECK("gemm_nn_kernel");
@@ -213,6 +215,7 @@ int launch_gemm_tn_acc(const float* A, int64_t lda, int a_split, int a_skip, con
     int chunk = 256;
     while (chunk < M && cdiv(M, chunk) > 96) chunk *= 2;
     dim3 grid(cdiv(N2 > 0 ? N2 : 1, BN), cdiv(N1, BM), cdiv(M, chunk));
+    MMS_PROF_BEGIN(st);
     gemm_tn_acc_kernel<<<grid, 256, 0, st>>>(A, lda, a_split, a_skip, Bm, ldb, shift, seq, C, ldc, bias_grad, M, N1, N2, chunk);
     MMS_LAUNCH_CHECK("gemm_tn_acc_kernel");
     return MMS_OK;

@@ -2,16 +2,24 @@
 // reverse-time backward, as persistent kernels: one CTA owns R batch rows of one direction for the
 // whole sequence, so there is no inter-CTA communication and one block barrier per time step.
 //
-// Layout of a CTA: 4*H threads, thread (j, q) = (tid >> 2, tid & 3).
-//   forward : thread (j,q) keeps W_hh[g*H + j, q*H/4 .. (q+1)*H/4) for the three gates g in registers
-//             (3*H/4 floats), multiplies by the matching quarter of h (shared memory, broadcast loads)
-//             and the four partial sums of a hidden unit meet by two warp-shuffle butterflies; the gate
-//             non-linearities and the state update then run in the same threads -> one barrier per step.
-//   backward: thread (k,q) keeps column k of W_hh for gate rows [g*H + q*H/4, +H/4); the step's
-//             (d r_pre, d z_pre, d q) vector goes through shared memory (double-buffered).
-// Everything the step needs from global memory (input projections, stashed gates, upstream
-// gradients) is prefetched PF steps ahead into registers, so only shared memory and the shuffles
-// sit on the serial dependency chain.  All arithmetic is fp32 (tolerance, SURVEY §7 hard part 2).
+// The kernels are latency-bound: a 240-step serial chain whose every step is a 3H x H mat-vec plus
+// the gate non-linearities.  The design therefore minimises the per-step dependent chain and the
+// instruction count, not bytes:
+//   * a CTA has 2*H threads; thread (p, q) = (tid >> 2, tid & 3) owns TWO hidden units (p and p + H/2)
+//     and a quarter q of the reduction index.  Its 3 gates x H/4 weights for both units sit in
+//     registers as float2 pairs, so every multiply-accumulate is one packed fma.rn.f32x2 (Blackwell's
+//     FFMA2: two fp32 FMAs per issue slot) against a broadcast h value;
+//   * the four partial sums of a unit meet by a two-stage warp-shuffle reduce-scatter (even lanes end
+//     with unit p, odd lanes with unit p + H/2), after which the same threads apply the gates: one
+//     block barrier per step;
+//   * h lives in shared memory, double-buffered, with each quarter padded by 4 floats so the four
+//     lanes of a quad hit distinct banks (conflict-free 128-bit loads);
+//   * every global address is a running pointer (no 64-bit multiplies in the loop) and everything a
+//     step needs from global memory (input projections, stashed gates, upstream gradients) is
+//     prefetched PF steps ahead into registers;
+//   * sigmoid / tanh use the ex2 / rcp special-function units (|error| ~ 2e-7, far inside the
+//     1e-4 logit tolerance).
+// All arithmetic is fp32 (SURVEY §7 hard part 2).
 #include "mms_common.cuh"
 
 namespace mms {
@@ -34,270 +42,342 @@ struct GruBwdParams {
     const int64_t* offset_dev;
 };
 
-__device__ __forceinline__ float quad_sum(float v) {
-    v += __shfl_xor_sync(0xffffffffu, v, 1);
-    v += __shfl_xor_sync(0xffffffffu, v, 2);
-    return v;
-}
+// sigmoid / tanh on the special-function units: ex2.approx + rcp.approx (2 MUFU ops each).
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return fmaf(2.f, fast_sigmoid(2.f * x), -1.f); }
+
+__device__ __forceinline__ float2 bcast2(float v) { return make_float2(v, v); }
+
+// padded position of element k of an H-vector split into quarters of KS floats
+template <int KS>
+__device__ __forceinline__ int padded(int k) { return k + (k / KS) * 4; }
 
 template <int H, int R>
-__global__ void __launch_bounds__(4 * H) gru_fwd_kernel(const GruFwdParams prm) {
-    constexpr int KS = H / 4;
-    const mms_gru_dir_fwd& d = prm.dir[blockIdx.y];
-    const int tid = threadIdx.x, j = tid >> 2, q = tid & 3;
+__global__ void __launch_bounds__(2 * H) gru_fwd_kernel(const GruFwdParams prm) {
+    constexpr int KS = H / 4, HP = H / 2, HPAD = H + 16;
+    const mms_gru_dir_fwd d = prm.dir[blockIdx.y];
+    const int tid = threadIdx.x, p = tid >> 2, q = tid & 3;
+    const int own = q & 1;                 // which of the two units this lane finishes
+    const int ju = p + own * HP;
+    const bool first = q < 2;              // first / second lane of the unit (splits the stores)
     const int b0 = blockIdx.x * R;
     const int B = prm.B;
+    const int nsteps = d.nsteps;
 
-    __shared__ __align__(16) float hsm[2][R][H];
+    __shared__ __align__(16) float hsm[2][R][HPAD];
 
-    // recurrent weights of this thread: rows g*H + j, columns [q*KS, q*KS + KS)
-    float w[3][KS];
+    // recurrent weights: rows g*H + {p, p+HP}, columns [q*KS, q*KS + KS), packed (unit A, unit B)
+    float2 w2[3][KS];
 #pragma unroll
     for (int g = 0; g < 3; ++g)
 #pragma unroll
-        for (int i = 0; i < KS; ++i) w[g][i] = __ldg(d.w_hh + (size_t)(g * H + j) * H + q * KS + i);
-    float bh[3];
+        for (int i = 0; i < KS; ++i)
+            w2[g][i] = make_float2(__ldg(d.w_hh + (size_t)(g * H + p) * H + q * KS + i),
+                                   __ldg(d.w_hh + (size_t)(g * H + p + HP) * H + q * KS + i));
+    float2 bh2[3];
 #pragma unroll
-    for (int g = 0; g < 3; ++g) bh[g] = (q == 0) ? __ldg(d.b_hh + g * H + j) : 0.f;
+    for (int g = 0; g < 3; ++g)
+        bh2[g] = q == 0 ? make_float2(__ldg(d.b_hh + g * H + p), __ldg(d.b_hh + g * H + p + HP)) : make_float2(0.f, 0.f);
 
-    for (int i = tid; i < 2 * R * H; i += 4 * H) (&hsm[0][0][0])[i] = 0.f;
+    for (int i = tid; i < 2 * R * HPAD; i += 2 * H) (&hsm[0][0][0])[i] = 0.f;
 
     DropRng rng;
     const bool do_drop = d.hs_drop != nullptr;
     if (do_drop) rng.init(prm.seed, resolve_offset(prm.offset, prm.offset_dev), prm.p);
+    const bool do_stash = d.stash != nullptr;
 
-    int bb[R];
+    // running pointers (advance by dt * stride per step); loads clamp the row, stores are guarded
+    const int64_t gi_step = (int64_t)d.dt * d.gi_ts, hs_step = (int64_t)d.dt * d.hs_ts, st_step = (int64_t)d.dt * d.st_ts;
+    const float* gi_p[R];
+    float* hs_p[R];
+    float* st_p[R];
+    int64_t he[R];          // element index of hs (dropout id / hs_drop offset)
+    bool live[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) bb[r] = min(b0 + r, B - 1);     // clamp loads; stores are guarded
+    for (int r = 0; r < R; ++r) {
+        const int bb = min(b0 + r, B - 1);
+        live[r] = (b0 + r) < B;
+        gi_p[r] = d.gi + (int64_t)bb * d.gi_bs + (int64_t)d.t0 * d.gi_ts + ju;
+        he[r] = (int64_t)bb * d.hs_bs + (int64_t)d.t0 * d.hs_ts + ju;
+        hs_p[r] = d.hs + he[r];
+        st_p[r] = do_stash ? d.stash + (int64_t)bb * d.st_bs + (int64_t)d.t0 * d.st_ts + ju : nullptr;
+    }
 
-    // gi ring: lane q < 3 holds gate q's input projection of unit j
-    float ring[PF][R];
-    const int gq = q < 3 ? q : 2;
+    // ring of input projections (r, z, n of unit ju), PF steps ahead
+    float ring[PF][R][3];
 #pragma unroll
     for (int u = 0; u < PF; ++u)
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            ring[u][r] = 0.f;
-            if (u < d.nsteps) {
-                const int t = d.t0 + u * d.dt;
-                ring[u][r] = __ldg(d.gi + (size_t)bb[r] * d.gi_bs + (size_t)t * d.gi_ts + gq * H + j);
-            }
+#pragma unroll
+            for (int g = 0; g < 3; ++g) ring[u][r][g] = __ldg(gi_p[r] + g * H);
+            if (u + 1 < nsteps) gi_p[r] += gi_step;      // never step past the last valid time index
         }
+    int loaded = min(PF, nsteps);                        // number of distinct steps already requested
     __syncthreads();
 
     int cur = 0;
-    for (int s0 = 0; s0 < d.nsteps; s0 += PF) {
+    for (int s0 = 0; s0 < nsteps; s0 += PF) {
 #pragma unroll
         for (int u = 0; u < PF; ++u) {
-            const int s = s0 + u;
-            if (s < d.nsteps) {
-                const int t = d.t0 + s * d.dt;
-                float gi_own[R];
+            if (s0 + u >= nsteps) break;
+            float gi[R][3];
 #pragma unroll
-                for (int r = 0; r < R; ++r) gi_own[r] = ring[u][r];
-                if (s + PF < d.nsteps) {
-                    const int tn = d.t0 + (s + PF) * d.dt;
+            for (int r = 0; r < R; ++r)
 #pragma unroll
-                    for (int r = 0; r < R; ++r)
-                        ring[u][r] = __ldg(d.gi + (size_t)bb[r] * d.gi_bs + (size_t)tn * d.gi_ts + gq * H + j);
+                for (int g = 0; g < 3; ++g) {
+                    gi[r][g] = ring[u][r][g];
+                    ring[u][r][g] = __ldg(gi_p[r] + g * H);   // step s + PF (a harmless re-read at the tail)
                 }
+            if (loaded + 1 < nsteps) {
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    float a0 = bh[0], a1 = bh[1], a2 = bh[2];
-                    const float4* hv = reinterpret_cast<const float4*>(&hsm[cur][r][q * KS]);
-#pragma unroll
-                    for (int i4 = 0; i4 < KS / 4; ++i4) {
-                        const float4 h4 = hv[i4];
-                        a0 = fmaf(w[0][4 * i4 + 0], h4.x, a0); a1 = fmaf(w[1][4 * i4 + 0], h4.x, a1); a2 = fmaf(w[2][4 * i4 + 0], h4.x, a2);
-                        a0 = fmaf(w[0][4 * i4 + 1], h4.y, a0); a1 = fmaf(w[1][4 * i4 + 1], h4.y, a1); a2 = fmaf(w[2][4 * i4 + 1], h4.y, a2);
-                        a0 = fmaf(w[0][4 * i4 + 2], h4.z, a0); a1 = fmaf(w[1][4 * i4 + 2], h4.z, a1); a2 = fmaf(w[2][4 * i4 + 2], h4.z, a2);
-                        a0 = fmaf(w[0][4 * i4 + 3], h4.w, a0); a1 = fmaf(w[1][4 * i4 + 3], h4.w, a1); a2 = fmaf(w[2][4 * i4 + 3], h4.w, a2);
-                    }
-                    // lanes 0 and 1 fold their input projection into the r / z partial sums
-                    if (q == 0) a0 += gi_own[r];
-                    if (q == 1) a1 += gi_own[r];
-                    a0 = quad_sum(a0);
-                    a1 = quad_sum(a1);
-                    a2 = quad_sum(a2);                                        // = W_hn h + b_hn
-                    const float gin = __shfl_sync(0xffffffffu, gi_own[r], 2, 4);   // lane 2 of the quad
-                    const float rg = sigmoid_f(a0);
-                    const float zg = sigmoid_f(a1);
-                    const float ng = tanhf(fmaf(rg, a2, gin));
-                    const float hp = hsm[cur][r][j];
-                    const float hn = fmaf(zg, hp - ng, ng);                   // (1-z)*n + z*h
-                    const bool live = (b0 + r) < B;
-                    if (q == 0) {
-                        hsm[cur ^ 1][r][j] = hn;
-                        if (live) d.hs[(size_t)(b0 + r) * d.hs_bs + (size_t)t * d.hs_ts + j] = hn;
-                    }
-                    if (q == 1 && do_drop && live) {
-                        const size_t e = (size_t)(b0 + r) * d.hs_bs + (size_t)t * d.hs_ts + j;
-                        d.hs_drop[e] = hn * rng.mult((uint64_t)d.drop_base + e);
-                    }
-                    if (d.stash && live) {
-                        const float sv = q == 0 ? rg : (q == 1 ? zg : (q == 2 ? ng : a2));
-                        d.stash[(size_t)(b0 + r) * d.st_bs + (size_t)t * d.st_ts + q * H + j] = sv;
-                    }
-                }
-                __syncthreads();
-                cur ^= 1;
+                for (int r = 0; r < R; ++r) gi_p[r] += gi_step;
             }
+            ++loaded;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                float2 acc[3] = {bh2[0], bh2[1], bh2[2]};
+                const float4* hv = reinterpret_cast<const float4*>(&hsm[cur][r][q * (KS + 4)]);
+#pragma unroll
+                for (int i4 = 0; i4 < KS / 4; ++i4) {
+                    const float4 h4 = hv[i4];
+#pragma unroll
+                    for (int g = 0; g < 3; ++g) acc[g] = __ffma2_rn(w2[g][4 * i4 + 0], bcast2(h4.x), acc[g]);
+#pragma unroll
+                    for (int g = 0; g < 3; ++g) acc[g] = __ffma2_rn(w2[g][4 * i4 + 1], bcast2(h4.y), acc[g]);
+#pragma unroll
+                    for (int g = 0; g < 3; ++g) acc[g] = __ffma2_rn(w2[g][4 * i4 + 2], bcast2(h4.z), acc[g]);
+#pragma unroll
+                    for (int g = 0; g < 3; ++g) acc[g] = __ffma2_rn(w2[g][4 * i4 + 3], bcast2(h4.w), acc[g]);
+                }
+                // reduce-scatter over the quad: stage 1 keeps this lane's unit, stage 2 completes it
+                float sg[3];
+#pragma unroll
+                for (int g = 0; g < 3; ++g) {
+                    const float keep = own ? acc[g].y : acc[g].x;
+                    const float send = own ? acc[g].x : acc[g].y;
+                    sg[g] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+                }
+#pragma unroll
+                for (int g = 0; g < 3; ++g) sg[g] += __shfl_xor_sync(0xffffffffu, sg[g], 2);
+                // sg = W_h{r,z,n} h + b_h{r,z,n} of unit ju
+                const float rg = fast_sigmoid(sg[0] + gi[r][0]);
+                const float zg = fast_sigmoid(sg[1] + gi[r][1]);
+                const float ng = fast_tanh(fmaf(rg, sg[2], gi[r][2]));
+                const float hp = hsm[cur][r][padded<KS>(ju)];
+                const float hn = fmaf(zg, hp - ng, ng);                        // (1-z)*n + z*h
+                if (first) hsm[cur ^ 1][r][padded<KS>(ju)] = hn;
+                if (live[r]) {
+                    if (first) {
+                        *hs_p[r] = hn;
+                        if (do_stash) { st_p[r][0] = rg; st_p[r][H] = zg; }
+                    } else {
+                        if (do_stash) { st_p[r][2 * H] = ng; st_p[r][3 * H] = sg[2]; }
+                        if (do_drop) d.hs_drop[he[r]] = hn * rng.mult((uint64_t)(d.drop_base + he[r]));
+                    }
+                }
+                he[r] += hs_step;
+                hs_p[r] += hs_step;
+                st_p[r] += st_step;
+            }
+            __syncthreads();
+            cur ^= 1;
         }
     }
 }
 
 template <int H, int R>
-__global__ void __launch_bounds__(4 * H) gru_bwd_kernel(const GruBwdParams prm) {
-    constexpr int KS = H / 4;
-    const mms_gru_dir_bwd& d = prm.dir[blockIdx.y];
-    const int tid = threadIdx.x, k = tid >> 2, q = tid & 3;
+__global__ void __launch_bounds__(2 * H) gru_bwd_kernel(const GruBwdParams prm) {
+    constexpr int KS = H / 4, HP = H / 2, GP = H + 16;      // GP: padded length of one gate vector
+    constexpr int PFB = R == 1 ? 4 : 2;                     // shallower prefetch ring when several rows share the registers
+    const mms_gru_dir_bwd d = prm.dir[blockIdx.y];
+    const int tid = threadIdx.x, p = tid >> 2, q = tid & 3;
+    const int own = q & 1;
+    const int ku = p + own * HP;           // the column (hidden unit) whose gate math this lane does
+    const bool first = q < 2;
     const int b0 = blockIdx.x * R;
     const int B = prm.B;
+    const int nsteps = d.nsteps;
 
-    __shared__ __align__(16) float dgh[2][R][3 * H];
+    __shared__ __align__(16) float dgh[2][R][3 * GP];
 
-    // column k of W_hh, gate rows [g*H + q*KS, +KS)
-    float w[3][KS];
+    // columns {p, p+HP} of W_hh, gate rows [g*H + q*KS, +KS), packed (column A, column B)
+    float2 w2[3][KS];
 #pragma unroll
     for (int g = 0; g < 3; ++g)
 #pragma unroll
-        for (int i = 0; i < KS; ++i) w[g][i] = __ldg(d.w_hh + (size_t)(g * H + q * KS + i) * H + k);
+        for (int i = 0; i < KS; ++i)
+            w2[g][i] = make_float2(__ldg(d.w_hh + (size_t)(g * H + q * KS + i) * H + p),
+                                   __ldg(d.w_hh + (size_t)(g * H + q * KS + i) * H + p + HP));
 
     DropRng rng;
-    const bool do_mask = d.drop_mask != 0 && d.dout != nullptr;
+    const bool has_dout = d.dout != nullptr;
+    const bool do_mask = d.drop_mask != 0 && has_dout;
     if (do_mask) rng.init(prm.seed, resolve_offset(prm.offset, prm.offset_dev), prm.p);
 
-    int bb[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) bb[r] = min(b0 + r, B - 1);
-
-    // initial recurrent gradient: optional projection of the head gradient (dlast = dhid @ W0)
+    // The visit order is the reverse of the forward order: forward step s = nsteps-1 ... 0 at time
+    // t = t0 + s*dt.  Running pointers start at the last forward step and move by -dt * stride.
+    const int t_last = d.t0 + (nsteps - 1) * d.dt;
+    const int64_t st_step = -(int64_t)d.dt * d.st_ts, hs_step = -(int64_t)d.dt * d.hs_ts;
+    const int64_t do_step = -(int64_t)d.dt * d.do_ts, d_step = -(int64_t)d.dt * d.d_ts;
+    const float* st_p[R];     // prefetch side (PF visits ahead)
+    const float* hp_p[R];     // h_{prev} of the prefetched step
+    const float* do_p[R];
+    int64_t doe[R];           // element index into dout (dropout id)
+    float* D_p[R];            // store side (current visit)
     float dh[R];
+    float dlast[R];
+    bool live[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
+        const int bb = min(b0 + r, B - 1);
+        live[r] = (b0 + r) < B;
+        st_p[r] = d.stash + (int64_t)bb * d.st_bs + (int64_t)t_last * d.st_ts + ku;
+        hp_p[r] = d.hs + (int64_t)bb * d.hs_bs + (int64_t)(t_last - d.dt) * d.hs_ts + ku;   // only read when s > 0
+        doe[r] = (int64_t)bb * d.do_bs + (int64_t)t_last * d.do_ts + ku;
+        do_p[r] = has_dout ? d.dout + doe[r] : nullptr;
+        D_p[r] = d.D + (int64_t)bb * d.d_bs + (int64_t)t_last * d.d_ts + (first ? 0 : 2 * H) + ku;
+        dlast[r] = d.dout_last ? __ldg(d.dout_last + (int64_t)bb * d.dl_ld + ku) : 0.f;
+        // initial recurrent gradient: optional projection of the head gradient (dlast = dhid @ W0)
         float s = 0.f;
         if (d.dh_head) {
             for (int i = 0; i < HEAD_HID; ++i)
-                s = fmaf(__ldg(d.dh_head + (size_t)bb[r] * HEAD_HID + i), __ldg(d.w0 + (size_t)i * d.w0_ld + d.w0_col + k), s);
+                s = fmaf(__ldg(d.dh_head + (size_t)bb * HEAD_HID + i), __ldg(d.w0 + (size_t)i * d.w0_ld + d.w0_col + ku), s);
         }
         dh[r] = s;
     }
 
-    // ring of per-step inputs: stash (r,z,n,qq), h_prev, dout -- every lane of the quad loads all
+    // ring of per-step inputs for column ku: stash (r,z,n,qq), h_prev, dout
     struct StepIn { float r, z, n, qq, hp, dout; };
-    StepIn ring[PF][R];
-    auto load_step = [&](int s, int r) {
+    StepIn ring[PFB][R];
+    int fetch_s = nsteps - 1;         // forward-step index the prefetch pointers refer to
+    auto fetch = [&](int r) {
         StepIn v;
-        const int t = d.t0 + s * d.dt;
-        const float* sp = d.stash + (size_t)bb[r] * d.st_bs + (size_t)t * d.st_ts + k;
+        const float* sp = st_p[r];
         v.r = __ldg(sp);
         v.z = __ldg(sp + H);
         v.n = __ldg(sp + 2 * H);
         v.qq = __ldg(sp + 3 * H);
-        v.hp = s > 0 ? __ldg(d.hs + (size_t)bb[r] * d.hs_bs + (size_t)(t - d.dt) * d.hs_ts + k) : 0.f;
+        v.hp = fetch_s > 0 ? __ldg(hp_p[r]) : 0.f;
         float g = 0.f;
-        if (d.dout) {
-            const size_t e = (size_t)bb[r] * d.do_bs + (size_t)t * d.do_ts + k;
-            g = __ldg(d.dout + e);
-            if (do_mask) g *= rng.mult((uint64_t)d.drop_base + e);
+        if (has_dout) {
+            g = __ldg(do_p[r]);
+            if (do_mask) g *= rng.mult((uint64_t)(d.drop_base + doe[r]));
         }
-        if (d.dout_last && s == d.nsteps - 1) g += __ldg(d.dout_last + (size_t)bb[r] * d.dl_ld + k);
         v.dout = g;
         return v;
     };
-    // steps are visited in reverse forward order: s = nsteps-1 ... 0; ring slot u <-> visit index
+    auto advance = [&]() {            // move the prefetch pointers one visit further (if any step is left)
+        if (fetch_s > 0) {
 #pragma unroll
-    for (int u = 0; u < PF; ++u)
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int s = d.nsteps - 1 - u;
-            if (s >= 0) ring[u][r] = load_step(s, r);
-            else ring[u][r] = StepIn{0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int r = 0; r < R; ++r) {
+                st_p[r] += st_step;
+                hp_p[r] += hs_step;
+                if (has_dout) { do_p[r] += do_step; doe[r] += do_step; }
+            }
         }
+        --fetch_s;
+    };
+#pragma unroll
+    for (int u = 0; u < PFB; ++u) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) ring[u][r] = fetch_s >= 0 ? fetch(r) : StepIn{0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        advance();
+    }
 
     int buf = 0;
-    for (int v0 = 0; v0 < d.nsteps; v0 += PF) {
+    for (int v0 = 0; v0 < nsteps; v0 += PFB) {
 #pragma unroll
-        for (int u = 0; u < PF; ++u) {
+        for (int u = 0; u < PFB; ++u) {
             const int v = v0 + u;
-            if (v < d.nsteps) {
-                const int s = d.nsteps - 1 - v;
-                const int t = d.t0 + s * d.dt;
-                StepIn in[R];
+            if (v >= nsteps) break;
+            const int s = nsteps - 1 - v;
+            StepIn in[R];
 #pragma unroll
-                for (int r = 0; r < R; ++r) in[r] = ring[u][r];
-                if (s - PF >= 0) {
+            for (int r = 0; r < R; ++r) in[r] = ring[u][r];
+            if (fetch_s >= 0) {
 #pragma unroll
-                    for (int r = 0; r < R; ++r) ring[u][r] = load_step(s - PF, r);
+                for (int r = 0; r < R; ++r) ring[u][r] = fetch(r);
+            }
+            advance();
+            float dhz[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const StepIn& x = in[r];
+                const float dht = dh[r] + x.dout + (v == 0 ? dlast[r] : 0.f);
+                const float dn = dht * (1.f - x.z);
+                const float dz = dht * (x.hp - x.n);
+                const float dnp = dn * (1.f - x.n * x.n);
+                const float dq = dnp * x.r;
+                const float dr = dnp * x.qq;
+                const float dzp = dz * x.z * (1.f - x.z);
+                const float drp = dr * x.r * (1.f - x.r);
+                dhz[r] = dht * x.z;
+                if (first) {
+                    float* g = &dgh[buf][r][padded<KS>(ku)];
+                    g[0] = drp; g[GP] = dzp; g[2 * GP] = dq;
                 }
-                float dhz[R];
+                if (live[r]) {          // D = (d r_pre, d z_pre, d n_pre, d q): first lane stores 0,1; second 2,3
+                    D_p[r][0] = first ? drp : dnp;
+                    D_p[r][H] = first ? dzp : dq;
+                }
+                D_p[r] += d_step;
+            }
+            __syncthreads();
+            if (s > 0) {     // the gradient flowing into h_{-1} = h0 is not needed
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    const StepIn& x = in[r];
-                    const float dht = dh[r] + x.dout;
-                    const float dn = dht * (1.f - x.z);
-                    const float dz = dht * (x.hp - x.n);
-                    const float dnp = dn * (1.f - x.n * x.n);
-                    const float dq = dnp * x.r;
-                    const float dr = dnp * x.qq;
-                    const float dzp = dz * x.z * (1.f - x.z);
-                    const float drp = dr * x.r * (1.f - x.r);
-                    dhz[r] = dht * x.z;
-                    if (q < 3) dgh[buf][r][q * H + k] = q == 0 ? drp : (q == 1 ? dzp : dq);
-                    if ((b0 + r) < B) {
-                        const float ov = q == 0 ? drp : (q == 1 ? dzp : (q == 2 ? dnp : dq));
-                        d.D[(size_t)(b0 + r) * d.d_bs + (size_t)t * d.d_ts + q * H + k] = ov;
-                    }
-                }
-                __syncthreads();
-                if (s > 0) {     // the gradient flowing into h_{-1} = h0 is not needed
+                    float2 acc[3] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        float a = 0.f;
+                    for (int g = 0; g < 3; ++g) {
+                        const float4* gv = reinterpret_cast<const float4*>(&dgh[buf][r][g * GP + q * (KS + 4)]);
 #pragma unroll
-                        for (int g = 0; g < 3; ++g) {
-                            const float4* gv = reinterpret_cast<const float4*>(&dgh[buf][r][g * H + q * KS]);
-#pragma unroll
-                            for (int i4 = 0; i4 < KS / 4; ++i4) {
-                                const float4 g4 = gv[i4];
-                                a = fmaf(w[g][4 * i4 + 0], g4.x, a);
-                                a = fmaf(w[g][4 * i4 + 1], g4.y, a);
-                                a = fmaf(w[g][4 * i4 + 2], g4.z, a);
-                                a = fmaf(w[g][4 * i4 + 3], g4.w, a);
-                            }
+                        for (int i4 = 0; i4 < KS / 4; ++i4) {
+                            const float4 g4 = gv[i4];
+                            acc[g] = __ffma2_rn(w2[g][4 * i4 + 0], bcast2(g4.x), acc[g]);
+                            acc[g] = __ffma2_rn(w2[g][4 * i4 + 1], bcast2(g4.y), acc[g]);
+                            acc[g] = __ffma2_rn(w2[g][4 * i4 + 2], bcast2(g4.z), acc[g]);
+                            acc[g] = __ffma2_rn(w2[g][4 * i4 + 3], bcast2(g4.w), acc[g]);
                         }
-                        dh[r] = dhz[r] + quad_sum(a);
                     }
+                    const float ax = (acc[0].x + acc[1].x) + acc[2].x, ay = (acc[0].y + acc[1].y) + acc[2].y;
+                    float t = (own ? ay : ax) + __shfl_xor_sync(0xffffffffu, own ? ax : ay, 1);
+                    t += __shfl_xor_sync(0xffffffffu, t, 2);
+                    dh[r] = dhz[r] + t;
                 }
-                buf ^= 1;
             }
+            buf ^= 1;
         }
     }
 }
 
-template <int H>
-static int gru_fwd_dispatch(const GruFwdParams& prm, int ndirs, cudaStream_t st) {
-    const int B = prm.B;
-    // rows per CTA: keep at most ~2 waves of CTAs on 148 SMs
+static inline int rows_per_cta(int B, int ndirs) {
+    // one row per CTA while all CTAs fit in ~2 waves on 148 SMs; more rows per CTA beyond that
     int R = 1;
     while (R < 4 && (int64_t)cdiv(B, R) * ndirs > 296) R *= 2;
-    dim3 grid(cdiv(B, R), ndirs);
-    if (R == 1) gru_fwd_kernel<H, 1><<<grid, 4 * H, 0, st>>>(prm);
-    else if (R == 2) gru_fwd_kernel<H, 2><<<grid, 4 * H, 0, st>>>(prm);
-    else gru_fwd_kernel<H, 4><<<grid, 4 * H, 0, st>>>(prm);
+    return R;
+}
+
+template <int H>
+static int gru_fwd_dispatch(const GruFwdParams& prm, int ndirs, cudaStream_t st) {
+    const int R = rows_per_cta(prm.B, ndirs);
+    dim3 grid(cdiv(prm.B, R), ndirs);
+    MMS_PROF_BEGIN(st);
+    if (R == 1) gru_fwd_kernel<H, 1><<<grid, 2 * H, 0, st>>>(prm);
+    else if (R == 2) gru_fwd_kernel<H, 2><<<grid, 2 * H, 0, st>>>(prm);
+    else gru_fwd_kernel<H, 4><<<grid, 2 * H, 0, st>>>(prm);
     MMS_LAUNCH_CHECK("gru_fwd_kernel");
     return MMS_OK;
 }
 
 template <int H>
 static int gru_bwd_dispatch(const GruBwdParams& prm, int ndirs, cudaStream_t st) {
-    const int B = prm.B;
-    int R = 1;
-    while (R < 4 && (int64_t)cdiv(B, R) * ndirs > 296) R *= 2;
-    dim3 grid(cdiv(B, R), ndirs);
-    if (R == 1) gru_bwd_kernel<H, 1><<<grid, 4 * H, 0, st>>>(prm);
-    else if (R == 2) gru_bwd_kernel<H, 2><<<grid, 4 * H, 0, st>>>(prm);
-    else gru_bwd_kernel<H, 4><<<grid, 4 * H, 0, st>>>(prm);
+    const int R = rows_per_cta(prm.B, ndirs);
+    dim3 grid(cdiv(prm.B, R), ndirs);
+    MMS_PROF_BEGIN(st);
+    if (R == 1) gru_bwd_kernel<H, 1><<<grid, 2 * H, 0, st>>>(prm);
+    else if (R == 2) gru_bwd_kernel<H, 2><<<grid, 2 * H, 0, st>>>(prm);
+    else gru_bwd_kernel<H, 4><<<grid, 2 * H, 0, st>>>(prm);
     MMS_LAUNCH_CHECK("gru_bwd_kernel");
     return MMS_OK;
 }
@@ -309,7 +389,7 @@ int launch_gru_fwd(const mms_gru_dir_fwd* dirs, int ndirs, int B, int H, float p
     GruFwdParams prm;
     for (int i = 0; i < ndirs; ++i) {
         prm.dir[i] = dirs[i];
-        MMS_REQUIRE(dirs[i].gi && dirs[i].w_hh && dirs[i].b_hh && dirs[i].hs && dirs[i].nsteps >= 0, "gru_recur_fwd: null pointer");
+        MMS_REQUIRE(dirs[i].gi && dirs[i].w_hh && dirs[i].b_hh && dirs[i].hs && dirs[i].nsteps >= 1, "gru_recur_fwd: null pointer / no steps");
     }
     for (int i = ndirs; i < GRU_MAX_DIRS; ++i) prm.dir[i] = dirs[0];
     prm.B = B; prm.p = p; prm.seed = seed; prm.offset = offset; prm.offset_dev = offset_dev;
@@ -323,7 +403,7 @@ int launch_gru_bwd(const mms_gru_dir_bwd* dirs, int ndirs, int B, int H, float p
     GruBwdParams prm;
     for (int i = 0; i < ndirs; ++i) {
         prm.dir[i] = dirs[i];
-        MMS_REQUIRE(dirs[i].w_hh && dirs[i].stash && dirs[i].hs && dirs[i].D && dirs[i].nsteps >= 0, "gru_recur_bwd: null pointer");
+        MMS_REQUIRE(dirs[i].w_hh && dirs[i].stash && dirs[i].hs && dirs[i].D && dirs[i].nsteps >= 1, "gru_recur_bwd: null pointer / no steps");
         MMS_REQUIRE(!dirs[i].dh_head || dirs[i].w0, "gru_recur_bwd: dh_head needs w0");
     }
     for (int i = ndirs; i < GRU_MAX_DIRS; ++i) prm.dir[i] = dirs[0];

@@ -175,6 +175,7 @@ int launch_head_fwd2(const float* src_a, int64_t lda, const float* src_b, int64_
                      const float* w3, const float* b3, int B, int H2, int nc, float p, uint64_t seed, uint64_t offset,
                      const int64_t* offset_dev, float* last_out, float* hid_out, float* logits, cudaStream_t st) {
     MMS_REQUIRE(nc >= 1 && nc <= MAX_NC, "head: num_classes %d outside [1,%d]", nc, MAX_NC);
+    MMS_PROF_BEGIN(st);
     head_fwd_kernel<<<B, HEAD_HID, H2 * sizeof(float), st>>>(src_a, lda, src_b, ldb, Hh, w0, b0, w3, b3, H2, nc, p, seed, offset,
                                                              offset_dev, last_out, hid_out, logits);
     MMS_LAUNCH_CHECK("head_fwd_kernel");
@@ -193,6 +194,7 @@ int launch_head_bwd(const float* last, const float* hid, const float* dlogits, c
                     float* db3, cudaStream_t st) {
     MMS_REQUIRE(nc >= 1 && nc <= MAX_NC, "head: num_classes %d outside [1,%d]", nc, MAX_NC);
     MMS_REQUIRE(B * sizeof(float) <= 40 * 1024, "head_bwd: batch %d too large for one CTA's shared memory", B);
+    MMS_PROF_BEGIN(st);
     head_bwd_kernel<<<HEAD_HID, 128, B * sizeof(float), st>>>(last, hid, dlogits, w3, B, H2, nc, p, seed, offset, offset_dev, dhid,
                                                               dw0, db0, dw3, db3);
     MMS_LAUNCH_CHECK("head_bwd_kernel");
@@ -202,6 +204,7 @@ int launch_head_bwd(const float* last, const float* hid, const float* dlogits, c
 int launch_cross_entropy(const float* logits, const int64_t* labels, int B, int nc, float* loss_out, float* dlogits,
                          double* loss_sum_accum, cudaStream_t st) {
     MMS_REQUIRE(nc >= 1 && nc <= MAX_NC, "cross_entropy: num_classes %d outside [1,%d]", nc, MAX_NC);
+    MMS_PROF_BEGIN(st);
     cross_entropy_kernel<<<1, 256, 0, st>>>(logits, labels, B, nc, loss_out, dlogits, loss_sum_accum);
     MMS_LAUNCH_CHECK("cross_entropy_kernel");
     return MMS_OK;
@@ -210,6 +213,7 @@ int launch_cross_entropy(const float* logits, const int64_t* labels, int B, int 
 int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, const float* lr_dev, float beta1, float beta2,
                 float eps, float wd, int64_t* step_dev, int32_t* scratch, cudaStream_t st) {
     const int blocks = (int)((n + 255) / 256 < 592 ? (n + 255) / 256 : 592);
+    MMS_PROF_BEGIN(st);
     adam_flat_kernel<<<blocks > 0 ? blocks : 1, 256, 0, st>>>(p, g, m, v, n, lr_dev, beta1, beta2, eps, wd, step_dev, scratch);
     MMS_LAUNCH_CHECK("adam_flat_kernel");
     return MMS_OK;

@@ -18,10 +18,19 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
         if (_e != cudaSuccess) return ::mms::cuda_fail(_e, #call, __FILE__, __LINE__); \
     } while (0)
 
+// Launch bookkeeping: every kernel launch is preceded by MMS_PROF_BEGIN(stream) and followed by
+// MMS_LAUNCH_CHECK(name).  Both are a counter increment unless mms_profile_enable(1) was called, in
+// which case the launch is bracketed by CUDA events on its stream (bench.py's live kernel times).
+void prof_begin(cudaStream_t st);
+void prof_end(const char* name);
+
+#define MMS_PROF_BEGIN(st) ::mms::prof_begin(st)
+
 #define MMS_LAUNCH_CHECK(name)                                                      \
     do {                                                                            \
         cudaError_t _e = cudaPeekAtLastError();                                     \
         if (_e != cudaSuccess) return ::mms::cuda_fail(_e, name, __FILE__, __LINE__);  \
+        ::mms::prof_end(name);                                                      \
     } while (0)
 
 #define MMS_REQUIRE(cond, ...)                                                      \

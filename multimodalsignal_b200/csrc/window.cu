@@ -111,9 +111,11 @@ extern "C" int mms_window_gather(const double* const* streams, int32_t n_ch, int
     cudaStream_t st = (cudaStream_t)stream;
     if (out_f32) {
         dim3 grid(cdiv(win, 1024), n_ch, n_win);
+        MMS_PROF_BEGIN(st);
         window_gather_f32_kernel<<<grid, 256, 0, st>>>(sp, n_ch, stream_len, starts, win, shift, scale, log_flag, (float*)out);
     } else {
         dim3 grid(cdiv(win, 128), n_win);
+        MMS_PROF_BEGIN(st);
         window_gather_f64_kernel<<<grid, 256, (size_t)128 * n_ch * sizeof(double), st>>>(sp, n_ch, stream_len, starts, win, (double*)out);
     }
     MMS_LAUNCH_CHECK("window_gather");
@@ -128,6 +130,7 @@ extern "C" int mms_window_stats(const double* const* streams, int32_t n_ch, int6
     int rc = fill_ptrs(streams, n_ch, &sp);
     if (rc) return rc;
     dim3 grid(cdiv(win, 1024), n_ch, n_win);
+    MMS_PROF_BEGIN((cudaStream_t)stream);
     window_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(sp, n_ch, stream_len, starts, win, log_flag, sums);
     MMS_LAUNCH_CHECK("window_stats_kernel");
     return MMS_OK;

@@ -105,3 +105,24 @@ def test_degenerate_attention_gate_is_half():
     x = torch.from_numpy(z["x"])
     _, gate, _ = mo.channel_attention(x, sd["channel_attention.fc.0.weight"], sd["channel_attention.fc.2.weight"])
     assert torch.all(gate == 0.5)
+
+
+@pytest.mark.parametrize("case", MODEL_CASES)
+def test_cpu_port_matches_reference(case):
+    """oracle/cpu_port.py (the CPU baseline bench.py times) against the reference fixtures."""
+    from oracle import cpu_port
+    z, meta = load_golden(f"model_{case}.npz")
+    sd = golden_state(z, "sd")
+    p = {k: v.clone().requires_grad_(v.numel() > 0) for k, v in sd.items() if "running" not in k and "num_batches" not in k}
+    bufs = {k: v.clone() for k, v in sd.items() if "running" in k}
+    x, y = torch.from_numpy(z["x"]), torch.from_numpy(z["y"])
+    logits = cpu_port.forward(p, bufs, x, training=True, dropout=0.0, layers=_layers(meta))
+    np.testing.assert_allclose(logits.detach().numpy(), z["train_logits"], atol=2e-5, rtol=1e-4)
+    loss = torch.nn.functional.cross_entropy(logits, y)
+    loss.backward()
+    for k, v in p.items():
+        if v.numel():
+            ref = z[f"grad/{k}"]
+            assert np.abs(v.grad.numpy() - ref).max() <= 2e-4 * max(1e-6, np.abs(ref).max()) + 1e-7, k
+    for k, v in bufs.items():
+        np.testing.assert_allclose(v.numpy(), z[f"sd_after_fwd/{k}"], atol=1e-6, rtol=1e-5)
