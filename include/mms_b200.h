@@ -189,17 +189,22 @@ int mms_gemm_tn_acc(const float* A, int64_t lda, int32_t a_split, int32_t a_skip
                     int32_t shift, int32_t seq, float* C, int64_t ldc, float* bias_grad,
                     int32_t M, int32_t N1, int32_t N2, mms_stream_t stream);
 
+/* models.py:62 inter-layer GRU dropout as a streaming pass: out[i] = in[i] * m(base_id + i) with
+ * m in {0, 1/(1-p)} drawn from the counter-based stream (seed, offset, element id); in == out is
+ * allowed.  Forward and backward call it with the same ids, so they see the same mask. */
+int mms_dropout_apply(const float* in, float* out, int64_t n, int64_t base_id, float dropout_p,
+                      uint64_t rng_seed, uint64_t rng_offset, const int64_t* rng_offset_dev, mms_stream_t stream);
+
 /* The GRU recurrence of one direction (models.py:56-63; gate order r,z,n; h0 = 0).
  * gi[(b*gi_bs + t*gi_ts) + 0..3H) are the input projections (incl. b_ih).  Runs `nsteps` steps
- * starting at t0 and moving by dt (+1 forward, -1 reverse).  Writes h to hs[b*hs_bs + t*hs_ts + j],
- * optionally a dropped copy to hs_drop (same indexing; element id for the RNG is
- * drop_base + b*hs_bs + t*hs_ts + j), and, if stash != NULL, (r,z,n,W_hn h + b_hn) to
+ * starting at t0 and moving by dt (+1 forward, -1 reverse).  Writes h to hs[b*hs_bs + t*hs_ts + j]
+ * and, if stash != NULL, (r,z,n,W_hn h + b_hn) to
  * stash[(b*st_bs + t*st_ts) + 0..4H). */
 typedef struct {
     const float* gi; int64_t gi_bs, gi_ts;
     const float* w_hh; const float* b_hh;
     float* hs; int64_t hs_bs, hs_ts;
-    float* hs_drop; int64_t drop_base;
+    float* hs_drop; int64_t drop_base;   /* reserved, must be NULL / 0: use mms_dropout_apply */
     float* stash; int64_t st_bs, st_ts;
     int32_t t0, dt, nsteps;
 } mms_gru_dir_fwd;
@@ -210,8 +215,7 @@ int mms_gru_recur_fwd(const mms_gru_dir_fwd* dirs_host, int32_t ndirs, int32_t B
 /* Reverse-time pass of one direction.  dout (optional) is the gradient w.r.t. the emitted h,
  * indexed like hs; dout_last [B, dl_ld] (optional) is added at the forward-order LAST step
  * only; dh_head/W0 (optional): initial dh[b,k] += sum_i dh_head[b*64+i] * w0[i*w0_ld + w0_col + k].
- * If drop_mask != 0 the incoming dout is multiplied by the same dropout multiplier the forward
- * applied to hs_drop.  Writes D[(b*d_bs + t*d_ts) + 0..4H) = (d r_pre, d z_pre, d n_pre, d q). */
+ * drop_base / drop_mask are reserved and must be 0 (apply mms_dropout_apply to dout first).  Writes D[(b*d_bs + t*d_ts) + 0..4H) = (d r_pre, d z_pre, d n_pre, d q). */
 typedef struct {
     const float* w_hh;
     const float* stash; int64_t st_bs, st_ts;

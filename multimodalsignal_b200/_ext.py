@@ -86,6 +86,7 @@ _SIGNATURES = {
     "mms_gemm_nt_bias": (c_i32, [P, c_i64, P, c_i64, P, P, c_i64, c_i32, c_i32, c_i32, P]),
     "mms_gemm_nn": (c_i32, [P, c_i64, P, c_i64, P, c_i64, c_i32, c_i32, c_i32, c_i32, P]),
     "mms_gemm_tn_acc": (c_i32, [P, c_i64, c_i32, c_i32, P, c_i64, c_i32, c_i32, P, c_i64, P, c_i32, c_i32, c_i32, P]),
+    "mms_dropout_apply": (c_i32, [P, P, c_i64, c_i64, c_f32, c_u64, c_u64, P, P]),
     "mms_gru_recur_fwd": (c_i32, [C.POINTER(GruDirFwd), c_i32, c_i32, c_i32, c_f32, c_u64, c_u64, P, P]),
     "mms_gru_recur_bwd": (c_i32, [C.POINTER(GruDirBwd), c_i32, c_i32, c_i32, c_f32, c_u64, c_u64, P, P]),
     "mms_head_fwd": (c_i32, [P, P, P, P, P, c_i32, c_i32, c_i32, c_f32, c_u64, c_u64, P, P, P, P]),

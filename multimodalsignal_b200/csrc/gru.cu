@@ -18,7 +18,9 @@
 //     step needs from global memory (input projections, stashed gates, upstream gradients) is
 //     prefetched PF steps ahead into registers;
 //   * sigmoid / tanh use the ex2 / rcp special-function units (|error| ~ 2e-7, far inside the
-//     1e-4 logit tolerance).
+//     1e-4 logit tolerance);
+//   * inter-layer dropout is NOT applied here: a 30-instruction hash per element inside an in-order
+//     step loop costs more than a separate streaming pass (mms_dropout_apply) over the layer output.
 // All arithmetic is fp32 (SURVEY §7 hard part 2).
 #include "mms_common.cuh"
 
@@ -43,7 +45,9 @@ struct GruBwdParams {
 };
 
 // sigmoid / tanh on the special-function units: ex2.approx + rcp.approx (2 MUFU ops each).
-__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_sigmoid(float x) { return rcp_ftz(1.f + ex2_ftz(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float fast_tanh(float x) { return fmaf(2.f, fast_sigmoid(2.f * x), -1.f); }
 
 __device__ __forceinline__ float2 bcast2(float v) { return make_float2(v, v); }
@@ -81,27 +85,23 @@ __global__ void __launch_bounds__(2 * H) gru_fwd_kernel(const GruFwdParams prm) 
 
     for (int i = tid; i < 2 * R * HPAD; i += 2 * H) (&hsm[0][0][0])[i] = 0.f;
 
-    DropRng rng;
-    const bool do_drop = d.hs_drop != nullptr;
-    if (do_drop) rng.init(prm.seed, resolve_offset(prm.offset, prm.offset_dev), prm.p);
     const bool do_stash = d.stash != nullptr;
 
     // running pointers (advance by dt * stride per step); loads clamp the row, stores are guarded
     const int64_t gi_step = (int64_t)d.dt * d.gi_ts, hs_step = (int64_t)d.dt * d.hs_ts, st_step = (int64_t)d.dt * d.st_ts;
     const float* gi_p[R];
     float* hs_p[R];
-    float* st_p[R];
-    int64_t he[R];          // element index of hs (dropout id / hs_drop offset)
+    float* st_p[R];         // first lane: stash slots 0,1 (r, z); second lane: slots 2,3 (n, W_hn h + b_hn)
     bool live[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const int bb = min(b0 + r, B - 1);
         live[r] = (b0 + r) < B;
         gi_p[r] = d.gi + (int64_t)bb * d.gi_bs + (int64_t)d.t0 * d.gi_ts + ju;
-        he[r] = (int64_t)bb * d.hs_bs + (int64_t)d.t0 * d.hs_ts + ju;
-        hs_p[r] = d.hs + he[r];
-        st_p[r] = do_stash ? d.stash + (int64_t)bb * d.st_bs + (int64_t)d.t0 * d.st_ts + ju : nullptr;
+        hs_p[r] = d.hs + (int64_t)bb * d.hs_bs + (int64_t)d.t0 * d.hs_ts + ju;
+        st_p[r] = do_stash ? d.stash + (int64_t)bb * d.st_bs + (int64_t)d.t0 * d.st_ts + (first ? 0 : 2 * H) + ju : nullptr;
     }
+    float* const h_wr = &hsm[0][0][0] + padded<KS>(ju);      // + (buffer * R + r) * HPAD
 
     // ring of input projections (r, z, n of unit ju), PF steps ahead
     float ring[PF][R][3];
@@ -164,19 +164,14 @@ __global__ void __launch_bounds__(2 * H) gru_fwd_kernel(const GruFwdParams prm) 
                 const float rg = fast_sigmoid(sg[0] + gi[r][0]);
                 const float zg = fast_sigmoid(sg[1] + gi[r][1]);
                 const float ng = fast_tanh(fmaf(rg, sg[2], gi[r][2]));
-                const float hp = hsm[cur][r][padded<KS>(ju)];
+                const float hp = h_wr[(cur * R + r) * HPAD];
                 const float hn = fmaf(zg, hp - ng, ng);                        // (1-z)*n + z*h
-                if (first) hsm[cur ^ 1][r][padded<KS>(ju)] = hn;
-                if (live[r]) {
-                    if (first) {
-                        *hs_p[r] = hn;
-                        if (do_stash) { st_p[r][0] = rg; st_p[r][H] = zg; }
-                    } else {
-                        if (do_stash) { st_p[r][2 * H] = ng; st_p[r][3 * H] = sg[2]; }
-                        if (do_drop) d.hs_drop[he[r]] = hn * rng.mult((uint64_t)(d.drop_base + he[r]));
-                    }
+                if (first) h_wr[((cur ^ 1) * R + r) * HPAD] = hn;
+                if (first && live[r]) *hs_p[r] = hn;
+                if (do_stash && live[r]) {                                     // uniform, predicated stores
+                    st_p[r][0] = first ? rg : ng;
+                    st_p[r][H] = first ? zg : sg[2];
                 }
-                he[r] += hs_step;
                 hs_p[r] += hs_step;
                 st_p[r] += st_step;
             }
@@ -210,10 +205,7 @@ __global__ void __launch_bounds__(2 * H) gru_bwd_kernel(const GruBwdParams prm) 
             w2[g][i] = make_float2(__ldg(d.w_hh + (size_t)(g * H + q * KS + i) * H + p),
                                    __ldg(d.w_hh + (size_t)(g * H + q * KS + i) * H + p + HP));
 
-    DropRng rng;
     const bool has_dout = d.dout != nullptr;
-    const bool do_mask = d.drop_mask != 0 && has_dout;
-    if (do_mask) rng.init(prm.seed, resolve_offset(prm.offset, prm.offset_dev), prm.p);
 
     // The visit order is the reverse of the forward order: forward step s = nsteps-1 ... 0 at time
     // t = t0 + s*dt.  Running pointers start at the last forward step and move by -dt * stride.
@@ -223,7 +215,6 @@ __global__ void __launch_bounds__(2 * H) gru_bwd_kernel(const GruBwdParams prm) 
     const float* st_p[R];     // prefetch side (PF visits ahead)
     const float* hp_p[R];     // h_{prev} of the prefetched step
     const float* do_p[R];
-    int64_t doe[R];           // element index into dout (dropout id)
     float* D_p[R];            // store side (current visit)
     float dh[R];
     float dlast[R];
@@ -234,8 +225,7 @@ __global__ void __launch_bounds__(2 * H) gru_bwd_kernel(const GruBwdParams prm) 
         live[r] = (b0 + r) < B;
         st_p[r] = d.stash + (int64_t)bb * d.st_bs + (int64_t)t_last * d.st_ts + ku;
         hp_p[r] = d.hs + (int64_t)bb * d.hs_bs + (int64_t)(t_last - d.dt) * d.hs_ts + ku;   // only read when s > 0
-        doe[r] = (int64_t)bb * d.do_bs + (int64_t)t_last * d.do_ts + ku;
-        do_p[r] = has_dout ? d.dout + doe[r] : nullptr;
+        do_p[r] = has_dout ? d.dout + (int64_t)bb * d.do_bs + (int64_t)t_last * d.do_ts + ku : nullptr;
         D_p[r] = d.D + (int64_t)bb * d.d_bs + (int64_t)t_last * d.d_ts + (first ? 0 : 2 * H) + ku;
         dlast[r] = d.dout_last ? __ldg(d.dout_last + (int64_t)bb * d.dl_ld + ku) : 0.f;
         // initial recurrent gradient: optional projection of the head gradient (dlast = dhid @ W0)
@@ -246,6 +236,8 @@ __global__ void __launch_bounds__(2 * H) gru_bwd_kernel(const GruBwdParams prm) 
         }
         dh[r] = s;
     }
+
+    float* const g_wr = &dgh[0][0][0] + padded<KS>(ku);     // + (buffer * R + r) * 3 * GP
 
     // ring of per-step inputs for column ku: stash (r,z,n,qq), h_prev, dout
     struct StepIn { float r, z, n, qq, hp, dout; };
@@ -259,12 +251,7 @@ __global__ void __launch_bounds__(2 * H) gru_bwd_kernel(const GruBwdParams prm) 
         v.n = __ldg(sp + 2 * H);
         v.qq = __ldg(sp + 3 * H);
         v.hp = fetch_s > 0 ? __ldg(hp_p[r]) : 0.f;
-        float g = 0.f;
-        if (has_dout) {
-            g = __ldg(do_p[r]);
-            if (do_mask) g *= rng.mult((uint64_t)(d.drop_base + doe[r]));
-        }
-        v.dout = g;
+        v.dout = has_dout ? __ldg(do_p[r]) : 0.f;
         return v;
     };
     auto advance = [&]() {            // move the prefetch pointers one visit further (if any step is left)
@@ -273,7 +260,7 @@ __global__ void __launch_bounds__(2 * H) gru_bwd_kernel(const GruBwdParams prm) 
             for (int r = 0; r < R; ++r) {
                 st_p[r] += st_step;
                 hp_p[r] += hs_step;
-                if (has_dout) { do_p[r] += do_step; doe[r] += do_step; }
+                if (has_dout) do_p[r] += do_step;
             }
         }
         --fetch_s;
@@ -314,7 +301,7 @@ __global__ void __launch_bounds__(2 * H) gru_bwd_kernel(const GruBwdParams prm) 
                 const float drp = dr * x.r * (1.f - x.r);
                 dhz[r] = dht * x.z;
                 if (first) {
-                    float* g = &dgh[buf][r][padded<KS>(ku)];
+                    float* g = g_wr + (buf * R + r) * 3 * GP;
                     g[0] = drp; g[GP] = dzp; g[2 * GP] = dq;
                 }
                 if (live[r]) {          // D = (d r_pre, d z_pre, d n_pre, d q): first lane stores 0,1; second 2,3
@@ -390,6 +377,7 @@ int launch_gru_fwd(const mms_gru_dir_fwd* dirs, int ndirs, int B, int H, float p
     for (int i = 0; i < ndirs; ++i) {
         prm.dir[i] = dirs[i];
         MMS_REQUIRE(dirs[i].gi && dirs[i].w_hh && dirs[i].b_hh && dirs[i].hs && dirs[i].nsteps >= 1, "gru_recur_fwd: null pointer / no steps");
+        MMS_REQUIRE(!dirs[i].hs_drop, "gru_recur_fwd: hs_drop is no longer written by the recurrence; use mms_dropout_apply");
     }
     for (int i = ndirs; i < GRU_MAX_DIRS; ++i) prm.dir[i] = dirs[0];
     prm.B = B; prm.p = p; prm.seed = seed; prm.offset = offset; prm.offset_dev = offset_dev;
@@ -405,6 +393,7 @@ int launch_gru_bwd(const mms_gru_dir_bwd* dirs, int ndirs, int B, int H, float p
         prm.dir[i] = dirs[i];
         MMS_REQUIRE(dirs[i].w_hh && dirs[i].stash && dirs[i].hs && dirs[i].D && dirs[i].nsteps >= 1, "gru_recur_bwd: null pointer / no steps");
         MMS_REQUIRE(!dirs[i].dh_head || dirs[i].w0, "gru_recur_bwd: dh_head needs w0");
+        MMS_REQUIRE(!dirs[i].drop_mask, "gru_recur_bwd: drop_mask is no longer applied by the recurrence; use mms_dropout_apply");
     }
     for (int i = ndirs; i < GRU_MAX_DIRS; ++i) prm.dir[i] = dirs[0];
     prm.B = B; prm.p = p; prm.seed = seed; prm.offset = offset; prm.offset_dev = offset_dev;

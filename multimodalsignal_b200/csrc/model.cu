@@ -32,6 +32,7 @@ int launch_cross_entropy(const float*, const int64_t*, int, int, float*, float*,
 int launch_adam(float*, const float*, float*, float*, int64_t, const float*, float, float, float, float, int64_t*, int32_t*,
                 cudaStream_t);
 int launch_chan_dx(const float*, const float*, const float*, int, int, int, float*, cudaStream_t);
+int launch_dropout_apply(const float*, float*, int64_t, int64_t, float, uint64_t, uint64_t, const int64_t*, cudaStream_t);
 
 constexpr int MAX_LAYERS = 8;
 constexpr int64_t DROP_LAYER_STRIDE = 1ll << 40;
@@ -224,14 +225,17 @@ static int model_forward(const mms_cnngru_desc* d, const float* x, const float* 
             g.w_hh = P + po.w_hh[l] + (int64_t)dd * 3 * H * H;
             g.b_hh = P + po.b_hh[l] + dd * 3 * H;
             g.hs = w.hs[l] + dd * H; g.hs_bs = (int64_t)L * 2 * H; g.hs_ts = 2 * H;
-            g.hs_drop = m.drop_gru ? w.outd[l] + dd * H : nullptr;
-            g.drop_base = (int64_t)l * DROP_LAYER_STRIDE + dd * H;
             g.stash = m.need_grad ? w.stash[l] + (int64_t)dd * M * 4 * H : nullptr;
             g.st_bs = (int64_t)L * 4 * H; g.st_ts = 4 * H;
             g.t0 = dd ? L - 1 : 0; g.dt = dd ? -1 : 1; g.nsteps = L;
         }
         rc = launch_gru_fwd(dirs, 2, B, H, m.p, d->rng_seed, d->rng_offset, d->rng_offset_dev, st);
         if (rc) return rc;
+        if (m.drop_gru) {      // models.py:62: dropout on the outputs of every layer but the last
+            rc = launch_dropout_apply(w.hs[l], w.outd[l], M * 2 * H, (int64_t)l * DROP_LAYER_STRIDE, m.p, d->rng_seed,
+                                      d->rng_offset, d->rng_offset_dev, st);
+            if (rc) return rc;
+        }
         in = w.outd[l];
         I = 2 * H;
     }
@@ -326,6 +330,11 @@ static int model_backward(const mms_cnngru_desc* d, const float* x, const float*
     for (int l = top - 1; l >= 0; --l) {
         const float* in_l = l == 0 ? w.seq : w.outd[l - 1];
         const int I_l = l == 0 ? m.O : 2 * H;
+        if (m.drop_gru) {      // gradient through the dropout between layer l and l + 1 (same multipliers)
+            rc = launch_dropout_apply(dxcur, dxcur, (int64_t)M * 2 * H, (int64_t)l * DROP_LAYER_STRIDE, p, d->rng_seed,
+                                      d->rng_offset, d->rng_offset_dev, st);
+            if (rc) return rc;
+        }
         mms_gru_dir_bwd dirs[2];
         memset(dirs, 0, sizeof(dirs));
         for (int dd = 0; dd < 2; ++dd) {
@@ -334,8 +343,6 @@ static int model_backward(const mms_cnngru_desc* d, const float* x, const float*
             g.stash = w.stash[l] + (int64_t)dd * M * 4 * H; g.st_bs = (int64_t)L * 4 * H; g.st_ts = 4 * H;
             g.hs = w.hs[l] + dd * H; g.hs_bs = (int64_t)L * 2 * H; g.hs_ts = 2 * H;
             g.dout = dxcur + dd * H; g.do_bs = (int64_t)L * 2 * H; g.do_ts = 2 * H;
-            g.drop_base = (int64_t)l * DROP_LAYER_STRIDE + dd * H;
-            g.drop_mask = m.drop_gru ? 1 : 0;
             g.D = w.D[l] + dd * 4 * H; g.d_bs = (int64_t)L * 8 * H; g.d_ts = 8 * H;
             g.t0 = dd ? L - 1 : 0; g.dt = dd ? -1 : 1; g.nsteps = L;
         }

@@ -411,3 +411,20 @@ def test_window_gather_and_stats(lib):
     want = ((refx - mean) / std).astype(np.float32).transpose(0, 2, 1)
     np.testing.assert_allclose(outf.cpu().numpy(), want, atol=2e-6)
     assert cnt == len(starts_np) * win
+
+
+def test_dropout_apply_same_mask_forward_and_backward(lib):
+    n, p = 100003, 0.5
+    x = torch.randn(n, device="cuda")
+    y = torch.empty_like(x)
+    ok(lib.mms_dropout_apply(P(x), P(y), n, 12345, p, 7, 3, None, ST()))
+    m = y / x
+    kept = (m.abs() > 0).float().mean().item()
+    assert 0.48 < kept < 0.52
+    assert torch.allclose(m[m.abs() > 0], torch.full_like(m[m.abs() > 0], 2.0), atol=1e-5)
+    g = torch.ones(n, device="cuda")
+    ok(lib.mms_dropout_apply(P(g), P(g), n, 12345, p, 7, 3, None, ST()))          # in place, same ids
+    assert torch.equal(g > 0, y != 0)
+    g2 = torch.ones(n, device="cuda")
+    ok(lib.mms_dropout_apply(P(g2), P(g2), n, 12345, p, 7, 4, None, ST()))        # next step: different mask
+    assert not torch.equal(g2 > 0, g > 0)
