@@ -1,9 +1,376 @@
-// FFT resampling (reference preprocess.py:70-75 -> scipy.signal.resample).  Placeholder for the
-// first bring-up run; replaced by the Bluestein/stockham implementation.
+// FFT resampling with scipy.signal.resample semantics (reference preprocess.py:70-75; algorithm of
+// scipy/signal/_signaltools.py for real input, no window):
+//     X = rfft(x);  keep the m2 = min(N, num)//2 + 1 lowest bins;  fix the unpaired bin when
+//     min(N, num) is even and num != N;  y = irfft(X * num/N, n = num).
+// Recording lengths are arbitrary (N ~ 4.2e6 with large prime factors), so both transforms are
+// evaluated as chirp-z transforms (Bluestein): a length-P DFT restricted to the bins that are
+// actually needed becomes a circular convolution of power-of-two length M, done with radix-2^k
+// passes through shared memory in float64.
+//   stage A:  X[k] = sum_n x[n] e^{-2 pi i nk/N},           k < m2   (only the kept bins)
+//   stage C:  y[j] = Re sum_k G[k] e^{+2 pi i jk/num} / num,  j < num  (one-sided Hermitian sum)
+// The forward passes leave the spectrum in digit-reversed order and the inverse passes undo exactly
+// that permutation, so no reordering pass exists: the point-wise product with the (identically
+// permuted) chirp-filter spectrum happens in the permuted domain.
+// HBM-bound: every pass streams the M complex values once (32*M bytes of traffic).
 #include "mms_common.cuh"
+
+namespace mms {
+
+constexpr int FFT_TC = 16;          // tile columns
+constexpr int FFT_THREADS = 256;
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+    return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
+}
+
+// e^{sign * pi * i * (n^2 mod 2P) / P}
+__device__ __forceinline__ double2 chirp(int64_t n, int64_t P, int sign) {
+    const uint64_t e = ((uint64_t)n * (uint64_t)n) % (uint64_t)(2 * P);
+    double s, c;
+    sincospi((double)e / (double)P, &s, &c);
+    return make_double2(c, sign > 0 ? s : -s);
+}
+
+__device__ __forceinline__ int bitrev(int v, int bits) { return bits ? (int)(__brev((unsigned)v) >> (32 - bits)) : 0; }
+
+// One radix-R pass over blocks of size Mc = R*S.  Forward (DIF): R-point butterflies over the
+// strided index, then the twiddle w_Mc^{r*k1}.  Inverse (DIT): conjugate twiddle first, then the
+// butterflies in reverse stage order -- the exact inverse of the forward pass (up to the factor R).
+template <int R>
+__global__ void __launch_bounds__(FFT_THREADS) fft_pass_kernel(double2* __restrict__ a, int64_t sig_stride, int64_t Mc, int tc,
+                                                               int inverse) {
+    constexpr int LOGR = R == 256 ? 8 : R == 128 ? 7 : R == 64 ? 6 : R == 32 ? 5 : R == 16 ? 4 : R == 8 ? 3 : R == 4 ? 2 : 1;
+    constexpr int LD = FFT_TC + 1;
+    extern __shared__ __align__(16) double2 fsm[];
+    double2* tile = fsm;                 // [R][LD]
+    double2* tw = fsm + R * LD;          // [R/2]  w_R^j (conjugated for the inverse)
+    const int tid = threadIdx.x;
+    const int64_t S = Mc / R;
+    double2* base = a + (int64_t)blockIdx.y * sig_stride;
+    const int64_t g0 = (int64_t)blockIdx.x * tc;          // first (block, r) column of this tile
+    const double tsign = inverse ? 1.0 : -1.0;
+
+    for (int j = tid; j < R / 2; j += FFT_THREADS) {
+        double s, c;
+        sincospi(2.0 * (double)j / (double)R, &s, &c);
+        tw[j] = make_double2(c, tsign * s);
+    }
+    const bool rowwise = S >= tc;
+    const int64_t blk0 = g0 / S, r0 = g0 % S;
+    double2* region = base + blk0 * Mc;                    // contiguous tc*R elements when !rowwise
+    const int total = R * tc;
+
+    auto twiddle = [&](int qrow, int64_t r) {
+        const int k1 = bitrev(qrow, LOGR);
+        const uint64_t e = ((uint64_t)r * (uint64_t)k1) & (uint64_t)(Mc - 1);
+        double s, c;
+        sincospi(2.0 * (double)e / (double)Mc, &s, &c);
+        return make_double2(c, tsign * s);
+    };
+
+    for (int idx = tid; idx < total; idx += FFT_THREADS) {
+        int q, c;
+        int64_t r;
+        double2 v;
+        if (rowwise) {
+            q = idx / tc; c = idx - q * tc; r = r0 + c;
+            v = base[blk0 * Mc + (int64_t)q * S + r];
+        } else {
+            const int64_t blk = idx / Mc, within = idx - blk * Mc;
+            q = (int)(within / S); r = within - (int64_t)q * S; c = (int)(blk * S + r);
+            v = region[idx];
+        }
+        if (inverse && S > 1) v = cmul(v, twiddle(q, r));
+        tile[q * LD + c] = v;
+    }
+    __syncthreads();
+
+    const int nbf = (R / 2) * tc;
+    if (!inverse) {
+#pragma unroll 1
+        for (int h = R / 2; h >= 1; h >>= 1) {
+            const int tstep = R / (2 * h);
+            for (int bf = tid; bf < nbf; bf += FFT_THREADS) {
+                const int c = bf % tc, pair = bf / tc, grp = pair / h, j = pair - grp * h;
+                const int q0 = grp * 2 * h + j, q1 = q0 + h;
+                const double2 x0 = tile[q0 * LD + c], x1 = tile[q1 * LD + c];
+                tile[q0 * LD + c] = make_double2(x0.x + x1.x, x0.y + x1.y);
+                tile[q1 * LD + c] = cmul(make_double2(x0.x - x1.x, x0.y - x1.y), tw[j * tstep]);
+            }
+            __syncthreads();
+        }
+    } else {
+#pragma unroll 1
+        for (int h = 1; h <= R / 2; h <<= 1) {
+            const int tstep = R / (2 * h);
+            for (int bf = tid; bf < nbf; bf += FFT_THREADS) {
+                const int c = bf % tc, pair = bf / tc, grp = pair / h, j = pair - grp * h;
+                const int q0 = grp * 2 * h + j, q1 = q0 + h;
+                const double2 u0 = tile[q0 * LD + c];
+                const double2 t = cmul(tile[q1 * LD + c], tw[j * tstep]);
+                tile[q0 * LD + c] = make_double2(u0.x + t.x, u0.y + t.y);
+                tile[q1 * LD + c] = make_double2(u0.x - t.x, u0.y - t.y);
+            }
+            __syncthreads();
+        }
+    }
+
+    for (int idx = tid; idx < total; idx += FFT_THREADS) {
+        int q, c;
+        int64_t r;
+        double2* dst;
+        if (rowwise) {
+            q = idx / tc; c = idx - q * tc; r = r0 + c;
+            dst = base + blk0 * Mc + (int64_t)q * S + r;
+        } else {
+            const int64_t blk = idx / Mc, within = idx - blk * Mc;
+            q = (int)(within / S); r = within - (int64_t)q * S; c = (int)(blk * S + r);
+            dst = region + idx;
+        }
+        double2 v = tile[q * LD + c];
+        if (!inverse && S > 1) v = cmul(v, twiddle(q, r));
+        *dst = v;
+    }
+}
+
+// a[sig][n] = x[sig][n] * chirp(n, P, sign) for n < n_in, zero up to M
+__global__ void __launch_bounds__(256) czt_pre_real_kernel(const double* __restrict__ x, int64_t n_in, int64_t P, int sign,
+                                                           double2* __restrict__ a, int64_t M) {
+    const double* xs = x + (int64_t)blockIdx.y * n_in;
+    double2* as = a + (int64_t)blockIdx.y * M;
+    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < M; n += (int64_t)gridDim.x * blockDim.x) {
+        double2 v = make_double2(0.0, 0.0);
+        if (n < n_in) {
+            const double2 c = chirp(n, P, sign);
+            const double xv = xs[n];
+            v = make_double2(xv * c.x, xv * c.y);
+        }
+        as[n] = v;
+    }
+}
+
+// Chirp filter b[j mod M] = conj(chirp(j, P, sign)) for j in (-n_in, n_out), zero elsewhere.
+__global__ void __launch_bounds__(256) czt_filter_kernel(double2* __restrict__ b, int64_t M, int64_t n_in, int64_t n_out,
+                                                         int64_t P, int sign) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (int64_t)gridDim.x * blockDim.x) {
+        double2 v = make_double2(0.0, 0.0);
+        if (i < n_out) v = chirp(i, P, -sign);
+        else if (M - i < n_in) v = chirp(M - i, P, -sign);
+        b[i] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) cmul_kernel(double2* __restrict__ a, const double2* __restrict__ b, int64_t M) {
+    double2* as = a + (int64_t)blockIdx.y * M;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (int64_t)gridDim.x * blockDim.x)
+        as[i] = cmul(as[i], b[i]);
+}
+
+// Stage A epilogue fused with stage C prologue.  From the convolution result conv[k] (k < m2):
+//   X[k] = conv[k]/M * chirp(k, N, -1) * (num/N)          the kept rfft bins, already rescaled
+//   unpaired-bin fix, one-sided weights (G = 2X, except the real DC / Nyquist bins)
+//   a2[k] = G[k] * chirp(k, num, +1),   zero up to M2
+// Reads and writes the same buffer (in place, element-wise); `src_stride`/`dst_stride` are the
+// per-signal strides of the two layouts (both views of the same allocation, processed signal by
+// signal from the host so that they never overlap destructively).
+__global__ void __launch_bounds__(256) spectrum_fix_kernel(const double2* __restrict__ conv, double2* __restrict__ a2, int64_t M,
+                                                           int64_t M2, int64_t N, int64_t num, int64_t m2) {
+    const int64_t m = N < num ? N : num;
+    const double scale = ((double)num / (double)N) / (double)M;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < M2; k += (int64_t)gridDim.x * blockDim.x) {
+        double2 v = make_double2(0.0, 0.0);
+        if (k < m2) {
+            double2 X = cmul(conv[k], chirp(k, N, -1));
+            X.x *= scale; X.y *= scale;
+            if ((m & 1) == 0 && num != N && k == m / 2) {
+                const double f = num < N ? 2.0 : 0.5;
+                X.x *= f; X.y *= f;
+            }
+            double2 G = make_double2(2.0 * X.x, 2.0 * X.y);
+            if (k == 0) G = make_double2(X.x, 0.0);
+            if ((num & 1) == 0 && k == num / 2) G = make_double2(X.x, 0.0);
+            v = cmul(G, chirp(k, num, +1));
+        }
+        a2[k] = v;
+    }
+}
+
+// y[j] = Re(conv[j] * chirp(j, num, +1)) / (M2 * num)
+__global__ void __launch_bounds__(256) czt_post_real_kernel(const double2* __restrict__ a, int64_t M2, int64_t num,
+                                                            double* __restrict__ y) {
+    const double2* as = a + (int64_t)blockIdx.y * M2;
+    double* ys = y + (int64_t)blockIdx.y * num;
+    const double scale = 1.0 / ((double)M2 * (double)num);
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < num; j += (int64_t)gridDim.x * blockDim.x) {
+        const double2 c = chirp(j, num, +1);
+        const double2 v = as[j];
+        ys[j] = (v.x * c.x - v.y * c.y) * scale;
+    }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+static int64_t pow2_at_least(int64_t v) { int64_t m = 1; while (m < v) m <<= 1; return m; }
+
+struct FftPlan { int n; int radix[8]; };
+
+static FftPlan make_plan(int64_t M) {
+    int bits = 0;
+    while (((int64_t)1 << bits) < M) ++bits;
+    FftPlan p;
+    p.n = bits == 0 ? 0 : (bits + 7) / 8;
+    int left = bits;
+    for (int i = 0; i < p.n; ++i) {
+        const int b = (left + (p.n - i) - 1) / (p.n - i);   // spread the bits evenly, larger radices first
+        p.radix[i] = 1 << b;
+        left -= b;
+    }
+    return p;
+}
+
+template <int R>
+static int launch_pass(double2* a, int64_t sig_stride, int64_t M, int64_t Mc, int n_sig, int inverse, cudaStream_t st) {
+    const int64_t cols = M / R;
+    const int tc = cols < FFT_TC ? (int)cols : FFT_TC;
+    const size_t smem = (size_t)(R * (FFT_TC + 1) + R / 2 + 1) * sizeof(double2);
+    auto kern = fft_pass_kernel<R>;
+    static bool attr_done = false;
+    if (!attr_done) { MMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr_done = true; }
+    dim3 grid((unsigned)(cols / tc), n_sig);
+    MMS_PROF_BEGIN(st);
+    kern<<<grid, FFT_THREADS, smem, st>>>(a, sig_stride, Mc, tc, inverse);
+    MMS_LAUNCH_CHECK("fft_pass_kernel");
+    return MMS_OK;
+}
+
+static int run_pass(int R, double2* a, int64_t sig_stride, int64_t M, int64_t Mc, int n_sig, int inverse, cudaStream_t st) {
+    switch (R) {
+        case 256: return launch_pass<256>(a, sig_stride, M, Mc, n_sig, inverse, st);
+        case 128: return launch_pass<128>(a, sig_stride, M, Mc, n_sig, inverse, st);
+        case 64: return launch_pass<64>(a, sig_stride, M, Mc, n_sig, inverse, st);
+        case 32: return launch_pass<32>(a, sig_stride, M, Mc, n_sig, inverse, st);
+        case 16: return launch_pass<16>(a, sig_stride, M, Mc, n_sig, inverse, st);
+        case 8: return launch_pass<8>(a, sig_stride, M, Mc, n_sig, inverse, st);
+        case 4: return launch_pass<4>(a, sig_stride, M, Mc, n_sig, inverse, st);
+        case 2: return launch_pass<2>(a, sig_stride, M, Mc, n_sig, inverse, st);
+    }
+    set_error("fft: unsupported radix %d", R);
+    return MMS_E_INVALID;
+}
+
+// digit-reversed forward transform (inverse = 0) or its exact inverse (inverse = 1, unnormalised)
+static int fft_inplace(double2* a, int64_t sig_stride, int64_t M, int n_sig, int inverse, cudaStream_t st) {
+    const FftPlan p = make_plan(M);
+    int64_t mc[8];
+    int64_t cur = M;
+    for (int i = 0; i < p.n; ++i) { mc[i] = cur; cur /= p.radix[i]; }
+    for (int ii = 0; ii < p.n; ++ii) {
+        const int i = inverse ? p.n - 1 - ii : ii;
+        int rc = run_pass(p.radix[i], a, sig_stride, M, mc[i], n_sig, inverse, st);
+        if (rc) return rc;
+    }
+    return MMS_OK;
+}
+
+static inline unsigned grid_for(int64_t n) {
+    int64_t b = (n + 255) / 256;
+    if (b > 148 * 16) b = 148 * 16;
+    return (unsigned)(b < 1 ? 1 : b);
+}
+
+struct ResampleDims { int64_t N, num, m2, M1, M2, Mmax; };
+
+static int resample_dims(int64_t n_in, int64_t n_out, ResampleDims* d) {
+    MMS_REQUIRE(n_in >= 1 && n_out >= 1 && n_in < ((int64_t)1 << 26) && n_out < ((int64_t)1 << 26),
+                "resample: lengths must be in [1, 2^26) (got %lld -> %lld)", (long long)n_in, (long long)n_out);
+    d->N = n_in; d->num = n_out;
+    const int64_t m = n_in < n_out ? n_in : n_out;
+    d->m2 = m / 2 + 1;
+    d->M1 = pow2_at_least(n_in + d->m2 - 1);
+    d->M2 = pow2_at_least(d->m2 + n_out - 1);
+    d->Mmax = d->M1 > d->M2 ? d->M1 : d->M2;
+    return MMS_OK;
+}
+
+}  // namespace mms
+
 using namespace mms;
-extern "C" int64_t mms_resample_workspace_bytes(int64_t n_in, int64_t n_out, int32_t n_sig) { return -1; }
+
+extern "C" int64_t mms_resample_workspace_bytes(int64_t n_in, int64_t n_out, int32_t n_sig) {
+    ResampleDims d;
+    if (resample_dims(n_in, n_out, &d) || n_sig < 1) return -1;
+    return (int64_t)sizeof(double2) * d.Mmax * ((int64_t)n_sig + 1);
+}
+
 extern "C" int mms_resample_f64(const double* x, int64_t n_in, int64_t n_out, int32_t n_sig, double* y, void* workspace,
                                 int64_t workspace_bytes, mms_stream_t stream) {
-    MMS_REQUIRE(false, "resample_f64: not built yet");
+    cudaStream_t st = (cudaStream_t)stream;
+    ResampleDims d;
+    int rc = resample_dims(n_in, n_out, &d);
+    if (rc) return rc;
+    MMS_REQUIRE(x && y && workspace && n_sig >= 1, "resample_f64: bad arguments");
+    const int64_t need = (int64_t)sizeof(double2) * d.Mmax * ((int64_t)n_sig + 1);
+    if (workspace_bytes < need) {
+        set_error("resample_f64: workspace %lld bytes < %lld", (long long)workspace_bytes, (long long)need);
+        return MMS_E_WORKSPACE;
+    }
+    double2* filt = (double2*)workspace;                 // [Mmax]
+    double2* work = filt + d.Mmax;                       // [n_sig][Mmax]
+
+    // ---- stage A: the m2 lowest bins of the length-N DFT ------------------------------------------
+    MMS_PROF_BEGIN(st);
+    czt_filter_kernel<<<grid_for(d.M1), 256, 0, st>>>(filt, d.M1, d.N, d.m2, d.N, -1);
+    MMS_LAUNCH_CHECK("czt_filter_kernel");
+    rc = fft_inplace(filt, d.M1, d.M1, 1, 0, st);
+    if (rc) return rc;
+    {
+        dim3 grid(grid_for(d.M1), n_sig);
+        MMS_PROF_BEGIN(st);
+        czt_pre_real_kernel<<<grid, 256, 0, st>>>(x, d.N, d.N, -1, work, d.M1);
+        MMS_LAUNCH_CHECK("czt_pre_real_kernel");
+    }
+    rc = fft_inplace(work, d.M1, d.M1, n_sig, 0, st);
+    if (rc) return rc;
+    {
+        dim3 grid(grid_for(d.M1), n_sig);
+        MMS_PROF_BEGIN(st);
+        cmul_kernel<<<grid, 256, 0, st>>>(work, filt, d.M1);
+        MMS_LAUNCH_CHECK("cmul_kernel");
+    }
+    rc = fft_inplace(work, d.M1, d.M1, n_sig, 1, st);
+    if (rc) return rc;
+
+    // ---- spectrum fix-up; re-pack the signals from stride M1 to stride M2 ---------------------------
+    // Signal s moves from work + s*M1 to work + s*M2.  With M2 <= M1 going upwards in s never
+    // overwrites an unread source; with M2 > M1 going downwards does the same.
+    for (int i = 0; i < n_sig; ++i) {
+        const int s = d.M2 <= d.M1 ? i : n_sig - 1 - i;
+        MMS_PROF_BEGIN(st);
+        spectrum_fix_kernel<<<grid_for(d.M2), 256, 0, st>>>(work + (int64_t)s * d.M1, work + (int64_t)s * d.M2, d.M1, d.M2, d.N,
+                                                          d.num, d.m2);
+        MMS_LAUNCH_CHECK("spectrum_fix_kernel");
+    }
+
+    // ---- stage C: one-sided inverse transform of length num ----------------------------------------
+    MMS_PROF_BEGIN(st);
+    czt_filter_kernel<<<grid_for(d.M2), 256, 0, st>>>(filt, d.M2, d.m2, d.num, d.num, +1);
+    MMS_LAUNCH_CHECK("czt_filter_kernel");
+    rc = fft_inplace(filt, d.M2, d.M2, 1, 0, st);
+    if (rc) return rc;
+    rc = fft_inplace(work, d.M2, d.M2, n_sig, 0, st);
+    if (rc) return rc;
+    {
+        dim3 grid(grid_for(d.M2), n_sig);
+        MMS_PROF_BEGIN(st);
+        cmul_kernel<<<grid, 256, 0, st>>>(work, filt, d.M2);
+        MMS_LAUNCH_CHECK("cmul_kernel");
+    }
+    rc = fft_inplace(work, d.M2, d.M2, n_sig, 1, st);
+    if (rc) return rc;
+    {
+        dim3 grid(grid_for(d.num), n_sig);
+        MMS_PROF_BEGIN(st);
+        czt_post_real_kernel<<<grid, 256, 0, st>>>(work, d.M2, d.num, y);
+        MMS_LAUNCH_CHECK("czt_post_real_kernel");
+    }
+    return MMS_OK;
 }

@@ -1,0 +1,243 @@
+"""Drop-in for the resample + windowing part of the reference ``preprocess.py`` ('raw' target).
+
+Same module constants, ``resample_signal(signal_data, original_fs, target_fs)``,
+``parse_quest_csv``, ``load_pkl`` and ``run_preprocessing()``; same output files
+(``data/chest_raw/{sid}_X.npy [N_win, W, 8] float64``, ``{sid}_y.npy [N_win] int64``,
+``_channel_names.txt``).  The FFT resampling (scipy.signal.resample semantics) and the window
+stacking run as sm_100a kernels (``mms_resample_f64`` / ``mms_window_gather``); the window start
+indices are computed on the host in float64 with the reference's exact expressions
+(preprocess.py:166-167,185-188), so they are bit-identical -- float traps included.
+
+Differences from the reference as shipped, all deliberate and documented:
+  * ``RAW_FS`` defaults to 64 (README / north star) instead of 128; it stays a module constant;
+  * ``PROCESS_TARGETS`` defaults to ``['raw']`` -- the directory ``main.py`` actually reads (D6);
+    the 'feature' / 'raw-align' branches need neurokit2 and are out of scope;
+  * wrist streams (extension, D2): ``include_wrist=True`` also resamples wrist ACC/BVP/EDA/TEMP
+    (32/64/4/4 Hz) with the same resampler and writes ``data/all_raw`` with 14 channels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import pickle
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from . import _ext
+from ._ext import check, ptr, stream
+
+# --- reference module constants (preprocess.py:13-28) -------------------------------------------
+WESAD_ROOT = Path('./WESAD')
+OUTPUT_PATH = Path('./data')
+ORIGINAL_CHEST_FS = 700
+PROCESS_TARGETS = ['raw']
+RAW_FS = 64
+RAW_WINDOW_SEC = 60
+RAW_STRIDE_SEC = 10
+CHEST_CHANNELS = ['ACC', 'ECG', 'EDA', 'EMG', 'Resp', 'Temp']
+TASK_TO_LABEL_MAP = {'Base': 1, 'TSST': 2, 'Fun': 3, 'Medi1': 4, 'Medi2': 4}
+WRIST_CHANNELS = {'ACC': 32, 'BVP': 64, 'EDA': 4, 'TEMP': 4}           # extension
+
+CHEST_CHANNEL_NAMES = [f"chest_ACC_{ax}" for ax in 'xyz'] + [f"chest_{c}" for c in ['ECG', 'EDA', 'EMG', 'Resp', 'Temp']]
+WRIST_CHANNEL_NAMES = [f"wrist_ACC_{ax}" for ax in 'xyz'] + ['wrist_BVP', 'wrist_EDA', 'wrist_TEMP']
+
+_MAX_SIGNALS_PER_CALL = 8
+
+
+def resampled_length(n: int, original_fs, target_fs) -> int:
+    """``int(len * (target_fs / original_fs))`` -- reference preprocess.py:72, same float64 order."""
+    return int(n * (target_fs / original_fs))
+
+
+def resample_on_device(x: torch.Tensor, num: int) -> torch.Tensor:
+    """``x`` float64 CUDA ``[n_sig, N]`` (rows contiguous) -> float64 ``[n_sig, num]``."""
+    lib = _ext.lib()
+    if x.dtype != torch.float64 or not x.is_cuda or x.dim() != 2:
+        raise _ext.MmsError("resample_on_device expects a float64 CUDA tensor [n_sig, N]")
+    x = x.contiguous()
+    n_sig, n = x.shape
+    y = torch.empty(n_sig, num, dtype=torch.float64, device=x.device)
+    for s0 in range(0, n_sig, _MAX_SIGNALS_PER_CALL):
+        k = min(_MAX_SIGNALS_PER_CALL, n_sig - s0)
+        nbytes = lib.mms_resample_workspace_bytes(n, num, k)
+        if nbytes < 0:
+            raise _ext.MmsError(f"resample: unsupported lengths {n} -> {num}")
+        ws = torch.empty(int(nbytes), dtype=torch.uint8, device=x.device)
+        check(lib.mms_resample_f64(ptr(x[s0:s0 + k]), n, num, k, ptr(y[s0:s0 + k]), ptr(ws), int(nbytes), stream()))
+    return y
+
+
+def resample_signal(signal_data, original_fs, target_fs):
+    """reference preprocess.py:70-75.  ``signal_data``: real ndarray ``[N]`` or ``[N, k]`` ->
+    float64 ndarray ``[num]`` / ``[num, k]`` with ``num = int(N * (target_fs / original_fs))``."""
+    arr = np.asarray(signal_data)
+    num = resampled_length(len(arr), original_fs, target_fs)
+    cols = arr.reshape(len(arr), -1).T                                   # [k, N]
+    x = torch.from_numpy(np.ascontiguousarray(cols, dtype=np.float64)).cuda()
+    y = resample_on_device(x, num).cpu().numpy()
+    return np.ascontiguousarray(y.T) if arr.ndim > 1 else y[0]
+
+
+def parse_quest_csv(subject_id: str, wesad_root: Path):
+    """reference preprocess.py:41-58 -> list of ``(task, start_min, end_min)`` (the reference
+    returns the same three columns as a DataFrame).  Includes the S2 / S6 quirk: the Base segment
+    starts at the midpoint of its span."""
+    quest_path = Path(wesad_root) / subject_id / f"{subject_id}_quest.csv"
+    rows = {}
+    for line in quest_path.read_text().splitlines():
+        if not line.strip():
+            continue
+        cells = line.split(';')
+        for tag in ('# ORDER', '# START', '# END'):
+            if tag in cells[0] and tag not in rows:
+                rows[tag] = [c.strip() for c in cells[1:] if c.strip() != '']
+    if len(rows) != 3:
+        raise ValueError(f"{quest_path}: missing # ORDER / # START / # END rows")
+    tasks = rows['# ORDER']
+    starts = [float(v) for v in rows['# START']]
+    ends = [float(v) for v in rows['# END']]
+    if not (len(tasks) == len(starts) == len(ends)):
+        raise ValueError(f"为受试者 {subject_id} 解析出的任务、开始、结束时间长度不匹配!")
+    protocol = [[t, s, e] for t, s, e in zip(tasks, starts, ends)]
+    if subject_id in ['S2', 'S6']:
+        for row in protocol:
+            if row[0] == 'Base':
+                row[1] = (row[1] + row[2]) / 2
+                break
+    return [tuple(r) for r in protocol]
+
+
+def load_pkl(subject_id: str, wesad_root: Path):
+    pkl_path = Path(wesad_root) / subject_id / f"{subject_id}.pkl"
+    try:
+        with open(pkl_path, 'rb') as f:
+            return pickle.load(f, encoding='bytes')
+    except FileNotFoundError:
+        print(f"警告: 无法找到文件 {pkl_path}")
+        return None
+
+
+def window_plan(protocol, target_fs, original_fs=ORIGINAL_CHEST_FS,
+                window_sec=RAW_WINDOW_SEC, stride_sec=RAW_STRIDE_SEC):
+    """Window start indices / raw labels / window length, reference preprocess.py:160-167,185-189.
+    Every product is evaluated left to right in float64 and truncated with ``int`` exactly as
+    the reference does."""
+    starts, labels = [], []
+    window = int(window_sec * target_fs)
+    stride = int(stride_sec * target_fs)
+    for task, start_min, end_min in protocol:
+        label = TASK_TO_LABEL_MAP.get(task.replace(" ", "").strip())
+        if label is None:
+            continue
+        start_idx_orig = int(start_min * 60 * original_fs)
+        end_idx_orig = int(end_min * 60 * original_fs)
+        start_idx_raw = int(start_idx_orig * (target_fs / original_fs))
+        end_idx_raw = int(end_idx_orig * (target_fs / original_fs))
+        for i in range(start_idx_raw, end_idx_raw - window + 1, stride):
+            starts.append(i)
+            labels.append(label)
+    return np.asarray(starts, dtype=np.int64), np.asarray(labels, dtype=np.int64), window
+
+
+def _stream_rows(sensor_dict, names):
+    """Stack the sensors of one device into float64 rows ``[n_channels, N]`` (ACC gives 3 rows)."""
+    rows = []
+    for name in names:
+        a = np.asarray(sensor_dict[name])
+        a = a.reshape(len(a), -1)
+        rows.extend(np.ascontiguousarray(a[:, j], dtype=np.float64) for j in range(a.shape[1]))
+    return np.stack(rows)
+
+
+class SubjectStreams:
+    """Resampled continuous streams of one subject on the device + its window plan.
+
+    ``streams`` float64 CUDA ``[n_channels, num]``; ``starts`` int64 CUDA ``[n_win]``; ``labels``
+    int64 numpy (raw labels 1..4).  This is what the on-device dataset keeps instead of the
+    6x-expanded window array."""
+
+    def __init__(self, sid, streams, starts, labels, window, channel_names):
+        self.sid, self.streams, self.labels, self.window = sid, streams, labels, window
+        self.starts_host = starts
+        self.starts = torch.from_numpy(starts).to(streams.device)
+        self.channel_names = list(channel_names)
+
+    def _ptr_array(self, idx):
+        rows = [self.streams[i] for i in idx]
+        return (C.c_void_p * len(rows))(*[r.data_ptr() for r in rows]), rows
+
+    def windows_f64(self, channel_idx=None) -> torch.Tensor:
+        """``[n_win, W, C]`` float64 on the device -- the array preprocess.py:218 saves."""
+        lib = _ext.lib()
+        idx = list(range(self.streams.shape[0])) if channel_idx is None else list(channel_idx)
+        arr, _keep = self._ptr_array(idx)
+        n_win = len(self.labels)
+        out = torch.empty(n_win, self.window, len(idx), dtype=torch.float64, device=self.streams.device)
+        check(lib.mms_window_gather(arr, len(idx), self.streams.shape[1], ptr(self.starts), n_win, self.window, 0,
+                                    None, None, None, ptr(out), stream()))
+        return out
+
+
+def preprocess_subject(sid, data, protocol, target_fs=None, include_wrist=False, device=None) -> SubjectStreams:
+    """One iteration of the reference subject loop (preprocess.py:138-200) up to, but not
+    including, the materialisation of the windows."""
+    target_fs = RAW_FS if target_fs is None else target_fs
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+    chest = {k.decode('utf-8') if isinstance(k, bytes) else k: v for k, v in data[b'signal'][b'chest'].items()}
+    rows = _stream_rows(chest, CHEST_CHANNELS)
+    num = resampled_length(rows.shape[1], ORIGINAL_CHEST_FS, target_fs)
+    streams = resample_on_device(torch.from_numpy(rows).to(device), num)
+    names = list(CHEST_CHANNEL_NAMES)
+    if include_wrist:
+        wrist = {k.decode('utf-8') if isinstance(k, bytes) else k: v for k, v in data[b'signal'][b'wrist'].items()}
+        parts = []
+        for name, fs in WRIST_CHANNELS.items():
+            r = _stream_rows(wrist, [name])
+            nw = resampled_length(r.shape[1], fs, target_fs)
+            y = resample_on_device(torch.from_numpy(r).to(device), nw)
+            if nw < num:                                   # wrist clock ends a few samples early: pad with the last value
+                y = torch.cat([y, y[:, -1:].expand(-1, num - nw)], dim=1)
+            parts.append(y[:, :num])
+        streams = torch.cat([streams] + parts, dim=0).contiguous()
+        names += WRIST_CHANNEL_NAMES
+    starts, labels, window = window_plan(protocol, target_fs)
+    if len(starts) and starts.max() + window > num:
+        raise ValueError(f"{sid}: a window runs past the end of the resampled stream")
+    return SubjectStreams(sid, streams, starts, labels, window, names)
+
+
+def run_preprocessing(wesad_root=None, output_path=None, subject_ids=None, include_wrist=False):
+    """reference preprocess.py:126-242 for ``PROCESS_TARGETS = ['raw']``."""
+    wesad_root = Path(WESAD_ROOT if wesad_root is None else wesad_root)
+    output_path = Path(OUTPUT_PATH if output_path is None else output_path)
+    for target in PROCESS_TARGETS:
+        if target != 'raw':
+            raise NotImplementedError(f"PROCESS_TARGETS entry {target!r}: only 'raw' is in scope "
+                                      "(the 'feature' / 'raw-align' branches need neurokit2)")
+    subject_ids = [f"S{i}" for i in range(2, 18) if i != 12] if subject_ids is None else subject_ids
+    raw_path = output_path / ('all_raw' if include_wrist else 'chest_raw')
+    raw_path.mkdir(parents=True, exist_ok=True)
+    names = CHEST_CHANNEL_NAMES + (WRIST_CHANNEL_NAMES if include_wrist else [])
+    with open(raw_path / '_channel_names.txt', 'w') as f:
+        for name in names:
+            f.write(f"{name}\n")
+    done = []
+    for sid in subject_ids:
+        data = load_pkl(sid, wesad_root)
+        if data is None:
+            continue
+        protocol = parse_quest_csv(sid, wesad_root)
+        sub = preprocess_subject(sid, data, protocol, RAW_FS, include_wrist=include_wrist)
+        if len(sub.labels):
+            X = sub.windows_f64().cpu().numpy()
+            np.save(raw_path / f'{sid}_X.npy', X)
+            np.save(raw_path / f'{sid}_y.npy', sub.labels)
+            print(f"  - {sid} (raw): Saved {len(sub.labels)} windows. Raw shape: {X.shape}")
+            done.append(sid)
+    print("\nPreprocessing complete.")
+    return done
+
+
+if __name__ == '__main__':
+    run_preprocessing()

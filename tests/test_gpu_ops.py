@@ -194,6 +194,7 @@ def test_gemms(lib):
     M = B * L
     D = torch.randn(M, 4 * H, dtype=torch.float64)
     hs = torch.randn(B, L, H, dtype=torch.float64)
+    Dd, hsd = dev(D), dev(hs.reshape(M, H))          # keep the device tensors alive across the launches
     for shift in (-1, 1, 0):
         hprev = torch.zeros_like(hs)
         if shift == -1:
@@ -206,11 +207,11 @@ def test_gemms(lib):
         ref = dgh.t() @ hprev.reshape(M, H)
         Cd = torch.zeros(3 * H, H, device="cuda")
         bgd = torch.zeros(3 * H, device="cuda")
-        ok(lib.mms_gemm_tn_acc(P(dev(D)), 4 * H, 2 * H, H, P(dev(hs.reshape(M, H))), H, shift, L, P(Cd), H, P(bgd), M, 3 * H, H, ST()))
+        ok(lib.mms_gemm_tn_acc(P(Dd), 4 * H, 2 * H, H, P(hsd), H, shift, L, P(Cd), H, P(bgd), M, 3 * H, H, ST()))
         close(Cd, ref, 2e-5, f"tn shift {shift}")
         close(bgd, dgh.sum(dim=0), 2e-5, "tn bias")
     bgd = torch.zeros(3 * H, device="cuda")
-    ok(lib.mms_gemm_tn_acc(P(dev(D)), 4 * H, 2 * H, H, None, 0, 0, 1, None, 0, P(bgd), M, 3 * H, 0, ST()))
+    ok(lib.mms_gemm_tn_acc(P(Dd), 4 * H, 2 * H, H, None, 0, 0, 1, None, 0, P(bgd), M, 3 * H, 0, ST()))
     close(bgd, torch.cat([D[:, :2 * H], D[:, 3 * H:]], dim=1).sum(dim=0), 2e-5, "tn bias only")
 
 
@@ -367,7 +368,8 @@ def test_adam_flat(lib):
         g = torch.randn(n)
         ref.grad = g.clone()
         opt.step()
-        ok(lib.mms_adam_flat_step(P(pd_), P(g.cuda()), P(md), P(vd), n, P(lr), 0.9, 0.999, 1e-8, 1e-4, P(step), P(scratch), ST()))
+        gd = g.cuda()
+        ok(lib.mms_adam_flat_step(P(pd_), P(gd), P(md), P(vd), n, P(lr), 0.9, 0.999, 1e-8, 1e-4, P(step), P(scratch), ST()))
         assert int(step.item()) == it + 1
         np.testing.assert_allclose(pd_.cpu().numpy(), ref.detach().numpy(), atol=2e-6)
         # oracle restatement agrees too

@@ -1,0 +1,156 @@
+"""Host-side logic of the drop-in modules (no GPU): index arithmetic, protocol parsing, fold
+tables, fold sharding over ranks (gloo, world_size 2), EarlyStopping semantics, file dataset."""
+import json
+import os
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, ROOT, load_golden
+from multimodalsignal_b200 import synth
+from oracle import preprocess_oracle as po
+
+
+@pytest.mark.parametrize("fs", [64, 128])
+def test_window_plan_bit_exact_vs_reference(fs):
+    """Window start indices and labels of the drop-in == the reference's own loop (golden, full
+    15-subject protocol with float-trap start times)."""
+    from multimodalsignal_b200 import preprocess as pp
+    z, _ = load_golden("preprocess_golden.npz")
+    for sid in synth.ALL_SUBJECTS:
+        protocol = po.apply_subject_quirk(sid, synth.FULL_PROTOCOL)
+        starts, labels, w = pp.window_plan(protocol, fs)
+        assert starts.dtype == np.int64 and labels.dtype == np.int64
+        assert np.array_equal(starts, z[f"full/{fs}/{sid}/starts"]), sid
+        assert np.array_equal(labels, z[f"full/{fs}/{sid}/labels"]), sid
+        assert w == 60 * fs
+
+
+def test_resampled_length_matches_reference_expression():
+    from multimodalsignal_b200 import preprocess as pp
+    for n in [1, 699, 700, 4200000, 4200137, 4201918, 7999999]:
+        for f0, f1 in [(700, 64), (700, 128), (32, 64), (4, 64), (64, 64)]:
+            assert pp.resampled_length(n, f0, f1) == int(n * (f1 / f0))
+
+
+def test_parse_quest_csv_and_quirk(tmp_path):
+    from multimodalsignal_b200 import preprocess as pp
+    for sid in ("S2", "S5"):
+        d = tmp_path / sid
+        d.mkdir()
+        (d / f"{sid}_quest.csv").write_text(synth.quest_csv_text(synth.FULL_PROTOCOL))
+    p5 = pp.parse_quest_csv("S5", tmp_path)
+    assert [t for t, _, _ in p5] == [t for t, _, _ in synth.FULL_PROTOCOL]
+    assert p5[1][1] == 32.05 and p5[1][2] == 43.5
+    p2 = pp.parse_quest_csv("S2", tmp_path)
+    assert p2[0] == ("Base", (5.0 + 25.0) / 2, 25.0)            # preprocess.py:53-57
+    assert p2[1:] == p5[1:]
+    assert pp.load_pkl("S99", tmp_path) is None                  # preprocess.py:66-68
+
+
+def test_constants_match_reference_contract():
+    from multimodalsignal_b200 import main as mm, preprocess as pp
+    assert pp.CHEST_CHANNEL_NAMES == ["chest_ACC_x", "chest_ACC_y", "chest_ACC_z", "chest_ECG", "chest_EDA",
+                                      "chest_EMG", "chest_Resp", "chest_Temp"]
+    assert pp.TASK_TO_LABEL_MAP == {'Base': 1, 'TSST': 2, 'Fun': 3, 'Medi1': 4, 'Medi2': 4}
+    assert (pp.RAW_WINDOW_SEC, pp.RAW_STRIDE_SEC, pp.ORIGINAL_CHEST_FS) == (60, 10, 700)
+    assert mm.ALL_SUBJECTS == synth.ALL_SUBJECTS and len(mm.ALL_SUBJECTS) == 15
+    assert (mm.SEED, mm.EPOCHS, mm.BATCH_SIZE, mm.LEARNING_RATE, mm.PATIENCE, mm.WEIGHTS_DECAY) == (42, 100, 64, 0.001, 20, 1e-4)
+    assert mm.CHANNELS_TO_USE == ['chest_ECG', 'chest_EDA', 'chest_Resp']
+    cfg = mm.trainer_config()['trainer']
+    assert cfg['early_stopping'] == {'enabled': True, 'patience': 20, 'delta': 0}
+
+
+def test_fold_split_matches_reference_table():
+    from multimodalsignal_b200 import main as mm
+    table = json.loads((GOLDEN / "fold_table.json").read_text())["folds"]
+    for s in mm.ALL_SUBJECTS:
+        tr, va = mm.fold_split(s)
+        assert tr == table[s]["train"] and va == table[s]["val"], s
+
+
+def test_folds_for_rank_partition():
+    from multimodalsignal_b200.main import folds_for_rank
+    for world in (1, 2, 4, 8, 15, 16):
+        seen = sorted(f for r in range(world) for f in folds_for_rank(15, r, world))
+        assert seen == list(range(15))
+        assert max(len(folds_for_rank(15, r, world)) for r in range(world)) == -(-15 // world)
+
+
+def test_early_stopping_is_bug_compatible(tmp_path):
+    """with val_loss as the score the reference saves when the loss does NOT improve."""
+    from multimodalsignal_b200.trainer import EarlyStopping
+    model = torch.nn.Linear(2, 2)
+    saves = []
+    es = EarlyStopping(patience=2, delta=0, checkpoint_path=tmp_path / "best_model.pt")
+    es.save_checkpoint = lambda m: saves.append(es.best_score)
+    es(1.0, model)            # first call always saves
+    es(0.9, model)            # loss improved -> reference counts patience (1/2), no save
+    assert es.counter == 1 and len(saves) == 1
+    es(1.2, model)            # loss got worse -> reference saves and resets
+    assert es.counter == 0 and len(saves) == 2 and es.best_score == 1.2
+    es(1.1, model); es(1.0, model)
+    assert es.early_stop
+    fixed = EarlyStopping(patience=2, delta=0, checkpoint_path=tmp_path / "b.pt", fixed=True)
+    fixed.save_checkpoint = lambda m: saves.append("fixed")
+    fixed(1.0, model); fixed(0.9, model)
+    assert fixed.counter == 0 and saves[-1] == "fixed"      # the intended behaviour: improvement saves
+
+
+def test_file_dataset_matches_reference(tmp_path):
+    """``WesadDataset`` (file path, host numpy) vs reference dataset.py output (golden)."""
+    from multimodalsignal_b200.dataset import WesadDataset
+    z, _ = load_golden("preprocess_golden.npz")
+    names = bytes(z["channel_names"]).decode().split()
+    for sid in ("S2", "S5"):
+        idx = synth.ALL_SUBJECTS.index(sid)
+        sub = synth.make_subject(sid, idx, minutes=synth.SHORT_MINUTES, protocol=synth.SHORT_PROTOCOL, with_wrist=False)
+        X, y = po.preprocess_subject(sid, sub.chest, sub.protocol, 64)
+        np.save(tmp_path / f"{sid}_X.npy", X)
+        np.save(tmp_path / f"{sid}_y.npy", y)
+    chans = ["chest_ECG", "chest_EDA", "chest_EMG", "chest_Resp"]
+    for mode in ("stress_binary", "ternary"):
+        ds = WesadDataset(tmp_path, ["S2", "S5", "S99"], chans, names, classification_mode=mode)
+        assert len(ds) == int(z[f"dataset/{mode}/len"])
+        assert np.array_equal(ds.labels, z[f"dataset/{mode}/labels"])
+        np.testing.assert_allclose(ds.data[:, ::61, :], z[f"dataset/{mode}/data_sub"], atol=1e-9)
+        x3, y3 = ds[3]
+        assert x3.dtype == torch.float32 and tuple(x3.shape) == (4, 3840) and y3.dtype == torch.int64
+        np.testing.assert_allclose(x3.numpy()[:, ::61], z[f"dataset/{mode}/item3_x_sub"], atol=1e-6)
+    with pytest.raises(ValueError):
+        WesadDataset(tmp_path, ["S2"], chans, names, classification_mode="amusement_binary")
+    with pytest.raises(ValueError):
+        WesadDataset(tmp_path, ["S98", "S99"], chans, names)                                     # dataset.py:53-54
+
+
+def test_fold_sharding_world_size_2_gloo(tmp_path):
+    """N > 1 path on CPU: two gloo ranks shard the 15 folds, rank 0 writes cv_summary.txt."""
+    script = tmp_path / "shard.py"
+    script.write_text(textwrap.dedent(f"""
+        import os, sys
+        sys.path.insert(0, {str(ROOT)!r})
+        import torch.distributed as dist
+        from multimodalsignal_b200 import main as mm
+        dist.init_process_group("gloo")
+        def fake_fold(fold_index, subject, out_dir, names, streams):
+            return {{'subject': subject, 'accuracy': 0.5 + 0.01 * fold_index, 'f1_score': 0.4 + 0.01 * fold_index,
+                    'rank': dist.get_rank()}}
+        res = mm.run_simple_experiment({str(tmp_path)!r}, None, [], fold_fn=fake_fold)
+        assert [r['subject'] for r in res] == mm.ALL_SUBJECTS
+        assert sorted(set(r['rank'] for r in res)) == [0, 1]
+        assert [r['rank'] for r in res] == [i % 2 for i in range(15)]
+        dist.destroy_process_group()
+    """))
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29611", str(script)],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    text = (tmp_path / "cv_summary.txt").read_text(encoding="utf-8")
+    assert "测试 S2: Accuracy = 0.5000, F1-score = 0.4000" in text
+    assert "测试 S17: Accuracy = 0.6400" in text
+    assert "平均准确率 (Accuracy): 0.5700" in text
