@@ -246,7 +246,66 @@ def main():
     make_resample_cases()
     make_preprocess_goldens()
     make_fold_table()
+    make_trainer_golden()
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--trainer-only" not in sys.argv:
     main()
+
+
+# --------------------------------------------------------------------------- trainer
+TRAINER_CASE = {"train": ["S3", "S4"], "val": ["S5"], "test": ["S2"], "channels": ["chest_ECG", "chest_EDA", "chest_Resp"],
+                "batch_size": 8, "epochs": 2, "seed": 42}
+
+
+def make_trainer_golden():
+    """Two epochs of the UNMODIFIED reference Trainer (CPU, dropout = 0 so the run is deterministic)
+    on short synthetic recordings preprocessed by the reference's own run_preprocessing()."""
+    import io
+    import contextlib
+    from torch.utils.data import DataLoader
+    case = TRAINER_CASE
+    with tempfile.TemporaryDirectory() as tmpd:
+        tmp = Path(tmpd)
+        synth.write_wesad_tree(tmp / "WESAD", subjects=["S2", "S3", "S4", "S5"], minutes=synth.SHORT_MINUTES,
+                               protocol=synth.SHORT_PROTOCOL, with_wrist=False)
+        path = _run_reference_preprocessing(tmp, 64, index_probe=False)
+        names = (path / "_channel_names.txt").read_text().split()
+        ds_mod = ref_harness.load("dataset")
+        models = ref_harness.load("models")
+        trainer_mod = ref_harness.load("trainer")
+        mk = lambda subs: ds_mod.WesadDataset(path, subs, case["channels"], names, classification_mode="stress_binary")
+        torch.manual_seed(case["seed"])
+        np.random.seed(case["seed"])
+        torch.set_num_threads(1)
+        train_ds, val_ds, test_ds = mk(case["train"]), mk(case["val"]), mk(case["test"])
+        tl = DataLoader(train_ds, batch_size=case["batch_size"], shuffle=True, num_workers=0)
+        vl = DataLoader(val_ds, batch_size=case["batch_size"], shuffle=False, num_workers=0)
+        te = DataLoader(test_ds, batch_size=case["batch_size"], shuffle=False, num_workers=0)
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            model = models.CnnGruAttentionModel(in_channels=3, num_classes=2, dropout=0.0)
+        cfg = {'trainer': {'epochs': case["epochs"], 'learning_rate': 1e-3,
+                           'early_stopping': {'enabled': True, 'patience': 20, 'delta': 0}, 'weight_decay': 1e-4}}
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf), contextlib.redirect_stderr(io.StringIO()):
+            tr = trainer_mod.Trainer(model, tmp / "fold", cfg)
+            tr.train(tl, vl)
+            test_loss, test_acc, test_f1 = tr.evaluate(te, is_test=True)
+        log = (tmp / "fold" / "training_log.txt").read_text(encoding="utf-8")
+        ckpt = torch.load(tmp / "fold" / "best_model.pt", weights_only=True)
+        out = {"case": case, "versions": _versions(), "log": log,
+               "n_train": len(train_ds), "n_val": len(val_ds), "n_test": len(test_ds),
+               "test": {"loss": test_loss, "acc": test_acc, "f1": test_f1},
+               "best_model_keys": list(ckpt.keys()),
+               "best_model_shapes": {k: list(v.shape) for k, v in ckpt.items()},
+               "final_fc3_bias": model.classifier[3].bias.detach().tolist(),
+               "final_bn1_running_mean": model.cnn_encoder[1].running_mean.tolist()}
+        (GOLDEN / "trainer_golden.json").write_text(json.dumps(out, indent=1, ensure_ascii=False))
+    print("trainer_golden written:", out["test"])
+
+
+if __name__ == "__main__" and "--trainer-only" in sys.argv:
+    GOLDEN.mkdir(parents=True, exist_ok=True)
+    make_trainer_golden()
