@@ -181,6 +181,11 @@ int mms_bn_relu_pool_bwd(const float* y, const double* stats, const float* gamma
  *   tn : C[i,j] += sum_m A[m*lda+acol(i)] * Bm[row(m)*ldb+j], bias_grad[i] += sum_m A[m*lda+acol(i)]
  *        acol(i) = i < a_split ? i : i + a_skip;  row(m) = m + shift within each block of
  *        `seq` rows (rows shifted outside their block read as zero) -- this is h_{t-1}. */
+/* Tensor-core version of the nt form: TMA-staged operands, tcgen05.mma kind::tf32 with the 3xTF32
+ * operand split (fp32-level accuracy), accumulators in TMEM.  C[m,n] (+)= sum_k A[m,k] W[n,k] + bias[n].
+ * A and W must be 16-byte aligned with lda, ldw multiples of 4. */
+int mms_tc_gemm_nt(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
+                   float* C, int64_t ldc, int32_t M, int32_t N, int32_t K, int32_t accumulate, mms_stream_t stream);
 int mms_gemm_nt_bias(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
                      float* C, int64_t ldc, int32_t M, int32_t N, int32_t K, mms_stream_t stream);
 int mms_gemm_nn(const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc,

@@ -1,0 +1,342 @@
+// Tensor-core GEMMs for the GRU input projections and their gradients (the x @ W_ih^T + b_ih part of
+// nn.GRU, reference models.py:56-63,78) on Blackwell's 5th-generation tensor cores:
+//   * operands staged by TMA (cp.async.bulk.tensor, 128-byte swizzle) straight from the fp32 tensors;
+//   * tcgen05.mma.kind::tf32 issued by one elected thread, accumulators in tensor memory (TMEM),
+//     read back with tcgen05.ld for the epilogue (bias add, optional accumulate, store);
+//   * fp32-level accuracy through the 3xTF32 split: every operand tile x is rewritten in shared
+//     memory as hi = x with the low 13 mantissa bits cleared (exactly representable in tf32) and
+//     lo = x - hi, and each k-step issues  A_lo*B_hi + A_hi*B_lo + A_hi*B_hi.  The dropped term
+//     lo*lo is ~2^-22 relative -- the result is indistinguishable from an fp32 FMA chain at the
+//     1e-4 logit tolerance, which a plain tf32 GEMM (2^-11) is not.
+// Warp roles in a 192-thread CTA: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
+// warps 2-5 = operand splitters, then epilogue (one TMEM lane quarter each).
+//
+//   NT :  C[m, n] (+)= sum_k A[m, k] * B[n, k] + bias[n]        (A, B both K-major = row-major)
+#include "mms_common.cuh"
+#include <cuda.h>
+
+namespace mms {
+
+constexpr int TC_BM = 128;          // rows per CTA tile = UMMA M
+constexpr int TC_BK = 32;           // fp32 elements per k-block = one 128-byte swizzle row
+constexpr int TC_STAGES = 2;
+constexpr int TC_THREADS = 192;
+constexpr int TC_UMMA_K = 8;        // tf32: 32 bytes per MMA k-step
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+// K-major operand tile, 128-byte swizzle: rows of 128 bytes, 8-row groups 1024 bytes apart.
+__device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);        // start address
+    d |= (uint64_t)1 << 16;                             // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                             // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
+    return d;
+}
+
+// kind::tf32, fp32 accumulate, both operands K-major, M = 128, N = n
+__device__ __forceinline__ uint32_t umma_idesc_tf32(int n) {
+    uint32_t d = 0;
+    d |= 1u << 4;                  // c_format = F32
+    d |= 2u << 7;                  // a_format = TF32
+    d |= 2u << 10;                 // b_format = TF32
+    d |= (uint32_t)(n >> 3) << 17; // n_dim
+    d |= (uint32_t)(TC_BM >> 4) << 24;  // m_dim
+    return d;
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct TcGemmParams {
+    float* C;
+    const float* bias;
+    int64_t ldc;
+    int M, N, K, BN, accumulate;
+};
+
+// dynamic smem: [stage][A_hi | A_lo | B_hi | B_lo] (1024-byte aligned tiles)
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                                   const __grid_constant__ CUtensorMap mapB, const TcGemmParams p) {
+    extern __shared__ __align__(1024) uint8_t tc_smem[];
+    __shared__ __align__(8) uint64_t full_bar[TC_STAGES], split_bar[TC_STAGES], empty_bar[TC_STAGES], acc_bar;
+    __shared__ uint32_t tmem_base_sh;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int BN = p.BN;
+    const uint32_t a_bytes = TC_BM * TC_BK * 4, b_bytes = (uint32_t)BN * TC_BK * 4;
+    const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem) + 1023) & ~(uintptr_t)1023);
+    const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN;
+    const int nkb = (p.K + TC_BK - 1) / TC_BK;
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < BN) tmem_cols <<= 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&split_bar[s], 4);      // one arrival per splitter warp
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(&acc_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_base_sh;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % TC_STAGES, round = kb / TC_STAGES;
+                if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);
+                uint8_t* st = base + (size_t)s * stage_bytes;
+                mbar_expect_tx(&full_bar[s], a_bytes + b_bytes);
+                tma_load_2d(&mapA, &full_bar[s], st, kb * TC_BK, m0);
+                tma_load_2d(&mapB, &full_bar[s], st + 2 * a_bytes, kb * TC_BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32(BN);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % TC_STAGES, round = kb / TC_STAGES;
+                mbar_wait(&split_bar[s], round & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t st = smem_u32(base + (size_t)s * stage_bytes);
+                const uint32_t a_hi = st, a_lo = st + a_bytes, b_hi = st + 2 * a_bytes, b_lo = st + 2 * a_bytes + b_bytes;
+#pragma unroll
+                for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+                    const uint32_t off = k * TC_UMMA_K * 4;
+                    const uint64_t dAh = umma_desc_kmajor_sw128(a_hi + off), dAl = umma_desc_kmajor_sw128(a_lo + off);
+                    const uint64_t dBh = umma_desc_kmajor_sw128(b_hi + off), dBl = umma_desc_kmajor_sw128(b_lo + off);
+                    umma_tf32(tmem_d, dAl, dBh, idesc, (kb | k) != 0);
+                    umma_tf32(tmem_d, dAh, dBl, idesc, 1);
+                    umma_tf32(tmem_d, dAh, dBh, idesc, 1);
+                }
+                umma_commit(&empty_bar[s]);            // frees the stage once these MMAs have read it
+            }
+            umma_commit(&acc_bar);                     // accumulator complete
+        }
+    } else {
+        // ===== operand splitters (warps 2..5), then epilogue =====
+        const int t = threadIdx.x - 64;                // 0..127
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % TC_STAGES, round = kb / TC_STAGES;
+            mbar_wait(&full_bar[s], round & 1);
+            uint8_t* st = base + (size_t)s * stage_bytes;
+            // A: hi in place, lo to the second tile (same offsets, so the swizzle is irrelevant)
+            {
+                float4* hi = reinterpret_cast<float4*>(st);
+                float4* lo = reinterpret_cast<float4*>(st + a_bytes);
+                for (int i = t; i < (int)(a_bytes / 16); i += 128) {
+                    const float4 v = hi[i];
+                    float4 h, l;
+                    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+                    h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+                    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+                    h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+                    hi[i] = h;
+                    lo[i] = l;
+                }
+            }
+            {
+                float4* hi = reinterpret_cast<float4*>(st + 2 * a_bytes);
+                float4* lo = reinterpret_cast<float4*>(st + 2 * a_bytes + b_bytes);
+                for (int i = t; i < (int)(b_bytes / 16); i += 128) {
+                    const float4 v = hi[i];
+                    float4 h, l;
+                    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+                    h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+                    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+                    h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+                    hi[i] = h;
+                    lo[i] = l;
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&split_bar[s]);
+        }
+        // ===== epilogue: TMEM lane quarter (warp % 4) -> registers -> global =====
+        mbar_wait(&acc_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int quarter = warp & 3;
+        const int row = m0 + quarter * 32 + lane;
+        float* crow = p.C + (int64_t)row * p.ldc + n0;
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+            uint32_t r[16];
+            const uint32_t taddr = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const bool fast = row < p.M && n0 + c0 + 16 <= p.N && !p.accumulate && (p.ldc & 3) == 0 &&
+                              (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && ((n0 + c0) & 3) == 0 &&
+                              (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0;
+            if (fast) {
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    float4 v = make_float4(__uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1]), __uint_as_float(r[4 * j4 + 2]),
+                                           __uint_as_float(r[4 * j4 + 3]));
+                    if (p.bias) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0) + j4);
+                        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                    }
+                    reinterpret_cast<float4*>(crow + c0)[j4] = v;
+                }
+            } else if (row < p.M) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int n = n0 + c0 + j;
+                    if (n < p.N) {
+                        float v = __uint_as_float(r[j]);
+                        if (p.bias) v += __ldg(p.bias + n);
+                        if (p.accumulate) v += crow[c0 + j];
+                        crow[c0 + j] = v;
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols) : "memory");
+    }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+    }
+    return fn;
+}
+
+// 2-D fp32 tensor [rows, cols] with row stride ld (floats); box = [box_rows, 32 cols], 128-byte swizzle
+static int make_map(CUtensorMap* map, const float* g, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    MMS_REQUIRE(fn, "tc_gemm: cuTensorMapEncodeTiled is not available from the driver");
+    MMS_REQUIRE((reinterpret_cast<uintptr_t>(g) & 15) == 0 && (ld * 4) % 16 == 0, "tc_gemm: operand must be 16-byte aligned with ld %% 4 == 0");
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)g, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("tc_gemm: cuTensorMapEncodeTiled failed with %d (rows %lld cols %lld ld %lld box %d)", (int)r, (long long)rows,
+                  (long long)cols, (long long)ld, box_rows);
+        return MMS_E_CUDA;
+    }
+    return MMS_OK;
+}
+
+static int pick_bn(int N) {
+    // UMMA N for M = 128: multiple of 16 in [16, 256]; split wide outputs into equal tiles
+    int tiles = (N + 255) / 256;
+    int bn = (N + tiles - 1) / tiles;
+    bn = (bn + 15) / 16 * 16;
+    return bn;
+}
+
+bool tc_gemm_supported(const float* A, int64_t lda, const float* W, int64_t ldw, int M, int N, int K) {
+    return encode_tiled_fn() && (reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
+           lda % 4 == 0 && ldw % 4 == 0 && M >= 1 && N >= 1 && K >= 1;
+}
+
+int launch_tc_gemm_nt(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, float* C, int64_t ldc, int M,
+                      int N, int K, int accumulate, cudaStream_t st) {
+    if (M <= 0 || N <= 0) return MMS_OK;
+    const int BN = pick_bn(N);
+    CUtensorMap mapA, mapB;
+    int rc = make_map(&mapA, A, M, K, lda, TC_BM);
+    if (rc) return rc;
+    rc = make_map(&mapB, W, N, K, ldw, BN);
+    if (rc) return rc;
+    const size_t stage = (size_t)2 * TC_BM * TC_BK * 4 + (size_t)2 * BN * TC_BK * 4;
+    const size_t smem = stage * TC_STAGES + 1024;
+    static bool attr_done = false;
+    if (!attr_done) {
+        MMS_CUDA(cudaFuncSetAttribute(tc_gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_done = true;
+    }
+    MMS_REQUIRE(smem <= 200 * 1024, "tc_gemm: shared memory %zu too large", smem);
+    TcGemmParams p;
+    p.C = C; p.bias = bias; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.BN = BN; p.accumulate = accumulate;
+    dim3 grid(cdiv(M, TC_BM), cdiv(N, BN));
+    MMS_PROF_BEGIN(st);
+    tc_gemm_nt_kernel<<<grid, TC_THREADS, smem, st>>>(mapA, mapB, p);
+    MMS_LAUNCH_CHECK("tc_gemm_nt_kernel");
+    return MMS_OK;
+}
+
+}  // namespace mms
+
+using namespace mms;
+
+extern "C" int mms_tc_gemm_nt(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, float* C, int64_t ldc,
+                              int32_t M, int32_t N, int32_t K, int32_t accumulate, mms_stream_t stream) {
+    MMS_REQUIRE(A && W && C && K > 0, "tc_gemm_nt: bad arguments");
+    return launch_tc_gemm_nt(A, lda, W, ldw, bias, C, ldc, M, N, K, accumulate, (cudaStream_t)stream);
+}
