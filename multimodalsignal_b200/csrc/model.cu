@@ -4,6 +4,7 @@
 // (so a Python caller pays one ctypes call per pass and the chain can be captured in a CUDA graph).
 #include "mms_common.cuh"
 #include <string.h>
+#include <stdlib.h>
 
 namespace mms {
 
@@ -32,10 +33,84 @@ int launch_cross_entropy(const float*, const int64_t*, int, int, float*, float*,
 int launch_adam(float*, const float*, float*, float*, int64_t, const float*, float, float, float, float, int64_t*, int32_t*,
                 cudaStream_t);
 int launch_chan_dx(const float*, const float*, const float*, int, int, int, float*, cudaStream_t);
+int launch_tc_gemm_nt(const float*, int64_t, const float*, int64_t, const float*, float*, int64_t, int, int, int, int, cudaStream_t);
+bool tc_gemm_supported(const float*, int64_t, const float*, int64_t, int, int, int);
+constexpr int TC_MIN_ROWS = 1024;      // below this a single tcgen05 CTA is pure latency: the SIMT kernels win
+int launch_transpose_pad(const float*, int, int, float*, int64_t, int, cudaStream_t);
 int launch_dropout_apply(const float*, float*, int64_t, int64_t, float, uint64_t, uint64_t, const int64_t*, cudaStream_t);
 
 constexpr int MAX_LAYERS = 8;
 constexpr int64_t DROP_LAYER_STRIDE = 1ll << 40;
+
+// MMS_DISABLE_TC=1 keeps every GEMM on the fp32 SIMT kernels (debugging / A-B measurements)
+static bool use_tc() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MMS_DISABLE_TC"); v = (e && e[0] == '1') ? 0 : 1; }
+    return v == 1;
+}
+
+// Side streams: weight-gradient kernels do not feed the backward critical path (recurrence -> dx ->
+// recurrence -> conv chain), so they are forked onto two library-owned streams and joined before the
+// caller's next kernel (Adam).  Event fork/join works identically in eager mode and under CUDA-graph
+// capture (the side streams become branches of the captured graph).  MMS_DISABLE_STREAMS=1 serialises.
+struct SideStreams {
+    cudaStream_t s[2] = {nullptr, nullptr};
+    cudaEvent_t fork_ev[8] = {}, join_ev[2] = {};
+    bool ok = false;
+};
+static SideStreams* side_streams() {
+    static SideStreams per_dev[16];
+    static int disabled = -1;
+    if (disabled < 0) { const char* e = getenv("MMS_DISABLE_STREAMS"); disabled = (e && e[0] == '1') ? 1 : 0; }
+    if (disabled) return nullptr;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    SideStreams& ss = per_dev[dev];
+    if (!ss.ok) {
+        for (int i = 0; i < 2; ++i)
+            if (cudaStreamCreateWithFlags(&ss.s[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        for (int i = 0; i < 8; ++i)
+            if (cudaEventCreateWithFlags(&ss.fork_ev[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        for (int i = 0; i < 2; ++i)
+            if (cudaEventCreateWithFlags(&ss.join_ev[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        ss.ok = true;
+    }
+    return &ss;
+}
+struct Forker {
+    SideStreams* ss;
+    cudaStream_t main;
+    int n_forks = 0;
+    bool used[2] = {false, false};
+    Forker(cudaStream_t m) : ss(side_streams()), main(m) {}
+    // stream on which work that only depends on what `main` has enqueued so far may run
+    cudaStream_t fork(int which) {
+        if (!ss || n_forks >= 8) return main;
+        if (cudaEventRecord(ss->fork_ev[n_forks], main) != cudaSuccess) return main;
+        if (cudaStreamWaitEvent(ss->s[which], ss->fork_ev[n_forks], 0) != cudaSuccess) return main;
+        ++n_forks;
+        used[which] = true;
+        return ss->s[which];
+    }
+    int join() {
+        if (!ss) return MMS_OK;
+        for (int i = 0; i < 2; ++i)
+            if (used[i]) {
+                MMS_CUDA(cudaEventRecord(ss->join_ev[i], ss->s[i]));
+                MMS_CUDA(cudaStreamWaitEvent(main, ss->join_ev[i], 0));
+                used[i] = false;
+            }
+        return MMS_OK;
+    }
+};
+
+// C[m,n] = sum_k A[m,k] W[n,k] + bias[n]: tcgen05 (3xTF32) when the operands qualify, fp32 SIMT otherwise
+static int gemm_nt(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, float* C, int64_t ldc, int M, int N,
+                   int K, cudaStream_t st) {
+    if (use_tc() && M >= TC_MIN_ROWS && tc_gemm_supported(A, lda, W, ldw, M, N, K))
+        return launch_tc_gemm_nt(A, lda, W, ldw, bias, C, ldc, M, N, K, 0, st);
+    return launch_gemm_nt_bias(A, lda, W, ldw, bias, C, ldc, M, N, K, st);
+}
 
 struct Dims {
     int B, C, T, nc, O, H, layers, A;
@@ -120,6 +195,7 @@ struct Workspace {
     float *mean, *gate, *y1, *p1, *y2, *seq;
     float *gi[MAX_LAYERS], *hs[MAX_LAYERS], *outd[MAX_LAYERS], *stash[MAX_LAYERS];   // bottom layers
     float *gi_tf, *gi_tr, *hs_tf, *h_tr, *stash_tf, *stash_tr, *last, *hid;
+    float *wT_top, *wT[MAX_LAYERS];
     float *dhid, *dlogits, *D_tf, *D_tr, *D[MAX_LAYERS], *dxa, *dxb, *dy2, *dp1, *dy1, *ca_scratch;
     int64_t total;
 };
@@ -170,6 +246,8 @@ static void carve(const Dims& m, char* base, Workspace* w) {
         w->D_tr = (float*)take(B * 4 * H * f);
         for (int l = 0; l < m.layers - 1; ++l) w->D[l] = (float*)take(M * 8 * H * f);
         const int64_t widest = 2 * H > m.O ? 2 * H : m.O;
+        w->wT_top = (float*)take(2 * widest * 3 * H * f);
+        for (int l = 0; l < m.layers - 1; ++l) w->wT[l] = (float*)take(widest * 8 * H * f);
         w->dxa = (float*)take(M * widest * f);
         w->dxb = (float*)take(M * widest * f);
         w->dy2 = (float*)take(B * m.O * m.L2c * f);
@@ -215,7 +293,7 @@ static int model_forward(const mms_cnngru_desc* d, const float* x, const float* 
     const float* in = w.seq;
     int I = m.O;
     for (int l = 0; l < m.layers - 1; ++l) {
-        rc = launch_gemm_nt_bias(in, I, P + po.w_ih[l], I, P + po.b_ih[l], w.gi[l], 6 * H, (int)M, 6 * H, I, st);
+        rc = gemm_nt(in, I, P + po.w_ih[l], I, P + po.b_ih[l], w.gi[l], 6 * H, (int)M, 6 * H, I, st);
         if (rc) return rc;
         mms_gru_dir_fwd dirs[2];
         for (int dd = 0; dd < 2; ++dd) {
@@ -241,10 +319,10 @@ static int model_forward(const mms_cnngru_desc* d, const float* x, const float* 
     }
     {   // top layer: forward direction over the whole sequence, reverse direction for its first step only
         const int l = m.layers - 1;
-        rc = launch_gemm_nt_bias(in, I, P + po.w_ih[l], I, P + po.b_ih[l], w.gi_tf, 3 * H, (int)M, 3 * H, I, st);
+        rc = gemm_nt(in, I, P + po.w_ih[l], I, P + po.b_ih[l], w.gi_tf, 3 * H, (int)M, 3 * H, I, st);
         if (rc) return rc;
-        rc = launch_gemm_nt_bias(in + (int64_t)(L - 1) * I, (int64_t)L * I, P + po.w_ih[l] + (int64_t)3 * H * I, I,
-                                 P + po.b_ih[l] + 3 * H, w.gi_tr, 3 * H, B, 3 * H, I, st);
+        rc = gemm_nt(in + (int64_t)(L - 1) * I, (int64_t)L * I, P + po.w_ih[l] + (int64_t)3 * H * I, I,
+                     P + po.b_ih[l] + 3 * H, w.gi_tr, 3 * H, B, 3 * H, I, st);
         if (rc) return rc;
         mms_gru_dir_fwd dirs[2];
         memset(dirs, 0, sizeof(dirs));
@@ -283,6 +361,7 @@ static int model_backward(const mms_cnngru_desc* d, const float* x, const float*
     const float p = m.p;
 
     MMS_CUDA(cudaMemsetAsync(w.bwd_zero, 0, w.bwd_zero_bytes, st));
+    Forker fk(st);
     rc = launch_head_bwd(w.last, w.hid, dlogits, P + po.fc3_w, B, 2 * H, m.nc, m.drop_head ? p : 0.f, d->rng_seed, d->rng_offset,
                          d->rng_offset_dev, w.dhid, G + po.fc0_w, G + po.fc0_b, G + po.fc3_w, G + po.fc3_b, st);
     if (rc) return rc;
@@ -309,20 +388,30 @@ static int model_backward(const mms_cnngru_desc* d, const float* x, const float*
         dirs[1].t0 = L - 1; dirs[1].dt = -1; dirs[1].nsteps = 1;
         rc = launch_gru_bwd(dirs, 2, B, H, p, d->rng_seed, d->rng_offset, d->rng_offset_dev, st);
         if (rc) return rc;
-        // weight gradients of the top layer
-        rc = launch_gemm_tn_acc(w.D_tf, 4 * H, 3 * H, 0, in_top, I_top, 0, L, G + po.w_ih[top], I_top, G + po.b_ih[top], M, 3 * H, I_top, st);
+        // weight gradients of the top layer (off the critical path -> side stream)
+        cudaStream_t sw = fk.fork(0);
+        rc = launch_gemm_tn_acc(w.D_tf, 4 * H, 3 * H, 0, in_top, I_top, 0, L, G + po.w_ih[top], I_top, G + po.b_ih[top], M, 3 * H, I_top, sw);
         if (rc) return rc;
-        rc = launch_gemm_tn_acc(w.D_tf, 4 * H, 2 * H, H, w.hs_tf, H, -1, L, G + po.w_hh[top], H, G + po.b_hh[top], M, 3 * H, H, st);
+        rc = launch_gemm_tn_acc(w.D_tf, 4 * H, 2 * H, H, w.hs_tf, H, -1, L, G + po.w_hh[top], H, G + po.b_hh[top], M, 3 * H, H, sw);
         if (rc) return rc;
         rc = launch_gemm_tn_acc(w.D_tr, 4 * H, 3 * H, 0, in_top + (int64_t)(L - 1) * I_top, (int64_t)L * I_top, 0, 1,
-                                G + po.w_ih[top] + (int64_t)3 * H * I_top, I_top, G + po.b_ih[top] + 3 * H, B, 3 * H, I_top, st);
+                                G + po.w_ih[top] + (int64_t)3 * H * I_top, I_top, G + po.b_ih[top] + 3 * H, B, 3 * H, I_top, sw);
         if (rc) return rc;
         // h_prev = 0 for the single reverse step: dW_hh(reverse) = 0, only the bias gradient remains
-        rc = launch_gemm_tn_acc(w.D_tr, 4 * H, 2 * H, H, nullptr, 0, 0, 1, nullptr, 0, G + po.b_hh[top] + 3 * H, B, 3 * H, 0, st);
+        rc = launch_gemm_tn_acc(w.D_tr, 4 * H, 2 * H, H, nullptr, 0, 0, 1, nullptr, 0, G + po.b_hh[top] + 3 * H, B, 3 * H, 0, sw);
         if (rc) return rc;
         // gradient w.r.t. the top layer's input
-        rc = launch_gemm_nn(w.D_tf, 4 * H, P + po.w_ih[top], I_top, dxcur, I_top, M, I_top, 3 * H, 0, st);
-        if (rc) return rc;
+        if (use_tc() && M >= TC_MIN_ROWS && tc_gemm_supported(w.D_tf, 4 * H, w.wT_top, 3 * H, M, I_top, 3 * H)) {
+            // tensor-core path: dx = D @ W_ih as an NT product against the transposed weights
+            rc = launch_transpose_pad(P + po.w_ih[top], 3 * H, I_top, w.wT_top, 3 * H, 0, st);
+            if (rc) return rc;
+            rc = launch_tc_gemm_nt(w.D_tf, 4 * H, w.wT_top, 3 * H, nullptr, dxcur, I_top, M, I_top, 3 * H, 0, st);
+            if (rc) return rc;
+        } else {
+            rc = launch_gemm_nn(w.D_tf, 4 * H, P + po.w_ih[top], I_top, dxcur, I_top, M, I_top, 3 * H, 0, st);
+            if (rc) return rc;
+        }
+        // the single reverse step only touches the rows t = L-1 (B rows: SIMT, accumulate)
         rc = launch_gemm_nn(w.D_tr, 4 * H, P + po.w_ih[top] + (int64_t)3 * H * I_top, I_top, dxcur + (int64_t)(L - 1) * I_top,
                             (int64_t)L * I_top, B, I_top, 3 * H, 1, st);
         if (rc) return rc;
@@ -348,16 +437,31 @@ static int model_backward(const mms_cnngru_desc* d, const float* x, const float*
         }
         rc = launch_gru_bwd(dirs, 2, B, H, p, d->rng_seed, d->rng_offset, d->rng_offset_dev, st);
         if (rc) return rc;
+        cudaStream_t sw = fk.fork(1 - (l & 1));
         for (int dd = 0; dd < 2; ++dd) {
             const float* Dd = w.D[l] + dd * 4 * H;
             rc = launch_gemm_tn_acc(Dd, 8 * H, 3 * H, 0, in_l, I_l, 0, L, G + po.w_ih[l] + (int64_t)dd * 3 * H * I_l, I_l,
-                                    G + po.b_ih[l] + dd * 3 * H, M, 3 * H, I_l, st);
+                                    G + po.b_ih[l] + dd * 3 * H, M, 3 * H, I_l, sw);
             if (rc) return rc;
             rc = launch_gemm_tn_acc(Dd, 8 * H, 2 * H, H, w.hs[l] + dd * H, 2 * H, dd ? 1 : -1, L,
-                                    G + po.w_hh[l] + (int64_t)dd * 3 * H * H, H, G + po.b_hh[l] + dd * 3 * H, M, 3 * H, H, st);
+                                    G + po.w_hh[l] + (int64_t)dd * 3 * H * H, H, G + po.b_hh[l] + dd * 3 * H, M, 3 * H, H, sw);
             if (rc) return rc;
-            rc = launch_gemm_nn(Dd, 8 * H, P + po.w_ih[l] + (int64_t)dd * 3 * H * I_l, I_l, dxnext, I_l, M, I_l, 3 * H, dd, st);
+        }
+        if (use_tc() && M >= TC_MIN_ROWS && tc_gemm_supported(w.D[l], 8 * H, w.wT[l], 8 * H, M, I_l, 8 * H)) {
+            // both directions in one NT product: K = [fwd 3H | (dq) | rev 3H | (dq)], zero weights on the dq columns
+            MMS_CUDA(cudaMemsetAsync(w.wT[l], 0, (size_t)I_l * 8 * H * sizeof(float), st));
+            for (int dd = 0; dd < 2; ++dd) {
+                rc = launch_transpose_pad(P + po.w_ih[l] + (int64_t)dd * 3 * H * I_l, 3 * H, I_l, w.wT[l], 8 * H, dd * 4 * H, st);
+                if (rc) return rc;
+            }
+            rc = launch_tc_gemm_nt(w.D[l], 8 * H, w.wT[l], 8 * H, nullptr, dxnext, I_l, M, I_l, 8 * H, 0, st);
             if (rc) return rc;
+        } else {
+            for (int dd = 0; dd < 2; ++dd) {
+                rc = launch_gemm_nn(w.D[l] + dd * 4 * H, 8 * H, P + po.w_ih[l] + (int64_t)dd * 3 * H * I_l, I_l, dxnext, I_l, M, I_l,
+                                    3 * H, dd, st);
+                if (rc) return rc;
+            }
         }
         float* t = dxcur; dxcur = dxnext; dxnext = t;
     }
@@ -365,14 +469,14 @@ static int model_backward(const mms_cnngru_desc* d, const float* x, const float*
     rc = launch_bn_relu_pool_bwd(w.y2, w.stats2, P + po.bn2_g, P + po.bn2_b, rm2, rv2, dxcur, B, m.O, m.L2c, m.training, 1, w.dy2,
                                  G + po.bn2_g, G + po.bn2_b, w.red2, st);
     if (rc) return rc;
-    rc = launch_conv_wgrad(2, w.p1, w.dy2, nullptr, B, CONV2_CI, m.O, m.P1, G + po.conv2_w, st);
+    rc = launch_conv_wgrad(2, w.p1, w.dy2, nullptr, B, CONV2_CI, m.O, m.P1, G + po.conv2_w, fk.fork(0));
     if (rc) return rc;
     rc = launch_conv_dgrad(2, w.dy2, P + po.conv2_w, B, CONV2_CI, m.O, m.P1, w.dp1, nullptr, nullptr, st);
     if (rc) return rc;
     rc = launch_bn_relu_pool_bwd(w.y1, w.stats1, P + po.bn1_g, P + po.bn1_b, rm1, rv1, w.dp1, B, CONV1_CO, m.L1c, m.training, 0,
                                  w.dy1, G + po.bn1_g, G + po.bn1_b, w.red1, st);
     if (rc) return rc;
-    rc = launch_conv_wgrad(1, x, w.dy1, m.attention ? w.gate : nullptr, B, m.C, CONV1_CO, m.T, G + po.conv1_w, st);
+    rc = launch_conv_wgrad(1, x, w.dy1, m.attention ? w.gate : nullptr, B, m.C, CONV1_CO, m.T, G + po.conv1_w, fk.fork(1));
     if (rc) return rc;
     if (m.attention) {
         if (m.A > 0 || dx) {
@@ -392,7 +496,7 @@ static int model_backward(const mms_cnngru_desc* d, const float* x, const float*
         rc = launch_conv_dgrad(1, w.dy1, P + po.conv1_w, B, m.C, CONV1_CO, m.T, dx, nullptr, nullptr, st);
         if (rc) return rc;
     }
-    return MMS_OK;
+    return fk.join();       // every gradient is complete before the caller's next kernel (Adam)
 }
 
 }  // namespace mms

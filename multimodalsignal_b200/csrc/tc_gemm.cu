@@ -331,6 +331,27 @@ int launch_tc_gemm_nt(const float* A, int64_t lda, const float* W, int64_t ldw, 
     return MMS_OK;
 }
 
+// out[c * ldo + col_off + r] = W[r * cols + c]   (W is [rows, cols] row-major)
+__global__ void __launch_bounds__(256) transpose_pad_kernel(const float* __restrict__ W, int rows, int cols, float* __restrict__ out,
+                                                            int64_t ldo, int col_off) {
+    __shared__ float tile[32][33];
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int i = ty; i < 32; i += 8)
+        if (r0 + i < rows && c0 + tx < cols) tile[i][tx] = __ldg(W + (int64_t)(r0 + i) * cols + c0 + tx);
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8)
+        if (c0 + i < cols && r0 + tx < rows) out[(int64_t)(c0 + i) * ldo + col_off + r0 + tx] = tile[tx][i];
+}
+
+int launch_transpose_pad(const float* W, int rows, int cols, float* out, int64_t ldo, int col_off, cudaStream_t st) {
+    dim3 grid(cdiv(cols, 32), cdiv(rows, 32));
+    MMS_PROF_BEGIN(st);
+    transpose_pad_kernel<<<grid, 256, 0, st>>>(W, rows, cols, out, ldo, col_off);
+    MMS_LAUNCH_CHECK("transpose_pad_kernel");
+    return MMS_OK;
+}
+
 }  // namespace mms
 
 using namespace mms;
