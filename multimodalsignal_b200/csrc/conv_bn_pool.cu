@@ -105,6 +105,15 @@ __device__ __forceinline__ BnAffine bn_affine(int training, const double* stats,
     return r;
 }
 
+// Block-uniform version: thread 0 does the float64 arithmetic once, everybody reads shared memory.
+__device__ __forceinline__ BnAffine bn_affine_block(int training, const double* stats, const float* gamma, const float* beta,
+                                                    const float* rm, const float* rv, int c, int C, double n) {
+    __shared__ BnAffine s_af;
+    if (threadIdx.x == 0) s_af = bn_affine(training, stats, gamma, beta, rm, rv, c, C, n);
+    __syncthreads();
+    return s_af;
+}
+
 __device__ __forceinline__ void bn_running_update(const double* stats, float* rm, float* rv, int64_t* nbt, int C,
                                                   double n, int tid) {
     if (tid < C) {
@@ -135,7 +144,7 @@ __global__ void __launch_bounds__(256) bn_relu_pool_fwd_ncl_kernel(const float* 
                                                                    int Lout, int training, float* __restrict__ out) {
     const int c = blockIdx.y, b = blockIdx.z;
     const double n = (double)B * (double)Lin;
-    const BnAffine af = bn_affine(training, stats, gamma, beta, rm, rv, c, C, n);
+    const BnAffine af = bn_affine_block(training, stats, gamma, beta, rm, rv, c, C, n);
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j < Lout) {
         const float* row = y + ((size_t)b * C + c) * Lin;
@@ -190,7 +199,7 @@ __global__ void __launch_bounds__(256) pool_relu_bwd_kernel(const float* __restr
     __shared__ double part[8][2];
     const int c = blockIdx.y, b = blockIdx.z;
     const double n = (double)B * (double)Lin;
-    const BnAffine af = bn_affine(training, stats, gamma, beta, rm, rv, c, C, n);
+    const BnAffine af = bn_affine_block(training, stats, gamma, beta, rm, rv, c, C, n);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     float dyn = 0.f, xhat = 0.f;
     if (i < Lin) {
@@ -248,7 +257,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
                                                            float* __restrict__ dbeta) {
     const int c = blockIdx.y, b = blockIdx.z;
     const double n = (double)B * (double)Lin;
-    const BnAffine af = bn_affine(training, stats, gamma, beta, rm, rv, c, C, n);
+    const BnAffine af = bn_affine_block(training, stats, gamma, beta, rm, rv, c, C, n);
     const float m1 = training ? (float)(red[c] / n) : 0.f;
     const float m2 = training ? (float)(red[C + c] / n) : 0.f;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -16,7 +16,10 @@
 //     lanes of a quad hit distinct banks (conflict-free 128-bit loads);
 //   * every global address is a running pointer (no 64-bit multiplies in the loop) and everything a
 //     step needs from global memory (input projections, stashed gates, upstream gradients) is
-//     prefetched PF steps ahead into registers;
+//     prefetched: the forward uses a shared-memory ring filled PF-1 steps ahead with cp.async (a register
+//     ring was collapsed to a distance of one step by the compiler's scheduler; wait_group pins the
+//     distance); the backward keeps a register ring, which measured faster there (six values per step
+//     and a shorter gate chain leave no slack to hide the extra shared-memory round trip);
 //   * sigmoid / tanh use the ex2 / rcp special-function units (|error| ~ 2e-7, far inside the
 //     1e-4 logit tolerance);
 //   * inter-layer dropout is NOT applied here: a 30-instruction hash per element inside an in-order
@@ -51,6 +54,15 @@ __device__ __forceinline__ float fast_sigmoid(float x) { return rcp_ftz(1.f + ex
 __device__ __forceinline__ float fast_tanh(float x) { return fmaf(2.f, fast_sigmoid(2.f * x), -1.f); }
 
 __device__ __forceinline__ float2 bcast2(float v) { return make_float2(v, v); }
+
+// 16-byte asynchronous global -> shared copy (LDGSTS): the prefetch distance is then fixed by
+// cp.async.wait_group and cannot be shortened by the compiler's scheduling of register loads.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // padded position of element k of an H-vector split into quarters of KS floats
 template <int KS>
@@ -89,7 +101,6 @@ __global__ void __launch_bounds__(2 * H) gru_fwd_kernel(const GruFwdParams prm) 
 
     // running pointers (advance by dt * stride per step); loads clamp the row, stores are guarded
     const int64_t gi_step = (int64_t)d.dt * d.gi_ts, hs_step = (int64_t)d.dt * d.hs_ts, st_step = (int64_t)d.dt * d.st_ts;
-    const float* gi_p[R];
     float* hs_p[R];
     float* st_p[R];         // first lane: stash slots 0,1 (r, z); second lane: slots 2,3 (n, W_hn h + b_hn)
     bool live[R];
@@ -97,23 +108,31 @@ __global__ void __launch_bounds__(2 * H) gru_fwd_kernel(const GruFwdParams prm) 
     for (int r = 0; r < R; ++r) {
         const int bb = min(b0 + r, B - 1);
         live[r] = (b0 + r) < B;
-        gi_p[r] = d.gi + (int64_t)bb * d.gi_bs + (int64_t)d.t0 * d.gi_ts + ju;
         hs_p[r] = d.hs + (int64_t)bb * d.hs_bs + (int64_t)d.t0 * d.hs_ts + ju;
         st_p[r] = do_stash ? d.stash + (int64_t)bb * d.st_bs + (int64_t)d.t0 * d.st_ts + (first ? 0 : 2 * H) + ju : nullptr;
     }
     float* const h_wr = &hsm[0][0][0] + padded<KS>(ju);      // + (buffer * R + r) * HPAD
 
-    // ring of input projections (r, z, n of unit ju), PF steps ahead
-    float ring[PF][R][3];
+    // Ring of input projections in shared memory, PF steps ahead: threads 0 .. 3H/4-1 each copy 16 bytes
+    // of the 3H-float row of step s + PF with cp.async; one commit group per step.
+    __shared__ __align__(16) float gsm[PF][R][3 * H];
+    constexpr int NCP = 3 * H / 4;
+    const float* gi_src[R];
 #pragma unroll
-    for (int u = 0; u < PF; ++u)
+    for (int r = 0; r < R; ++r)
+        gi_src[r] = d.gi + (int64_t)min(b0 + r, B - 1) * d.gi_bs + (int64_t)d.t0 * d.gi_ts + 4 * (tid < NCP ? tid : 0);
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
+    for (int u = 0; u < PF; ++u) {
+        if (tid < NCP && u < nsteps) {
 #pragma unroll
-            for (int g = 0; g < 3; ++g) ring[u][r][g] = __ldg(gi_p[r] + g * H);
-            if (u + 1 < nsteps) gi_p[r] += gi_step;      // never step past the last valid time index
+            for (int r = 0; r < R; ++r) {
+                cp_async16(&gsm[u][r][4 * tid], gi_src[r]);
+                gi_src[r] += gi_step;
+            }
         }
-    int loaded = min(PF, nsteps);                        // number of distinct steps already requested
+        cp_async_commit();
+    }
+    cp_async_wait<PF - 1>();          // step 0 has landed (for the copying threads); the barrier publishes it
     __syncthreads();
 
     int cur = 0;
@@ -121,22 +140,28 @@ __global__ void __launch_bounds__(2 * H) gru_fwd_kernel(const GruFwdParams prm) 
 #pragma unroll
         for (int u = 0; u < PF; ++u) {
             if (s0 + u >= nsteps) break;
+            {   // Refill the slot that was read in the PREVIOUS step (all of its readers are past the barrier that
+                // ended that step) with step s - 1 + PF; one commit group per step keeps the group count uniform.
+                const int s = s0 + u;
+                const int PREV = (u + PF - 1) % PF;
+                if (tid < NCP && s >= 1 && s - 1 + PF < nsteps) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        cp_async16(&gsm[PREV][r][4 * tid], gi_src[r]);
+                        gi_src[r] += gi_step;
+                    }
+                }
+                cp_async_commit();
+            }
             float gi[R][3];
 #pragma unroll
             for (int r = 0; r < R; ++r)
 #pragma unroll
-                for (int g = 0; g < 3; ++g) {
-                    gi[r][g] = ring[u][r][g];
-                    ring[u][r][g] = __ldg(gi_p[r] + g * H);   // step s + PF (a harmless re-read at the tail)
-                }
-            if (loaded + 1 < nsteps) {
-#pragma unroll
-                for (int r = 0; r < R; ++r) gi_p[r] += gi_step;
-            }
-            ++loaded;
+                for (int g = 0; g < 3; ++g) gi[r][g] = gsm[u][r][g * H + ju];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 float2 acc[3] = {bh2[0], bh2[1], bh2[2]};
+                const float hp = h_wr[(cur * R + r) * HPAD];                   // h_{t-1}[ju], off the dependent chain
                 const float4* hv = reinterpret_cast<const float4*>(&hsm[cur][r][q * (KS + 4)]);
 #pragma unroll
                 for (int i4 = 0; i4 < KS / 4; ++i4) {
@@ -164,7 +189,6 @@ __global__ void __launch_bounds__(2 * H) gru_fwd_kernel(const GruFwdParams prm) 
                 const float rg = fast_sigmoid(sg[0] + gi[r][0]);
                 const float zg = fast_sigmoid(sg[1] + gi[r][1]);
                 const float ng = fast_tanh(fmaf(rg, sg[2], gi[r][2]));
-                const float hp = h_wr[(cur * R + r) * HPAD];
                 const float hn = fmaf(zg, hp - ng, ng);                        // (1-z)*n + z*h
                 if (first) h_wr[((cur ^ 1) * R + r) * HPAD] = hn;
                 if (first && live[r]) *hs_p[r] = hn;
@@ -175,7 +199,8 @@ __global__ void __launch_bounds__(2 * H) gru_fwd_kernel(const GruFwdParams prm) 
                 hs_p[r] += hs_step;
                 st_p[r] += st_step;
             }
-            __syncthreads();
+            cp_async_wait<PF - 2>();      // the copies for step s + 1 are complete for the copying threads ...
+            __syncthreads();              // ... and, with h[cur^1], visible to every thread
             cur ^= 1;
         }
     }
@@ -378,6 +403,8 @@ int launch_gru_fwd(const mms_gru_dir_fwd* dirs, int ndirs, int B, int H, float p
         prm.dir[i] = dirs[i];
         MMS_REQUIRE(dirs[i].gi && dirs[i].w_hh && dirs[i].b_hh && dirs[i].hs && dirs[i].nsteps >= 1, "gru_recur_fwd: null pointer / no steps");
         MMS_REQUIRE(!dirs[i].hs_drop, "gru_recur_fwd: hs_drop is no longer written by the recurrence; use mms_dropout_apply");
+        MMS_REQUIRE((reinterpret_cast<uintptr_t>(dirs[i].gi) & 15) == 0 && dirs[i].gi_bs % 4 == 0 && dirs[i].gi_ts % 4 == 0,
+                    "gru_recur_fwd: gi must be 16-byte aligned with strides that are multiples of 4 floats");
     }
     for (int i = ndirs; i < GRU_MAX_DIRS; ++i) prm.dir[i] = dirs[0];
     prm.B = B; prm.p = p; prm.seed = seed; prm.offset = offset; prm.offset_dev = offset_dev;

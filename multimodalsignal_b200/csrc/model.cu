@@ -92,15 +92,16 @@ struct Forker {
         used[which] = true;
         return ss->s[which];
     }
-    int join() {
-        if (!ss) return MMS_OK;
-        for (int i = 0; i < 2; ++i)
-            if (used[i]) {
-                MMS_CUDA(cudaEventRecord(ss->join_ev[i], ss->s[i]));
-                MMS_CUDA(cudaStreamWaitEvent(main, ss->join_ev[i], 0));
-                used[i] = false;
-            }
+    int join_one(int i) {
+        if (!ss || !used[i]) return MMS_OK;
+        MMS_CUDA(cudaEventRecord(ss->join_ev[i], ss->s[i]));
+        MMS_CUDA(cudaStreamWaitEvent(main, ss->join_ev[i], 0));
+        used[i] = false;
         return MMS_OK;
+    }
+    int join() {
+        int rc = join_one(0);
+        return rc ? rc : join_one(1);
     }
 };
 
@@ -362,6 +363,23 @@ static int model_backward(const mms_cnngru_desc* d, const float* x, const float*
 
     MMS_CUDA(cudaMemsetAsync(w.bwd_zero, 0, w.bwd_zero_bytes, st));
     Forker fk(st);
+    const bool tc_bwd = use_tc() && M >= TC_MIN_ROWS;
+    if (tc_bwd) {
+        // W_ih^T (zero-padded over the dq columns for the bottom layers) for the tensor-core dx products:
+        // side stream, hidden behind the head backward and the top-layer recurrence
+        cudaStream_t sw = fk.fork(1);
+        const int I_t = m.layers == 1 ? m.O : 2 * H;
+        rc = launch_transpose_pad(P + po.w_ih[m.layers - 1], 3 * H, I_t, w.wT_top, 3 * H, 0, sw);
+        if (rc) return rc;
+        for (int l = 0; l < m.layers - 1; ++l) {
+            const int I_l = l == 0 ? m.O : 2 * H;
+            MMS_CUDA(cudaMemsetAsync(w.wT[l], 0, (size_t)I_l * 8 * H * sizeof(float), sw));
+            for (int dd = 0; dd < 2; ++dd) {
+                rc = launch_transpose_pad(P + po.w_ih[l] + (int64_t)dd * 3 * H * I_l, 3 * H, I_l, w.wT[l], 8 * H, dd * 4 * H, sw);
+                if (rc) return rc;
+            }
+        }
+    }
     rc = launch_head_bwd(w.last, w.hid, dlogits, P + po.fc3_w, B, 2 * H, m.nc, m.drop_head ? p : 0.f, d->rng_seed, d->rng_offset,
                          d->rng_offset_dev, w.dhid, G + po.fc0_w, G + po.fc0_b, G + po.fc3_w, G + po.fc3_b, st);
     if (rc) return rc;
@@ -401,9 +419,9 @@ static int model_backward(const mms_cnngru_desc* d, const float* x, const float*
         rc = launch_gemm_tn_acc(w.D_tr, 4 * H, 2 * H, H, nullptr, 0, 0, 1, nullptr, 0, G + po.b_hh[top] + 3 * H, B, 3 * H, 0, sw);
         if (rc) return rc;
         // gradient w.r.t. the top layer's input
-        if (use_tc() && M >= TC_MIN_ROWS && tc_gemm_supported(w.D_tf, 4 * H, w.wT_top, 3 * H, M, I_top, 3 * H)) {
+        if (tc_bwd && tc_gemm_supported(w.D_tf, 4 * H, w.wT_top, 3 * H, M, I_top, 3 * H)) {
             // tensor-core path: dx = D @ W_ih as an NT product against the transposed weights
-            rc = launch_transpose_pad(P + po.w_ih[top], 3 * H, I_top, w.wT_top, 3 * H, 0, st);
+            rc = fk.join_one(1);          // the transposed weights (side stream 1) are needed from here on
             if (rc) return rc;
             rc = launch_tc_gemm_nt(w.D_tf, 4 * H, w.wT_top, 3 * H, nullptr, dxcur, I_top, M, I_top, 3 * H, 0, st);
             if (rc) return rc;
@@ -447,13 +465,8 @@ static int model_backward(const mms_cnngru_desc* d, const float* x, const float*
                                     G + po.w_hh[l] + (int64_t)dd * 3 * H * H, H, G + po.b_hh[l] + dd * 3 * H, M, 3 * H, H, sw);
             if (rc) return rc;
         }
-        if (use_tc() && M >= TC_MIN_ROWS && tc_gemm_supported(w.D[l], 8 * H, w.wT[l], 8 * H, M, I_l, 8 * H)) {
+        if (tc_bwd && tc_gemm_supported(w.D[l], 8 * H, w.wT[l], 8 * H, M, I_l, 8 * H)) {
             // both directions in one NT product: K = [fwd 3H | (dq) | rev 3H | (dq)], zero weights on the dq columns
-            MMS_CUDA(cudaMemsetAsync(w.wT[l], 0, (size_t)I_l * 8 * H * sizeof(float), st));
-            for (int dd = 0; dd < 2; ++dd) {
-                rc = launch_transpose_pad(P + po.w_ih[l] + (int64_t)dd * 3 * H * I_l, 3 * H, I_l, w.wT[l], 8 * H, dd * 4 * H, st);
-                if (rc) return rc;
-            }
             rc = launch_tc_gemm_nt(w.D[l], 8 * H, w.wT[l], 8 * H, nullptr, dxnext, I_l, M, I_l, 8 * H, 0, st);
             if (rc) return rc;
         } else {
