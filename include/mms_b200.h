@@ -49,6 +49,10 @@ int mms_init(int device);
 int64_t mms_launch_count(void);
 int mms_profile_enable(int32_t on);
 int mms_profile_report(char* buf_host, int64_t buf_bytes);
+/* Weight-gradient kernels normally run on two library-owned side streams (forked from and joined
+ * back into the caller's stream, also under CUDA-graph capture).  0 serialises everything on the
+ * caller's stream (used while per-kernel times are taken); also MMS_DISABLE_STREAMS=1. */
+int mms_set_side_streams(int32_t on);
 
 /* ------------------------------------------------------------------------------------------
  * Model description (reference models.py:39-40 constructor arguments + call-time facts).

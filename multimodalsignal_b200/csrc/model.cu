@@ -58,11 +58,11 @@ struct SideStreams {
     cudaEvent_t fork_ev[8] = {}, join_ev[2] = {};
     bool ok = false;
 };
+static int g_streams_disabled = -1;
 static SideStreams* side_streams() {
     static SideStreams per_dev[16];
-    static int disabled = -1;
-    if (disabled < 0) { const char* e = getenv("MMS_DISABLE_STREAMS"); disabled = (e && e[0] == '1') ? 1 : 0; }
-    if (disabled) return nullptr;
+    if (g_streams_disabled < 0) { const char* e = getenv("MMS_DISABLE_STREAMS"); g_streams_disabled = (e && e[0] == '1') ? 1 : 0; }
+    if (g_streams_disabled) return nullptr;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
     SideStreams& ss = per_dev[dev];
@@ -530,6 +530,11 @@ extern "C" int mms_cnngru_param_layout(const mms_cnngru_desc* d, int64_t* offset
     }
     if (total_floats_host) *total_floats_host = po.total;
     return po.nseg;
+}
+
+extern "C" int mms_set_side_streams(int32_t on) {
+    g_streams_disabled = on ? 0 : 1;
+    return MMS_OK;
 }
 
 extern "C" int64_t mms_cnngru_workspace_bytes(const mms_cnngru_desc* d) {

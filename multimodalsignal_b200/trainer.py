@@ -146,6 +146,44 @@ class FusedTrainStep:
         self.x.copy_(x, non_blocking=True)
         self.y.copy_(y, non_blocking=True)
 
+    # ---- double-buffered input pipeline: the H2D copy of batch i+1 overlaps the step of batch i ----------
+    def _pipeline(self):
+        if getattr(self, "_copy_stream", None) is None:
+            dev = self.x.device
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._stage_x = [torch.empty_like(self.x) for _ in range(2)]
+            self._stage_y = [torch.empty_like(self.y) for _ in range(2)]
+            self._ready = [torch.cuda.Event() for _ in range(2)]
+            self._consumed = [torch.cuda.Event() for _ in range(2)]
+            self._queued, self._next_slot = [], 0
+        return self._copy_stream
+
+    def prefetch(self, x, y):
+        """Enqueue the host->device copy of an upcoming batch on the copy stream (staging slot)."""
+        cs = self._pipeline()
+        slot = self._next_slot
+        cs.wait_event(self._consumed[slot])            # the step that last read this slot has copied it out
+        if x.is_cuda:                                  # device-resident batch: produced on the current stream
+            cs.wait_stream(torch.cuda.current_stream())
+            x.record_stream(cs)
+            y.record_stream(cs)
+        with torch.cuda.stream(cs):
+            self._stage_x[slot].copy_(x, non_blocking=True)
+            self._stage_y[slot].copy_(y, non_blocking=True)
+            self._ready[slot].record(cs)
+        self._queued.append(slot)
+        self._next_slot ^= 1
+
+    def run_prefetched(self):
+        """Run one step on the oldest prefetched batch (device-to-device hand-over, then the graph)."""
+        slot = self._queued.pop(0)
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._ready[slot])
+        self.x.copy_(self._stage_x[slot], non_blocking=True)
+        self.y.copy_(self._stage_y[slot], non_blocking=True)
+        self._consumed[slot].record(cur)
+        self.run()
+
     def run(self):
         """Enqueue one step on the static inputs (graph replay after the first two calls)."""
         if self.model.flat_parameters().data_ptr() != self.flat.data_ptr():
@@ -161,6 +199,25 @@ class FusedTrainStep:
                 self._enqueue()
             self.graph = graph
         self.graph.replay()
+
+    def post_loss(self):
+        """Enqueue an asynchronous device->host copy of this step's loss into a pinned two-slot ring
+        and return a ticket; ``read_loss(ticket)`` waits for exactly that copy.  Lets a caller read
+        every step's loss (as reference trainer.py:152 does) one step late, so the GPU never idles
+        while Python enqueues the next step."""
+        if getattr(self, "_loss_host", None) is None:
+            self._loss_host = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+            self._loss_ev = [torch.cuda.Event() for _ in range(2)]
+            self._loss_slot = 0
+        k = self._loss_slot
+        self._loss_host[k].copy_(self.loss, non_blocking=True)
+        self._loss_ev[k].record(torch.cuda.current_stream())
+        self._loss_slot ^= 1
+        return k
+
+    def read_loss(self, ticket) -> float:
+        self._loss_ev[ticket].synchronize()
+        return float(self._loss_host[ticket][0])
 
     def __call__(self, x, y):
         self.load(x, y)
@@ -239,6 +296,11 @@ class Trainer:
             self._steps[key] = FusedTrainStep(self.model, self.optimizer, batch, seq_len, use_graph=self.use_graph)
         return self._steps[key]
 
+    @staticmethod
+    def _check_batch(batch):
+        if isinstance(batch[0], (list, tuple)):
+            raise NotImplementedError("HybridDataset inputs (reference void/dataset.py) are out of scope")
+
     def _loss_sum(self):
         return sum(float(s.loss_sum.item()) for s in self._steps.values())
 
@@ -249,11 +311,21 @@ class Trainer:
             self.model.train()
             for s in self._steps.values():
                 s.loss_sum.zero_()
-            for inputs, labels in train_loader:
-                if isinstance(inputs, (list, tuple)):
-                    raise NotImplementedError("HybridDataset inputs (reference void/dataset.py) are out of scope")
+            # trainer.py:130-149 with a one-batch look-ahead: the H2D copy of the next batch runs on a copy
+            # stream while the current step (one CUDA-graph replay) executes
+            it = iter(train_loader)
+            nxt = next(it, None)
+            if nxt is not None:
+                self._check_batch(nxt)
+                self._fused(nxt[0].shape[0], nxt[0].shape[2]).prefetch(*nxt)
+            while nxt is not None:
+                inputs, labels = nxt
                 step = self._fused(inputs.shape[0], inputs.shape[2])
-                step(inputs, labels)                       # trainer.py:140-149 in one graph replay
+                nxt = next(it, None)
+                if nxt is not None:
+                    self._check_batch(nxt)
+                    self._fused(nxt[0].shape[0], nxt[0].shape[2]).prefetch(*nxt)
+                step.run_prefetched()
                 self.windows_trained += inputs.shape[0]
             train_loss = self._loss_sum()                  # one sync per epoch instead of two per step
             epoch_duration = time.time() - t0
