@@ -75,6 +75,9 @@ typedef struct {
     uint64_t rng_offset;    /* dropout stream offset used when rng_offset_dev == NULL   */
     const int64_t* rng_offset_dev; /* optional device counter read by the kernels
                                       (the fused train step passes its Adam step count) */
+    int32_t global_batch;   /* 0 or == batch: single GPU.  > batch: intra-fold data parallelism -- BatchNorm
+                               statistics are counted over the global batch (SyncBN) and the BN affine
+                               gradients are scaled by batch/global_batch so that a sum all-reduce is exact */
 } mms_cnngru_desc;
 
 /* Flat parameter buffer.  The model's parameters live in ONE float32 buffer so that Adam and
@@ -111,6 +114,26 @@ int mms_cnngru_forward(const mms_cnngru_desc* d, const float* x, const float* pa
 int mms_cnngru_backward(const mms_cnngru_desc* d, const float* x, const float* params,
                         const float* bn_buffers, void* workspace, const float* dlogits,
                         float* grads, float* dx, mms_stream_t stream);
+
+/* Data-parallel form of the two calls above (intra-fold DP).  `phases` is a bit mask:
+ *   forward : 1 = gate + conv1 (+BN1 sums) | 2 = BN1/pool1 + conv2 (+BN2 sums) | 4 = the rest
+ *   backward: 1 = head..GRU..stage-2 pool/ReLU backward (+BN2 reductions) | 2 = stage-2 BN apply, conv2
+ *             gradients, stage-1 pool/ReLU backward (+BN1 reductions) | 4 = the rest
+ * Between the phases the caller sum-all-reduces the float64 vectors whose byte offsets inside the
+ * workspace mms_cnngru_sync_offsets() reports: [0] BN1 sums, [1] BN2 sums (forward), [2] BN1
+ * reductions, [3] BN2 reductions (backward); counts are in doubles.  desc.global_batch must be set. */
+int mms_cnngru_forward_phase(const mms_cnngru_desc* d, int32_t phases, const float* x, const float* params,
+                             float* bn_buffers, int64_t* num_batches_tracked, void* workspace, float* logits,
+                             mms_stream_t stream);
+int mms_cnngru_backward_phase(const mms_cnngru_desc* d, int32_t phases, const float* x, const float* params,
+                              const float* bn_buffers, void* workspace, const float* dlogits, float* grads,
+                              mms_stream_t stream);
+int mms_cnngru_sync_offsets(const mms_cnngru_desc* d, int64_t* byte_offsets_host, int64_t* counts_host);
+/* Cross entropy of a rank's share of a global batch: loss_out = sum_local(...)/global_batch (the per-rank
+ * values add up to the global mean), dlogits = (softmax - onehot)/global_batch. */
+int mms_cross_entropy_partial(const float* logits, const int64_t* labels, int32_t batch, int32_t num_classes,
+                              int32_t global_batch, float* loss_out, float* dlogits, double* loss_sum_accum,
+                              mms_stream_t stream);
 
 /* trainer.py:69,147 CrossEntropyLoss() (mean): loss_out[0] = mean_b(lse - logit[y]),
  * dlogits = (softmax - onehot)/B (NULL to skip).  If loss_sum_accum != NULL it receives

@@ -33,6 +33,7 @@ class CnnGruDesc(C.Structure):
         ("cnn_out", c_i32), ("hidden", c_i32), ("layers", c_i32), ("training", c_i32),
         ("attention", c_i32), ("need_grad", c_i32), ("dropout_p", c_f32),
         ("rng_seed", c_u64), ("rng_offset", c_u64), ("rng_offset_dev", C.c_void_p),
+        ("global_batch", c_i32),
     ]
 
 
@@ -74,6 +75,10 @@ _SIGNATURES = {
     "mms_cnngru_forward": (c_i32, [C.POINTER(CnnGruDesc), P, P, P, P, P, P, P]),
     "mms_cnngru_backward": (c_i32, [C.POINTER(CnnGruDesc), P, P, P, P, P, P, P, P]),
     "mms_cross_entropy": (c_i32, [P, P, c_i32, c_i32, P, P, P, P]),
+    "mms_cross_entropy_partial": (c_i32, [P, P, c_i32, c_i32, c_i32, P, P, P, P]),
+    "mms_cnngru_forward_phase": (c_i32, [C.POINTER(CnnGruDesc), c_i32, P, P, P, P, P, P, P]),
+    "mms_cnngru_backward_phase": (c_i32, [C.POINTER(CnnGruDesc), c_i32, P, P, P, P, P, P, P]),
+    "mms_cnngru_sync_offsets": (c_i32, [C.POINTER(CnnGruDesc), C.POINTER(c_i64), C.POINTER(c_i64)]),
     "mms_adam_flat_step": (c_i32, [P, P, P, P, c_i64, P, c_f32, c_f32, c_f32, c_f32, P, P, P]),
     "mms_cnngru_train_step": (c_i32, [C.POINTER(CnnGruDesc), P, P, P, P, P, P, P, P, P, P, P, P, P,
                                       c_f32, c_f32, c_f32, c_f32, P, P, P]),

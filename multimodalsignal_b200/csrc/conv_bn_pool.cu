@@ -140,10 +140,10 @@ __device__ __forceinline__ float pooled_value(const float* __restrict__ row, int
 // out[b,c,j] (channel-major)       grid = (ceil(Lout/256), C, B), block = 256
 __global__ void __launch_bounds__(256) bn_relu_pool_fwd_ncl_kernel(const float* __restrict__ y, const double* __restrict__ stats,
                                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                                   float* rm, float* rv, int64_t* nbt, int B, int C, int Lin,
+                                                                   float* rm, float* rv, int64_t* nbt, int Bn, int C, int Lin,
                                                                    int Lout, int training, float* __restrict__ out) {
     const int c = blockIdx.y, b = blockIdx.z;
-    const double n = (double)B * (double)Lin;
+    const double n = (double)Bn * (double)Lin;
     const BnAffine af = bn_affine_block(training, stats, gamma, beta, rm, rv, c, C, n);
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j < Lout) {
@@ -159,13 +159,13 @@ __global__ void __launch_bounds__(256) bn_relu_pool_fwd_ncl_kernel(const float* 
 // out[b,j,c] (time-major)          grid = (ceil(Lout/32), B), block = 256, C <= 64
 __global__ void __launch_bounds__(256) bn_relu_pool_fwd_tm_kernel(const float* __restrict__ y, const double* __restrict__ stats,
                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                                  float* rm, float* rv, int64_t* nbt, int B, int C, int Lin,
+                                                                  float* rm, float* rv, int64_t* nbt, int Bn, int C, int Lin,
                                                                   int Lout, int training, float* __restrict__ out) {
     __shared__ float tile[32][65];
     __shared__ float sa[64], sb[64];
     const int b = blockIdx.y, j0 = blockIdx.x * 32;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const double n = (double)B * (double)Lin;
+    const double n = (double)Bn * (double)Lin;
     if (threadIdx.x < C) {
         const BnAffine af = bn_affine(training, stats, gamma, beta, rm, rv, threadIdx.x, C, n);
         sa[threadIdx.x] = af.a;
@@ -193,12 +193,12 @@ __global__ void __launch_bounds__(256) bn_relu_pool_fwd_tm_kernel(const float* _
 __global__ void __launch_bounds__(256) pool_relu_bwd_kernel(const float* __restrict__ y, const double* __restrict__ stats,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             const float* __restrict__ rm, const float* __restrict__ rv,
-                                                            const float* __restrict__ dout, int B, int C, int Lin, int Lout,
+                                                            const float* __restrict__ dout, int Bn, int C, int Lin, int Lout,
                                                             int training, int time_major, float* __restrict__ dy,
                                                             double* __restrict__ red) {
     __shared__ double part[8][2];
     const int c = blockIdx.y, b = blockIdx.z;
-    const double n = (double)B * (double)Lin;
+    const double n = (double)Bn * (double)Lin;
     const BnAffine af = bn_affine_block(training, stats, gamma, beta, rm, rv, c, C, n);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     float dyn = 0.f, xhat = 0.f;
@@ -252,11 +252,11 @@ __global__ void __launch_bounds__(256) pool_relu_bwd_kernel(const float* __restr
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restrict__ y, const double* __restrict__ stats,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            const float* __restrict__ rm, const float* __restrict__ rv,
-                                                           const double* __restrict__ red, int B, int C, int Lin, int training,
+                                                           const double* __restrict__ red, int Bn, int C, int Lin, int training,
                                                            float* __restrict__ dy, float* __restrict__ dgamma,
-                                                           float* __restrict__ dbeta) {
+                                                           float* __restrict__ dbeta, float grad_scale) {
     const int c = blockIdx.y, b = blockIdx.z;
-    const double n = (double)B * (double)Lin;
+    const double n = (double)Bn * (double)Lin;
     const BnAffine af = bn_affine_block(training, stats, gamma, beta, rm, rv, c, C, n);
     const float m1 = training ? (float)(red[c] / n) : 0.f;
     const float m2 = training ? (float)(red[C + c] / n) : 0.f;
@@ -267,8 +267,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
         dy[idx] = af.a * (dy[idx] - m1 - xhat * m2);
     }
     if (blockIdx.x == 0 && b == 0 && threadIdx.x == 0) {
-        dgamma[c] += (float)red[C + c];
-        dbeta[c] += (float)red[c];
+        dgamma[c] += grad_scale * (float)red[C + c];     // grad_scale = 1/world under data parallelism: every
+        dbeta[c] += grad_scale * (float)red[c];          // rank holds the GLOBAL sums, the all-reduce adds them up
     }
 }
 
@@ -479,35 +479,44 @@ int launch_conv_wgrad(int which, const float* x, const float* dy, const float* g
 
 int launch_bn_relu_pool_fwd(const float* y, const double* stats, const float* gamma, const float* beta, float* rm,
                             float* rv, int64_t* nbt, int B, int C, int l_in, int training, int time_major, float* out,
-                            cudaStream_t st) {
+                            cudaStream_t st, int Bstat = 0) {
+    if (Bstat <= 0) Bstat = B;        // batch the statistics were reduced over (global batch under data parallelism)
     const int Lout = pool_out_len(l_in);
     MMS_REQUIRE(C >= 1 && C <= 64, "bn_relu_pool: channels %d outside [1,64]", C);
     MMS_REQUIRE(!training || stats, "bn_relu_pool: training mode needs batch statistics");
     if (time_major) {
         dim3 grid(cdiv(Lout, 32), B);
         MMS_PROF_BEGIN(st);
-        bn_relu_pool_fwd_tm_kernel<<<grid, 256, 0, st>>>(y, stats, gamma, beta, rm, rv, nbt, B, C, l_in, Lout, training, out);
+        bn_relu_pool_fwd_tm_kernel<<<grid, 256, 0, st>>>(y, stats, gamma, beta, rm, rv, nbt, Bstat, C, l_in, Lout, training, out);
     } else {
         dim3 grid(cdiv(Lout, 256), C, B);
         MMS_PROF_BEGIN(st);
-        bn_relu_pool_fwd_ncl_kernel<<<grid, 256, 0, st>>>(y, stats, gamma, beta, rm, rv, nbt, B, C, l_in, Lout, training, out);
+        bn_relu_pool_fwd_ncl_kernel<<<grid, 256, 0, st>>>(y, stats, gamma, beta, rm, rv, nbt, Bstat, C, l_in, Lout, training, out);
     }
     MMS_LAUNCH_CHECK("bn_relu_pool_fwd");
     return MMS_OK;
 }
 
+// which: bit 0 = pool/ReLU backward + the two BN reductions into `red`; bit 1 = BN apply (+ dgamma, dbeta).
+// Under data parallelism the caller all-reduces `red` between the two.
 int launch_bn_relu_pool_bwd(const float* y, const double* stats, const float* gamma, const float* beta, const float* rm,
                             const float* rv, const float* dout, int B, int C, int l_in, int training, int time_major,
-                            float* dy, float* dgamma, float* dbeta, double* red, cudaStream_t st) {
+                            float* dy, float* dgamma, float* dbeta, double* red, cudaStream_t st, int which = 3, int Bstat = 0,
+                            float grad_scale = 1.f) {
     const int Lout = pool_out_len(l_in);
+    if (Bstat <= 0) Bstat = B;
     MMS_REQUIRE(C >= 1 && C <= 64, "bn_relu_pool_bwd: channels %d outside [1,64]", C);
     dim3 grid(cdiv(l_in, 256), C, B);
-    MMS_PROF_BEGIN(st);
-    pool_relu_bwd_kernel<<<grid, 256, 0, st>>>(y, stats, gamma, beta, rm, rv, dout, B, C, l_in, Lout, training, time_major, dy, red);
-    MMS_LAUNCH_CHECK("pool_relu_bwd_kernel");
-    MMS_PROF_BEGIN(st);
-    bn_bwd_apply_kernel<<<grid, 256, 0, st>>>(y, stats, gamma, beta, rm, rv, red, B, C, l_in, training, dy, dgamma, dbeta);
-    MMS_LAUNCH_CHECK("bn_bwd_apply_kernel");
+    if (which & 1) {
+        MMS_PROF_BEGIN(st);
+        pool_relu_bwd_kernel<<<grid, 256, 0, st>>>(y, stats, gamma, beta, rm, rv, dout, Bstat, C, l_in, Lout, training, time_major, dy, red);
+        MMS_LAUNCH_CHECK("pool_relu_bwd_kernel");
+    }
+    if (which & 2) {
+        MMS_PROF_BEGIN(st);
+        bn_bwd_apply_kernel<<<grid, 256, 0, st>>>(y, stats, gamma, beta, rm, rv, red, Bstat, C, l_in, training, dy, dgamma, dbeta, grad_scale);
+        MMS_LAUNCH_CHECK("bn_bwd_apply_kernel");
+    }
     return MMS_OK;
 }
 

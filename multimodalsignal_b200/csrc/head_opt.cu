@@ -109,10 +109,11 @@ __global__ void __launch_bounds__(128) head_bwd_kernel(const float* __restrict__
 // Single CTA.  loss_out[0] = mean_b(lse_b - logit[b, y_b]); dlogits = (softmax - onehot) / B.
 __global__ void __launch_bounds__(256) cross_entropy_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels,
                                                             int B, int nc, float* __restrict__ loss_out,
-                                                            float* __restrict__ dlogits, double* __restrict__ loss_sum_accum) {
+                                                            float* __restrict__ dlogits, double* __restrict__ loss_sum_accum,
+                                                            int div_batch) {
     __shared__ float s_part[8];
     float local = 0.f;
-    const float invB = 1.f / (float)B;
+    const float invB = 1.f / (float)div_batch;     // global batch under data parallelism: the per-rank losses add up
     for (int b = threadIdx.x; b < B; b += blockDim.x) {
         float v[MAX_NC];
         float mx = -INFINITY;
@@ -133,7 +134,7 @@ __global__ void __launch_bounds__(256) cross_entropy_kernel(const float* __restr
         for (int w = 0; w < (blockDim.x >> 5); ++w) s += s_part[w];
         const float mean = s * invB;
         loss_out[0] = mean;
-        if (loss_sum_accum) *loss_sum_accum += (double)mean * (double)B;
+        if (loss_sum_accum) *loss_sum_accum += (double)mean * (double)div_batch;
     }
 }
 
@@ -202,10 +203,11 @@ int launch_head_bwd(const float* last, const float* hid, const float* dlogits, c
 }
 
 int launch_cross_entropy(const float* logits, const int64_t* labels, int B, int nc, float* loss_out, float* dlogits,
-                         double* loss_sum_accum, cudaStream_t st) {
+                         double* loss_sum_accum, cudaStream_t st, int div_batch = 0) {
+    if (div_batch <= 0) div_batch = B;
     MMS_REQUIRE(nc >= 1 && nc <= MAX_NC, "cross_entropy: num_classes %d outside [1,%d]", nc, MAX_NC);
     MMS_PROF_BEGIN(st);
-    cross_entropy_kernel<<<1, 256, 0, st>>>(logits, labels, B, nc, loss_out, dlogits, loss_sum_accum);
+    cross_entropy_kernel<<<1, 256, 0, st>>>(logits, labels, B, nc, loss_out, dlogits, loss_sum_accum, div_batch);
     MMS_LAUNCH_CHECK("cross_entropy_kernel");
     return MMS_OK;
 }
@@ -240,7 +242,13 @@ extern "C" int mms_head_bwd(const float* last, const float* hid, const float* dl
 extern "C" int mms_cross_entropy(const float* logits, const int64_t* labels, int32_t batch, int32_t num_classes, float* loss_out,
                                  float* dlogits, double* loss_sum_accum, mms_stream_t stream) {
     MMS_REQUIRE(logits && labels && loss_out && batch > 0, "cross_entropy: bad arguments");
-    return launch_cross_entropy(logits, labels, batch, num_classes, loss_out, dlogits, loss_sum_accum, (cudaStream_t)stream);
+    return launch_cross_entropy(logits, labels, batch, num_classes, loss_out, dlogits, loss_sum_accum, (cudaStream_t)stream, batch);
+}
+extern "C" int mms_cross_entropy_partial(const float* logits, const int64_t* labels, int32_t batch, int32_t num_classes,
+                                         int32_t global_batch, float* loss_out, float* dlogits, double* loss_sum_accum,
+                                         mms_stream_t stream) {
+    MMS_REQUIRE(logits && labels && loss_out && batch > 0 && global_batch >= batch, "cross_entropy_partial: bad arguments");
+    return launch_cross_entropy(logits, labels, batch, num_classes, loss_out, dlogits, loss_sum_accum, (cudaStream_t)stream, global_batch);
 }
 extern "C" int mms_adam_flat_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                                   const float* lr_dev, float beta1, float beta2, float eps, float weight_decay, int64_t* step_dev,

@@ -16,9 +16,9 @@ int launch_conv_fwd(int, const float*, const float*, const float*, int, int, int
 int launch_conv_dgrad(int, const float*, const float*, int, int, int, int, float*, const float*, float*, cudaStream_t);
 int launch_conv_wgrad(int, const float*, const float*, const float*, int, int, int, int, float*, cudaStream_t);
 int launch_bn_relu_pool_fwd(const float*, const double*, const float*, const float*, float*, float*, int64_t*, int, int, int, int,
-                            int, float*, cudaStream_t);
+                            int, float*, cudaStream_t, int Bstat);
 int launch_bn_relu_pool_bwd(const float*, const double*, const float*, const float*, const float*, const float*, const float*, int,
-                            int, int, int, int, float*, float*, float*, double*, cudaStream_t);
+                            int, int, int, int, float*, float*, float*, double*, cudaStream_t, int which, int Bstat, float grad_scale);
 int launch_gemm_nt_bias(const float*, int64_t, const float*, int64_t, const float*, float*, int64_t, int, int, int, cudaStream_t);
 int launch_gemm_nn(const float*, int64_t, const float*, int64_t, float*, int64_t, int, int, int, int, cudaStream_t);
 int launch_gemm_tn_acc(const float*, int64_t, int, int, const float*, int64_t, int, int, float*, int64_t, float*, int, int, int,
@@ -29,7 +29,7 @@ int launch_head_fwd2(const float*, int64_t, const float*, int64_t, int, const fl
                      int, int, float, uint64_t, uint64_t, const int64_t*, float*, float*, float*, cudaStream_t);
 int launch_head_bwd(const float*, const float*, const float*, const float*, int, int, int, float, uint64_t, uint64_t,
                     const int64_t*, float*, float*, float*, float*, float*, cudaStream_t);
-int launch_cross_entropy(const float*, const int64_t*, int, int, float*, float*, double*, cudaStream_t);
+int launch_cross_entropy(const float*, const int64_t*, int, int, float*, float*, double*, cudaStream_t, int div_batch);
 int launch_adam(float*, const float*, float*, float*, int64_t, const float*, float, float, float, float, int64_t*, int32_t*,
                 cudaStream_t);
 int launch_chan_dx(const float*, const float*, const float*, int, int, int, float*, cudaStream_t);
@@ -114,7 +114,7 @@ static int gemm_nt(const float* A, int64_t lda, const float* W, int64_t ldw, con
 }
 
 struct Dims {
-    int B, C, T, nc, O, H, layers, A;
+    int B, Bg, C, T, nc, O, H, layers, A;      // Bg: global batch (== B unless data-parallel)
     int L1c, P1, L2c, L;   // conv1 out, pool1 out, conv2 out, pool2 out (= GRU sequence length)
     bool training, attention, need_grad, drop_gru, drop_head;
     float p;
@@ -125,6 +125,8 @@ static int make_dims(const mms_cnngru_desc* d, Dims* o) {
     o->B = d->batch; o->C = d->in_channels; o->T = d->seq_len; o->nc = d->num_classes; o->O = d->cnn_out;
     o->H = d->hidden; o->layers = d->layers; o->A = d->in_channels / 4;
     MMS_REQUIRE(o->B >= 1, "batch must be >= 1 (got %d)", o->B);
+    o->Bg = d->global_batch > 0 ? d->global_batch : o->B;
+    MMS_REQUIRE(o->Bg >= o->B, "global_batch %d smaller than the local batch %d", o->Bg, o->B);
     MMS_REQUIRE(o->C >= 1 && o->C <= 16, "in_channels %d outside [1,16]", o->C);
     MMS_REQUIRE(o->nc >= 1 && o->nc <= 8, "num_classes %d outside [1,8]", o->nc);
     MMS_REQUIRE(o->O == 16 || o->O == 32 || o->O == 64, "cnn_out_channels %d not in {16,32,64}", o->O);
@@ -259,8 +261,10 @@ static void carve(const Dims& m, char* base, Workspace* w) {
     w->total = cur;
 }
 
+// phases: bit 0 = gate + conv1 (+ BN1 batch sums), bit 1 = BN1/pool1 + conv2 (+ BN2 sums), bit 2 = the rest.
+// A data-parallel caller all-reduces the float64 BN sums between the phases (SyncBN); 7 = everything.
 static int model_forward(const mms_cnngru_desc* d, const float* x, const float* P, float* bn, int64_t* nbt, void* ws,
-                         float* logits, cudaStream_t st) {
+                         float* logits, cudaStream_t st, int phases = 7) {
     Dims m;
     int rc = make_dims(d, &m);
     if (rc) return rc;
@@ -274,21 +278,25 @@ static int model_forward(const mms_cnngru_desc* d, const float* x, const float* 
     const int64_t M = (int64_t)B * L;
     float *rm1 = bn, *rv1 = bn + CONV1_CO, *rm2 = bn + 2 * CONV1_CO, *rv2 = bn + 2 * CONV1_CO + m.O;
 
-    MMS_CUDA(cudaMemsetAsync(w.fwd_zero, 0, w.fwd_zero_bytes, st));
-    const float* gate = nullptr;
-    if (m.attention) {
-        rc = launch_chan_gate(x, P + po.ca_w1, P + po.ca_w2, B, m.C, m.T, w.mean, w.gate, st);
+    const float* gate = m.attention ? w.gate : nullptr;
+    if (phases & 1) {
+        MMS_CUDA(cudaMemsetAsync(w.fwd_zero, 0, w.fwd_zero_bytes, st));
+        if (m.attention) {
+            rc = launch_chan_gate(x, P + po.ca_w1, P + po.ca_w2, B, m.C, m.T, w.mean, w.gate, st);
+            if (rc) return rc;
+        }
+        rc = launch_conv_fwd(1, x, P + po.conv1_w, gate, B, m.C, CONV1_CO, m.T, w.y1, m.training ? w.stats1 : nullptr, st);
         if (rc) return rc;
-        gate = w.gate;
     }
-    rc = launch_conv_fwd(1, x, P + po.conv1_w, gate, B, m.C, CONV1_CO, m.T, w.y1, m.training ? w.stats1 : nullptr, st);
-    if (rc) return rc;
-    rc = launch_bn_relu_pool_fwd(w.y1, w.stats1, P + po.bn1_g, P + po.bn1_b, rm1, rv1, nbt, B, CONV1_CO, m.L1c, m.training, 0, w.p1, st);
-    if (rc) return rc;
-    rc = launch_conv_fwd(2, w.p1, P + po.conv2_w, nullptr, B, CONV2_CI, m.O, m.P1, w.y2, m.training ? w.stats2 : nullptr, st);
-    if (rc) return rc;
+    if (phases & 2) {
+        rc = launch_bn_relu_pool_fwd(w.y1, w.stats1, P + po.bn1_g, P + po.bn1_b, rm1, rv1, nbt, B, CONV1_CO, m.L1c, m.training, 0, w.p1, st, m.Bg);
+        if (rc) return rc;
+        rc = launch_conv_fwd(2, w.p1, P + po.conv2_w, nullptr, B, CONV2_CI, m.O, m.P1, w.y2, m.training ? w.stats2 : nullptr, st);
+        if (rc) return rc;
+    }
+    if (!(phases & 4)) return MMS_OK;
     rc = launch_bn_relu_pool_fwd(w.y2, w.stats2, P + po.bn2_g, P + po.bn2_b, rm2, rv2, nbt ? nbt + 1 : nullptr, B, m.O, m.L2c,
-                                 m.training, 1, w.seq, st);
+                                 m.training, 1, w.seq, st, m.Bg);
     if (rc) return rc;
 
     const float* in = w.seq;
@@ -345,8 +353,11 @@ static int model_forward(const mms_cnngru_desc* d, const float* x, const float* 
                             w.last, w.hid, logits, st);
 }
 
+// phases: bit 0 = head ... GRU ... pool/ReLU backward of stage 2 (+ its BN reductions), bit 1 = BN apply of stage 2,
+// conv2 gradients, pool/ReLU backward of stage 1 (+ reductions), bit 2 = the rest.  A data-parallel caller
+// all-reduces the float64 reductions between the phases; 7 = everything.
 static int model_backward(const mms_cnngru_desc* d, const float* x, const float* P, const float* bn, void* ws,
-                          const float* dlogits, float* G, float* dx, cudaStream_t st) {
+                          const float* dlogits, float* G, float* dx, cudaStream_t st, int phases = 7) {
     Dims m;
     int rc = make_dims(d, &m);
     if (rc) return rc;
@@ -361,8 +372,10 @@ static int model_backward(const mms_cnngru_desc* d, const float* x, const float*
     const float *rm1 = bn, *rv1 = bn + CONV1_CO, *rm2 = bn + 2 * CONV1_CO, *rv2 = bn + 2 * CONV1_CO + m.O;
     const float p = m.p;
 
-    MMS_CUDA(cudaMemsetAsync(w.bwd_zero, 0, w.bwd_zero_bytes, st));
+    const float gscale = (float)m.B / (float)m.Bg;       // share of the global BN affine gradient this rank adds
     Forker fk(st);
+    if (phases & 1) {
+    MMS_CUDA(cudaMemsetAsync(w.bwd_zero, 0, w.bwd_zero_bytes, st));
     const bool tc_bwd = use_tc() && M >= TC_MIN_ROWS;
     if (tc_bwd) {
         // W_ih^T (zero-padded over the dq columns for the bottom layers) for the tensor-core dx products:
@@ -480,14 +493,24 @@ static int model_backward(const mms_cnngru_desc* d, const float* x, const float*
     }
     // dxcur = d(seq) [B, L, O] time-major
     rc = launch_bn_relu_pool_bwd(w.y2, w.stats2, P + po.bn2_g, P + po.bn2_b, rm2, rv2, dxcur, B, m.O, m.L2c, m.training, 1, w.dy2,
-                                 G + po.bn2_g, G + po.bn2_b, w.red2, st);
+                                 G + po.bn2_g, G + po.bn2_b, w.red2, st, 1, m.Bg, gscale);
     if (rc) return rc;
-    rc = launch_conv_wgrad(2, w.p1, w.dy2, nullptr, B, CONV2_CI, m.O, m.P1, G + po.conv2_w, fk.fork(0));
-    if (rc) return rc;
-    rc = launch_conv_dgrad(2, w.dy2, P + po.conv2_w, B, CONV2_CI, m.O, m.P1, w.dp1, nullptr, nullptr, st);
-    if (rc) return rc;
-    rc = launch_bn_relu_pool_bwd(w.y1, w.stats1, P + po.bn1_g, P + po.bn1_b, rm1, rv1, w.dp1, B, CONV1_CO, m.L1c, m.training, 0,
-                                 w.dy1, G + po.bn1_g, G + po.bn1_b, w.red1, st);
+    }   // phase bit 0
+    if (phases & 2) {
+        rc = launch_bn_relu_pool_bwd(w.y2, w.stats2, P + po.bn2_g, P + po.bn2_b, rm2, rv2, nullptr, B, m.O, m.L2c, m.training, 1, w.dy2,
+                                     G + po.bn2_g, G + po.bn2_b, w.red2, st, 2, m.Bg, gscale);
+        if (rc) return rc;
+        rc = launch_conv_wgrad(2, w.p1, w.dy2, nullptr, B, CONV2_CI, m.O, m.P1, G + po.conv2_w, fk.fork(0));
+        if (rc) return rc;
+        rc = launch_conv_dgrad(2, w.dy2, P + po.conv2_w, B, CONV2_CI, m.O, m.P1, w.dp1, nullptr, nullptr, st);
+        if (rc) return rc;
+        rc = launch_bn_relu_pool_bwd(w.y1, w.stats1, P + po.bn1_g, P + po.bn1_b, rm1, rv1, w.dp1, B, CONV1_CO, m.L1c, m.training, 0,
+                                     w.dy1, G + po.bn1_g, G + po.bn1_b, w.red1, st, 1, m.Bg, gscale);
+        if (rc) return rc;
+    }
+    if (!(phases & 4)) return fk.join();
+    rc = launch_bn_relu_pool_bwd(w.y1, w.stats1, P + po.bn1_g, P + po.bn1_b, rm1, rv1, nullptr, B, CONV1_CO, m.L1c, m.training, 0,
+                                 w.dy1, G + po.bn1_g, G + po.bn1_b, w.red1, st, 2, m.Bg, gscale);
     if (rc) return rc;
     rc = launch_conv_wgrad(1, x, w.dy1, m.attention ? w.gate : nullptr, B, m.C, CONV1_CO, m.T, G + po.conv1_w, fk.fork(1));
     if (rc) return rc;
@@ -555,6 +578,35 @@ extern "C" int mms_cnngru_backward(const mms_cnngru_desc* d, const float* x, con
     return model_backward(d, x, params, bn_buffers, workspace, dlogits, grads, dx, (cudaStream_t)stream);
 }
 
+extern "C" int mms_cnngru_forward_phase(const mms_cnngru_desc* d, int32_t phases, const float* x, const float* params,
+                                        float* bn_buffers, int64_t* num_batches_tracked, void* workspace, float* logits,
+                                        mms_stream_t stream) {
+    MMS_REQUIRE(phases >= 1 && phases <= 7, "forward_phase: phases must be a mask in [1,7]");
+    return model_forward(d, x, params, bn_buffers, num_batches_tracked, workspace, logits, (cudaStream_t)stream, phases);
+}
+
+extern "C" int mms_cnngru_backward_phase(const mms_cnngru_desc* d, int32_t phases, const float* x, const float* params,
+                                         const float* bn_buffers, void* workspace, const float* dlogits, float* grads,
+                                         mms_stream_t stream) {
+    MMS_REQUIRE(phases >= 1 && phases <= 7, "backward_phase: phases must be a mask in [1,7]");
+    return model_backward(d, x, params, bn_buffers, workspace, dlogits, grads, nullptr, (cudaStream_t)stream, phases);
+}
+
+extern "C" int mms_cnngru_sync_offsets(const mms_cnngru_desc* d, int64_t* byte_offsets_host, int64_t* counts_host) {
+    Dims m;
+    int rc = make_dims(d, &m);
+    if (rc) return rc;
+    MMS_REQUIRE(byte_offsets_host && counts_host, "sync_offsets: null pointer");
+    Workspace w;
+    char* base = reinterpret_cast<char*>(4096);          // any non-null base: only differences are used
+    carve(m, base, &w);
+    byte_offsets_host[0] = (char*)w.stats1 - base; counts_host[0] = 2 * CONV1_CO;
+    byte_offsets_host[1] = (char*)w.stats2 - base; counts_host[1] = 2 * m.O;
+    byte_offsets_host[2] = (char*)w.red1 - base;   counts_host[2] = 2 * CONV1_CO;
+    byte_offsets_host[3] = (char*)w.red2 - base;   counts_host[3] = 2 * m.O;
+    return MMS_OK;
+}
+
 extern "C" int mms_cnngru_train_step(const mms_cnngru_desc* d, const float* x, const int64_t* labels, float* params, float* grads,
                                      float* exp_avg, float* exp_avg_sq, float* bn_buffers, int64_t* num_batches_tracked,
                                      void* workspace, float* logits, float* loss_out, double* loss_sum_accum, const float* lr_dev,
@@ -573,7 +625,7 @@ extern "C" int mms_cnngru_train_step(const mms_cnngru_desc* d, const float* x, c
     MMS_CUDA(cudaMemsetAsync(grads, 0, po.total * sizeof(float), st));                      // trainer.py:144
     rc = model_forward(d, x, params, bn_buffers, num_batches_tracked, workspace, logits, st);  // trainer.py:146
     if (rc) return rc;
-    rc = launch_cross_entropy(logits, labels, m.B, m.nc, loss_out, w.dlogits, loss_sum_accum, st);  // trainer.py:147
+    rc = launch_cross_entropy(logits, labels, m.B, m.nc, loss_out, w.dlogits, loss_sum_accum, st, m.Bg);  // trainer.py:147
     if (rc) return rc;
     rc = model_backward(d, x, params, bn_buffers, workspace, w.dlogits, grads, nullptr, st);        // trainer.py:148
     if (rc) return rc;
