@@ -27,6 +27,7 @@ __global__ void __launch_bounds__(TL) conv1d_fwd_kernel(const float* __restrict_
     const int b = blockIdx.y, l0 = blockIdx.x * TL, tid = threadIdx.x;
     const int in0 = l0 * S - P;
     const float* xb = x + (size_t)b * CI * Lin;
+#pragma unroll 4
     for (int idx = tid; idx < CI * SPAN; idx += TL) {
         const int c = idx / SPAN, i = idx - c * SPAN, gi = in0 + i;
         xs[idx] = (gi >= 0 && gi < Lin) ? __ldg(xb + (size_t)c * Lin + gi) : 0.f;
@@ -137,23 +138,42 @@ __device__ __forceinline__ float pooled_value(const float* __restrict__ row, int
     return m;
 }
 
-// out[b,c,j] (channel-major)       grid = (ceil(Lout/256), C, B), block = 256
+// Stage one row of y in shared memory as z = relu(a*y + b) with 128-bit loads where possible.
+__device__ __forceinline__ void stage_row_relu(const float* __restrict__ row, int Lin, float a, float bsh, float* __restrict__ zs) {
+    if ((Lin & 3) == 0 && (reinterpret_cast<uintptr_t>(row) & 15) == 0) {
+        const float4* r4 = reinterpret_cast<const float4*>(row);
+        for (int i = threadIdx.x; i < (Lin >> 2); i += blockDim.x) {
+            const float4 v = __ldg(r4 + i);
+            float4 z;
+            z.x = fmaxf(fmaf(a, v.x, bsh), 0.f); z.y = fmaxf(fmaf(a, v.y, bsh), 0.f);
+            z.z = fmaxf(fmaf(a, v.z, bsh), 0.f); z.w = fmaxf(fmaf(a, v.w, bsh), 0.f);
+            reinterpret_cast<float4*>(zs)[i] = z;
+        }
+    } else {
+        for (int i = threadIdx.x; i < Lin; i += blockDim.x) zs[i] = fmaxf(fmaf(a, __ldg(row + i), bsh), 0.f);
+    }
+}
+
+// out[b,c,j] (channel-major)       grid = (C, B), block = 256, dynamic smem = Lin floats: one CTA per row
 __global__ void __launch_bounds__(256) bn_relu_pool_fwd_ncl_kernel(const float* __restrict__ y, const double* __restrict__ stats,
                                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                    float* rm, float* rv, int64_t* nbt, int Bn, int C, int Lin,
                                                                    int Lout, int training, float* __restrict__ out) {
-    const int c = blockIdx.y, b = blockIdx.z;
+    extern __shared__ __align__(16) float zs[];
+    const int c = blockIdx.x, b = blockIdx.y;
     const double n = (double)Bn * (double)Lin;
     const BnAffine af = bn_affine_block(training, stats, gamma, beta, rm, rv, c, C, n);
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < Lout) {
-        const float* row = y + ((size_t)b * C + c) * Lin;
-        out[((size_t)b * C + c) * Lout + j] = pooled_value(row, j, Lin, af.a, af.b);
+    stage_row_relu(y + ((size_t)b * C + c) * Lin, Lin, af.a, af.b, zs);
+    __syncthreads();
+    float* orow = out + ((size_t)b * C + c) * Lout;
+    for (int j = threadIdx.x; j < Lout; j += blockDim.x) {
+        const int i = 2 * j;
+        float m = zs[i];
+        if (i - 1 >= 0) m = fmaxf(m, zs[i - 1]);
+        if (i + 1 < Lin) m = fmaxf(m, zs[i + 1]);
+        orow[j] = m;
     }
-    if (training && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
-        __syncthreads();
-        bn_running_update(stats, rm, rv, nbt, C, n, threadIdx.x);
-    }
+    if (training && blockIdx.x == 0 && blockIdx.y == 0) bn_running_update(stats, rm, rv, nbt, C, n, threadIdx.x);
 }
 
 // out[b,j,c] (time-major)          grid = (ceil(Lout/32), B), block = 256, C <= 64
@@ -189,55 +209,62 @@ __global__ void __launch_bounds__(256) bn_relu_pool_fwd_tm_kernel(const float* _
 }
 
 // ---- backward pass A: d(pool) -> d(relu) -> dyn, plus the two BN reductions --------------------
-// grid = (ceil(Lin/256), C, B), block = 256.  dyn is written to dy.
+// grid = (C, B), block = 256, dynamic smem = (Lin + Lout) floats: one CTA per (b, c) row -> 128-bit row loads and
+// one pair of float64 atomics per row (was per 256 elements).  dyn is written to dy.
 __global__ void __launch_bounds__(256) pool_relu_bwd_kernel(const float* __restrict__ y, const double* __restrict__ stats,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             const float* __restrict__ rm, const float* __restrict__ rv,
                                                             const float* __restrict__ dout, int Bn, int C, int Lin, int Lout,
                                                             int training, int time_major, float* __restrict__ dy,
                                                             double* __restrict__ red) {
+    extern __shared__ __align__(16) float bsm[];
+    float* zs = bsm;                 // [Lin]  relu(bn(y))
+    float* ds = bsm + ((Lin + 3) & ~3);   // [Lout] upstream gradient of this row
     __shared__ double part[8][2];
-    const int c = blockIdx.y, b = blockIdx.z;
+    const int c = blockIdx.x, b = blockIdx.y;
     const double n = (double)Bn * (double)Lin;
     const BnAffine af = bn_affine_block(training, stats, gamma, beta, rm, rv, c, C, n);
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    float dyn = 0.f, xhat = 0.f;
-    if (i < Lin) {
-        const float* row = y + ((size_t)b * C + c) * Lin;
-        float z[5];
-#pragma unroll
-        for (int e = 0; e < 5; ++e) {
-            const int ii = i - 2 + e;
-            z[e] = (ii >= 0 && ii < Lin) ? fmaxf(fmaf(af.a, __ldg(row + ii), af.b), 0.f) : -INFINITY;
-        }
-        // windows that contain i: centre j=i/2 for even i; j=(i+1)/2 (i is element 0) and
-        // j=(i-1)/2 (i is element 2) for odd i.  First maximal element wins (ATen: val > maxval).
-        float dsum = 0.f;
-        int js[2], nj = 0;
-        if ((i & 1) == 0) { js[nj++] = i >> 1; }
-        else { js[nj++] = (i + 1) >> 1; js[nj++] = (i - 1) >> 1; }
-        for (int q = 0; q < nj; ++q) {
-            const int j = js[q];
-            if (j < 0 || j >= Lout) continue;
-            float best = -INFINITY;
-            int arg = -1;
-#pragma unroll
-            for (int e = 0; e < 3; ++e) {
-                const int ii = 2 * j - 1 + e;
-                if (ii < 0 || ii >= Lin) continue;
-                const float v = z[ii - i + 2];
-                if (v > best || arg < 0) { if (v > best || arg < 0) { best = v; arg = ii; } }
-            }
-            if (arg == i) {
-                const size_t di = time_major ? ((size_t)b * Lout + j) * C + c : ((size_t)b * C + c) * Lout + j;
-                dsum += __ldg(dout + di);
-            }
-        }
-        dyn = z[2] > 0.f ? dsum : 0.f;
-        xhat = (__ldg(row + i) - af.mean) * af.inv;
-        dy[((size_t)b * C + c) * Lin + i] = dyn;
+    const float* row = y + ((size_t)b * C + c) * Lin;
+    stage_row_relu(row, Lin, af.a, af.b, zs);
+    if (time_major) {
+        for (int j = threadIdx.x; j < Lout; j += blockDim.x) ds[j] = __ldg(dout + ((size_t)b * Lout + j) * C + c);
+    } else {
+        const float* drow = dout + ((size_t)b * C + c) * Lout;
+        for (int j = threadIdx.x; j < Lout; j += blockDim.x) ds[j] = __ldg(drow + j);
     }
-    const float s1 = warp_sum(dyn), s2 = warp_sum(dyn * xhat);
+    __syncthreads();
+    float s1 = 0.f, s2 = 0.f;
+    float* dyrow = dy + ((size_t)b * C + c) * Lin;
+    for (int i = threadIdx.x; i < Lin; i += blockDim.x) {
+        // windows that contain i: centre j = i/2 for even i; j = (i+1)/2 (i is element 0) and j = (i-1)/2 (i is
+        // element 2) for odd i.  First maximal element wins (ATen: val > maxval), -inf padding never wins.
+        const float zi = zs[i];
+        float dsum = 0.f;
+        if ((i & 1) == 0) {
+            const int j = i >> 1;                       // window (i-1, i, i+1)
+            const bool left_wins = i - 1 >= 0 && zs[i - 1] >= zi;       // an earlier element with the same value wins
+            const bool right_wins = i + 1 < Lin && zs[i + 1] > zi;
+            if (j < Lout && !left_wins && !right_wins) dsum += ds[j];
+        } else {
+            const int ja = (i + 1) >> 1;                // window (i, i+1, i+2): i is the first element
+            if (ja < Lout) {
+                const bool lose = (i + 1 < Lin && zs[i + 1] > zi) || (i + 2 < Lin && zs[i + 2] > zi);
+                if (!lose) dsum += ds[ja];
+            }
+            const int jb = (i - 1) >> 1;                // window (i-2, i-1, i): i is the last element
+            if (jb < Lout) {
+                const bool lose = (i - 2 >= 0 && zs[i - 2] >= zi) || zs[i - 1] >= zi;
+                if (!lose) dsum += ds[jb];
+            }
+        }
+        const float dyn = zi > 0.f ? dsum : 0.f;
+        const float xhat = (__ldg(row + i) - af.mean) * af.inv;
+        dyrow[i] = dyn;
+        s1 += dyn;
+        s2 += dyn * xhat;
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (lane == 0) { part[warp][0] = (double)s1; part[warp][1] = (double)s2; }
     __syncthreads();
@@ -249,6 +276,7 @@ __global__ void __launch_bounds__(256) pool_relu_bwd_kernel(const float* __restr
 }
 
 // ---- backward pass B: BN input gradient in place, dgamma / dbeta ---------------------------
+// grid = (ceil(Lin/1024), C, B), block = 256: four elements per thread, 128-bit loads / stores
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restrict__ y, const double* __restrict__ stats,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            const float* __restrict__ rm, const float* __restrict__ rv,
@@ -260,11 +288,24 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
     const BnAffine af = bn_affine_block(training, stats, gamma, beta, rm, rv, c, C, n);
     const float m1 = training ? (float)(red[c] / n) : 0.f;
     const float m2 = training ? (float)(red[C + c] / n) : 0.f;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < Lin) {
-        const size_t idx = ((size_t)b * C + c) * Lin + i;
-        const float xhat = (__ldg(y + idx) - af.mean) * af.inv;
-        dy[idx] = af.a * (dy[idx] - m1 - xhat * m2);
+    const size_t base = ((size_t)b * C + c) * Lin;
+    const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const bool vec = (Lin & 3) == 0 && ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dy)) & 15) == 0;
+    if (vec) {
+        if (i0 < Lin) {
+            const float4 yv = __ldg(reinterpret_cast<const float4*>(y + base + i0));
+            float4 d = *reinterpret_cast<float4*>(dy + base + i0);
+            d.x = af.a * (d.x - m1 - (yv.x - af.mean) * af.inv * m2);
+            d.y = af.a * (d.y - m1 - (yv.y - af.mean) * af.inv * m2);
+            d.z = af.a * (d.z - m1 - (yv.z - af.mean) * af.inv * m2);
+            d.w = af.a * (d.w - m1 - (yv.w - af.mean) * af.inv * m2);
+            *reinterpret_cast<float4*>(dy + base + i0) = d;
+        }
+    } else {
+        for (int i = i0; i < min(i0 + 4, Lin); ++i) {
+            const float xhat = (__ldg(y + base + i) - af.mean) * af.inv;
+            dy[base + i] = af.a * (dy[base + i] - m1 - xhat * m2);
+        }
     }
     if (blockIdx.x == 0 && b == 0 && threadIdx.x == 0) {
         dgamma[c] += grad_scale * (float)red[C + c];     // grad_scale = 1/world under data parallelism: every
@@ -290,6 +331,7 @@ __global__ void __launch_bounds__(TI) conv1d_dgrad_kernel(const float* __restric
     const int b = blockIdx.y, i0 = blockIdx.x * TI, tid = threadIdx.x;
     const int lbase = floor_div2(i0 + P - (KW - 1));
     const float* dyb = dy + (size_t)b * CO * Lout;
+#pragma unroll 4
     for (int idx = tid; idx < CO * NL; idx += TI) {
         const int o = idx / NL, ll = idx - o * NL, l = lbase + ll;
         dys[idx] = (l >= 0 && l < Lout) ? __ldg(dyb + (size_t)o * Lout + l) : 0.f;
@@ -489,9 +531,10 @@ int launch_bn_relu_pool_fwd(const float* y, const double* stats, const float* ga
         MMS_PROF_BEGIN(st);
         bn_relu_pool_fwd_tm_kernel<<<grid, 256, 0, st>>>(y, stats, gamma, beta, rm, rv, nbt, Bstat, C, l_in, Lout, training, out);
     } else {
-        dim3 grid(cdiv(Lout, 256), C, B);
+        dim3 grid(C, B);
+        MMS_REQUIRE((size_t)l_in * sizeof(float) <= 40 * 1024, "bn_relu_pool: row length %d too long for one CTA's shared memory", l_in);
         MMS_PROF_BEGIN(st);
-        bn_relu_pool_fwd_ncl_kernel<<<grid, 256, 0, st>>>(y, stats, gamma, beta, rm, rv, nbt, Bstat, C, l_in, Lout, training, out);
+        bn_relu_pool_fwd_ncl_kernel<<<grid, 256, (size_t)l_in * sizeof(float), st>>>(y, stats, gamma, beta, rm, rv, nbt, Bstat, C, l_in, Lout, training, out);
     }
     MMS_LAUNCH_CHECK("bn_relu_pool_fwd");
     return MMS_OK;
@@ -506,13 +549,16 @@ int launch_bn_relu_pool_bwd(const float* y, const double* stats, const float* ga
     const int Lout = pool_out_len(l_in);
     if (Bstat <= 0) Bstat = B;
     MMS_REQUIRE(C >= 1 && C <= 64, "bn_relu_pool_bwd: channels %d outside [1,64]", C);
-    dim3 grid(cdiv(l_in, 256), C, B);
     if (which & 1) {
+        dim3 grid(C, B);
+        const size_t smem = (size_t)(((l_in + 3) & ~3) + Lout) * sizeof(float);
+        MMS_REQUIRE(smem <= 44 * 1024, "bn_relu_pool_bwd: row length %d too long for one CTA's shared memory", l_in);
         MMS_PROF_BEGIN(st);
-        pool_relu_bwd_kernel<<<grid, 256, 0, st>>>(y, stats, gamma, beta, rm, rv, dout, Bstat, C, l_in, Lout, training, time_major, dy, red);
+        pool_relu_bwd_kernel<<<grid, 256, smem, st>>>(y, stats, gamma, beta, rm, rv, dout, Bstat, C, l_in, Lout, training, time_major, dy, red);
         MMS_LAUNCH_CHECK("pool_relu_bwd_kernel");
     }
     if (which & 2) {
+        dim3 grid(cdiv(l_in, 1024), C, B);
         MMS_PROF_BEGIN(st);
         bn_bwd_apply_kernel<<<grid, 256, 0, st>>>(y, stats, gamma, beta, rm, rv, red, Bstat, C, l_in, training, dy, dgamma, dbeta, grad_scale);
         MMS_LAUNCH_CHECK("bn_bwd_apply_kernel");
