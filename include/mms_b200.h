@@ -246,14 +246,14 @@ int mms_gru_recur_fwd(const mms_gru_dir_fwd* dirs_host, int32_t ndirs, int32_t B
 
 /* Reverse-time pass of one direction.  dout (optional) is the gradient w.r.t. the emitted h,
  * indexed like hs; dout_last [B, dl_ld] (optional) is added at the forward-order LAST step
- * only; dh_head/W0 (optional): initial dh[b,k] += sum_i dh_head[b*64+i] * w0[i*w0_ld + w0_col + k].
+ * only (or at the first one if dl_at_first); dh_head/W0 (optional): initial dh[b,k] += sum_i dh_head[b*64+i] * w0[i*w0_ld + w0_col + k].
  * drop_base / drop_mask are reserved and must be 0 (apply mms_dropout_apply to dout first).  Writes D[(b*d_bs + t*d_ts) + 0..4H) = (d r_pre, d z_pre, d n_pre, d q). */
 typedef struct {
     const float* w_hh;
     const float* stash; int64_t st_bs, st_ts;
     const float* hs; int64_t hs_bs, hs_ts;
     const float* dout; int64_t do_bs, do_ts; int64_t drop_base; int32_t drop_mask;
-    const float* dout_last; int64_t dl_ld;
+    const float* dout_last; int64_t dl_ld; int32_t dl_at_first;  /* 1: add dout_last at the FIRST forward step instead */
     const float* dh_head; const float* w0; int64_t w0_ld; int32_t w0_col;
     float* D; int64_t d_bs, d_ts;
     int32_t t0, dt, nsteps;

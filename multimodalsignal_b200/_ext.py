@@ -54,7 +54,7 @@ class GruDirBwd(C.Structure):
         ("stash", C.c_void_p), ("st_bs", c_i64), ("st_ts", c_i64),
         ("hs", C.c_void_p), ("hs_bs", c_i64), ("hs_ts", c_i64),
         ("dout", C.c_void_p), ("do_bs", c_i64), ("do_ts", c_i64), ("drop_base", c_i64), ("drop_mask", c_i32),
-        ("dout_last", C.c_void_p), ("dl_ld", c_i64),
+        ("dout_last", C.c_void_p), ("dl_ld", c_i64), ("dl_at_first", c_i32),
         ("dh_head", C.c_void_p), ("w0", C.c_void_p), ("w0_ld", c_i64), ("w0_col", c_i32),
         ("D", C.c_void_p), ("d_bs", c_i64), ("d_ts", c_i64),
         ("t0", c_i32), ("dt", c_i32), ("nsteps", c_i32),

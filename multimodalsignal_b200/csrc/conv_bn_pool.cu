@@ -317,7 +317,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
 __device__ __forceinline__ int floor_div2(int a) { return a >= 0 ? a / 2 : -((-a + 1) / 2); }
 
 // dx[b,c,i] = sum_{o,k : S*l + k - P == i} w[o,c,k] * dy[b,o,l];   optional dot with xdot -> dgate
-template <int CO, int KW, int S, int P, int TI>
+// CPAD = input channels rounded up to 8 or 16: the accumulator count (C = 6 needs 8, not 16)
+template <int CO, int KW, int S, int P, int TI, int CPAD>
 __global__ void __launch_bounds__(TI) conv1d_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w,
                                                           float* __restrict__ dx, const float* __restrict__ xdot,
                                                           float* __restrict__ dgate, int CI, int Lin, int Lout) {
@@ -325,8 +326,8 @@ __global__ void __launch_bounds__(TI) conv1d_dgrad_kernel(const float* __restric
     constexpr int NL = (TI - 1 + KW - 1) / S + 2;
     extern __shared__ __align__(16) float smem[];
     float* ws = smem;                           // [KW][CO][16]
-    float* dys = smem + KW * CO * CONV_CI_PAD;  // [CO][NL]
-    __shared__ float red[TI / 32][CONV_CI_PAD];
+    float* dys = smem + KW * CO * CPAD;  // [CO][NL]
+    __shared__ float red[TI / 32][CPAD];
 
     const int b = blockIdx.y, i0 = blockIdx.x * TI, tid = threadIdx.x;
     const int lbase = floor_div2(i0 + P - (KW - 1));
@@ -336,24 +337,24 @@ __global__ void __launch_bounds__(TI) conv1d_dgrad_kernel(const float* __restric
         const int o = idx / NL, ll = idx - o * NL, l = lbase + ll;
         dys[idx] = (l >= 0 && l < Lout) ? __ldg(dyb + (size_t)o * Lout + l) : 0.f;
     }
-    for (int idx = tid; idx < KW * CO * CONV_CI_PAD; idx += TI) {
-        const int c = idx % CONV_CI_PAD, ko = idx / CONV_CI_PAD, o = ko % CO, k = ko / CO;
+    for (int idx = tid; idx < KW * CO * CPAD; idx += TI) {
+        const int c = idx % CPAD, ko = idx / CPAD, o = ko % CO, k = ko / CO;
         ws[idx] = c < CI ? w[((size_t)o * CI + c) * KW + k] : 0.f;
     }
     __syncthreads();
 
     const int i = i0 + tid;
-    float acc[CONV_CI_PAD];
+    float acc[CPAD];
 #pragma unroll
-    for (int c = 0; c < CONV_CI_PAD; ++c) acc[c] = 0.f;
+    for (int c = 0; c < CPAD; ++c) acc[c] = 0.f;
     for (int k = (i + P) & 1; k < KW; k += S) {
         const int ll = (i + P - k) / S - lbase;     // i + P - k is even; may be negative -> staged as zero
         if (ll < 0 || ll >= NL) continue;
         for (int o = 0; o < CO; ++o) {
             const float d = dys[o * NL + ll];
-            const float4* wv = reinterpret_cast<const float4*>(ws + (k * CO + o) * CONV_CI_PAD);
+            const float4* wv = reinterpret_cast<const float4*>(ws + (k * CO + o) * CPAD);
 #pragma unroll
-            for (int c4 = 0; c4 < CONV_CI_PAD / 4; ++c4) {
+            for (int c4 = 0; c4 < CPAD / 4; ++c4) {
                 const float4 wq = wv[c4];
                 acc[4 * c4 + 0] += wq.x * d;
                 acc[4 * c4 + 1] += wq.y * d;
@@ -365,13 +366,13 @@ __global__ void __launch_bounds__(TI) conv1d_dgrad_kernel(const float* __restric
     const bool valid = i < Lin;
     if (dx && valid) {
 #pragma unroll
-        for (int c = 0; c < CONV_CI_PAD; ++c)
+        for (int c = 0; c < CPAD; ++c)
             if (c < CI) dx[((size_t)b * CI + c) * Lin + i] = acc[c];
     }
     if (xdot) {
         const int warp = tid >> 5, lane = tid & 31;
 #pragma unroll
-        for (int c = 0; c < CONV_CI_PAD; ++c) {
+        for (int c = 0; c < CPAD; ++c) {
             float v = 0.f;
             if (valid && c < CI) v = acc[c] * __ldg(xdot + ((size_t)b * CI + c) * Lin + i);
             v = warp_sum(v);
@@ -446,13 +447,13 @@ static int conv_fwd_launch(const float* x, const float* w, const float* gate, in
     return MMS_OK;
 }
 
-template <int CO, int KW, int S, int P, int TI>
-static int conv_dgrad_launch(const float* dy, const float* w, int B, int CI, int Lin, float* dx, const float* xdot,
-                             float* dgate, cudaStream_t st) {
+template <int CO, int KW, int S, int P, int TI, int CPAD>
+static int conv_dgrad_launch_pad(const float* dy, const float* w, int B, int CI, int Lin, float* dx, const float* xdot,
+                                 float* dgate, cudaStream_t st) {
     const int Lout = conv_out_len(Lin, KW, S, P);
     constexpr int NL = (TI - 1 + KW - 1) / S + 2;
-    const size_t smem = (size_t)(KW * CO * CONV_CI_PAD + CO * NL) * sizeof(float);
-    auto kern = conv1d_dgrad_kernel<CO, KW, S, P, TI>;
+    const size_t smem = (size_t)(KW * CO * CPAD + CO * NL) * sizeof(float);
+    auto kern = conv1d_dgrad_kernel<CO, KW, S, P, TI, CPAD>;
     static bool attr_done = false;
     if (!attr_done) { MMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr_done = true; }
     dim3 grid(cdiv(Lin, TI), B);
@@ -460,6 +461,13 @@ static int conv_dgrad_launch(const float* dy, const float* w, int B, int CI, int
     kern<<<grid, TI, smem, st>>>(dy, w, dx, xdot, dgate, CI, Lin, Lout);
     MMS_LAUNCH_CHECK("conv1d_dgrad_kernel");
     return MMS_OK;
+}
+
+template <int CO, int KW, int S, int P, int TI>
+static int conv_dgrad_launch(const float* dy, const float* w, int B, int CI, int Lin, float* dx, const float* xdot,
+                             float* dgate, cudaStream_t st) {
+    if (CI <= 8) return conv_dgrad_launch_pad<CO, KW, S, P, TI, 8>(dy, w, B, CI, Lin, dx, xdot, dgate, st);
+    return conv_dgrad_launch_pad<CO, KW, S, P, TI, 16>(dy, w, B, CI, Lin, dx, xdot, dgate, st);
 }
 
 template <int CO, int KW, int S, int P, int TL>

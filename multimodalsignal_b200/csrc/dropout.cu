@@ -28,6 +28,30 @@ __global__ void __launch_bounds__(256) dropout_apply_kernel(const float* in, flo
     }
 }
 
+// rows of `row_len` contiguous floats whose element ids advance by id_row_stride per row (a strided slice
+// of a larger tensor, e.g. the t = L-1 rows of [B, L, 2H]); in == out allowed.
+__global__ void __launch_bounds__(256) dropout_rows_kernel(const float* in, float* out, int rows, int row_len, int64_t base_id,
+                                                           int64_t id_row_stride, float p, uint64_t seed, uint64_t offset,
+                                                           const int64_t* offset_dev) {
+    DropRng rng;
+    rng.init(seed, resolve_offset(offset, offset_dev), p);
+    const int64_t n = (int64_t)rows * row_len;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / row_len, c = i - r * row_len;
+        out[i] = in[i] * rng.mult((uint64_t)(base_id + r * id_row_stride + c));
+    }
+}
+
+int launch_dropout_rows(const float* in, float* out, int rows, int row_len, int64_t base_id, int64_t id_row_stride, float p,
+                        uint64_t seed, uint64_t offset, const int64_t* offset_dev, cudaStream_t st) {
+    if (rows <= 0 || row_len <= 0) return MMS_OK;
+    const int blocks = cdiv((int64_t)rows * row_len, 256);
+    MMS_PROF_BEGIN(st);
+    dropout_rows_kernel<<<blocks > 592 ? 592 : blocks, 256, 0, st>>>(in, out, rows, row_len, base_id, id_row_stride, p, seed, offset, offset_dev);
+    MMS_LAUNCH_CHECK("dropout_rows_kernel");
+    return MMS_OK;
+}
+
 int launch_dropout_apply(const float* in, float* out, int64_t n, int64_t base_id, float p, uint64_t seed, uint64_t offset,
                          const int64_t* offset_dev, cudaStream_t st) {
     if (n <= 0) return MMS_OK;

@@ -297,6 +297,7 @@ __global__ void __launch_bounds__(2 * H) gru_bwd_kernel(const GruBwdParams prm) 
         advance();
     }
 
+    const int v_extra = d.dl_at_first ? nsteps - 1 : 0;     // visit at which dout_last is added
     int buf = 0;
     for (int v0 = 0; v0 < nsteps; v0 += PFB) {
 #pragma unroll
@@ -316,7 +317,7 @@ __global__ void __launch_bounds__(2 * H) gru_bwd_kernel(const GruBwdParams prm) 
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const StepIn& x = in[r];
-                const float dht = dh[r] + x.dout + (v == 0 ? dlast[r] : 0.f);
+                const float dht = dh[r] + x.dout + (v == v_extra ? dlast[r] : 0.f);
                 const float dn = dht * (1.f - x.z);
                 const float dz = dht * (x.hp - x.n);
                 const float dnp = dn * (1.f - x.n * x.n);

@@ -38,6 +38,7 @@ bool tc_gemm_supported(const float*, int64_t, const float*, int64_t, int, int, i
 constexpr int TC_MIN_ROWS = 1024;      // below this a single tcgen05 CTA is pure latency: the SIMT kernels win
 int launch_transpose_pad(const float*, int, int, float*, int64_t, int, cudaStream_t);
 int launch_dropout_apply(const float*, float*, int64_t, int64_t, float, uint64_t, uint64_t, const int64_t*, cudaStream_t);
+int launch_dropout_rows(const float*, float*, int, int, int64_t, int64_t, float, uint64_t, uint64_t, const int64_t*, cudaStream_t);
 
 constexpr int MAX_LAYERS = 8;
 constexpr int64_t DROP_LAYER_STRIDE = 1ll << 40;
@@ -54,8 +55,8 @@ static bool use_tc() {
 // caller's next kernel (Adam).  Event fork/join works identically in eager mode and under CUDA-graph
 // capture (the side streams become branches of the captured graph).  MMS_DISABLE_STREAMS=1 serialises.
 struct SideStreams {
-    cudaStream_t s[2] = {nullptr, nullptr};
-    cudaEvent_t fork_ev[8] = {}, join_ev[2] = {};
+    cudaStream_t s[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t fork_ev[8] = {}, join_ev[3] = {};
     bool ok = false;
 };
 static int g_streams_disabled = -1;
@@ -67,11 +68,11 @@ static SideStreams* side_streams() {
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
     SideStreams& ss = per_dev[dev];
     if (!ss.ok) {
-        for (int i = 0; i < 2; ++i)
+        for (int i = 0; i < 3; ++i)
             if (cudaStreamCreateWithFlags(&ss.s[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
         for (int i = 0; i < 8; ++i)
             if (cudaEventCreateWithFlags(&ss.fork_ev[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        for (int i = 0; i < 2; ++i)
+        for (int i = 0; i < 3; ++i)
             if (cudaEventCreateWithFlags(&ss.join_ev[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
         ss.ok = true;
     }
@@ -81,7 +82,7 @@ struct Forker {
     SideStreams* ss;
     cudaStream_t main;
     int n_forks = 0;
-    bool used[2] = {false, false};
+    bool used[3] = {false, false, false};
     Forker(cudaStream_t m) : ss(side_streams()), main(m) {}
     // stream on which work that only depends on what `main` has enqueued so far may run
     cudaStream_t fork(int which) {
@@ -100,8 +101,11 @@ struct Forker {
         return MMS_OK;
     }
     int join() {
-        int rc = join_one(0);
-        return rc ? rc : join_one(1);
+        for (int i = 0; i < 3; ++i) {
+            int rc = join_one(i);
+            if (rc) return rc;
+        }
+        return MMS_OK;
     }
 };
 
@@ -198,7 +202,7 @@ struct Workspace {
     float *mean, *gate, *y1, *p1, *y2, *seq;
     float *gi[MAX_LAYERS], *hs[MAX_LAYERS], *outd[MAX_LAYERS], *stash[MAX_LAYERS];   // bottom layers
     float *gi_tf, *gi_tr, *hs_tf, *h_tr, *stash_tf, *stash_tr, *last, *hid;
-    float *wT_top, *wT[MAX_LAYERS];
+    float *wT_top, *wT[MAX_LAYERS], *dx_extra;
     float *dhid, *dlogits, *D_tf, *D_tr, *D[MAX_LAYERS], *dxa, *dxb, *dy2, *dp1, *dy1, *ca_scratch;
     int64_t total;
 };
@@ -251,6 +255,7 @@ static void carve(const Dims& m, char* base, Workspace* w) {
         const int64_t widest = 2 * H > m.O ? 2 * H : m.O;
         w->wT_top = (float*)take(2 * widest * 3 * H * f);
         for (int l = 0; l < m.layers - 1; ++l) w->wT[l] = (float*)take(widest * 8 * H * f);
+        w->dx_extra = (float*)take(B * widest * f);
         w->dxa = (float*)take(M * widest * f);
         w->dxb = (float*)take(M * widest * f);
         w->dy2 = (float*)take(B * m.O * m.L2c * f);
@@ -328,10 +333,13 @@ static int model_forward(const mms_cnngru_desc* d, const float* x, const float* 
     }
     {   // top layer: forward direction over the whole sequence, reverse direction for its first step only
         const int l = m.layers - 1;
+        Forker fkf(st);
+        rc = gemm_nt(in + (int64_t)(L - 1) * I, (int64_t)L * I, P + po.w_ih[l] + (int64_t)3 * H * I, I,
+                     P + po.b_ih[l] + 3 * H, w.gi_tr, 3 * H, B, 3 * H, I, fkf.fork(0));     // B rows: beside the big one
+        if (rc) return rc;
         rc = gemm_nt(in, I, P + po.w_ih[l], I, P + po.b_ih[l], w.gi_tf, 3 * H, (int)M, 3 * H, I, st);
         if (rc) return rc;
-        rc = gemm_nt(in + (int64_t)(L - 1) * I, (int64_t)L * I, P + po.w_ih[l] + (int64_t)3 * H * I, I,
-                     P + po.b_ih[l] + 3 * H, w.gi_tr, 3 * H, B, 3 * H, I, st);
+        rc = fkf.join();
         if (rc) return rc;
         mms_gru_dir_fwd dirs[2];
         memset(dirs, 0, sizeof(dirs));
@@ -431,6 +439,18 @@ static int model_backward(const mms_cnngru_desc* d, const float* x, const float*
         // h_prev = 0 for the single reverse step: dW_hh(reverse) = 0, only the bias gradient remains
         rc = launch_gemm_tn_acc(w.D_tr, 4 * H, 2 * H, H, nullptr, 0, 0, 1, nullptr, 0, G + po.b_hh[top] + 3 * H, B, 3 * H, 0, sw);
         if (rc) return rc;
+        if (top >= 1) {
+            // the single reverse step only touches the rows t = L-1: its B-row product goes to dx_extra on a side
+            // stream, beside the big product below; the layer underneath adds it at t = L-1
+            cudaStream_t sx = fk.fork(2);
+            rc = launch_gemm_nn(w.D_tr, 4 * H, P + po.w_ih[top] + (int64_t)3 * H * I_top, I_top, w.dx_extra, I_top, B, I_top, 3 * H, 0, sx);
+            if (rc) return rc;
+            if (m.drop_gru) {
+                rc = launch_dropout_rows(w.dx_extra, w.dx_extra, B, I_top, (int64_t)(top - 1) * DROP_LAYER_STRIDE + (int64_t)(L - 1) * I_top,
+                                         (int64_t)L * I_top, p, d->rng_seed, d->rng_offset, d->rng_offset_dev, sx);
+                if (rc) return rc;
+            }
+        }
         // gradient w.r.t. the top layer's input
         if (tc_bwd && tc_gemm_supported(w.D_tf, 4 * H, w.wT_top, 3 * H, M, I_top, 3 * H)) {
             // tensor-core path: dx = D @ W_ih as an NT product against the transposed weights
@@ -442,10 +462,12 @@ static int model_backward(const mms_cnngru_desc* d, const float* x, const float*
             rc = launch_gemm_nn(w.D_tf, 4 * H, P + po.w_ih[top], I_top, dxcur, I_top, M, I_top, 3 * H, 0, st);
             if (rc) return rc;
         }
-        // the single reverse step only touches the rows t = L-1 (B rows: SIMT, accumulate)
-        rc = launch_gemm_nn(w.D_tr, 4 * H, P + po.w_ih[top] + (int64_t)3 * H * I_top, I_top, dxcur + (int64_t)(L - 1) * I_top,
-                            (int64_t)L * I_top, B, I_top, 3 * H, 1, st);
-        if (rc) return rc;
+        // the single reverse step only touches the rows t = L-1 (B rows, SIMT)
+        if (top == 0) {
+            rc = launch_gemm_nn(w.D_tr, 4 * H, P + po.w_ih[top] + (int64_t)3 * H * I_top, I_top, dxcur + (int64_t)(L - 1) * I_top,
+                                (int64_t)L * I_top, B, I_top, 3 * H, 1, st);
+            if (rc) return rc;
+        }
     }
     for (int l = top - 1; l >= 0; --l) {
         const float* in_l = l == 0 ? w.seq : w.outd[l - 1];
@@ -453,6 +475,10 @@ static int model_backward(const mms_cnngru_desc* d, const float* x, const float*
         if (m.drop_gru) {      // gradient through the dropout between layer l and l + 1 (same multipliers)
             rc = launch_dropout_apply(dxcur, dxcur, (int64_t)M * 2 * H, (int64_t)l * DROP_LAYER_STRIDE, p, d->rng_seed,
                                       d->rng_offset, d->rng_offset_dev, st);
+            if (rc) return rc;
+        }
+        if (l == top - 1) {
+            rc = fk.join_one(2);     // dx_extra is complete
             if (rc) return rc;
         }
         mms_gru_dir_bwd dirs[2];
@@ -463,6 +489,10 @@ static int model_backward(const mms_cnngru_desc* d, const float* x, const float*
             g.stash = w.stash[l] + (int64_t)dd * M * 4 * H; g.st_bs = (int64_t)L * 4 * H; g.st_ts = 4 * H;
             g.hs = w.hs[l] + dd * H; g.hs_bs = (int64_t)L * 2 * H; g.hs_ts = 2 * H;
             g.dout = dxcur + dd * H; g.do_bs = (int64_t)L * 2 * H; g.do_ts = 2 * H;
+            if (l == top - 1) {      // the top layer's single reverse step contributes at t = L-1 only
+                g.dout_last = w.dx_extra + dd * H; g.dl_ld = 2 * H;
+                g.dl_at_first = dd;  // t = L-1 is the LAST forward step of direction 0 and the FIRST of direction 1
+            }
             g.D = w.D[l] + dd * 4 * H; g.d_bs = (int64_t)L * 8 * H; g.d_ts = 8 * H;
             g.t0 = dd ? L - 1 : 0; g.dt = dd ? -1 : 1; g.nsteps = L;
         }
