@@ -538,6 +538,8 @@ def run_loso(args):
                 "accuracy_mean": float(np.mean([r["accuracy"] for r in results])),
                 "f1_mean": float(np.mean([r["f1_score"] for r in results])),
                 "folds": [{k: r[k] for k in ("subject", "accuracy", "f1_score", "windows_trained", "seconds")} for r in results],
+                "host_seconds_by_phase": {k: round(sum(r.get("timing", {}).get(k, 0.0) for r in results), 3)
+                                          for k in ("train_enqueue", "train_wait", "evaluate", "bookkeeping")},
                 "gpu_launches_rank0_uncaptured": launches,
                 "summary_file": str(out_dir / "cv_summary.txt")}
         print(json.dumps(line), flush=True)

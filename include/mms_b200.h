@@ -150,6 +150,24 @@ int mms_adam_flat_step(float* params, const float* grads, float* exp_avg, float*
                        int64_t n, const float* lr_dev, float beta1, float beta2, float eps,
                        float weight_decay, int64_t* step_dev, int32_t* scratch_dev, mms_stream_t stream);
 
+/* trainer.py:130,140-142 -- one batch of DataLoader(dataset, batch_size, shuffle=True) (main.py:111) assembled on
+ * the device: out_x[b, :] = data[perm[cursor + b], :], out_y[b] = labels[perm[cursor + b]] for b < batch.
+ * data: float32 [n_rows, row_floats] (the normalised [N, C*W] window array), labels int64 [n_rows], perm: int64
+ * permutation (NULL = identity), *cursor_dev: int64 position inside perm (NULL = 0).  With advance != 0 the kernel
+ * moves *cursor_dev forward by `batch` when it is done, so a captured CUDA graph (gather + train step) can be
+ * replayed once per batch with no host work; scratch_dev: one zero-initialised int32. */
+int mms_batch_gather(const float* data, const int64_t* labels, const int64_t* perm, int64_t* cursor_dev,
+                     int64_t n_rows, int64_t row_floats, int32_t batch, float* out_x, int64_t* out_y,
+                     int32_t advance, int32_t* scratch_dev, mms_stream_t stream);
+
+/* trainer.py:217-228 -- the per-batch bookkeeping of Trainer.evaluate: *loss_sum += sum_b(lse_b - logit[b, y_b])
+ * (float64; the reference adds loss.item() * batch), preds_out[b] = argmax_c logits[b, c] (first maximum, as
+ * torch.argmax of the softmax), confusion[y_b * nc + pred_b] += 1 (int64 [nc, nc], rows = true class).
+ * accuracy_score and the weighted f1_score of trainer.py:229-230 are functions of that matrix.
+ * preds_out, confusion and loss_sum may each be NULL. */
+int mms_eval_accumulate(const float* logits, const int64_t* labels, int32_t batch, int32_t num_classes,
+                        int64_t* preds_out, int64_t* confusion, double* loss_sum, mms_stream_t stream);
+
 /* One whole training step, trainer.py:144-149: zero_grad, forward, CE, backward, Adam.
  * (With world_size > 1 the host calls forward/backward/adam separately around its NCCL
  * all-reduce instead.) */

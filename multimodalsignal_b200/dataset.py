@@ -77,6 +77,10 @@ class WesadDataset(Dataset):
 def normalise_gather(sub, channels_to_use):
     """One subject: overlap-weighted statistics + normalised float32 ``[n_win, C, W]`` on the device
     (the arithmetic of dataset.py:37-48 followed by dataset.py:63's cast and permute)."""
+    cache = sub.__dict__.setdefault("_normalised", {})      # the statistics are per subject: every LOSO fold reuses them
+    key = tuple(channels_to_use)
+    if key in cache:
+        return cache[key]
     lib = _ext.lib()
     idx = [sub.channel_names.index(ch) for ch in channels_to_use]
     rows = [sub.streams[i] for i in idx]
@@ -93,6 +97,7 @@ def normalise_gather(sub, channels_to_use):
     out = torch.empty(n_win, len(idx), W, dtype=torch.float32, device=dev)
     check(lib.mms_window_gather(arr, len(idx), sub.streams.shape[1], ptr(sub.starts), n_win, W, 1,
                                 ptr(mean.contiguous()), ptr(scale.contiguous()), ptr(flags), ptr(out), stream()))
+    cache[key] = out
     return out
 
 

@@ -101,7 +101,7 @@ def run_fold(fold_index, subject_to_test, run_output_dir, all_channel_names, sub
     trainer.train(train_loader, val_loader)
     _, test_acc, test_f1 = trainer.evaluate(test_loader, is_test=True)
     return {'subject': subject_to_test, 'accuracy': float(test_acc), 'f1_score': float(test_f1),
-            'windows_trained': int(trainer.windows_trained)}
+            'windows_trained': int(trainer.windows_trained), 'timing': dict(trainer.timing)}
 
 
 def write_summary(run_output_dir, results):

@@ -76,6 +76,11 @@ class ChannelAttention(nn.Module):
         return _ChanAttnFn.apply(x.float(), self.fc[0].weight, self.fc[2].weight)
 
 
+def _no_flatten():
+    """Stands in for ``nn.GRU.flatten_parameters``: the GRU module here only holds parameters (its cuDNN path is
+    never run), so ``.to(device)`` must not pay for cuDNN's weight re-packing (and a cuDNN handle)."""
+
+
 def _require_cuda(x):
     if not x.is_cuda:
         raise _ext.MmsError("multimodalsignal_b200 runs on a B200 only: got a CPU tensor and there is no CPU fallback")
@@ -172,6 +177,7 @@ class CnnGruAttentionModel(nn.Module):
         )
         self.gru = nn.GRU(input_size=cnn_out_channels, hidden_size=gru_hidden_size, num_layers=gru_num_layers,
                           batch_first=True, bidirectional=True, dropout=dropout if gru_num_layers > 1 else 0)
+        self.gru.flatten_parameters = _no_flatten
         self.classifier = nn.Sequential(
             nn.Linear(gru_hidden_size * 2, 64),
             nn.ReLU(),

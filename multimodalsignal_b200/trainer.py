@@ -10,6 +10,7 @@ device (the reference syncs twice per step through ``loss.item()``, trainer.py:1
 from __future__ import annotations
 
 import ctypes as C
+import threading
 import time
 from pathlib import Path
 
@@ -53,7 +54,101 @@ class EarlyStopping:
 
     def save_checkpoint(self, model):
         # plain tensors (not views of the flat buffer) so the file equals the reference's layout
-        torch.save({k: v.detach().clone() for k, v in model.state_dict().items()}, self.checkpoint_path)
+        writer = getattr(model, "_checkpoint_writer", None)
+        if writer is not None:
+            writer.submit(model, self.checkpoint_path)
+        else:
+            torch.save({k: v.detach().clone() for k, v in model.state_dict().items()}, self.checkpoint_path)
+
+
+class CheckpointWriter:
+    """``torch.save(model.state_dict(), path)`` (reference trainer.py:38-39) off the training thread.
+
+    ``submit`` snapshots the model's three flat device buffers (parameters, BN running statistics,
+    ``num_batches_tracked``) with three stream-ordered device copies and returns; a worker thread
+    rebuilds the reference's 34-entry ``state_dict`` as plain tensors from the snapshot and writes the
+    file.  Only the newest pending snapshot is written ("latest wins": the reference overwrites the
+    same file).  ``flush()`` blocks until the file on disk is the last submitted one -- ``Trainer``
+    calls it before it re-loads ``best_model.pt`` and before ``train()`` returns."""
+
+    def __init__(self):
+        self._cv = threading.Condition()
+        self._pending = None
+        self._busy = False
+        self._error = None
+        self._thread = None
+        self._stream = None
+
+    def submit(self, model, path):
+        model.flat_parameters()                                   # make sure the flat views exist
+        snap = (model._flat.clone(), model._bn_flat.clone(), model._nbt_flat.clone())
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream())
+        layout = self._layout(model)
+        with self._cv:
+            self._pending = (snap, ready, layout, Path(path), snap[0].device)
+            if self._thread is None:
+                self._thread = threading.Thread(target=self._work, name="mms-checkpoint", daemon=True)
+                self._thread.start()
+            self._cv.notify_all()
+
+    @staticmethod
+    def _layout(model):
+        """state_dict key -> (buffer index, offset, numel, shape) inside the three flat buffers."""
+        cached = getattr(model, "_ckpt_layout", None)
+        if cached is not None and cached[0] is model._flat:
+            return cached[1]
+        bases = (model._flat, model._bn_flat, model._nbt_flat)
+        out = []
+        for k, v in model.state_dict().items():
+            for bi, base in enumerate(bases):
+                lo, hi = base.data_ptr(), base.data_ptr() + base.numel() * base.element_size()
+                if v.numel() == 0:
+                    out.append((k, -1, 0, 0, tuple(v.shape), v.dtype))
+                    break
+                if v.dtype == base.dtype and lo <= v.data_ptr() < hi:
+                    out.append((k, bi, (v.data_ptr() - lo) // base.element_size(), v.numel(), tuple(v.shape), v.dtype))
+                    break
+            else:
+                raise _ext.MmsError(f"state_dict entry {k} does not live in the model's flat buffers")
+        model._ckpt_layout = (model._flat, out)
+        return out
+
+    def _work(self):
+        while True:
+            with self._cv:
+                while self._pending is None:
+                    self._cv.wait()
+                job, self._pending, self._busy = self._pending, None, True
+            try:
+                snap, ready, layout, path, dev = job
+                torch.cuda.set_device(dev)
+                if self._stream is None:
+                    self._stream = torch.cuda.Stream(device=dev)     # non-blocking: never queues behind the training stream
+                with torch.cuda.stream(self._stream):
+                    self._stream.wait_event(ready)
+                    host = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in snap]
+                    for h, t in zip(host, snap):
+                        h.copy_(t, non_blocking=True)
+                    self._stream.synchronize()
+                sd = {}
+                for k, bi, off, n, shape, dtype in layout:
+                    sd[k] = torch.zeros(shape, dtype=dtype) if bi < 0 else host[bi][off:off + n].clone().view(shape)
+                torch.save(sd, path)
+            except Exception as e:                                   # surfaced by flush()
+                self._error = e
+            finally:
+                with self._cv:
+                    self._busy = False
+                    self._cv.notify_all()
+
+    def flush(self):
+        with self._cv:
+            while self._pending is not None or self._busy:
+                self._cv.wait(timeout=0.05)
+        if self._error is not None:
+            err, self._error = self._error, None
+            raise err
 
 
 class FlatAdam(torch.optim.Optimizer):
@@ -107,9 +202,10 @@ class FusedTrainStep:
     a CUDA graph and replayed.  ``__call__(x, y)`` accepts device tensors or pinned host tensors
     (copied into the static graph inputs on the current stream)."""
 
-    def __init__(self, model, optimizer: FlatAdam, batch: int, seq_len: int, use_graph: bool = True):
+    def __init__(self, model, optimizer: FlatAdam, batch: int, seq_len: int, use_graph: bool = True, source=None):
         self.lib = _ext.lib()
         self.model, self.opt = model, optimizer
+        self.source = source            # DeviceBatchSource: the batch is gathered on the device inside the graph
         self.flat = model.flat_parameters()
         dev = self.flat.device
         self.x = torch.zeros(batch, model.in_channels, seq_len, dtype=torch.float32, device=dev)
@@ -136,6 +232,10 @@ class FusedTrainStep:
 
     def _enqueue(self):
         m, o, g = self.model, self.opt, self.opt.param_groups[0]
+        if self.source is not None:     # trainer.py:130,140-142: next batch of the shuffled epoch, cursor advanced on the device
+            src = self.source
+            check(self.lib.mms_batch_gather(ptr(src.data), ptr(src.labels), ptr(src.perm), ptr(src.cursor), src.n, src.row_floats,
+                                            self.x.shape[0], ptr(self.x), ptr(self.y), 1, ptr(src.scratch), stream()))
         check(self.lib.mms_cnngru_train_step(
             C.byref(self.desc), ptr(self.x), ptr(self.y), ptr(self.flat), ptr(o.grads), ptr(o.exp_avg), ptr(o.exp_avg_sq),
             ptr(m._bn_flat), ptr(m._nbt_flat), ptr(self.workspace), ptr(self.logits), ptr(self.loss), ptr(self.loss_sum),
@@ -186,7 +286,7 @@ class FusedTrainStep:
 
     def run(self):
         """Enqueue one step on the static inputs (graph replay after the first two calls)."""
-        if self.model.flat_parameters().data_ptr() != self.flat.data_ptr():
+        if self.model._flat is not self.flat:       # .to() / .cuda() drop the flat buffer (models.py: _apply)
             raise _ext.MmsError("the model's parameter storage moved after FusedTrainStep was built")
         self.opt.sync_lr()
         self.calls += 1
@@ -227,6 +327,84 @@ class FusedTrainStep:
         return float(self.loss.item())
 
 
+class DeviceBatchSource:
+    """What ``mms_batch_gather`` reads: a device-resident dataset (float32 ``[N, C, W]`` + int64 labels), the
+    epoch's permutation and a cursor, both on the device.  ``start_epoch`` draws the permutation exactly as
+    ``DeviceBatchLoader.__iter__`` does (``torch.randperm`` on the CPU generator) and uploads it."""
+
+    def __init__(self, dataset, batch_size):
+        self.data, self.labels = dataset.data, dataset.labels
+        dev = self.data.device
+        self.n = int(self.data.shape[0])
+        self.row_floats = int(self.data.shape[1] * self.data.shape[2])
+        self.perm = torch.zeros(self.n + batch_size, dtype=torch.int64, device=dev)     # slack: a tail batch never reads past the end
+        self.perm_host = torch.zeros(self.n, dtype=torch.int64).pin_memory()
+        self.cursor = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.scratch = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def start_epoch(self, shuffle):
+        if shuffle:
+            torch.randperm(self.n, out=self.perm_host)
+        else:
+            torch.arange(self.n, out=self.perm_host)
+        self.perm[:self.n].copy_(self.perm_host, non_blocking=True)
+        self.cursor.zero_()
+
+
+class EvalStep:
+    """One evaluation batch (reference trainer.py:213-228) = eval-mode forward + ``mms_eval_accumulate``
+    (summed loss, arg-max predictions, confusion counts) on static buffers, replayed as a CUDA graph."""
+
+    def __init__(self, model, batch, seq_len, confusion, loss_sum, use_graph=True):
+        self.lib = _ext.lib()
+        self.model = model
+        self.flat = model.flat_parameters()
+        dev = self.flat.device
+        self.x = torch.zeros(batch, model.in_channels, seq_len, dtype=torch.float32, device=dev)
+        self.y = torch.zeros(batch, dtype=torch.int64, device=dev)
+        self.logits = torch.zeros(batch, model.num_classes, dtype=torch.float32, device=dev)
+        self.pred = torch.zeros(batch, dtype=torch.int64, device=dev)
+        self.confusion, self.loss_sum = confusion, loss_sum
+        self.engine = model.engine(batch, seq_len, False, False, dev)
+        self.use_graph, self.graph, self.calls = use_graph, None, 0
+
+    def _enqueue(self):
+        m, e = self.model, self.engine
+        check(self.lib.mms_cnngru_forward(C.byref(e.desc), ptr(self.x), ptr(self.flat), ptr(m._bn_flat), ptr(m._nbt_flat),
+                                          ptr(e.workspace), ptr(self.logits), stream()))
+        check(self.lib.mms_eval_accumulate(ptr(self.logits), ptr(self.y), self.x.shape[0], m.num_classes, ptr(self.pred),
+                                           ptr(self.confusion), ptr(self.loss_sum), stream()))
+
+    def run(self):
+        if self.model._flat is not self.flat:
+            raise _ext.MmsError("the model's parameter storage moved after EvalStep was built")
+        self.calls += 1
+        if not self.use_graph or self.calls == 1:
+            self._enqueue()
+            return
+        if self.graph is None:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._enqueue()
+            self.graph = graph
+        self.graph.replay()
+
+
+def metrics_from_confusion(conf):
+    """``accuracy_score(y, p)`` and ``f1_score(y, p, average='weighted')`` (reference trainer.py:229-230) as
+    functions of the confusion matrix ``conf[true, pred]``: per-class F1 = 2 tp / (2 tp + fp + fn) (0 where
+    the denominator is 0, sklearn's zero_division default), weighted by the class support."""
+    conf = np.asarray(conf, dtype=np.float64)
+    total = conf.sum()
+    if total == 0:
+        return 0.0, 0.0
+    tp = np.diag(conf)
+    support = conf.sum(axis=1)
+    denom = support + conf.sum(axis=0)                 # 2 tp + fn + fp
+    f1 = np.divide(2.0 * tp, denom, out=np.zeros_like(tp), where=denom > 0)
+    return float(tp.sum() / total), float((f1 * support).sum() / total)
+
+
 class _CrossEntropy(torch.autograd.Function):
     @staticmethod
     def forward(ctx, logits, labels):
@@ -250,6 +428,16 @@ class CrossEntropyLoss(torch.nn.Module):
 
     def forward(self, logits, labels):
         return _CrossEntropy.apply(logits, labels)
+
+
+_WRITER = None
+
+
+def _checkpoint_writer():
+    global _WRITER
+    if _WRITER is None:
+        _WRITER = CheckpointWriter()
+    return _WRITER
 
 
 class Trainer:
@@ -282,19 +470,35 @@ class Trainer:
                                                 checkpoint_path=self.fold_dir / 'best_model.pt', verbose=True,
                                                 log_func=self._log, fixed=t['early_stopping'].get('fixed', False))
         self._steps = {}
+        self._eval_steps = {}
+        self._sources = {}
+        self._eval_conf = torch.zeros(model.num_classes * model.num_classes, dtype=torch.int64, device=self.device)
+        self._eval_loss = torch.zeros(1, dtype=torch.float64, device=self.device)
+        self.async_checkpoint = t.get('async_checkpoint', True)
+        if self.async_checkpoint:
+            self.model._checkpoint_writer = _checkpoint_writer()
         self.total_start_time = time.time()
         self.windows_trained = 0
+        self.timing = {'train_enqueue': 0.0, 'train_wait': 0.0, 'evaluate': 0.0, 'bookkeeping': 0.0}
 
     def _log(self, message):
         print(message)
         with open(self.log_file, 'a') as f:
             f.write(message + '\n')
 
-    def _fused(self, batch, seq_len):
-        key = (batch, seq_len)
+    def _fused(self, batch, seq_len, source=None):
+        key = (batch, seq_len, id(source))
         if key not in self._steps:
-            self._steps[key] = FusedTrainStep(self.model, self.optimizer, batch, seq_len, use_graph=self.use_graph)
+            self._steps[key] = FusedTrainStep(self.model, self.optimizer, batch, seq_len, use_graph=self.use_graph, source=source)
         return self._steps[key]
+
+    def _eval_step(self, batch, seq_len):
+        key = (batch, seq_len)
+        st = self._eval_steps.get(key)
+        if st is None or st.flat is not self.model._flat:
+            st = EvalStep(self.model, batch, seq_len, self._eval_conf, self._eval_loss, use_graph=self.use_graph)
+            self._eval_steps[key] = st
+        return st
 
     @staticmethod
     def _check_batch(batch):
@@ -304,33 +508,64 @@ class Trainer:
     def _loss_sum(self):
         return sum(float(s.loss_sum.item()) for s in self._steps.values())
 
+    def _train_epoch_host(self, train_loader):
+        """trainer.py:130-149 with a one-batch look-ahead: the H2D copy of the next batch runs on a copy
+        stream while the current step (one CUDA-graph replay) executes."""
+        it = iter(train_loader)
+        nxt = next(it, None)
+        if nxt is not None:
+            self._check_batch(nxt)
+            self._fused(nxt[0].shape[0], nxt[0].shape[2]).prefetch(*nxt)
+        while nxt is not None:
+            inputs, labels = nxt
+            step = self._fused(inputs.shape[0], inputs.shape[2])
+            nxt = next(it, None)
+            if nxt is not None:
+                self._check_batch(nxt)
+                self._fused(nxt[0].shape[0], nxt[0].shape[2]).prefetch(*nxt)
+            step.run_prefetched()
+            self.windows_trained += inputs.shape[0]
+
+    def _train_epoch_device(self, loader):
+        """The same epoch for a ``DeviceBatchLoader``: the permutation is uploaded once, every step is ONE graph
+        replay (batch gather through the device cursor + the fused train step); a ragged last batch (the
+        reference's DataLoader keeps it, drop_last=False) replays a second graph of that size."""
+        ds = loader.dataset
+        src = self._sources.get(id(ds))
+        if src is None or src.data is not ds.data:
+            src = DeviceBatchSource(ds, loader.batch_size)
+            self._sources[id(ds)] = src
+        src.start_epoch(loader.shuffle)
+        full, tail = divmod(src.n, loader.batch_size)
+        T = int(ds.data.shape[2])
+        if full:
+            step = self._fused(loader.batch_size, T, src)
+            for _ in range(full):
+                step.run()
+        if tail and not loader.drop_last:
+            self._fused(tail, T, src).run()
+        self.windows_trained += src.n if not loader.drop_last else full * loader.batch_size
+
     def train(self, train_loader, val_loader):
+        from .dataset import DeviceBatchLoader
         best_val_acc = 0
         for epoch in range(self.epochs):
             t0 = time.time()
             self.model.train()
             for s in self._steps.values():
                 s.loss_sum.zero_()
-            # trainer.py:130-149 with a one-batch look-ahead: the H2D copy of the next batch runs on a copy
-            # stream while the current step (one CUDA-graph replay) executes
-            it = iter(train_loader)
-            nxt = next(it, None)
-            if nxt is not None:
-                self._check_batch(nxt)
-                self._fused(nxt[0].shape[0], nxt[0].shape[2]).prefetch(*nxt)
-            while nxt is not None:
-                inputs, labels = nxt
-                step = self._fused(inputs.shape[0], inputs.shape[2])
-                nxt = next(it, None)
-                if nxt is not None:
-                    self._check_batch(nxt)
-                    self._fused(nxt[0].shape[0], nxt[0].shape[2]).prefetch(*nxt)
-                step.run_prefetched()
-                self.windows_trained += inputs.shape[0]
+            if isinstance(train_loader, DeviceBatchLoader):
+                self._train_epoch_device(train_loader)
+            else:
+                self._train_epoch_host(train_loader)
+            t1 = time.time()
             train_loss = self._loss_sum()                  # one sync per epoch instead of two per step
             epoch_duration = time.time() - t0
+            self.timing['train_enqueue'] += t1 - t0
+            self.timing['train_wait'] += epoch_duration - (t1 - t0)
 
             val_loss, val_acc, val_f1, val_preds, val_labels = self.evaluate(val_loader, is_val=True)
+            t2 = time.time()
             self.scheduler.step(val_loss)
             best_val_acc = max(best_val_acc, val_acc)
             self._log(f"Epoch {epoch + 1}/{self.epochs} | "
@@ -339,37 +574,70 @@ class Trainer:
                       f"验证损失: {val_loss:.4f} | "
                       f"验证Acc: {val_acc:.4f} | "
                       f"验证F1: {val_f1:.4f}")
+            stop = False
             if self.early_stopping:
                 self.early_stopping(val_loss, self.model)
                 if self.early_stopping.early_stop:
                     self._log("触发早停")
-                    break
+                    stop = True
+            self.timing['bookkeeping'] += time.time() - t2
+            if stop:
+                break
+        self._flush_checkpoints()
         if self.early_stopping and self.early_stopping.early_stop:
             self._log(f"加载性能最佳的模型权重从: {self.early_stopping.checkpoint_path}")
             self.model.load_state_dict(torch.load(self.early_stopping.checkpoint_path, weights_only=True))
         self._log(f"--- 训练完成 --- 总训练时长: {time.time() - self.total_start_time:.2f}秒")
 
+    def _flush_checkpoints(self):
+        writer = getattr(self.model, "_checkpoint_writer", None)
+        if writer is not None:
+            writer.flush()
+
+    EVAL_CHUNK = 256        # windows per evaluation launch on the device-resident path
+
     def evaluate(self, data_loader, is_test=False, is_val=False):
-        from sklearn.metrics import accuracy_score, f1_score
+        """reference trainer.py:193-247.  Loss sum, predictions and the confusion matrix are accumulated on
+        the device (``mms_eval_accumulate``); accuracy and weighted F1 are computed from the matrix
+        (``metrics_from_confusion`` == sklearn's accuracy_score / f1_score(average='weighted')).
+        A ``DeviceBatchLoader`` is evaluated in slices of ``EVAL_CHUNK`` windows straight from the
+        device-resident array: in eval mode every window's logits are independent of its batch."""
+        from .dataset import DeviceBatchLoader
+        t0 = time.time()
         self.model.eval()
-        loss_acc = torch.zeros(1, dtype=torch.float64, device=self.device)
+        self._eval_conf.zero_()
+        self._eval_loss.zero_()
         preds, labels_all = [], []
-        lib = _ext.lib()
-        scratch = torch.empty(1, dtype=torch.float32, device=self.device)
-        with torch.no_grad():
+        if isinstance(data_loader, DeviceBatchLoader) and not data_loader.shuffle:
+            ds = data_loader.dataset
+            n, T = len(ds), int(ds.data.shape[2])
+            n_eval = n if not data_loader.drop_last else (n // data_loader.batch_size) * data_loader.batch_size
+            for i in range(0, n_eval, self.EVAL_CHUNK):
+                b = min(self.EVAL_CHUNK, n_eval - i)
+                st = self._eval_step(b, T)
+                st.x.copy_(ds.data[i:i + b])
+                st.y.copy_(ds.labels[i:i + b])
+                st.run()
+                preds.append(st.pred.clone())
+            labels_all.append(ds.labels[:n_eval])
+        else:
             for inputs, labels in data_loader:
-                inputs = inputs.to(self.device, non_blocking=True)
-                labels = labels.to(self.device, non_blocking=True)
-                outputs = self.model(inputs)
-                check(lib.mms_cross_entropy(ptr(outputs), ptr(labels), outputs.shape[0], outputs.shape[1], ptr(scratch),
-                                            None, ptr(loss_acc), stream()))
-                preds.append(torch.argmax(outputs, dim=1))          # argmax(softmax) == argmax(logits), trainer.py:224-225
-                labels_all.append(labels)
-        all_preds = torch.cat(preds).cpu().numpy()
-        all_labels = torch.cat(labels_all).cpu().numpy()
-        loss = float(loss_acc.item()) / len(data_loader.dataset)
-        acc = accuracy_score(all_labels, all_preds)
-        f1 = f1_score(all_labels, all_preds, average='weighted')
+                self._check_batch((inputs, labels))
+                st = self._eval_step(inputs.shape[0], inputs.shape[2])
+                st.x.copy_(inputs, non_blocking=True)
+                st.y.copy_(labels, non_blocking=True)
+                st.run()
+                preds.append(st.pred.clone())
+                labels_all.append(st.y.clone())
+        n_seen = sum(int(p.shape[0]) for p in preds)
+        conf = self._eval_conf.cpu().numpy().reshape(self.model.num_classes, self.model.num_classes)   # the sync
+        loss = float(self._eval_loss.item()) / len(data_loader.dataset)
+        acc, f1 = metrics_from_confusion(conf)
+        assert int(conf.sum()) == n_seen
+        self.timing['evaluate'] += time.time() - t0
+        if is_test or is_val:
+            all_preds = torch.cat(preds).cpu().numpy()
+            all_labels = torch.cat(labels_all).cpu().numpy()
         if is_test:
             self.plot_confusion_matrix(all_labels, all_preds, filename="test_confusion_matrix.png")
             self._log(f"\n--- 最终测试结果 (模型原始输出) ---")

@@ -154,3 +154,32 @@ def test_fold_sharding_world_size_2_gloo(tmp_path):
     assert "测试 S2: Accuracy = 0.5000, F1-score = 0.4000" in text
     assert "测试 S17: Accuracy = 0.6400" in text
     assert "平均准确率 (Accuracy): 0.5700" in text
+
+
+@pytest.mark.parametrize("nc", [2, 3, 5])
+def test_metrics_from_confusion_equal_sklearn(nc):
+    """accuracy / weighted F1 from the on-device confusion matrix == sklearn's accuracy_score and
+    f1_score(average='weighted') on the prediction lists (reference trainer.py:229-230), including classes
+    that never occur or are never predicted."""
+    import warnings
+    from sklearn.metrics import accuracy_score, f1_score
+    from multimodalsignal_b200.trainer import metrics_from_confusion
+    rng = np.random.default_rng(nc)
+    for trial in range(40):
+        n = int(rng.integers(1, 400))
+        y = rng.integers(0, nc, n)
+        p = rng.integers(0, nc, n)
+        if trial % 4 == 1:
+            p[:] = 0                              # one class predicted only
+        if trial % 4 == 2:
+            y[y == nc - 1] = 0                    # a class without support
+        if trial % 4 == 3:
+            p = y.copy()                          # perfect
+        conf = np.zeros((nc, nc), dtype=np.int64)
+        np.add.at(conf, (y, p), 1)
+        acc, f1 = metrics_from_confusion(conf)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            assert abs(acc - accuracy_score(y, p)) <= 1e-15
+            assert abs(f1 - f1_score(y, p, average='weighted')) <= 1e-12
+    assert metrics_from_confusion(np.zeros((nc, nc))) == (0.0, 0.0)
