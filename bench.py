@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--workload", default="train_step", choices=["train_step", "loso", "preprocess", "dp"],
                     help="train_step = headline metric (default); loso = 15-fold LOSO wall-clock; preprocess = resample+window")
     ap.add_argument("--epochs", type=int, default=100, help="loso: EPOCHS (reference main.py:62 uses 100, patience 20)")
+    ap.add_argument("--concurrent-folds", type=int, default=4, help="loso: folds interleaved per GPU on separate CUDA streams (1 = one after another)")
     ap.add_argument("--subjects", type=int, default=15, help="loso / preprocess: number of synthetic subjects")
     ap.add_argument("--minutes", type=float, default=100.0, help="loso / preprocess: recording length (100 = 4.2 M chest samples)")
     return ap.parse_args()
@@ -520,7 +521,8 @@ def run_loso(args):
 
     with contextlib.redirect_stdout(io.StringIO()):
         results = mm.run_simple_experiment(out_dir, None, pp.CHEST_CHANNEL_NAMES + pp.WRIST_CHANNEL_NAMES, subject_streams=streams,
-                                           fold_fn=timed_fold)
+                                           fold_fn=timed_fold if args.concurrent_folds <= 1 else None,
+                                           concurrent_folds=args.concurrent_folds)
     torch.cuda.synchronize()
     total = torch.tensor([time.perf_counter() - t0], device="cuda")
     if world > 1:
@@ -533,11 +535,11 @@ def run_loso(args):
                 "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": "cnn_gru_attention full LOSO-CV, folds sharded over ranks (BASELINE.json configs[2])",
                            "subjects": len(sids), "channels": NORTH_STAR_CHANNELS, "epochs_max": args.epochs, "patience": mm.PATIENCE,
-                           "batch": mm.BATCH_SIZE, "minutes": args.minutes},
+                           "batch": mm.BATCH_SIZE, "minutes": args.minutes, "concurrent_folds_per_gpu": args.concurrent_folds},
                 "preprocess_s": t_pre, "windows_trained": windows, "train_windows_per_s": windows / max(1e-9, float(total.item()) - t_pre),
                 "accuracy_mean": float(np.mean([r["accuracy"] for r in results])),
                 "f1_mean": float(np.mean([r["f1_score"] for r in results])),
-                "folds": [{k: r[k] for k in ("subject", "accuracy", "f1_score", "windows_trained", "seconds")} for r in results],
+                "folds": [{k: r[k] for k in ("subject", "accuracy", "f1_score", "windows_trained", "seconds") if k in r} for r in results],
                 "host_seconds_by_phase": {k: round(sum(r.get("timing", {}).get(k, 0.0) for r in results), 3)
                                           for k in ("train_enqueue", "train_wait", "evaluate", "bookkeeping")},
                 "gpu_launches_rank0_uncaptured": launches,

@@ -231,6 +231,14 @@ int mms_bn_relu_pool_bwd(const float* y, const double* stats, const float* gamma
  * A and W must be 16-byte aligned with lda, ldw multiples of 4. */
 int mms_tc_gemm_nt(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
                    float* C, int64_t ldc, int32_t M, int32_t N, int32_t K, int32_t accumulate, mms_stream_t stream);
+/* Tensor-core version of the tn form below (same arguments and meaning as mms_gemm_tn_acc): both row-major operands
+ * are consumed MN-major by tcgen05.mma.kind::tf32 (3xTF32 split), split-K over the grid, partial tiles added to C
+ * with red.global.add; the bias gradient is the product with an implicit column of ones.  Requires 16-byte aligned
+ * operands, lda/ldb/ldc % 4 == 0, N1 % 32 == 0 (<= 256), N2 % 32 == 0 (<= 224, 0 = bias gradient only),
+ * a_split % 32 == 0, a_skip % 32 == 0, M >= 128. */
+int mms_tc_gemm_tn(const float* A, int64_t lda, int32_t a_split, int32_t a_skip, const float* Bm, int64_t ldb,
+                   int32_t shift, int32_t seq, float* C, int64_t ldc, float* bias_grad,
+                   int32_t M, int32_t N1, int32_t N2, mms_stream_t stream);
 int mms_gemm_nt_bias(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
                      float* C, int64_t ldc, int32_t M, int32_t N, int32_t K, mms_stream_t stream);
 int mms_gemm_nn(const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc,

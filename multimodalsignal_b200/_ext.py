@@ -92,6 +92,7 @@ _SIGNATURES = {
     "mms_bn_relu_pool_fwd": (c_i32, [P, P, P, P, P, P, P, c_i32, c_i32, c_i32, c_i32, c_i32, P, P]),
     "mms_bn_relu_pool_bwd": (c_i32, [P, P, P, P, P, P, P, c_i32, c_i32, c_i32, c_i32, c_i32, P, P, P, P, P]),
     "mms_tc_gemm_nt": (c_i32, [P, c_i64, P, c_i64, P, P, c_i64, c_i32, c_i32, c_i32, c_i32, P]),
+    "mms_tc_gemm_tn": (c_i32, [P, c_i64, c_i32, c_i32, P, c_i64, c_i32, c_i32, P, c_i64, P, c_i32, c_i32, c_i32, P]),
     "mms_gemm_nt_bias": (c_i32, [P, c_i64, P, c_i64, P, P, c_i64, c_i32, c_i32, c_i32, P]),
     "mms_gemm_nn": (c_i32, [P, c_i64, P, c_i64, P, c_i64, c_i32, c_i32, c_i32, c_i32, P]),
     "mms_gemm_tn_acc": (c_i32, [P, c_i64, c_i32, c_i32, P, c_i64, c_i32, c_i32, P, c_i64, P, c_i32, c_i32, c_i32, P]),

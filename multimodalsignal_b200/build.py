@@ -21,7 +21,7 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function",
     "--expt-relaxed-constexpr",
-    "-Xptxas", "-v",
+    "-Xptxas", "-v", *os.environ.get("MMS_NVCC_EXTRA", "").split(),
 ]
 
 

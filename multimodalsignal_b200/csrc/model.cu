@@ -23,6 +23,9 @@ int launch_gemm_nt_bias(const float*, int64_t, const float*, int64_t, const floa
 int launch_gemm_nn(const float*, int64_t, const float*, int64_t, float*, int64_t, int, int, int, int, cudaStream_t);
 int launch_gemm_tn_acc(const float*, int64_t, int, int, const float*, int64_t, int, int, float*, int64_t, float*, int, int, int,
                        cudaStream_t);
+bool tc_gemm_tn_supported(const float*, int64_t, int, int, const float*, int64_t, float*, int64_t, int, int, int);
+int launch_tc_gemm_tn(const float*, int64_t, int, int, const float*, int64_t, int, int, float*, int64_t, float*, int, int, int,
+                      cudaStream_t);
 int launch_gru_fwd(const mms_gru_dir_fwd*, int, int, int, float, uint64_t, uint64_t, const int64_t*, cudaStream_t);
 int launch_gru_bwd(const mms_gru_dir_bwd*, int, int, int, float, uint64_t, uint64_t, const int64_t*, cudaStream_t);
 int launch_head_fwd2(const float*, int64_t, const float*, int64_t, int, const float*, const float*, const float*, const float*, int,
@@ -48,6 +51,14 @@ static bool use_tc() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("MMS_DISABLE_TC"); v = (e && e[0] == '1') ? 0 : 1; }
     return v == 1;
+}
+
+// Weight-gradient (TN) products: tcgen05 split-K kernel when the shape allows it, fp32 SIMT otherwise.
+static int gemm_tn(const float* A, int64_t lda, int a_split, int a_skip, const float* Bm, int64_t ldb, int shift, int seq, float* C,
+                   int64_t ldc, float* bias_grad, int M, int N1, int N2, cudaStream_t st) {
+    if (use_tc() && M >= 1024 && tc_gemm_tn_supported(A, lda, a_split, a_skip, N2 > 0 ? Bm : nullptr, ldb, N2 > 0 ? C : nullptr, ldc, M, N1, N2))
+        return launch_tc_gemm_tn(A, lda, a_split, a_skip, Bm, ldb, shift, seq, C, ldc, bias_grad, M, N1, N2, st);
+    return launch_gemm_tn_acc(A, lda, a_split, a_skip, Bm, ldb, shift, seq, C, ldc, bias_grad, M, N1, N2, st);
 }
 
 // Side streams: weight-gradient kernels do not feed the backward critical path (recurrence -> dx ->
@@ -429,15 +440,15 @@ static int model_backward(const mms_cnngru_desc* d, const float* x, const float*
         if (rc) return rc;
         // weight gradients of the top layer (off the critical path -> side stream)
         cudaStream_t sw = fk.fork(0);
-        rc = launch_gemm_tn_acc(w.D_tf, 4 * H, 3 * H, 0, in_top, I_top, 0, L, G + po.w_ih[top], I_top, G + po.b_ih[top], M, 3 * H, I_top, sw);
+        rc = gemm_tn(w.D_tf, 4 * H, 3 * H, 0, in_top, I_top, 0, L, G + po.w_ih[top], I_top, G + po.b_ih[top], M, 3 * H, I_top, sw);
         if (rc) return rc;
-        rc = launch_gemm_tn_acc(w.D_tf, 4 * H, 2 * H, H, w.hs_tf, H, -1, L, G + po.w_hh[top], H, G + po.b_hh[top], M, 3 * H, H, sw);
+        rc = gemm_tn(w.D_tf, 4 * H, 2 * H, H, w.hs_tf, H, -1, L, G + po.w_hh[top], H, G + po.b_hh[top], M, 3 * H, H, sw);
         if (rc) return rc;
-        rc = launch_gemm_tn_acc(w.D_tr, 4 * H, 3 * H, 0, in_top + (int64_t)(L - 1) * I_top, (int64_t)L * I_top, 0, 1,
+        rc = gemm_tn(w.D_tr, 4 * H, 3 * H, 0, in_top + (int64_t)(L - 1) * I_top, (int64_t)L * I_top, 0, 1,
                                 G + po.w_ih[top] + (int64_t)3 * H * I_top, I_top, G + po.b_ih[top] + 3 * H, B, 3 * H, I_top, sw);
         if (rc) return rc;
         // h_prev = 0 for the single reverse step: dW_hh(reverse) = 0, only the bias gradient remains
-        rc = launch_gemm_tn_acc(w.D_tr, 4 * H, 2 * H, H, nullptr, 0, 0, 1, nullptr, 0, G + po.b_hh[top] + 3 * H, B, 3 * H, 0, sw);
+        rc = gemm_tn(w.D_tr, 4 * H, 2 * H, H, nullptr, 0, 0, 1, nullptr, 0, G + po.b_hh[top] + 3 * H, B, 3 * H, 0, sw);
         if (rc) return rc;
         if (top >= 1) {
             // the single reverse step only touches the rows t = L-1: its B-row product goes to dx_extra on a side
@@ -501,10 +512,10 @@ static int model_backward(const mms_cnngru_desc* d, const float* x, const float*
         cudaStream_t sw = fk.fork(1 - (l & 1));
         for (int dd = 0; dd < 2; ++dd) {
             const float* Dd = w.D[l] + dd * 4 * H;
-            rc = launch_gemm_tn_acc(Dd, 8 * H, 3 * H, 0, in_l, I_l, 0, L, G + po.w_ih[l] + (int64_t)dd * 3 * H * I_l, I_l,
+            rc = gemm_tn(Dd, 8 * H, 3 * H, 0, in_l, I_l, 0, L, G + po.w_ih[l] + (int64_t)dd * 3 * H * I_l, I_l,
                                     G + po.b_ih[l] + dd * 3 * H, M, 3 * H, I_l, sw);
             if (rc) return rc;
-            rc = launch_gemm_tn_acc(Dd, 8 * H, 2 * H, H, w.hs[l] + dd * H, 2 * H, dd ? 1 : -1, L,
+            rc = gemm_tn(Dd, 8 * H, 2 * H, H, w.hs[l] + dd * H, 2 * H, dd ? 1 : -1, L,
                                     G + po.w_hh[l] + (int64_t)dd * 3 * H * H, H, G + po.b_hh[l] + dd * 3 * H, M, 3 * H, H, sw);
             if (rc) return rc;
         }

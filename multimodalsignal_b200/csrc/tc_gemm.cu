@@ -274,7 +274,8 @@ static EncodeTiledFn encode_tiled_fn() {
 }
 
 // 2-D fp32 tensor [rows, cols] with row stride ld (floats); box = [box_rows, 32 cols], 128-byte swizzle
-static int make_map(CUtensorMap* map, const float* g, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+static int make_map(CUtensorMap* map, const float* g, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                    CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn fn = encode_tiled_fn();
     MMS_REQUIRE(fn, "tc_gemm: cuTensorMapEncodeTiled is not available from the driver");
     MMS_REQUIRE((reinterpret_cast<uintptr_t>(g) & 15) == 0 && (ld * 4) % 16 == 0, "tc_gemm: operand must be 16-byte aligned with ld %% 4 == 0");
@@ -283,7 +284,7 @@ static int make_map(CUtensorMap* map, const float* g, int64_t rows, int64_t cols
     cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)g, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("tc_gemm: cuTensorMapEncodeTiled failed with %d (rows %lld cols %lld ld %lld box %d)", (int)r, (long long)rows,
                   (long long)cols, (long long)ld, box_rows);
@@ -331,6 +332,273 @@ int launch_tc_gemm_nt(const float* A, int64_t lda, const float* W, int64_t ldw, 
     return MMS_OK;
 }
 
+// ---- TN form: weight gradients of the GRU projections ----------------------------------------------
+//   C[i, j] += sum_m A[m, acol(i)] * Bm[m + shift, j]        bias_grad[i] += sum_m A[m, acol(i)]
+// with acol(i) = i < a_split ? i : i + a_skip (skips the n-gate or dq column block of the backward's D rows) and
+// rows whose shifted partner leaves its sequence (t + shift outside [0, seq)) reading as zero (h_{t-1} / h_{t+1}).
+// The reduction index m is the ROW index of both row-major operands, i.e. both are MN-major for the tensor core:
+// a TMA box of [KB rows x 32 floats] with the 128-byte / 32-byte-atom swizzle is exactly the canonical MN-major layout
+// of 32-bit operands (see umma_desc_mnmajor_sw128), so the fp32 tensors are consumed in place, no transposition pass.
+//   * M side = up to 256 columns of A as two UMMA M = 128 tiles sharing the B tile;
+//   * the bias gradient comes out of the same MMAs: B gets one extra 32-column block whose first column is 1.0;
+//   * split-K over the grid (the outputs are tiny, the reduction is B*L rows long); the partial tiles are added
+//     to C with vector red.global.add.f32 (C is the zero-initialised flat gradient buffer);
+//   * 3xTF32 operand split and warp roles as in the NT kernel; the splitter warps also zero the B rows that the
+//     shift moves across a sequence boundary.
+constexpr int TN_KB = 32;           // reduction rows per k-block
+constexpr int TN_STAGES = 2;
+constexpr int TN_BLK = TN_KB * 128; // bytes of one [KB x 32 floats] column block
+
+// MN-major 32-bit operands have ONE legal shared-memory layout: SWIZZLE_128B with a 32-byte base (Swizzle<2,5,2> on the
+// byte address): rows of 128 bytes (32 elements along M/N), the 32-byte chunks of a row XOR-ed with (row % 4); atoms of
+// 4 k-rows.  TMA produces it with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);        // start address
+    d |= (uint64_t)(TN_BLK >> 4) << 16;                 // leading byte offset: next 32-element block along M/N
+    d |= (uint64_t)(512 >> 4) << 32;                    // stride byte offset: next atom of 4 k-rows
+    d |= (uint64_t)1 << 46;                             // descriptor version (Blackwell)
+    d |= (uint64_t)1 << 61;                             // SWIZZLE_128B_BASE32B
+    return d;
+}
+
+__device__ __forceinline__ uint32_t umma_idesc_tf32_mn(int n) {
+    return umma_idesc_tf32(n) | (1u << 15) | (1u << 16);   // A and B both MN-major
+}
+
+struct TcGemmTnParams {
+    float* C;
+    float* bias_grad;
+    int64_t ldc;
+    int M, N1, N2, a_split, a_skip, shift, seq, chunk, nblkA, nblkB;   // nblkB counts the data blocks (without the ones block)
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// dynamic smem per stage: [A_hi (nblkA blocks) | A_lo | B_hi (nblkB + 1 blocks) | B_lo], 1024-byte aligned
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                                   const __grid_constant__ CUtensorMap mapB, const TcGemmTnParams p) {
+    extern __shared__ __align__(1024) uint8_t tc_smem[];
+    __shared__ __align__(8) uint64_t full_bar[TN_STAGES], split_bar[TN_STAGES], empty_bar[TN_STAGES], acc_bar;
+    __shared__ uint32_t tmem_base_sh;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool hasB = p.nblkB > 0;
+    const int nbB = p.nblkB + 1;                                   // + the ones block
+    const uint32_t a_bytes = (uint32_t)p.nblkA * TN_BLK, b_bytes = (uint32_t)nbB * TN_BLK;
+    const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem) + 1023) & ~(uintptr_t)1023);
+    const int mbeg = blockIdx.x * p.chunk, mend = min(p.M, mbeg + p.chunk);
+    const int nkb = (mend - mbeg + TN_KB - 1) / TN_KB;
+    const int ntiles = (p.N1 + 127) / 128;
+    const int Nmma = p.N2 + 16;                                    // data columns + the ones column (padded to the UMMA N step)
+    const int Nstride = (Nmma + 31) & ~31;                         // TMEM columns between the accumulators of the two M tiles
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < ntiles * Nstride) tmem_cols <<= 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TN_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&split_bar[s], 4);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(&acc_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // constant ones block of B (never touched by TMA): logical (row r, column 0) = 1 sits in 32-byte chunk (r & 3) of row r
+    if (warp >= 2) {
+        const int t = threadIdx.x - 64;
+        for (int s = 0; s < TN_STAGES; ++s) {
+            float4* hi = reinterpret_cast<float4*>(base + (size_t)s * stage_bytes + 2 * a_bytes + (size_t)p.nblkB * TN_BLK);
+            float4* lo = reinterpret_cast<float4*>(base + (size_t)s * stage_bytes + 2 * a_bytes + b_bytes + (size_t)p.nblkB * TN_BLK);
+            for (int i = t; i < TN_BLK / 16; i += 128) {
+                const int r = i >> 3, c = i & 7;
+                hi[i] = make_float4(c == 2 * (r & 3) ? 1.f : 0.f, 0.f, 0.f, 0.f);
+                lo[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_base_sh;
+
+    if (warp == 0) {
+        // ===== TMA producer: one box per 32-column block =====
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % TN_STAGES, round = kb / TN_STAGES;
+                if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);
+                uint8_t* st = base + (size_t)s * stage_bytes;
+                const int m0 = mbeg + kb * TN_KB;
+                mbar_expect_tx(&full_bar[s], (uint32_t)(p.nblkA + p.nblkB) * TN_BLK);
+                for (int b = 0; b < p.nblkA; ++b) {
+                    const int i0 = b * 32;
+                    tma_load_2d(&mapA, &full_bar[s], st + (size_t)b * TN_BLK, i0 < p.a_split ? i0 : i0 + p.a_skip, m0);
+                }
+                for (int b = 0; b < p.nblkB; ++b)
+                    tma_load_2d(&mapB, &full_bar[s], st + 2 * a_bytes + (size_t)b * TN_BLK, b * 32, m0 + p.shift);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32_mn(Nmma);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % TN_STAGES, round = kb / TN_STAGES;
+                mbar_wait(&split_bar[s], round & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t st = smem_u32(base + (size_t)s * stage_bytes);
+                const uint32_t a_hi = st, a_lo = st + a_bytes, b_hi = st + 2 * a_bytes, b_lo = st + 2 * a_bytes + b_bytes;
+#pragma unroll
+                for (int k = 0; k < TN_KB / TC_UMMA_K; ++k) {
+                    const uint32_t off = k * 1024;                  // 8 k-rows of 128 bytes
+                    const uint64_t dBh = umma_desc_mnmajor_sw128(b_hi + off), dBl = umma_desc_mnmajor_sw128(b_lo + off);
+                    for (int tile = 0; tile < ntiles; ++tile) {
+                        const uint32_t toff = off + (uint32_t)tile * 4 * TN_BLK;      // 128 columns = 4 blocks further
+                        const uint64_t dAh = umma_desc_mnmajor_sw128(a_hi + toff), dAl = umma_desc_mnmajor_sw128(a_lo + toff);
+                        const uint32_t dst = tmem_d + (uint32_t)(tile * Nstride);
+                        umma_tf32(dst, dAl, dBh, idesc, (kb | k) != 0);
+                        umma_tf32(dst, dAh, dBl, idesc, 1);
+                        umma_tf32(dst, dAh, dBh, idesc, 1);
+                    }
+                }
+                umma_commit(&empty_bar[s]);
+            }
+            umma_commit(&acc_bar);
+        }
+    } else {
+        // ===== operand splitters (warps 2..5), then epilogue =====
+        const int t = threadIdx.x - 64;
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % TN_STAGES, round = kb / TN_STAGES;
+            mbar_wait(&full_bar[s], round & 1);
+            uint8_t* st = base + (size_t)s * stage_bytes;
+            const int m0 = mbeg + kb * TN_KB;
+            {
+                float4* hi = reinterpret_cast<float4*>(st);
+                float4* lo = reinterpret_cast<float4*>(st + a_bytes);
+                for (int i = t; i < (int)(a_bytes / 16); i += 128) {
+                    const int m = m0 + ((i >> 3) & (TN_KB - 1));
+                    float4 v = hi[i];
+                    if (m >= mend) v = make_float4(0.f, 0.f, 0.f, 0.f);      // rows of the next CTA's chunk
+                    float4 h, l;
+                    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+                    h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+                    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+                    h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+                    hi[i] = h;
+                    lo[i] = l;
+                }
+            }
+            if (hasB) {
+                float4* hi = reinterpret_cast<float4*>(st + 2 * a_bytes);
+                float4* lo = reinterpret_cast<float4*>(st + 2 * a_bytes + b_bytes);
+                for (int i = t; i < p.nblkB * (TN_BLK / 16); i += 128) {
+                    const int m = m0 + ((i >> 3) & (TN_KB - 1));
+                    const int tt = (m % p.seq) + p.shift;
+                    float4 v = hi[i];
+                    if (tt < 0 || tt >= p.seq) v = make_float4(0.f, 0.f, 0.f, 0.f);   // h_{t-1} of the first / h_{t+1} of the last step
+                    float4 h, l;
+                    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+                    h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+                    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+                    h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+                    hi[i] = h;
+                    lo[i] = l;
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&split_bar[s]);
+        }
+        // ===== epilogue: TMEM lane quarter (warp % 4) -> registers -> red.global.add =====
+        mbar_wait(&acc_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int quarter = warp & 3;
+        for (int tile = 0; tile < ntiles; ++tile) {
+            const int i = tile * 128 + quarter * 32 + lane;
+            const bool live = i < p.N1;
+            float* crow = p.C ? p.C + (int64_t)i * p.ldc : nullptr;
+            for (int c0 = 0; c0 < Nmma; c0 += 16) {
+                uint32_t r[16];
+                const uint32_t taddr = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(tile * Nstride + c0);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                      "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (!live) continue;
+                if (c0 < p.N2) {
+                    if (crow) {
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4)
+                            red_add_v4(crow + c0 + 4 * j4, __uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1]),
+                                       __uint_as_float(r[4 * j4 + 2]), __uint_as_float(r[4 * j4 + 3]));
+                    }
+                } else if (p.bias_grad) {
+                    atomicAdd(p.bias_grad + i, __uint_as_float(r[0]));      // the ones column
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols) : "memory");
+    }
+}
+
+bool tc_gemm_tn_supported(const float* A, int64_t lda, int a_split, int a_skip, const float* Bm, int64_t ldb, float* C, int64_t ldc,
+                          int M, int N1, int N2) {
+    if (!encode_tiled_fn() || M < 4 * TN_KB) return false;
+    if ((reinterpret_cast<uintptr_t>(A) & 15) || lda % 4 || N1 < 1 || N1 > 256 || N1 % 32 || a_split % 32 || a_skip % 32) return false;
+    if (N2 > 0 && ((reinterpret_cast<uintptr_t>(Bm) & 15) || ldb % 4 || N2 % 32 || N2 > 224 || !C ||
+                   (reinterpret_cast<uintptr_t>(C) & 15) || ldc % 4)) return false;
+    return true;
+}
+
+int launch_tc_gemm_tn(const float* A, int64_t lda, int a_split, int a_skip, const float* Bm, int64_t ldb, int shift, int seq,
+                      float* C, int64_t ldc, float* bias_grad, int M, int N1, int N2, cudaStream_t st) {
+    if (M <= 0 || N1 <= 0) return MMS_OK;
+    if (N2 <= 0 || !Bm) { N2 = 0; Bm = nullptr; C = nullptr; }
+    MMS_REQUIRE(tc_gemm_tn_supported(A, lda, a_split, a_skip, Bm, ldb, C, ldc, M, N1, N2), "tc_gemm_tn: unsupported shape / alignment");
+    MMS_REQUIRE(seq >= 1 && (shift == 0 || M % seq == 0), "tc_gemm_tn: M must be a multiple of seq when rows are shifted");
+    CUtensorMap mapA, mapB;
+    int rc = make_map(&mapA, A, M, (a_split < N1 ? a_skip : 0) + N1, lda, TN_KB, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc) return rc;
+    if (N2 > 0) rc = make_map(&mapB, Bm, M, N2, ldb, TN_KB, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    else mapB = mapA;
+    if (rc) return rc;
+    TcGemmTnParams p;
+    p.C = C; p.bias_grad = bias_grad; p.ldc = ldc; p.M = M; p.N1 = N1; p.N2 = N2; p.a_split = a_split; p.a_skip = a_skip;
+    p.shift = shift; p.seq = seq; p.nblkA = N1 / 32; p.nblkB = N2 / 32;
+    // split-K: ~one CTA per SM pair for long reductions, never fewer than 2 k-blocks per CTA
+    int chunk = (int)align_up(cdiv(M, 96), TN_KB);
+    if (chunk < 2 * TN_KB) chunk = 2 * TN_KB;
+    p.chunk = chunk;
+    const size_t stage = (size_t)2 * p.nblkA * TN_BLK + (size_t)2 * (p.nblkB + 1) * TN_BLK;
+    const size_t smem = stage * TN_STAGES + 1024;
+    static bool attr_done = false;
+    if (!attr_done) {
+        MMS_CUDA(cudaFuncSetAttribute(tc_gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        attr_done = true;
+    }
+    MMS_REQUIRE(smem <= 220 * 1024, "tc_gemm_tn: shared memory %zu too large", smem);
+    MMS_PROF_BEGIN(st);
+    tc_gemm_tn_kernel<<<cdiv(M, chunk), TC_THREADS, smem, st>>>(mapA, mapB, p);
+    MMS_LAUNCH_CHECK("tc_gemm_tn_kernel");
+    return MMS_OK;
+}
+
 // out[c * ldo + col_off + r] = W[r * cols + c]   (W is [rows, cols] row-major)
 __global__ void __launch_bounds__(256) transpose_pad_kernel(const float* __restrict__ W, int rows, int cols, float* __restrict__ out,
                                                             int64_t ldo, int col_off) {
@@ -355,6 +623,12 @@ int launch_transpose_pad(const float* W, int rows, int cols, float* out, int64_t
 }  // namespace mms
 
 using namespace mms;
+
+extern "C" int mms_tc_gemm_tn(const float* A, int64_t lda, int32_t a_split, int32_t a_skip, const float* Bm, int64_t ldb, int32_t shift,
+                              int32_t seq, float* C, int64_t ldc, float* bias_grad, int32_t M, int32_t N1, int32_t N2, mms_stream_t stream) {
+    MMS_REQUIRE(A && (N2 == 0 || (Bm && C)), "tc_gemm_tn: null pointer");
+    return launch_tc_gemm_tn(A, lda, a_split, a_skip, Bm, ldb, shift, seq, C, ldc, bias_grad, M, N1, N2, (cudaStream_t)stream);
+}
 
 extern "C" int mms_tc_gemm_nt(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, float* C, int64_t ldc,
                               int32_t M, int32_t N, int32_t K, int32_t accumulate, mms_stream_t stream) {

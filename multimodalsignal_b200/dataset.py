@@ -135,8 +135,10 @@ class DeviceBatchLoader:
     index-gathers on the device (``torch.randperm`` on the CPU generator keeps the reference's
     shuffling semantics: a fresh permutation per epoch)."""
 
-    def __init__(self, dataset: DeviceWesadDataset, batch_size: int, shuffle: bool = False, drop_last: bool = False):
+    def __init__(self, dataset: DeviceWesadDataset, batch_size: int, shuffle: bool = False, drop_last: bool = False,
+                 generator=None):
         self.dataset, self.batch_size, self.shuffle, self.drop_last = dataset, batch_size, shuffle, drop_last
+        self.generator = generator          # as DataLoader(generator=...): the CPU generator the permutations come from
 
     def __len__(self):
         n = len(self.dataset)
@@ -144,7 +146,7 @@ class DeviceBatchLoader:
 
     def __iter__(self):
         n = len(self.dataset)
-        order = torch.randperm(n) if self.shuffle else torch.arange(n)
+        order = torch.randperm(n, generator=self.generator) if self.shuffle else torch.arange(n)
         order = order.to(self.dataset.data.device)
         for i in range(len(self)):
             sel = order[i * self.batch_size:(i + 1) * self.batch_size]

@@ -45,6 +45,7 @@ LEARNING_RATE = 0.001
 PATIENCE = 20
 WEIGHTS_DECAY = 1e-4
 ALL_SUBJECTS = [f"S{i}" for i in range(2, 18) if i != 12]
+CONCURRENT_FOLDS = int(os.environ.get("MMS_CONCURRENT_FOLDS", "1"))     # folds interleaved per GPU (new; 1 = the reference's loop)
 
 
 def fold_split(subject_to_test, all_subjects=None, seed=SEED):
@@ -67,8 +68,12 @@ def trainer_config():
                         'weight_decay': WEIGHTS_DECAY}}
 
 
-def run_fold(fold_index, subject_to_test, run_output_dir, all_channel_names, subject_streams=None):
-    """One LOSO fold (the body of the reference loop, main.py:98-125)."""
+def run_fold_async(fold_index, subject_to_test, run_output_dir, all_channel_names, subject_streams=None, stream=None,
+                   quiet=False):
+    """One LOSO fold (the body of the reference loop, main.py:98-125) as a generator that yields the CUDA events it
+    waits for (see ``trainer.Trainer``), so several folds can be interleaved on one GPU.  The shuffling generator is
+    private to the fold (``SEED + fold_index``), which makes a fold's batches independent of what runs beside it."""
+    import contextlib
     from torch.utils.data import DataLoader
     from .dataset import DeviceBatchLoader, DeviceWesadDataset, WesadDataset
     from .models import CnnGruAttentionModel
@@ -76,32 +81,78 @@ def run_fold(fold_index, subject_to_test, run_output_dir, all_channel_names, sub
 
     torch.manual_seed(SEED + fold_index)
     np.random.seed(SEED + fold_index)
-    print(f"\n--- 处理折叠: 测试受试者 {subject_to_test} ---")
+    shuffle_gen = torch.Generator().manual_seed(SEED + fold_index)
+    if not quiet:
+        print(f"\n--- 处理折叠: 测试受试者 {subject_to_test} ---")
     fold_output_dir = Path(run_output_dir) / f'fold_test_on_{subject_to_test}'
     fold_output_dir.mkdir(parents=True, exist_ok=True)
     train_subjects, val_subjects = fold_split(subject_to_test)
 
-    if subject_streams is not None:         # device-resident path
-        mk = lambda subs: DeviceWesadDataset(subject_streams, subs, CHANNELS_TO_USE, classification_mode=CLASSIFICATION_MODE)
-        train_ds, val_ds, test_ds = mk(train_subjects), mk(val_subjects), mk([subject_to_test])
-        train_loader = DeviceBatchLoader(train_ds, BATCH_SIZE, shuffle=True)
-        val_loader = DeviceBatchLoader(val_ds, BATCH_SIZE)
-        test_loader = DeviceBatchLoader(test_ds, BATCH_SIZE)
-    else:                                   # file path, exactly the reference's data flow
-        mk = lambda subs: WesadDataset(EARLY_DATA_PATH, subs, CHANNELS_TO_USE, all_channel_names,
-                                       classification_mode=CLASSIFICATION_MODE)
-        train_ds, val_ds, test_ds = mk(train_subjects), mk(val_subjects), mk([subject_to_test])
-        train_loader = DataLoader(train_ds, batch_size=BATCH_SIZE, shuffle=True, num_workers=NUM_WORKERS, pin_memory=True)
-        val_loader = DataLoader(val_ds, batch_size=BATCH_SIZE, shuffle=False, num_workers=NUM_WORKERS, pin_memory=True)
-        test_loader = DataLoader(test_ds, batch_size=BATCH_SIZE, shuffle=False, num_workers=NUM_WORKERS, pin_memory=True)
-
-    model = CnnGruAttentionModel(in_channels=len(CHANNELS_TO_USE), num_classes=NUM_CLASSES,
-                                 attention=(MODEL_TO_USE != 'cnn_gru'), **MODEL_PARAMS[MODEL_TO_USE])
-    trainer = Trainer(model, fold_output_dir, trainer_config())
-    trainer.train(train_loader, val_loader)
-    _, test_acc, test_f1 = trainer.evaluate(test_loader, is_test=True)
+    with (torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()):
+        if subject_streams is not None:         # device-resident path
+            mk = lambda subs: DeviceWesadDataset(subject_streams, subs, CHANNELS_TO_USE, classification_mode=CLASSIFICATION_MODE)
+            train_ds, val_ds, test_ds = mk(train_subjects), mk(val_subjects), mk([subject_to_test])
+            train_loader = DeviceBatchLoader(train_ds, BATCH_SIZE, shuffle=True, generator=shuffle_gen)
+            val_loader = DeviceBatchLoader(val_ds, BATCH_SIZE)
+            test_loader = DeviceBatchLoader(test_ds, BATCH_SIZE)
+        else:                                   # file path, exactly the reference's data flow
+            mk = lambda subs: WesadDataset(EARLY_DATA_PATH, subs, CHANNELS_TO_USE, all_channel_names,
+                                           classification_mode=CLASSIFICATION_MODE)
+            train_ds, val_ds, test_ds = mk(train_subjects), mk(val_subjects), mk([subject_to_test])
+            train_loader = DataLoader(train_ds, batch_size=BATCH_SIZE, shuffle=True, num_workers=NUM_WORKERS, pin_memory=True,
+                                      generator=shuffle_gen)
+            val_loader = DataLoader(val_ds, batch_size=BATCH_SIZE, shuffle=False, num_workers=NUM_WORKERS, pin_memory=True)
+            test_loader = DataLoader(test_ds, batch_size=BATCH_SIZE, shuffle=False, num_workers=NUM_WORKERS, pin_memory=True)
+        model = CnnGruAttentionModel(in_channels=len(CHANNELS_TO_USE), num_classes=NUM_CLASSES,
+                                     attention=(MODEL_TO_USE != 'cnn_gru'), **MODEL_PARAMS[MODEL_TO_USE])
+    config = trainer_config()
+    config['trainer']['quiet'] = quiet
+    trainer = Trainer(model, fold_output_dir, config, stream=stream)
+    yield from trainer.train_async(train_loader, val_loader)
+    out = yield from trainer.evaluate_async(test_loader, want_lists=True)
+    _, test_acc, test_f1 = trainer.finish_test(*out)
     return {'subject': subject_to_test, 'accuracy': float(test_acc), 'f1_score': float(test_f1),
             'windows_trained': int(trainer.windows_trained), 'timing': dict(trainer.timing)}
+
+
+def run_fold(fold_index, subject_to_test, run_output_dir, all_channel_names, subject_streams=None):
+    """One LOSO fold, blocking (the reference's loop body)."""
+    from .trainer import drive
+    return drive(run_fold_async(fold_index, subject_to_test, run_output_dir, all_channel_names, subject_streams))
+
+
+def run_folds_interleaved(fold_indices, make_fold, concurrent_folds):
+    """Drive up to ``concurrent_folds`` fold generators at once from this thread, each on its own CUDA stream.
+
+    A single training step of this model keeps a B200 mostly idle (the GRU recurrences are latency-bound and occupy
+    128 thread blocks of 4 warps), and LOSO folds share nothing, so co-resident folds overlap almost for free.
+    ``make_fold(fold_index, stream)`` returns a generator that yields CUDA events; a fold is resumed as soon as the
+    event it waits for has completed.  Returns the fold results in ``fold_indices`` order."""
+    import time
+    pending = list(fold_indices)
+    results, active = {}, []
+    streams = [torch.cuda.Stream() for _ in range(max(1, concurrent_folds))]
+    free = list(range(len(streams)))
+    while pending or active:
+        while pending and free:
+            k = free.pop(0)
+            idx = pending.pop(0)
+            active.append([idx, k, make_fold(idx, streams[k]), None])
+        progressed = False
+        for slot in list(active):
+            idx, k, gen, ev = slot
+            if ev is not None and not ev.query():
+                continue
+            progressed = True
+            try:
+                slot[3] = next(gen)
+            except StopIteration as done:
+                results[idx] = done.value
+                active.remove(slot)
+                free.append(k)
+        if not progressed:
+            time.sleep(20e-6)
+    return [results[i] for i in fold_indices]
 
 
 def write_summary(run_output_dir, results):
@@ -142,18 +193,31 @@ def gather_results(local_results, world):
     return sorted(merged, key=lambda r: order.get(r['subject'], len(order)))
 
 
-def run_simple_experiment(run_output_dir, device, all_channel_names, subject_streams=None, fold_fn=None):
-    """Standard LOSO experiment; with torch.distributed initialised the folds are sharded."""
+def run_simple_experiment(run_output_dir, device, all_channel_names, subject_streams=None, fold_fn=None,
+                          concurrent_folds=1):
+    """Standard LOSO experiment; with torch.distributed initialised the folds are sharded over the ranks, and with
+    ``concurrent_folds > 1`` each rank additionally interleaves that many of its folds on separate CUDA streams."""
     import torch.distributed as dist
     world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank() if world > 1 else 0
-    fold_fn = run_fold if fold_fn is None else fold_fn
     print("\n" + "=" * 80)
     print(f"开始执行标准二分类实验 (模式: {CLASSIFICATION_MODE})")
     print("=" * 80)
-    local = []
-    for fold_index in folds_for_rank(len(ALL_SUBJECTS), rank, world):
-        local.append(fold_fn(fold_index, ALL_SUBJECTS[fold_index], run_output_dir, all_channel_names, subject_streams))
+    mine = folds_for_rank(len(ALL_SUBJECTS), rank, world)
+    if concurrent_folds > 1 and fold_fn is None:
+        if subject_streams is not None:        # normalise every subject once, before the fold streams start reading them
+            from .dataset import normalise_gather
+            for sub in subject_streams.values():
+                if len(sub.labels):
+                    normalise_gather(sub, CHANNELS_TO_USE)
+        torch.cuda.synchronize()
+        make = lambda i, st: run_fold_async(i, ALL_SUBJECTS[i], run_output_dir, all_channel_names, subject_streams, stream=st,
+                                            quiet=True)
+        local = run_folds_interleaved(mine, make, concurrent_folds)
+        torch.cuda.synchronize()
+    else:
+        fold_fn = run_fold if fold_fn is None else fold_fn
+        local = [fold_fn(i, ALL_SUBJECTS[i], run_output_dir, all_channel_names, subject_streams) for i in mine]
     results = gather_results(local, world)
     if rank == 0:
         print("\n\n====== 留一法交叉验证全部完成 ======")
@@ -184,7 +248,7 @@ def main():
         all_channel_names = [line.strip() for line in f]
     if USE_HIERARCHICAL_CLASSIFICATION:
         raise NotImplementedError("the hierarchical experiment is dead code upstream (SURVEY D7) and out of scope")
-    run_simple_experiment(run_output_dir, device, all_channel_names)
+    run_simple_experiment(run_output_dir, device, all_channel_names, concurrent_folds=CONCURRENT_FOLDS)
     if world > 1:
         dist.destroy_process_group()
 

@@ -9,6 +9,7 @@ device (the reference syncs twice per step through ``loss.item()``, trainer.py:1
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import threading
 import time
@@ -67,14 +68,14 @@ class CheckpointWriter:
     ``submit`` snapshots the model's three flat device buffers (parameters, BN running statistics,
     ``num_batches_tracked``) with three stream-ordered device copies and returns; a worker thread
     rebuilds the reference's 34-entry ``state_dict`` as plain tensors from the snapshot and writes the
-    file.  Only the newest pending snapshot is written ("latest wins": the reference overwrites the
-    same file).  ``flush()`` blocks until the file on disk is the last submitted one -- ``Trainer``
+    file.  Per file only the newest pending snapshot is written ("latest wins": the reference overwrites
+    the same file).  ``flush()`` blocks until the file on disk is the last submitted one -- ``Trainer``
     calls it before it re-loads ``best_model.pt`` and before ``train()`` returns."""
 
     def __init__(self):
         self._cv = threading.Condition()
-        self._pending = None
-        self._busy = False
+        self._pending = {}          # path -> newest snapshot for that file (insertion-ordered)
+        self._busy = None           # path being written
         self._error = None
         self._thread = None
         self._stream = None
@@ -86,7 +87,8 @@ class CheckpointWriter:
         ready.record(torch.cuda.current_stream())
         layout = self._layout(model)
         with self._cv:
-            self._pending = (snap, ready, layout, Path(path), snap[0].device)
+            self._pending.pop(str(path), None)
+            self._pending[str(path)] = (snap, ready, layout, Path(path), snap[0].device)
             if self._thread is None:
                 self._thread = threading.Thread(target=self._work, name="mms-checkpoint", daemon=True)
                 self._thread.start()
@@ -117,9 +119,11 @@ class CheckpointWriter:
     def _work(self):
         while True:
             with self._cv:
-                while self._pending is None:
+                while not self._pending:
                     self._cv.wait()
-                job, self._pending, self._busy = self._pending, None, True
+                key = next(iter(self._pending))
+                job = self._pending.pop(key)
+                self._busy = key
             try:
                 snap, ready, layout, path, dev = job
                 torch.cuda.set_device(dev)
@@ -139,16 +143,46 @@ class CheckpointWriter:
                 self._error = e
             finally:
                 with self._cv:
-                    self._busy = False
+                    self._busy = None
                     self._cv.notify_all()
 
-    def flush(self):
+    def flush(self, path=None):
+        """Wait until `path` (default: every submitted file) is on disk."""
+        key = None if path is None else str(path)
         with self._cv:
-            while self._pending is not None or self._busy:
+            while (self._pending or self._busy) if key is None else (key in self._pending or self._busy == key):
                 self._cv.wait(timeout=0.05)
         if self._error is not None:
             err, self._error = self._error, None
             raise err
+
+
+_CAPTURE_STREAMS = {}
+
+
+def capture_graph(enqueue):
+    """Record ``enqueue()`` (kernel launches on the current stream) into a ``torch.cuda.CUDAGraph``.
+
+    ``torch.cuda.graph(...)`` is deliberately not used: its ``__enter__`` synchronises the whole device, runs
+    ``gc.collect()`` and empties the allocator cache -- tens of milliseconds per capture and a stall for every
+    other stream (the concurrently training LOSO folds).  Nothing here allocates during capture, so the bare
+    ``capture_begin`` / ``capture_end`` pair on a side stream is enough; ``thread_local`` error mode lets other
+    threads (the checkpoint writer) keep issuing CUDA calls."""
+    dev = torch.cuda.current_device()
+    side = _CAPTURE_STREAMS.get(dev)
+    if side is None:
+        side = _CAPTURE_STREAMS[dev] = torch.cuda.Stream(device=dev)
+    cur = torch.cuda.current_stream()
+    side.wait_stream(cur)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        graph.capture_begin(capture_error_mode="thread_local")
+        try:
+            enqueue()
+        finally:
+            graph.capture_end()
+    cur.wait_stream(side)
+    return graph
 
 
 class FlatAdam(torch.optim.Optimizer):
@@ -202,7 +236,7 @@ class FusedTrainStep:
     a CUDA graph and replayed.  ``__call__(x, y)`` accepts device tensors or pinned host tensors
     (copied into the static graph inputs on the current stream)."""
 
-    def __init__(self, model, optimizer: FlatAdam, batch: int, seq_len: int, use_graph: bool = True, source=None):
+    def __init__(self, model, optimizer: FlatAdam, batch: int, seq_len: int, use_graph: bool = True, source=None, loss_sum=None):
         self.lib = _ext.lib()
         self.model, self.opt = model, optimizer
         self.source = source            # DeviceBatchSource: the batch is gathered on the device inside the graph
@@ -212,7 +246,7 @@ class FusedTrainStep:
         self.y = torch.zeros(batch, dtype=torch.int64, device=dev)
         self.logits = torch.zeros(batch, model.num_classes, dtype=torch.float32, device=dev)
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
-        self.loss_sum = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.loss_sum = torch.zeros(1, dtype=torch.float64, device=dev) if loss_sum is None else loss_sum
         d = CnnGruDesc()
         d.batch, d.in_channels, d.seq_len, d.num_classes = batch, model.in_channels, seq_len, model.num_classes
         d.cnn_out, d.hidden, d.layers = model.cnn_out_channels, model.gru_hidden_size, model.gru_num_layers
@@ -294,10 +328,7 @@ class FusedTrainStep:
             self._enqueue()                       # first call eager: sets kernel attributes, warms caches
             return
         if self.graph is None:
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                self._enqueue()
-            self.graph = graph
+            self.graph = capture_graph(self._enqueue)
         self.graph.replay()
 
     def post_loss(self):
@@ -342,9 +373,9 @@ class DeviceBatchSource:
         self.cursor = torch.zeros(1, dtype=torch.int64, device=dev)
         self.scratch = torch.zeros(1, dtype=torch.int32, device=dev)
 
-    def start_epoch(self, shuffle):
+    def start_epoch(self, shuffle, generator=None):
         if shuffle:
-            torch.randperm(self.n, out=self.perm_host)
+            torch.randperm(self.n, out=self.perm_host, generator=generator)
         else:
             torch.arange(self.n, out=self.perm_host)
         self.perm[:self.n].copy_(self.perm_host, non_blocking=True)
@@ -383,10 +414,7 @@ class EvalStep:
             self._enqueue()
             return
         if self.graph is None:
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                self._enqueue()
-            self.graph = graph
+            self.graph = capture_graph(self._enqueue)
         self.graph.replay()
 
 
@@ -440,10 +468,27 @@ def _checkpoint_writer():
     return _WRITER
 
 
-class Trainer:
-    """reference trainer.py:41-247."""
+def drive(gen):
+    """Run one of the ``*_async`` generators below to completion on the calling thread: wait for every CUDA
+    event it yields and return its result."""
+    try:
+        while True:
+            next(gen).synchronize()
+    except StopIteration as done:
+        return done.value
 
-    def __init__(self, model, fold_output_dir: Path, config):
+
+class Trainer:
+    """reference trainer.py:41-247.
+
+    ``train`` / ``evaluate`` keep the reference's blocking signatures.  Underneath they are generators
+    (``train_async`` / ``evaluate_async``) that enqueue device work and *yield a CUDA event* wherever the reference
+    reads a result back (``loss.item()``, the prediction lists): a caller that owns several trainers -- the LOSO
+    folds of ``main.run_simple_experiment(concurrent_folds=K)`` -- resumes whichever one's event has completed, so
+    K independent folds keep K CUDA streams busy from ONE host thread.  ``stream`` (optional) is the CUDA stream all
+    of this trainer's work is issued on."""
+
+    def __init__(self, model, fold_output_dir: Path, config, stream=None):
         self.model, self.fold_dir, self.config = model, Path(fold_output_dir), config
         self.fold_dir.mkdir(parents=True, exist_ok=True)
         self.log_file = self.fold_dir / 'training_log.txt'
@@ -453,15 +498,23 @@ class Trainer:
         if not torch.cuda.is_available():
             raise _ext.MmsError("Trainer needs a CUDA device (B200); there is no CPU fallback")
         self.device = torch.device("cuda", torch.cuda.current_device())
-        self.model.to(self.device)
-
+        self.stream = stream
         t = config['trainer']
         self.epochs, self.learning_rate = t['epochs'], t['learning_rate']
         self.patience, self.weight_decay = t['early_stopping']['patience'], t['weight_decay']
         self.use_class_weights = t.get('use_class_weights', False)     # never enabled upstream
         self.use_graph = t.get('cuda_graph', True)
+        self.quiet = t.get('quiet', False)                             # log to the file only
 
-        self.optimizer = FlatAdam(self.model, lr=self.learning_rate, weight_decay=self.weight_decay)
+        with self._on_stream():
+            self.model.to(self.device)
+            self.optimizer = FlatAdam(self.model, lr=self.learning_rate, weight_decay=self.weight_decay)
+            nc = model.num_classes
+            self._eval_conf = torch.zeros(nc * nc, dtype=torch.int64, device=self.device)
+            self._eval_loss = torch.zeros(1, dtype=torch.float64, device=self.device)
+            self._train_loss = torch.zeros(1, dtype=torch.float64, device=self.device)
+        self._host_conf = torch.zeros(nc * nc, dtype=torch.int64).pin_memory()
+        self._host_loss = torch.zeros(2, dtype=torch.float64).pin_memory()       # [0] training sum, [1] evaluation sum
         self.criterion = CrossEntropyLoss()
         self.scheduler = ReduceLROnPlateau(self.optimizer, mode='min', factor=0.1, patience=3)
         self.early_stopping = None
@@ -472,8 +525,6 @@ class Trainer:
         self._steps = {}
         self._eval_steps = {}
         self._sources = {}
-        self._eval_conf = torch.zeros(model.num_classes * model.num_classes, dtype=torch.int64, device=self.device)
-        self._eval_loss = torch.zeros(1, dtype=torch.float64, device=self.device)
         self.async_checkpoint = t.get('async_checkpoint', True)
         if self.async_checkpoint:
             self.model._checkpoint_writer = _checkpoint_writer()
@@ -481,15 +532,25 @@ class Trainer:
         self.windows_trained = 0
         self.timing = {'train_enqueue': 0.0, 'train_wait': 0.0, 'evaluate': 0.0, 'bookkeeping': 0.0}
 
+    def _on_stream(self):
+        return torch.cuda.stream(self.stream) if self.stream is not None else contextlib.nullcontext()
+
+    def _event(self):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        return ev
+
     def _log(self, message):
-        print(message)
+        if not self.quiet:
+            print(message)
         with open(self.log_file, 'a') as f:
             f.write(message + '\n')
 
     def _fused(self, batch, seq_len, source=None):
         key = (batch, seq_len, id(source))
         if key not in self._steps:
-            self._steps[key] = FusedTrainStep(self.model, self.optimizer, batch, seq_len, use_graph=self.use_graph, source=source)
+            self._steps[key] = FusedTrainStep(self.model, self.optimizer, batch, seq_len, use_graph=self.use_graph, source=source,
+                                              loss_sum=self._train_loss)
         return self._steps[key]
 
     def _eval_step(self, batch, seq_len):
@@ -504,9 +565,6 @@ class Trainer:
     def _check_batch(batch):
         if isinstance(batch[0], (list, tuple)):
             raise NotImplementedError("HybridDataset inputs (reference void/dataset.py) are out of scope")
-
-    def _loss_sum(self):
-        return sum(float(s.loss_sum.item()) for s in self._steps.values())
 
     def _train_epoch_host(self, train_loader):
         """trainer.py:130-149 with a one-batch look-ahead: the H2D copy of the next batch runs on a copy
@@ -535,7 +593,7 @@ class Trainer:
         if src is None or src.data is not ds.data:
             src = DeviceBatchSource(ds, loader.batch_size)
             self._sources[id(ds)] = src
-        src.start_epoch(loader.shuffle)
+        src.start_epoch(loader.shuffle, getattr(loader, "generator", None))
         full, tail = divmod(src.n, loader.batch_size)
         T = int(ds.data.shape[2])
         if full:
@@ -546,25 +604,34 @@ class Trainer:
             self._fused(tail, T, src).run()
         self.windows_trained += src.n if not loader.drop_last else full * loader.batch_size
 
-    def train(self, train_loader, val_loader):
+    def _enqueue_train_epoch(self, train_loader):
         from .dataset import DeviceBatchLoader
+        self.model.train()
+        self._train_loss.zero_()
+        if isinstance(train_loader, DeviceBatchLoader):
+            self._train_epoch_device(train_loader)
+        else:
+            self._train_epoch_host(train_loader)
+        self._host_loss[0:1].copy_(self._train_loss, non_blocking=True)
+        return self._event()
+
+    def train(self, train_loader, val_loader):
+        return drive(self.train_async(train_loader, val_loader))
+
+    def train_async(self, train_loader, val_loader):
         best_val_acc = 0
         for epoch in range(self.epochs):
             t0 = time.time()
-            self.model.train()
-            for s in self._steps.values():
-                s.loss_sum.zero_()
-            if isinstance(train_loader, DeviceBatchLoader):
-                self._train_epoch_device(train_loader)
-            else:
-                self._train_epoch_host(train_loader)
+            with self._on_stream():
+                done = self._enqueue_train_epoch(train_loader)
             t1 = time.time()
-            train_loss = self._loss_sum()                  # one sync per epoch instead of two per step
+            yield done                                     # one read-back per epoch instead of two syncs per step
+            train_loss = float(self._host_loss[0])
             epoch_duration = time.time() - t0
             self.timing['train_enqueue'] += t1 - t0
             self.timing['train_wait'] += epoch_duration - (t1 - t0)
 
-            val_loss, val_acc, val_f1, val_preds, val_labels = self.evaluate(val_loader, is_val=True)
+            val_loss, val_acc, val_f1 = yield from self.evaluate_async(val_loader)
             t2 = time.time()
             self.scheduler.step(val_loss)
             best_val_acc = max(best_val_acc, val_acc)
@@ -576,7 +643,8 @@ class Trainer:
                       f"验证F1: {val_f1:.4f}")
             stop = False
             if self.early_stopping:
-                self.early_stopping(val_loss, self.model)
+                with self._on_stream():
+                    self.early_stopping(val_loss, self.model)
                 if self.early_stopping.early_stop:
                     self._log("触发早停")
                     stop = True
@@ -586,24 +654,19 @@ class Trainer:
         self._flush_checkpoints()
         if self.early_stopping and self.early_stopping.early_stop:
             self._log(f"加载性能最佳的模型权重从: {self.early_stopping.checkpoint_path}")
-            self.model.load_state_dict(torch.load(self.early_stopping.checkpoint_path, weights_only=True))
+            with self._on_stream():
+                self.model.load_state_dict(torch.load(self.early_stopping.checkpoint_path, weights_only=True))
         self._log(f"--- 训练完成 --- 总训练时长: {time.time() - self.total_start_time:.2f}秒")
 
     def _flush_checkpoints(self):
         writer = getattr(self.model, "_checkpoint_writer", None)
-        if writer is not None:
-            writer.flush()
+        if writer is not None and self.early_stopping is not None:
+            writer.flush(self.early_stopping.checkpoint_path)
 
     EVAL_CHUNK = 256        # windows per evaluation launch on the device-resident path
 
-    def evaluate(self, data_loader, is_test=False, is_val=False):
-        """reference trainer.py:193-247.  Loss sum, predictions and the confusion matrix are accumulated on
-        the device (``mms_eval_accumulate``); accuracy and weighted F1 are computed from the matrix
-        (``metrics_from_confusion`` == sklearn's accuracy_score / f1_score(average='weighted')).
-        A ``DeviceBatchLoader`` is evaluated in slices of ``EVAL_CHUNK`` windows straight from the
-        device-resident array: in eval mode every window's logits are independent of its batch."""
+    def _enqueue_evaluate(self, data_loader, want_lists):
         from .dataset import DeviceBatchLoader
-        t0 = time.time()
         self.model.eval()
         self._eval_conf.zero_()
         self._eval_loss.zero_()
@@ -618,33 +681,71 @@ class Trainer:
                 st.x.copy_(ds.data[i:i + b])
                 st.y.copy_(ds.labels[i:i + b])
                 st.run()
-                preds.append(st.pred.clone())
-            labels_all.append(ds.labels[:n_eval])
+                if want_lists:
+                    preds.append(st.pred.clone())
+            if want_lists:
+                labels_all.append(ds.labels[:n_eval])
+            n_seen = n_eval
         else:
+            n_seen = 0
             for inputs, labels in data_loader:
                 self._check_batch((inputs, labels))
                 st = self._eval_step(inputs.shape[0], inputs.shape[2])
                 st.x.copy_(inputs, non_blocking=True)
                 st.y.copy_(labels, non_blocking=True)
                 st.run()
-                preds.append(st.pred.clone())
-                labels_all.append(st.y.clone())
-        n_seen = sum(int(p.shape[0]) for p in preds)
-        conf = self._eval_conf.cpu().numpy().reshape(self.model.num_classes, self.model.num_classes)   # the sync
-        loss = float(self._eval_loss.item()) / len(data_loader.dataset)
-        acc, f1 = metrics_from_confusion(conf)
-        assert int(conf.sum()) == n_seen
+                n_seen += int(inputs.shape[0])
+                if want_lists:
+                    preds.append(st.pred.clone())
+                    labels_all.append(st.y.clone())
+        self._host_conf.copy_(self._eval_conf, non_blocking=True)
+        self._host_loss[1:2].copy_(self._eval_loss, non_blocking=True)
+        lists = None
+        if want_lists:
+            lists = []
+            for t in (preds, labels_all):
+                dev_t = torch.cat(t) if t else torch.zeros(0, dtype=torch.int64, device=self.device)
+                host_t = torch.empty(dev_t.shape, dtype=dev_t.dtype).pin_memory()
+                lists.append(host_t.copy_(dev_t, non_blocking=True))
+        return self._event(), n_seen, lists
+
+    def evaluate_async(self, data_loader, want_lists=False):
+        """Generator form of ``evaluate``: yields the CUDA event that marks the read-back, then returns
+        ``(loss, acc, f1)`` (plus the prediction / label arrays with ``want_lists``)."""
+        t0 = time.time()
+        with self._on_stream():
+            done, n_seen, lists = self._enqueue_evaluate(data_loader, want_lists)
         self.timing['evaluate'] += time.time() - t0
-        if is_test or is_val:
-            all_preds = torch.cat(preds).cpu().numpy()
-            all_labels = torch.cat(labels_all).cpu().numpy()
+        yield done
+        nc = self.model.num_classes
+        conf = self._host_conf.numpy().reshape(nc, nc).copy()
+        loss = float(self._host_loss[1]) / len(data_loader.dataset)
+        acc, f1 = metrics_from_confusion(conf)
+        if int(conf.sum()) != n_seen:
+            raise _ext.MmsError(f"evaluation counted {int(conf.sum())} windows, expected {n_seen}")
+        if want_lists:
+            return loss, acc, f1, lists[0].numpy(), lists[1].numpy()
+        return loss, acc, f1
+
+    def evaluate(self, data_loader, is_test=False, is_val=False):
+        """reference trainer.py:193-247.  Loss sum, predictions and the confusion matrix are accumulated on
+        the device (``mms_eval_accumulate``); accuracy and weighted F1 are computed from the matrix
+        (``metrics_from_confusion`` == sklearn's accuracy_score / f1_score(average='weighted')).
+        A ``DeviceBatchLoader`` is evaluated in slices of ``EVAL_CHUNK`` windows straight from the
+        device-resident array: in eval mode every window's logits are independent of its batch."""
+        out = drive(self.evaluate_async(data_loader, want_lists=is_test or is_val))
         if is_test:
-            self.plot_confusion_matrix(all_labels, all_preds, filename="test_confusion_matrix.png")
-            self._log(f"\n--- 最终测试结果 (模型原始输出) ---")
-            self._log(f"测试损失: {loss:.4f} | 测试Acc: {acc:.4f} | 测试F1: {f1:.4f}")
-            return loss, acc, f1
+            return self.finish_test(*out)
         if is_val:
+            loss, acc, f1, all_preds, all_labels = out
             return loss, acc, f1, list(all_preds), list(all_labels)
+        return out
+
+    def finish_test(self, loss, acc, f1, all_preds, all_labels):
+        """The is_test tail of reference trainer.py:231-240: confusion-matrix plot + the two log lines."""
+        self.plot_confusion_matrix(all_labels, all_preds, filename="test_confusion_matrix.png")
+        self._log(f"\n--- 最终测试结果 (模型原始输出) ---")
+        self._log(f"测试损失: {loss:.4f} | 测试Acc: {acc:.4f} | 测试F1: {f1:.4f}")
         return loss, acc, f1
 
     def plot_confusion_matrix(self, true_labels, pred_labels, filename="confusion_matrix.png"):

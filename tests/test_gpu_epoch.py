@@ -203,3 +203,46 @@ def test_sync_checkpoint_option_matches_async(tmp_path):
         if k != "classifier.3.bias":
             assert torch.equal(a[k], sd[k].cpu()), k
             assert a[k].dtype == sd[k].dtype and a[k].shape == sd[k].shape
+
+
+def test_interleaved_folds_equal_sequential_folds(tmp_path):
+    """``run_folds_interleaved`` (several trainers resumed from one host thread, each on its own CUDA stream) gives
+    every fold what it gets when the folds run one after another: same epochs, accuracy/F1 and -- up to the
+    fp32-atomic ordering noise of the weight-gradient reductions -- the same losses."""
+    import warnings
+    from multimodalsignal_b200 import main as mm
+    from multimodalsignal_b200.dataset import DeviceBatchLoader
+    from multimodalsignal_b200.models import CnnGruAttentionModel
+    from multimodalsignal_b200.trainer import Trainer, drive
+    g = torch.Generator().manual_seed(9)
+    Cc, T, B = 3, 640, 32
+    def mk(n):
+        y = torch.randint(0, 2, (n,), generator=g)
+        x = torch.randn(n, Cc, T, generator=g) + y[:, None, None].float() * torch.sin(torch.arange(T) / 5.0)
+        return _DevSet(x, y)
+    data = {i: (mk(100 + 7 * i), mk(40), mk(30)) for i in range(3)}
+    cfg = {'trainer': {'epochs': 3, 'learning_rate': 1e-3, 'quiet': True,
+                       'early_stopping': {'enabled': True, 'patience': 20, 'delta': 0}, 'weight_decay': 1e-4}}
+
+    def fold(i, stream, tag):
+        torch.manual_seed(100 + i)
+        gen = torch.Generator().manual_seed(100 + i)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            model = CnnGruAttentionModel(Cc, 2, dropout=0.0)
+        tr = Trainer(model, tmp_path / f"{tag}{i}", cfg, stream=stream)
+        tl = DeviceBatchLoader(data[i][0], B, shuffle=True, generator=gen)
+        yield from tr.train_async(tl, DeviceBatchLoader(data[i][1], B))
+        out = yield from tr.evaluate_async(DeviceBatchLoader(data[i][2], B))
+        log = (tmp_path / f"{tag}{i}" / "training_log.txt").read_text(encoding="utf-8")
+        return out, [tuple(float(v) for v in m.groups()) for m in EPOCH_RE.finditer(log)], model.flat_parameters().clone()
+
+    seq = [drive(fold(i, None, "seq")) for i in range(3)]
+    par = mm.run_folds_interleaved([0, 1, 2], lambda i, st: fold(i, st, "par"), concurrent_folds=3)
+    torch.cuda.synchronize()
+    for (o1, e1, p1), (o2, e2, p2) in zip(seq, par):
+        assert len(e1) == len(e2) == 3
+        for a, b in zip(e1, e2):
+            assert abs(a[0] - b[0]) <= 2e-4 and abs(a[1] - b[1]) <= 2e-4 and a[2:] == b[2:]
+        assert abs(o1[0] - o2[0]) <= 1e-4 and o1[1:] == o2[1:]
+        torch.testing.assert_close(p1, p2, rtol=0, atol=2e-5)

@@ -28,3 +28,61 @@ def test_tc_gemm_nt_3xtf32(M, N, K, lda, acc):
     err = (Cd.double().cpu() - ref).abs().max().item()
     scale = ref.abs().max().item()
     assert err <= 1e-5 * scale, (err, scale)
+
+
+@pytest.mark.parametrize("B,L,H,N2,lda_mul,ldb_mul,mode,shift", [
+    (64, 240, 64, 128, 4, 1, "ih", 0),        # dW_ih of the top layer: D[:, r|z|n] x layer input
+    (64, 240, 64, 64, 4, 1, "hh", -1),        # dW_hh forward direction: D[:, r|z|dq] x h_{t-1}
+    (64, 240, 64, 64, 8, 2, "hh", 1),         # layer 0, reverse direction (operands are column slices of wider rows)
+    (64, 240, 64, 32, 8, 1, "ih", 0),         # layer 0 input projection (I = cnn_out = 32)
+    (7, 37, 64, 64, 4, 1, "hh", -1),          # ragged: M = 259 is not a multiple of the k-block
+    (9, 50, 32, 32, 4, 1, "hh", 1),           # H = 32 (N1 = 96)
+    (64, 240, 64, 0, 4, 1, "hh", 0),          # bias gradient only
+])
+def test_tc_gemm_tn_3xtf32(B, L, H, N2, lda_mul, ldb_mul, mode, shift):
+    """Weight-gradient products on tcgen05 (MN-major operands, split-K, red.global.add) against float64:
+    C[i, j] += sum_m A[m, acol(i)] * Bm[m + shift, j] with the sequence-boundary rows zeroed, and the bias gradient
+    from the implicit ones column.  Tolerance 2e-5 of max|C| (fp32-class; plain tf32 would be ~5e-4)."""
+    from multimodalsignal_b200 import _ext
+    lib = _ext.lib()
+    torch.manual_seed(B + L + N2 + shift)
+    M = B * L
+    lda, ldb = lda_mul * H, max(N2, 1) * ldb_mul
+    D = torch.randn(M, lda, dtype=torch.float64)
+    Bsrc = torch.randn(M, ldb, dtype=torch.float64)
+    col_off = ldb - N2 if ldb_mul > 1 else 0         # read the right-hand half of wider rows
+    Dd, Bd = D.float().cuda(), Bsrc.float().cuda()
+    a_split, a_skip = (3 * H, 0) if mode == "ih" else (2 * H, H)
+    A64 = Dd.double().cpu()
+    Asel = A64[:, :3 * H] if mode == "ih" else torch.cat([A64[:, :2 * H], A64[:, 3 * H:4 * H]], dim=1)
+    C0 = torch.randn(3 * H, max(N2, 1), dtype=torch.float64)
+    b0 = torch.randn(3 * H, dtype=torch.float64)
+    Cd, bd = C0.float().cuda(), b0.float().cuda()
+    if N2:
+        Bv = Bd.double().cpu()[:, col_off:col_off + N2].reshape(B, L, N2)
+        Bsh = torch.zeros_like(Bv)
+        if shift == -1:
+            Bsh[:, 1:] = Bv[:, :-1]
+        elif shift == 1:
+            Bsh[:, :-1] = Bv[:, 1:]
+        else:
+            Bsh = Bv
+        refC = Cd.double().cpu() + Asel.t() @ Bsh.reshape(M, N2)
+    refb = bd.double().cpu() + Asel.sum(dim=0)
+    _ext.check(lib.mms_tc_gemm_tn(Dd.data_ptr(), lda, a_split, a_skip, Bd.data_ptr() + 4 * col_off if N2 else None, ldb, shift, L,
+                                  Cd.data_ptr() if N2 else None, N2, bd.data_ptr(), M, 3 * H, N2,
+                                  torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    if N2:
+        err = (Cd.double().cpu() - refC).abs().max().item()
+        assert err <= 2e-5 * refC.abs().max().item(), (err, refC.abs().max().item())
+    errb = (bd.double().cpu() - refb).abs().max().item()
+    assert errb <= 2e-5 * refb.abs().max().item(), (errb, refb.abs().max().item())
+    # the SIMT kernel it replaces agrees too
+    C2, b2 = C0.float().cuda(), b0.float().cuda()
+    _ext.check(lib.mms_gemm_tn_acc(Dd.data_ptr(), lda, a_split, a_skip, Bd.data_ptr() + 4 * col_off if N2 else None, ldb, shift, L,
+                                   C2.data_ptr() if N2 else None, N2, b2.data_ptr(), M, 3 * H, N2, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    if N2:
+        assert (C2 - Cd).abs().max().item() <= 4e-5 * refC.abs().max().item()
+    assert (b2 - bd).abs().max().item() <= 4e-5 * refb.abs().max().item()
