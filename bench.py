@@ -386,8 +386,9 @@ def run_preprocess(args):
     def on_device(i):
         chest = {k.decode(): v for k, v in datas[i][b"signal"][b"chest"].items()}
         wrist = {k.decode(): v for k, v in datas[i][b"signal"][b"wrist"].items()}
-        rows = torch.from_numpy(pp._stream_rows(chest, pp.CHEST_CHANNELS)).cuda()
-        wr = {n: torch.from_numpy(pp._stream_rows(wrist, [n])).cuda() for n in pp.WRIST_CHANNELS}
+        dev = torch.device("cuda", torch.cuda.current_device())
+        rows = pp._UPLOADER.rows(chest, pp.CHEST_CHANNELS, dev)          # pinned, threaded staging (what preprocess_subject uses)
+        wr = {n: pp._UPLOADER.rows(wrist, [n], dev) for n in pp.WRIST_CHANNELS}
         return rows, wr
 
     def process(rows, wr, proto, want_windows):
@@ -425,14 +426,19 @@ def run_preprocess(args):
     dev_s = e0.elapsed_time(e1) * 1e-3
     launches = int(lib.mms_launch_count() - l0)
     # e2e: host arrays in, host float64 windows out
+    pinned_out = None
     t0 = time.perf_counter()
     h2d = d2h = 0
     for i in range(len(subs)):
         rows, wr = on_device(i)
         h2d += rows.numel() * 8 + sum(v.numel() * 8 for v in wr.values())
         w, n, window = process(rows, wr, protos[i], True)
-        host = w.cpu().numpy()
-        d2h += host.nbytes
+        if pinned_out is None or pinned_out.numel() < w.numel():
+            pinned_out = torch.empty(int(w.numel() * 1.25), dtype=torch.float64).pin_memory()
+        host = pinned_out[:w.numel()].view(w.shape)
+        host.copy_(w, non_blocking=True)                              # the float64 window array preprocess.py:218 saves
+        torch.cuda.current_stream().synchronize()
+        d2h += host.numel() * 8
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()
@@ -500,10 +506,10 @@ def run_loso(args):
         dist.barrier()
     l0 = lib.mms_launch_count()
     t0 = time.perf_counter()
-    streams = {}
-    for s in subs:                                          # every rank keeps all subjects resident (replicated, ~0.9 GB)
-        streams[s.sid] = pp.preprocess_subject(s.sid, s.as_pickle_dict(), po.apply_subject_quirk(s.sid, s.protocol), 64,
-                                               include_wrist=True)
+    # every rank keeps all subjects resident (replicated, ~0.65 GB); the resampling itself is sharded over the ranks
+    # and the streams are exchanged GPU-to-GPU (NCCL broadcast over NVLink)
+    streams = pp.preprocess_subjects_sharded([(s.sid, s.as_pickle_dict, po.apply_subject_quirk(s.sid, s.protocol)) for s in subs],
+                                             64, include_wrist=True)
     torch.cuda.synchronize()
     t_pre = time.perf_counter() - t0
     out_dir = Path(tempfile.mkdtemp(prefix="mms_loso_"))
@@ -539,7 +545,7 @@ def run_loso(args):
                 "preprocess_s": t_pre, "windows_trained": windows, "train_windows_per_s": windows / max(1e-9, float(total.item()) - t_pre),
                 "accuracy_mean": float(np.mean([r["accuracy"] for r in results])),
                 "f1_mean": float(np.mean([r["f1_score"] for r in results])),
-                "folds": [{k: r[k] for k in ("subject", "accuracy", "f1_score", "windows_trained", "seconds") if k in r} for r in results],
+                "folds": [{k: r[k] for k in ("subject", "accuracy", "f1_score", "windows_trained", "seconds", "start_s", "end_s") if k in r} for r in results],
                 "host_seconds_by_phase": {k: round(sum(r.get("timing", {}).get(k, 0.0) for r in results), 3)
                                           for k in ("train_enqueue", "train_wait", "evaluate", "bookkeeping")},
                 "gpu_launches_rank0_uncaptured": launches,

@@ -131,16 +131,17 @@ def run_folds_interleaved(fold_indices, make_fold, concurrent_folds):
     import time
     pending = list(fold_indices)
     results, active = {}, []
+    t_begin = time.perf_counter()
     streams = [torch.cuda.Stream() for _ in range(max(1, concurrent_folds))]
     free = list(range(len(streams)))
     while pending or active:
         while pending and free:
             k = free.pop(0)
             idx = pending.pop(0)
-            active.append([idx, k, make_fold(idx, streams[k]), None])
+            active.append([idx, k, make_fold(idx, streams[k]), None, time.perf_counter() - t_begin])
         progressed = False
         for slot in list(active):
-            idx, k, gen, ev = slot
+            idx, k, gen, ev, started = slot
             if ev is not None and not ev.query():
                 continue
             progressed = True
@@ -148,6 +149,8 @@ def run_folds_interleaved(fold_indices, make_fold, concurrent_folds):
                 slot[3] = next(gen)
             except StopIteration as done:
                 results[idx] = done.value
+                if isinstance(done.value, dict):
+                    done.value['start_s'], done.value['end_s'] = started, time.perf_counter() - t_begin
                 active.remove(slot)
                 free.append(k)
         if not progressed:

@@ -74,3 +74,19 @@ def test_nccl_data_parallel_two_gpus():
                        capture_output=True, text=True, timeout=600, env=dict(os.environ))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "dp_check ok" in r.stdout
+
+
+def test_sharded_preprocess_two_gpus():
+    """Subject-sharded resampling + NCCL broadcast of the streams == single-process preprocessing, bit for bit
+    (skipped on a single-GPU box)."""
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29637", str(ROOT / "tools" / "shard_check.py")],
+                       capture_output=True, text=True, timeout=600, env=dict(os.environ))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "shard_check ok" in r.stdout
