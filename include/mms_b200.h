@@ -197,6 +197,12 @@ int mms_chan_attn_bwd(const float* x, const float* dy, const float* w1, const fl
  * stats (float64 [2][C_out]: sum, sum of squares over (B,L_out)) optional, accumulated (+=). */
 int mms_conv1d_fwd(int32_t which, const float* x, const float* w, const float* gate, int32_t B,
                    int32_t c_in, int32_t c_out, int32_t l_in, float* y, double* stats, mms_stream_t stream);
+/* The same convolution as an implicit GEMM on the tensor cores: TMA-staged input tile (the zero padding is TMA's
+ * out-of-bounds fill), im2col + 3xTF32 operand expansion in shared memory, tcgen05.mma.kind::tf32 with the accumulator in
+ * TMEM.  Same arguments and results (fp32-class accuracy); needs l_in % 4 == 0, l_in >= 64, x 16-byte aligned and
+ * C_out <= 32.  mms_conv1d_fwd uses it when MMS_CONV_TC=1 (measured slower than the SIMT kernel at K = 42 / 80). */
+int mms_conv1d_fwd_tc(int32_t which, const float* x, const float* w, const float* gate, int32_t B,
+                      int32_t c_in, int32_t c_out, int32_t l_in, float* y, double* stats, mms_stream_t stream);
 /* dgrad: dy [B,C_out,L_out] -> dx [B,C_in,L_in] (may be NULL) and, if xdot != NULL,
  * dgate[b,c] += sum_t dx[b,c,t]*xdot[b,c,t] (the only part of conv1's dgrad training needs). */
 int mms_conv1d_dgrad(int32_t which, const float* dy, const float* w, int32_t B, int32_t c_in, int32_t c_out,

@@ -87,6 +87,7 @@ _SIGNATURES = {
     "mms_chan_attn_fwd": (c_i32, [P, P, P, c_i32, c_i32, c_i32, P, P, P, P]),
     "mms_chan_attn_bwd": (c_i32, [P, P, P, P, P, P, c_i32, c_i32, c_i32, P, P, P, P, P]),
     "mms_conv1d_fwd": (c_i32, [c_i32, P, P, P, c_i32, c_i32, c_i32, c_i32, P, P, P]),
+    "mms_conv1d_fwd_tc": (c_i32, [c_i32, P, P, P, c_i32, c_i32, c_i32, c_i32, P, P, P]),
     "mms_conv1d_dgrad": (c_i32, [c_i32, P, P, c_i32, c_i32, c_i32, c_i32, P, P, P, P]),
     "mms_conv1d_wgrad": (c_i32, [c_i32, P, P, P, c_i32, c_i32, c_i32, c_i32, P, P]),
     "mms_bn_relu_pool_fwd": (c_i32, [P, P, P, P, P, P, P, c_i32, c_i32, c_i32, c_i32, c_i32, P, P]),

@@ -8,6 +8,7 @@
 //   backward      : pool/ReLU/BN-reduction pass, BN apply pass, dgrad (optionally reduced against x
 //                   for the attention gate) and wgrad.
 #include "mms_common.cuh"
+#include <stdlib.h>
 
 namespace mms {
 
@@ -497,10 +498,26 @@ static int check_conv(int which, int c_in, int c_out) {
     return MMS_OK;
 }
 
+bool conv_fwd_tc_supported(int which, const float* x, int c_in, int c_out, int l_in);
+int launch_conv_fwd_tc(int which, const float* x, const float* w, const float* gate, int B, int c_in, int c_out, int l_in, float* y,
+                       double* stats, cudaStream_t st);
+
+// The tcgen05 implicit-GEMM convolution (conv_tc.cu) is correct to fp32 accuracy but, measured inside the training step
+// (B = 64, T = 3840), it does not beat the SIMT kernel: 22.4 us against 21.0 us per launch and +19 us per step -- with
+// K = 42 / 80 the tensor-core work is ~1 us and the per-CTA set-up (TMEM allocation, TMA round trip, operand expansion,
+// commit / wait) is exposed.  It is therefore opt-in: MMS_CONV_TC=1 (profiles/r1_conv_tc_vs_simt.md).
+static bool conv_use_tc() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MMS_CONV_TC"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+
 int launch_conv_fwd(int which, const float* x, const float* w, const float* gate, int B, int c_in, int c_out, int l_in,
                     float* y, double* stats, cudaStream_t st) {
     int rc = check_conv(which, c_in, c_out);
     if (rc) return rc;
+    if (conv_use_tc() && conv_fwd_tc_supported(which, x, c_in, c_out, l_in))     // implicit GEMM on tcgen05 (conv_tc.cu)
+        return launch_conv_fwd_tc(which, x, w, gate, B, c_in, c_out, l_in, y, stats, st);
     if (which == 1) return conv_fwd_launch<16, CONV1_K, CONV1_S, CONV1_P, 256>(x, w, gate, B, c_in, l_in, y, stats, st);
     if (c_out == 16) return conv_fwd_launch<16, CONV2_K, CONV2_S, CONV2_P, 128>(x, w, gate, B, c_in, l_in, y, stats, st);
     if (c_out == 32) return conv_fwd_launch<32, CONV2_K, CONV2_S, CONV2_P, 128>(x, w, gate, B, c_in, l_in, y, stats, st);
@@ -577,6 +594,14 @@ int launch_bn_relu_pool_bwd(const float* y, const double* stats, const float* ga
 }  // namespace mms
 
 using namespace mms;
+
+extern "C" int mms_conv1d_fwd_tc(int32_t which, const float* x, const float* w, const float* gate, int32_t B, int32_t c_in, int32_t c_out,
+                                 int32_t l_in, float* y, double* stats, mms_stream_t stream) {
+    MMS_REQUIRE(x && w && y && B > 0 && l_in > 0, "conv1d_fwd_tc: bad arguments");
+    int rc = check_conv(which, c_in, c_out);
+    if (rc) return rc;
+    return launch_conv_fwd_tc(which, x, w, gate, B, c_in, c_out, l_in, y, stats, (cudaStream_t)stream);
+}
 
 extern "C" int mms_conv1d_fwd(int32_t which, const float* x, const float* w, const float* gate, int32_t B, int32_t c_in,
                               int32_t c_out, int32_t l_in, float* y, double* stats, mms_stream_t stream) {

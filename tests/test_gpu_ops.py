@@ -82,7 +82,8 @@ CONV = {1: (7, 2, 3), 2: (5, 2, 2)}
 
 @pytest.mark.parametrize("which,ci,co,lin,gated", [(1, 6, 16, 3840, True), (1, 14, 16, 641, True), (1, 3, 16, 336, False),
                                                    (2, 16, 32, 960, False), (2, 16, 32, 85, False), (2, 16, 16, 160, False),
-                                                   (2, 16, 64, 161, False)])
+                                                   (2, 16, 64, 161, False), (1, 14, 16, 1000, True), (2, 16, 32, 100, False),
+                                                   (1, 16, 16, 520, True)])
 def test_conv1d_fwd_dgrad_wgrad(lib, which, ci, co, lin, gated):
     torch.manual_seed(which * 100 + ci)
     k, s, p = CONV[which]
@@ -106,6 +107,14 @@ def test_conv1d_fwd_dgrad_wgrad(lib, which, ci, co, lin, gated):
     close(yd, y, 1e-5, "conv fwd")
     close(stats[:co], y.detach().sum(dim=(0, 2)), 1e-5, "sum")
     close(stats[co:], (y.detach() ** 2).sum(dim=(0, 2)), 1e-5, "sumsq")
+
+    if lin % 4 == 0 and lin >= 64 and co <= 32:      # the tcgen05 implicit-GEMM version of the same convolution
+        yd2 = torch.empty(B, co, lout, device="cuda")
+        stats2 = torch.zeros(2 * co, device="cuda", dtype=torch.float64)
+        ok(lib.mms_conv1d_fwd_tc(which, P(xd), P(wd), P(gd), B, ci, co, lin, P(yd2), P(stats2), ST()))
+        close(yd2, y, 1e-5, "conv fwd (tcgen05)")
+        close(stats2[:co], y.detach().sum(dim=(0, 2)), 1e-5, "sum (tcgen05)")
+        close(stats2[co:], (y.detach() ** 2).sum(dim=(0, 2)), 1e-5, "sumsq (tcgen05)")
 
     dxd = torch.empty_like(xd)
     dgate = torch.zeros(B, ci, device="cuda")
