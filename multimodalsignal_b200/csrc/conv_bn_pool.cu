@@ -14,6 +14,18 @@ namespace mms {
 
 constexpr int CONV_CI_PAD = 16;
 
+// cp.async copies with zero fill (src-size 0 when !ok): the source address must still be valid, callers clamp it
+__device__ __forceinline__ void cp_async4_zfill(float* smem_dst, const float* gsrc, bool ok) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(ok ? 4 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async16_zfill(float* smem_dst, const float* gsrc, bool ok) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(ok ? 16 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 // ------------------------------------------------------------------------------------------
 template <int CO, int KW, int S, int P, int TL>
 __global__ void __launch_bounds__(TL) conv1d_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
@@ -28,16 +40,21 @@ __global__ void __launch_bounds__(TL) conv1d_fwd_kernel(const float* __restrict_
     const int b = blockIdx.y, l0 = blockIdx.x * TL, tid = threadIdx.x;
     const int in0 = l0 * S - P;
     const float* xb = x + (size_t)b * CI * Lin;
-#pragma unroll 4
+    // the input tile goes to shared memory with cp.async (all copies of a thread in flight at once: one memory latency
+    // for the whole tile); the weight staging below overlaps with it
     for (int idx = tid; idx < CI * SPAN; idx += TL) {
         const int c = idx / SPAN, i = idx - c * SPAN, gi = in0 + i;
-        xs[idx] = (gi >= 0 && gi < Lin) ? __ldg(xb + (size_t)c * Lin + gi) : 0.f;
+        const bool ok = gi >= 0 && gi < Lin;
+        cp_async4_zfill(xs + idx, xb + (size_t)c * Lin + (ok ? gi : 0), ok);
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#pragma unroll 4
     for (int idx = tid; idx < CO * CI * KW; idx += TL) {
         const int o = idx / (CI * KW), ck = idx - o * (CI * KW), c = ck / KW;
         const float g = gate ? gate[b * CI + c] : 1.f;
         ws[ck * CO + o] = w[idx] * g;
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
     float acc[CO];
@@ -333,15 +350,18 @@ __global__ void __launch_bounds__(TI) conv1d_dgrad_kernel(const float* __restric
     const int b = blockIdx.y, i0 = blockIdx.x * TI, tid = threadIdx.x;
     const int lbase = floor_div2(i0 + P - (KW - 1));
     const float* dyb = dy + (size_t)b * CO * Lout;
-#pragma unroll 4
-    for (int idx = tid; idx < CO * NL; idx += TI) {
+    for (int idx = tid; idx < CO * NL; idx += TI) {          // cp.async: the whole dy tile in flight at once
         const int o = idx / NL, ll = idx - o * NL, l = lbase + ll;
-        dys[idx] = (l >= 0 && l < Lout) ? __ldg(dyb + (size_t)o * Lout + l) : 0.f;
+        const bool ok = l >= 0 && l < Lout;
+        cp_async4_zfill(dys + idx, dyb + (size_t)o * Lout + (ok ? l : 0), ok);
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#pragma unroll 4
     for (int idx = tid; idx < KW * CO * CPAD; idx += TI) {
         const int c = idx % CPAD, ko = idx / CPAD, o = ko % CO, k = ko / CO;
-        ws[idx] = c < CI ? w[((size_t)o * CI + c) * KW + k] : 0.f;
+        ws[idx] = c < CI ? __ldg(w + ((size_t)o * CI + c) * KW + k) : 0.f;
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
     const int i = i0 + tid;
@@ -389,45 +409,83 @@ __global__ void __launch_bounds__(TI) conv1d_dgrad_kernel(const float* __restric
     }
 }
 
-// dw[o,c,k] += gate[b,c] * sum_l dy[b,o,l] * x[b,c,S*l+k-P]     grid = (ceil(Lout/TL), B), block 256
-template <int CO, int KW, int S, int P, int TL>
-__global__ void __launch_bounds__(256) conv1d_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
-                                                           const float* __restrict__ gate, float* __restrict__ dw, int CI,
-                                                           int Lin, int Lout) {
-    constexpr int SPAN = (TL - 1) * S + KW;
-    constexpr int TLP = TL + 1;
+// dw[o,c,k] += gate[b,c] * sum_l dy[b,o,l] * x[b,c,S*l+k-P]
+// One CTA = one batch row x TLW output positions, staged in shared memory.  A thread owns one input channel c, one group
+// of 16 output channels and every NPL-th position of the tile: its 16 x KW partial sums live in registers, so a position
+// costs 16 + KW shared-memory loads for 16 * KW FMAs (the first version re-read both operands for every FMA pair and kept
+// 96 of 256 threads busy).  The NPL position lanes of a (c, group) pair sit in one warp and are combined with shuffles;
+// one atomicAdd per weight and CTA follows (4x fewer CTAs than before).  grid = (ceil(Lout/TLW), B), block = NT.
+template <int CO, int KW, int S, int P, int TLW, int NPL, int NT>
+__global__ void __launch_bounds__(NT) conv1d_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                          const float* __restrict__ gate, float* __restrict__ dw, int CI,
+                                                          int Lin, int Lout) {
+    constexpr int SPAN = (TLW - 1) * S + KW;
+    constexpr int OG = 16, NOG = CO / OG;
+    constexpr int DLD = TLW + 4;            // padded row of the dy tile
+    static_assert(CO % OG == 0 && 32 % NPL == 0 && TLW % NPL == 0 && TLW % 4 == 0, "conv1d_wgrad: bad tiling");
     extern __shared__ __align__(16) float smem[];
-    float* dys = smem;                 // [CO][TLP]
-    float* xs = smem + CO * TLP;       // [CI][SPAN]
-    const int b = blockIdx.y, l0 = blockIdx.x * TL, tid = threadIdx.x;
+    float* dys = smem;                 // [CO][DLD]
+    float* xs = smem + CO * DLD;       // [CI][SPAN]
+    const int b = blockIdx.y, l0 = blockIdx.x * TLW, tid = threadIdx.x;
     const int in0 = l0 * S - P;
     const float* xb = x + (size_t)b * CI * Lin;
     const float* dyb = dy + (size_t)b * CO * Lout;
-    for (int idx = tid; idx < CI * SPAN; idx += 256) {
+    // Both tiles go to shared memory with cp.async (zero-filled outside the tensors): every copy of a thread is in flight at
+    // once, so the load phase costs one memory latency instead of one per row.
+    for (int idx = tid; idx < CI * SPAN; idx += NT) {
         const int c = idx / SPAN, i = idx - c * SPAN, gi = in0 + i;
-        xs[idx] = (gi >= 0 && gi < Lin) ? __ldg(xb + (size_t)c * Lin + gi) : 0.f;
+        const bool ok = gi >= 0 && gi < Lin;
+        cp_async4_zfill(xs + idx, xb + (size_t)c * Lin + (ok ? gi : 0), ok);
     }
-    for (int idx = tid; idx < CO * TL; idx += 256) {
-        const int o = idx / TL, ll = idx - o * TL, l = l0 + ll;
-        dys[o * TLP + ll] = l < Lout ? __ldg(dyb + (size_t)o * Lout + l) : 0.f;
-    }
-    __syncthreads();
-    for (int p = tid; p < CO * CI; p += 256) {
-        const int o = p / CI, c = p - o * CI;
-        float acc[KW];
-#pragma unroll
-        for (int k = 0; k < KW; ++k) acc[k] = 0.f;
-        const float* dr = dys + o * TLP;
-        const float* xr = xs + c * SPAN;
-        for (int l = 0; l < TL; ++l) {
-            const float d = dr[l];
-#pragma unroll
-            for (int k = 0; k < KW; ++k) acc[k] += d * xr[l * S + k];
+    if ((Lout & 3) == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0) {
+        for (int idx = tid; idx < CO * (TLW / 4); idx += NT) {
+            const int o = idx / (TLW / 4), i = (idx - o * (TLW / 4)) * 4;
+            const bool ok = l0 + i < Lout;            // Lout % 4 == 0: a 16-byte group is inside or outside as a whole
+            cp_async16_zfill(dys + o * DLD + i, dyb + (size_t)o * Lout + (ok ? l0 + i : 0), ok);
         }
-        const float g = gate ? gate[b * CI + c] : 1.f;
-#pragma unroll
-        for (int k = 0; k < KW; ++k) atomicAdd(dw + ((size_t)o * CI + c) * KW + k, acc[k] * g);
+    } else {
+        for (int idx = tid; idx < CO * TLW; idx += NT) {
+            const int o = idx / TLW, i = idx - o * TLW;
+            const bool ok = l0 + i < Lout;
+            cp_async4_zfill(dys + o * DLD + i, dyb + (size_t)o * Lout + (ok ? l0 + i : 0), ok);
+        }
     }
+    cp_async_wait_all();
+    __syncthreads();
+    // thread -> (pair = (c, og), position lane j); the NPL lanes of a pair are adjacent lanes of one warp
+    const int pair = tid / NPL, j = tid % NPL;
+    const int npairs = CI * NOG;
+    const bool active = pair < npairs;  // idle lanes still take part in the shuffles below
+    const int c = active ? pair / NOG : 0, og = active ? pair % NOG : 0;
+    float acc[OG][KW];
+#pragma unroll
+    for (int o = 0; o < OG; ++o)
+#pragma unroll
+        for (int k = 0; k < KW; ++k) acc[o][k] = 0.f;
+    const float* xr = xs + c * SPAN;
+    const float* dr = dys + (og * OG) * DLD;
+    for (int l = active ? j : TLW; l < TLW; l += NPL) {
+        float xv[KW];
+#pragma unroll
+        for (int k = 0; k < KW; ++k) xv[k] = xr[l * S + k];
+#pragma unroll
+        for (int o = 0; o < OG; ++o) {
+            const float d = dr[o * DLD + l];
+#pragma unroll
+            for (int k = 0; k < KW; ++k) acc[o][k] = fmaf(d, xv[k], acc[o][k]);
+        }
+    }
+    const float g = gate ? gate[b * CI + c] : 1.f;
+    float* dwp = dw + ((size_t)(og * OG) * CI + c) * KW;
+#pragma unroll
+    for (int o = 0; o < OG; ++o)
+#pragma unroll
+        for (int k = 0; k < KW; ++k) {
+            float v = acc[o][k];
+#pragma unroll
+            for (int m = NPL / 2; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+            if (active && j == (o * KW + k) % NPL) atomicAdd(dwp + (size_t)o * CI * KW + k, v * g);
+        }
 }
 
 // ---- launchers -------------------------------------------------------------------------------
@@ -471,18 +529,20 @@ static int conv_dgrad_launch(const float* dy, const float* w, int B, int CI, int
     return conv_dgrad_launch_pad<CO, KW, S, P, TI, 16>(dy, w, B, CI, Lin, dx, xdot, dgate, st);
 }
 
-template <int CO, int KW, int S, int P, int TL>
+template <int CO, int KW, int S, int P, int TLW, int NPL, int NT>
 static int conv_wgrad_launch(const float* x, const float* dy, const float* gate, int B, int CI, int Lin, float* dw,
                              cudaStream_t st) {
     const int Lout = conv_out_len(Lin, KW, S, P);
-    constexpr int SPAN = (TL - 1) * S + KW;
-    const size_t smem = (size_t)(CO * (TL + 1) + CI * SPAN) * sizeof(float);
-    auto kern = conv1d_wgrad_kernel<CO, KW, S, P, TL>;
+    constexpr int SPAN = (TLW - 1) * S + KW;
+    MMS_REQUIRE(CI * (CO / 16) * NPL <= NT, "conv1d_wgrad: %d input channels do not fit the thread mapping", CI);
+    const size_t smem = (size_t)(CO * (TLW + 4) + CI * SPAN) * sizeof(float);
+    auto kern = conv1d_wgrad_kernel<CO, KW, S, P, TLW, NPL, NT>;
     static bool attr_done = false;
-    if (!attr_done) { MMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr_done = true; }
-    dim3 grid(cdiv(Lout, TL), B);
+    if (!attr_done) { MMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr_done = true; }
+    MMS_REQUIRE(smem <= 160 * 1024, "conv1d_wgrad: shared memory %zu too large", smem);
+    dim3 grid(cdiv(Lout, TLW), B);
     MMS_PROF_BEGIN(st);
-    kern<<<grid, 256, smem, st>>>(x, dy, gate, dw, CI, Lin, Lout);
+    kern<<<grid, NT, smem, st>>>(x, dy, gate, dw, CI, Lin, Lout);
     MMS_LAUNCH_CHECK("conv1d_wgrad_kernel");
     return MMS_OK;
 }
@@ -538,10 +598,14 @@ int launch_conv_wgrad(int which, const float* x, const float* dy, const float* g
                       int l_in, float* dw, cudaStream_t st) {
     int rc = check_conv(which, c_in, c_out);
     if (rc) return rc;
-    if (which == 1) return conv_wgrad_launch<16, CONV1_K, CONV1_S, CONV1_P, 128>(x, dy, gate, B, c_in, l_in, dw, st);
-    if (c_out == 16) return conv_wgrad_launch<16, CONV2_K, CONV2_S, CONV2_P, 128>(x, dy, gate, B, c_in, l_in, dw, st);
-    if (c_out == 32) return conv_wgrad_launch<32, CONV2_K, CONV2_S, CONV2_P, 128>(x, dy, gate, B, c_in, l_in, dw, st);
-    return conv_wgrad_launch<64, CONV2_K, CONV2_S, CONV2_P, 128>(x, dy, gate, B, c_in, l_in, dw, st);
+    // conv1: C_in <= 16 pairs x 32 position lanes (512 threads); conv2: 16 channels x C_out/16 groups x 8 lanes
+    if (which == 1) {
+        if (c_in <= 8) return conv_wgrad_launch<16, CONV1_K, CONV1_S, CONV1_P, 480, 32, 256>(x, dy, gate, B, c_in, l_in, dw, st);
+        return conv_wgrad_launch<16, CONV1_K, CONV1_S, CONV1_P, 480, 32, 512>(x, dy, gate, B, c_in, l_in, dw, st);
+    }
+    if (c_out == 16) return conv_wgrad_launch<16, CONV2_K, CONV2_S, CONV2_P, 240, 8, 128>(x, dy, gate, B, c_in, l_in, dw, st);
+    if (c_out == 32) return conv_wgrad_launch<32, CONV2_K, CONV2_S, CONV2_P, 240, 8, 256>(x, dy, gate, B, c_in, l_in, dw, st);
+    return conv_wgrad_launch<64, CONV2_K, CONV2_S, CONV2_P, 240, 8, 512>(x, dy, gate, B, c_in, l_in, dw, st);
 }
 
 int launch_bn_relu_pool_fwd(const float* y, const double* stats, const float* gamma, const float* beta, float* rm,
