@@ -107,11 +107,15 @@ __global__ void __launch_bounds__(2 * H) gru_fwd_kernel(const GruFwdParams prm) 
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const int bb = min(b0 + r, B - 1);
-        live[r] = (b0 + r) < B;
+        int lv = (b0 + r) < B ? 1 : 0;
+        asm volatile("" : "+r"(lv));       // opaque: otherwise the compiler re-derives it from %ctaid and a constant-bank load every step
+        live[r] = lv != 0;
         hs_p[r] = d.hs + (int64_t)bb * d.hs_bs + (int64_t)d.t0 * d.hs_ts + ju;
         st_p[r] = do_stash ? d.stash + (int64_t)bb * d.st_bs + (int64_t)d.t0 * d.st_ts + (first ? 0 : 2 * H) + ju : nullptr;
     }
     float* const h_wr = &hsm[0][0][0] + padded<KS>(ju);      // + (buffer * R + r) * HPAD
+    uint32_t h_wr_s = (uint32_t)__cvta_generic_to_shared(h_wr);
+    asm volatile("" : "+r"(h_wr_s));                        // opaque: keep the address in a register instead of re-deriving it every step
 
     // Ring of input projections in shared memory, PF steps ahead: threads 0 .. 3H/4-1 each copy 16 bytes
     // of the 3H-float row of step s + PF with cp.async; one commit group per step.
@@ -135,11 +139,15 @@ __global__ void __launch_bounds__(2 * H) gru_fwd_kernel(const GruFwdParams prm) 
     cp_async_wait<PF - 1>();          // step 0 has landed (for the copying threads); the barrier publishes it
     __syncthreads();
 
-    int cur = 0;
+    float hprev[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) hprev[r] = 0.f;       // h0 = 0
+    static_assert(PF % 2 == 0, "the h double buffer index is the parity of the unrolled step");
     for (int s0 = 0; s0 < nsteps; s0 += PF) {
 #pragma unroll
         for (int u = 0; u < PF; ++u) {
             if (s0 + u >= nsteps) break;
+            const int cur = u & 1;    // compile-time in the unrolled body (s0 is a multiple of the even PF)
             {   // Refill the slot that was read in the PREVIOUS step (all of its readers are past the barrier that
                 // ended that step) with step s - 1 + PF; one commit group per step keeps the group count uniform.
                 const int s = s0 + u;
@@ -161,7 +169,7 @@ __global__ void __launch_bounds__(2 * H) gru_fwd_kernel(const GruFwdParams prm) 
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 float2 acc[3] = {bh2[0], bh2[1], bh2[2]};
-                const float hp = h_wr[(cur * R + r) * HPAD];                   // h_{t-1}[ju], off the dependent chain
+                const float hp = hprev[r];                                     // h_{t-1}[ju]: this thread produced it in the previous step
                 const float4* hv = reinterpret_cast<const float4*>(&hsm[cur][r][q * (KS + 4)]);
 #pragma unroll
                 for (int i4 = 0; i4 < KS / 4; ++i4) {
@@ -190,7 +198,9 @@ __global__ void __launch_bounds__(2 * H) gru_fwd_kernel(const GruFwdParams prm) 
                 const float zg = fast_sigmoid(sg[1] + gi[r][1]);
                 const float ng = fast_tanh(fmaf(rg, sg[2], gi[r][2]));
                 const float hn = fmaf(zg, hp - ng, ng);                        // (1-z)*n + z*h
-                if (first) h_wr[((cur ^ 1) * R + r) * HPAD] = hn;
+                hprev[r] = hn;
+                if (first)                                                     // predicated store, no branch; the next step waits on it
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(h_wr_s + (uint32_t)(((cur ^ 1) * R + r) * HPAD * 4)), "f"(hn) : "memory");
                 if (first && live[r]) *hs_p[r] = hn;
                 if (do_stash && live[r]) {                                     // uniform, predicated stores
                     st_p[r][0] = first ? rg : ng;
@@ -201,7 +211,6 @@ __global__ void __launch_bounds__(2 * H) gru_fwd_kernel(const GruFwdParams prm) 
             }
             cp_async_wait<PF - 2>();      // the copies for step s + 1 are complete for the copying threads ...
             __syncthreads();              // ... and, with h[cur^1], visible to every thread
-            cur ^= 1;
         }
     }
 }
