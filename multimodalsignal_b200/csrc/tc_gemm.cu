@@ -29,6 +29,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const __grid_
     extern __shared__ __align__(1024) uint8_t tc_smem[];
     __shared__ __align__(8) uint64_t full_bar[TC_STAGES], split_bar[TC_STAGES], empty_bar[TC_STAGES], acc_bar;
     __shared__ uint32_t tmem_base_sh;
+    __shared__ __align__(16) float s_bias[256];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int BN = p.BN;
@@ -39,6 +40,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const __grid_
     const int nkb = (p.K + TC_BK - 1) / TC_BK;
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < BN) tmem_cols <<= 1;
+    for (int i = threadIdx.x; i < 256; i += TC_THREADS) s_bias[i] = (p.bias && i < BN && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
@@ -137,40 +139,79 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const __grid_
         mbar_wait(&acc_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int quarter = warp & 3;
-        const int row = m0 + quarter * 32 + lane;
-        float* crow = p.C + (int64_t)row * p.ldc + n0;
-        for (int c0 = 0; c0 < BN; c0 += 16) {
-            uint32_t r[16];
-            const uint32_t taddr = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            const bool fast = row < p.M && n0 + c0 + 16 <= p.N && !p.accumulate && (p.ldc & 3) == 0 &&
-                              (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && ((n0 + c0) & 3) == 0 &&
-                              (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0;
-            if (fast) {
+        const bool aligned = !p.accumulate && (p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && (n0 & 3) == 0 &&
+                             (p.N & 3) == 0;
+        if (aligned) {
+            // Transposed store: a thread owns one accumulator ROW in TMEM, but a warp-wide store of per-row pieces touches 32
+            // different 128-byte lines (ncu: the store queue was the second-largest stall).  Each warp therefore passes its
+            // 32 x 32 block through a private shared-memory tile (the operand stages are free once acc_bar has fired) and
+            // writes 4 rows x 128 contiguous bytes per instruction.  The bias comes from shared memory (loaded at kernel
+            // start; fetching it here from global memory was the largest stall).
+            float* tb = reinterpret_cast<float*>(base) + (warp - 2) * (32 * 36);
+            const int rbase = m0 + quarter * 32;
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                const int wcols = min(32, BN - c0);           // 32 or 16 (BN is a multiple of 16)
+                uint32_t r[32];
+                const uint32_t taddr = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                      "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                    : "r"(taddr));
+                if (wcols == 32) {
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                        : "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                        : "r"(taddr + 16));
+                } else {
 #pragma unroll
-                for (int j4 = 0; j4 < 4; ++j4) {
-                    float4 v = make_float4(__uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1]), __uint_as_float(r[4 * j4 + 2]),
-                                           __uint_as_float(r[4 * j4 + 3]));
-                    if (p.bias) {
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0) + j4);
-                        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-                    }
-                    reinterpret_cast<float4*>(crow + c0)[j4] = v;
+                    for (int j = 16; j < 32; ++j) r[j] = 0u;
                 }
-            } else if (row < p.M) {
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                float4* trow = reinterpret_cast<float4*>(tb + lane * 36);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int n = n0 + c0 + j;
-                    if (n < p.N) {
-                        float v = __uint_as_float(r[j]);
-                        if (p.bias) v += __ldg(p.bias + n);
-                        if (p.accumulate) v += crow[c0 + j];
-                        crow[c0 + j] = v;
+                for (int j4 = 0; j4 < 8; ++j4)
+                    trow[j4] = make_float4(__uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1]), __uint_as_float(r[4 * j4 + 2]),
+                                           __uint_as_float(r[4 * j4 + 3]));
+                __syncwarp();
+                const int col4 = lane & 7, rsub = lane >> 3;
+                const int n = n0 + c0 + 4 * col4;
+                if (4 * col4 < wcols && n < p.N) {
+                    const float4 bv = *reinterpret_cast<const float4*>(&s_bias[c0 + 4 * col4]);
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int rr = it * 4 + rsub;
+                        if (rbase + rr < p.M) {
+                            float4 v = *reinterpret_cast<const float4*>(tb + rr * 36 + 4 * col4);
+                            v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+                            *reinterpret_cast<float4*>(p.C + (int64_t)(rbase + rr) * p.ldc + n) = v;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        } else {
+            const int row = m0 + quarter * 32 + lane;
+            float* crow = p.C + (int64_t)row * p.ldc + n0;
+            for (int c0 = 0; c0 < BN; c0 += 16) {
+                uint32_t r[16];
+                const uint32_t taddr = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                      "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (row < p.M) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int n = n0 + c0 + j;
+                        if (n < p.N) {
+                            float v = __uint_as_float(r[j]) + s_bias[c0 + j];
+                            if (p.accumulate) v += crow[c0 + j];
+                            crow[c0 + j] = v;
+                        }
                     }
                 }
             }
