@@ -502,8 +502,12 @@ def run_loso(args):
         _st(torch.zeros(mm.BATCH_SIZE, len(NORTH_STAR_CHANNELS), 3840, device="cuda"), torch.zeros(mm.BATCH_SIZE, dtype=torch.int64, device="cuda"))
     del _st, _m
     torch.cuda.synchronize()
-    if world > 1:
+    if world > 1:        # NCCL builds its communicator lazily at the first collective: also a one-time process cost
+        _w = torch.zeros(1 << 20, device="cuda")
+        dist.broadcast(_w, src=0)
+        dist.all_reduce(_w)
         dist.barrier()
+        del _w
     l0 = lib.mms_launch_count()
     t0 = time.perf_counter()
     # every rank keeps all subjects resident (replicated, ~0.65 GB); the resampling itself is sharded over the ranks
