@@ -52,6 +52,9 @@ def parse():
     ap.add_argument("--workload", default="train_step", choices=["train_step", "loso", "preprocess", "dp"],
                     help="train_step = headline metric (default); loso = 15-fold LOSO wall-clock; preprocess = resample+window")
     ap.add_argument("--epochs", type=int, default=100, help="loso: EPOCHS (reference main.py:62 uses 100, patience 20)")
+    ap.add_argument("--dp-exchange", default="peer", choices=["peer", "nccl"],
+                    help="dp: 'peer' = symmetric memory + our peer kernels (gradient all-reduce fused with Adam, CUDA graph); "
+                         "'nccl' = torch.distributed all-reduces")
     ap.add_argument("--concurrent-folds", type=int, default=4, help="loso: folds interleaved per GPU on separate CUDA streams (1 = one after another)")
     ap.add_argument("--subjects", type=int, default=15, help="loso / preprocess: number of synthetic subjects")
     ap.add_argument("--minutes", type=float, default=100.0, help="loso / preprocess: recording length (100 = 4.2 M chest samples)")
@@ -578,7 +581,8 @@ def run_dp(args):
     b = B // world
     torch.manual_seed(42)
     model = CnnGruAttentionModel(Cc, 2, dropout=0.5).to(dev).train()
-    step = DataParallelTrainStep(model, FlatAdam(model, lr=1e-3, weight_decay=1e-4), b, B, T, rank=rank)
+    peer = "symm" if args.dp_exchange == "peer" else None
+    step = DataParallelTrainStep(model, FlatAdam(model, lr=1e-3, weight_decay=1e-4), b, B, T, rank=rank, peer=peer)
     gen = torch.Generator(device=dev).manual_seed(7 + rank)
     NB = 16
     px = torch.randn(NB, b, Cc, T, device=dev, generator=gen)
@@ -602,8 +606,10 @@ def run_dp(args):
                 "unit": "windows/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms.item() / args.steps,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": "intra-fold data parallel (BASELINE.json configs[4])", "global_batch": B, "local_batch": b, "channels": Cc,
-                           "seq_len": T, "parallelism": f"dp{world}: SyncBN (4 x <=1 KB all-reduce) + 1 flat gradient all-reduce (0.5 MB) per step",
-                           "cuda_graph": False},
+                           "seq_len": T, "parallelism": (f"dp{world}: SyncBN (4 x <=1 KB) + flat gradient (0.5 MB) exchanged by peer-memory kernels over NVLink, "
+                                           "gradient all-reduce fused with Adam, one CUDA graph per rank") if peer else
+                                          f"dp{world}: SyncBN (4 x <=1 KB all-reduce) + 1 flat gradient all-reduce (0.5 MB) per step (NCCL)",
+                           "exchange": args.dp_exchange, "cuda_graph": bool(peer)},
                 "final_loss": loss}
         print(json.dumps(line), flush=True)
     dist.destroy_process_group()

@@ -135,6 +135,26 @@ int mms_cross_entropy_partial(const float* logits, const int64_t* labels, int32_
                               int32_t global_batch, float* loss_out, float* dlogits, double* loss_sum_accum,
                               mms_stream_t stream);
 
+/* The two exchange steps of intra-fold data parallelism WITHOUT a communication library on the data path:
+ * the peers' buffers (symmetric memory mapped into this process, e.g. torch.distributed._symmetric_memory) are read
+ * directly over NVLink and the ranks synchronise through flags in each other's signal pads.
+ *   bufs_host / grads_host : HOST array of `world` device pointers, entry p = rank p's copy of the buffer;
+ *   signals_host           : HOST array of `world` device pointers to the ranks' signal pads (uint32 words, zero at start);
+ *                            a call uses words [signal_base, signal_base + 2*world) of every pad;
+ *   epoch_dev              : local uint32 counter (zero at start), advanced by the call.
+ * Every rank must make the same sequence of calls.  Nothing here blocks the host.
+ * mms_peer_allreduce_f64: in-place sum of `count` (<= 256) doubles -- the SyncBN (sum, sum of squares) / (sum dy, sum dy*xhat)
+ * vectors whose workspace offsets mms_cnngru_sync_offsets() reports.
+ * mms_peer_allreduce_adam: flat gradient all-reduce FUSED with mms_adam_flat_step (trainer.py:148-149): the gradients of
+ * all ranks are summed on the fly in rank order (bit-identical parameters on every rank) and consumed by the Adam update;
+ * scratch2_dev: two zero-initialised local uint32. */
+int mms_peer_allreduce_f64(const void* const* bufs_host, void* const* signals_host, int32_t world, int32_t rank,
+                           int32_t signal_base, int32_t count, uint32_t* epoch_dev, mms_stream_t stream);
+int mms_peer_allreduce_adam(float* params, const void* const* grads_host, void* const* signals_host, int32_t world,
+                            int32_t rank, int32_t signal_base, float* exp_avg, float* exp_avg_sq, int64_t n,
+                            const float* lr_dev, float beta1, float beta2, float eps, float weight_decay,
+                            int64_t* step_dev, uint32_t* epoch_dev, uint32_t* scratch2_dev, mms_stream_t stream);
+
 /* trainer.py:69,147 CrossEntropyLoss() (mean): loss_out[0] = mean_b(lse - logit[y]),
  * dlogits = (softmax - onehot)/B (NULL to skip).  If loss_sum_accum != NULL it receives
  * += loss * B in float64 (trainer.py:152 accumulates loss.item()*batch_size on the host;

@@ -10,6 +10,12 @@ on NVLink 5 / NVSwitch, which is why the gradient is one flat buffer and one col
 
 The step is written as a generator that yields the tensors to reduce, so the same code runs under
 ``torch.distributed`` (NCCL) and in the single-process emulation the parity tests use.
+
+``peer=`` selects the B200-native exchange instead: the workspace and the gradient buffer live in symmetric memory
+(``torch.distributed._symmetric_memory``: allocation + rendezvous are plumbing), and the five exchange points are OUR
+kernels reading the peers' buffers over NVLink -- ``mms_peer_allreduce_f64`` for the SyncBN vectors and
+``mms_peer_allreduce_adam``, the gradient all-reduce fused with the Adam update (csrc/peer.cu).  No communication-library
+call is left on the data path, and the whole step (kernels + flag barriers) is one CUDA graph per rank.
 """
 from __future__ import annotations
 
@@ -25,9 +31,14 @@ from .trainer import FlatAdam
 class DataParallelTrainStep:
     """One rank's share of a data-parallel training step.  ``local_batch`` rows of a ``global_batch`` batch."""
 
-    def __init__(self, model, optimizer: FlatAdam, local_batch: int, global_batch: int, seq_len: int, rank: int = 0, group=None):
+    def __init__(self, model, optimizer: FlatAdam, local_batch: int, global_batch: int, seq_len: int, rank: int = 0, group=None,
+                 peer=None, use_graph: bool = True):
+        """``peer``: None = ``torch.distributed`` all-reduces (NCCL); ``"symm"`` = symmetric memory + the peer kernels
+        (one process per GPU, needs an initialised process group); a ``LocalPeers`` registry = several ranks emulated
+        inside one process on one GPU (tests)."""
         self.lib = _ext.lib()
         self.model, self.opt, self.group = model, optimizer, group
+        self.peer, self.rank = peer, rank
         self.flat = model.flat_parameters()
         dev = self.flat.device
         d = CnnGruDesc()
@@ -43,7 +54,7 @@ class DataParallelTrainStep:
         nbytes = self.lib.mms_cnngru_workspace_bytes(C.byref(d))
         if nbytes < 0:
             check(int(nbytes))
-        self.workspace = torch.zeros(int(nbytes), dtype=torch.uint8, device=dev)
+        self.workspace = self._alloc(int(nbytes), torch.uint8, dev)
         offs = (C.c_int64 * 4)()
         cnts = (C.c_int64 * 4)()
         check(self.lib.mms_cnngru_sync_offsets(C.byref(d), offs, cnts))
@@ -52,6 +63,99 @@ class DataParallelTrainStep:
         self.logits = torch.zeros(local_batch, model.num_classes, dtype=torch.float32, device=dev)
         self.dlogits = torch.zeros_like(self.logits)
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev)        # this rank's share of the global mean
+        self._sync_offsets = [(int(offs[i]), int(cnts[i])) for i in range(4)]
+        self.use_graph, self.graph, self.calls = use_graph, None, 0
+        self.x = torch.zeros(local_batch, model.in_channels, seq_len, dtype=torch.float32, device=dev)
+        self.y = torch.zeros(local_batch, dtype=torch.int64, device=dev)
+        if peer is not None:
+            self._setup_peer(dev)
+
+    # ------------------------------------------------------------------ peer-memory exchange (csrc/peer.cu)
+    def _alloc(self, n, dtype, dev):
+        if self.peer == "symm":
+            import torch.distributed._symmetric_memory as symm
+            t = symm.empty(n, dtype=dtype, device=dev)
+            t.zero_()
+            return t
+        return torch.zeros(n, dtype=dtype, device=dev)
+
+    def _setup_peer(self, dev):
+        opt = self.opt
+        grads = self._alloc(opt.grads.numel(), torch.float32, dev)          # the gradient buffer the peers read
+        opt.grads = grads
+        self.signals = self._alloc(256, torch.int32, dev)                   # this rank's signal pad
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.scratch2 = torch.zeros(2, dtype=torch.int32, device=dev)
+        if self.peer == "symm":
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm
+            group = self.group if self.group is not None else dist.group.WORLD
+            self.world = dist.get_world_size(group)
+            hw, hg, hs = (symm.rendezvous(t, group) for t in (self.workspace, grads, self.signals))
+            self._handles = (hw, hg, hs)
+            ws_ptrs, g_ptrs, s_ptrs = list(hw.buffer_ptrs), list(hg.buffer_ptrs), list(hs.buffer_ptrs)
+            torch.cuda.synchronize()
+            dist.barrier(group)                   # every rank has zeroed its buffers before anybody signals
+        else:                                     # LocalPeers: ranks of one process, plain device memory
+            self.peer.register(self.rank, self.workspace, grads, self.signals)
+            self.world = self.peer.world
+            ws_ptrs = g_ptrs = s_ptrs = None
+        self._ptrs = (ws_ptrs, g_ptrs, s_ptrs)
+        self._tables = None
+
+    def _peer_tables(self):
+        """HOST arrays of device pointers (one entry per rank) for the four SyncBN vectors, the gradients and the pads."""
+        if self._tables is None:
+            ws_ptrs, g_ptrs, s_ptrs = self._ptrs if self._ptrs[0] is not None else self.peer.pointers()
+            arr = lambda ps: (C.c_void_p * self.world)(*[int(p) for p in ps])
+            self._tables = ([arr([p + off for p in ws_ptrs]) for off, _ in self._sync_offsets], arr(g_ptrs), arr(s_ptrs))
+        return self._tables
+
+    def _peer_sum(self, k):
+        stats, _, sig = self._peer_tables()
+        check(self.lib.mms_peer_allreduce_f64(stats[k], sig, self.world, self.rank, 0, self._sync_offsets[k][1], ptr(self.epoch), stream()))
+
+    def _peer_phases(self):
+        """The whole data-parallel step with the peer kernels at the five exchange points, as a generator that yields
+        after every exchange kernel has been enqueued (the single-process emulation interleaves the ranks there)."""
+        x, y, o, g = self.x, self.y, self.opt, self.opt.param_groups[0]
+        o.grads.zero_()                                          # trainer.py:144
+        self._fwd(1, x)
+        self._peer_sum(0)                                        # SyncBN stage 1
+        yield
+        self._fwd(2, x)
+        self._peer_sum(1)
+        yield
+        self._fwd(4, x)                                          # trainer.py:146
+        check(self.lib.mms_cross_entropy_partial(ptr(self.logits), ptr(y), self.local_batch, self.model.num_classes,
+                                                 self.global_batch, ptr(self.loss), ptr(self.dlogits), None, stream()))   # :147
+        self._bwd(1, x)                                          # trainer.py:148
+        self._peer_sum(3)                                        # SyncBN backward, stage 2
+        yield
+        self._bwd(2, x)
+        self._peer_sum(2)
+        yield
+        self._bwd(4, x)
+        _, grads, sig = self._peer_tables()
+        check(self.lib.mms_peer_allreduce_adam(ptr(self.flat), grads, sig, self.world, self.rank, 0, ptr(o.exp_avg), ptr(o.exp_avg_sq),
+                                               self.flat.numel(), ptr(o.lr_dev), g['betas'][0], g['betas'][1], g['eps'],
+                                               g['weight_decay'], ptr(o.step_dev), ptr(self.epoch), ptr(self.scratch2), stream()))   # :149
+
+    def _enqueue_peer(self):
+        for _ in self._peer_phases():
+            pass
+
+    def run_peer(self):
+        """One step on the static inputs ``self.x`` / ``self.y`` (graph replay after the first call)."""
+        from .trainer import capture_graph
+        self.opt.sync_lr()
+        self.calls += 1
+        if not self.use_graph or self.calls == 1:
+            self._enqueue_peer()
+            return
+        if self.graph is None:
+            self.graph = capture_graph(self._enqueue_peer)
+        self.graph.replay()
 
     def _fwd(self, phases, x):
         m = self.model
@@ -84,6 +188,11 @@ class DataParallelTrainStep:
         self.opt.flat_step(self.flat)                            # trainer.py:149
 
     def __call__(self, x, y):
+        if self.peer is not None:
+            self.x.copy_(x, non_blocking=True)
+            self.y.copy_(y, non_blocking=True)
+            self.run_peer()
+            return
         import torch.distributed as dist
         for t in self.phases(x, y):
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
@@ -95,6 +204,44 @@ class DataParallelTrainStep:
         if dist.is_available() and dist.is_initialized():
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
         return float(t.item())
+
+
+class LocalPeers:
+    """Registry that lets several ``DataParallelTrainStep`` "ranks" of ONE process (one GPU, one stream per rank) find
+    each other's buffers: the single-GPU stand-in for symmetric memory that the peer-kernel tests use."""
+
+    def __init__(self, world):
+        self.world = world
+        self._bufs = {}
+
+    def register(self, rank, workspace, grads, signals):
+        self._bufs[rank] = (workspace, grads, signals)
+
+    def pointers(self):
+        assert len(self._bufs) == self.world, "every rank must be constructed before the first step"
+        return tuple([self._bufs[r][k].data_ptr() for r in range(self.world)] for k in range(3))
+
+
+def emulate_peer_ranks(steps, batches, streams):
+    """Single-process emulation of the peer exchange: rank r's kernels go to ``streams[r]``; the host interleaves the
+    ranks at every exchange point, so that no rank's later work is queued (possibly in the same hardware queue) in front
+    of a peer's earlier work that its flag barrier waits for.  Eager only; the graph path is exercised with one process
+    per GPU."""
+    gens = []
+    for s, (x, y), st in zip(steps, batches, streams):
+        with torch.cuda.stream(st):
+            s.x.copy_(x, non_blocking=True)
+            s.y.copy_(y, non_blocking=True)
+            s.opt.sync_lr()
+        gens.append(s._peer_phases())
+    live = list(range(len(gens)))
+    while live:
+        for r in list(live):
+            with torch.cuda.stream(streams[r]):
+                try:
+                    next(gens[r])
+                except StopIteration:
+                    live.remove(r)
 
 
 def emulate_ranks(steps, batches):

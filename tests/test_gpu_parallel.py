@@ -90,3 +90,71 @@ def test_sharded_preprocess_two_gpus():
                        capture_output=True, text=True, timeout=600, env=dict(os.environ))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "shard_check ok" in r.stdout
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("case,splits", [("c6_t640", (2, 2)), ("c6_t640", (1, 3)), ("c6_t640", (1, 1, 2)), ("c8_h32_l1", (2, 1))])
+def test_peer_memory_exchange_equals_full_batch(case, splits):
+    """The B200-native exchange (csrc/peer.cu): every rank's step -- phase-split forward/backward, SyncBN vectors summed by
+    ``mms_peer_allreduce_f64``, gradient all-reduce fused with Adam in ``mms_peer_allreduce_adam``, flag barriers through
+    the peers' signal pads -- here with the ranks emulated inside one process (one stream per rank, plain device memory in
+    place of symmetric memory).  It must reproduce the single-device full-batch step, and the ranks' parameters must
+    stay bit-identical to each other (the gradients are summed in rank order on every rank)."""
+    from multimodalsignal_b200.parallel import DataParallelTrainStep, LocalPeers, emulate_peer_ranks
+    from multimodalsignal_b200.trainer import FlatAdam, FusedTrainStep
+    z, meta = load_golden(f"model_{case}.npz")
+    sd = golden_state(z, "sd")
+    x, y = torch.from_numpy(z["x"]).cuda(), torch.from_numpy(z["y"]).cuda()
+    B, T = x.shape[0], x.shape[2]
+    assert sum(splits) == B
+    ref = _model(meta, sd)
+    ref_step = FusedTrainStep(ref, FlatAdam(ref, lr=1e-3, weight_decay=1e-4), B, T, use_graph=False)
+    # The library's side streams are process-global: with several emulated ranks enqueued one after the other from ONE
+    # host thread, rank 0's later side-stream work would queue in front of rank 1's earlier work and wait for a flag that
+    # rank 1 can then never set.  (One process per GPU -- the real configuration -- has its own side streams.)
+    from multimodalsignal_b200 import _ext
+    _ext.lib().mms_set_side_streams(0)
+    peers = LocalPeers(len(splits))
+    streams = [torch.cuda.Stream() for _ in splits]
+    ranks, steps = [], []
+    for r, b in enumerate(splits):
+        with torch.cuda.stream(streams[r]):
+            m = _model(meta, sd)
+            ranks.append(m)
+            steps.append(DataParallelTrainStep(m, FlatAdam(m, lr=1e-3, weight_decay=1e-4), b, B, T, rank=r, peer=peers, use_graph=False))
+    torch.cuda.synchronize()
+    for it in range(4):
+        ref_step(x, y)
+        lo, batches = 0, []
+        for b in splits:
+            batches.append((x[lo:lo + b], y[lo:lo + b]))
+            lo += b
+        emulate_peer_ranks(steps, batches, streams)      # rank r on stream r; the peer kernels of the ranks meet on the device
+        torch.cuda.synchronize()
+        loss = sum(float(s.loss.item()) for s in steps)
+        assert abs(loss - ref_step.last_loss()) < 2e-5, (it, loss, ref_step.last_loss())
+    ref_sd = ref.state_dict()
+    for m in ranks:
+        for k, v in m.state_dict().items():
+            if v.numel() == 0:
+                continue
+            np.testing.assert_allclose(v.float().cpu().numpy(), ref_sd[k].float().cpu().numpy(), atol=2e-5, err_msg=k)
+    _ext.lib().mms_set_side_streams(1)
+    for m in ranks[1:]:
+        assert torch.equal(m.flat_parameters(), ranks[0].flat_parameters())
+    assert int(steps[0].opt.step_dev.item()) == 4
+
+
+def test_peer_memory_exchange_two_gpus():
+    """The same over real symmetric memory / NVLink, one process per GPU (skipped on a single-GPU box)."""
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29641", str(ROOT / "tools" / "dp_check.py"), "--peer"],
+                       capture_output=True, text=True, timeout=600, env=dict(os.environ))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "dp_check ok" in r.stdout
