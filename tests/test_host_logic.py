@@ -183,3 +183,39 @@ def test_metrics_from_confusion_equal_sklearn(nc):
             assert abs(acc - accuracy_score(y, p)) <= 1e-15
             assert abs(f1 - f1_score(y, p, average='weighted')) <= 1e-12
     assert metrics_from_confusion(np.zeros((nc, nc))) == (0.0, 0.0)
+
+
+def test_run_folds_interleaved_schedules_generators_by_event_completion():
+    """The single-thread fold scheduler (main.run_folds_interleaved): at most K generators are live, a generator is resumed
+    only once the event it yielded reports completion, a finished fold frees its stream for the next pending one, and the
+    results come back in fold order.  CUDA events / streams are replaced by stand-ins (no GPU here)."""
+    from unittest import mock
+    from multimodalsignal_b200 import main as mm
+
+    class Ev:
+        def __init__(self, polls):
+            self.polls = polls
+
+        def query(self):
+            self.polls -= 1
+            return self.polls <= 0
+
+    live, max_live, order = set(), [0], []
+
+    def fold(i, stream):
+        live.add(i)
+        max_live[0] = max(max_live[0], len(live))
+        for step in range(3 + i % 2):
+            ev = Ev(polls=1 + (i * 7 + step) % 4)
+            yield ev
+            assert ev.polls <= 0, "resumed before its event completed"
+        live.discard(i)
+        order.append(i)
+        return {"fold": i, "stream": stream}
+
+    with mock.patch.object(mm.torch.cuda, "Stream", side_effect=lambda: object()):
+        res = mm.run_folds_interleaved([0, 1, 2, 3, 4, 5, 6], fold, concurrent_folds=3)
+    assert [r["fold"] for r in res] == [0, 1, 2, 3, 4, 5, 6]
+    assert max_live[0] == 3 and sorted(order) == list(range(7))
+    assert all("start_s" in r and r["end_s"] >= r["start_s"] for r in res)
+    assert len({id(r["stream"]) for r in res}) == 3          # three streams shared by seven folds
