@@ -8,43 +8,61 @@ namespace mms {
 constexpr int MAX_NC = 8;
 constexpr uint64_t HEAD_DROP_BASE = 0x4000000000ull;   // element ids of the head dropout site
 
-// grid = B, block = 64.  hid_out keeps relu(W0 last + b0) (before dropout).
-// The classifier input is the concatenation [src_a[b, 0:Hh) | src_b[b, 0:H2-Hh)] (forward-direction
+// grid = B, block = 4 * 64: thread (i, q) = (tid >> 2, tid & 3) sums a quarter of hidden unit i's dot product (128-bit
+// weight loads, all in flight at once) and the four quarters meet by shuffles.  hid_out keeps relu(W0 last + b0)
+// (before dropout).  The classifier input is the concatenation [src_a[b, 0:Hh) | src_b[b, 0:H2-Hh)] (forward-direction
 // final state and reverse-direction first-step state, models.py:79); it is also written to last_out.
-__global__ void __launch_bounds__(HEAD_HID) head_fwd_kernel(const float* __restrict__ src_a, int64_t lda,
-                                                            const float* __restrict__ src_b, int64_t ldb, int Hh,
-                                                            const float* __restrict__ w0,
-                                                            const float* __restrict__ b0, const float* __restrict__ w3,
-                                                            const float* __restrict__ b3, int H2, int nc, float p,
-                                                            uint64_t seed, uint64_t offset, const int64_t* offset_dev,
-                                                            float* __restrict__ last_out,
-                                                            float* __restrict__ hid_out, float* __restrict__ logits) {
-    extern __shared__ float s_last[];        // [H2]
+__global__ void __launch_bounds__(4 * HEAD_HID) head_fwd_kernel(const float* __restrict__ src_a, int64_t lda,
+                                                                const float* __restrict__ src_b, int64_t ldb, int Hh,
+                                                                const float* __restrict__ w0,
+                                                                const float* __restrict__ b0, const float* __restrict__ w3,
+                                                                const float* __restrict__ b3, int H2, int nc, float p,
+                                                                uint64_t seed, uint64_t offset, const int64_t* offset_dev,
+                                                                float* __restrict__ last_out,
+                                                                float* __restrict__ hid_out, float* __restrict__ logits) {
+    extern __shared__ __align__(16) float s_last[];        // [H2]
     __shared__ float s_hid[HEAD_HID];
-    const int b = blockIdx.x, i = threadIdx.x;
-    for (int k = i; k < H2; k += HEAD_HID) {
+    const int b = blockIdx.x, tid = threadIdx.x, i = tid >> 2, q = tid & 3;
+    for (int k = tid; k < H2; k += 4 * HEAD_HID) {
         const float v = k < Hh ? src_a[(size_t)b * lda + k] : src_b[(size_t)b * ldb + (k - Hh)];
         s_last[k] = v;
         if (last_out) last_out[(size_t)b * H2 + k] = v;
     }
     __syncthreads();
-    float acc = b0[i];
+    float acc = 0.f;
     const float* wr = w0 + (size_t)i * H2;
-    for (int k = 0; k < H2; ++k) acc = fmaf(__ldg(wr + k), s_last[k], acc);
-    const float h = fmaxf(acc, 0.f);
-    hid_out[(size_t)b * HEAD_HID + i] = h;
-    float m = 1.f;
-    if (p > 0.f) {
-        DropRng rng;
-        rng.init(seed, resolve_offset(offset, offset_dev), p);
-        m = rng.mult(HEAD_DROP_BASE + (uint64_t)b * HEAD_HID + i);
+    if ((H2 & 15) == 0 && (reinterpret_cast<uintptr_t>(w0) & 15) == 0) {
+        const int kq = H2 >> 2;                            // this lane's quarter [q*kq, (q+1)*kq), a multiple of 4
+        const float4* w4 = reinterpret_cast<const float4*>(wr + q * kq);
+        const float4* l4 = reinterpret_cast<const float4*>(s_last + q * kq);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 8
+        for (int k4 = 0; k4 < (kq >> 2); ++k4) {
+            const float4 wv = __ldg(w4 + k4), lv = l4[k4];
+            a0 = fmaf(wv.x, lv.x, a0); a1 = fmaf(wv.y, lv.y, a1); a2 = fmaf(wv.z, lv.z, a2); a3 = fmaf(wv.w, lv.w, a3);
+        }
+        acc = (a0 + a1) + (a2 + a3);
+    } else {
+        for (int k = q; k < H2; k += 4) acc = fmaf(__ldg(wr + k), s_last[k], acc);
     }
-    s_hid[i] = h * m;
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (q == 0) {
+        const float h = fmaxf(acc + b0[i], 0.f);
+        hid_out[(size_t)b * HEAD_HID + i] = h;
+        float m = 1.f;
+        if (p > 0.f) {
+            DropRng rng;
+            rng.init(seed, resolve_offset(offset, offset_dev), p);
+            m = rng.mult(HEAD_DROP_BASE + (uint64_t)b * HEAD_HID + i);
+        }
+        s_hid[i] = h * m;
+    }
     __syncthreads();
-    if (i < nc) {
-        float l = b3[i];
-        for (int k = 0; k < HEAD_HID; ++k) l = fmaf(w3[i * HEAD_HID + k], s_hid[k], l);
-        logits[(size_t)b * nc + i] = l;
+    if (tid < nc) {
+        float l = b3[tid];
+        for (int k = 0; k < HEAD_HID; ++k) l = fmaf(w3[tid * HEAD_HID + k], s_hid[k], l);
+        logits[(size_t)b * nc + tid] = l;
     }
 }
 
@@ -177,7 +195,7 @@ int launch_head_fwd2(const float* src_a, int64_t lda, const float* src_b, int64_
                      const int64_t* offset_dev, float* last_out, float* hid_out, float* logits, cudaStream_t st) {
     MMS_REQUIRE(nc >= 1 && nc <= MAX_NC, "head: num_classes %d outside [1,%d]", nc, MAX_NC);
     MMS_PROF_BEGIN(st);
-    head_fwd_kernel<<<B, HEAD_HID, H2 * sizeof(float), st>>>(src_a, lda, src_b, ldb, Hh, w0, b0, w3, b3, H2, nc, p, seed, offset,
+    head_fwd_kernel<<<B, 4 * HEAD_HID, H2 * sizeof(float), st>>>(src_a, lda, src_b, ldb, Hh, w0, b0, w3, b3, H2, nc, p, seed, offset,
                                                              offset_dev, last_out, hid_out, logits);
     MMS_LAUNCH_CHECK("head_fwd_kernel");
     return MMS_OK;
