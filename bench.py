@@ -337,7 +337,7 @@ def run_ours(args):
         if flop_launch:
             roof["tensor_view"] = {"flop_per_launch": flop_launch, "achieved_tflops": flop_launch / t_launch / 1e12,
                                    "frac_of_bf16_sustained": flop_launch / t_launch / 1e12 / pk["bf16_tflops_sustained"]}
-        roof["note"] = ("fp32 recurrence: 12-14 FLOP per byte, far below the ridge, so HBM is the roof that bounds it; what it actually "
+        roof["note"] = ("fp32 recurrence: ~10 FLOP per byte, far below the ridge, so HBM is the roof that bounds it; what it actually "
                         f"runs into is latency -- 240 serial time steps per launch, {1e3 * kern[top]['avg_us'] / L:.0f} ns per time step")
     elif flop_launch:
         roof.update({"bound": "tensor", "unit": "TFLOP/s", "peak": pk["bf16_tflops_sustained"],
