@@ -256,6 +256,41 @@ def preprocess_subject(sid, data, protocol, target_fs=None, include_wrist=False,
     return SubjectStreams(sid, streams, starts, labels, window, names)
 
 
+class _NpyWriter:
+    """``np.save(path, array)`` (reference preprocess.py:217-218) for a DEVICE tensor without the two extra host copies of
+    ``tensor.cpu().numpy()`` + ``np.save``: the tensor is copied once into a reusable pinned buffer and the ``.npy`` file
+    (format 1.0 header + C-order payload, byte-identical to what ``np.save`` writes) is streamed from that buffer
+    (SURVEY §8f N4).  ``dtype`` may down-convert on the device first (e.g. ``torch.float32`` for a half-size file; the
+    reference's format is float64, which stays the default everywhere)."""
+
+    def __init__(self):
+        self._pinned = None
+
+    def save(self, path, tensor: torch.Tensor, dtype=None):
+        t = tensor.detach().contiguous()
+        if dtype is not None and t.dtype != dtype:
+            t = t.to(dtype)
+        nbytes = t.numel() * t.element_size()
+        if t.is_cuda:
+            if self._pinned is None or self._pinned.numel() < nbytes:
+                self._pinned = torch.empty(int(nbytes * 1.25) + 64, dtype=torch.uint8).pin_memory()
+            host = self._pinned[:nbytes].view(t.dtype).view(t.shape)
+            host.copy_(t, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        else:
+            host = t
+        arr = host.numpy()
+        with open(path, 'wb') as f:
+            np.lib.format.write_array_header_1_0(f, {'descr': np.lib.format.dtype_to_descr(arr.dtype), 'fortran_order': False,
+                                                     'shape': tuple(arr.shape)})
+            if arr.size:
+                f.write(memoryview(arr.reshape(-1)).cast('B'))
+        return nbytes
+
+
+_NPY_WRITER = _NpyWriter()
+
+
 def preprocess_subjects_sharded(items, target_fs=None, include_wrist=False, group=None):
     """Preprocess a list of subjects with the work sharded over the ranks of a process group, then give every rank
     every subject's resampled streams (each LOSO fold trains on 11 subjects, validates on 3, tests on 1 -- all 15
@@ -314,10 +349,10 @@ def run_preprocessing(wesad_root=None, output_path=None, subject_ids=None, inclu
         protocol = parse_quest_csv(sid, wesad_root)
         sub = preprocess_subject(sid, data, protocol, RAW_FS, include_wrist=include_wrist)
         if len(sub.labels):
-            X = sub.windows_f64().cpu().numpy()
-            np.save(raw_path / f'{sid}_X.npy', X)
+            X = sub.windows_f64()                                   # [n_win, W, C] float64 on the device
+            _NPY_WRITER.save(raw_path / f'{sid}_X.npy', X)          # == np.save of the same array (preprocess.py:217)
             np.save(raw_path / f'{sid}_y.npy', sub.labels)
-            print(f"  - {sid} (raw): Saved {len(sub.labels)} windows. Raw shape: {X.shape}")
+            print(f"  - {sid} (raw): Saved {len(sub.labels)} windows. Raw shape: {tuple(X.shape)}")
             done.append(sid)
     print("\nPreprocessing complete.")
     return done

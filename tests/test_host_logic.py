@@ -219,3 +219,20 @@ def test_run_folds_interleaved_schedules_generators_by_event_completion():
     assert max_live[0] == 3 and sorted(order) == list(range(7))
     assert all("start_s" in r and r["end_s"] >= r["start_s"] for r in res)
     assert len({id(r["stream"]) for r in res}) == 3          # three streams shared by seven folds
+
+
+@pytest.mark.parametrize("shape,dtype", [((7, 5, 3), torch.float64), ((0, 4, 8), torch.float64), ((3, 11), torch.float32), ((5,), torch.int64)])
+def test_npy_writer_is_byte_identical_to_np_save(tmp_path, shape, dtype):
+    """The direct .npy writer of the preprocess path (header + payload streamed from one staging buffer) produces the
+    very bytes ``np.save`` writes for the same array (reference preprocess.py:217-218), and ``np.load`` reads it back."""
+    from multimodalsignal_b200.preprocess import _NpyWriter
+    g = torch.Generator().manual_seed(sum(shape) + 1)
+    t = (torch.randn(shape, generator=g, dtype=torch.float64) * 100).to(dtype)
+    _NpyWriter().save(tmp_path / "a.npy", t)
+    np.save(tmp_path / "b.npy", t.numpy())
+    assert (tmp_path / "a.npy").read_bytes() == (tmp_path / "b.npy").read_bytes()
+    back = np.load(tmp_path / "a.npy")
+    assert back.dtype == t.numpy().dtype and back.shape == tuple(shape) and np.array_equal(back, t.numpy())
+    if dtype == torch.float64:            # the optional half-size on-disk variant
+        _NpyWriter().save(tmp_path / "c.npy", t, dtype=torch.float32)
+        assert np.array_equal(np.load(tmp_path / "c.npy"), t.numpy().astype(np.float32))
