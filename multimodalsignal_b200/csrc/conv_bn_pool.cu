@@ -600,7 +600,7 @@ int launch_conv_wgrad(int which, const float* x, const float* dy, const float* g
     if (rc) return rc;
     // conv1: C_in <= 16 pairs x 32 position lanes (512 threads); conv2: 16 channels x C_out/16 groups x 8 lanes
     if (which == 1) {
-        if (c_in <= 8) return conv_wgrad_launch<16, CONV1_K, CONV1_S, CONV1_P, 480, 32, 256>(x, dy, gate, B, c_in, l_in, dw, st);
+        if (c_in <= 8) return conv_wgrad_launch<16, CONV1_K, CONV1_S, CONV1_P, 960, 32, 256>(x, dy, gate, B, c_in, l_in, dw, st);
         return conv_wgrad_launch<16, CONV1_K, CONV1_S, CONV1_P, 480, 32, 512>(x, dy, gate, B, c_in, l_in, dw, st);
     }
     if (c_out == 16) return conv_wgrad_launch<16, CONV2_K, CONV2_S, CONV2_P, 240, 8, 128>(x, dy, gate, B, c_in, l_in, dw, st);
