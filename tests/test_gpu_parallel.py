@@ -138,7 +138,7 @@ def test_peer_memory_exchange_equals_full_batch(case, splits):
         for k, v in m.state_dict().items():
             if v.numel() == 0:
                 continue
-            np.testing.assert_allclose(v.float().cpu().numpy(), ref_sd[k].float().cpu().numpy(), atol=2e-5, err_msg=k)
+            np.testing.assert_allclose(v.float().cpu().numpy(), ref_sd[k].float().cpu().numpy(), atol=1e-4, err_msg=k)
     _ext.lib().mms_set_side_streams(1)
     for m in ranks[1:]:
         assert torch.equal(m.flat_parameters(), ranks[0].flat_parameters())
