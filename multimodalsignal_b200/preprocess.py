@@ -291,7 +291,7 @@ class _NpyWriter:
 _NPY_WRITER = _NpyWriter()
 
 
-def preprocess_subjects_sharded(items, target_fs=None, include_wrist=False, group=None):
+def preprocess_subjects_sharded(items, target_fs=None, include_wrist=False, group=None, device=None, subject_fn=None):
     """Preprocess a list of subjects with the work sharded over the ranks of a process group, then give every rank
     every subject's resampled streams (each LOSO fold trains on 11 subjects, validates on 3, tests on 1 -- all 15
     are needed everywhere).
@@ -300,17 +300,20 @@ def preprocess_subjects_sharded(items, target_fs=None, include_wrist=False, grou
     that loads it (only the owning rank calls it).  Subject ``i`` is resampled by rank ``i % world``; the streams
     (``[n_channels, num]`` float64, ~43 MB per subject) then travel GPU-to-GPU with one NCCL broadcast per subject
     over NVLink instead of every rank pushing all raw recordings (269 MB per subject) through its own PCIe link.
-    Without an initialised process group this is a plain loop.  Returns ``{sid: SubjectStreams}``."""
+    Without an initialised process group this is a plain loop.  Returns ``{sid: SubjectStreams}``.
+    ``device`` / ``subject_fn`` (default: the current CUDA device / ``preprocess_subject``) exist so that the exchange
+    logic can be exercised over gloo on a CPU-only box; the default path has no CPU fallback."""
     import torch.distributed as dist
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank(group) if world > 1 else 0
     target_fs = RAW_FS if target_fs is None else target_fs
-    device = torch.device("cuda", torch.cuda.current_device())
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+    subject_fn = preprocess_subject if subject_fn is None else subject_fn
     mine = {}
     for i, (sid, data, protocol) in enumerate(items):
         if i % world == rank:
-            mine[sid] = preprocess_subject(sid, data() if callable(data) else data, protocol, target_fs, include_wrist=include_wrist,
-                                           device=device)
+            mine[sid] = subject_fn(sid, data() if callable(data) else data, protocol, target_fs, include_wrist=include_wrist,
+                                   device=device)
     if world == 1:
         return mine
     meta = [None] * world

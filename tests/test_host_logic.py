@@ -236,3 +236,50 @@ def test_npy_writer_is_byte_identical_to_np_save(tmp_path, shape, dtype):
     if dtype == torch.float64:            # the optional half-size on-disk variant
         _NpyWriter().save(tmp_path / "c.npy", t, dtype=torch.float32)
         assert np.array_equal(np.load(tmp_path / "c.npy"), t.numpy().astype(np.float32))
+
+
+def test_sharded_preprocess_exchange_world_size_2_gloo(tmp_path):
+    """N > 1 path of ``preprocess_subjects_sharded`` on CPU (gloo, two ranks): subject i is produced by rank i % 2 only
+    (the loader callable of the other rank's subjects is never invoked), every rank ends up with every subject's streams,
+    window plan and labels, bit for bit.  The per-subject GPU work is replaced by a stand-in (no GPU here)."""
+    script = tmp_path / "shard_pre.py"
+    script.write_text(textwrap.dedent(f"""
+        import sys
+        sys.path.insert(0, {str(ROOT)!r})
+        import numpy as np, torch
+        import torch.distributed as dist
+        from multimodalsignal_b200 import preprocess as pp
+        dist.init_process_group("gloo")
+        rank = dist.get_rank()
+        loaded = []
+        def loader(i):
+            def f():
+                loaded.append(i)
+                return {{"i": i}}
+            return f
+        def fake_subject(sid, data, protocol, target_fs, include_wrist=False, device=None):
+            i = data["i"]
+            streams = (torch.arange(3 * (50 + i), dtype=torch.float64).view(3, 50 + i) + 1000 * i).to(device)
+            starts = np.arange(0, 10 + i, 5, dtype=np.int64)
+            labels = (np.arange(len(starts)) % 4 + 1).astype(np.int64)
+            return pp.SubjectStreams(sid, streams, starts, labels, 20, ["a", "b", "c"])
+        items = [(f"S{{i}}", loader(i), []) for i in range(5)]
+        out = pp.preprocess_subjects_sharded(items, 64, device=torch.device("cpu"), subject_fn=fake_subject)
+        assert loaded == [i for i in range(5) if i % 2 == rank], loaded
+        assert list(out) == [f"S{{i}}" for i in range(5)]
+        for i in range(5):
+            s = out[f"S{{i}}"]
+            assert torch.equal(s.streams, torch.arange(3 * (50 + i), dtype=torch.float64).view(3, 50 + i) + 1000 * i)
+            assert np.array_equal(s.starts_host, np.arange(0, 10 + i, 5)) and s.window == 20 and s.channel_names == ["a", "b", "c"]
+            assert np.array_equal(s.labels, np.arange(len(s.starts_host)) % 4 + 1)
+        dist.barrier()
+        if rank == 0:
+            print("sharded ok")
+        dist.destroy_process_group()
+    """))
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29613", str(script)],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "sharded ok" in r.stdout
