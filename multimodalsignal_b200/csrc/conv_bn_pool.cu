@@ -331,6 +331,21 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
     }
 }
 
+// per-channel constants of the folded BatchNorm backward: s_bn[o] = {a, mean, inv, m1, m2}
+template <int CO>
+__device__ __forceinline__ void bn_bwd_constants(const BnBwd& bn, int Lout, float (*s_bn)[5]) {
+    if (threadIdx.x < CO) {
+        const int o = threadIdx.x;
+        const double n = (double)bn.Bstat * (double)Lout;
+        const BnAffine af = bn_affine(bn.training, bn.stats, bn.gamma, bn.beta, bn.rm, bn.rv, o, CO, n);
+        s_bn[o][0] = af.a;
+        s_bn[o][1] = af.mean;
+        s_bn[o][2] = af.inv;
+        s_bn[o][3] = bn.training ? (float)(bn.red[o] / n) : 0.f;
+        s_bn[o][4] = bn.training ? (float)(bn.red[CO + o] / n) : 0.f;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ int floor_div2(int a) { return a >= 0 ? a / 2 : -((-a + 1) / 2); }
 
@@ -339,13 +354,17 @@ __device__ __forceinline__ int floor_div2(int a) { return a >= 0 ? a / 2 : -((-a
 template <int CO, int KW, int S, int P, int TI, int CPAD>
 __global__ void __launch_bounds__(TI) conv1d_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w,
                                                           float* __restrict__ dx, const float* __restrict__ xdot,
-                                                          float* __restrict__ dgate, int CI, int Lin, int Lout) {
+                                                          float* __restrict__ dgate, int CI, int Lin, int Lout, const BnBwd bn) {
     static_assert(S == 2, "stride-2 convolutions only");
+    static_assert(CO <= TI, "one thread per output channel for the BN constants");
     constexpr int NL = (TI - 1 + KW - 1) / S + 2;
     extern __shared__ __align__(16) float smem[];
     float* ws = smem;                           // [KW][CO][16]
     float* dys = smem + KW * CO * CPAD;  // [CO][NL]
+    float* ys = dys + CO * NL;                  // [CO][NL], only with the folded BatchNorm backward
     __shared__ float red[TI / 32][CPAD];
+    __shared__ float s_bn[CO][5];
+    if (bn.y) bn_bwd_constants<CO>(bn, Lout, s_bn);
 
     const int b = blockIdx.y, i0 = blockIdx.x * TI, tid = threadIdx.x;
     const int lbase = floor_div2(i0 + P - (KW - 1));
@@ -354,6 +373,7 @@ __global__ void __launch_bounds__(TI) conv1d_dgrad_kernel(const float* __restric
         const int o = idx / NL, ll = idx - o * NL, l = lbase + ll;
         const bool ok = l >= 0 && l < Lout;
         cp_async4_zfill(dys + idx, dyb + (size_t)o * Lout + (ok ? l : 0), ok);
+        if (bn.y) cp_async4_zfill(ys + idx, bn.y + (size_t)b * CO * Lout + (size_t)o * Lout + (ok ? l : 0), ok);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
 #pragma unroll 4
@@ -363,6 +383,14 @@ __global__ void __launch_bounds__(TI) conv1d_dgrad_kernel(const float* __restric
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
+    if (bn.y) {          // dyn -> dy in place (positions outside the tensor stay zero)
+        for (int idx = tid; idx < CO * NL; idx += TI) {
+            const int o = idx / NL, l = lbase + (idx - o * NL);
+            if (l >= 0 && l < Lout)
+                dys[idx] = s_bn[o][0] * (dys[idx] - s_bn[o][3] - (ys[idx] - s_bn[o][1]) * s_bn[o][2] * s_bn[o][4]);
+        }
+        __syncthreads();
+    }
 
     const int i = i0 + tid;
     float acc[CPAD];
@@ -418,14 +446,23 @@ __global__ void __launch_bounds__(TI) conv1d_dgrad_kernel(const float* __restric
 template <int CO, int KW, int S, int P, int TLW, int NPL, int NT>
 __global__ void __launch_bounds__(NT) conv1d_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                           const float* __restrict__ gate, float* __restrict__ dw, int CI,
-                                                          int Lin, int Lout) {
+                                                          int Lin, int Lout, const BnBwd bn) {
     constexpr int SPAN = (TLW - 1) * S + KW;
     constexpr int OG = 16, NOG = CO / OG;
     constexpr int DLD = TLW + 4;            // padded row of the dy tile
-    static_assert(CO % OG == 0 && 32 % NPL == 0 && TLW % NPL == 0 && TLW % 4 == 0, "conv1d_wgrad: bad tiling");
+    static_assert(CO % OG == 0 && 32 % NPL == 0 && TLW % NPL == 0 && TLW % 4 == 0 && CO <= NT, "conv1d_wgrad: bad tiling");
     extern __shared__ __align__(16) float smem[];
     float* dys = smem;                 // [CO][DLD]
     float* xs = smem + CO * DLD;       // [CI][SPAN]
+    float* ys = xs + ((CI * SPAN + 3) & ~3);      // [CO][DLD], only with the folded BatchNorm backward
+    __shared__ float s_bn[CO][5];
+    if (bn.y) {
+        bn_bwd_constants<CO>(bn, Lout, s_bn);
+        if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < CO) {      // dgamma / dbeta once per launch
+            if (bn.dgamma) bn.dgamma[threadIdx.x] += bn.grad_scale * (float)bn.red[CO + threadIdx.x];
+            if (bn.dbeta) bn.dbeta[threadIdx.x] += bn.grad_scale * (float)bn.red[threadIdx.x];
+        }
+    }
     const int b = blockIdx.y, l0 = blockIdx.x * TLW, tid = threadIdx.x;
     const int in0 = l0 * S - P;
     const float* xb = x + (size_t)b * CI * Lin;
@@ -437,21 +474,33 @@ __global__ void __launch_bounds__(NT) conv1d_wgrad_kernel(const float* __restric
         const bool ok = gi >= 0 && gi < Lin;
         cp_async4_zfill(xs + idx, xb + (size_t)c * Lin + (ok ? gi : 0), ok);
     }
-    if ((Lout & 3) == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0) {
+    if ((Lout & 3) == 0 && ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(bn.y)) & 15) == 0) {
         for (int idx = tid; idx < CO * (TLW / 4); idx += NT) {
             const int o = idx / (TLW / 4), i = (idx - o * (TLW / 4)) * 4;
             const bool ok = l0 + i < Lout;            // Lout % 4 == 0: a 16-byte group is inside or outside as a whole
             cp_async16_zfill(dys + o * DLD + i, dyb + (size_t)o * Lout + (ok ? l0 + i : 0), ok);
+            if (bn.y) cp_async16_zfill(ys + o * DLD + i, bn.y + (size_t)b * CO * Lout + (size_t)o * Lout + (ok ? l0 + i : 0), ok);
         }
     } else {
         for (int idx = tid; idx < CO * TLW; idx += NT) {
             const int o = idx / TLW, i = idx - o * TLW;
             const bool ok = l0 + i < Lout;
             cp_async4_zfill(dys + o * DLD + i, dyb + (size_t)o * Lout + (ok ? l0 + i : 0), ok);
+            if (bn.y) cp_async4_zfill(ys + o * DLD + i, bn.y + (size_t)b * CO * Lout + (size_t)o * Lout + (ok ? l0 + i : 0), ok);
         }
     }
     cp_async_wait_all();
     __syncthreads();
+    if (bn.y) {          // dyn -> dy in place (positions outside the tensor stay zero)
+        for (int idx = tid; idx < CO * TLW; idx += NT) {
+            const int o = idx / TLW, i = idx - o * TLW;
+            if (l0 + i < Lout) {
+                float* d = dys + o * DLD + i;
+                *d = s_bn[o][0] * (*d - s_bn[o][3] - (ys[o * DLD + i] - s_bn[o][1]) * s_bn[o][2] * s_bn[o][4]);
+            }
+        }
+        __syncthreads();
+    }
     // thread -> (pair = (c, og), position lane j); the NPL lanes of a pair are adjacent lanes of one warp
     const int pair = tid / NPL, j = tid % NPL;
     const int npairs = CI * NOG;
@@ -508,41 +557,41 @@ static int conv_fwd_launch(const float* x, const float* w, const float* gate, in
 
 template <int CO, int KW, int S, int P, int TI, int CPAD>
 static int conv_dgrad_launch_pad(const float* dy, const float* w, int B, int CI, int Lin, float* dx, const float* xdot,
-                                 float* dgate, cudaStream_t st) {
+                                 float* dgate, cudaStream_t st, const BnBwd& bn) {
     const int Lout = conv_out_len(Lin, KW, S, P);
     constexpr int NL = (TI - 1 + KW - 1) / S + 2;
-    const size_t smem = (size_t)(KW * CO * CPAD + CO * NL) * sizeof(float);
+    const size_t smem = (size_t)(KW * CO * CPAD + (bn.y ? 2 : 1) * CO * NL) * sizeof(float);
     auto kern = conv1d_dgrad_kernel<CO, KW, S, P, TI, CPAD>;
     static bool attr_done = false;
     if (!attr_done) { MMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr_done = true; }
     dim3 grid(cdiv(Lin, TI), B);
     MMS_PROF_BEGIN(st);
-    kern<<<grid, TI, smem, st>>>(dy, w, dx, xdot, dgate, CI, Lin, Lout);
+    kern<<<grid, TI, smem, st>>>(dy, w, dx, xdot, dgate, CI, Lin, Lout, bn);
     MMS_LAUNCH_CHECK("conv1d_dgrad_kernel");
     return MMS_OK;
 }
 
 template <int CO, int KW, int S, int P, int TI>
 static int conv_dgrad_launch(const float* dy, const float* w, int B, int CI, int Lin, float* dx, const float* xdot,
-                             float* dgate, cudaStream_t st) {
-    if (CI <= 8) return conv_dgrad_launch_pad<CO, KW, S, P, TI, 8>(dy, w, B, CI, Lin, dx, xdot, dgate, st);
-    return conv_dgrad_launch_pad<CO, KW, S, P, TI, 16>(dy, w, B, CI, Lin, dx, xdot, dgate, st);
+                             float* dgate, cudaStream_t st, const BnBwd& bn) {
+    if (CI <= 8) return conv_dgrad_launch_pad<CO, KW, S, P, TI, 8>(dy, w, B, CI, Lin, dx, xdot, dgate, st, bn);
+    return conv_dgrad_launch_pad<CO, KW, S, P, TI, 16>(dy, w, B, CI, Lin, dx, xdot, dgate, st, bn);
 }
 
 template <int CO, int KW, int S, int P, int TLW, int NPL, int NT>
 static int conv_wgrad_launch(const float* x, const float* dy, const float* gate, int B, int CI, int Lin, float* dw,
-                             cudaStream_t st) {
+                             cudaStream_t st, const BnBwd& bn) {
     const int Lout = conv_out_len(Lin, KW, S, P);
     constexpr int SPAN = (TLW - 1) * S + KW;
     MMS_REQUIRE(CI * (CO / 16) * NPL <= NT, "conv1d_wgrad: %d input channels do not fit the thread mapping", CI);
-    const size_t smem = (size_t)(CO * (TLW + 4) + CI * SPAN) * sizeof(float);
+    const size_t smem = (size_t)((bn.y ? 2 : 1) * CO * (TLW + 4) + ((CI * SPAN + 3) & ~3)) * sizeof(float);
     auto kern = conv1d_wgrad_kernel<CO, KW, S, P, TLW, NPL, NT>;
     static bool attr_done = false;
-    if (!attr_done) { MMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr_done = true; }
-    MMS_REQUIRE(smem <= 160 * 1024, "conv1d_wgrad: shared memory %zu too large", smem);
+    if (!attr_done) { MMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr_done = true; }
+    MMS_REQUIRE(smem <= 220 * 1024, "conv1d_wgrad: shared memory %zu too large", smem);
     dim3 grid(cdiv(Lout, TLW), B);
     MMS_PROF_BEGIN(st);
-    kern<<<grid, NT, smem, st>>>(x, dy, gate, dw, CI, Lin, Lout);
+    kern<<<grid, NT, smem, st>>>(x, dy, gate, dw, CI, Lin, Lout, bn);
     MMS_LAUNCH_CHECK("conv1d_wgrad_kernel");
     return MMS_OK;
 }
@@ -584,28 +633,32 @@ int launch_conv_fwd(int which, const float* x, const float* w, const float* gate
     return conv_fwd_launch<64, CONV2_K, CONV2_S, CONV2_P, 128>(x, w, gate, B, c_in, l_in, y, stats, st);
 }
 
+static const BnBwd NO_BN = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 1.f};
+
 int launch_conv_dgrad(int which, const float* dy, const float* w, int B, int c_in, int c_out, int l_in, float* dx,
-                      const float* xdot, float* dgate, cudaStream_t st) {
+                      const float* xdot, float* dgate, cudaStream_t st, const BnBwd* bnp = nullptr) {
     int rc = check_conv(which, c_in, c_out);
     if (rc) return rc;
-    if (which == 1) return conv_dgrad_launch<16, CONV1_K, CONV1_S, CONV1_P, 256>(dy, w, B, c_in, l_in, dx, xdot, dgate, st);
-    if (c_out == 16) return conv_dgrad_launch<16, CONV2_K, CONV2_S, CONV2_P, 128>(dy, w, B, c_in, l_in, dx, xdot, dgate, st);
-    if (c_out == 32) return conv_dgrad_launch<32, CONV2_K, CONV2_S, CONV2_P, 128>(dy, w, B, c_in, l_in, dx, xdot, dgate, st);
-    return conv_dgrad_launch<64, CONV2_K, CONV2_S, CONV2_P, 128>(dy, w, B, c_in, l_in, dx, xdot, dgate, st);
+    const BnBwd& bn = bnp ? *bnp : NO_BN;
+    if (which == 1) return conv_dgrad_launch<16, CONV1_K, CONV1_S, CONV1_P, 256>(dy, w, B, c_in, l_in, dx, xdot, dgate, st, bn);
+    if (c_out == 16) return conv_dgrad_launch<16, CONV2_K, CONV2_S, CONV2_P, 128>(dy, w, B, c_in, l_in, dx, xdot, dgate, st, bn);
+    if (c_out == 32) return conv_dgrad_launch<32, CONV2_K, CONV2_S, CONV2_P, 128>(dy, w, B, c_in, l_in, dx, xdot, dgate, st, bn);
+    return conv_dgrad_launch<64, CONV2_K, CONV2_S, CONV2_P, 128>(dy, w, B, c_in, l_in, dx, xdot, dgate, st, bn);
 }
 
 int launch_conv_wgrad(int which, const float* x, const float* dy, const float* gate, int B, int c_in, int c_out,
-                      int l_in, float* dw, cudaStream_t st) {
+                      int l_in, float* dw, cudaStream_t st, const BnBwd* bnp = nullptr) {
     int rc = check_conv(which, c_in, c_out);
     if (rc) return rc;
+    const BnBwd& bn = bnp ? *bnp : NO_BN;
     // conv1: C_in <= 16 pairs x 32 position lanes (512 threads); conv2: 16 channels x C_out/16 groups x 8 lanes
     if (which == 1) {
-        if (c_in <= 8) return conv_wgrad_launch<16, CONV1_K, CONV1_S, CONV1_P, 960, 32, 256>(x, dy, gate, B, c_in, l_in, dw, st);
-        return conv_wgrad_launch<16, CONV1_K, CONV1_S, CONV1_P, 480, 32, 512>(x, dy, gate, B, c_in, l_in, dw, st);
+        if (c_in <= 8) return conv_wgrad_launch<16, CONV1_K, CONV1_S, CONV1_P, 960, 32, 256>(x, dy, gate, B, c_in, l_in, dw, st, bn);
+        return conv_wgrad_launch<16, CONV1_K, CONV1_S, CONV1_P, 480, 32, 512>(x, dy, gate, B, c_in, l_in, dw, st, bn);
     }
-    if (c_out == 16) return conv_wgrad_launch<16, CONV2_K, CONV2_S, CONV2_P, 240, 8, 128>(x, dy, gate, B, c_in, l_in, dw, st);
-    if (c_out == 32) return conv_wgrad_launch<32, CONV2_K, CONV2_S, CONV2_P, 240, 8, 256>(x, dy, gate, B, c_in, l_in, dw, st);
-    return conv_wgrad_launch<64, CONV2_K, CONV2_S, CONV2_P, 240, 8, 512>(x, dy, gate, B, c_in, l_in, dw, st);
+    if (c_out == 16) return conv_wgrad_launch<16, CONV2_K, CONV2_S, CONV2_P, 240, 8, 128>(x, dy, gate, B, c_in, l_in, dw, st, bn);
+    if (c_out == 32) return conv_wgrad_launch<32, CONV2_K, CONV2_S, CONV2_P, 240, 8, 256>(x, dy, gate, B, c_in, l_in, dw, st, bn);
+    return conv_wgrad_launch<64, CONV2_K, CONV2_S, CONV2_P, 240, 8, 512>(x, dy, gate, B, c_in, l_in, dw, st, bn);
 }
 
 int launch_bn_relu_pool_fwd(const float* y, const double* stats, const float* gamma, const float* beta, float* rm,

@@ -51,6 +51,27 @@ constexpr int HEAD_HID = 64;
 constexpr float BN_EPS = 1e-5f;
 constexpr float BN_MOMENTUM = 0.1f;
 
+// BatchNorm backward folded into the consumers of a conv layer's output gradient (conv1d_dgrad / conv1d_wgrad): when
+// y != nullptr the `dy` those kernels are given is the UN-normalised gradient dyn = d(relu/pool) and they form
+//     dy = a * (dyn - mean(dyn) - xhat * mean(dyn * xhat)),   a = gamma / sqrt(var + eps),  xhat = (y - mean) / sqrt(var + eps)
+// themselves while staging their tile (red = the two float64 reductions of pool_relu_bwd; eval mode: dy = a * dyn), which
+// removes the separate BN-apply pass (one launch and one read + write of the whole gradient) from the critical path.
+// dgamma / dbeta (optional) are added once, by the weight-gradient kernel.
+struct BnBwd {
+    const float* y;
+    const double* stats;
+    const float* gamma;
+    const float* beta;
+    const float* rm;
+    const float* rv;
+    const double* red;
+    float* dgamma;
+    float* dbeta;
+    int Bstat;
+    int training;
+    float grad_scale;
+};
+
 // ---- device helpers -----------------------------------------------------------------
 #ifdef __CUDACC__
 

@@ -13,8 +13,8 @@ int launch_chan_gate(const float*, const float*, const float*, int, int, int, fl
 int launch_chan_param_bwd(const float*, const float*, const float*, const float*, const float*, int, int, float*, float*, float*,
                           float*, cudaStream_t);
 int launch_conv_fwd(int, const float*, const float*, const float*, int, int, int, int, float*, double*, cudaStream_t);
-int launch_conv_dgrad(int, const float*, const float*, int, int, int, int, float*, const float*, float*, cudaStream_t);
-int launch_conv_wgrad(int, const float*, const float*, const float*, int, int, int, int, float*, cudaStream_t);
+int launch_conv_dgrad(int, const float*, const float*, int, int, int, int, float*, const float*, float*, cudaStream_t, const BnBwd* = nullptr);
+int launch_conv_wgrad(int, const float*, const float*, const float*, int, int, int, int, float*, cudaStream_t, const BnBwd* = nullptr);
 int launch_bn_relu_pool_fwd(const float*, const double*, const float*, const float*, float*, float*, int64_t*, int, int, int, int,
                             int, float*, cudaStream_t, int Bstat);
 int launch_bn_relu_pool_bwd(const float*, const double*, const float*, const float*, const float*, const float*, const float*, int,
@@ -50,6 +50,13 @@ constexpr int64_t DROP_LAYER_STRIDE = 1ll << 40;
 static bool use_tc() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("MMS_DISABLE_TC"); v = (e && e[0] == '1') ? 0 : 1; }
+    return v == 1;
+}
+
+// MMS_BN_FOLD=0 keeps the BatchNorm-backward apply as its own pass instead of folding it into conv dgrad / wgrad (A/B)
+static bool bn_fold() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MMS_BN_FOLD"); v = (e && e[0] == '0') ? 0 : 1; }
     return v == 1;
 }
 
@@ -537,28 +544,42 @@ static int model_backward(const mms_cnngru_desc* d, const float* x, const float*
                                  G + po.bn2_g, G + po.bn2_b, w.red2, st, 1, m.Bg, gscale);
     if (rc) return rc;
     }   // phase bit 0
+    // The BatchNorm-backward apply pass is folded into the consumers of dy (BnBwd, mms_common.cuh): w.dy2 / w.dy1 hold the
+    // un-normalised gradients written by pool_relu_bwd, and conv dgrad / wgrad form dy while staging their tiles (after the
+    // reductions in w.red2 / w.red1 are complete -- all-reduced by the caller under data parallelism).
+    const bool fold = bn_fold();
     if (phases & 2) {
-        rc = launch_bn_relu_pool_bwd(w.y2, w.stats2, P + po.bn2_g, P + po.bn2_b, rm2, rv2, nullptr, B, m.O, m.L2c, m.training, 1, w.dy2,
-                                     G + po.bn2_g, G + po.bn2_b, w.red2, st, 2, m.Bg, gscale);
+        if (!fold) {
+            rc = launch_bn_relu_pool_bwd(w.y2, w.stats2, P + po.bn2_g, P + po.bn2_b, rm2, rv2, nullptr, B, m.O, m.L2c, m.training, 1, w.dy2,
+                                         G + po.bn2_g, G + po.bn2_b, w.red2, st, 2, m.Bg, gscale);
+            if (rc) return rc;
+        }
+        const BnBwd bn2w = {fold ? w.y2 : nullptr, w.stats2, P + po.bn2_g, P + po.bn2_b, rm2, rv2, w.red2, G + po.bn2_g, G + po.bn2_b, m.Bg, m.training, gscale};
+        BnBwd bn2d = bn2w;
+        bn2d.dgamma = nullptr; bn2d.dbeta = nullptr;
+        rc = launch_conv_wgrad(2, w.p1, w.dy2, nullptr, B, CONV2_CI, m.O, m.P1, G + po.conv2_w, fk.fork(0), &bn2w);
         if (rc) return rc;
-        rc = launch_conv_wgrad(2, w.p1, w.dy2, nullptr, B, CONV2_CI, m.O, m.P1, G + po.conv2_w, fk.fork(0));
-        if (rc) return rc;
-        rc = launch_conv_dgrad(2, w.dy2, P + po.conv2_w, B, CONV2_CI, m.O, m.P1, w.dp1, nullptr, nullptr, st);
+        rc = launch_conv_dgrad(2, w.dy2, P + po.conv2_w, B, CONV2_CI, m.O, m.P1, w.dp1, nullptr, nullptr, st, &bn2d);
         if (rc) return rc;
         rc = launch_bn_relu_pool_bwd(w.y1, w.stats1, P + po.bn1_g, P + po.bn1_b, rm1, rv1, w.dp1, B, CONV1_CO, m.L1c, m.training, 0,
                                      w.dy1, G + po.bn1_g, G + po.bn1_b, w.red1, st, 1, m.Bg, gscale);
         if (rc) return rc;
     }
     if (!(phases & 4)) return fk.join();
-    rc = launch_bn_relu_pool_bwd(w.y1, w.stats1, P + po.bn1_g, P + po.bn1_b, rm1, rv1, nullptr, B, CONV1_CO, m.L1c, m.training, 0,
-                                 w.dy1, G + po.bn1_g, G + po.bn1_b, w.red1, st, 2, m.Bg, gscale);
-    if (rc) return rc;
-    rc = launch_conv_wgrad(1, x, w.dy1, m.attention ? w.gate : nullptr, B, m.C, CONV1_CO, m.T, G + po.conv1_w, fk.fork(1));
+    if (!fold) {
+        rc = launch_bn_relu_pool_bwd(w.y1, w.stats1, P + po.bn1_g, P + po.bn1_b, rm1, rv1, nullptr, B, CONV1_CO, m.L1c, m.training, 0,
+                                     w.dy1, G + po.bn1_g, G + po.bn1_b, w.red1, st, 2, m.Bg, gscale);
+        if (rc) return rc;
+    }
+    const BnBwd bn1w = {fold ? w.y1 : nullptr, w.stats1, P + po.bn1_g, P + po.bn1_b, rm1, rv1, w.red1, G + po.bn1_g, G + po.bn1_b, m.Bg, m.training, gscale};
+    BnBwd bn1d = bn1w;
+    bn1d.dgamma = nullptr; bn1d.dbeta = nullptr;
+    rc = launch_conv_wgrad(1, x, w.dy1, m.attention ? w.gate : nullptr, B, m.C, CONV1_CO, m.T, G + po.conv1_w, fk.fork(1), &bn1w);
     if (rc) return rc;
     if (m.attention) {
         if (m.A > 0 || dx) {
             // dx (if requested) first receives d(x*gate); dgate[b,c] = sum_t d(x*gate) * x
-            rc = launch_conv_dgrad(1, w.dy1, P + po.conv1_w, B, m.C, CONV1_CO, m.T, dx, x, w.dgate, st);
+            rc = launch_conv_dgrad(1, w.dy1, P + po.conv1_w, B, m.C, CONV1_CO, m.T, dx, x, w.dgate, st, &bn1d);
             if (rc) return rc;
             float* ds = dx && m.A > 0 ? w.ca_scratch : nullptr;
             rc = launch_chan_param_bwd(w.dgate, w.mean, w.gate, P + po.ca_w1, P + po.ca_w2, B, m.C, w.ca_scratch + (int64_t)B * m.C, ds,
@@ -570,7 +591,7 @@ static int model_backward(const mms_cnngru_desc* d, const float* x, const float*
             }
         }
     } else if (dx) {
-        rc = launch_conv_dgrad(1, w.dy1, P + po.conv1_w, B, m.C, CONV1_CO, m.T, dx, nullptr, nullptr, st);
+        rc = launch_conv_dgrad(1, w.dy1, P + po.conv1_w, B, m.C, CONV1_CO, m.T, dx, nullptr, nullptr, st, &bn1d);
         if (rc) return rc;
     }
     return fk.join();       // every gradient is complete before the caller's next kernel (Adam)
