@@ -283,3 +283,44 @@ def test_sharded_preprocess_exchange_world_size_2_gloo(tmp_path):
                        capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "sharded ok" in r.stdout
+
+
+def test_window_plan_edge_cases_equal_oracle():
+    """Host index arithmetic on irregular protocols -- unknown task names (skipped, reference preprocess.py:163-164), task
+    names with inner spaces ('Medi 1'), segments shorter than one window (no window), segments of exactly one window,
+    two-decimal start times that hit the float64 truncation trap -- is bit-identical to the oracle (itself pinned to the
+    reference's loop by tests/test_oracle_preprocess.py)."""
+    from multimodalsignal_b200 import preprocess as pp
+    rng = np.random.default_rng(7)
+    names = ["Base", "TSST", "Medi 1", "Fun", "Medi 2", "sRead", "fRead", "bRead", " Base ", "Medi1"]
+    for trial in range(200):
+        protocol = []
+        t = 0.0
+        for _ in range(int(rng.integers(0, 7))):
+            start = round(t + float(rng.uniform(0.0, 3.0)), 2)
+            dur = [0.2, 0.99, 1.0, 1.01, float(rng.uniform(0.0, 12.0))][int(rng.integers(0, 5))]
+            end = round(start + dur, 2)
+            protocol.append((names[int(rng.integers(0, len(names)))], start, end))
+            t = end
+        for fs in (64, 128):
+            s1, l1, w1 = pp.window_plan(protocol, fs)
+            s2, l2, w2 = po.window_plan(protocol, fs)
+            assert w1 == w2 == 60 * fs
+            assert s1.dtype == np.int64 and l1.dtype == np.int64
+            assert np.array_equal(s1, s2) and np.array_equal(l1, l2), (protocol, fs)
+    assert pp.window_plan([], 64)[0].shape == (0,)
+    assert pp.window_plan([("sRead", 1.0, 30.0)], 64)[0].shape == (0,)            # unknown task: no windows
+    assert pp.window_plan([("Base", 5.0, 5.99)], 64)[0].shape == (0,)             # shorter than 60 s: no window
+    assert len(pp.window_plan([("Base", 5.0, 6.0)], 64)[0]) == 1                  # exactly one window
+
+
+def test_map_labels_modes_and_error():
+    """reference dataset.py:28-34."""
+    from multimodalsignal_b200.dataset import map_labels
+    raw = np.array([1, 2, 3, 4, 2, 1])
+    assert map_labels(raw, "stress_binary").tolist() == [0, 1, 0, 0, 1, 0]
+    assert map_labels(raw, "ternary").tolist() == [0, 2, 1, 0, 2, 0]
+    assert map_labels(raw, "stress_binary").tolist() == po.map_labels(raw, "stress_binary").tolist()
+    assert map_labels(raw, "ternary").tolist() == po.map_labels(raw, "ternary").tolist()
+    with pytest.raises(ValueError):
+        map_labels(raw, "quaternary")
