@@ -83,6 +83,40 @@ void prof_end(const char* name) {
 
 }  // namespace mms
 
+// ---- run-time switches ------------------------------------------------------------------------
+#include <mutex>
+#include <stdlib.h>
+
+namespace mms {
+
+static std::mutex g_opt_mu;
+static std::map<std::string, int> g_opt;        // explicit settings and cached environment reads
+
+int option_get(const char* name, int dflt) {
+    std::lock_guard<std::mutex> lk(g_opt_mu);
+    auto it = g_opt.find(name);
+    if (it != g_opt.end()) return it->second;
+    int v = dflt;
+    const std::string env = std::string("MMS_") + name;
+    if (const char* e = getenv(env.c_str())) { if (e[0]) v = atoi(e); }
+    g_opt[name] = v;
+    return v;
+}
+
+}  // namespace mms
+
+extern "C" int mms_set_option(const char* name, int32_t value) {
+    MMS_REQUIRE(name && name[0], "set_option: empty name");
+    std::lock_guard<std::mutex> lk(g_opt_mu);
+    g_opt[name] = value;
+    return MMS_OK;
+}
+
+extern "C" int32_t mms_get_option(const char* name, int32_t dflt) {
+    if (!name || !name[0]) return dflt;
+    return option_get(name, dflt);
+}
+
 extern "C" int64_t mms_launch_count(void) { return (int64_t)g_launches.load(); }
 
 extern "C" int mms_profile_enable(int32_t on) {

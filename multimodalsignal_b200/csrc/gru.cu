@@ -381,6 +381,213 @@ __global__ void __launch_bounds__(2 * H) gru_bwd_kernel(const GruBwdParams prm) 
     }
 }
 
+// Backward recurrence with the per-visit inputs staged through a shared-memory ring (one batch row per CTA).
+//
+// Why a second variant: in gru_bwd_kernel the six values a visit needs travel through a register ring of plain global
+// loads.  ptxas gives every one of those LDGs the SAME scoreboard (decoded from the SASS control words: all 24 ring loads
+// write SB5), and a scoreboard wait is a wait for its counter to reach zero, i.e. for the YOUNGEST load in flight -- so the
+// consumer of the 4-visits-old slot also waits for the slot that was refilled a moment ago (in one of the four unrolled
+// visits literally: a register move the allocator inserted after the refill), and the nominal prefetch distance of four
+// visits collapses to one or less (ncu: 35-39 % of the stall samples are long_scoreboard, on two instructions of the four
+// unrolled visits).  cp.async (LDGSTS) completion is tracked by commit groups instead of scoreboards, groups complete in
+// order and cp.async.wait_group N only waits for the groups older than the N youngest: a true ring.  Threads 0 .. 6H/4-1
+// copy 16 bytes each of the visit's row (stash 4H | h_prev H | dout H) PF-1 visits ahead; the barrier every visit already
+// has publishes the slot, and the six scalars of visit v+1 are read from shared memory into registers right after the
+// barrier of visit v, behind the mat-vec, so no shared-memory round trip is added to the dependent chain.
+//
+// Everything that is invariant over the visits (roles, shared-memory addresses, strides, step counts) is computed once
+// and made opaque to the compiler: at ~170 registers ptxas otherwise re-derives such values inside every visit from
+// %tid / %ctaid / constant-bank loads (S2R, LDC and S2UR + LEA chains between the barrier and the loads of the mat-vec),
+// which is what made the earlier register-lean variants slower than the 254-register kernel.  Shared memory is
+// addressed through 32-bit window addresses with immediate offsets, stores to the gate buffer are unconditional (the
+// two lanes that finish the same unit store the same value), copies are predicated instead of branched around.
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 lds_v4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+// predicated 16-byte asynchronous copy: no branch around the LDGSTS
+__device__ __forceinline__ void cp_async16_if(uint32_t smem_dst, const void* gmem_src, int pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}" ::"r"(smem_dst), "l"(gmem_src),
+                 "r"(pred)
+                 : "memory");
+}
+#define MMS_OPAQUE32(x) asm volatile("" : "+r"(x))
+#define MMS_OPAQUE64(x) asm volatile("" : "+l"(x))
+#define MMS_OPAQUEF(x) asm volatile("" : "+f"(x))
+
+template <int H, int PF>
+__global__ void __launch_bounds__(2 * H) gru_bwd_ring_kernel(const GruBwdParams prm) {
+    constexpr int KS = H / 4, HP = H / 2, GP = H + 16;      // GP: padded length of one gate vector
+    constexpr int ROW = 6 * H;                              // floats per ring slot: r, z, n, q | h_prev | dout
+    constexpr int NCP = ROW / 4;                            // 16-byte chunks per slot, one per copying thread
+    static_assert(PF % 2 == 0 && PF >= 4, "the gate double-buffer index is the parity of the unrolled visit");
+    static_assert(NCP <= 2 * H, "one chunk per thread");
+    const mms_gru_dir_bwd d = prm.dir[blockIdx.y];
+    const int tid = threadIdx.x, p = tid >> 2, q = tid & 3;
+    const int own = q & 1;
+    const int ku = p + own * HP;           // the column (hidden unit) whose gate math this lane does
+    const bool first = q < 2;
+    const int bb = blockIdx.x;             // one batch row per CTA: grid.x == B
+    int nsteps = d.nsteps;
+    MMS_OPAQUE32(nsteps);
+
+    __shared__ __align__(16) float dgh[2][3 * GP];
+    __shared__ __align__(16) float ring[PF][ROW];
+
+    // columns {p, p+HP} of W_hh, gate rows [g*H + q*KS, +KS), packed (column A, column B)
+    float2 w2[3][KS];
+#pragma unroll
+    for (int g = 0; g < 3; ++g)
+#pragma unroll
+        for (int i = 0; i < KS; ++i)
+            w2[g][i] = make_float2(__ldg(d.w_hh + (size_t)(g * H + q * KS + i) * H + p),
+                                   __ldg(d.w_hh + (size_t)(g * H + q * KS + i) * H + p + HP));
+
+    int has_dout = d.dout != nullptr ? 1 : 0;
+    MMS_OPAQUE32(has_dout);
+    // visit v handles forward step s = nsteps-1-v at time t_last - v*dt
+    const int t_last = d.t0 + (nsteps - 1) * d.dt;
+
+    // copy role of this thread: chunk tid of the row.  Threads without a role keep a valid pointer that is never read.
+    int copier = 0, is_hp = 0;
+    const float* src = d.stash;
+    int64_t sstep = 0;
+    if (tid < H) {
+        copier = 1; src = d.stash + (int64_t)bb * d.st_bs + (int64_t)t_last * d.st_ts + 4 * tid; sstep = -(int64_t)d.dt * d.st_ts;
+    } else if (tid < H + H / 4) {
+        copier = 1; is_hp = 1;
+        src = d.hs + (int64_t)bb * d.hs_bs + (int64_t)(t_last - d.dt) * d.hs_ts + 4 * (tid - H); sstep = -(int64_t)d.dt * d.hs_ts;
+    } else if (tid < NCP && has_dout) {
+        copier = 1; src = d.dout + (int64_t)bb * d.do_bs + (int64_t)t_last * d.do_ts + 4 * (tid - H - H / 4); sstep = -(int64_t)d.dt * d.do_ts;
+    }
+    // h_prev of the first forward step (= the last visit) is h0 = 0, not memory: copies of h_prev stop one visit early
+    int n_copy = is_hp ? nsteps - 1 : nsteps;
+    if (!copier) n_copy = 0;
+    MMS_OPAQUE32(n_copy);
+    MMS_OPAQUE64(sstep);
+    uint32_t ring_wr_s = (uint32_t)__cvta_generic_to_shared(&ring[0][0]) + 16u * (uint32_t)tid;
+    uint32_t ring_rd_s = (uint32_t)__cvta_generic_to_shared(&ring[0][0]) + 4u * (uint32_t)ku;
+    uint32_t g_wr_s = (uint32_t)__cvta_generic_to_shared(&dgh[0][0]) + 4u * (uint32_t)padded<KS>(ku);
+    uint32_t g_rd_s = (uint32_t)__cvta_generic_to_shared(&dgh[0][0]) + 4u * (uint32_t)(q * (KS + 4));
+    MMS_OPAQUE32(ring_wr_s);
+    MMS_OPAQUE32(ring_rd_s);
+    MMS_OPAQUE32(g_wr_s);
+    MMS_OPAQUE32(g_rd_s);
+
+    // the copies of visit w go to slot w % PF (compile-time at every call site)
+#define MMS_RING_ISSUE(w, slot)                                                       \
+    do {                                                                              \
+        cp_async16_if(ring_wr_s + (uint32_t)((slot) * ROW * 4), src, (w) < n_copy);   \
+        src += sstep;                                                                 \
+    } while (0)
+
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+        MMS_RING_ISSUE(u, u);
+        cp_async_commit();
+    }
+
+    float* D_p = d.D + (int64_t)bb * d.d_bs + (int64_t)t_last * d.d_ts + (first ? 0 : 2 * H) + ku;
+    int64_t d_step = -(int64_t)d.dt * d.d_ts;
+    MMS_OPAQUE64(d_step);
+    float dlast = d.dout_last ? __ldg(d.dout_last + (int64_t)bb * d.dl_ld + ku) : 0.f;
+    // initial recurrent gradient: optional projection of the head gradient (dhid @ W0)
+    float dh = 0.f;
+    if (d.dh_head) {
+        for (int i = 0; i < HEAD_HID; ++i)
+            dh = fmaf(__ldg(d.dh_head + (size_t)bb * HEAD_HID + i), __ldg(d.w0 + (size_t)i * d.w0_ld + d.w0_col + ku), dh);
+    }
+    int v_extra = d.dl_at_first ? nsteps - 1 : 0;           // visit at which dout_last is added
+    MMS_OPAQUE32(v_extra);
+    MMS_OPAQUEF(dlast);
+    int sel_first = first ? 1 : 0, sel_own = own;
+    MMS_OPAQUE32(sel_first);
+    MMS_OPAQUE32(sel_own);
+
+    // What the dependent chain of a visit needs is dht = dh + (dout [+ dout_last]) and then one multiply per output:
+    //   d r_pre = dht * cr,  d z_pre = dht * cz,  d n_pre = dht * cn,  d q = dht * cq,  dh_next = dht * z + W^T (...)
+    // with coefficients that depend only on the stashed gates.  They are formed from the ring slot of visit v+1 behind the
+    // mat-vec of visit v (off the chain), which leaves FADD -> FMUL -> STS between the last shuffle and the barrier.
+    struct StepIn { float add, cr, cz, cn, cq, z; };
+#define MMS_RING_LOAD(dst, slot, vn)                                                  \
+    do {                                                                              \
+        const uint32_t a_ = ring_rd_s + (uint32_t)((slot) * ROW * 4);                 \
+        const float r_ = lds_f32(a_), z_ = lds_f32(a_ + 4 * H), n_ = lds_f32(a_ + 8 * H), q_ = lds_f32(a_ + 12 * H); \
+        const float hpl_ = lds_f32(a_ + 16 * H), dol_ = lds_f32(a_ + 20 * H);         \
+        const float hp_ = (vn) < nsteps - 1 ? hpl_ : 0.f;      /* h_prev of forward step 0 is h0 = 0 */ \
+        const float cn_ = (1.f - z_) * (1.f - n_ * n_);                               \
+        dst.add = (has_dout ? dol_ : 0.f) + ((vn) == v_extra ? dlast : 0.f);          \
+        dst.cn = cn_;                                                                 \
+        dst.cq = cn_ * r_;                                                            \
+        dst.cr = cn_ * q_ * (r_ * (1.f - r_));                                        \
+        dst.cz = (hp_ - n_) * (z_ * (1.f - z_));                                      \
+        dst.z = z_;                                                                   \
+    } while (0)
+
+    cp_async_wait<PF - 1>();          // visit 0 has landed (for the copying threads); the barrier publishes it
+    __syncthreads();
+    StepIn nx;
+    MMS_RING_LOAD(nx, 0, 0);
+
+    for (int v0 = 0; v0 < nsteps; v0 += PF) {
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+            const int v = v0 + u;
+            if (v >= nsteps) break;
+            const int cur = u & 1;    // compile-time in the unrolled body (v0 is a multiple of the even PF)
+            const StepIn x = nx;
+            const float dht = dh + x.add;
+            const float drp = dht * x.cr, dzp = dht * x.cz, dnp = dht * x.cn, dq = dht * x.cq;
+            const float dhz = dht * x.z;
+            {   // both lanes that finish unit ku hold the same three values: unconditional stores, no branch
+                const uint32_t g = g_wr_s + (uint32_t)(cur * 3 * GP * 4);
+                sts_f32(g, drp);
+                sts_f32(g + GP * 4, dzp);
+                sts_f32(g + 2 * GP * 4, dq);
+            }
+            // D = (d r_pre, d z_pre, d n_pre, d q): first lane stores 0,1; second 2,3
+            D_p[0] = sel_first ? drp : dnp;
+            D_p[H] = sel_first ? dzp : dq;
+            D_p += d_step;
+            cp_async_wait<PF - 2>();      // the copies for visit v + 1 are complete for the copying threads ...
+            __syncthreads();              // ... and, with the gate buffer `cur`, visible to every thread
+            if (v + 1 < nsteps) {         // the gradient flowing into h_{-1} = h0 is not needed
+                // Slot u held THIS visit's inputs; every thread read them before it arrived at the barrier above, so the
+                // slot is free: refill it with visit v + PF.  One commit group per visit keeps the group count uniform.
+                MMS_RING_ISSUE(v + PF, u);
+                cp_async_commit();
+                float2 acc[3] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+                for (int g = 0; g < 3; ++g) {
+                    const uint32_t ga = g_rd_s + (uint32_t)((cur * 3 * GP + g * GP) * 4);
+#pragma unroll
+                    for (int i4 = 0; i4 < KS / 4; ++i4) {
+                        const float4 g4 = lds_v4(ga + 16 * i4);
+                        acc[g] = __ffma2_rn(w2[g][4 * i4 + 0], bcast2(g4.x), acc[g]);
+                        acc[g] = __ffma2_rn(w2[g][4 * i4 + 1], bcast2(g4.y), acc[g]);
+                        acc[g] = __ffma2_rn(w2[g][4 * i4 + 2], bcast2(g4.z), acc[g]);
+                        acc[g] = __ffma2_rn(w2[g][4 * i4 + 3], bcast2(g4.w), acc[g]);
+                    }
+                }
+                MMS_RING_LOAD(nx, (u + 1) % PF, v + 1);      // next visit's inputs, behind the mat-vec
+                const float ax = (acc[0].x + acc[1].x) + acc[2].x, ay = (acc[0].y + acc[1].y) + acc[2].y;
+                float t = (sel_own ? ay : ax) + __shfl_xor_sync(0xffffffffu, sel_own ? ax : ay, 1);
+                t += __shfl_xor_sync(0xffffffffu, t, 2);
+                dh = dhz + t;
+            }
+        }
+    }
+#undef MMS_RING_ISSUE
+#undef MMS_RING_LOAD
+}
+
 static inline int rows_per_cta(int B, int ndirs) {
     // one row per CTA while all CTAs fit in ~2 waves on 148 SMs; more rows per CTA beyond that
     int R = 1;
@@ -400,10 +607,30 @@ static int gru_fwd_dispatch(const GruFwdParams& prm, int ndirs, cudaStream_t st)
     return MMS_OK;
 }
 
+// the shared-memory-ring variant copies whole 16-byte pieces of the stash / h / dout rows
+static bool bwd_ring_ok(const GruBwdParams& prm, int ndirs) {
+    auto ok = [](const void* p, int64_t bs, int64_t ts) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && bs % 4 == 0 && ts % 4 == 0; };
+    for (int i = 0; i < ndirs; ++i) {
+        const mms_gru_dir_bwd& d = prm.dir[i];
+        if (!ok(d.stash, d.st_bs, d.st_ts) || !ok(d.hs, d.hs_bs, d.hs_ts)) return false;
+        if (d.dout && !ok(d.dout, d.do_bs, d.do_ts)) return false;
+    }
+    return true;
+}
+
 template <int H>
 static int gru_bwd_dispatch(const GruBwdParams& prm, int ndirs, cudaStream_t st) {
     const int R = rows_per_cta(prm.B, ndirs);
     dim3 grid(cdiv(prm.B, R), ndirs);
+    // MMS_GRU_BWD_RING / mms_set_option("GRU_BWD_RING", n): 0 = register ring (gru_bwd_kernel), 4 / 8 = shared-memory ring of that depth
+    const int ring = option_get("GRU_BWD_RING", 0);
+    if (ring > 0 && R == 1 && bwd_ring_ok(prm, ndirs)) {
+        MMS_PROF_BEGIN(st);
+        if (ring >= 8) gru_bwd_ring_kernel<H, 8><<<grid, 2 * H, 0, st>>>(prm);
+        else gru_bwd_ring_kernel<H, 4><<<grid, 2 * H, 0, st>>>(prm);
+        MMS_LAUNCH_CHECK("gru_bwd_kernel");
+        return MMS_OK;
+    }
     MMS_PROF_BEGIN(st);
     if (R == 1) gru_bwd_kernel<H, 1><<<grid, 2 * H, 0, st>>>(prm);
     else if (R == 2) gru_bwd_kernel<H, 2><<<grid, 2 * H, 0, st>>>(prm);

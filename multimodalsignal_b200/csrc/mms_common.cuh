@@ -38,6 +38,10 @@ void prof_end(const char* name);
         if (!(cond)) { ::mms::set_error(__VA_ARGS__); return MMS_E_INVALID; }       \
     } while (0)
 
+// Integer run-time switches (A/B measurements, opt-in kernels): the value set by mms_set_option(name, v) wins, else the
+// environment variable MMS_<name> read once, else `dflt`.
+int option_get(const char* name, int dflt);
+
 static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
