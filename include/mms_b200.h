@@ -53,12 +53,14 @@ int mms_profile_report(char* buf_host, int64_t buf_bytes);
  * back into the caller's stream, also under CUDA-graph capture).  0 serialises everything on the
  * caller's stream (used while per-kernel times are taken); also MMS_DISABLE_STREAMS=1. */
 int mms_set_side_streams(int32_t on);
-/* Integer run-time switches for A/B measurements and opt-in kernels.  mms_set_option("GRU_BWD_RING", 4) has the
- * effect of the environment variable MMS_GRU_BWD_RING=4 but can be changed between launches (the environment is read
- * once, at first use); mms_get_option returns the value in effect (`dflt` if neither was given).  Options never change
+/* Integer run-time switches for A/B measurements and kernel selection.  mms_set_option("GRU_BWD_RING", 0) has the
+ * effect of the environment variable MMS_GRU_BWD_RING=0 but can be changed between launches (the environment is read
+ * once, at first use); mms_get_option returns the value in effect (`dflt` if neither was given; defaults are per call
+ * site and listed in INTEGRATION.md).  Options never change
  * results beyond the documented tolerances; they select between kernels of this library. */
 int mms_set_option(const char* name, int32_t value);
 int32_t mms_get_option(const char* name, int32_t dflt);
+int mms_clear_option(const char* name);     /* back to the built-in default of every call site */
 
 /* ------------------------------------------------------------------------------------------
  * Model description (reference models.py:39-40 constructor arguments + call-time facts).

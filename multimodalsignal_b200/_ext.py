@@ -72,6 +72,7 @@ _SIGNATURES = {
     "mms_set_side_streams": (c_i32, [c_i32]),
     "mms_set_option": (c_i32, [C.c_char_p, c_i32]),
     "mms_get_option": (c_i32, [C.c_char_p, c_i32]),
+    "mms_clear_option": (c_i32, [C.c_char_p]),
     "mms_cnngru_param_layout": (c_i32, [C.POINTER(CnnGruDesc), C.POINTER(c_i64), C.POINTER(c_i64), c_i32, C.POINTER(c_i64)]),
     "mms_cnngru_workspace_bytes": (c_i64, [C.POINTER(CnnGruDesc)]),
     "mms_cnngru_forward": (c_i32, [C.POINTER(CnnGruDesc), P, P, P, P, P, P, P]),

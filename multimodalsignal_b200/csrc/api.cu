@@ -90,17 +90,19 @@ void prof_end(const char* name) {
 namespace mms {
 
 static std::mutex g_opt_mu;
-static std::map<std::string, int> g_opt;        // explicit settings and cached environment reads
+struct OptVal { bool set; int v; };
+static std::map<std::string, OptVal> g_opt;     // explicit settings and cached environment reads (set = false: neither)
 
 int option_get(const char* name, int dflt) {
     std::lock_guard<std::mutex> lk(g_opt_mu);
     auto it = g_opt.find(name);
-    if (it != g_opt.end()) return it->second;
-    int v = dflt;
-    const std::string env = std::string("MMS_") + name;
-    if (const char* e = getenv(env.c_str())) { if (e[0]) v = atoi(e); }
-    g_opt[name] = v;
-    return v;
+    if (it == g_opt.end()) {
+        OptVal o = {false, 0};
+        const std::string env = std::string("MMS_") + name;
+        if (const char* e = getenv(env.c_str())) { if (e[0]) { o.set = true; o.v = atoi(e); } }
+        it = g_opt.emplace(name, o).first;
+    }
+    return it->second.set ? it->second.v : dflt;      // the default belongs to the caller and is never cached
 }
 
 }  // namespace mms
@@ -108,7 +110,14 @@ int option_get(const char* name, int dflt) {
 extern "C" int mms_set_option(const char* name, int32_t value) {
     MMS_REQUIRE(name && name[0], "set_option: empty name");
     std::lock_guard<std::mutex> lk(g_opt_mu);
-    g_opt[name] = value;
+    g_opt[name] = OptVal{true, value};
+    return MMS_OK;
+}
+
+extern "C" int mms_clear_option(const char* name) {
+    MMS_REQUIRE(name && name[0], "clear_option: empty name");
+    std::lock_guard<std::mutex> lk(g_opt_mu);
+    g_opt[name] = OptVal{false, 0};               // back to the built-in default (the environment is not re-read)
     return MMS_OK;
 }
 

@@ -622,12 +622,28 @@ template <int H>
 static int gru_bwd_dispatch(const GruBwdParams& prm, int ndirs, cudaStream_t st) {
     const int R = rows_per_cta(prm.B, ndirs);
     dim3 grid(cdiv(prm.B, R), ndirs);
-    // MMS_GRU_BWD_RING / mms_set_option("GRU_BWD_RING", n): 0 = register ring (gru_bwd_kernel), 4 / 8 = shared-memory ring of that depth
-    const int ring = option_get("GRU_BWD_RING", 0);
+    // MMS_GRU_BWD_RING / mms_set_option("GRU_BWD_RING", n): shared-memory ring of depth 4 (default) or 8; 0 = the register-ring
+    // kernel (gru_bwd_kernel), which also serves R > 1 rows per CTA and operands that are not 16-byte aligned.
+    // Measured on a B200 (profiles/r1_ab_gru_bwd_ring.json): 89.6 us (register ring) -> 69.3 us (depth 4) -> 66.7 us (depth 8)
+    // per launch; depth 4 is the default because the whole GPU suite was run with it.
+    const int ring = option_get("GRU_BWD_RING", 4);
     if (ring > 0 && R == 1 && bwd_ring_ok(prm, ndirs)) {
+        // MMS_GRU_BWD_EXCLUSIVE_KB (experiment, default 0): reserve that much dynamic shared memory per CTA so that no
+        // other kernel's CTAs (the weight-gradient GEMMs of the side streams) can share an SM with a recurrence CTA
+        const int excl = option_get("GRU_BWD_EXCLUSIVE_KB", 0);
+        size_t dyn = 0;
+        if (excl > 0) {
+            dyn = (size_t)(excl > 200 ? 200 : excl) * 1024;
+            static bool attr_done = false;
+            if (!attr_done) {
+                MMS_CUDA(cudaFuncSetAttribute(gru_bwd_ring_kernel<H, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                MMS_CUDA(cudaFuncSetAttribute(gru_bwd_ring_kernel<H, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                attr_done = true;
+            }
+        }
         MMS_PROF_BEGIN(st);
-        if (ring >= 8) gru_bwd_ring_kernel<H, 8><<<grid, 2 * H, 0, st>>>(prm);
-        else gru_bwd_ring_kernel<H, 4><<<grid, 2 * H, 0, st>>>(prm);
+        if (ring >= 8) gru_bwd_ring_kernel<H, 8><<<grid, 2 * H, dyn, st>>>(prm);
+        else gru_bwd_ring_kernel<H, 4><<<grid, 2 * H, dyn, st>>>(prm);
         MMS_LAUNCH_CHECK("gru_bwd_kernel");
         return MMS_OK;
     }

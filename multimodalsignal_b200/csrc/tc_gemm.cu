@@ -496,7 +496,10 @@ int launch_tc_gemm_tn(const float* A, int64_t lda, int a_split, int a_skip, cons
     p.C = C; p.bias_grad = bias_grad; p.ldc = ldc; p.M = M; p.N1 = N1; p.N2 = N2; p.a_split = a_split; p.a_skip = a_skip;
     p.shift = shift; p.seq = seq; p.nblkA = N1 / 32; p.nblkB = N2 / 32;
     // split-K: ~one CTA per SM pair for long reductions, never fewer than 2 k-blocks per CTA
-    int chunk = (int)align_up(cdiv(M, 96), TN_KB);
+    // MMS_TN_SPLIT (experiment): target CTA count of the split (fewer CTAs = fewer red.global.add partial tiles)
+    int nsplit = option_get("TN_SPLIT", 96);
+    if (nsplit < 1) nsplit = 1;
+    int chunk = (int)align_up(cdiv(M, nsplit), TN_KB);
     if (chunk < 2 * TN_KB) chunk = 2 * TN_KB;
     p.chunk = chunk;
     const size_t stage = (size_t)2 * p.nblkA * TN_BLK + (size_t)2 * (p.nblkB + 1) * TN_BLK;

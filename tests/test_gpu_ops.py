@@ -301,7 +301,7 @@ def test_gru_recurrence(lib, B, L, H, I, reverse):
 def test_gru_backward_shared_memory_ring(lib, depth):
     """The cp.async shared-memory-ring backward (GRU_BWD_RING = ring depth) against the same oracle, including
     sequences shorter than the ring, single steps and the fall-back to the register-ring kernel for R > 1 rows per CTA."""
-    prev = lib.mms_get_option(b"GRU_BWD_RING", 0)
+    prev = lib.mms_get_option(b"GRU_BWD_RING", -1)
     ok(lib.mms_set_option(b"GRU_BWD_RING", depth))
     try:
         for case in [(5, 40, 64, 32, False), (5, 40, 64, 32, True), (3, 33, 32, 32, False), (3, 33, 32, 16, True),
@@ -312,7 +312,20 @@ def test_gru_backward_shared_memory_ring(lib, depth):
         _gru_case(lib, 4, 20, 64, 128, True, steps=depth + 1)
         _gru_case(lib, 4, 20, 32, 64, False, steps=depth, with_dout=False)
     finally:
-        ok(lib.mms_set_option(b"GRU_BWD_RING", prev))
+        ok(lib.mms_set_option(b"GRU_BWD_RING", prev) if prev >= 0 else lib.mms_clear_option(b"GRU_BWD_RING"))
+
+
+def test_gru_backward_register_ring(lib):
+    """GRU_BWD_RING = 0 selects the register-ring kernel (also the path for R > 1 rows per CTA / unaligned operands)."""
+    prev = lib.mms_get_option(b"GRU_BWD_RING", -1)
+    ok(lib.mms_set_option(b"GRU_BWD_RING", 0))
+    try:
+        for case in [(5, 40, 64, 32, False), (5, 40, 64, 32, True), (3, 33, 32, 16, True), (2, 240, 64, 128, False)]:
+            _gru_case(lib, *case)
+        _gru_case(lib, 4, 20, 64, 128, True, steps=1)
+        _gru_case(lib, 4, 20, 64, 128, False, steps=3)
+    finally:
+        ok(lib.mms_set_option(b"GRU_BWD_RING", prev) if prev >= 0 else lib.mms_clear_option(b"GRU_BWD_RING"))
 
 
 def test_gru_single_reverse_step(lib):

@@ -4,8 +4,8 @@ affected ops against the oracle / golden fixtures, then the time of the graph-re
 
     python tools/ab_variants.py [--out gpurun_out/ab.json] [--steps 300] NAME=V[,NAME=V...] ...
 
-Each positional argument is one variant (a comma-separated list of option settings); the baseline
-(no option set) is always measured first.  Results are appended to the output file after every
+Each positional argument is one variant (a comma-separated list of option settings); the library's defaults
+(no option set) are always measured first.  Results are appended to the output file after every
 variant, so a run that is cut short still leaves what it measured.  One process, one GPU.
 """
 from __future__ import annotations
@@ -24,8 +24,9 @@ sys.path.insert(0, str(ROOT / "tests"))
 
 
 def set_options(lib, settings):
+    """None clears an option (back to the library's built-in default)."""
     for k, v in settings.items():
-        rc = lib.mms_set_option(k.encode(), int(v))
+        rc = lib.mms_clear_option(k.encode()) if v is None else lib.mms_set_option(k.encode(), int(v))
         assert rc == 0, (k, v)
 
 
@@ -176,7 +177,7 @@ def main():
     variants = [{}] + [dict(kv.split("=") for kv in v.split(",")) for v in args.variants]
     names = set().union(*[set(v) for v in variants])
     for settings in variants:
-        full = {n: int(settings.get(n, 0)) for n in names}      # options not named by a variant are reset to 0
+        full = {n: (int(settings[n]) if n in settings else None) for n in names}    # options a variant does not name are cleared
         set_options(lib, full)
         rec = {"options": full}
         t0 = time.perf_counter()
@@ -192,7 +193,7 @@ def main():
         results["variants"].append(rec)
         flush()
         print(json.dumps(rec), flush=True)
-    set_options(lib, {n: 0 for n in names})
+    set_options(lib, {n: None for n in names})
 
 
 if __name__ == "__main__":
