@@ -428,6 +428,22 @@ static int model_backward(const mms_cnngru_desc* d, const float* x, const float*
     const int I_top = top == 0 ? m.O : 2 * H;
     float* dxcur = w.dxa;
     float* dxnext = w.dxb;
+    // Weight gradients of the top layer: side stream 0, forked from wherever this is called.  MMS_WGRAD_DEFER=1 (experiment)
+    // forks them after the NEXT layer's recurrence has been enqueued instead of right after the top one, so that they overlap
+    // the conv backward chain rather than the layer-0 recurrence (whose CTAs lose issue slots to co-resident GEMM CTAs).
+    auto top_wgrad = [&]() -> int {
+        cudaStream_t sw = fk.fork(0);
+        int r = gemm_tn(w.D_tf, 4 * H, 3 * H, 0, in_top, I_top, 0, L, G + po.w_ih[top], I_top, G + po.b_ih[top], M, 3 * H, I_top, sw);
+        if (r) return r;
+        r = gemm_tn(w.D_tf, 4 * H, 2 * H, H, w.hs_tf, H, -1, L, G + po.w_hh[top], H, G + po.b_hh[top], M, 3 * H, H, sw);
+        if (r) return r;
+        r = gemm_tn(w.D_tr, 4 * H, 3 * H, 0, in_top + (int64_t)(L - 1) * I_top, (int64_t)L * I_top, 0, 1,
+                    G + po.w_ih[top] + (int64_t)3 * H * I_top, I_top, G + po.b_ih[top] + 3 * H, B, 3 * H, I_top, sw);
+        if (r) return r;
+        // h_prev = 0 for the single reverse step: dW_hh(reverse) = 0, only the bias gradient remains
+        return gemm_tn(w.D_tr, 4 * H, 2 * H, H, nullptr, 0, 0, 1, nullptr, 0, G + po.b_hh[top] + 3 * H, B, 3 * H, 0, sw);
+    };
+    const bool defer_top_wgrad = top >= 1 && option_get("WGRAD_DEFER", 0) == 1;
     {
         mms_gru_dir_bwd dirs[2];
         memset(dirs, 0, sizeof(dirs));
@@ -445,18 +461,11 @@ static int model_backward(const mms_cnngru_desc* d, const float* x, const float*
         dirs[1].t0 = L - 1; dirs[1].dt = -1; dirs[1].nsteps = 1;
         rc = launch_gru_bwd(dirs, 2, B, H, p, d->rng_seed, d->rng_offset, d->rng_offset_dev, st);
         if (rc) return rc;
-        // weight gradients of the top layer (off the critical path -> side stream)
-        cudaStream_t sw = fk.fork(0);
-        rc = gemm_tn(w.D_tf, 4 * H, 3 * H, 0, in_top, I_top, 0, L, G + po.w_ih[top], I_top, G + po.b_ih[top], M, 3 * H, I_top, sw);
-        if (rc) return rc;
-        rc = gemm_tn(w.D_tf, 4 * H, 2 * H, H, w.hs_tf, H, -1, L, G + po.w_hh[top], H, G + po.b_hh[top], M, 3 * H, H, sw);
-        if (rc) return rc;
-        rc = gemm_tn(w.D_tr, 4 * H, 3 * H, 0, in_top + (int64_t)(L - 1) * I_top, (int64_t)L * I_top, 0, 1,
-                                G + po.w_ih[top] + (int64_t)3 * H * I_top, I_top, G + po.b_ih[top] + 3 * H, B, 3 * H, I_top, sw);
-        if (rc) return rc;
-        // h_prev = 0 for the single reverse step: dW_hh(reverse) = 0, only the bias gradient remains
-        rc = gemm_tn(w.D_tr, 4 * H, 2 * H, H, nullptr, 0, 0, 1, nullptr, 0, G + po.b_hh[top] + 3 * H, B, 3 * H, 0, sw);
-        if (rc) return rc;
+        // weight gradients of the top layer (off the critical path -> side stream), here or after the next recurrence
+        if (!defer_top_wgrad) {
+            rc = top_wgrad();
+            if (rc) return rc;
+        }
         if (top >= 1) {
             // the single reverse step only touches the rows t = L-1: its B-row product goes to dx_extra on a side
             // stream, beside the big product below; the layer underneath adds it at t = L-1
@@ -516,6 +525,10 @@ static int model_backward(const mms_cnngru_desc* d, const float* x, const float*
         }
         rc = launch_gru_bwd(dirs, 2, B, H, p, d->rng_seed, d->rng_offset, d->rng_offset_dev, st);
         if (rc) return rc;
+        if (defer_top_wgrad && l == top - 1) {
+            rc = top_wgrad();
+            if (rc) return rc;
+        }
         cudaStream_t sw = fk.fork(1 - (l & 1));
         for (int dd = 0; dd < 2; ++dd) {
             const float* Dd = w.D[l] + dd * 4 * H;

@@ -10,6 +10,7 @@ device (the reference syncs twice per step through ``loss.item()``, trainer.py:1
 from __future__ import annotations
 
 import contextlib
+import os
 import ctypes as C
 import threading
 import time
@@ -171,7 +172,10 @@ def capture_graph(enqueue):
     dev = torch.cuda.current_device()
     side = _CAPTURE_STREAMS.get(dev)
     if side is None:
-        side = _CAPTURE_STREAMS[dev] = torch.cuda.Stream(device=dev)
+        # MMS_CAPTURE_PRIORITY=-1 (experiment): kernel nodes inherit the priority of the stream they were captured on, so
+        # the step's critical chain outranks the library's weight-gradient side streams (default priority) in CTA dispatch
+        prio = int(os.environ.get("MMS_CAPTURE_PRIORITY", "0"))
+        side = _CAPTURE_STREAMS[dev] = torch.cuda.Stream(device=dev, priority=prio)
     cur = torch.cuda.current_stream()
     side.wait_stream(cur)
     graph = torch.cuda.CUDAGraph()

@@ -57,3 +57,23 @@ def test_no_cpu_fallback_without_gpu():
         pytest.skip("GPU present")
     with pytest.raises(_ext.MmsError):
         _ext.lib()
+
+
+def test_option_registry_is_host_only_and_defaults_belong_to_the_caller(monkeypatch):
+    """mms_set_option / mms_get_option / mms_clear_option (include/mms_b200.h): explicit value > environment (read once) >
+    the default of the call site, which is never cached."""
+    from multimodalsignal_b200 import _ext
+    lib = _ext.load_library()
+    assert lib.mms_get_option(b"TEST_ONLY_A", 7) == 7
+    assert lib.mms_get_option(b"TEST_ONLY_A", 9) == 9          # a default passed earlier is not remembered
+    assert lib.mms_set_option(b"TEST_ONLY_A", 3) == 0
+    assert lib.mms_get_option(b"TEST_ONLY_A", 9) == 3
+    assert lib.mms_clear_option(b"TEST_ONLY_A") == 0
+    assert lib.mms_get_option(b"TEST_ONLY_A", 9) == 9
+    monkeypatch.setenv("MMS_TEST_ONLY_B", "5")
+    assert lib.mms_get_option(b"TEST_ONLY_B", 1) == 5          # environment, read at first use
+    monkeypatch.setenv("MMS_TEST_ONLY_B", "6")
+    assert lib.mms_get_option(b"TEST_ONLY_B", 1) == 5          # ... and only then
+    assert lib.mms_set_option(b"TEST_ONLY_B", 2) == 0
+    assert lib.mms_get_option(b"TEST_ONLY_B", 1) == 2
+    assert lib.mms_set_option(b"", 1) < 0 and b"empty name" in lib.mms_last_error()
