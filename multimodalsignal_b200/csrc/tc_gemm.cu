@@ -247,7 +247,12 @@ int launch_tc_gemm_nt(const float* A, int64_t lda, const float* W, int64_t ldw, 
     rc = make_map(&mapB, W, N, K, ldw, BN);
     if (rc) return rc;
     const size_t stage = (size_t)2 * TC_BM * TC_BK * 4 + (size_t)2 * BN * TC_BK * 4;
-    const size_t smem = stage * TC_STAGES + 1024;
+    // MMS_NT_TRIM_STAGES=1 (experiment): a product with a single k-block (K <= 32: the layer-0 input projection) only
+    // ever touches stage 0, so it can ask for one stage of shared memory and let two CTAs share an SM (81 KB, 2 x 256
+    // TMEM columns), overlapping one CTA's epilogue with the other's TMA / split / MMA
+    const int nkb = (K + TC_BK - 1) / TC_BK;
+    const int stages = (option_get("NT_TRIM_STAGES", 0) == 1 && nkb < TC_STAGES) ? nkb : TC_STAGES;
+    const size_t smem = stage * stages + 1024;
     static bool attr_done = false;
     if (!attr_done) {
         MMS_CUDA(cudaFuncSetAttribute(tc_gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -277,7 +282,7 @@ int launch_tc_gemm_nt(const float* A, int64_t lda, const float* W, int64_t ldw, 
 //   * 3xTF32 operand split and warp roles as in the NT kernel; the splitter warps also zero the B rows that the
 //     shift moves across a sequence boundary.
 constexpr int TN_KB = 32;           // reduction rows per k-block
-constexpr int TN_STAGES = 2;
+constexpr int TN_STAGES = 2;        // pipeline depth of the default instantiation (NS below)
 constexpr int TN_BLK = TN_KB * 128; // bytes of one [KB x 32 floats] column block
 
 struct TcGemmTnParams {
@@ -291,11 +296,14 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-// dynamic smem per stage: [A_hi (nblkA blocks) | A_lo | B_hi (nblkB + 1 blocks) | B_lo], 1024-byte aligned
+// dynamic smem per stage: [A_hi (nblkA blocks) | A_lo | B_hi (nblkB + 1 blocks) | B_lo], 1024-byte aligned.
+// NS = pipeline stages: 2 by default; 1 (MMS_TN_STAGES=1, experiment) halves the shared-memory footprint (<= 88 KB), so
+// that a weight-gradient CTA on a side stream no longer blocks its SM for the conv / pool kernels of the main chain.
+template <int NS>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                    const __grid_constant__ CUtensorMap mapB, const TcGemmTnParams p) {
     extern __shared__ __align__(1024) uint8_t tc_smem[];
-    __shared__ __align__(8) uint64_t full_bar[TN_STAGES], split_bar[TN_STAGES], empty_bar[TN_STAGES], acc_bar;
+    __shared__ __align__(8) uint64_t full_bar[NS], split_bar[NS], empty_bar[NS], acc_bar;
     __shared__ uint32_t tmem_base_sh;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -313,7 +321,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_tn_kernel(const __grid_
     while ((int)tmem_cols < ntiles * Nstride) tmem_cols <<= 1;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TN_STAGES; ++s) {
+        for (int s = 0; s < NS; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&split_bar[s], 4);
             mbar_init(&empty_bar[s], 1);
@@ -328,7 +336,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_tn_kernel(const __grid_
     // constant ones block of B (never touched by TMA): logical (row r, column 0) = 1 sits in 32-byte chunk (r & 3) of row r
     if (warp >= 2) {
         const int t = threadIdx.x - 64;
-        for (int s = 0; s < TN_STAGES; ++s) {
+        for (int s = 0; s < NS; ++s) {
             float4* hi = reinterpret_cast<float4*>(base + (size_t)s * stage_bytes + 2 * a_bytes + (size_t)p.nblkB * TN_BLK);
             float4* lo = reinterpret_cast<float4*>(base + (size_t)s * stage_bytes + 2 * a_bytes + b_bytes + (size_t)p.nblkB * TN_BLK);
             for (int i = t; i < TN_BLK / 16; i += 128) {
@@ -348,7 +356,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_tn_kernel(const __grid_
         // ===== TMA producer: one box per 32-column block =====
         if (lane == 0) {
             for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % TN_STAGES, round = kb / TN_STAGES;
+                const int s = kb % NS, round = kb / NS;
                 if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);
                 uint8_t* st = base + (size_t)s * stage_bytes;
                 const int m0 = mbeg + kb * TN_KB;
@@ -366,7 +374,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_tn_kernel(const __grid_
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_tf32_mn(Nmma);
             for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % TN_STAGES, round = kb / TN_STAGES;
+                const int s = kb % NS, round = kb / NS;
                 mbar_wait(&split_bar[s], round & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t st = smem_u32(base + (size_t)s * stage_bytes);
@@ -392,7 +400,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_tn_kernel(const __grid_
         // ===== operand splitters (warps 2..5), then epilogue =====
         const int t = threadIdx.x - 64;
         for (int kb = 0; kb < nkb; ++kb) {
-            const int s = kb % TN_STAGES, round = kb / TN_STAGES;
+            const int s = kb % NS, round = kb / NS;
             mbar_wait(&full_bar[s], round & 1);
             uint8_t* st = base + (size_t)s * stage_bytes;
             const int m0 = mbeg + kb * TN_KB;
@@ -503,15 +511,18 @@ int launch_tc_gemm_tn(const float* A, int64_t lda, int a_split, int a_skip, cons
     if (chunk < 2 * TN_KB) chunk = 2 * TN_KB;
     p.chunk = chunk;
     const size_t stage = (size_t)2 * p.nblkA * TN_BLK + (size_t)2 * (p.nblkB + 1) * TN_BLK;
-    const size_t smem = stage * TN_STAGES + 1024;
+    const int ns = option_get("TN_STAGES", TN_STAGES) == 1 ? 1 : TN_STAGES;
+    const size_t smem = stage * ns + 1024;
     static bool attr_done = false;
     if (!attr_done) {
-        MMS_CUDA(cudaFuncSetAttribute(tc_gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        MMS_CUDA(cudaFuncSetAttribute(tc_gemm_tn_kernel<TN_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        MMS_CUDA(cudaFuncSetAttribute(tc_gemm_tn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         attr_done = true;
     }
     MMS_REQUIRE(smem <= 220 * 1024, "tc_gemm_tn: shared memory %zu too large", smem);
     MMS_PROF_BEGIN(st);
-    tc_gemm_tn_kernel<<<cdiv(M, chunk), TC_THREADS, smem, st>>>(mapA, mapB, p);
+    if (ns == 1) tc_gemm_tn_kernel<1><<<cdiv(M, chunk), TC_THREADS, smem, st>>>(mapA, mapB, p);
+    else tc_gemm_tn_kernel<TN_STAGES><<<cdiv(M, chunk), TC_THREADS, smem, st>>>(mapA, mapB, p);
     MMS_LAUNCH_CHECK("tc_gemm_tn_kernel");
     return MMS_OK;
 }
