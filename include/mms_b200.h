@@ -273,6 +273,16 @@ int mms_tc_gemm_nt(const float* A, int64_t lda, const float* W, int64_t ldw, con
 int mms_tc_gemm_tn(const float* A, int64_t lda, int32_t a_split, int32_t a_skip, const float* Bm, int64_t ldb,
                    int32_t shift, int32_t seq, float* C, int64_t ldc, float* bias_grad,
                    int32_t M, int32_t N1, int32_t N2, mms_stream_t stream);
+/* Several tensor-core TN products (2..4, each within the limits of mms_tc_gemm_tn) in ONE launch: the weight-gradient
+ * products of a GRU layer (reference models.py:56-63 backward: dW_ih, dW_hh, db_ih, db_hh of both directions) reduce over
+ * the same B*L rows, so one grid of ~148 CTAs covers all of them.  Used by the model when MMS_TN_BATCH=1. */
+typedef struct {
+    const float* A; int64_t lda; int32_t a_split, a_skip;
+    const float* Bm; int64_t ldb; int32_t shift, seq;
+    float* C; int64_t ldc; float* bias_grad;
+    int32_t M, N1, N2;
+} mms_tn_call;
+int mms_tc_gemm_tn_batch(const mms_tn_call* calls_host, int32_t n, mms_stream_t stream);
 int mms_gemm_nt_bias(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
                      float* C, int64_t ldc, int32_t M, int32_t N, int32_t K, mms_stream_t stream);
 int mms_gemm_nn(const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc,

@@ -61,6 +61,16 @@ class GruDirBwd(C.Structure):
     ]
 
 
+class TnCall(C.Structure):
+    """mms_tn_call (include/mms_b200.h): one weight-gradient product of the batched tensor-core kernel."""
+    _fields_ = [
+        ("A", C.c_void_p), ("lda", c_i64), ("a_split", c_i32), ("a_skip", c_i32),
+        ("Bm", C.c_void_p), ("ldb", c_i64), ("shift", c_i32), ("seq", c_i32),
+        ("C", C.c_void_p), ("ldc", c_i64), ("bias_grad", C.c_void_p),
+        ("M", c_i32), ("N1", c_i32), ("N2", c_i32),
+    ]
+
+
 P = C.c_void_p
 _SIGNATURES = {
     "mms_version": (c_i32, []),
@@ -98,6 +108,7 @@ _SIGNATURES = {
     "mms_bn_relu_pool_fwd": (c_i32, [P, P, P, P, P, P, P, c_i32, c_i32, c_i32, c_i32, c_i32, P, P]),
     "mms_bn_relu_pool_bwd": (c_i32, [P, P, P, P, P, P, P, c_i32, c_i32, c_i32, c_i32, c_i32, P, P, P, P, P]),
     "mms_tc_gemm_nt": (c_i32, [P, c_i64, P, c_i64, P, P, c_i64, c_i32, c_i32, c_i32, c_i32, P]),
+    "mms_tc_gemm_tn_batch": (c_i32, [C.POINTER(TnCall), c_i32, P]),
     "mms_tc_gemm_tn": (c_i32, [P, c_i64, c_i32, c_i32, P, c_i64, c_i32, c_i32, P, c_i64, P, c_i32, c_i32, c_i32, P]),
     "mms_gemm_nt_bias": (c_i32, [P, c_i64, P, c_i64, P, P, c_i64, c_i32, c_i32, c_i32, P]),
     "mms_gemm_nn": (c_i32, [P, c_i64, P, c_i64, P, c_i64, c_i32, c_i32, c_i32, c_i32, P]),

@@ -42,6 +42,15 @@ void prof_end(const char* name);
 // environment variable MMS_<name> read once, else `dflt`.
 int option_get(const char* name, int dflt);
 
+// One weight-gradient (TN) product, the argument list of launch_tc_gemm_tn / mms_gemm_tn_acc as a record, so that the
+// products of a GRU layer can be handed to the batched tensor-core kernel in one call.
+struct TnCall {
+    const float* A; int64_t lda; int a_split, a_skip;
+    const float* Bm; int64_t ldb; int shift, seq;
+    float* C; int64_t ldc; float* bias_grad;
+    int M, N1, N2;
+};
+
 static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 

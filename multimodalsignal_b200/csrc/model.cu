@@ -68,6 +68,25 @@ static int gemm_tn(const float* A, int64_t lda, int a_split, int a_skip, const f
     return launch_gemm_tn_acc(A, lda, a_split, a_skip, Bm, ldb, shift, seq, C, ldc, bias_grad, M, N1, N2, st);
 }
 
+int launch_tc_gemm_tn_batch(const TnCall*, int, cudaStream_t);
+
+// Several TN products on one stream: one launch of the batched tensor-core kernel when MMS_TN_BATCH=1 (experiment) and every
+// problem qualifies for it, otherwise one launch each (the default).
+static int gemm_tn_many(const TnCall* c, int n, cudaStream_t st) {
+    bool batch = n > 1 && n <= 4 && use_tc() && option_get("TN_BATCH", 0) == 1;
+    for (int j = 0; batch && j < n; ++j)
+        batch = c[j].M >= 1024 && c[j].N1 > 0 &&
+                tc_gemm_tn_supported(c[j].A, c[j].lda, c[j].a_split, c[j].a_skip, c[j].N2 > 0 ? c[j].Bm : nullptr, c[j].ldb,
+                                     c[j].N2 > 0 ? c[j].C : nullptr, c[j].ldc, c[j].M, c[j].N1, c[j].N2);
+    if (batch) return launch_tc_gemm_tn_batch(c, n, st);
+    for (int j = 0; j < n; ++j) {
+        int rc = gemm_tn(c[j].A, c[j].lda, c[j].a_split, c[j].a_skip, c[j].Bm, c[j].ldb, c[j].shift, c[j].seq, c[j].C, c[j].ldc,
+                         c[j].bias_grad, c[j].M, c[j].N1, c[j].N2, st);
+        if (rc) return rc;
+    }
+    return MMS_OK;
+}
+
 // Side streams: weight-gradient kernels do not feed the backward critical path (recurrence -> dx ->
 // recurrence -> conv chain), so they are forked onto two library-owned streams and joined before the
 // caller's next kernel (Adam).  Event fork/join works identically in eager mode and under CUDA-graph
@@ -433,9 +452,10 @@ static int model_backward(const mms_cnngru_desc* d, const float* x, const float*
     // the conv backward chain rather than the layer-0 recurrence (whose CTAs lose issue slots to co-resident GEMM CTAs).
     auto top_wgrad = [&]() -> int {
         cudaStream_t sw = fk.fork(0);
-        int r = gemm_tn(w.D_tf, 4 * H, 3 * H, 0, in_top, I_top, 0, L, G + po.w_ih[top], I_top, G + po.b_ih[top], M, 3 * H, I_top, sw);
-        if (r) return r;
-        r = gemm_tn(w.D_tf, 4 * H, 2 * H, H, w.hs_tf, H, -1, L, G + po.w_hh[top], H, G + po.b_hh[top], M, 3 * H, H, sw);
+        const TnCall big[2] = {
+            {w.D_tf, 4 * H, 3 * H, 0, in_top, I_top, 0, L, G + po.w_ih[top], I_top, G + po.b_ih[top], M, 3 * H, I_top},
+            {w.D_tf, 4 * H, 2 * H, H, w.hs_tf, H, -1, L, G + po.w_hh[top], H, G + po.b_hh[top], M, 3 * H, H}};
+        int r = gemm_tn_many(big, 2, sw);
         if (r) return r;
         r = gemm_tn(w.D_tr, 4 * H, 3 * H, 0, in_top + (int64_t)(L - 1) * I_top, (int64_t)L * I_top, 0, 1,
                     G + po.w_ih[top] + (int64_t)3 * H * I_top, I_top, G + po.b_ih[top] + 3 * H, B, 3 * H, I_top, sw);
@@ -530,15 +550,16 @@ static int model_backward(const mms_cnngru_desc* d, const float* x, const float*
             if (rc) return rc;
         }
         cudaStream_t sw = fk.fork(1 - (l & 1));
+        TnCall four[4];
         for (int dd = 0; dd < 2; ++dd) {
             const float* Dd = w.D[l] + dd * 4 * H;
-            rc = gemm_tn(Dd, 8 * H, 3 * H, 0, in_l, I_l, 0, L, G + po.w_ih[l] + (int64_t)dd * 3 * H * I_l, I_l,
-                                    G + po.b_ih[l] + dd * 3 * H, M, 3 * H, I_l, sw);
-            if (rc) return rc;
-            rc = gemm_tn(Dd, 8 * H, 2 * H, H, w.hs[l] + dd * H, 2 * H, dd ? 1 : -1, L,
-                                    G + po.w_hh[l] + (int64_t)dd * 3 * H * H, H, G + po.b_hh[l] + dd * 3 * H, M, 3 * H, H, sw);
-            if (rc) return rc;
+            four[2 * dd] = {Dd, 8 * H, 3 * H, 0, in_l, I_l, 0, L, G + po.w_ih[l] + (int64_t)dd * 3 * H * I_l, I_l,
+                            G + po.b_ih[l] + dd * 3 * H, M, 3 * H, I_l};
+            four[2 * dd + 1] = {Dd, 8 * H, 2 * H, H, w.hs[l] + dd * H, 2 * H, dd ? 1 : -1, L,
+                                G + po.w_hh[l] + (int64_t)dd * 3 * H * H, H, G + po.b_hh[l] + dd * 3 * H, M, 3 * H, H};
         }
+        rc = gemm_tn_many(four, 4, sw);
+        if (rc) return rc;
         if (tc_bwd && tc_gemm_supported(w.D[l], 8 * H, w.wT[l], 8 * H, M, I_l, 8 * H)) {
             // both directions in one NT product: K = [fwd 3H | (dq) | rev 3H | (dq)], zero weights on the dq columns
             rc = launch_tc_gemm_nt(w.D[l], 8 * H, w.wT[l], 8 * H, nullptr, dxnext, I_l, M, I_l, 8 * H, 0, st);

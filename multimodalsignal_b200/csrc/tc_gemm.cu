@@ -13,6 +13,7 @@
 //
 //   NT :  C[m, n] (+)= sum_k A[m, k] * B[n, k] + bias[n]        (A, B both K-major = row-major)
 #include "tc_common.cuh"
+#include <string.h>
 
 namespace mms {
 
@@ -302,181 +303,35 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 template <int NS>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                    const __grid_constant__ CUtensorMap mapB, const TcGemmTnParams p) {
-    extern __shared__ __align__(1024) uint8_t tc_smem[];
-    __shared__ __align__(8) uint64_t full_bar[NS], split_bar[NS], empty_bar[NS], acc_bar;
-    __shared__ uint32_t tmem_base_sh;
+#define TN_MAPA (&mapA)
+#define TN_MAPB (&mapB)
+#define TN_CHUNK_IDX blockIdx.x
+#include "tc_gemm_tn_body.inc"
+#undef TN_MAPA
+#undef TN_MAPB
+#undef TN_CHUNK_IDX
+}
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool hasB = p.nblkB > 0;
-    const int nbB = p.nblkB + 1;                                   // + the ones block
-    const uint32_t a_bytes = (uint32_t)p.nblkA * TN_BLK, b_bytes = (uint32_t)nbB * TN_BLK;
-    const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
-    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem) + 1023) & ~(uintptr_t)1023);
-    const int mbeg = blockIdx.x * p.chunk, mend = min(p.M, mbeg + p.chunk);
-    const int nkb = (mend - mbeg + TN_KB - 1) / TN_KB;
-    const int ntiles = (p.N1 + 127) / 128;
-    const int Nmma = p.N2 + 16;                                    // data columns + the ones column (padded to the UMMA N step)
-    const int Nstride = (Nmma + 31) & ~31;                         // TMEM columns between the accumulators of the two M tiles
-    uint32_t tmem_cols = 32;
-    while ((int)tmem_cols < ntiles * Nstride) tmem_cols <<= 1;
+// Up to TN_MAX_BATCH independent problems in ONE launch (MMS_TN_BATCH=1, experiment): the weight-gradient products of a
+// GRU layer are four small split-K GEMMs over the same B*L rows; launched one after the other they cost four launches,
+// four prologues / epilogues and 4 x 96 partial-tile reductions.  Batched, ~148 CTAs cover all of them at once, each with
+// a 2-4 times longer reduction chunk (better pipelining, proportionally fewer red.global.add tiles).
+constexpr int TN_MAX_BATCH = 4;
+struct TnBatchMaps { CUtensorMap a[TN_MAX_BATCH], b[TN_MAX_BATCH]; };
+struct TnBatchParams { TcGemmTnParams p[TN_MAX_BATCH]; int nchunks[TN_MAX_BATCH]; };
 
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < NS; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&split_bar[s], 4);
-            mbar_init(&empty_bar[s], 1);
-        }
-        mbar_init(&acc_bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)), "r"(tmem_cols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    // constant ones block of B (never touched by TMA): logical (row r, column 0) = 1 sits in 32-byte chunk (r & 3) of row r
-    if (warp >= 2) {
-        const int t = threadIdx.x - 64;
-        for (int s = 0; s < NS; ++s) {
-            float4* hi = reinterpret_cast<float4*>(base + (size_t)s * stage_bytes + 2 * a_bytes + (size_t)p.nblkB * TN_BLK);
-            float4* lo = reinterpret_cast<float4*>(base + (size_t)s * stage_bytes + 2 * a_bytes + b_bytes + (size_t)p.nblkB * TN_BLK);
-            for (int i = t; i < TN_BLK / 16; i += 128) {
-                const int r = i >> 3, c = i & 7;
-                hi[i] = make_float4(c == 2 * (r & 3) ? 1.f : 0.f, 0.f, 0.f, 0.f);
-                lo[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_d = tmem_base_sh;
-
-    if (warp == 0) {
-        // ===== TMA producer: one box per 32-column block =====
-        if (lane == 0) {
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % NS, round = kb / NS;
-                if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);
-                uint8_t* st = base + (size_t)s * stage_bytes;
-                const int m0 = mbeg + kb * TN_KB;
-                mbar_expect_tx(&full_bar[s], (uint32_t)(p.nblkA + p.nblkB) * TN_BLK);
-                for (int b = 0; b < p.nblkA; ++b) {
-                    const int i0 = b * 32;
-                    tma_load_2d(&mapA, &full_bar[s], st + (size_t)b * TN_BLK, i0 < p.a_split ? i0 : i0 + p.a_skip, m0);
-                }
-                for (int b = 0; b < p.nblkB; ++b)
-                    tma_load_2d(&mapB, &full_bar[s], st + 2 * a_bytes + (size_t)b * TN_BLK, b * 32, m0 + p.shift);
-            }
-        }
-    } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_tf32_mn(Nmma);
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % NS, round = kb / NS;
-                mbar_wait(&split_bar[s], round & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t st = smem_u32(base + (size_t)s * stage_bytes);
-                const uint32_t a_hi = st, a_lo = st + a_bytes, b_hi = st + 2 * a_bytes, b_lo = st + 2 * a_bytes + b_bytes;
-#pragma unroll
-                for (int k = 0; k < TN_KB / TC_UMMA_K; ++k) {
-                    const uint32_t off = k * 1024;                  // 8 k-rows of 128 bytes
-                    const uint64_t dBh = umma_desc_mnmajor_sw128(b_hi + off, TN_BLK), dBl = umma_desc_mnmajor_sw128(b_lo + off, TN_BLK);
-                    for (int tile = 0; tile < ntiles; ++tile) {
-                        const uint32_t toff = off + (uint32_t)tile * 4 * TN_BLK;      // 128 columns = 4 blocks further
-                        const uint64_t dAh = umma_desc_mnmajor_sw128(a_hi + toff, TN_BLK), dAl = umma_desc_mnmajor_sw128(a_lo + toff, TN_BLK);
-                        const uint32_t dst = tmem_d + (uint32_t)(tile * Nstride);
-                        umma_tf32(dst, dAl, dBh, idesc, (kb | k) != 0);
-                        umma_tf32(dst, dAh, dBl, idesc, 1);
-                        umma_tf32(dst, dAh, dBh, idesc, 1);
-                    }
-                }
-                umma_commit(&empty_bar[s]);
-            }
-            umma_commit(&acc_bar);
-        }
-    } else {
-        // ===== operand splitters (warps 2..5), then epilogue =====
-        const int t = threadIdx.x - 64;
-        for (int kb = 0; kb < nkb; ++kb) {
-            const int s = kb % NS, round = kb / NS;
-            mbar_wait(&full_bar[s], round & 1);
-            uint8_t* st = base + (size_t)s * stage_bytes;
-            const int m0 = mbeg + kb * TN_KB;
-            {
-                float4* hi = reinterpret_cast<float4*>(st);
-                float4* lo = reinterpret_cast<float4*>(st + a_bytes);
-                for (int i = t; i < (int)(a_bytes / 16); i += 128) {
-                    const int m = m0 + ((i >> 3) & (TN_KB - 1));
-                    float4 v = hi[i];
-                    if (m >= mend) v = make_float4(0.f, 0.f, 0.f, 0.f);      // rows of the next CTA's chunk
-                    float4 h, l;
-                    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
-                    h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
-                    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
-                    h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
-                    hi[i] = h;
-                    lo[i] = l;
-                }
-            }
-            if (hasB) {
-                float4* hi = reinterpret_cast<float4*>(st + 2 * a_bytes);
-                float4* lo = reinterpret_cast<float4*>(st + 2 * a_bytes + b_bytes);
-                for (int i = t; i < p.nblkB * (TN_BLK / 16); i += 128) {
-                    const int m = m0 + ((i >> 3) & (TN_KB - 1));
-                    const int tt = (m % p.seq) + p.shift;
-                    float4 v = hi[i];
-                    if (tt < 0 || tt >= p.seq) v = make_float4(0.f, 0.f, 0.f, 0.f);   // h_{t-1} of the first / h_{t+1} of the last step
-                    float4 h, l;
-                    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
-                    h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
-                    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
-                    h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
-                    hi[i] = h;
-                    lo[i] = l;
-                }
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&split_bar[s]);
-        }
-        // ===== epilogue: TMEM lane quarter (warp % 4) -> registers -> red.global.add =====
-        mbar_wait(&acc_bar, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int quarter = warp & 3;
-        for (int tile = 0; tile < ntiles; ++tile) {
-            const int i = tile * 128 + quarter * 32 + lane;
-            const bool live = i < p.N1;
-            float* crow = p.C ? p.C + (int64_t)i * p.ldc : nullptr;
-            for (int c0 = 0; c0 < Nmma; c0 += 16) {
-                uint32_t r[16];
-                const uint32_t taddr = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(tile * Nstride + c0);
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                      "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                    : "r"(taddr));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (!live) continue;
-                if (c0 < p.N2) {
-                    if (crow) {
-#pragma unroll
-                        for (int j4 = 0; j4 < 4; ++j4)
-                            red_add_v4(crow + c0 + 4 * j4, __uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1]),
-                                       __uint_as_float(r[4 * j4 + 2]), __uint_as_float(r[4 * j4 + 3]));
-                    }
-                } else if (p.bias_grad) {
-                    atomicAdd(p.bias_grad + i, __uint_as_float(r[0]));      // the ones column
-                }
-            }
-        }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols) : "memory");
-    }
+template <int NS>
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_tn_batch_kernel(const __grid_constant__ TnBatchMaps maps, const TnBatchParams bp) {
+    const int j = blockIdx.y;
+    if ((int)blockIdx.x >= bp.nchunks[j]) return;      // whole CTA leaves before any barrier / TMEM allocation
+    const TcGemmTnParams p = bp.p[j];
+#define TN_MAPA (&maps.a[j])
+#define TN_MAPB (&maps.b[j])
+#define TN_CHUNK_IDX blockIdx.x
+#include "tc_gemm_tn_body.inc"
+#undef TN_MAPA
+#undef TN_MAPB
+#undef TN_CHUNK_IDX
 }
 
 bool tc_gemm_tn_supported(const float* A, int64_t lda, int a_split, int a_skip, const float* Bm, int64_t ldb, float* C, int64_t ldc,
@@ -527,6 +382,58 @@ int launch_tc_gemm_tn(const float* A, int64_t lda, int a_split, int a_skip, cons
     return MMS_OK;
 }
 
+// All of `calls` (2 .. TN_MAX_BATCH problems, each acceptable to tc_gemm_tn_supported) in one launch of the batched kernel.
+// The CTA budget (MMS_TN_BATCH_CTAS, default 148 = one per SM) is shared equally: every problem of a GRU layer reduces over
+// the same B*L rows.
+int launch_tc_gemm_tn_batch(const TnCall* calls, int n, cudaStream_t st) {
+    MMS_REQUIRE(calls && n >= 1 && n <= TN_MAX_BATCH, "tc_gemm_tn_batch: 1..%d problems", TN_MAX_BATCH);
+    TnBatchMaps maps;
+    TnBatchParams bp;
+    memset(&bp, 0, sizeof(bp));
+    int budget = option_get("TN_BATCH_CTAS", 148);
+    if (budget < n) budget = n;
+    const int ns = option_get("TN_STAGES", TN_STAGES) == 1 ? 1 : TN_STAGES;
+    size_t smem = 0;
+    int max_chunks = 0;
+    for (int j = 0; j < n; ++j) {
+        TnCall c = calls[j];
+        MMS_REQUIRE(c.M > 0 && c.N1 > 0, "tc_gemm_tn_batch: problem %d is empty", j);
+        if (c.N2 <= 0 || !c.Bm) { c.N2 = 0; c.Bm = nullptr; c.C = nullptr; }
+        MMS_REQUIRE(tc_gemm_tn_supported(c.A, c.lda, c.a_split, c.a_skip, c.Bm, c.ldb, c.C, c.ldc, c.M, c.N1, c.N2),
+                    "tc_gemm_tn_batch: problem %d has an unsupported shape / alignment", j);
+        MMS_REQUIRE(c.seq >= 1 && (c.shift == 0 || c.M % c.seq == 0), "tc_gemm_tn_batch: M must be a multiple of seq when rows are shifted");
+        int rc = make_map(&maps.a[j], c.A, c.M, (c.a_split < c.N1 ? c.a_skip : 0) + c.N1, c.lda, TN_KB, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        if (rc) return rc;
+        if (c.N2 > 0) rc = make_map(&maps.b[j], c.Bm, c.M, c.N2, c.ldb, TN_KB, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        else maps.b[j] = maps.a[j];
+        if (rc) return rc;
+        TcGemmTnParams& p = bp.p[j];
+        p.C = c.C; p.bias_grad = c.bias_grad; p.ldc = c.ldc; p.M = c.M; p.N1 = c.N1; p.N2 = c.N2; p.a_split = c.a_split; p.a_skip = c.a_skip;
+        p.shift = c.shift; p.seq = c.seq; p.nblkA = c.N1 / 32; p.nblkB = c.N2 / 32;
+        int chunk = (int)align_up(cdiv(c.M, budget / n), TN_KB);
+        if (chunk < 2 * TN_KB) chunk = 2 * TN_KB;
+        p.chunk = chunk;
+        bp.nchunks[j] = cdiv(c.M, chunk);
+        if (bp.nchunks[j] > max_chunks) max_chunks = bp.nchunks[j];
+        const size_t stage = (size_t)2 * p.nblkA * TN_BLK + (size_t)2 * (p.nblkB + 1) * TN_BLK;
+        if (stage * ns + 1024 > smem) smem = stage * ns + 1024;
+    }
+    for (int j = n; j < TN_MAX_BATCH; ++j) { maps.a[j] = maps.a[0]; maps.b[j] = maps.b[0]; }     // unused slots: valid bytes, never read
+    static bool attr_done = false;
+    if (!attr_done) {
+        MMS_CUDA(cudaFuncSetAttribute(tc_gemm_tn_batch_kernel<TN_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        MMS_CUDA(cudaFuncSetAttribute(tc_gemm_tn_batch_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        attr_done = true;
+    }
+    MMS_REQUIRE(smem <= 220 * 1024, "tc_gemm_tn_batch: shared memory %zu too large", smem);
+    dim3 grid(max_chunks, n);
+    MMS_PROF_BEGIN(st);
+    if (ns == 1) tc_gemm_tn_batch_kernel<1><<<grid, TC_THREADS, smem, st>>>(maps, bp);
+    else tc_gemm_tn_batch_kernel<TN_STAGES><<<grid, TC_THREADS, smem, st>>>(maps, bp);
+    MMS_LAUNCH_CHECK("tc_gemm_tn_kernel");
+    return MMS_OK;
+}
+
 // out[c * ldo + col_off + r] = W[r * cols + c]   (W is [rows, cols] row-major)
 __global__ void __launch_bounds__(256) transpose_pad_kernel(const float* __restrict__ W, int rows, int cols, float* __restrict__ out,
                                                             int64_t ldo, int col_off) {
@@ -551,6 +458,16 @@ int launch_transpose_pad(const float* W, int rows, int cols, float* out, int64_t
 }  // namespace mms
 
 using namespace mms;
+
+extern "C" int mms_tc_gemm_tn_batch(const mms_tn_call* calls_host, int32_t n, mms_stream_t stream) {
+    MMS_REQUIRE(calls_host && n >= 1 && n <= TN_MAX_BATCH, "tc_gemm_tn_batch: 1..%d problems", TN_MAX_BATCH);
+    TnCall c[TN_MAX_BATCH];
+    for (int j = 0; j < n; ++j) {
+        const mms_tn_call& h = calls_host[j];
+        c[j] = {h.A, h.lda, h.a_split, h.a_skip, h.Bm, h.ldb, h.shift, h.seq, h.C, h.ldc, h.bias_grad, h.M, h.N1, h.N2};
+    }
+    return launch_tc_gemm_tn_batch(c, n, (cudaStream_t)stream);
+}
 
 extern "C" int mms_tc_gemm_tn(const float* A, int64_t lda, int32_t a_split, int32_t a_skip, const float* Bm, int64_t ldb, int32_t shift,
                               int32_t seq, float* C, int64_t ldc, float* bias_grad, int32_t M, int32_t N1, int32_t N2, mms_stream_t stream) {

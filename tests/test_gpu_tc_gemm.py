@@ -1,5 +1,7 @@
 """tcgen05 / TMA GEMM (3xTF32) against a float64 matmul.  Stated tolerance: 1e-5 of max|C| -- two
 orders of magnitude tighter than a plain tf32 GEMM would pass (5e-4), i.e. fp32-class accuracy."""
+import os
+
 import pytest
 import torch
 
@@ -86,3 +88,67 @@ def test_tc_gemm_tn_3xtf32(B, L, H, N2, lda_mul, ldb_mul, mode, shift):
     if N2:
         assert (C2 - Cd).abs().max().item() <= 4e-5 * refC.abs().max().item()
     assert (b2 - bd).abs().max().item() <= 4e-5 * refb.abs().max().item()
+
+
+@pytest.mark.skipif(os.environ.get("MMS_TEST_EXPERIMENTAL") != "1",
+                    reason="batched TN kernel: written without GPU access at the end of round 1, opt-in until it has run once")
+@pytest.mark.parametrize("stages", [2, 1])
+def test_tc_gemm_tn_batch_equals_single_launches(stages):
+    """mms_tc_gemm_tn_batch on the four weight-gradient products of a bidirectional GRU layer (both directions' dW_ih and
+    dW_hh out of one D [M, 8H]) against float64 and against four single launches."""
+    from multimodalsignal_b200 import _ext
+    lib = _ext.lib()
+    B, L, H, I = 64, 240, 64, 32
+    M = B * L
+    torch.manual_seed(7)
+    D = torch.randn(M, 8 * H).cuda()
+    X = torch.randn(M, I).cuda()
+    Hs = torch.randn(M, 2 * H).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    prev = lib.mms_get_option(b"TN_STAGES", -1)
+    _ext.check(lib.mms_set_option(b"TN_STAGES", stages))
+    try:
+        outs, refs, calls = [], [], (_ext.TnCall * 4)()
+        for dd in range(2):
+            Dd = D[:, dd * 4 * H:(dd + 1) * 4 * H].double().cpu()
+            for which in range(2):
+                N2 = I if which == 0 else H
+                Cd = torch.zeros(3 * H, N2, device="cuda")
+                bd = torch.zeros(3 * H, device="cuda")
+                if which == 0:
+                    Asel, Bm, ldb, shift, a_split, a_skip = Dd[:, :3 * H], X, I, 0, 3 * H, 0
+                    Bsh = X.double().cpu()
+                else:
+                    Asel = torch.cat([Dd[:, :2 * H], Dd[:, 3 * H:]], dim=1)
+                    Bm, ldb, shift, a_split, a_skip = Hs[:, dd * H:], 2 * H, (1 if dd else -1), 2 * H, H
+                    Bv = Hs[:, dd * H:(dd + 1) * H].double().cpu().reshape(B, L, H)
+                    Bsh = torch.zeros_like(Bv)
+                    if shift == -1:
+                        Bsh[:, 1:] = Bv[:, :-1]
+                    else:
+                        Bsh[:, :-1] = Bv[:, 1:]
+                    Bsh = Bsh.reshape(M, H)
+                refs.append((Asel.t() @ Bsh, Asel.sum(dim=0)))
+                outs.append((Cd, bd))
+                c = calls[2 * dd + which]
+                c.A, c.lda, c.a_split, c.a_skip = D.data_ptr() + 4 * dd * 4 * H, 8 * H, a_split, a_skip
+                c.Bm, c.ldb, c.shift, c.seq = Bm.data_ptr(), ldb, shift, L
+                c.C, c.ldc, c.bias_grad = Cd.data_ptr(), N2, bd.data_ptr()
+                c.M, c.N1, c.N2 = M, 3 * H, N2
+        _ext.check(lib.mms_tc_gemm_tn_batch(calls, 4, st))
+        torch.cuda.synchronize()
+        for (Cd, bd), (refC, refb) in zip(outs, refs):
+            assert (Cd.double().cpu() - refC).abs().max().item() <= 2e-5 * refC.abs().max().item()
+            assert (bd.double().cpu() - refb).abs().max().item() <= 2e-5 * refb.abs().max().item()
+        # and the same four products launched one by one
+        for j in range(4):
+            c = calls[j]
+            C1 = torch.zeros_like(outs[j][0])
+            b1 = torch.zeros_like(outs[j][1])
+            _ext.check(lib.mms_tc_gemm_tn(c.A, c.lda, c.a_split, c.a_skip, c.Bm, c.ldb, c.shift, c.seq, C1.data_ptr(), c.ldc, b1.data_ptr(),
+                                          c.M, c.N1, c.N2, st))
+            torch.cuda.synchronize()
+            assert (C1 - outs[j][0]).abs().max().item() <= 4e-5 * refs[j][0].abs().max().item()
+            assert (b1 - outs[j][1]).abs().max().item() <= 4e-5 * refs[j][1].abs().max().item()
+    finally:
+        _ext.check(lib.mms_set_option(b"TN_STAGES", prev) if prev >= 0 else lib.mms_clear_option(b"TN_STAGES"))
