@@ -653,6 +653,10 @@ int launch_conv_wgrad(int which, const float* x, const float* dy, const float* g
     const BnBwd& bn = bnp ? *bnp : NO_BN;
     // conv1: C_in <= 16 pairs x 32 position lanes (512 threads); conv2: 16 channels x C_out/16 groups x 8 lanes
     if (which == 1) {
+        // MMS_WGRAD1_TILE=480 (experiment): the 480-position tile of the earlier version (85 KB instead of 170 KB of shared memory
+        // per CTA, twice the atomics) -- the weight-gradient kernels run beside the main chain and block SMs by their footprint
+        if (c_in <= 8 && option_get("WGRAD1_TILE", 960) == 480)
+            return conv_wgrad_launch<16, CONV1_K, CONV1_S, CONV1_P, 480, 32, 256>(x, dy, gate, B, c_in, l_in, dw, st, bn);
         if (c_in <= 8) return conv_wgrad_launch<16, CONV1_K, CONV1_S, CONV1_P, 960, 32, 256>(x, dy, gate, B, c_in, l_in, dw, st, bn);
         return conv_wgrad_launch<16, CONV1_K, CONV1_S, CONV1_P, 480, 32, 512>(x, dy, gate, B, c_in, l_in, dw, st, bn);
     }
