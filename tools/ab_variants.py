@@ -52,6 +52,9 @@ def parity(lib, quick=False):
         if not quick:
             tm.test_input_gradient_matches_oracle()
             done.append("input_gradient")
+        import __graft_entry__ as entry      # B = 8, T = 3840: M = 1920 rows, the tcgen05 NT / TN GEMM paths, vs the oracle
+        entry.smoke()
+        done.append("smoke_tcgen05_sized")
         return {"ok": True, "checked": done, "seconds": round(time.perf_counter() - t0, 2)}
     except Exception as e:      # noqa: BLE001 - the harness reports, it does not judge
         return {"ok": False, "checked": done, "error": f"{type(e).__name__}: {str(e)[:400]}",

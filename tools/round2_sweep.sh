@@ -1,0 +1,19 @@
+#!/bin/bash
+# First GPU call of round 2: everything the end of round 1 left unmeasured, ~60 s on one B200.
+#   gpurun --timeout 240 -- 'bash tools/round2_sweep.sh'
+# 1. parity + eager kernel times of the switches that select different KERNELS (each variant: GRU op cases, golden model
+#    cases, smoke() at the tcgen05-sized batch; a variant whose parity fails is not timed)
+# 2. the batched TN kernel's own op test (written without GPU access)
+# 3. interleaved graph timings of the side-stream experiments against the default
+set -u
+mkdir -p gpurun_out
+timeout 100 python tools/ab_variants.py --quick --out gpurun_out/r2_parity.json \
+    TN_STAGES=1 TN_SPLIT=48 WGRAD1_TILE=480 NT_TRIM_STAGES=1 GRU_BWD_RING=8 TN_BATCH=1 TN_BATCH=1,TN_STAGES=1 \
+    > gpurun_out/r2_parity.log 2>&1
+MMS_TEST_EXPERIMENTAL=1 timeout 60 python -m pytest tests/test_gpu_tc_gemm.py -q -k batch > gpurun_out/r2_tn_batch_test.log 2>&1
+timeout 120 python tools/ab_variants.py --interleave 3 --steps 300 --out gpurun_out/r2_interleaved.json \
+    GRU_BWD_RING=4 TN_STAGES=1 TN_SPLIT=48 TN_STAGES=1,TN_SPLIT=48 WGRAD1_TILE=480 TN_STAGES=1,WGRAD1_TILE=480 \
+    GRU_BWD_EXCLUSIVE_KB=200 WGRAD_DEFER=1 NT_TRIM_STAGES=1 GRU_BWD_RING=8 TN_BATCH=1 TN_BATCH=1,WGRAD1_TILE=480 \
+    SIDE_STREAMS=0,GRU_BWD_RING=4 \
+    > gpurun_out/r2_interleaved.log 2>&1
+tail -3 gpurun_out/r2_parity.log gpurun_out/r2_tn_batch_test.log gpurun_out/r2_interleaved.log
