@@ -124,8 +124,9 @@ def interleaved(lib, variants, steps, reps, B=64, Cc=6, T=3840):
     pool_y = torch.randint(0, 2, (NB, B), device=dev, generator=gen)
     pool_x[:, :, 0, :] += pool_y[:, :, None].float() * 0.5
     built = []
+    names = set().union(*[set(v) for v in variants]) - {"SIDE_STREAMS"}
     for settings in variants:
-        opts = {k: int(v) for k, v in settings.items() if k != "SIDE_STREAMS"}
+        opts = {k: (int(settings[k]) if k in settings else None) for k in names}      # options a variant does not name are cleared
         set_options(lib, opts)
         lib.mms_set_side_streams(int(settings.get("SIDE_STREAMS", 1)))
         torch.manual_seed(42)
@@ -137,6 +138,7 @@ def interleaved(lib, variants, steps, reps, B=64, Cc=6, T=3840):
         torch.cuda.synchronize()
         built.append((settings, step, model, opt, []))
     lib.mms_set_side_streams(1)
+    set_options(lib, {k: None for k in names})
     for rep in range(reps):
         for settings, step, _, _, times in built:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
