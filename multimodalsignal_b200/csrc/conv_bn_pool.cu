@@ -102,6 +102,112 @@ __global__ void __launch_bounds__(TL) conv1d_fwd_kernel(const float* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------
+// conv1d_fwd, second version (MMS_CONV_FWD_V2=1, experiment; written without GPU access at the end of round 1).
+// ncu on conv1d_fwd_kernel: 40 % of the stall samples are short_scoreboard (waiting for shared-memory loads) and 10 % mio:
+// per (input channel, tap) a thread issues 1 + CO/4 shared-memory loads for CO FFMAs.  Here a thread owns NP output
+// positions (tid + j * TL: the stores stay coalesced), so the CO/4 broadcast weight loads are shared by NP * CO FMAs, the
+// output channels are processed in pairs as packed fma.rn.f32x2 (FFMA2: weights (w[o], w[o+1]) against a broadcast x), and
+// the BatchNorm partial sums of a thread cover NP positions before the warp reduction (NP times fewer shuffles per output).
+// The (c, k) summation order per output is that of conv1d_fwd_kernel, so y is bit-identical; the statistics differ in
+// the last bits only (fp32 partial sums of NP values before the warp reduction).
+template <int CO, int KW, int S, int P, int TL, int NP>
+__global__ void __launch_bounds__(TL) conv1d_fwd_v2_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                           const float* __restrict__ gate, float* __restrict__ y,
+                                                           double* __restrict__ stats, int CI, int Lin, int Lout) {
+    constexpr int TPOS = TL * NP;                 // output positions per CTA
+    constexpr int SPAN = (TPOS - 1) * S + KW;
+    static_assert(CO % 4 == 0 && TL % 32 == 0, "channel quads, whole warps");
+    extern __shared__ __align__(16) float smem[];
+    float* ws = smem;                             // [CI*KW][CO]
+    float* xs = smem + CI * KW * CO;              // [CI][SPAN]   (CI*KW*CO is a multiple of 4: ws rows stay 16-byte aligned)
+    __shared__ double red[TL / 32][2 * CO];
+
+    const int b = blockIdx.y, l0 = blockIdx.x * TPOS, tid = threadIdx.x;
+    const int in0 = l0 * S - P;
+    const float* xb = x + (size_t)b * CI * Lin;
+    for (int idx = tid; idx < CI * SPAN; idx += TL) {
+        const int c = idx / SPAN, i = idx - c * SPAN, gi = in0 + i;
+        const bool ok = gi >= 0 && gi < Lin;
+        cp_async4_zfill(xs + idx, xb + (size_t)c * Lin + (ok ? gi : 0), ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#pragma unroll 4
+    for (int idx = tid; idx < CO * CI * KW; idx += TL) {
+        const int o = idx / (CI * KW), ck = idx - o * (CI * KW), c = ck / KW;
+        const float g = gate ? gate[b * CI + c] : 1.f;
+        ws[ck * CO + o] = w[idx] * g;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+
+    float2 acc[NP][CO / 2];
+#pragma unroll
+    for (int j = 0; j < NP; ++j)
+#pragma unroll
+        for (int o2 = 0; o2 < CO / 2; ++o2) acc[j][o2] = make_float2(0.f, 0.f);
+    const float* xr = xs + tid * S;
+    for (int c = 0; c < CI; ++c) {
+#pragma unroll
+        for (int k = 0; k < KW; ++k) {
+            float xv[NP];
+#pragma unroll
+            for (int j = 0; j < NP; ++j) xv[j] = xr[c * SPAN + j * (TL * S) + k];
+            const float4* wv = reinterpret_cast<const float4*>(ws + (c * KW + k) * CO);
+#pragma unroll
+            for (int o4 = 0; o4 < CO / 4; ++o4) {
+                const float4 wq = wv[o4];
+                const float2 wa = make_float2(wq.x, wq.y), wb = make_float2(wq.z, wq.w);
+#pragma unroll
+                for (int j = 0; j < NP; ++j) {
+                    const float2 xx = make_float2(xv[j], xv[j]);
+                    acc[j][2 * o4] = __ffma2_rn(wa, xx, acc[j][2 * o4]);
+                    acc[j][2 * o4 + 1] = __ffma2_rn(wb, xx, acc[j][2 * o4 + 1]);
+                }
+            }
+        }
+    }
+    bool valid[NP];
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+        const int l = l0 + tid + j * TL;
+        valid[j] = l < Lout;
+        if (valid[j]) {
+            float* yb = y + (size_t)b * CO * Lout + l;
+#pragma unroll
+            for (int o2 = 0; o2 < CO / 2; ++o2) {
+                yb[(size_t)(2 * o2) * Lout] = acc[j][o2].x;
+                yb[(size_t)(2 * o2 + 1) * Lout] = acc[j][o2].y;
+            }
+        }
+    }
+    if (stats) {
+        const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+        for (int o2 = 0; o2 < CO / 2; ++o2) {
+            float sx = 0.f, sy = 0.f, qx = 0.f, qy = 0.f;
+#pragma unroll
+            for (int j = 0; j < NP; ++j) {
+                const float vx = valid[j] ? acc[j][o2].x : 0.f, vy = valid[j] ? acc[j][o2].y : 0.f;
+                sx += vx; sy += vy;
+                qx = fmaf(vx, vx, qx); qy = fmaf(vy, vy, qy);
+            }
+            sx = warp_sum(sx); sy = warp_sum(sy); qx = warp_sum(qx); qy = warp_sum(qy);
+            if (lane == 0) {
+                red[warp][2 * o2] = (double)sx; red[warp][2 * o2 + 1] = (double)sy;
+                red[warp][CO + 2 * o2] = (double)qx; red[warp][CO + 2 * o2 + 1] = (double)qy;
+            }
+        }
+        __syncthreads();
+        if (tid < 2 * CO) {
+            double t = 0.0;
+#pragma unroll
+            for (int wq = 0; wq < TL / 32; ++wq) t += red[wq][tid];
+            atomicAdd(stats + tid, t);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 struct BnAffine { float a, b, mean, inv; };
 
 __device__ __forceinline__ BnAffine bn_affine(int training, const double* stats, const float* gamma, const float* beta,
@@ -555,6 +661,24 @@ static int conv_fwd_launch(const float* x, const float* w, const float* gate, in
     return MMS_OK;
 }
 
+template <int CO, int KW, int S, int P, int TL, int NP>
+static int conv_fwd_v2_launch(const float* x, const float* w, const float* gate, int B, int CI, int Lin, float* y,
+                              double* stats, cudaStream_t st) {
+    static_assert(2 * CO <= TL, "the statistics epilogue needs 2 * CO threads");
+    const int Lout = conv_out_len(Lin, KW, S, P);
+    constexpr int SPAN = (TL * NP - 1) * S + KW;
+    const size_t smem = (size_t)(CI * KW * CO + CI * SPAN) * sizeof(float);
+    auto kern = conv1d_fwd_v2_kernel<CO, KW, S, P, TL, NP>;
+    static bool attr_done = false;
+    if (!attr_done) { MMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr_done = true; }
+    MMS_REQUIRE(smem <= 96 * 1024, "conv1d_fwd_v2: shared memory %zu too large", smem);
+    dim3 grid(cdiv(Lout, TL * NP), B);
+    MMS_PROF_BEGIN(st);
+    kern<<<grid, TL, smem, st>>>(x, w, gate, y, stats, CI, Lin, Lout);
+    MMS_LAUNCH_CHECK("conv1d_fwd_kernel");
+    return MMS_OK;
+}
+
 template <int CO, int KW, int S, int P, int TI, int CPAD>
 static int conv_dgrad_launch_pad(const float* dy, const float* w, int B, int CI, int Lin, float* dx, const float* xdot,
                                  float* dgate, cudaStream_t st, const BnBwd& bn) {
@@ -627,6 +751,10 @@ int launch_conv_fwd(int which, const float* x, const float* w, const float* gate
     if (rc) return rc;
     if (conv_use_tc() && conv_fwd_tc_supported(which, x, c_in, c_out, l_in))     // implicit GEMM on tcgen05 (conv_tc.cu)
         return launch_conv_fwd_tc(which, x, w, gate, B, c_in, c_out, l_in, y, stats, st);
+    if (option_get("CONV_FWD_V2", 0) == 1) {      // experiment: NP = 2 positions per thread, FFMA2 channel pairs
+        if (which == 1) return conv_fwd_v2_launch<16, CONV1_K, CONV1_S, CONV1_P, 128, 2>(x, w, gate, B, c_in, l_in, y, stats, st);
+        if (c_out == 32) return conv_fwd_v2_launch<32, CONV2_K, CONV2_S, CONV2_P, 64, 2>(x, w, gate, B, c_in, l_in, y, stats, st);
+    }
     if (which == 1) return conv_fwd_launch<16, CONV1_K, CONV1_S, CONV1_P, 256>(x, w, gate, B, c_in, l_in, y, stats, st);
     if (c_out == 16) return conv_fwd_launch<16, CONV2_K, CONV2_S, CONV2_P, 128>(x, w, gate, B, c_in, l_in, y, stats, st);
     if (c_out == 32) return conv_fwd_launch<32, CONV2_K, CONV2_S, CONV2_P, 128>(x, w, gate, B, c_in, l_in, y, stats, st);
