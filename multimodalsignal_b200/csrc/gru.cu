@@ -588,6 +588,149 @@ __global__ void __launch_bounds__(2 * H) gru_bwd_ring_kernel(const GruBwdParams 
 #undef MMS_RING_LOAD
 }
 
+// Forward recurrence, second version (MMS_GRU_FWD_V2=1, experiment; written without GPU access at the end of round 1; one
+// batch row per CTA).  Same algorithm and data movement as gru_fwd_kernel, three changes aimed at the dependent chain of a
+// step (ncu: 36 % fixed-latency waits, 21 % short scoreboard, 4 % branch resolving on one warp per scheduler):
+//   * thread (j, q) = (tid >> 1, tid & 1) owns ONE hidden unit and half of the reduction index, so the partial sums meet in
+//     ONE shuffle stage instead of two.  FFMA2 packing: (r, z) gate weights of the unit against a broadcast h_k, and the n
+//     gate over pairs of k against (h_k, h_k+1); the (r, z) chain is split in two accumulators to keep three 16-deep chains;
+//   * -log2(e) is folded into W_h{r,z}, b_h{r,z} and (off the chain) into the input projections, -2 log2(e) into the n gate:
+//     sigma(x) = 1 / (1 + 2^x') and tanh(a) = 2 / (1 + 2^a'') - 1 lose the multiplies in front of ex2;
+//   * both lanes of a unit hold the same h: the shared-memory store is unconditional, global stores are predicated by
+//     selects -- no divergent branch in the loop; every loop invariant is pinned (see gru_bwd_ring_kernel).
+// The stashed W_hn h + b_hn is un-scaled again off the chain (one rounding, ~1e-7 relative).
+template <int H>
+__global__ void __launch_bounds__(2 * H) gru_fwd_v2_kernel(const GruFwdParams prm) {
+    constexpr int KH = H / 2;                 // reduction elements per thread
+    constexpr int HPAD = H + 8;               // two halves, each padded by 4 floats (distinct banks for the two lanes of a unit)
+    constexpr float C1 = -1.4426950408889634f, C2 = 2.f * C1, INV_C2 = 1.f / C2;
+    static_assert(KH % 4 == 0, "float4 reads of h");
+    const mms_gru_dir_fwd d = prm.dir[blockIdx.y];
+    const int tid = threadIdx.x, j = tid >> 1, q = tid & 1;
+    const int bb = blockIdx.x;                // one batch row per CTA: grid.x == B
+    int nsteps = d.nsteps;
+    MMS_OPAQUE32(nsteps);
+
+    __shared__ __align__(16) float hsm[2][HPAD];
+    __shared__ __align__(16) float gsm[PF][3 * H];
+
+    // recurrent weights of unit j, columns [q*KH, q*KH + KH), pre-scaled
+    float2 w_rz[KH];      // (W_hr, W_hz)[j][k] * C1
+    float2 w_n[KH / 2];   // (W_hn[j][2i], W_hn[j][2i+1]) * C2
+#pragma unroll
+    for (int i = 0; i < KH; ++i)
+        w_rz[i] = make_float2(C1 * __ldg(d.w_hh + (size_t)(0 * H + j) * H + q * KH + i), C1 * __ldg(d.w_hh + (size_t)(1 * H + j) * H + q * KH + i));
+#pragma unroll
+    for (int i = 0; i < KH / 2; ++i)
+        w_n[i] = make_float2(C2 * __ldg(d.w_hh + (size_t)(2 * H + j) * H + q * KH + 2 * i),
+                             C2 * __ldg(d.w_hh + (size_t)(2 * H + j) * H + q * KH + 2 * i + 1));
+    const float2 b_rz = q == 0 ? make_float2(C1 * __ldg(d.b_hh + j), C1 * __ldg(d.b_hh + H + j)) : make_float2(0.f, 0.f);
+    const float2 b_n = q == 0 ? make_float2(C2 * __ldg(d.b_hh + 2 * H + j), 0.f) : make_float2(0.f, 0.f);
+
+    for (int i = tid; i < 2 * HPAD; i += 2 * H) (&hsm[0][0])[i] = 0.f;        // h0 = 0
+
+    int do_stash = d.stash != nullptr ? 1 : 0;
+    MMS_OPAQUE32(do_stash);
+    int64_t hs_step = (int64_t)d.dt * d.hs_ts, st_step = (int64_t)d.dt * d.st_ts, gi_step = (int64_t)d.dt * d.gi_ts;
+    MMS_OPAQUE64(hs_step);
+    MMS_OPAQUE64(st_step);
+    MMS_OPAQUE64(gi_step);
+    float* hs_p = d.hs + (int64_t)bb * d.hs_bs + (int64_t)d.t0 * d.hs_ts + j;
+    // lane 0 of a unit stores stash slots 0, 1 (r, z); lane 1 stores slots 2, 3 (n, W_hn h + b_hn).  Without a stash the
+    // pointer stays valid (the h row) and is never written.
+    float* st_p = do_stash ? d.stash + (int64_t)bb * d.st_bs + (int64_t)d.t0 * d.st_ts + (q ? 2 * H : 0) + j : hs_p;
+    int q0 = q == 0 ? 1 : 0;
+    MMS_OPAQUE32(q0);
+
+    uint32_t h_wr_s = (uint32_t)__cvta_generic_to_shared(&hsm[0][0]) + 4u * (uint32_t)(j + (j / KH) * 4);
+    uint32_t h_rd_s = (uint32_t)__cvta_generic_to_shared(&hsm[0][0]) + 4u * (uint32_t)(q * (KH + 4));
+    uint32_t g_rd_s = (uint32_t)__cvta_generic_to_shared(&gsm[0][0]) + 4u * (uint32_t)j;
+    uint32_t g_wr_s = (uint32_t)__cvta_generic_to_shared(&gsm[0][0]) + 16u * (uint32_t)tid;
+    MMS_OPAQUE32(h_wr_s);
+    MMS_OPAQUE32(h_rd_s);
+    MMS_OPAQUE32(g_rd_s);
+    MMS_OPAQUE32(g_wr_s);
+
+    // ring of input projections: threads 0 .. 3H/4-1 copy 16 bytes each of the 3H-float row of a step, PF steps ahead
+    constexpr int NCP = 3 * H / 4;
+    const float* gi_src = d.gi + (int64_t)bb * d.gi_bs + (int64_t)d.t0 * d.gi_ts + 4 * (tid < NCP ? tid : 0);
+    int n_copy = tid < NCP ? nsteps : 0;
+    MMS_OPAQUE32(n_copy);
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+        cp_async16_if(g_wr_s + (uint32_t)(u * 3 * H * 4), gi_src, u < n_copy);
+        gi_src += gi_step;
+        cp_async_commit();
+    }
+    cp_async_wait<PF - 1>();          // step 0 has landed (for the copying threads); the barrier publishes it (and h0)
+    __syncthreads();
+
+    float hprev = 0.f;
+    float p_h = 0.f, p_a = 0.f, p_b = 0.f;        // h and the two stash values of the previous step, stored one step late
+    static_assert(PF % 2 == 0, "the h double buffer index is the parity of the unrolled step");
+    for (int s0 = 0; s0 < nsteps; s0 += PF) {
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+            const int s = s0 + u;
+            if (s >= nsteps) break;
+            const int cur = u & 1;    // compile-time in the unrolled body
+            // pre-scaled input projections of this step (available long before the reduction ends)
+            const uint32_t ga = g_rd_s + (uint32_t)(u * 3 * H * 4);
+            const float g_r = C1 * lds_f32(ga), g_z = C1 * lds_f32(ga + 4 * H), g_n = C2 * lds_f32(ga + 8 * H);
+            float2 a0 = b_rz, a1 = make_float2(0.f, 0.f), an = b_n;
+            const uint32_t ha = h_rd_s + (uint32_t)(cur * HPAD * 4);
+#pragma unroll
+            for (int i4 = 0; i4 < KH / 4; ++i4) {
+                const float4 h4 = lds_v4(ha + 16 * i4);
+                a0 = __ffma2_rn(w_rz[4 * i4 + 0], bcast2(h4.x), a0);
+                a1 = __ffma2_rn(w_rz[4 * i4 + 1], bcast2(h4.y), a1);
+                an = __ffma2_rn(w_n[2 * i4 + 0], make_float2(h4.x, h4.y), an);
+                a0 = __ffma2_rn(w_rz[4 * i4 + 2], bcast2(h4.z), a0);
+                a1 = __ffma2_rn(w_rz[4 * i4 + 3], bcast2(h4.w), a1);
+                an = __ffma2_rn(w_n[2 * i4 + 1], make_float2(h4.z, h4.w), an);
+            }
+            // The global stores of the PREVIOUS step go out here, behind the shared-memory loads of the mat-vec: nothing in
+            // the recurrence depends on them, so they must not sit between a barrier and the loads that follow it.
+            if (s > 0) {
+                if (q0) *hs_p = p_h;
+                if (do_stash) {
+                    st_p[0] = p_a;
+                    st_p[H] = p_b;
+                }
+                hs_p += hs_step;
+                st_p += st_step;
+            }
+            float sr = a0.x + a1.x, sz = a0.y + a1.y, sn = an.x + an.y;
+            sr += __shfl_xor_sync(0xffffffffu, sr, 1);
+            sz += __shfl_xor_sync(0xffffffffu, sz, 1);
+            sn += __shfl_xor_sync(0xffffffffu, sn, 1);
+            // sr, sz = C1 * (W_h{r,z} h + b_h{r,z}); sn = C2 * (W_hn h + b_hn)
+            const float rg = rcp_ftz(1.f + ex2_ftz(sr + g_r));
+            const float zg = rcp_ftz(1.f + ex2_ftz(sz + g_z));
+            const float sg = rcp_ftz(1.f + ex2_ftz(fmaf(rg, sn, g_n)));
+            const float ng = fmaf(2.f, sg, -1.f);
+            const float hn = fmaf(zg, hprev - ng, ng);                        // (1-z)*n + z*h
+            hprev = hn;
+            sts_f32(h_wr_s + (uint32_t)((cur ^ 1) * HPAD * 4), hn);           // both lanes of the unit: same value, same address
+            cp_async_wait<PF - 2>();      // the copies for step s + 1 are complete for the copying threads ...
+            __syncthreads();              // ... and, with h[cur^1], visible to every thread
+            p_h = hn;
+            p_a = q0 ? rg : ng;
+            p_b = q0 ? zg : sn * INV_C2;
+            // every thread has read slot u (before the barrier): refill it with step s + PF; one commit group per step
+            cp_async16_if(g_wr_s + (uint32_t)(u * 3 * H * 4), gi_src, s + PF < n_copy);
+            gi_src += gi_step;
+            cp_async_commit();
+        }
+    }
+    // the last step's outputs (nsteps >= 1)
+    if (q0) *hs_p = p_h;
+    if (do_stash) {
+        st_p[0] = p_a;
+        st_p[H] = p_b;
+    }
+}
+
 static inline int rows_per_cta(int B, int ndirs) {
     // one row per CTA while all CTAs fit in ~2 waves on 148 SMs; more rows per CTA beyond that
     int R = 1;
@@ -599,6 +742,12 @@ template <int H>
 static int gru_fwd_dispatch(const GruFwdParams& prm, int ndirs, cudaStream_t st) {
     const int R = rows_per_cta(prm.B, ndirs);
     dim3 grid(cdiv(prm.B, R), ndirs);
+    if (R == 1 && option_get("GRU_FWD_V2", 0) == 1) {      // experiment (see gru_fwd_v2_kernel)
+        MMS_PROF_BEGIN(st);
+        gru_fwd_v2_kernel<H><<<grid, 2 * H, 0, st>>>(prm);
+        MMS_LAUNCH_CHECK("gru_fwd_kernel");
+        return MMS_OK;
+    }
     MMS_PROF_BEGIN(st);
     if (R == 1) gru_fwd_kernel<H, 1><<<grid, 2 * H, 0, st>>>(prm);
     else if (R == 2) gru_fwd_kernel<H, 2><<<grid, 2 * H, 0, st>>>(prm);
