@@ -327,7 +327,9 @@ def run_ours(args):
             "share_of_critical_path_kernel_time": kern[top]["ms_per_step"] / sum(v["ms_per_step"] for v in critical.values()),
             "selection": "largest per-step time among kernels on the step's critical path (side-stream kernels excluded)",
             "traffic": traffic,
-            "traffic_source": "profiles/r1_ncu_full_summary.json (ncu --set full, dram bytes read + written per launch)" if traffic else None}
+            "traffic_source": ("profiles/r1_ncu_full_summary.json (ncu --set full, dram bytes read + written per launch"
+                               + ("; captured with the register-ring backward kernel of round 1 -- the cp.async-ring kernel that is "
+                                  "now the default reads and writes the same rows" if top == "gru_bwd_kernel" else "") + ")") if traffic else None}
     if hbm_bound:
         roof.update({"bound": "hbm", "unit": "GB/s", "peak": pk["hbm_gbs"], "peak_source": f"{pk['source']} HBM copy bandwidth",
                      "achieved": byte_launch / t_launch / 1e9, "algorithmic_bytes_per_launch": byte_launch,
