@@ -1,0 +1,56 @@
+"""Static facts about the built library (no GPU): the hot kernels use the Blackwell instructions DESIGN.md says they
+use, and the kernels on the default path of the training step do not spill registers.  Reads cuobjdump's SASS and
+ptxas' log through tools/sass_evidence.py; skipped where the CUDA toolkit is absent."""
+import shutil
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT / "tools"))
+
+pytestmark = pytest.mark.skipif(shutil.which("cuobjdump") is None or shutil.which("c++filt") is None,
+                                reason="cuobjdump / c++filt not on PATH")
+
+
+@pytest.fixture(scope="module")
+def facts():
+    from multimodalsignal_b200.build import build
+    build()
+    import sass_evidence
+    return sass_evidence.kernel_facts(), sass_evidence.ptxas_facts()
+
+
+def test_tensor_core_kernels_use_tcgen05_tma_and_tmem(facts):
+    k, _ = facts
+    for name in ("tc_gemm_nt_kernel", "tc_gemm_tn_kernel<2>", "tc_gemm_tn_batch_kernel<2>", "conv1d_fwd_tc_kernel<16, 7, 2, 3>"):
+        f = k[name]
+        assert f.get("UTMALDG (TMA load)", 0) > 0, name
+        assert f.get("UTC*MMA (tcgen05.mma)", 0) > 0, name
+        assert f.get("LDTM (tcgen05.ld)", 0) > 0, name
+
+
+def test_recurrence_kernels_use_packed_fma_and_async_copies(facts):
+    k, _ = facts
+    for name in ("gru_fwd_kernel<64, 1>", "gru_bwd_ring_kernel<64, 4>", "gru_bwd_ring_kernel<64, 8>", "gru_fwd_v2_kernel<64>"):
+        f = k[name]
+        assert f.get("FFMA2 (fma.rn.f32x2)", 0) >= 4 * 48, name        # 48 packed FMAs per step, 4 (or 8) unrolled steps
+        assert f.get("LDGSTS (cp.async)", 0) >= 8, name                 # ring prologue + one refill per unrolled step
+    # the shared-memory-ring backward has no global load inside its loop: every LDG belongs to the weight / head prologue
+    assert "LDGSTS (cp.async)" not in k["gru_bwd_kernel<64, 1>"]        # the register-ring kernel it replaced
+
+
+def test_peer_kernels_use_system_scope_accesses(facts):
+    k, _ = facts
+    assert k["peer_allreduce_adam_kernel"].get("*.SYS loads/stores (peer memory)", 0) > 0
+    assert k["peer_allreduce_f64_kernel"].get("*.SYS loads/stores (peer memory)", 0) > 0
+
+
+def test_no_register_spills_on_the_default_path(facts):
+    _, px = facts
+    spilled = sorted(n for n, v in px.items() if v.get("spill_stores") or v.get("spill_loads"))
+    # known: the 4-rows-per-CTA instantiation of the register-ring GRU backward (B > 592 only) keeps 254 registers busy
+    assert all("gru_bwd_kernelILi64ELi4" in n for n in spilled), spilled
+    ring = [v for n, v in px.items() if "gru_bwd_ring_kernelILi64ELi4" in n]
+    assert ring and ring[0]["registers"] <= 168          # three recurrence CTAs per SM (65536 / (168 * 128))
