@@ -49,6 +49,13 @@ int mms_init(int device);
 int64_t mms_launch_count(void);
 int mms_profile_enable(int32_t on);
 int mms_profile_report(char* buf_host, int64_t buf_bytes);
+/* In-graph timeline (diagnostic; the one place the library allocates: a 16 KB device buffer on first enable).  While
+ * enabled, every launch is bracketed by one-thread kernels that store %globaltimer, on the launch's own stream -- also
+ * under CUDA-graph capture, where the stamps become graph nodes.  mms_timeline_report() synchronises the device and
+ * writes one line per launch of the LAST execution, "name stream_index start_ns end_ns" (relative to the earliest
+ * start), into a host buffer.  Enable before capturing / launching, report after; enabling clears earlier records. */
+int mms_timeline_enable(int32_t on);
+int mms_timeline_report(char* buf_host, int64_t buf_bytes);
 /* Weight-gradient kernels normally run on two library-owned side streams (forked from and joined
  * back into the caller's stream, also under CUDA-graph capture).  0 serialises everything on the
  * caller's stream (used while per-kernel times are taken); also MMS_DISABLE_STREAMS=1. */

@@ -79,6 +79,8 @@ _SIGNATURES = {
     "mms_launch_count": (c_i64, []),
     "mms_profile_enable": (c_i32, [c_i32]),
     "mms_profile_report": (c_i32, [C.c_char_p, c_i64]),
+    "mms_timeline_enable": (c_i32, [c_i32]),
+    "mms_timeline_report": (c_i32, [C.c_char_p, c_i64]),
     "mms_set_side_streams": (c_i32, [c_i32]),
     "mms_set_option": (c_i32, [C.c_char_p, c_i32]),
     "mms_get_option": (c_i32, [C.c_char_p, c_i32]),

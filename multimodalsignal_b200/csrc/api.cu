@@ -60,8 +60,34 @@ static std::vector<ProfRec> g_recs;
 static thread_local cudaStream_t tl_stream = nullptr;
 static thread_local cudaEvent_t tl_begin = nullptr;
 
+// ---- in-graph timeline (diagnostic, mms_timeline_enable): every launch is bracketed by two one-thread kernels that write
+// %globaltimer into a device buffer, on the launch's own stream.  Unlike the event profile above this also works under
+// CUDA-graph capture (the stamps become graph nodes and every replay overwrites the buffer), so it shows what the kernels
+// of the main chain and of the side streams cost WHILE they overlap.  The stamps add ~2 launches of latency per kernel:
+// read overlaps and relative stretch from it, not absolute step times.
+constexpr int TL_MAX = 1024;
+static bool g_tl_on = false;
+static unsigned long long* g_tl_buf = nullptr;          // [TL_MAX][2] start / end, device
+struct TlRec { const char* name; cudaStream_t stream; };
+static std::vector<TlRec> g_tl_recs;
+static thread_local int tl_idx = -1;
+
+__global__ void timeline_stamp_kernel(unsigned long long* slot) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    *slot = t;
+}
+
 void prof_begin(cudaStream_t st) {
     tl_stream = st;
+    if (g_tl_on) {
+        tl_idx = -1;
+        if ((int)g_tl_recs.size() < TL_MAX) {
+            tl_idx = (int)g_tl_recs.size();
+            g_tl_recs.push_back({"?", st});
+            timeline_stamp_kernel<<<1, 1, 0, st>>>(g_tl_buf + 2 * tl_idx);
+        }
+    }
     if (!g_prof_on) return;
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return;
@@ -71,6 +97,11 @@ void prof_begin(cudaStream_t st) {
 
 void prof_end(const char* name) {
     g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (g_tl_on && tl_idx >= 0) {
+        g_tl_recs[tl_idx].name = name;
+        timeline_stamp_kernel<<<1, 1, 0, tl_stream>>>(g_tl_buf + 2 * tl_idx + 1);
+        tl_idx = -1;
+    }
     if (!g_prof_on || !tl_begin) return;
     ProfRec r;
     r.name = name;
@@ -132,6 +163,39 @@ extern "C" int mms_profile_enable(int32_t on) {
     for (auto& r : g_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     g_recs.clear();
     g_prof_on = on != 0;
+    return MMS_OK;
+}
+
+extern "C" int mms_timeline_enable(int32_t on) {
+    g_tl_recs.clear();
+    if (on && !g_tl_buf) MMS_CUDA(cudaMalloc(&g_tl_buf, sizeof(unsigned long long) * 2 * TL_MAX));      // diagnostic only
+    if (on) MMS_CUDA(cudaMemset(g_tl_buf, 0, sizeof(unsigned long long) * 2 * TL_MAX));
+    g_tl_on = on != 0;
+    return MMS_OK;
+}
+
+extern "C" int mms_timeline_report(char* buf_host, int64_t buf_bytes) {
+    MMS_REQUIRE(buf_host && buf_bytes > 0, "timeline_report: bad buffer");
+    MMS_REQUIRE(g_tl_buf, "timeline_report: mms_timeline_enable(1) was never called");
+    MMS_CUDA(cudaDeviceSynchronize());
+    const size_t n = g_tl_recs.size();
+    std::vector<unsigned long long> t(2 * n + 2);
+    if (n) MMS_CUDA(cudaMemcpy(t.data(), g_tl_buf, sizeof(unsigned long long) * 2 * n, cudaMemcpyDeviceToHost));
+    unsigned long long t0 = ~0ull;
+    for (size_t i = 0; i < n; ++i)
+        if (t[2 * i] && t[2 * i] < t0) t0 = t[2 * i];
+    std::map<cudaStream_t, int> sid;
+    std::string out;
+    char line[256];
+    for (size_t i = 0; i < n; ++i) {
+        if (!t[2 * i] || !t[2 * i + 1]) continue;                  // recorded but not executed (yet)
+        auto it = sid.find(g_tl_recs[i].stream);
+        if (it == sid.end()) it = sid.emplace(g_tl_recs[i].stream, (int)sid.size()).first;
+        snprintf(line, sizeof(line), "%s %d %llu %llu\n", g_tl_recs[i].name, it->second, t[2 * i] - t0, t[2 * i + 1] - t0);
+        out += line;
+    }
+    if ((int64_t)out.size() + 1 > buf_bytes) out.resize(buf_bytes - 1);
+    memcpy(buf_host, out.c_str(), out.size() + 1);
     return MMS_OK;
 }
 
