@@ -543,6 +543,125 @@ __global__ void __launch_bounds__(TI) conv1d_dgrad_kernel(const float* __restric
     }
 }
 
+// conv1d_dgrad, second version (MMS_CONV_DGRAD_V2=1, experiment; written without GPU access at the end of round 1).  As
+// conv1d_fwd_v2_kernel: a thread owns NP input positions (tid + j * TI, all of one parity because TI is even, hence the same
+// kernel taps), so the CPAD/4 broadcast weight loads of a (tap, output channel) pair serve NP * CPAD FMAs, and the input
+// channels are processed in pairs as packed fma.rn.f32x2.  The (k, o) summation order per element is that of
+// conv1d_dgrad_kernel: dx is bit-identical, dgate differs in the last bits (fp32 partial sums over NP positions).
+template <int CO, int KW, int S, int P, int TI, int CPAD, int NP>
+__global__ void __launch_bounds__(TI) conv1d_dgrad_v2_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+                                                             float* __restrict__ dx, const float* __restrict__ xdot,
+                                                             float* __restrict__ dgate, int CI, int Lin, int Lout, const BnBwd bn) {
+    static_assert(S == 2 && TI % 2 == 0, "stride-2 convolutions; the positions of a thread share their parity");
+    static_assert(CO <= TI && CPAD % 4 == 0, "one thread per output channel for the BN constants; channel quads");
+    constexpr int TPOS = TI * NP;
+    constexpr int NL = (TPOS - 1 + KW - 1) / S + 2;
+    extern __shared__ __align__(16) float smem[];
+    float* ws = smem;                    // [KW][CO][CPAD]
+    float* dys = smem + KW * CO * CPAD;  // [CO][NL]
+    float* ys = dys + CO * NL;           // [CO][NL], only with the folded BatchNorm backward
+    __shared__ float red[TI / 32][CPAD];
+    __shared__ float s_bn[CO][5];
+    if (bn.y) bn_bwd_constants<CO>(bn, Lout, s_bn);
+
+    const int b = blockIdx.y, i0 = blockIdx.x * TPOS, tid = threadIdx.x;
+    const int lbase = floor_div2(i0 + P - (KW - 1));
+    const float* dyb = dy + (size_t)b * CO * Lout;
+    for (int idx = tid; idx < CO * NL; idx += TI) {
+        const int o = idx / NL, ll = idx - o * NL, l = lbase + ll;
+        const bool ok = l >= 0 && l < Lout;
+        cp_async4_zfill(dys + idx, dyb + (size_t)o * Lout + (ok ? l : 0), ok);
+        if (bn.y) cp_async4_zfill(ys + idx, bn.y + (size_t)b * CO * Lout + (size_t)o * Lout + (ok ? l : 0), ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#pragma unroll 4
+    for (int idx = tid; idx < KW * CO * CPAD; idx += TI) {
+        const int c = idx % CPAD, ko = idx / CPAD, o = ko % CO, k = ko / CO;
+        ws[idx] = c < CI ? __ldg(w + ((size_t)o * CI + c) * KW + k) : 0.f;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    if (bn.y) {          // dyn -> dy in place (positions outside the tensor stay zero)
+        for (int idx = tid; idx < CO * NL; idx += TI) {
+            const int o = idx / NL, l = lbase + (idx - o * NL);
+            if (l >= 0 && l < Lout)
+                dys[idx] = s_bn[o][0] * (dys[idx] - s_bn[o][3] - (ys[idx] - s_bn[o][1]) * s_bn[o][2] * s_bn[o][4]);
+        }
+        __syncthreads();
+    }
+
+    const int ibase = i0 + tid;
+    float2 acc[NP][CPAD / 2];
+#pragma unroll
+    for (int j = 0; j < NP; ++j)
+#pragma unroll
+        for (int c2 = 0; c2 < CPAD / 2; ++c2) acc[j][c2] = make_float2(0.f, 0.f);
+    for (int k = (ibase + P) & 1; k < KW; k += S) {
+        // ibase + P - k is even (may be negative: staged as zero); position j sits TI / S tile entries further
+        const int ll0 = (ibase + P - k) / S - lbase;
+        int llc[NP];
+        float keep[NP];
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+            const int ll = ll0 + j * (TI / S);
+            const bool ok = ll >= 0 && ll < NL;
+            llc[j] = ok ? ll : 0;
+            keep[j] = ok ? 1.f : 0.f;
+        }
+        for (int o = 0; o < CO; ++o) {
+            float d[NP];
+#pragma unroll
+            for (int j = 0; j < NP; ++j) d[j] = dys[o * NL + llc[j]] * keep[j];
+            const float4* wv = reinterpret_cast<const float4*>(ws + (k * CO + o) * CPAD);
+#pragma unroll
+            for (int c4 = 0; c4 < CPAD / 4; ++c4) {
+                const float4 wq = wv[c4];
+                const float2 wa = make_float2(wq.x, wq.y), wb = make_float2(wq.z, wq.w);
+#pragma unroll
+                for (int j = 0; j < NP; ++j) {
+                    const float2 dd = make_float2(d[j], d[j]);
+                    acc[j][2 * c4] = __ffma2_rn(wa, dd, acc[j][2 * c4]);
+                    acc[j][2 * c4 + 1] = __ffma2_rn(wb, dd, acc[j][2 * c4 + 1]);
+                }
+            }
+        }
+    }
+    bool valid[NP];
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+        const int i = ibase + j * TI;
+        valid[j] = i < Lin;
+        if (dx && valid[j]) {
+#pragma unroll
+            for (int c2 = 0; c2 < CPAD / 2; ++c2) {
+                if (2 * c2 < CI) dx[((size_t)b * CI + 2 * c2) * Lin + i] = acc[j][c2].x;
+                if (2 * c2 + 1 < CI) dx[((size_t)b * CI + 2 * c2 + 1) * Lin + i] = acc[j][c2].y;
+            }
+        }
+    }
+    if (xdot) {
+        const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+        for (int c = 0; c < CPAD; ++c) {
+            float v = 0.f;
+#pragma unroll
+            for (int j = 0; j < NP; ++j) {
+                const float a = (c & 1) ? acc[j][c / 2].y : acc[j][c / 2].x;
+                if (valid[j] && c < CI) v = fmaf(a, __ldg(xdot + ((size_t)b * CI + c) * Lin + ibase + j * TI), v);
+            }
+            v = warp_sum(v);
+            if (lane == 0) red[warp][c] = v;
+        }
+        __syncthreads();
+        if (tid < CI) {
+            float t = 0.f;
+#pragma unroll
+            for (int wq = 0; wq < TI / 32; ++wq) t += red[wq][tid];
+            atomicAdd(dgate + b * CI + tid, t);
+        }
+    }
+}
+
 // dw[o,c,k] += gate[b,c] * sum_l dy[b,o,l] * x[b,c,S*l+k-P]
 // One CTA = one batch row x TLW output positions, staged in shared memory.  A thread owns one input channel c, one group
 // of 16 output channels and every NPL-th position of the tile: its 16 x KW partial sums live in registers, so a position
@@ -695,6 +814,23 @@ static int conv_dgrad_launch_pad(const float* dy, const float* w, int B, int CI,
     return MMS_OK;
 }
 
+template <int CO, int KW, int S, int P, int TI, int CPAD, int NP>
+static int conv_dgrad_v2_launch_pad(const float* dy, const float* w, int B, int CI, int Lin, float* dx, const float* xdot,
+                                    float* dgate, cudaStream_t st, const BnBwd& bn) {
+    const int Lout = conv_out_len(Lin, KW, S, P);
+    constexpr int NL = (TI * NP - 1 + KW - 1) / S + 2;
+    const size_t smem = (size_t)(KW * CO * CPAD + (bn.y ? 2 : 1) * CO * NL) * sizeof(float);
+    auto kern = conv1d_dgrad_v2_kernel<CO, KW, S, P, TI, CPAD, NP>;
+    static bool attr_done = false;
+    if (!attr_done) { MMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr_done = true; }
+    MMS_REQUIRE(smem <= 96 * 1024, "conv1d_dgrad_v2: shared memory %zu too large", smem);
+    dim3 grid(cdiv(Lin, TI * NP), B);
+    MMS_PROF_BEGIN(st);
+    kern<<<grid, TI, smem, st>>>(dy, w, dx, xdot, dgate, CI, Lin, Lout, bn);
+    MMS_LAUNCH_CHECK("conv1d_dgrad_kernel");
+    return MMS_OK;
+}
+
 template <int CO, int KW, int S, int P, int TI>
 static int conv_dgrad_launch(const float* dy, const float* w, int B, int CI, int Lin, float* dx, const float* xdot,
                              float* dgate, cudaStream_t st, const BnBwd& bn) {
@@ -768,6 +904,12 @@ int launch_conv_dgrad(int which, const float* dy, const float* w, int B, int c_i
     int rc = check_conv(which, c_in, c_out);
     if (rc) return rc;
     const BnBwd& bn = bnp ? *bnp : NO_BN;
+    if (option_get("CONV_DGRAD_V2", 0) == 1) {     // experiment: NP = 2 positions per thread, FFMA2 channel pairs
+        if (which == 1 && c_in <= 8)
+            return conv_dgrad_v2_launch_pad<16, CONV1_K, CONV1_S, CONV1_P, 128, 8, 2>(dy, w, B, c_in, l_in, dx, xdot, dgate, st, bn);
+        if (which == 2 && c_out == 32)
+            return conv_dgrad_v2_launch_pad<32, CONV2_K, CONV2_S, CONV2_P, 64, 16, 2>(dy, w, B, c_in, l_in, dx, xdot, dgate, st, bn);
+    }
     if (which == 1) return conv_dgrad_launch<16, CONV1_K, CONV1_S, CONV1_P, 256>(dy, w, B, c_in, l_in, dx, xdot, dgate, st, bn);
     if (c_out == 16) return conv_dgrad_launch<16, CONV2_K, CONV2_S, CONV2_P, 128>(dy, w, B, c_in, l_in, dx, xdot, dgate, st, bn);
     if (c_out == 32) return conv_dgrad_launch<32, CONV2_K, CONV2_S, CONV2_P, 128>(dy, w, B, c_in, l_in, dx, xdot, dgate, st, bn);

@@ -8,13 +8,13 @@
 set -u
 mkdir -p gpurun_out
 timeout 100 python tools/ab_variants.py --quick --out gpurun_out/r2_parity.json \
-    TN_STAGES=1 TN_SPLIT=48 WGRAD1_TILE=480 NT_TRIM_STAGES=1 GRU_BWD_RING=8 CONV_FWD_V2=1 GRU_FWD_V2=1 TN_BATCH=1 TN_BATCH=1,TN_STAGES=1 \
+    TN_STAGES=1 TN_SPLIT=48 WGRAD1_TILE=480 NT_TRIM_STAGES=1 GRU_BWD_RING=8 CONV_FWD_V2=1 CONV_DGRAD_V2=1 GRU_FWD_V2=1 TN_BATCH=1 TN_BATCH=1,TN_STAGES=1 \
     > gpurun_out/r2_parity.log 2>&1
 MMS_TEST_EXPERIMENTAL=1 timeout 60 python -m pytest tests/test_gpu_tc_gemm.py -q -k batch > gpurun_out/r2_tn_batch_test.log 2>&1
-MMS_CONV_FWD_V2=1 timeout 60 python -m pytest tests/test_gpu_ops.py -q -k conv1d >> gpurun_out/r2_tn_batch_test.log 2>&1
+MMS_CONV_FWD_V2=1 MMS_CONV_DGRAD_V2=1 timeout 60 python -m pytest tests/test_gpu_ops.py -q -k conv1d >> gpurun_out/r2_tn_batch_test.log 2>&1
 timeout 120 python tools/ab_variants.py --interleave 3 --steps 300 --out gpurun_out/r2_interleaved.json \
     GRU_BWD_RING=4 TN_STAGES=1 TN_SPLIT=48 TN_STAGES=1,TN_SPLIT=48 WGRAD1_TILE=480 TN_STAGES=1,WGRAD1_TILE=480 \
-    GRU_BWD_EXCLUSIVE_KB=200 WGRAD_DEFER=1 NT_TRIM_STAGES=1 GRU_BWD_RING=8 CONV_FWD_V2=1 GRU_FWD_V2=1 GRU_FWD_V2=1,CONV_FWD_V2=1,GRU_BWD_RING=8 TN_BATCH=1 TN_BATCH=1,WGRAD1_TILE=480 \
+    GRU_BWD_EXCLUSIVE_KB=200 WGRAD_DEFER=1 NT_TRIM_STAGES=1 GRU_BWD_RING=8 CONV_FWD_V2=1 CONV_DGRAD_V2=1 GRU_FWD_V2=1 GRU_FWD_V2=1,CONV_FWD_V2=1,CONV_DGRAD_V2=1,GRU_BWD_RING=8 TN_BATCH=1 TN_BATCH=1,WGRAD1_TILE=480 \
     SIDE_STREAMS=0,GRU_BWD_RING=4 \
     > gpurun_out/r2_interleaved.log 2>&1
 # 4. where the time goes INSIDE the graph: per-launch start / end with the side streams on and off (stretch per kernel)
