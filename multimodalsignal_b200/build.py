@@ -69,5 +69,38 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
+def build_pdl(force: bool = False) -> Path:
+    """The programmatic-dependent-launch variant (-DMMS_PDL, see csrc/mms_common.cuh) as a SECOND library,
+    ``libmms_b200_pdl.so``, beside the default one; select it with ``MMS_B200_LIB=<path>``.  Round-2 experiment:
+    compiled and checked for the griddepcontrol instructions (ACQBULK / PREEXIT in the SASS), not yet run on a GPU."""
+    lib = PKG / "libmms_b200_pdl.so"
+    stamp = CSRC / ".build_stamp_pdl"
+    digest = _digest() + ":pdl"
+    if not force and lib.exists() and stamp.exists() and stamp.read_text() == digest:
+        return lib
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    objdir = CSRC / "pdl_objs"
+    objdir.mkdir(exist_ok=True)
+    procs = []
+    for src in _sources():
+        obj = objdir / (src.stem + ".o")
+        flags = [f for f in NVCC_FLAGS if f not in ("-Xptxas", "-v")]
+        cmd = [nvcc, *flags, "-DMMS_PDL", "-c", str(src), "-o", str(obj)]
+        procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    objs = []
+    for src, obj, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            sys.stderr.write(out)
+            raise RuntimeError(f"nvcc -DMMS_PDL failed on {src.name}")
+        objs.append(str(obj))
+    subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(lib), *objs], check=True)
+    stamp.write_text(digest)
+    return lib
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--pdl" in sys.argv:
+        print(build_pdl(force="--force" in sys.argv))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

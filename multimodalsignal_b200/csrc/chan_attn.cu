@@ -13,6 +13,7 @@ constexpr int CA_MAX_A = 8;
 __global__ void __launch_bounds__(256) chan_gate_kernel(const float* __restrict__ x, const float* __restrict__ w1,
                                                         const float* __restrict__ w2, int C, int A, int T,
                                                         float* __restrict__ mean_out, float* __restrict__ gate_out) {
+    MMS_PDL_PROLOGUE();
     __shared__ float s_mean[CA_MAX_C];
     __shared__ float s_hid[CA_MAX_A];
     const int b = blockIdx.x;
@@ -91,6 +92,7 @@ __global__ void __launch_bounds__(256) chan_param_bwd_kernel(const float* __rest
                                                              const float* __restrict__ w2, int B, int C, int A,
                                                              float* __restrict__ scratch, float* __restrict__ ds,
                                                              float* __restrict__ dw1, float* __restrict__ dw2) {
+    MMS_PDL_PROLOGUE();
     float* dpre2 = scratch;
     float* hid = scratch + (size_t)B * C;
     float* dhid = hid + (size_t)B * A;
@@ -154,6 +156,8 @@ int launch_chan_gate(const float* x, const float* w1, const float* w2, int B, in
     MMS_REQUIRE(C >= 1 && C <= CA_MAX_C, "chan_attn: in_channels %d outside [1,%d]", C, CA_MAX_C);
     const int A = C / 4;
     MMS_PROF_BEGIN(st);
+    // plain launch on purpose (never MMS_LAUNCH): the first kernel of a step must depend on the previous step's Adam in full,
+    // so that no kernel of this step can start -- and read parameters ahead of its MMS_PDL_WAIT -- while Adam still writes them
     chan_gate_kernel<<<B, 256, 0, st>>>(x, w1, w2, C, A, T, mean_out, gate_out);
     MMS_LAUNCH_CHECK("chan_gate_kernel");
     return MMS_OK;
@@ -164,7 +168,7 @@ int launch_chan_param_bwd(const float* dg, const float* mean, const float* gate,
     const int A = C / 4;
     if (A == 0) return MMS_OK;          // no parameters
     MMS_PROF_BEGIN(st);
-    chan_param_bwd_kernel<<<1, 256, 0, st>>>(dg, mean, gate, w1, w2, B, C, A, scratch, ds, dw1, dw2);
+    MMS_LAUNCH(chan_param_bwd_kernel, dim3(1), dim3(256), 0, st, dg, mean, gate, w1, w2, B, C, A, scratch, ds, dw1, dw2);
     MMS_LAUNCH_CHECK("chan_param_bwd_kernel");
     return MMS_OK;
 }

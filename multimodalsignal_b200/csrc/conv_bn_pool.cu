@@ -31,6 +31,7 @@ template <int CO, int KW, int S, int P, int TL>
 __global__ void __launch_bounds__(TL) conv1d_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ gate, float* __restrict__ y,
                                                         double* __restrict__ stats, int CI, int Lin, int Lout) {
+    MMS_PDL_PROLOGUE();
     constexpr int SPAN = (TL - 1) * S + KW;
     extern __shared__ __align__(16) float smem[];
     float* ws = smem;                       // [CI*KW][CO]
@@ -114,6 +115,7 @@ template <int CO, int KW, int S, int P, int TL, int NP>
 __global__ void __launch_bounds__(TL) conv1d_fwd_v2_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                            const float* __restrict__ gate, float* __restrict__ y,
                                                            double* __restrict__ stats, int CI, int Lin, int Lout) {
+    MMS_PDL_PROLOGUE();
     constexpr int TPOS = TL * NP;                 // output positions per CTA
     constexpr int SPAN = (TPOS - 1) * S + KW;
     static_assert(CO % 4 == 0 && TL % 32 == 0, "channel quads, whole warps");
@@ -283,6 +285,7 @@ __global__ void __launch_bounds__(256) bn_relu_pool_fwd_ncl_kernel(const float* 
                                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                    float* rm, float* rv, int64_t* nbt, int Bn, int C, int Lin,
                                                                    int Lout, int training, float* __restrict__ out) {
+    MMS_PDL_PROLOGUE();
     extern __shared__ __align__(16) float zs[];
     const int c = blockIdx.x, b = blockIdx.y;
     const double n = (double)Bn * (double)Lin;
@@ -305,6 +308,7 @@ __global__ void __launch_bounds__(256) bn_relu_pool_fwd_tm_kernel(const float* _
                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                   float* rm, float* rv, int64_t* nbt, int Bn, int C, int Lin,
                                                                   int Lout, int training, float* __restrict__ out) {
+    MMS_PDL_PROLOGUE();
     __shared__ float tile[32][65];
     __shared__ float sa[64], sb[64];
     const int b = blockIdx.y, j0 = blockIdx.x * 32;
@@ -341,6 +345,7 @@ __global__ void __launch_bounds__(256) pool_relu_bwd_kernel(const float* __restr
                                                             const float* __restrict__ dout, int Bn, int C, int Lin, int Lout,
                                                             int training, int time_major, float* __restrict__ dy,
                                                             double* __restrict__ red) {
+    MMS_PDL_PROLOGUE();
     extern __shared__ __align__(16) float bsm[];
     float* zs = bsm;                 // [Lin]  relu(bn(y))
     float* ds = bsm + ((Lin + 3) & ~3);   // [Lout] upstream gradient of this row
@@ -461,6 +466,7 @@ template <int CO, int KW, int S, int P, int TI, int CPAD>
 __global__ void __launch_bounds__(TI) conv1d_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w,
                                                           float* __restrict__ dx, const float* __restrict__ xdot,
                                                           float* __restrict__ dgate, int CI, int Lin, int Lout, const BnBwd bn) {
+    MMS_PDL_PROLOGUE();
     static_assert(S == 2, "stride-2 convolutions only");
     static_assert(CO <= TI, "one thread per output channel for the BN constants");
     constexpr int NL = (TI - 1 + KW - 1) / S + 2;
@@ -552,6 +558,7 @@ template <int CO, int KW, int S, int P, int TI, int CPAD, int NP>
 __global__ void __launch_bounds__(TI) conv1d_dgrad_v2_kernel(const float* __restrict__ dy, const float* __restrict__ w,
                                                              float* __restrict__ dx, const float* __restrict__ xdot,
                                                              float* __restrict__ dgate, int CI, int Lin, int Lout, const BnBwd bn) {
+    MMS_PDL_PROLOGUE();
     static_assert(S == 2 && TI % 2 == 0, "stride-2 convolutions; the positions of a thread share their parity");
     static_assert(CO <= TI && CPAD % 4 == 0, "one thread per output channel for the BN constants; channel quads");
     constexpr int TPOS = TI * NP;
@@ -775,7 +782,7 @@ static int conv_fwd_launch(const float* x, const float* w, const float* gate, in
     MMS_REQUIRE(smem <= 96 * 1024, "conv1d_fwd: shared memory %zu too large", smem);
     dim3 grid(cdiv(Lout, TL), B);
     MMS_PROF_BEGIN(st);
-    kern<<<grid, TL, smem, st>>>(x, w, gate, y, stats, CI, Lin, Lout);
+    MMS_LAUNCH(kern, grid, dim3(TL), smem, st, x, w, gate, y, stats, CI, Lin, Lout);
     MMS_LAUNCH_CHECK("conv1d_fwd_kernel");
     return MMS_OK;
 }
@@ -793,7 +800,7 @@ static int conv_fwd_v2_launch(const float* x, const float* w, const float* gate,
     MMS_REQUIRE(smem <= 96 * 1024, "conv1d_fwd_v2: shared memory %zu too large", smem);
     dim3 grid(cdiv(Lout, TL * NP), B);
     MMS_PROF_BEGIN(st);
-    kern<<<grid, TL, smem, st>>>(x, w, gate, y, stats, CI, Lin, Lout);
+    MMS_LAUNCH(kern, grid, dim3(TL), smem, st, x, w, gate, y, stats, CI, Lin, Lout);
     MMS_LAUNCH_CHECK("conv1d_fwd_kernel");
     return MMS_OK;
 }
@@ -809,7 +816,7 @@ static int conv_dgrad_launch_pad(const float* dy, const float* w, int B, int CI,
     if (!attr_done) { MMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr_done = true; }
     dim3 grid(cdiv(Lin, TI), B);
     MMS_PROF_BEGIN(st);
-    kern<<<grid, TI, smem, st>>>(dy, w, dx, xdot, dgate, CI, Lin, Lout, bn);
+    MMS_LAUNCH(kern, grid, dim3(TI), smem, st, dy, w, dx, xdot, dgate, CI, Lin, Lout, bn);
     MMS_LAUNCH_CHECK("conv1d_dgrad_kernel");
     return MMS_OK;
 }
@@ -826,7 +833,7 @@ static int conv_dgrad_v2_launch_pad(const float* dy, const float* w, int B, int 
     MMS_REQUIRE(smem <= 96 * 1024, "conv1d_dgrad_v2: shared memory %zu too large", smem);
     dim3 grid(cdiv(Lin, TI * NP), B);
     MMS_PROF_BEGIN(st);
-    kern<<<grid, TI, smem, st>>>(dy, w, dx, xdot, dgate, CI, Lin, Lout, bn);
+    MMS_LAUNCH(kern, grid, dim3(TI), smem, st, dy, w, dx, xdot, dgate, CI, Lin, Lout, bn);
     MMS_LAUNCH_CHECK("conv1d_dgrad_kernel");
     return MMS_OK;
 }
@@ -945,12 +952,12 @@ int launch_bn_relu_pool_fwd(const float* y, const double* stats, const float* ga
     if (time_major) {
         dim3 grid(cdiv(Lout, 32), B);
         MMS_PROF_BEGIN(st);
-        bn_relu_pool_fwd_tm_kernel<<<grid, 256, 0, st>>>(y, stats, gamma, beta, rm, rv, nbt, Bstat, C, l_in, Lout, training, out);
+        MMS_LAUNCH(bn_relu_pool_fwd_tm_kernel, grid, dim3(256), 0, st, y, stats, gamma, beta, rm, rv, nbt, Bstat, C, l_in, Lout, training, out);
     } else {
         dim3 grid(C, B);
         MMS_REQUIRE((size_t)l_in * sizeof(float) <= 40 * 1024, "bn_relu_pool: row length %d too long for one CTA's shared memory", l_in);
         MMS_PROF_BEGIN(st);
-        bn_relu_pool_fwd_ncl_kernel<<<grid, 256, (size_t)l_in * sizeof(float), st>>>(y, stats, gamma, beta, rm, rv, nbt, Bstat, C, l_in, Lout, training, out);
+        MMS_LAUNCH(bn_relu_pool_fwd_ncl_kernel, grid, dim3(256), (size_t)l_in * sizeof(float), st, y, stats, gamma, beta, rm, rv, nbt, Bstat, C, l_in, Lout, training, out);
     }
     MMS_LAUNCH_CHECK("bn_relu_pool_fwd");
     return MMS_OK;
@@ -970,7 +977,7 @@ int launch_bn_relu_pool_bwd(const float* y, const double* stats, const float* ga
         const size_t smem = (size_t)(((l_in + 3) & ~3) + Lout) * sizeof(float);
         MMS_REQUIRE(smem <= 44 * 1024, "bn_relu_pool_bwd: row length %d too long for one CTA's shared memory", l_in);
         MMS_PROF_BEGIN(st);
-        pool_relu_bwd_kernel<<<grid, 256, smem, st>>>(y, stats, gamma, beta, rm, rv, dout, Bstat, C, l_in, Lout, training, time_major, dy, red);
+        MMS_LAUNCH(pool_relu_bwd_kernel, grid, dim3(256), smem, st, y, stats, gamma, beta, rm, rv, dout, Bstat, C, l_in, Lout, training, time_major, dy, red);
         MMS_LAUNCH_CHECK("pool_relu_bwd_kernel");
     }
     if (which & 2) {

@@ -8,6 +8,7 @@ namespace mms {
 __global__ void __launch_bounds__(256) dropout_apply_kernel(const float* in, float* out, int64_t n,   // in == out allowed
                                                             int64_t base_id, float p, uint64_t seed, uint64_t offset,
                                                             const int64_t* offset_dev) {
+    MMS_PDL_PROLOGUE();
     DropRng rng;
     rng.init(seed, resolve_offset(offset, offset_dev), p);
     const int64_t n4 = n >> 2;
@@ -59,7 +60,7 @@ int launch_dropout_apply(const float* in, float* out, int64_t n, int64_t base_id
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (blocks < 1) blocks = 1;
     MMS_PROF_BEGIN(st);
-    dropout_apply_kernel<<<(int)blocks, 256, 0, st>>>(in, out, n, base_id, p, seed, offset, offset_dev);
+    MMS_LAUNCH(dropout_apply_kernel, dim3((int)blocks), dim3(256), 0, st, in, out, n, base_id, p, seed, offset, offset_dev);
     MMS_LAUNCH_CHECK("dropout_apply_kernel");
     return MMS_OK;
 }

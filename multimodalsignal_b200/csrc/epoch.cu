@@ -21,6 +21,7 @@ __global__ void __launch_bounds__(256) batch_gather_kernel(const float4* __restr
                                                            const int64_t* __restrict__ perm, int64_t* cursor, int64_t n_rows,
                                                            int64_t row_f4, float4* __restrict__ out_x, int64_t* __restrict__ out_y,
                                                            int advance, int32_t* scratch) {
+    MMS_PDL_PROLOGUE();
     const int b = blockIdx.y;
     const int64_t base = cursor ? *cursor : 0;
     int64_t src = perm ? perm[base + b] : base + b;

@@ -75,6 +75,7 @@ __device__ __forceinline__ int padded(int k) { return k + (k / KS) * 4; }
 
 template <int H, int R>
 __global__ void __launch_bounds__(2 * H) gru_fwd_kernel(const GruFwdParams prm) {
+    MMS_PDL_TRIGGER();
     constexpr int KS = H / 4, HP = H / 2, HPAD = H + 16;
     const mms_gru_dir_fwd d = prm.dir[blockIdx.y];
     const int tid = threadIdx.x, p = tid >> 2, q = tid & 3;
@@ -101,6 +102,7 @@ __global__ void __launch_bounds__(2 * H) gru_fwd_kernel(const GruFwdParams prm) 
         bh2[g] = q == 0 ? make_float2(__ldg(d.b_hh + g * H + p), __ldg(d.b_hh + g * H + p + HP)) : make_float2(0.f, 0.f);
 
     for (int i = tid; i < 2 * R * HPAD; i += 2 * H) (&hsm[0][0][0])[i] = 0.f;
+    MMS_PDL_WAIT();       // everything above read parameters only; gi / hs / stash belong to the kernels before this one
 
     const bool do_stash = d.stash != nullptr;
 
@@ -424,6 +426,7 @@ __device__ __forceinline__ void cp_async16_if(uint32_t smem_dst, const void* gme
 
 template <int H, int PF>
 __global__ void __launch_bounds__(2 * H) gru_bwd_ring_kernel(const GruBwdParams prm) {
+    MMS_PDL_TRIGGER();
     constexpr int KS = H / 4, HP = H / 2, GP = H + 16;      // GP: padded length of one gate vector
     constexpr int ROW = 6 * H;                              // floats per ring slot: r, z, n, q | h_prev | dout
     constexpr int NCP = ROW / 4;                            // 16-byte chunks per slot, one per copying thread
@@ -450,6 +453,7 @@ __global__ void __launch_bounds__(2 * H) gru_bwd_ring_kernel(const GruBwdParams 
             w2[g][i] = make_float2(__ldg(d.w_hh + (size_t)(g * H + q * KS + i) * H + p),
                                    __ldg(d.w_hh + (size_t)(g * H + q * KS + i) * H + p + HP));
 
+    MMS_PDL_WAIT();       // the weights above are parameters; stash / hs / dout / dh_head belong to the kernels before this one
     int has_dout = d.dout != nullptr ? 1 : 0;
     MMS_OPAQUE32(has_dout);
     // visit v handles forward step s = nsteps-1-v at time t_last - v*dt
@@ -601,6 +605,7 @@ __global__ void __launch_bounds__(2 * H) gru_bwd_ring_kernel(const GruBwdParams 
 // The stashed W_hn h + b_hn is un-scaled again off the chain (one rounding, ~1e-7 relative).
 template <int H>
 __global__ void __launch_bounds__(2 * H) gru_fwd_v2_kernel(const GruFwdParams prm) {
+    MMS_PDL_TRIGGER();
     constexpr int KH = H / 2;                 // reduction elements per thread
     constexpr int HPAD = H + 8;               // two halves, each padded by 4 floats (distinct banks for the two lanes of a unit)
     constexpr float C1 = -1.4426950408889634f, C2 = 2.f * C1, INV_C2 = 1.f / C2;
@@ -628,6 +633,7 @@ __global__ void __launch_bounds__(2 * H) gru_fwd_v2_kernel(const GruFwdParams pr
     const float2 b_n = q == 0 ? make_float2(C2 * __ldg(d.b_hh + 2 * H + j), 0.f) : make_float2(0.f, 0.f);
 
     for (int i = tid; i < 2 * HPAD; i += 2 * H) (&hsm[0][0])[i] = 0.f;        // h0 = 0
+    MMS_PDL_WAIT();       // parameters only above
 
     int do_stash = d.stash != nullptr ? 1 : 0;
     MMS_OPAQUE32(do_stash);
@@ -744,14 +750,18 @@ static int gru_fwd_dispatch(const GruFwdParams& prm, int ndirs, cudaStream_t st)
     dim3 grid(cdiv(prm.B, R), ndirs);
     if (R == 1 && option_get("GRU_FWD_V2", 0) == 1) {      // experiment (see gru_fwd_v2_kernel)
         MMS_PROF_BEGIN(st);
-        gru_fwd_v2_kernel<H><<<grid, 2 * H, 0, st>>>(prm);
+        auto k2 = gru_fwd_v2_kernel<H>;
+        MMS_LAUNCH(k2, grid, dim3(2 * H), 0, st, prm);
         MMS_LAUNCH_CHECK("gru_fwd_kernel");
         return MMS_OK;
     }
     MMS_PROF_BEGIN(st);
-    if (R == 1) gru_fwd_kernel<H, 1><<<grid, 2 * H, 0, st>>>(prm);
-    else if (R == 2) gru_fwd_kernel<H, 2><<<grid, 2 * H, 0, st>>>(prm);
-    else gru_fwd_kernel<H, 4><<<grid, 2 * H, 0, st>>>(prm);
+    auto k1 = gru_fwd_kernel<H, 1>;
+    auto k2 = gru_fwd_kernel<H, 2>;
+    auto k4 = gru_fwd_kernel<H, 4>;
+    if (R == 1) MMS_LAUNCH(k1, grid, dim3(2 * H), 0, st, prm);
+    else if (R == 2) MMS_LAUNCH(k2, grid, dim3(2 * H), 0, st, prm);
+    else MMS_LAUNCH(k4, grid, dim3(2 * H), 0, st, prm);
     MMS_LAUNCH_CHECK("gru_fwd_kernel");
     return MMS_OK;
 }
@@ -791,8 +801,10 @@ static int gru_bwd_dispatch(const GruBwdParams& prm, int ndirs, cudaStream_t st)
             }
         }
         MMS_PROF_BEGIN(st);
-        if (ring >= 8) gru_bwd_ring_kernel<H, 8><<<grid, 2 * H, dyn, st>>>(prm);
-        else gru_bwd_ring_kernel<H, 4><<<grid, 2 * H, dyn, st>>>(prm);
+        auto r8 = gru_bwd_ring_kernel<H, 8>;
+        auto r4 = gru_bwd_ring_kernel<H, 4>;
+        if (ring >= 8) MMS_LAUNCH(r8, grid, dim3(2 * H), dyn, st, prm);
+        else MMS_LAUNCH(r4, grid, dim3(2 * H), dyn, st, prm);
         MMS_LAUNCH_CHECK("gru_bwd_kernel");
         return MMS_OK;
     }

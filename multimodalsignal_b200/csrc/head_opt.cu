@@ -20,6 +20,7 @@ __global__ void __launch_bounds__(4 * HEAD_HID) head_fwd_kernel(const float* __r
                                                                 uint64_t seed, uint64_t offset, const int64_t* offset_dev,
                                                                 float* __restrict__ last_out,
                                                                 float* __restrict__ hid_out, float* __restrict__ logits) {
+    MMS_PDL_PROLOGUE();
     extern __shared__ __align__(16) float s_last[];        // [H2]
     __shared__ float s_hid[HEAD_HID];
     const int b = blockIdx.x, tid = threadIdx.x, i = tid >> 2, q = tid & 3;
@@ -73,6 +74,7 @@ __global__ void __launch_bounds__(128) head_bwd_kernel(const float* __restrict__
                                                        const int64_t* offset_dev, float* __restrict__ dhid,
                                                        float* __restrict__ dw0, float* __restrict__ db0,
                                                        float* __restrict__ dw3, float* __restrict__ db3) {
+    MMS_PDL_PROLOGUE();
     extern __shared__ float s_dh[];          // [B]
     __shared__ float s_red[4][MAX_NC + 1];
     const int i = blockIdx.x, tid = threadIdx.x;
@@ -129,6 +131,7 @@ __global__ void __launch_bounds__(256) cross_entropy_kernel(const float* __restr
                                                             int B, int nc, float* __restrict__ loss_out,
                                                             float* __restrict__ dlogits, double* __restrict__ loss_sum_accum,
                                                             int div_batch) {
+    MMS_PDL_PROLOGUE();
     __shared__ float s_part[8];
     float local = 0.f;
     const float invB = 1.f / (float)div_batch;     // global batch under data parallelism: the per-rank losses add up
@@ -164,6 +167,7 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, c
                                                         float* __restrict__ v, int64_t n, const float* __restrict__ lr_dev,
                                                         float beta1, float beta2, float eps, float wd, int64_t* step_dev,
                                                         int32_t* scratch) {
+    MMS_PDL_PROLOGUE();
     const double t = (double)(*step_dev + 1);
     const float lr = *lr_dev;
     const float bc1 = (float)(1.0 - pow((double)beta1, t));
@@ -195,7 +199,7 @@ int launch_head_fwd2(const float* src_a, int64_t lda, const float* src_b, int64_
                      const int64_t* offset_dev, float* last_out, float* hid_out, float* logits, cudaStream_t st) {
     MMS_REQUIRE(nc >= 1 && nc <= MAX_NC, "head: num_classes %d outside [1,%d]", nc, MAX_NC);
     MMS_PROF_BEGIN(st);
-    head_fwd_kernel<<<B, 4 * HEAD_HID, H2 * sizeof(float), st>>>(src_a, lda, src_b, ldb, Hh, w0, b0, w3, b3, H2, nc, p, seed, offset,
+    MMS_LAUNCH(head_fwd_kernel, dim3(B), dim3(4 * HEAD_HID), H2 * sizeof(float), st, src_a, lda, src_b, ldb, Hh, w0, b0, w3, b3, H2, nc, p, seed, offset,
                                                              offset_dev, last_out, hid_out, logits);
     MMS_LAUNCH_CHECK("head_fwd_kernel");
     return MMS_OK;
@@ -214,7 +218,7 @@ int launch_head_bwd(const float* last, const float* hid, const float* dlogits, c
     MMS_REQUIRE(nc >= 1 && nc <= MAX_NC, "head: num_classes %d outside [1,%d]", nc, MAX_NC);
     MMS_REQUIRE(B * sizeof(float) <= 40 * 1024, "head_bwd: batch %d too large for one CTA's shared memory", B);
     MMS_PROF_BEGIN(st);
-    head_bwd_kernel<<<HEAD_HID, 128, B * sizeof(float), st>>>(last, hid, dlogits, w3, B, H2, nc, p, seed, offset, offset_dev, dhid,
+    MMS_LAUNCH(head_bwd_kernel, dim3(HEAD_HID), dim3(128), B * sizeof(float), st, last, hid, dlogits, w3, B, H2, nc, p, seed, offset, offset_dev, dhid,
                                                               dw0, db0, dw3, db3);
     MMS_LAUNCH_CHECK("head_bwd_kernel");
     return MMS_OK;
@@ -225,7 +229,7 @@ int launch_cross_entropy(const float* logits, const int64_t* labels, int B, int 
     if (div_batch <= 0) div_batch = B;
     MMS_REQUIRE(nc >= 1 && nc <= MAX_NC, "cross_entropy: num_classes %d outside [1,%d]", nc, MAX_NC);
     MMS_PROF_BEGIN(st);
-    cross_entropy_kernel<<<1, 256, 0, st>>>(logits, labels, B, nc, loss_out, dlogits, loss_sum_accum, div_batch);
+    MMS_LAUNCH(cross_entropy_kernel, dim3(1), dim3(256), 0, st, logits, labels, B, nc, loss_out, dlogits, loss_sum_accum, div_batch);
     MMS_LAUNCH_CHECK("cross_entropy_kernel");
     return MMS_OK;
 }
@@ -234,7 +238,7 @@ int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, const f
                 float eps, float wd, int64_t* step_dev, int32_t* scratch, cudaStream_t st) {
     const int blocks = (int)((n + 255) / 256 < 592 ? (n + 255) / 256 : 592);
     MMS_PROF_BEGIN(st);
-    adam_flat_kernel<<<blocks > 0 ? blocks : 1, 256, 0, st>>>(p, g, m, v, n, lr_dev, beta1, beta2, eps, wd, step_dev, scratch);
+    MMS_LAUNCH(adam_flat_kernel, dim3(blocks > 0 ? blocks : 1), dim3(256), 0, st, p, g, m, v, n, lr_dev, beta1, beta2, eps, wd, step_dev, scratch);
     MMS_LAUNCH_CHECK("adam_flat_kernel");
     return MMS_OK;
 }

@@ -85,8 +85,49 @@ struct BnBwd {
     float grad_scale;
 };
 
+// ---- programmatic dependent launch (build variant, -DMMS_PDL; default build: every macro below is a no-op) ---------
+// 25 dependent launches make up the critical path of a step, and each edge costs the drain of the producer plus the launch,
+// CTA scheduling and prologue of the consumer.  With MMS_PDL the kernels of the main chain are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization: MMS_PDL_TRIGGER() (griddepcontrol.launch_dependents) at the top of a
+// kernel lets the NEXT kernel of the stream start while this one runs, and that kernel executes MMS_PDL_WAIT()
+// (griddepcontrol.wait: every prerequisite grid complete and its memory visible) before it touches anything an earlier
+// kernel of the step wrote or still reads -- after its weight / invariant prologue where that prologue only reads
+// parameters (constant within a step; the first kernel of a step is not launched this way).  Rule: a kernel may be passed to
+// MMS_LAUNCH only if it executes MMS_PDL_WAIT() on every path before its first such access.  The first kernel of the
+// forward and of the backward pass follows a memset node (full dependency) and chan_gate is a plain launch, so every kernel
+// of a step starts after the previous step's Adam has completed: reading parameters ahead of the wait is safe.
+// Build: MMS_NVCC_EXTRA="-DMMS_PDL" python -m multimodalsignal_b200.build --force   (unverified on a GPU, round-2 experiment)
+#ifdef MMS_PDL
+#define MMS_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+#define MMS_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+#else
+#define MMS_PDL_TRIGGER() ((void)0)
+#define MMS_PDL_WAIT() ((void)0)
+#endif
+#define MMS_PDL_PROLOGUE() do { MMS_PDL_TRIGGER(); MMS_PDL_WAIT(); } while (0)
+
 // ---- device helpers -----------------------------------------------------------------
 #ifdef __CUDACC__
+
+#ifdef MMS_PDL
+template <typename... KArgs, typename... Args>
+static inline void pdl_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);      // errors surface in MMS_LAUNCH_CHECK (cudaPeekAtLastError)
+}
+#define MMS_LAUNCH(kern, grid, block, smem, st, ...) ::mms::pdl_launch(kern, grid, block, smem, st, __VA_ARGS__)
+#else
+#define MMS_LAUNCH(kern, grid, block, smem, st, ...) kern<<<grid, block, smem, st>>>(__VA_ARGS__)
+#endif
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -27,6 +27,7 @@ struct TcGemmParams {
 // dynamic smem: [stage][A_hi | A_lo | B_hi | B_lo] (1024-byte aligned tiles)
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                    const __grid_constant__ CUtensorMap mapB, const TcGemmParams p) {
+    MMS_PDL_TRIGGER();
     extern __shared__ __align__(1024) uint8_t tc_smem[];
     __shared__ __align__(8) uint64_t full_bar[TC_STAGES], split_bar[TC_STAGES], empty_bar[TC_STAGES], acc_bar;
     __shared__ uint32_t tmem_base_sh;
@@ -59,6 +60,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const __grid_
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    MMS_PDL_WAIT();       // barrier / TMEM set-up and the bias (a parameter) are done; A and C belong to the kernels before this one
     const uint32_t tmem_d = tmem_base_sh;
 
     if (warp == 0) {
@@ -264,7 +266,7 @@ int launch_tc_gemm_nt(const float* A, int64_t lda, const float* W, int64_t ldw, 
     p.C = C; p.bias = bias; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.BN = BN; p.accumulate = accumulate;
     dim3 grid(cdiv(M, TC_BM), cdiv(N, BN));
     MMS_PROF_BEGIN(st);
-    tc_gemm_nt_kernel<<<grid, TC_THREADS, smem, st>>>(mapA, mapB, p);
+    MMS_LAUNCH(tc_gemm_nt_kernel, grid, dim3(TC_THREADS), smem, st, mapA, mapB, p);
     MMS_LAUNCH_CHECK("tc_gemm_nt_kernel");
     return MMS_OK;
 }

@@ -17,6 +17,9 @@ timeout 120 python tools/ab_variants.py --interleave 3 --steps 300 --out gpurun_
     GRU_BWD_EXCLUSIVE_KB=200 WGRAD_DEFER=1 NT_TRIM_STAGES=1 GRU_BWD_RING=8 CONV_FWD_V2=1 CONV_DGRAD_V2=1 GRU_FWD_V2=1 GRU_FWD_V2=1,CONV_FWD_V2=1,CONV_DGRAD_V2=1,GRU_BWD_RING=8 TN_BATCH=1 TN_BATCH=1,WGRAD1_TILE=480 \
     SIDE_STREAMS=0,GRU_BWD_RING=4 \
     > gpurun_out/r2_interleaved.log 2>&1
+# 3b. the programmatic-dependent-launch build (libmms_b200_pdl.so): parity, then its step time against r2_parity.json's baseline
+MMS_B200_LIB=$PWD/multimodalsignal_b200/libmms_b200_pdl.so timeout 60 python tools/ab_variants.py --quick \
+    --out gpurun_out/r2_pdl.json GRU_BWD_RING=4 > gpurun_out/r2_pdl.log 2>&1
 # 4. where the time goes INSIDE the graph: per-launch start / end with the side streams on and off (stretch per kernel)
 timeout 60 python tools/graph_timeline.py --out gpurun_out/r2_timeline.json > gpurun_out/r2_timeline.log 2>&1
-tail -3 gpurun_out/r2_parity.log gpurun_out/r2_tn_batch_test.log gpurun_out/r2_interleaved.log
+tail -3 gpurun_out/r2_parity.log gpurun_out/r2_tn_batch_test.log gpurun_out/r2_interleaved.log gpurun_out/r2_pdl.log
