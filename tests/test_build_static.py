@@ -54,3 +54,26 @@ def test_no_register_spills_on_the_default_path(facts):
     assert all("gru_bwd_kernelILi64ELi4" in n for n in spilled), spilled
     ring = [v for n, v in px.items() if "gru_bwd_ring_kernelILi64ELi4" in n]
     assert ring and ring[0]["registers"] <= 168          # three recurrence CTAs per SM (65536 / (168 * 128))
+
+
+def test_pdl_variant_carries_griddepcontrol_and_default_does_not():
+    """-DMMS_PDL build (programmatic dependent launch): griddepcontrol.wait / launch_dependents show up as ACQBULK / PREEXIT
+    in the main-chain kernels; the default library has neither (the macros expand to nothing there)."""
+    import subprocess
+    from multimodalsignal_b200.build import build, build_pdl
+    default_sass = subprocess.run(["cuobjdump", "-sass", str(build())], capture_output=True, text=True, check=True).stdout
+    pdl_sass = subprocess.run(["cuobjdump", "-sass", str(build_pdl())], capture_output=True, text=True, check=True).stdout
+    assert "ACQBULK" not in default_sass and "PREEXIT" not in default_sass
+    cur, have = None, {}
+    for line in pdl_sass.splitlines():
+        if "Function :" in line:
+            cur = line.split("Function :")[1].strip()
+            have[cur] = set()
+        elif cur and ("ACQBULK" in line or "PREEXIT" in line):
+            have[cur].add("ACQBULK" if "ACQBULK" in line else "PREEXIT")
+    for frag in ("gru_fwd_kernelILi64ELi1", "gru_bwd_ring_kernelILi64ELi4", "tc_gemm_nt_kernel", "conv1d_fwd_kernelILi16ELi7",
+                 "conv1d_dgrad_kernelILi32ELi5", "pool_relu_bwd_kernel", "head_fwd_kernel", "adam_flat_kernel", "dropout_apply_kernel"):
+        names = [n for n in have if frag in n]
+        assert names and all(have[n] == {"ACQBULK", "PREEXIT"} for n in names), (frag, {n: have[n] for n in names})
+    # kernels that are always launched plainly keep a full dependency: no wait needed, none emitted
+    assert all(not have[n] for n in have if "gru_bwd_kernelILi64ELi1" in n or "tc_gemm_tn_kernel" in n)
