@@ -16,10 +16,11 @@
 //     lanes of a quad hit distinct banks (conflict-free 128-bit loads);
 //   * every global address is a running pointer (no 64-bit multiplies in the loop) and everything a
 //     step needs from global memory (input projections, stashed gates, upstream gradients) is
-//     prefetched: the forward uses a shared-memory ring filled PF-1 steps ahead with cp.async (a register
-//     ring was collapsed to a distance of one step by the compiler's scheduler; wait_group pins the
-//     distance); the backward keeps a register ring, which measured faster there (six values per step
-//     and a shorter gate chain leave no slack to hide the extra shared-memory round trip);
+//     prefetched through a shared-memory ring filled with cp.async, in both directions: commit groups complete in
+//     order, so cp.async.wait_group pins the prefetch distance.  A register ring of plain loads does not work --
+//     the forward's was collapsed to one step by the compiler's scheduler, and the backward's (gru_bwd_kernel, kept
+//     for R > 1 rows per CTA and unaligned operands) stalls on memory although it is four visits deep, because every
+//     one of its loads shares a scoreboard (see gru_bwd_ring_kernel, the default backward, 69 us against 90 us);
 //   * sigmoid / tanh use the ex2 / rcp special-function units (|error| ~ 2e-7, far inside the
 //     1e-4 logit tolerance);
 //   * inter-layer dropout is NOT applied here: a 30-instruction hash per element inside an in-order
