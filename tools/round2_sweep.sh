@@ -1,6 +1,6 @@
 #!/bin/bash
-# First GPU call of round 2: everything the end of round 1 left unmeasured, ~60 s on one B200.
-#   gpurun --timeout 240 -- 'bash tools/round2_sweep.sh'
+# First GPU call of round 2: everything the end of round 1 left unmeasured, ~3 minutes on one B200.
+#   gpurun --timeout 420 -- 'bash tools/round2_sweep.sh'
 # 1. parity + eager kernel times of the switches that select different KERNELS (each variant: GRU op cases, golden model
 #    cases, smoke() at the tcgen05-sized batch; a variant whose parity fails is not timed)
 # 2. the batched TN kernel's own op test (written without GPU access)
@@ -20,6 +20,8 @@ timeout 120 python tools/ab_variants.py --interleave 3 --steps 300 --out gpurun_
 # 3b. the programmatic-dependent-launch build (libmms_b200_pdl.so): parity, then its step time against r2_parity.json's baseline
 MMS_B200_LIB=$PWD/multimodalsignal_b200/libmms_b200_pdl.so timeout 60 python tools/ab_variants.py --quick \
     --out gpurun_out/r2_pdl.json GRU_BWD_RING=4 > gpurun_out/r2_pdl.log 2>&1
+# 3c. the whole GPU suite with the depth-8 backward ring (66.7 us against 69.3 us per launch at depth 4): green = it may become the default
+MMS_GRU_BWD_RING=8 timeout 90 python -m pytest tests -m gpu -x -q > gpurun_out/r2_suite_ring8.log 2>&1
 # 4. where the time goes INSIDE the graph: per-launch start / end with the side streams on and off (stretch per kernel)
 timeout 60 python tools/graph_timeline.py --out gpurun_out/r2_timeline.json > gpurun_out/r2_timeline.log 2>&1
-tail -3 gpurun_out/r2_parity.log gpurun_out/r2_tn_batch_test.log gpurun_out/r2_interleaved.log gpurun_out/r2_pdl.log
+tail -3 gpurun_out/r2_parity.log gpurun_out/r2_tn_batch_test.log gpurun_out/r2_interleaved.log gpurun_out/r2_pdl.log gpurun_out/r2_suite_ring8.log gpurun_out/r2_timeline.log
