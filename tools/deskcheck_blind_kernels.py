@@ -2,7 +2,7 @@
 conv1d_dgrad_v2_kernel): numpy re-enactments of each kernel's THREAD MAPPING and index arithmetic (who owns which unit /
 position, shared-memory layouts and paddings, packed-weight layouts, shuffle partners, tile bounds, truncating division)
 against a direct evaluation of the operator.  They validate the index logic, not the CUDA: the GPU parity tests remain
-the gate (tools/round2_sweep.sh).  Run: python tools/deskcheck_blind_kernels.py
+the gate (tools/round2_sweep.py).  Run: python tools/deskcheck_blind_kernels.py
 """
 import sys
 from pathlib import Path
