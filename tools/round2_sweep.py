@@ -24,10 +24,10 @@ ROOT = Path(__file__).resolve().parents[1]
 OUT = ROOT / "gpurun_out"
 PY = sys.executable
 
-KERNEL_VARIANTS = ["GRU_BWD_RING=8", "TN_STAGES=1", "TN_SPLIT=48", "WGRAD1_TILE=480", "NT_TRIM_STAGES=1",
+KERNEL_VARIANTS = ["GRU_BWD_RING=8", "TN_STAGES=1", "TN_SPLIT=48", "WGRAD1_TILE=480", "WGRAD2_TILE=120", "NT_TRIM_STAGES=1",
                    "CONV_FWD_V2=1", "CONV_DGRAD_V2=1", "GRU_FWD_V2=1", "TN_BATCH=1", "TN_BATCH=1,TN_STAGES=1"]
 SCHEDULING_VARIANTS = ["GRU_BWD_EXCLUSIVE_KB=200", "WGRAD_DEFER=1"]        # same kernels, different placement: no parity risk
-COMBINATIONS = ["TN_STAGES=1,TN_SPLIT=48", "TN_STAGES=1,WGRAD1_TILE=480", "TN_BATCH=1,WGRAD1_TILE=480",
+COMBINATIONS = ["TN_STAGES=1,TN_SPLIT=48", "TN_STAGES=1,WGRAD1_TILE=480", "TN_STAGES=1,WGRAD1_TILE=480,WGRAD2_TILE=120", "TN_BATCH=1,WGRAD1_TILE=480",
                 "GRU_FWD_V2=1,CONV_FWD_V2=1,CONV_DGRAD_V2=1,GRU_BWD_RING=8"]
 
 
