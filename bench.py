@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--seq-len", type=int, default=3840)
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-library-baseline", action="store_true", help="skip the stock PyTorch/cuDNN leg (reference model on the same GPU)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--workload", default="train_step", choices=["train_step", "loso", "preprocess", "dp"],
                     help="train_step = headline metric (default); loso = 15-fold LOSO wall-clock; preprocess = resample+window")
@@ -116,14 +117,54 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+class _ReferenceStep:
+    """The reference's own training step -- ``CnnGruAttentionModel`` from the UNMODIFIED reference ``models.py``
+    (``/root/reference`` or its byte-identical staging ``baseline/_ref``, oracle/build_ref.py), driven exactly as
+    trainer.py:68-69,140-153 drives it: ``inputs.to(device)``, ``zero_grad``, forward, ``CrossEntropyLoss``,
+    ``backward``, ``Adam(lr=1e-3, weight_decay=1e-4).step()``, ``loss.item()``.  ``device`` = "cpu" is the reference arm;
+    ``device`` = "cuda" is the same stock PyTorch / cuDNN path on the B200 ("the library kernel to beat")."""
+
+    def __init__(self, args, device):
+        import torch
+        from oracle import ref_harness
+        models = ref_harness.load("models")
+        torch.manual_seed(0)
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            self.model = models.CnnGruAttentionModel(in_channels=args.channels, num_classes=2).to(device)   # main.py:116, trainer.py:58
+        self.model.train()
+        self.opt = torch.optim.Adam(self.model.parameters(), lr=1e-3, weight_decay=1e-4)                  # trainer.py:68
+        self.crit = torch.nn.CrossEntropyLoss().to(device)                                                # trainer.py:69
+        self.device = device
+
+    def __call__(self, x, y):
+        x, y = x.to(self.device), y.to(self.device)                                                        # trainer.py:140-142
+        self.opt.zero_grad()
+        loss = self.crit(self.model(x), y)
+        loss.backward()
+        self.opt.step()
+        return loss.item()                                                                                 # trainer.py:152
+
+
 def cpu_reference_run(args, steps, warmup, budget_s):
-    """Time oracle/cpu_port.py (bounded by ``budget_s`` seconds of CPU work)."""
+    """Time the reference's CPU training step (bounded by ``budget_s`` seconds of CPU work): the unmodified reference
+    ``models.py`` when it is present (kind "reference"), else oracle/cpu_port.py (kind "port")."""
     import torch
-    from oracle import cpu_port
+    from oracle import ref_harness
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    p, bufs = cpu_port.make_state(C=args.channels, seed=0)
-    step = cpu_port.CpuTrainStep(p, bufs)
+    if ref_harness.available():
+        step = _ReferenceStep(args, "cpu")
+        kind = "reference"
+        what = (f"the unmodified reference models.py ({ref_harness.REFERENCE_ROOT}) driven as trainer.py:140-153 "
+                f"(zero_grad, forward, CrossEntropyLoss, backward, Adam, loss.item())")
+    else:
+        from oracle import cpu_port
+        p, bufs = cpu_port.make_state(C=args.channels, seed=0)
+        step = cpu_port.CpuTrainStep(p, bufs)
+        kind = "port"
+        what = "oracle/cpu_port.py = the reference step through the same ATen CPU kernels (reference tree not staged)"
     g = torch.Generator().manual_seed(1)
     x = torch.randn(args.batch, args.channels, args.seq_len, generator=g)
     y = torch.randint(0, 2, (args.batch,), generator=g)
@@ -138,10 +179,64 @@ def cpu_reference_run(args, steps, warmup, budget_s):
     for _ in range(n):
         step(x, y)
     dt = time.perf_counter() - t0
-    return {"value": args.batch * n / dt, "unit": "windows/s", "cores": threads, "kind": "port",
+    return {"value": args.batch * n / dt, "unit": "windows/s", "cores": threads, "kind": kind,
             "ms_per_step": 1e3 * dt / n, "timed_steps": n,
             "sample": f"{n} full training steps (B={args.batch}, C={args.channels}, T={args.seq_len}, dropout 0.5, Adam) of "
-                      f"oracle/cpu_port.py = the reference step through the same ATen CPU kernels, {threads} threads"}
+                      f"{what}, {threads} threads"}
+
+
+def library_gpu_run(args, dev, steps=30, warmup=5):
+    """the UNMODIFIED reference model on the SAME B200 through stock PyTorch (cuDNN GRU / conv, ATen
+    BatchNorm / pooling, torch.optim.Adam) -- "the library kernel to beat".  Same B / C / T, three precision settings:
+    PyTorch's defaults (what the reference runs: trainer.py never enables AMP and sets no backend flag), strict fp32
+    (TF32 off for matmul and cuDNN -- the arithmetic our kernels match) and TF32 allowed everywhere.  Device-timed with CUDA events, inputs resident in HBM
+    (``value``) and with the reference's own per-step H2D copy + ``loss.item()`` (``e2e``)."""
+    import torch
+    from oracle import ref_harness
+    if not ref_harness.available():
+        return {"unavailable": "reference modules not staged under baseline/_ref"}
+    B, C, T = args.batch, args.channels, args.seq_len
+    gen = torch.Generator().manual_seed(7)
+    hx = torch.randn(8, B, C, T, generator=gen).pin_memory()
+    hy = torch.randint(0, 2, (8, B), generator=gen).pin_memory()
+    dx, dy = hx.to(dev), hy.to(dev)
+    out = {"unit": "windows/s", "kind": "reference models.py on cuda via stock PyTorch/cuDNN (unmodified)",
+           "torch": torch.__version__, "cudnn": torch.backends.cudnn.version(), "steps": steps, "warmup": warmup}
+    saved = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    try:
+        for tag, tf32 in (("pytorch_default", None), ("fp32_strict", (False, False)), ("tf32_allowed", (True, True))):
+            torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32 if tf32 else saved
+            step = _ReferenceStep(args, dev)
+
+            def dev_step(i):                       # inputs already in HBM; no host read-back inside the loop
+                step.opt.zero_grad()
+                loss = step.crit(step.model(dx[i % 8]), dy[i % 8])
+                loss.backward()
+                step.opt.step()
+                return loss
+            for i in range(warmup):
+                dev_step(i)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(steps):
+                dev_step(i)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            t0 = time.perf_counter()
+            for i in range(steps):
+                step(hx[i % 8], hy[i % 8])         # trainer.py:140-153 verbatim: H2D, step, loss.item()
+            torch.cuda.synchronize()
+            e2e_ms = 1e3 * (time.perf_counter() - t0) / steps
+            out[tag] = {"value": B / (ms * 1e-3), "ms_per_step": ms, "e2e_value": B / (e2e_ms * 1e-3), "e2e_ms_per_step": e2e_ms}
+            del step
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = saved
+    out["flags"] = {"pytorch_default": {"matmul.allow_tf32": saved[0], "cudnn.allow_tf32": saved[1]}}
+    out["value"] = out["pytorch_default"]["value"]            # what the unmodified reference runs (trainer.py sets no flag)
+    out["ms_per_step"] = out["pytorch_default"]["ms_per_step"]
+    return out
 
 
 def config_dict(args, n_gpus):
@@ -370,6 +465,15 @@ def run_ours(args):
         "kernels": kernel_table,
         "eager_kernel_ms_per_step": kern_total, "final_loss": loss_after,
     }
+    if world == 1 and not args.no_library_baseline:
+        try:
+            line["library_gpu_baseline"] = library_gpu_run(args, dev)
+            lg = line["library_gpu_baseline"]
+            if "value" in lg:
+                lg["ours_over_library"] = value / lg["value"]
+                lg["ours_over_library_e2e"] = e2e_value / lg["pytorch_default"]["e2e_value"]
+        except Exception as exc:                          # the baseline leg must never take the bench line down
+            line["library_gpu_baseline"] = {"unavailable": f"{type(exc).__name__}: {exc}"}
     if not args.no_cpu_baseline and world == 1:
         r = cpu_reference_run(args, steps=10 ** 6, warmup=2, budget_s=args.cpu_seconds)
         line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -402,12 +506,11 @@ def run_preprocess(args):
     import numpy as np
     import torch
     from multimodalsignal_b200 import _ext, preprocess as pp
-    from oracle import preprocess_oracle as po
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
     lib = _ext.lib()
     sids, subs = _synthetic_subjects(args)
     datas = [s.as_pickle_dict() for s in subs]
-    protos = [po.apply_subject_quirk(s.sid, s.protocol) for s in subs]
+    protos = [pp.base_halving_quirk(s.sid, s.protocol) for s in subs]
 
     def on_device(i):
         chest = {k.decode(): v for k, v in datas[i][b"signal"][b"chest"].items()}
@@ -475,6 +578,7 @@ def run_preprocess(args):
     algo = src_bytes + win_bytes
     pk = peaks()
     # cpu baseline: the numpy oracle (== scipy.signal.resample arithmetic) on a bounded sample: one subject, chest only
+    from oracle import preprocess_oracle as po      # cpu_baseline leg only
     t0 = time.perf_counter()
     po.preprocess_subject(subs[0].sid, subs[0].chest, subs[0].protocol, 64)
     cpu_s = time.perf_counter() - t0
@@ -505,7 +609,6 @@ def run_loso(args):
     import torch
     import torch.distributed as dist
     from multimodalsignal_b200 import _ext, main as mm, preprocess as pp
-    from oracle import preprocess_oracle as po
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -538,7 +641,7 @@ def run_loso(args):
     t0 = time.perf_counter()
     # every rank keeps all subjects resident (replicated, ~0.65 GB); the resampling itself is sharded over the ranks
     # and the streams are exchanged GPU-to-GPU (NCCL broadcast over NVLink)
-    streams = pp.preprocess_subjects_sharded([(s.sid, s.as_pickle_dict, po.apply_subject_quirk(s.sid, s.protocol)) for s in subs],
+    streams = pp.preprocess_subjects_sharded([(s.sid, s.as_pickle_dict, pp.base_halving_quirk(s.sid, s.protocol)) for s in subs],
                                              64, include_wrist=True)
     torch.cuda.synchronize()
     t_pre = time.perf_counter() - t0

@@ -777,8 +777,8 @@ static int conv_fwd_launch(const float* x, const float* w, const float* gate, in
     constexpr int SPAN = (TL - 1) * S + KW;
     const size_t smem = (size_t)(CI * KW * CO + CI * SPAN) * sizeof(float);
     auto kern = conv1d_fwd_kernel<CO, KW, S, P, TL>;
-    static bool attr_done = false;
-    if (!attr_done) { MMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr_done = true; }
+    static PerDeviceOnce attr_once;
+    if (attr_once.need()) { MMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); }
     MMS_REQUIRE(smem <= 96 * 1024, "conv1d_fwd: shared memory %zu too large", smem);
     dim3 grid(cdiv(Lout, TL), B);
     MMS_PROF_BEGIN(st);
@@ -795,8 +795,8 @@ static int conv_fwd_v2_launch(const float* x, const float* w, const float* gate,
     constexpr int SPAN = (TL * NP - 1) * S + KW;
     const size_t smem = (size_t)(CI * KW * CO + CI * SPAN) * sizeof(float);
     auto kern = conv1d_fwd_v2_kernel<CO, KW, S, P, TL, NP>;
-    static bool attr_done = false;
-    if (!attr_done) { MMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr_done = true; }
+    static PerDeviceOnce attr_once;
+    if (attr_once.need()) { MMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); }
     MMS_REQUIRE(smem <= 96 * 1024, "conv1d_fwd_v2: shared memory %zu too large", smem);
     dim3 grid(cdiv(Lout, TL * NP), B);
     MMS_PROF_BEGIN(st);
@@ -812,8 +812,8 @@ static int conv_dgrad_launch_pad(const float* dy, const float* w, int B, int CI,
     constexpr int NL = (TI - 1 + KW - 1) / S + 2;
     const size_t smem = (size_t)(KW * CO * CPAD + (bn.y ? 2 : 1) * CO * NL) * sizeof(float);
     auto kern = conv1d_dgrad_kernel<CO, KW, S, P, TI, CPAD>;
-    static bool attr_done = false;
-    if (!attr_done) { MMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr_done = true; }
+    static PerDeviceOnce attr_once;
+    if (attr_once.need()) { MMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); }
     dim3 grid(cdiv(Lin, TI), B);
     MMS_PROF_BEGIN(st);
     MMS_LAUNCH(kern, grid, dim3(TI), smem, st, dy, w, dx, xdot, dgate, CI, Lin, Lout, bn);
@@ -828,8 +828,8 @@ static int conv_dgrad_v2_launch_pad(const float* dy, const float* w, int B, int 
     constexpr int NL = (TI * NP - 1 + KW - 1) / S + 2;
     const size_t smem = (size_t)(KW * CO * CPAD + (bn.y ? 2 : 1) * CO * NL) * sizeof(float);
     auto kern = conv1d_dgrad_v2_kernel<CO, KW, S, P, TI, CPAD, NP>;
-    static bool attr_done = false;
-    if (!attr_done) { MMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr_done = true; }
+    static PerDeviceOnce attr_once;
+    if (attr_once.need()) { MMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); }
     MMS_REQUIRE(smem <= 96 * 1024, "conv1d_dgrad_v2: shared memory %zu too large", smem);
     dim3 grid(cdiv(Lin, TI * NP), B);
     MMS_PROF_BEGIN(st);
@@ -853,8 +853,8 @@ static int conv_wgrad_launch(const float* x, const float* dy, const float* gate,
     MMS_REQUIRE(CI * (CO / 16) * NPL <= NT, "conv1d_wgrad: %d input channels do not fit the thread mapping", CI);
     const size_t smem = (size_t)((bn.y ? 2 : 1) * CO * (TLW + 4) + ((CI * SPAN + 3) & ~3)) * sizeof(float);
     auto kern = conv1d_wgrad_kernel<CO, KW, S, P, TLW, NPL, NT>;
-    static bool attr_done = false;
-    if (!attr_done) { MMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr_done = true; }
+    static PerDeviceOnce attr_once;
+    if (attr_once.need()) { MMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); }
     MMS_REQUIRE(smem <= 220 * 1024, "conv1d_wgrad: shared memory %zu too large", smem);
     dim3 grid(cdiv(Lout, TLW), B);
     MMS_PROF_BEGIN(st);

@@ -227,8 +227,8 @@ static int conv_fwd_tc_launch(const float* x, const float* w, const float* gate,
     const size_t xs_bytes = (size_t)((CI * (CT_BOX0 + CT_BOX1) * 4 + 1023) & ~1023);
     const size_t smem = xs_bytes + (size_t)2 * 4 * KP * 128 + (size_t)2 * KP * 128 + 1024;
     auto kern = conv1d_fwd_tc_kernel<CO, KW, S, P>;
-    static bool attr_done = false;
-    if (!attr_done) { MMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_done = true; }
+    static PerDeviceOnce attr_once;
+    if (attr_once.need()) { MMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); }
     MMS_REQUIRE(smem <= 200 * 1024, "conv1d_fwd_tc: shared memory %zu too large", smem);
     dim3 grid(cdiv(Lout, CT_TILE), B);
     MMS_PROF_BEGIN(st);

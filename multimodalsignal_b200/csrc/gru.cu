@@ -794,11 +794,11 @@ static int gru_bwd_dispatch(const GruBwdParams& prm, int ndirs, cudaStream_t st)
         size_t dyn = 0;
         if (excl > 0) {
             dyn = (size_t)(excl > 200 ? 200 : excl) * 1024;
-            static bool attr_done = false;
-            if (!attr_done) {
+            static PerDeviceOnce attr_once;
+            if (attr_once.need()) {
                 MMS_CUDA(cudaFuncSetAttribute(gru_bwd_ring_kernel<H, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
                 MMS_CUDA(cudaFuncSetAttribute(gru_bwd_ring_kernel<H, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                attr_done = true;
+               
             }
         }
         MMS_PROF_BEGIN(st);

@@ -51,6 +51,20 @@ struct TnCall {
     int M, N1, N2;
 };
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE property of a kernel: the opt-in guards at the launch
+// sites remember it per device (several devices in one process: mms_init(dev), per-device side streams), not per process.
+struct PerDeviceOnce {
+    bool done[64] = {};
+    bool need() {
+        int d = 0;
+        cudaGetDevice(&d);
+        d &= 63;
+        if (done[d]) return false;
+        done[d] = true;
+        return true;
+    }
+};
+
 static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 

@@ -233,8 +233,8 @@ static int launch_pass(double2* a, int64_t sig_stride, int64_t M, int64_t Mc, in
     const int tc = cols < FFT_TC ? (int)cols : FFT_TC;
     const size_t smem = (size_t)(R * (FFT_TC + 1) + R / 2 + 1) * sizeof(double2);
     auto kern = fft_pass_kernel<R>;
-    static bool attr_done = false;
-    if (!attr_done) { MMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr_done = true; }
+    static PerDeviceOnce attr_once;
+    if (attr_once.need()) { MMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); }
     dim3 grid((unsigned)(cols / tc), n_sig);
     MMS_PROF_BEGIN(st);
     kern<<<grid, FFT_THREADS, smem, st>>>(a, sig_stride, Mc, tc, inverse);

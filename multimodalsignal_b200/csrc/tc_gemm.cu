@@ -256,10 +256,10 @@ int launch_tc_gemm_nt(const float* A, int64_t lda, const float* W, int64_t ldw, 
     const int nkb = (K + TC_BK - 1) / TC_BK;
     const int stages = (option_get("NT_TRIM_STAGES", 0) == 1 && nkb < TC_STAGES) ? nkb : TC_STAGES;
     const size_t smem = stage * stages + 1024;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.need()) {
         MMS_CUDA(cudaFuncSetAttribute(tc_gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_done = true;
+       
     }
     MMS_REQUIRE(smem <= 200 * 1024, "tc_gemm: shared memory %zu too large", smem);
     TcGemmParams p;
@@ -370,11 +370,11 @@ int launch_tc_gemm_tn(const float* A, int64_t lda, int a_split, int a_skip, cons
     const size_t stage = (size_t)2 * p.nblkA * TN_BLK + (size_t)2 * (p.nblkB + 1) * TN_BLK;
     const int ns = option_get("TN_STAGES", TN_STAGES) == 1 ? 1 : TN_STAGES;
     const size_t smem = stage * ns + 1024;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.need()) {
         MMS_CUDA(cudaFuncSetAttribute(tc_gemm_tn_kernel<TN_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         MMS_CUDA(cudaFuncSetAttribute(tc_gemm_tn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        attr_done = true;
+       
     }
     MMS_REQUIRE(smem <= 220 * 1024, "tc_gemm_tn: shared memory %zu too large", smem);
     MMS_PROF_BEGIN(st);
@@ -421,11 +421,11 @@ int launch_tc_gemm_tn_batch(const TnCall* calls, int n, cudaStream_t st) {
         if (stage * ns + 1024 > smem) smem = stage * ns + 1024;
     }
     for (int j = n; j < TN_MAX_BATCH; ++j) { maps.a[j] = maps.a[0]; maps.b[j] = maps.b[0]; }     // unused slots: valid bytes, never read
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.need()) {
         MMS_CUDA(cudaFuncSetAttribute(tc_gemm_tn_batch_kernel<TN_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         MMS_CUDA(cudaFuncSetAttribute(tc_gemm_tn_batch_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        attr_done = true;
+       
     }
     MMS_REQUIRE(smem <= 220 * 1024, "tc_gemm_tn_batch: shared memory %zu too large", smem);
     dim3 grid(max_chunks, n);

@@ -99,7 +99,12 @@ def parse_quest_csv(subject_id: str, wesad_root: Path):
     ends = [float(v) for v in rows['# END']]
     if not (len(tasks) == len(starts) == len(ends)):
         raise ValueError(f"为受试者 {subject_id} 解析出的任务、开始、结束时间长度不匹配!")
-    protocol = [[t, s, e] for t, s, e in zip(tasks, starts, ends)]
+    return base_halving_quirk(subject_id, zip(tasks, starts, ends))
+
+
+def base_halving_quirk(subject_id: str, protocol):
+    """reference preprocess.py:53-57: the Base segment of S2 and S6 starts at the midpoint of its span."""
+    protocol = [list(row) for row in protocol]
     if subject_id in ['S2', 'S6']:
         for row in protocol:
             if row[0] == 'Base':

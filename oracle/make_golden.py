@@ -42,6 +42,9 @@ MODEL_CASES = {
     "c3_t336_ternary": (3, 3, 3, 336, {}, 0),
     "c14_t3840": (14, 2, 2, 3840, {}, 0),
     "c8_h32_l1": (8, 2, 3, 320, {"gru_hidden_size": 32, "gru_num_layers": 1}, 2),
+    # north-star window length with M = B*L = 1920 rows >= 1024: the tcgen05 NT / TN GEMMs of the product path
+    # (model.cu TC_MIN_ROWS) are pinned to the reference itself, not only to the oracle
+    "c6_t3840_b8": (6, 2, 8, 3840, {}, 2),
 }
 
 
@@ -241,8 +244,12 @@ def make_fold_table():
 
 def main():
     GOLDEN.mkdir(parents=True, exist_ok=True)
+    only = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--model-case=")]
     for name, spec in MODEL_CASES.items():
-        make_model_case(name, *spec)
+        if not only or name in only:
+            make_model_case(name, *spec)
+    if only:
+        return
     make_resample_cases()
     make_preprocess_goldens()
     make_fold_table()

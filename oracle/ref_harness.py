@@ -1,5 +1,6 @@
-"""Import the UNMODIFIED reference modules from ``/root/reference`` (authoring
-container only -- the GPU box has no ``/root/reference``).
+"""Import the UNMODIFIED reference modules from ``/root/reference`` (authoring container) or,
+on the GPU box where that tree does not exist, from the byte-identical staging ``baseline/_ref``
+made by ``oracle/build_ref.py`` (git-ignored; it travels with the gpurun snapshot).
 
 TEST INFRASTRUCTURE ONLY.  Used by ``oracle/make_golden.py`` to produce the
 committed fixtures under ``tests/golden/`` and by ``bench.py --impl reference``
@@ -20,12 +21,35 @@ import sys
 import types
 from pathlib import Path
 
-REFERENCE_ROOT = Path(os.environ.get("MMS_REFERENCE_ROOT", "/root/reference"))
+_STAGED = Path(__file__).resolve().parents[1] / "baseline" / "_ref"     # oracle/build_ref.py (git-ignored, travels to the GPU box)
+
+
+def _find_root() -> Path:
+    env = os.environ.get("MMS_REFERENCE_ROOT")
+    if env:
+        return Path(env)
+    if Path("/root/reference/models.py").exists():
+        return Path("/root/reference")
+    return _STAGED
+
+
+REFERENCE_ROOT = _find_root()
 _STUBS = ("matplotlib", "matplotlib.pyplot", "seaborn", "neurokit2")
 
 
 def available() -> bool:
     return (REFERENCE_ROOT / "models.py").exists()
+
+
+def staged_ok() -> bool:
+    """True when the files under ``baseline/_ref`` still hash to their manifest (i.e. are the unmodified reference)."""
+    import hashlib
+    import json
+    man = _STAGED / "MANIFEST.json"
+    if not man.exists():
+        return False
+    want = json.loads(man.read_text())["sha256"]
+    return all((_STAGED / n).exists() and hashlib.sha256((_STAGED / n).read_bytes()).hexdigest() == h for n, h in want.items())
 
 
 def _install_stubs():

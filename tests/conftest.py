@@ -46,4 +46,4 @@ def golden_state(z, prefix):
     return out
 
 
-MODEL_CASES = ["c6_t640", "c3_t336_ternary", "c14_t3840", "c8_h32_l1"]
+MODEL_CASES = ["c6_t640", "c3_t336_ternary", "c14_t3840", "c8_h32_l1", "c6_t3840_b8"]

@@ -135,7 +135,7 @@ def test_cnn_gru_baseline_variant():
         assert np.abs(got - ref).max() <= 3e-4 * scale + 1e-9, k
 
 
-@pytest.mark.parametrize("case", ["c6_t640", "c8_h32_l1"])
+@pytest.mark.parametrize("case", ["c6_t640", "c8_h32_l1", "c6_t3840_b8"])
 def test_fused_train_step_follows_reference_adam_trajectory(case):
     """mms_cnngru_train_step (zero_grad+forward+CE+backward+Adam in one call, CUDA-graph replayed)
     against the reference's torch.optim.Adam trajectory (trainer.py:68,144-149)."""
@@ -159,6 +159,89 @@ def test_fused_train_step_follows_reference_adam_trajectory(case):
             continue
         np.testing.assert_allclose(mine[k].cpu().numpy(), ref, atol=5e-5, err_msg=k)
     assert int(mine["cnn_encoder.1.num_batches_tracked"].item()) == int(z["adam_steps"])
+
+
+def _random_state(C, seed):
+    """Reference-shaped parameters with non-trivial BN affine values (oracle/cpu_port.make_state: same keys / shapes as the
+    reference state_dict)."""
+    from oracle import cpu_port
+    p, bufs = cpu_port.make_state(C=C, seed=seed)
+    g = torch.Generator().manual_seed(seed + 100)
+    for k in ("cnn_encoder.1", "cnn_encoder.5"):
+        p[f"{k}.weight"] = p[f"{k}.weight"] + 0.1 * torch.randn(p[f"{k}.weight"].shape, generator=g)
+        p[f"{k}.bias"] = p[f"{k}.bias"] + 0.1 * torch.randn(p[f"{k}.bias"].shape, generator=g)
+    return p, bufs
+
+
+def _model_from(p, bufs, C):
+    from multimodalsignal_b200.models import CnnGruAttentionModel
+    m = CnnGruAttentionModel(C, 2, dropout=0.0)
+    sd = dict(p)
+    sd.update(bufs)
+    sd["cnn_encoder.1.num_batches_tracked"] = torch.zeros((), dtype=torch.int64)
+    sd["cnn_encoder.5.num_batches_tracked"] = torch.zeros((), dtype=torch.int64)
+    m.load_state_dict(sd, strict=True)
+    return m.cuda().train()
+
+
+# The configurations the numbers are QUOTED on (BASELINE.json configs[1], the as-shipped RAW_FS = 128 window of
+# preprocess.py:21 -> T = 7680 / L = 480 with the shipped 3 channels, and the all-channel ablation): the whole step
+# (forward, CE, backward) through the C ABI against the float64 oracle.  M = B*L = 15 360 / 30 720 rows: every GEMM of
+# the GRU runs on the tcgen05 kernels here, which the small golden cases never reach.
+@pytest.mark.parametrize("B,C,T", [(64, 6, 3840), (64, 3, 7680), (64, 14, 3840)])
+def test_whole_step_at_quoted_configs_vs_float64_oracle(B, C, T):
+    from multimodalsignal_b200.synth import synthetic_windows
+    p, bufs = _random_state(C, seed=11 + C)
+    x, y = synthetic_windows(B, C, T, seed=5 + C)
+    xt, yt = torch.from_numpy(x), torch.from_numpy(y)
+    params = {k: v.double() for k, v in p.items()}
+    ref_loss, ref_logits, ref_grads, aux = mo.loss_and_grads(params, xt.double(), yt, training=True, prune=True)
+    m = _model_from(p, bufs, C)
+    out = m(xt.cuda())
+    np.testing.assert_allclose(out.detach().cpu().numpy(), ref_logits.numpy(), atol=LOGIT_ATOL)
+    loss = torch.nn.functional.cross_entropy(out, yt.cuda())
+    assert abs(loss.item() - ref_loss.item()) < 1e-4
+    loss.backward()
+    for k, prm in m.named_parameters():
+        ref = ref_grads[k].numpy()
+        if ref.size == 0:
+            continue
+        got = prm.grad.detach().cpu().numpy()
+        scale = max(np.abs(ref).max(), 1e-6)
+        assert np.abs(got - ref).max() <= GRAD_RTOL * scale, (k, np.abs(got - ref).max(), scale)
+    # BatchNorm running statistics after one training forward (momentum 0.1, unbiased variance)
+    for prefix, key in (("cnn_encoder.1", "s1"), ("cnn_encoder.5", "s2")):
+        n = aux[f"{key}_conv"].shape[0] * aux[f"{key}_conv"].shape[2]
+        rm, rv = mo.running_stats_update(bufs[f"{prefix}.running_mean"].double(), bufs[f"{prefix}.running_var"].double(),
+                                         aux[f"{key}_mean"].detach(), aux[f"{key}_var"].detach(), n)
+        sd = m.state_dict()
+        np.testing.assert_allclose(sd[f"{prefix}.running_mean"].cpu().numpy(), rm.numpy(), atol=2e-6, rtol=1e-5)
+        np.testing.assert_allclose(sd[f"{prefix}.running_var"].cpu().numpy(), rv.numpy(), atol=2e-6, rtol=1e-5)
+
+
+def test_whole_step_c14_batch256_vs_library_cpu_step():
+    """cfg5's largest single-GPU batch in the parity suite (C = 14, B = 256, M = 61 440 rows).  The float64 oracle's
+    Python recurrence needs minutes at this size, so the checker is oracle/cpu_port.py (float32 ATen CPU kernels,
+    pinned to the reference fixtures by tests/test_oracle_model.py::test_cpu_port_*)."""
+    from oracle import cpu_port
+    from multimodalsignal_b200.synth import synthetic_windows
+    B, C, T = 256, 14, 3840
+    p, bufs = _random_state(C, seed=31)
+    x, y = synthetic_windows(B, C, T, seed=17)
+    xt, yt = torch.from_numpy(x), torch.from_numpy(y)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    ref_logits = cpu_port.forward(leaves, {k: v.clone() for k, v in bufs.items()}, xt, training=True, dropout=0.0)
+    ref_loss = torch.nn.functional.cross_entropy(ref_logits, yt)
+    ref_loss.backward()
+    m = _model_from(p, bufs, C)
+    out = m(xt.cuda())
+    np.testing.assert_allclose(out.detach().cpu().numpy(), ref_logits.detach().numpy(), atol=LOGIT_ATOL)
+    torch.nn.functional.cross_entropy(out, yt.cuda()).backward()
+    for k, prm in m.named_parameters():
+        ref = leaves[k].grad.numpy()
+        got = prm.grad.detach().cpu().numpy()
+        scale = max(np.abs(ref).max(), 1e-6)
+        assert np.abs(got - ref).max() <= GRAD_RTOL * scale, (k, np.abs(got - ref).max(), scale)
 
 
 def test_dropout_training_runs_and_is_stochastic():
