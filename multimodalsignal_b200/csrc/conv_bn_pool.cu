@@ -7,7 +7,7 @@
 //                   models.py:77 costs nothing;
 //   backward      : pool/ReLU/BN-reduction pass, BN apply pass, dgrad (optionally reduced against x
 //                   for the attention gate) and wgrad.
-#include "mms_common.cuh"
+#include "conv_common.cuh"
 #include <stdlib.h>
 
 namespace mms {
@@ -210,50 +210,6 @@ __global__ void __launch_bounds__(TL) conv1d_fwd_v2_kernel(const float* __restri
 }
 
 // ------------------------------------------------------------------------------------------
-struct BnAffine { float a, b, mean, inv; };
-
-__device__ __forceinline__ BnAffine bn_affine(int training, const double* stats, const float* gamma, const float* beta,
-                                              const float* rm, const float* rv, int c, int C, double n) {
-    double mean, var;
-    if (training) {
-        mean = stats[c] / n;
-        var = stats[C + c] / n - mean * mean;
-        if (var < 0.0) var = 0.0;
-    } else {
-        mean = (double)rm[c];
-        var = (double)rv[c];
-    }
-    const double inv = 1.0 / sqrt(var + (double)BN_EPS);
-    BnAffine r;
-    r.inv = (float)inv;
-    r.mean = (float)mean;
-    r.a = gamma[c] * r.inv;
-    r.b = beta[c] - r.mean * r.a;
-    return r;
-}
-
-// Block-uniform version: thread 0 does the float64 arithmetic once, everybody reads shared memory.
-__device__ __forceinline__ BnAffine bn_affine_block(int training, const double* stats, const float* gamma, const float* beta,
-                                                    const float* rm, const float* rv, int c, int C, double n) {
-    __shared__ BnAffine s_af;
-    if (threadIdx.x == 0) s_af = bn_affine(training, stats, gamma, beta, rm, rv, c, C, n);
-    __syncthreads();
-    return s_af;
-}
-
-__device__ __forceinline__ void bn_running_update(const double* stats, float* rm, float* rv, int64_t* nbt, int C,
-                                                  double n, int tid) {
-    if (tid < C) {
-        const double mean = stats[tid] / n;
-        double var = stats[C + tid] / n - mean * mean;
-        if (var < 0.0) var = 0.0;
-        const double unbiased = n > 1.0 ? var * (n / (n - 1.0)) : var;
-        rm[tid] = (1.f - BN_MOMENTUM) * rm[tid] + BN_MOMENTUM * (float)mean;
-        rv[tid] = (1.f - BN_MOMENTUM) * rv[tid] + BN_MOMENTUM * (float)unbiased;
-    }
-    if (tid == 0 && nbt) *nbt += 1;
-}
-
 __device__ __forceinline__ float pooled_value(const float* __restrict__ row, int j, int Lin, float a, float bsh) {
     float m = -INFINITY;
 #pragma unroll

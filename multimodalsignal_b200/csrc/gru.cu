@@ -749,7 +749,7 @@ template <int H>
 static int gru_fwd_dispatch(const GruFwdParams& prm, int ndirs, cudaStream_t st) {
     const int R = rows_per_cta(prm.B, ndirs);
     dim3 grid(cdiv(prm.B, R), ndirs);
-    if (R == 1 && option_get("GRU_FWD_V2", 0) == 1) {      // experiment (see gru_fwd_v2_kernel)
+    if (R == 1 && option_get("GRU_FWD_V2", 1) == 1) {      // experiment (see gru_fwd_v2_kernel)
         MMS_PROF_BEGIN(st);
         auto k2 = gru_fwd_v2_kernel<H>;
         MMS_LAUNCH(k2, grid, dim3(2 * H), 0, st, prm);
@@ -786,7 +786,7 @@ static int gru_bwd_dispatch(const GruBwdParams& prm, int ndirs, cudaStream_t st)
     // kernel (gru_bwd_kernel), which also serves R > 1 rows per CTA and operands that are not 16-byte aligned.
     // Measured on a B200 (profiles/r1_ab_gru_bwd_ring.json): 89.6 us (register ring) -> 69.3 us (depth 4) -> 66.7 us (depth 8)
     // per launch; depth 4 is the default because the whole GPU suite was run with it.
-    const int ring = option_get("GRU_BWD_RING", 4);
+    const int ring = option_get("GRU_BWD_RING", 8);
     if (ring > 0 && R == 1 && bwd_ring_ok(prm, ndirs)) {
         // MMS_GRU_BWD_EXCLUSIVE_KB (experiment, default 0): reserve that much dynamic shared memory per CTA so that no
         // other kernel's CTAs (the weight-gradient GEMMs of the side streams) can share an SM with a recurrence CTA

@@ -33,9 +33,17 @@ int launch_head_fwd2(const float*, int64_t, const float*, int64_t, int, const fl
 int launch_head_bwd(const float*, const float*, const float*, const float*, int, int, int, float, uint64_t, uint64_t,
                     const int64_t*, float*, float*, float*, float*, float*, cudaStream_t);
 int launch_cross_entropy(const float*, const int64_t*, int, int, float*, float*, double*, cudaStream_t, int div_batch);
+int launch_head_ce_fused(const float*, int64_t, const float*, int64_t, int, const float*, const float*, const float*, const float*,
+                         const int64_t*, int, int, int, float, uint64_t, uint64_t, const int64_t*, int, float*, float*, float*, float*,
+                         float*, float*, int32_t*, float*, double*, cudaStream_t);
 int launch_adam(float*, const float*, float*, float*, int64_t, const float*, float, float, float, float, int64_t*, int32_t*,
                 cudaStream_t);
 int launch_chan_dx(const float*, const float*, const float*, int, int, int, float*, cudaStream_t);
+bool conv_fused_supported(const float*, int, int, int);
+int launch_attn_conv1_fwd(const float*, const float*, const float*, const float*, int, int, int, int, float*, float*, float*, double*,
+                          cudaStream_t);
+int launch_bn_pool_conv2_fwd(const float*, const double*, const float*, const float*, float*, float*, int64_t*, int, int, const float*,
+                             int, int, int, float*, float*, double*, cudaStream_t);
 int launch_tc_gemm_nt(const float*, int64_t, const float*, int64_t, const float*, float*, int64_t, int, int, int, int, cudaStream_t);
 bool tc_gemm_supported(const float*, int64_t, const float*, int64_t, int, int, int);
 constexpr int TC_MIN_ROWS = 1024;      // below this a single tcgen05 CTA is pure latency: the SIMT kernels win
@@ -73,7 +81,7 @@ int launch_tc_gemm_tn_batch(const TnCall*, int, cudaStream_t);
 // Several TN products on one stream: one launch of the batched tensor-core kernel when MMS_TN_BATCH=1 (experiment) and every
 // problem qualifies for it, otherwise one launch each (the default).
 static int gemm_tn_many(const TnCall* c, int n, cudaStream_t st) {
-    bool batch = n > 1 && n <= 4 && use_tc() && option_get("TN_BATCH", 0) == 1;
+    bool batch = n > 1 && n <= 4 && use_tc() && option_get("TN_BATCH", 1) == 1;
     for (int j = 0; batch && j < n; ++j)
         batch = c[j].M >= 1024 && c[j].N1 > 0 &&
                 tc_gemm_tn_supported(c[j].A, c[j].lda, c[j].a_split, c[j].a_skip, c[j].N2 > 0 ? c[j].Bm : nullptr, c[j].ldb,
@@ -240,6 +248,7 @@ struct Workspace {
     float *gi[MAX_LAYERS], *hs[MAX_LAYERS], *outd[MAX_LAYERS], *stash[MAX_LAYERS];   // bottom layers
     float *gi_tf, *gi_tr, *hs_tf, *h_tr, *stash_tf, *stash_tr, *last, *hid;
     float *wT_top, *wT[MAX_LAYERS], *dx_extra;
+    int32_t* head_counter; float* rowloss;
     float *dhid, *dlogits, *D_tf, *D_tr, *D[MAX_LAYERS], *dxa, *dxb, *dy2, *dp1, *dy1, *ca_scratch;
     int64_t total;
 };
@@ -253,10 +262,11 @@ static void carve(const Dims& m, char* base, Workspace* w) {
     };
     const int64_t B = m.B, L = m.L, H = m.H, M = B * L;
     const int64_t f = sizeof(float);
-    w->fwd_zero = take((int64_t)sizeof(double) * 2 * (CONV1_CO + m.O));
+    w->fwd_zero_bytes = sizeof(double) * 2 * (CONV1_CO + m.O) + 16;        // BN batch sums + the fused head's CTA counter
+    w->fwd_zero = take((int64_t)w->fwd_zero_bytes);
     w->stats1 = (double*)w->fwd_zero;
     w->stats2 = w->stats1 ? w->stats1 + 2 * CONV1_CO : nullptr;
-    w->fwd_zero_bytes = sizeof(double) * 2 * (CONV1_CO + m.O);
+    w->head_counter = w->stats1 ? (int32_t*)(w->stats2 + 2 * m.O) : nullptr;
     const int64_t bz = (int64_t)sizeof(double) * 2 * (CONV1_CO + m.O) + align_up(B * m.C, 4) * f;
     w->bwd_zero = take(bz);
     w->red1 = (double*)w->bwd_zero;
@@ -283,6 +293,7 @@ static void carve(const Dims& m, char* base, Workspace* w) {
     w->stash_tr = m.need_grad ? (float*)take(B * 4 * H * f) : nullptr;
     w->last = (float*)take(B * 2 * H * f);
     w->hid = (float*)take(B * HEAD_HID * f);
+    w->rowloss = (float*)take(B * f);
     if (m.need_grad) {
         w->dhid = (float*)take(B * HEAD_HID * f);
         w->dlogits = (float*)take(B * 8 * f);
@@ -305,8 +316,17 @@ static void carve(const Dims& m, char* base, Workspace* w) {
 
 // phases: bit 0 = gate + conv1 (+ BN1 batch sums), bit 1 = BN1/pool1 + conv2 (+ BN2 sums), bit 2 = the rest.
 // A data-parallel caller all-reduces the float64 BN sums between the phases (SyncBN); 7 = everything.
+// Training-step fusion (mms_cnngru_train_step): with `fl` the head forward, CrossEntropyLoss and the head's input-side
+// backward are ONE launch at the end of the forward pass (head_ce_fused_kernel); model_backward is then told that dhid /
+// dlogits exist (head_done) and only computes the head's weight gradients, on a side stream.
+struct FusedLoss {
+    const int64_t* labels;
+    float* loss_out;
+    double* loss_sum_accum;
+};
+
 static int model_forward(const mms_cnngru_desc* d, const float* x, const float* P, float* bn, int64_t* nbt, void* ws,
-                         float* logits, cudaStream_t st, int phases = 7) {
+                         float* logits, cudaStream_t st, int phases = 7, const FusedLoss* fl = nullptr) {
     Dims m;
     int rc = make_dims(d, &m);
     if (rc) return rc;
@@ -321,7 +341,22 @@ static int model_forward(const mms_cnngru_desc* d, const float* x, const float* 
     float *rm1 = bn, *rv1 = bn + CONV1_CO, *rm2 = bn + 2 * CONV1_CO, *rv2 = bn + 2 * CONV1_CO + m.O;
 
     const float* gate = m.attention ? w.gate : nullptr;
-    if (phases & 1) {
+    // fused encoder kernels (conv_fused.cu): attention + conv1 in one cluster launch, BN1/ReLU/pool + conv2 in one launch
+    const bool fused = option_get("CONV_FUSED", 1) == 1 && conv_fused_supported(x, m.C, m.T, m.O);
+    if (fused) {
+        if (phases & 1) {
+            MMS_CUDA(cudaMemsetAsync(w.fwd_zero, 0, w.fwd_zero_bytes, st));
+            rc = launch_attn_conv1_fwd(x, P + po.conv1_w, P + po.ca_w1, P + po.ca_w2, m.attention ? 1 : 0, B, m.C, m.T, w.mean, w.gate,
+                                       w.y1, m.training ? w.stats1 : nullptr, st);
+            if (rc) return rc;
+        }
+        if (phases & 2) {
+            rc = launch_bn_pool_conv2_fwd(w.y1, w.stats1, P + po.bn1_g, P + po.bn1_b, rm1, rv1, nbt, m.Bg, m.training, P + po.conv2_w, B,
+                                          m.O, m.L1c, w.p1, w.y2, m.training ? w.stats2 : nullptr, st);
+            if (rc) return rc;
+        }
+    }
+    if ((phases & 1) && !fused) {
         MMS_CUDA(cudaMemsetAsync(w.fwd_zero, 0, w.fwd_zero_bytes, st));
         if (m.attention) {
             rc = launch_chan_gate(x, P + po.ca_w1, P + po.ca_w2, B, m.C, m.T, w.mean, w.gate, st);
@@ -330,7 +365,7 @@ static int model_forward(const mms_cnngru_desc* d, const float* x, const float* 
         rc = launch_conv_fwd(1, x, P + po.conv1_w, gate, B, m.C, CONV1_CO, m.T, w.y1, m.training ? w.stats1 : nullptr, st);
         if (rc) return rc;
     }
-    if (phases & 2) {
+    if ((phases & 2) && !fused) {
         rc = launch_bn_relu_pool_fwd(w.y1, w.stats1, P + po.bn1_g, P + po.bn1_b, rm1, rv1, nbt, B, CONV1_CO, m.L1c, m.training, 0, w.p1, st, m.Bg);
         if (rc) return rc;
         rc = launch_conv_fwd(2, w.p1, P + po.conv2_w, nullptr, B, CONV2_CI, m.O, m.P1, w.y2, m.training ? w.stats2 : nullptr, st);
@@ -393,6 +428,11 @@ static int model_forward(const mms_cnngru_desc* d, const float* x, const float* 
         rc = launch_gru_fwd(dirs, 2, B, H, 0.f, d->rng_seed, d->rng_offset, d->rng_offset_dev, st);
         if (rc) return rc;
     }
+    if (fl && m.need_grad)
+        return launch_head_ce_fused(w.hs_tf + (int64_t)(L - 1) * H, (int64_t)L * H, w.h_tr, H, H, P + po.fc0_w, P + po.fc0_b,
+                                    P + po.fc3_w, P + po.fc3_b, fl->labels, B, 2 * H, m.nc, m.drop_head ? m.p : 0.f, d->rng_seed,
+                                    d->rng_offset, d->rng_offset_dev, m.Bg, w.last, w.hid, logits, w.dlogits, w.dhid, w.rowloss,
+                                    w.head_counter, fl->loss_out, fl->loss_sum_accum, st);
     return launch_head_fwd2(w.hs_tf + (int64_t)(L - 1) * H, (int64_t)L * H, w.h_tr, H, H, P + po.fc0_w, P + po.fc0_b, P + po.fc3_w,
                             P + po.fc3_b, B, 2 * H, m.nc, m.drop_head ? m.p : 0.f, d->rng_seed, d->rng_offset, d->rng_offset_dev,
                             w.last, w.hid, logits, st);
@@ -402,7 +442,7 @@ static int model_forward(const mms_cnngru_desc* d, const float* x, const float* 
 // conv2 gradients, pool/ReLU backward of stage 1 (+ reductions), bit 2 = the rest.  A data-parallel caller
 // all-reduces the float64 reductions between the phases; 7 = everything.
 static int model_backward(const mms_cnngru_desc* d, const float* x, const float* P, const float* bn, void* ws,
-                          const float* dlogits, float* G, float* dx, cudaStream_t st, int phases = 7) {
+                          const float* dlogits, float* G, float* dx, cudaStream_t st, int phases = 7, bool head_done = false) {
     Dims m;
     int rc = make_dims(d, &m);
     if (rc) return rc;
@@ -438,8 +478,11 @@ static int model_backward(const mms_cnngru_desc* d, const float* x, const float*
             }
         }
     }
+    // head: dhid feeds the top recurrence; with the fused forward it already exists and only the weight gradients remain,
+    // which nothing on the chain needs -> side stream
     rc = launch_head_bwd(w.last, w.hid, dlogits, P + po.fc3_w, B, 2 * H, m.nc, m.drop_head ? p : 0.f, d->rng_seed, d->rng_offset,
-                         d->rng_offset_dev, w.dhid, G + po.fc0_w, G + po.fc0_b, G + po.fc3_w, G + po.fc3_b, st);
+                         d->rng_offset_dev, head_done ? nullptr : w.dhid, G + po.fc0_w, G + po.fc0_b, G + po.fc3_w, G + po.fc3_b,
+                         head_done ? fk.fork(2) : st);
     if (rc) return rc;
 
     const int top = m.layers - 1;
@@ -463,7 +506,7 @@ static int model_backward(const mms_cnngru_desc* d, const float* x, const float*
         // h_prev = 0 for the single reverse step: dW_hh(reverse) = 0, only the bias gradient remains
         return gemm_tn(w.D_tr, 4 * H, 2 * H, H, nullptr, 0, 0, 1, nullptr, 0, G + po.b_hh[top] + 3 * H, B, 3 * H, 0, sw);
     };
-    const bool defer_top_wgrad = top >= 1 && option_get("WGRAD_DEFER", 0) == 1;
+    const bool defer_top_wgrad = top >= 1 && option_get("WGRAD_DEFER", 1) == 1;
     {
         mms_gru_dir_bwd dirs[2];
         memset(dirs, 0, sizeof(dirs));
@@ -719,11 +762,15 @@ extern "C" int mms_cnngru_train_step(const mms_cnngru_desc* d, const float* x, c
     Workspace w;
     carve(m, (char*)workspace, &w);
     MMS_CUDA(cudaMemsetAsync(grads, 0, po.total * sizeof(float), st));                      // trainer.py:144
-    rc = model_forward(d, x, params, bn_buffers, num_batches_tracked, workspace, logits, st);  // trainer.py:146
+    const bool fuse_head = option_get("HEAD_FUSED", 1) == 1;
+    const FusedLoss fl = {labels, loss_out, loss_sum_accum};
+    rc = model_forward(d, x, params, bn_buffers, num_batches_tracked, workspace, logits, st, 7, fuse_head ? &fl : nullptr);  // trainer.py:146-147
     if (rc) return rc;
-    rc = launch_cross_entropy(logits, labels, m.B, m.nc, loss_out, w.dlogits, loss_sum_accum, st, m.Bg);  // trainer.py:147
-    if (rc) return rc;
-    rc = model_backward(d, x, params, bn_buffers, workspace, w.dlogits, grads, nullptr, st);        // trainer.py:148
+    if (!fuse_head) {
+        rc = launch_cross_entropy(logits, labels, m.B, m.nc, loss_out, w.dlogits, loss_sum_accum, st, m.Bg);  // trainer.py:147
+        if (rc) return rc;
+    }
+    rc = model_backward(d, x, params, bn_buffers, workspace, w.dlogits, grads, nullptr, st, 7, fuse_head);        // trainer.py:148
     if (rc) return rc;
     return launch_adam(params, grads, exp_avg, exp_avg_sq, po.total, lr_dev, beta1, beta2, eps, weight_decay, step_dev,
                        scratch_dev, st);                                                          // trainer.py:149

@@ -254,7 +254,7 @@ int launch_tc_gemm_nt(const float* A, int64_t lda, const float* W, int64_t ldw, 
     // ever touches stage 0, so it can ask for one stage of shared memory and let two CTAs share an SM (81 KB, 2 x 256
     // TMEM columns), overlapping one CTA's epilogue with the other's TMA / split / MMA
     const int nkb = (K + TC_BK - 1) / TC_BK;
-    const int stages = (option_get("NT_TRIM_STAGES", 0) == 1 && nkb < TC_STAGES) ? nkb : TC_STAGES;
+    const int stages = (option_get("NT_TRIM_STAGES", 1) == 1 && nkb < TC_STAGES) ? nkb : TC_STAGES;
     const size_t smem = stage * stages + 1024;
     static PerDeviceOnce attr_once;
     if (attr_once.need()) {
@@ -368,7 +368,7 @@ int launch_tc_gemm_tn(const float* A, int64_t lda, int a_split, int a_skip, cons
     if (chunk < 2 * TN_KB) chunk = 2 * TN_KB;
     p.chunk = chunk;
     const size_t stage = (size_t)2 * p.nblkA * TN_BLK + (size_t)2 * (p.nblkB + 1) * TN_BLK;
-    const int ns = option_get("TN_STAGES", TN_STAGES) == 1 ? 1 : TN_STAGES;
+    const int ns = option_get("TN_STAGES", 1) == 1 ? 1 : TN_STAGES;
     const size_t smem = stage * ns + 1024;
     static PerDeviceOnce attr_once;
     if (attr_once.need()) {
@@ -394,7 +394,7 @@ int launch_tc_gemm_tn_batch(const TnCall* calls, int n, cudaStream_t st) {
     memset(&bp, 0, sizeof(bp));
     int budget = option_get("TN_BATCH_CTAS", 148);
     if (budget < n) budget = n;
-    const int ns = option_get("TN_STAGES", TN_STAGES) == 1 ? 1 : TN_STAGES;
+    const int ns = option_get("TN_STAGES", 1) == 1 ? 1 : TN_STAGES;
     size_t smem = 0;
     int max_chunks = 0;
     for (int j = 0; j < n; ++j) {
