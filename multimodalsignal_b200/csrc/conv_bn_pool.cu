@@ -14,18 +14,6 @@ namespace mms {
 
 constexpr int CONV_CI_PAD = 16;
 
-// cp.async copies with zero fill (src-size 0 when !ok): the source address must still be valid, callers clamp it
-__device__ __forceinline__ void cp_async4_zfill(float* smem_dst, const float* gsrc, bool ok) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(ok ? 4 : 0) : "memory");
-}
-__device__ __forceinline__ void cp_async16_zfill(float* smem_dst, const float* gsrc, bool ok) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(ok ? 16 : 0) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-}
-
 // ------------------------------------------------------------------------------------------
 template <int CO, int KW, int S, int P, int TL>
 __global__ void __launch_bounds__(TL) conv1d_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
@@ -395,21 +383,6 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
     if (blockIdx.x == 0 && b == 0 && threadIdx.x == 0) {
         dgamma[c] += grad_scale * (float)red[C + c];     // grad_scale = 1/world under data parallelism: every
         dbeta[c] += grad_scale * (float)red[c];          // rank holds the GLOBAL sums, the all-reduce adds them up
-    }
-}
-
-// per-channel constants of the folded BatchNorm backward: s_bn[o] = {a, mean, inv, m1, m2}
-template <int CO>
-__device__ __forceinline__ void bn_bwd_constants(const BnBwd& bn, int Lout, float (*s_bn)[5]) {
-    if (threadIdx.x < CO) {
-        const int o = threadIdx.x;
-        const double n = (double)bn.Bstat * (double)Lout;
-        const BnAffine af = bn_affine(bn.training, bn.stats, bn.gamma, bn.beta, bn.rm, bn.rv, o, CO, n);
-        s_bn[o][0] = af.a;
-        s_bn[o][1] = af.mean;
-        s_bn[o][2] = af.inv;
-        s_bn[o][3] = bn.training ? (float)(bn.red[o] / n) : 0.f;
-        s_bn[o][4] = bn.training ? (float)(bn.red[CO + o] / n) : 0.f;
     }
 }
 
