@@ -40,6 +40,18 @@ int launch_adam(float*, const float*, float*, float*, int64_t, const float*, flo
                 cudaStream_t);
 int launch_chan_dx(const float*, const float*, const float*, int, int, int, float*, cudaStream_t);
 bool conv_fused_supported(const float*, int, int, int);
+bool conv_bwd_supported(const float*, int, int, int);
+int64_t conv2_bwd_scratch_floats(int, int);
+int64_t conv1_bwd_scratch_floats(int, int);
+int conv2_bwd_parts(int, int);
+int launch_pool_bwd_tm(const float*, const double*, const float*, const float*, const float*, const float*, const float*, int, int, int,
+                       int, float*, double*, cudaStream_t, int);
+int launch_pool_bwd_ncl(const float*, const double*, const float*, const float*, const float*, const float*, const float*, int, int, int,
+                        int, float*, double*, cudaStream_t, int);
+int launch_conv2_bwd(const float*, const float*, const float*, int, int, float*, float*, cudaStream_t, const BnBwd*);
+int launch_wgrad_reduce(const float*, int, int, float*, cudaStream_t);
+int launch_conv1_bwd(const float*, const float*, const float*, const float*, const float*, const float*, const float*, int, int, int,
+                     float*, int*, float*, float*, float*, cudaStream_t, const BnBwd*);
 bool pool_bwd_tile_supported(int, int);
 int launch_pool_relu_bwd_tile(const float*, const double*, const float*, const float*, const float*, const float*, const float*, int, int,
                               int, int, int, float*, double*, cudaStream_t, int);
@@ -248,7 +260,7 @@ struct Workspace {
     // zeroed at the start of every forward
     double* stats1; double* stats2;
     // zeroed at the start of every backward
-    double* red1; double* red2; float* dgate;
+    double* red1; double* red2; float* dgate; int* row_counter;
     size_t fwd_zero_bytes, bwd_zero_bytes;
     char* fwd_zero; char* bwd_zero;
     float *mean, *gate, *y1, *p1, *y2, *seq;
@@ -256,7 +268,7 @@ struct Workspace {
     float *gi_tf, *gi_tr, *hs_tf, *h_tr, *stash_tf, *stash_tr, *last, *hid;
     float *wT_top, *wT[MAX_LAYERS], *dx_extra;
     int32_t* head_counter; float* rowloss;
-    float *dhid, *dlogits, *D_tf, *D_tr, *D[MAX_LAYERS], *dxa, *dxb, *dy2, *dp1, *dy1, *ca_scratch;
+    float *dhid, *dlogits, *D_tf, *D_tr, *D[MAX_LAYERS], *dxa, *dxb, *dy2, *dp1, *dy1, *ca_scratch, *c2_part, *c1_part;
     int64_t total;
 };
 
@@ -274,11 +286,12 @@ static void carve(const Dims& m, char* base, Workspace* w) {
     w->stats1 = (double*)w->fwd_zero;
     w->stats2 = w->stats1 ? w->stats1 + 2 * CONV1_CO : nullptr;
     w->head_counter = w->stats1 ? (int32_t*)(w->stats2 + 2 * m.O) : nullptr;
-    const int64_t bz = (int64_t)sizeof(double) * 2 * (CONV1_CO + m.O) + align_up(B * m.C, 4) * f;
+    const int64_t bz = (int64_t)sizeof(double) * 2 * (CONV1_CO + m.O) + align_up(B * m.C, 4) * f + align_up(B, 4) * (int64_t)sizeof(int);
     w->bwd_zero = take(bz);
     w->red1 = (double*)w->bwd_zero;
     w->red2 = w->red1 ? w->red1 + 2 * CONV1_CO : nullptr;
     w->dgate = w->red1 ? (float*)(w->red2 + 2 * m.O) : nullptr;
+    w->row_counter = w->red1 ? (int*)(w->dgate + align_up(B * m.C, 4)) : nullptr;     // conv1_bwd: chunks of a row that have finished
     w->bwd_zero_bytes = bz;
     w->mean = (float*)take(B * m.C * f);
     w->gate = (float*)take(B * m.C * f);
@@ -317,6 +330,8 @@ static void carve(const Dims& m, char* base, Workspace* w) {
         w->dp1 = (float*)take(B * CONV1_CO * m.P1 * f);
         w->dy1 = (float*)take(B * CONV1_CO * m.L1c * f);
         w->ca_scratch = (float*)take(4 * B * m.C * f);
+        w->c2_part = (float*)take(conv2_bwd_scratch_floats(m.B, m.P1) * f);      // partial conv2 weight gradients, one per CTA
+        w->c1_part = (float*)take(conv1_bwd_scratch_floats(m.B, m.C) * f);       // partial conv1 G per (row, chunk)
     }
     w->total = cur;
 }
@@ -468,6 +483,8 @@ static int model_backward(const mms_cnngru_desc* d, const float* x, const float*
     // tile / cluster kernels of conv_fused_bwd.cu: T % 8 == 0, BatchNorm backward folded, no input gradient requested
     const bool fused_bwd = bn_fold() && !dx && option_get("CONV_BWD_FUSED", 0) == 1 && conv1_wgrad_dgate_supported(x, m.C, m.T) &&
                            pool_bwd_tile_supported(m.O, 1);
+    // conv_bwd.cu (the default when the shapes allow it): T % 32 == 0, C_out == 32, BatchNorm backward folded, no input gradient
+    const bool bwd2 = !fused_bwd && bn_fold() && !dx && option_get("CONV_BWD", 1) == 1 && conv_bwd_supported(x, m.C, m.T, m.O);
     Forker fk(st);
     if (phases & 1) {
     MMS_CUDA(cudaMemsetAsync(w.bwd_zero, 0, w.bwd_zero_bytes, st));
@@ -627,7 +644,10 @@ static int model_backward(const mms_cnngru_desc* d, const float* x, const float*
         float* t = dxcur; dxcur = dxnext; dxnext = t;
     }
     // dxcur = d(seq) [B, L, O] time-major
-    if (fused_bwd)
+    if (bwd2)
+        rc = launch_pool_bwd_tm(w.y2, w.stats2, P + po.bn2_g, P + po.bn2_b, rm2, rv2, dxcur, B, m.O, m.L2c, m.training, w.dy2, w.red2, st,
+                                m.Bg);
+    else if (fused_bwd)
         rc = launch_pool_relu_bwd_tile(w.y2, w.stats2, P + po.bn2_g, P + po.bn2_b, rm2, rv2, dxcur, B, m.O, m.L2c, m.training, 1, w.dy2,
                                        w.red2, st, m.Bg);
     else
@@ -648,6 +668,16 @@ static int model_backward(const mms_cnngru_desc* d, const float* x, const float*
         const BnBwd bn2w = {fold ? w.y2 : nullptr, w.stats2, P + po.bn2_g, P + po.bn2_b, rm2, rv2, w.red2, G + po.bn2_g, G + po.bn2_b, m.Bg, m.training, gscale};
         BnBwd bn2d = bn2w;
         bn2d.dgamma = nullptr; bn2d.dbeta = nullptr;
+        if (bwd2) {
+            // both gradients of conv2 from one staged tile; the per-CTA partial weight gradients are summed on a side stream
+            rc = launch_conv2_bwd(w.dy2, P + po.conv2_w, w.p1, B, m.P1, w.dp1, w.c2_part, st, &bn2w);
+            if (rc) return rc;
+            rc = launch_wgrad_reduce(w.c2_part, conv2_bwd_parts(B, m.P1), m.O * CONV2_CI * CONV2_K, G + po.conv2_w, fk.fork(0));
+            if (rc) return rc;
+            rc = launch_pool_bwd_ncl(w.y1, w.stats1, P + po.bn1_g, P + po.bn1_b, rm1, rv1, w.dp1, B, CONV1_CO, m.L1c, m.training, w.dy1,
+                                     w.red1, st, m.Bg);
+            if (rc) return rc;
+        } else {
         rc = launch_conv_wgrad(2, w.p1, w.dy2, nullptr, B, CONV2_CI, m.O, m.P1, G + po.conv2_w, fk.fork(0), &bn2w);
         if (rc) return rc;
         if (fused_bwd) {
@@ -662,8 +692,17 @@ static int model_backward(const mms_cnngru_desc* d, const float* x, const float*
                                          w.dy1, G + po.bn1_g, G + po.bn1_b, w.red1, st, 1, m.Bg, gscale);
         }
         if (rc) return rc;
+        }
     }
     if (!(phases & 4)) return fk.join();
+    if (bwd2) {
+        // conv1 weight gradient, attention-gate gradient and the ChannelAttention parameter gradients in one launch
+        const BnBwd bn1f = {w.y1, w.stats1, P + po.bn1_g, P + po.bn1_b, rm1, rv1, w.red1, G + po.bn1_g, G + po.bn1_b, m.Bg, m.training, gscale};
+        rc = launch_conv1_bwd(x, w.dy1, P + po.conv1_w, m.attention ? w.gate : nullptr, w.mean, P + po.ca_w1, P + po.ca_w2, B, m.C, m.T,
+                              w.c1_part, w.row_counter, G + po.conv1_w, G + po.ca_w1, G + po.ca_w2, st, &bn1f);
+        if (rc) return rc;
+        return fk.join();
+    }
     if (fused_bwd) {
         // conv1 weight gradient, attention-gate gradient and the ChannelAttention parameter gradients in one cluster launch
         const BnBwd bn1f = {w.y1, w.stats1, P + po.bn1_g, P + po.bn1_b, rm1, rv1, w.red1, G + po.bn1_g, G + po.bn1_b, m.Bg, m.training, gscale};
