@@ -91,9 +91,8 @@ __device__ __forceinline__ void pool_bwd_8(const float (&yv)[16], const float (&
 
 // ---- stage 2: time-major upstream gradient --------------------------------------------------------------------------
 // grid = (ceil(Lin / (8 * NS * PB_ITERS)), B), block = 256 = C channels x NS position slots; a thread handles PB_ITERS groups
-// of 8 positions.  Lin % 8 == 0.
-constexpr int PB_ITERS = 4;
-template <int C>
+// of 8 positions (2 or 4: MMS_POOL_TM_ITERS).  Lin % 8 == 0.
+template <int C, int PB_ITERS>
 __global__ void __launch_bounds__(256) pool_bwd_tm_kernel(const float* __restrict__ y, const double* __restrict__ stats,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           const float* __restrict__ rm, const float* __restrict__ rv,
@@ -209,7 +208,7 @@ __global__ void __launch_bounds__(256) pool_bwd_ncl_kernel(const float* __restri
 constexpr int C2B_TM = 128, C2B_RW = 136, C2B_PW = 140, C2B_DS = 132, C2B_CO = 32, C2B_TS = C2B_CO + 4, C2B_NW = C2B_CO * 80;
 constexpr int C2B_SMEM_FLOATS = 2 * C2B_CO * C2B_RW + 2 * 16 * C2B_PW + C2B_NW + C2B_CO * C2B_DS + 130 * C2B_TS;
 
-__global__ void __launch_bounds__(128) conv2_bwd_kernel(const float* __restrict__ dyn, const float* __restrict__ w,
+__global__ void __launch_bounds__(128) conv2_bwd_kernel(const float* __restrict__ dyn, const float* __restrict__ wdg,
                                                         const float* __restrict__ p1, float* __restrict__ dp1,
                                                         float* __restrict__ dw_part, int Lin, int Lout, const BnBwd bn) {
     MMS_PDL_TRIGGER();
@@ -227,13 +226,8 @@ __global__ void __launch_bounds__(128) conv2_bwd_kernel(const float* __restrict_
     const int b = blockIdx.y, m0 = blockIdx.x * C2B_TM;
     const bool fold = bn.y != nullptr;
     if (tid == 0) {
-        mbar_init(&bar, (uint32_t)(CO2 * (fold ? 2 : 1) + 32));
+        mbar_init(&bar, (uint32_t)(CO2 * (fold ? 2 : 1) + 32 + 1));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    // weights (parameters: may be read ahead of the grid dependency)
-    for (int idx = tid; idx < C2B_NW; idx += 128) {
-        const int o = idx / 80, r = idx - o * 80, ci = r / 5, k = r - ci * 5;
-        wd[(o * 5 + k) * 16 + ci] = __ldg(w + idx);
     }
     MMS_PDL_WAIT();
     __syncthreads();
@@ -245,35 +239,43 @@ __global__ void __launch_bounds__(128) conv2_bwd_kernel(const float* __restrict_
         }
         const int h = lane >> 4, ci = lane & 15;
         row_load(p1s + (h * 16 + ci) * C2B_PW, p1 + ((size_t)b * 16 + ci) * Lin, 2 * m0 + 128 * h - 4, C2B_PW, Lin, &bar);
-    }
-    if (fold) {
-        if (warp == 1) {          // constants of the folded BatchNorm backward (float64 arithmetic) beside the copies
-            const int o = lane;
-            const double n = (double)bn.Bstat * (double)Lout;
-            const BnAffine af = bn_affine(bn.training, bn.stats, bn.gamma, bn.beta, bn.rm, bn.rv, o, CO2, n);
-            s_bn[o][0] = af.a;
-            s_bn[o][1] = af.mean;
-            s_bn[o][2] = af.inv;
-            s_bn[o][3] = bn.training ? (float)(bn.red[o] / n) : 0.f;
-            s_bn[o][4] = bn.training ? (float)(bn.red[CO2 + o] / n) : 0.f;
-            if (blockIdx.x == 0 && blockIdx.y == 0) {      // dgamma / dbeta once per launch
-                if (bn.dgamma) bn.dgamma[o] += bn.grad_scale * (float)bn.red[CO2 + o];
-                if (bn.dbeta) bn.dbeta[o] += bn.grad_scale * (float)bn.red[o];
-            }
+        if (lane == 0) {              // the weights, already in the [o][k][ci] order the input gradient reads (conv2_w_relayout_kernel)
+            mbar_expect_tx(&bar, (uint32_t)C2B_NW * 4u);
+            bulk_g2s(wd, wdg, (uint32_t)C2B_NW * 4u, &bar);
+        }
+    } else if (warp == 1 && fold) {   // constants of the folded BatchNorm backward (float64 arithmetic) beside the copies
+        const int o = lane;
+        const double n = (double)bn.Bstat * (double)Lout;
+        const BnAffine af = bn_affine(bn.training, bn.stats, bn.gamma, bn.beta, bn.rm, bn.rv, o, CO2, n);
+        s_bn[o][0] = af.a;
+        s_bn[o][1] = af.mean;
+        s_bn[o][2] = af.inv;
+        s_bn[o][3] = bn.training ? (float)(bn.red[o] / n) : 0.f;
+        s_bn[o][4] = bn.training ? (float)(bn.red[CO2 + o] / n) : 0.f;
+        if (blockIdx.x == 0 && blockIdx.y == 0) {      // dgamma / dbeta once per launch
+            if (bn.dgamma) bn.dgamma[o] += bn.grad_scale * (float)bn.red[CO2 + o];
+            if (bn.dbeta) bn.dbeta[o] += bn.grad_scale * (float)bn.red[o];
         }
     }
     mbar_wait(&bar, 0);
     __syncthreads();
-    // dyn -> dy2 (BnBwd), into both layouts; zero outside the tensor
-    for (int idx = tid; idx < CO2 * 130; idx += 128) {
-        const int o = idx / 130, mm = idx - o * 130, m = m0 - 1 + mm;
-        float v = 0.f;
-        if (m >= 0 && m < Lout) {
-            v = raw_d[o * C2B_RW + mm + 3];
-            if (fold) v = s_bn[o][0] * (v - s_bn[o][3] - (raw_y[o * C2B_RW + mm + 3] - s_bn[o][1]) * s_bn[o][2] * s_bn[o][4]);
+    {   // dyn -> dy2 (BnBwd) into both layouts, zero outside the tensor: 4 threads per output channel, positions q, q + 4, ...
+        const int o = tid >> 2, q = tid & 3;
+        float ca = 1.f, cm1 = 0.f, cmean = 0.f, cim2 = 0.f;
+        if (fold) { ca = s_bn[o][0]; cm1 = s_bn[o][3]; cmean = s_bn[o][1]; cim2 = s_bn[o][2] * s_bn[o][4]; }
+        const float* rd = raw_d + o * C2B_RW + 3;
+        const float* ry = raw_y + o * C2B_RW + 3;
+#pragma unroll 4
+        for (int mm = q; mm < 130; mm += 4) {
+            const int m = m0 - 1 + mm;
+            float v = 0.f;
+            if (m >= 0 && m < Lout) {
+                v = rd[mm];
+                if (fold) v = ca * (v - cm1 - (ry[mm] - cmean) * cim2);
+            }
+            dys[o * C2B_DS + mm] = v;
+            dyT[mm * C2B_TS + o] = v;
         }
-        dys[o * C2B_DS + mm] = v;
-        dyT[mm * C2B_TS + o] = v;
     }
     __syncthreads();
 
@@ -409,6 +411,15 @@ __global__ void __launch_bounds__(128) conv2_bwd_kernel(const float* __restrict_
     }
 }
 
+// wd[(o*5 + k)*16 + ci] = w[o][ci][k]: the order conv2_bwd_kernel's input-gradient warps read (one bulk copy per CTA instead of a
+// strided gather by every CTA); runs on a side stream at the start of the backward pass.
+__global__ void __launch_bounds__(256) conv2_w_relayout_kernel(const float* __restrict__ w, int n, float* __restrict__ wd) {
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= n) return;
+    const int o = idx / 80, r = idx - o * 80, ci = r / 5, k = r - ci * 5;
+    wd[(o * 5 + k) * 16 + ci] = __ldg(w + idx);
+}
+
 // dw[idx] += sum_p part[p][idx].  grid = (ceil(n / 256), S), block = 256: block (x, s) sums the partials s, s + S, ...
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ part, int P, int n, float* __restrict__ dw) {
     const int idx = blockIdx.x * 256 + threadIdx.x;
@@ -474,11 +485,21 @@ __global__ void __launch_bounds__(256) conv1_bwd_kernel(const float* __restrict_
     }
     mbar_wait(&bar, 0);
     __syncthreads();
-    if (fold) {         // dyn -> dy1 in place (rows beyond the tensor stay zero)
+    if (fold) {         // dyn -> dy1 in place (rows beyond the tensor stay zero): a warp per output channel, 128-bit accesses
         const int nl = Lout - l0 < CH ? Lout - l0 : CH;
-        for (int idx = tid; idx < 16 * CH; idx += NT) {
-            const int o = idx / CH, ll = idx - o * CH;
-            if (ll < nl) dys[idx] = s_bn[o][0] * (dys[idx] - s_bn[o][3] - (ys[idx] - s_bn[o][1]) * s_bn[o][2] * s_bn[o][4]);
+        for (int o = warp; o < 16; o += NW) {
+            const float ca = s_bn[o][0], cm1 = s_bn[o][3], cmean = s_bn[o][1], cim2 = s_bn[o][2] * s_bn[o][4];
+            float4* dr = reinterpret_cast<float4*>(dys + o * CH);
+            const float4* yr = reinterpret_cast<const float4*>(ys + o * CH);
+            for (int q = lane; 4 * q < nl; q += 32) {
+                float4 d = dr[q];
+                const float4 yv = yr[q];
+                d.x = ca * (d.x - cm1 - (yv.x - cmean) * cim2);
+                d.y = ca * (d.y - cm1 - (yv.y - cmean) * cim2);
+                d.z = ca * (d.z - cm1 - (yv.z - cmean) * cim2);
+                d.w = ca * (d.w - cm1 - (yv.w - cmean) * cim2);
+                dr[q] = d;
+            }
         }
         __syncthreads();
     }
@@ -630,11 +651,14 @@ int launch_pool_bwd_tm(const float* y, const double* stats, const float* gamma, 
     const int Lout = pool_out_len(Lin);
     if (Bstat <= 0) Bstat = B;
     const int NS = 256 / C;
-    dim3 grid(cdiv(Lin, 8 * NS * PB_ITERS), B);
+    const int iters = option_get("POOL_TM_ITERS", 2) >= 4 ? 4 : 2;
+    dim3 grid(cdiv(Lin, 8 * NS * iters), B);
     MMS_PROF_BEGIN(st);
-    if (C == 16) MMS_LAUNCH(pool_bwd_tm_kernel<16>, grid, dim3(256), 0, st, y, stats, gamma, beta, rm, rv, dout, Bstat, Lin, Lout, training, dy, red);
-    else if (C == 32) MMS_LAUNCH(pool_bwd_tm_kernel<32>, grid, dim3(256), 0, st, y, stats, gamma, beta, rm, rv, dout, Bstat, Lin, Lout, training, dy, red);
-    else MMS_LAUNCH(pool_bwd_tm_kernel<64>, grid, dim3(256), 0, st, y, stats, gamma, beta, rm, rv, dout, Bstat, Lin, Lout, training, dy, red);
+#define MMS_POOL_TM(CC, IT) MMS_LAUNCH((pool_bwd_tm_kernel<CC, IT>), grid, dim3(256), 0, st, y, stats, gamma, beta, rm, rv, dout, Bstat, Lin, Lout, training, dy, red)
+    if (C == 16) { if (iters == 4) MMS_POOL_TM(16, 4); else MMS_POOL_TM(16, 2); }
+    else if (C == 32) { if (iters == 4) MMS_POOL_TM(32, 4); else MMS_POOL_TM(32, 2); }
+    else { if (iters == 4) MMS_POOL_TM(64, 4); else MMS_POOL_TM(64, 2); }
+#undef MMS_POOL_TM
     MMS_LAUNCH_CHECK("pool_bwd_tm_kernel");
     return MMS_OK;
 }
@@ -655,14 +679,22 @@ int launch_pool_bwd_ncl(const float* y, const double* stats, const float* gamma,
 static const BnBwd kNoBn = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 1.f};
 
 // Both gradients of conv2 (C_out = 32).  dp1 [B,16,P1] is written; dw (+=) receives the weight gradient through `scratch`
-// (conv2_bwd_scratch_floats) and wgrad_reduce_kernel on stream `st_reduce` (the caller has made it wait for `st`... see model.cu).
+// (conv2_bwd_scratch_floats) and launch_wgrad_reduce.  w: the weights in conv2_w_relayout_kernel's order.
+int launch_conv2_w_relayout(const float* w, float* wd, cudaStream_t st) {
+    MMS_PROF_BEGIN(st);
+    conv2_w_relayout_kernel<<<cdiv(C2B_NW, 256), 256, 0, st>>>(w, C2B_NW, wd);
+    MMS_LAUNCH_CHECK("conv2_w_relayout_kernel");
+    return MMS_OK;
+}
+int64_t conv2_w_relayout_floats() { return C2B_NW; }
+
 int launch_conv2_bwd(const float* dyn, const float* w, const float* p1, int B, int P1, float* dp1, float* scratch, cudaStream_t st,
                      const BnBwd* bnp) {
     const BnBwd& bn = bnp ? *bnp : kNoBn;
     const int Lout = conv_out_len(P1, CONV2_K, CONV2_S, CONV2_P);
     MMS_REQUIRE(P1 % 4 == 0 && Lout % 4 == 0, "conv2_bwd: lengths %d / %d must be multiples of 4", P1, Lout);
     MMS_REQUIRE(((reinterpret_cast<uintptr_t>(dyn) | reinterpret_cast<uintptr_t>(p1) | reinterpret_cast<uintptr_t>(dp1) |
-                  reinterpret_cast<uintptr_t>(scratch) | reinterpret_cast<uintptr_t>(bn.y)) & 15) == 0, "conv2_bwd: operands must be 16-byte aligned");
+                  reinterpret_cast<uintptr_t>(scratch) | reinterpret_cast<uintptr_t>(bn.y) | reinterpret_cast<uintptr_t>(w)) & 15) == 0, "conv2_bwd: operands must be 16-byte aligned");
     const size_t smem = (size_t)C2B_SMEM_FLOATS * sizeof(float);
     static PerDeviceOnce attr_once;
     if (attr_once.need()) MMS_CUDA(cudaFuncSetAttribute(conv2_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

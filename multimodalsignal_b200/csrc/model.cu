@@ -50,6 +50,8 @@ int launch_pool_bwd_ncl(const float*, const double*, const float*, const float*,
                         int, float*, double*, cudaStream_t, int);
 int launch_conv2_bwd(const float*, const float*, const float*, int, int, float*, float*, cudaStream_t, const BnBwd*);
 int launch_wgrad_reduce(const float*, int, int, float*, cudaStream_t);
+int launch_conv2_w_relayout(const float*, float*, cudaStream_t);
+int64_t conv2_w_relayout_floats();
 int launch_conv1_bwd(const float*, const float*, const float*, const float*, const float*, const float*, const float*, int, int, int,
                      float*, int*, float*, float*, float*, cudaStream_t, const BnBwd*);
 bool pool_bwd_tile_supported(int, int);
@@ -120,7 +122,7 @@ static int gemm_tn_many(const TnCall* c, int n, cudaStream_t st) {
 // capture (the side streams become branches of the captured graph).  MMS_DISABLE_STREAMS=1 serialises.
 struct SideStreams {
     cudaStream_t s[3] = {nullptr, nullptr, nullptr};
-    cudaEvent_t fork_ev[8] = {}, join_ev[3] = {};
+    cudaEvent_t fork_ev[8] = {}, join_ev[3] = {}, aux_ev = nullptr;
     bool ok = false;
 };
 static int g_streams_disabled = -1;
@@ -138,6 +140,7 @@ static SideStreams* side_streams() {
             if (cudaEventCreateWithFlags(&ss.fork_ev[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
         for (int i = 0; i < 3; ++i)
             if (cudaEventCreateWithFlags(&ss.join_ev[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&ss.aux_ev, cudaEventDisableTiming) != cudaSuccess) return nullptr;
         ss.ok = true;
     }
     return &ss;
@@ -156,6 +159,21 @@ struct Forker {
         ++n_forks;
         used[which] = true;
         return ss->s[which];
+    }
+    // one early result of a side stream that `main` needs before that stream's final join: mark() after the producer has been
+    // enqueued on side stream `which`, wait_mark() in front of the consumer on `main`
+    bool marked = false;
+    int mark(int which) {
+        if (!ss || !used[which]) return MMS_OK;       // the producer ran on `main` itself
+        MMS_CUDA(cudaEventRecord(ss->aux_ev, ss->s[which]));
+        marked = true;
+        return MMS_OK;
+    }
+    int wait_mark() {
+        if (!marked) return MMS_OK;
+        MMS_CUDA(cudaStreamWaitEvent(main, ss->aux_ev, 0));
+        marked = false;
+        return MMS_OK;
     }
     int join_one(int i) {
         if (!ss || !used[i]) return MMS_OK;
@@ -268,7 +286,7 @@ struct Workspace {
     float *gi_tf, *gi_tr, *hs_tf, *h_tr, *stash_tf, *stash_tr, *last, *hid;
     float *wT_top, *wT[MAX_LAYERS], *dx_extra;
     int32_t* head_counter; float* rowloss;
-    float *dhid, *dlogits, *D_tf, *D_tr, *D[MAX_LAYERS], *dxa, *dxb, *dy2, *dp1, *dy1, *ca_scratch, *c2_part, *c1_part;
+    float *dhid, *dlogits, *D_tf, *D_tr, *D[MAX_LAYERS], *dxa, *dxb, *dy2, *dp1, *dy1, *ca_scratch, *c2_part, *c1_part, *c2_wd;
     int64_t total;
 };
 
@@ -332,6 +350,7 @@ static void carve(const Dims& m, char* base, Workspace* w) {
         w->ca_scratch = (float*)take(4 * B * m.C * f);
         w->c2_part = (float*)take(conv2_bwd_scratch_floats(m.B, m.P1) * f);      // partial conv2 weight gradients, one per CTA
         w->c1_part = (float*)take(conv1_bwd_scratch_floats(m.B, m.C) * f);       // partial conv1 G per (row, chunk)
+        w->c2_wd = (float*)take(conv2_w_relayout_floats() * f);                  // conv2 weights as [o][k][ci]
     }
     w->total = cur;
 }
@@ -489,6 +508,12 @@ static int model_backward(const mms_cnngru_desc* d, const float* x, const float*
     if (phases & 1) {
     MMS_CUDA(cudaMemsetAsync(w.bwd_zero, 0, w.bwd_zero_bytes, st));
     const bool tc_bwd = use_tc() && M >= TC_MIN_ROWS;
+    if (bwd2 && phases == 7) {       // conv2 weights in the order conv2_bwd_kernel stages them: side stream, long before they are needed
+        rc = launch_conv2_w_relayout(P + po.conv2_w, w.c2_wd, fk.fork(1));
+        if (rc) return rc;
+        rc = fk.mark(1);
+        if (rc) return rc;
+    }
     if (tc_bwd) {
         // W_ih^T (zero-padded over the dq columns for the bottom layers) for the tensor-core dx products:
         // side stream, hidden behind the head backward and the top-layer recurrence
@@ -670,7 +695,13 @@ static int model_backward(const mms_cnngru_desc* d, const float* x, const float*
         bn2d.dgamma = nullptr; bn2d.dbeta = nullptr;
         if (bwd2) {
             // both gradients of conv2 from one staged tile; the per-CTA partial weight gradients are summed on a side stream
-            rc = launch_conv2_bwd(w.dy2, P + po.conv2_w, w.p1, B, m.P1, w.dp1, w.c2_part, st, &bn2w);
+            if (phases != 7) {       // phase-split call (data parallel): the re-arranged weights are made here
+                rc = launch_conv2_w_relayout(P + po.conv2_w, w.c2_wd, st);
+                if (rc) return rc;
+            }
+            rc = fk.wait_mark();
+            if (rc) return rc;
+            rc = launch_conv2_bwd(w.dy2, w.c2_wd, w.p1, B, m.P1, w.dp1, w.c2_part, st, &bn2w);
             if (rc) return rc;
             rc = launch_wgrad_reduce(w.c2_part, conv2_bwd_parts(B, m.P1), m.O * CONV2_CI * CONV2_K, G + po.conv2_w, fk.fork(0));
             if (rc) return rc;

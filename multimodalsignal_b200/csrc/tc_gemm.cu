@@ -368,7 +368,7 @@ int launch_tc_gemm_tn(const float* A, int64_t lda, int a_split, int a_skip, cons
     if (chunk < 2 * TN_KB) chunk = 2 * TN_KB;
     p.chunk = chunk;
     const size_t stage = (size_t)2 * p.nblkA * TN_BLK + (size_t)2 * (p.nblkB + 1) * TN_BLK;
-    const int ns = option_get("TN_STAGES", 1) == 1 ? 1 : TN_STAGES;
+    const int ns = option_get("TN_STAGES", 2) == 1 ? 1 : TN_STAGES;
     const size_t smem = stage * ns + 1024;
     static PerDeviceOnce attr_once;
     if (attr_once.need()) {
@@ -394,8 +394,9 @@ int launch_tc_gemm_tn_batch(const TnCall* calls, int n, cudaStream_t st) {
     memset(&bp, 0, sizeof(bp));
     int budget = option_get("TN_BATCH_CTAS", 148);
     if (budget < n) budget = n;
-    const int ns = option_get("TN_STAGES", 1) == 1 ? 1 : TN_STAGES;
-    size_t smem = 0;
+    int ns = option_get("TN_STAGES", 2);           // 1, 2 or 3 pipeline stages; reduced until the largest problem's stages fit
+    ns = ns < 1 ? 1 : (ns > 3 ? 3 : ns);
+    size_t stage_max = 0;
     int max_chunks = 0;
     for (int j = 0; j < n; ++j) {
         TnCall c = calls[j];
@@ -418,20 +419,23 @@ int launch_tc_gemm_tn_batch(const TnCall* calls, int n, cudaStream_t st) {
         bp.nchunks[j] = cdiv(c.M, chunk);
         if (bp.nchunks[j] > max_chunks) max_chunks = bp.nchunks[j];
         const size_t stage = (size_t)2 * p.nblkA * TN_BLK + (size_t)2 * (p.nblkB + 1) * TN_BLK;
-        if (stage * ns + 1024 > smem) smem = stage * ns + 1024;
+        if (stage > stage_max) stage_max = stage;
     }
+    while (ns > 1 && stage_max * ns + 1024 > 220 * 1024) --ns;
+    const size_t smem = stage_max * ns + 1024;
     for (int j = n; j < TN_MAX_BATCH; ++j) { maps.a[j] = maps.a[0]; maps.b[j] = maps.b[0]; }     // unused slots: valid bytes, never read
     static PerDeviceOnce attr_once;
     if (attr_once.need()) {
-        MMS_CUDA(cudaFuncSetAttribute(tc_gemm_tn_batch_kernel<TN_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        MMS_CUDA(cudaFuncSetAttribute(tc_gemm_tn_batch_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        MMS_CUDA(cudaFuncSetAttribute(tc_gemm_tn_batch_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         MMS_CUDA(cudaFuncSetAttribute(tc_gemm_tn_batch_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-       
     }
     MMS_REQUIRE(smem <= 220 * 1024, "tc_gemm_tn_batch: shared memory %zu too large", smem);
     dim3 grid(max_chunks, n);
     MMS_PROF_BEGIN(st);
     if (ns == 1) tc_gemm_tn_batch_kernel<1><<<grid, TC_THREADS, smem, st>>>(maps, bp);
-    else tc_gemm_tn_batch_kernel<TN_STAGES><<<grid, TC_THREADS, smem, st>>>(maps, bp);
+    else if (ns == 2) tc_gemm_tn_batch_kernel<2><<<grid, TC_THREADS, smem, st>>>(maps, bp);
+    else tc_gemm_tn_batch_kernel<3><<<grid, TC_THREADS, smem, st>>>(maps, bp);
     MMS_LAUNCH_CHECK("tc_gemm_tn_kernel");
     return MMS_OK;
 }
