@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-library-baseline", action="store_true", help="skip the stock PyTorch/cuDNN leg (reference model on the same GPU)")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-subrecords", action="store_true",
+                    help="train_step: skip the loso / preprocess / dp sub-records (BASELINE.json configs[2..4]) of the default line")
     ap.add_argument("--workload", default="train_step", choices=["train_step", "loso", "preprocess", "dp"],
                     help="train_step = headline metric (default); loso = 15-fold LOSO wall-clock; preprocess = resample+window")
     ap.add_argument("--epochs", type=int, default=100, help="loso: EPOCHS (reference main.py:62 uses 100, patience 20)")
@@ -251,7 +253,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_reference_run(args, args.steps, args.warmup, budget_s=120.0)
+    r = cpu_reference_run(args, args.steps, args.warmup, budget_s=60.0)
     line = {"impl": "reference", "metric": "train windows/sec (fwd+bwd+Adam) CnnGruAttention", "value": r["value"],
             "unit": "windows/s", "n_gpus": args.gpus, "steps": r["timed_steps"], "requested_steps": args.steps,
             "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
@@ -259,6 +261,11 @@ def run_reference(args):
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if not args.no_subrecords:
+        try:
+            line["loso"] = reference_loso_leg(args)
+        except Exception as exc:                          # never take the reference line down
+            line["loso"] = {"unavailable": f"{type(exc).__name__}: {exc}"}
     print(json.dumps(line), flush=True)
 
 
@@ -358,6 +365,39 @@ def run_ours(args):
         clocks = sampler.stop()
     barrier()
 
+    # ---- sub-records: BASELINE.json configs[2..4] in the same driver-run line (every rank takes part in the sharded legs) ----
+    sub = {}
+    if not args.no_subrecords and args.workload == "train_step":
+        import copy
+        largs = copy.copy(args)
+        largs.subjects, largs.minutes, largs.epochs, largs.concurrent_folds = 15, 100.0, 100, 4
+        try:
+            sub["loso"], streams, mine = loso_measure(largs, world, rank, local, init_pg=False)
+        except Exception as exc:                          # a sub-record must never take the headline down
+            sub["loso"], streams, mine = {"unavailable": f"{type(exc).__name__}: {exc}"}, None, None
+        if world > 1:
+            dp = {}
+            for exch in ("peer", "nccl"):
+                try:
+                    dp[exch] = dp_measure(args, world, rank, dev, 256, 14, 3840, 200, exch)
+                except Exception as exc:
+                    dp[exch] = {"unavailable": f"{type(exc).__name__}: {exc}"}
+            sub["dp"] = dict(dp.get("peer", {}), nccl={k: dp["nccl"].get(k) for k in ("value", "ms_per_step", "unavailable") if k in dp["nccl"]})
+        elif rank == 0:
+            if streams is not None and not args.no_cpu_baseline:
+                try:
+                    sub["loso"]["fold_vs_reference"] = fold_parity_measure(largs, streams)
+                    sub["loso"]["accuracy_delta_vs_reference"] = sub["loso"]["fold_vs_reference"].get("accuracy_delta_vs_reference")
+                except Exception as exc:
+                    sub["loso"]["fold_vs_reference"] = {"unavailable": f"{type(exc).__name__}: {exc}"}
+            try:
+                largs.steps = 3
+                sub["preprocess"] = preprocess_measure(largs, mine)
+            except Exception as exc:
+                sub["preprocess"] = {"unavailable": f"{type(exc).__name__}: {exc}"}
+            sub["dp"] = {"unavailable": "intra-fold data parallelism needs N > 1 (measured in the N = 2, 4, 8 lines)"}
+        streams = mine = None
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -391,8 +431,9 @@ def run_ours(args):
     #   tc_gemm_tn : dW_ih / dW_hh of the top forward direction and of both layer-0 directions
     gru_flops = 2.0 * 3 * H * H * B * (2 * L + L + 1)
     flops_by_kernel = {
-        "gru_fwd_kernel": gru_flops, "gru_bwd_kernel": gru_flops,
+        "gru_fwd_v2_kernel": gru_flops, "gru_bwd_ring_kernel": gru_flops, "gru_fwd_kernel": gru_flops, "gru_bwd_kernel": gru_flops,
         "tc_gemm_nt_kernel": 2.0 * M * (6 * H * O + 3 * H * 2 * H + 2 * H * 3 * H + O * 6 * H),
+        "tc_gemm_tn_batch_kernel": 2.0 * M * 3 * H * ((2 * H + H) + 2 * (O + H)),
         "tc_gemm_tn_kernel": 2.0 * M * 3 * H * ((2 * H + H) + 2 * (O + H)),
     }
     # weight-gradient kernels and weight transposes run on side streams, hidden behind the recurrences
@@ -401,16 +442,22 @@ def run_ours(args):
     #   backward: read stash (4H) + h_{t-1} (H) + upstream gradient (H) + write D (dr, dz, dn, dq: 4H) = 10H floats
     # over 2L direction-steps of layer 0 plus L + 1 of the top layer
     dir_steps = B * (2 * L + L + 1)
-    bytes_by_kernel = {"gru_fwd_kernel": 4.0 * 8 * H * dir_steps, "gru_bwd_kernel": 4.0 * 10 * H * dir_steps}
-    overlapped = {"tc_gemm_tn_kernel", "gemm_tn_acc_kernel", "conv1d_wgrad_kernel", "transpose_pad_kernel"}
+    bytes_by_kernel = {"gru_fwd_v2_kernel": 4.0 * 8 * H * dir_steps, "gru_bwd_ring_kernel": 4.0 * 10 * H * dir_steps,
+                       "gru_fwd_kernel": 4.0 * 8 * H * dir_steps, "gru_bwd_kernel": 4.0 * 10 * H * dir_steps}
+    overlapped = {"tc_gemm_tn_kernel", "tc_gemm_tn_batch_kernel", "gemm_tn_acc_kernel", "conv1d_wgrad_kernel", "transpose_pad_kernel",
+                  "wgrad_reduce_kernel", "conv2_w_relayout_kernel", "head_bwd_kernel", "gemm_nn_kernel", "dropout_rows_kernel", "gemm_nt_bias_kernel"}
     critical = {k: v for k, v in kern.items() if k not in overlapped}
     top = max(critical, key=lambda k: critical[k]["ms_per_step"])
-    traffic = None
-    summ = ROOT / "profiles" / "r1_ncu_full_summary.json"
-    if summ.exists():
-        recs = [r for k, v in json.loads(summ.read_text()).items() if k.startswith(top.replace("_kernel", "")) for r in v]
-        if recs:
-            traffic = sum(r["dram_read_bytes"] + r["dram_write_bytes"] for r in recs) / len(recs)
+    # DRAM traffic of the SAME kernel (name as launched, template arguments ignored) from the ncu --set full capture of this
+    # round's default step: profiles/r2_ncu_full_summary.json (tools/ncu_summary.py over gpurun_out/r2c6_default + r2c8_convbwd)
+    traffic, traffic_src = None, None
+    for summ in (ROOT / "profiles" / "r2_ncu_full_summary.json",):
+        if summ.exists():
+            recs = [r for k, v in json.loads(summ.read_text()).items() if k.split("<")[0] == top for r in v]
+            if recs:
+                traffic = sum(r["dram_read_bytes"] + r["dram_write_bytes"] for r in recs) / len(recs)
+                traffic_src = (f"profiles/{summ.name}: ncu --set full of {top}, dram__bytes_read.sum + dram__bytes_write.sum, mean of its "
+                               f"{len(recs)} launches in one step (cold L2: ncu flushes the caches between replays)")
     launches = kern[top]["launches_per_step"]
     flop_launch = flops_by_kernel[top] / launches if top in flops_by_kernel else None
     byte_launch = bytes_by_kernel[top] / launches if top in bytes_by_kernel else None
@@ -421,10 +468,7 @@ def run_ours(args):
     roof = {"kernel": top, "avg_us": kern[top]["avg_us"], "launches_per_step": launches,
             "share_of_critical_path_kernel_time": kern[top]["ms_per_step"] / sum(v["ms_per_step"] for v in critical.values()),
             "selection": "largest per-step time among kernels on the step's critical path (side-stream kernels excluded)",
-            "traffic": traffic,
-            "traffic_source": ("profiles/r1_ncu_full_summary.json (ncu --set full, dram bytes read + written per launch"
-                               + ("; captured with the register-ring backward kernel of round 1 -- the cp.async-ring kernel that is "
-                                  "now the default reads and writes the same rows" if top == "gru_bwd_kernel" else "") + ")") if traffic else None}
+            "traffic": traffic, "traffic_source": traffic_src, "ns_per_time_step": 1e3 * kern[top]["avg_us"] / L if top.startswith("gru_") else None}
     if hbm_bound:
         roof.update({"bound": "hbm", "unit": "GB/s", "peak": pk["hbm_gbs"], "peak_source": f"{pk['source']} HBM copy bandwidth",
                      "achieved": byte_launch / t_launch / 1e9, "algorithmic_bytes_per_launch": byte_launch,
@@ -465,6 +509,7 @@ def run_ours(args):
         "kernels": kernel_table,
         "eager_kernel_ms_per_step": kern_total, "final_loss": loss_after,
     }
+    line.update(sub)
     if world == 1 and not args.no_library_baseline:
         try:
             line["library_gpu_baseline"] = library_gpu_run(args, dev)
@@ -492,14 +537,20 @@ def model_seq_len(T):
 NORTH_STAR_CHANNELS = ["chest_ECG", "chest_EDA", "chest_EMG", "chest_Resp", "wrist_BVP", "wrist_EDA"]   # README.md:85
 
 
-def _synthetic_subjects(args):
+def _synthetic_subjects(args, rank=0, world=1):
+    """The synthetic recordings of the subjects rank ``rank`` owns (subject i belongs to rank i % world), generated on a
+    small thread pool (numpy releases the GIL): (all subject ids, {sid: SyntheticSubject}, protocol)."""
+    from concurrent.futures import ThreadPoolExecutor
     from multimodalsignal_b200 import synth
     sids = synth.ALL_SUBJECTS[:args.subjects]
     protocol = synth.FULL_PROTOCOL if args.minutes >= 80 else synth.SHORT_PROTOCOL
-    return sids, [synth.make_subject(sid, synth.ALL_SUBJECTS.index(sid), minutes=args.minutes, protocol=protocol) for sid in sids]
+    mine = [sid for i, sid in enumerate(sids) if i % world == rank]
+    with ThreadPoolExecutor(max(1, min(8, (os.cpu_count() or 1) // max(1, world)))) as ex:
+        subs = list(ex.map(lambda sid: synth.make_subject(sid, synth.ALL_SUBJECTS.index(sid), minutes=args.minutes, protocol=protocol), mine))
+    return sids, dict(zip(mine, subs)), protocol
 
 
-def run_preprocess(args):
+def preprocess_measure(args, subjects=None):
     """BASELINE.json configs[3]: resample (700/64/32/4 Hz -> 64 Hz) + windowing of synthetic recordings, chest 8 +
     wrist 6 channels.  value = subjects/s with the raw recordings resident in HBM; e2e includes the H2D copy of
     the raw streams and the D2H copy of the float64 window array the reference saves (preprocess.py:217-222)."""
@@ -508,7 +559,10 @@ def run_preprocess(args):
     from multimodalsignal_b200 import _ext, preprocess as pp
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
     lib = _ext.lib()
-    sids, subs = _synthetic_subjects(args)
+    if subjects is None:
+        sids, subjects, _ = _synthetic_subjects(args)
+    sids = list(subjects.keys())
+    subs = [subjects[sid] for sid in sids]
     datas = [s.as_pickle_dict() for s in subs]
     protos = [pp.base_halving_quirk(s.sid, s.protocol) for s in subs]
 
@@ -597,26 +651,34 @@ def run_preprocess(args):
             "cpu_baseline": {"value": 1.0 / cpu_s, "unit": "subjects/s", "cores": os.cpu_count(), "kind": "port",
                              "sample": "oracle/preprocess_oracle.py on 1 synthetic subject, chest channels only (8 FFT round trips "
                                        "of N = 4.2 M + window stacking); the reference's scipy path measured the same arithmetic"}}
-    print(json.dumps(line), flush=True)
+    return line
 
 
-def run_loso(args):
+def run_preprocess(args):
+    print(json.dumps(preprocess_measure(args)), flush=True)
+
+
+def _gru_bytes_per_window(T, H=64):
+    """Algorithmic HBM bytes of the four recurrence launches per trained window: forward 8 H floats and
+    backward 10 H floats per (time step, direction), over 2 L direction-steps of layer 0 + L + 1 of the top layer."""
+    L = model_seq_len(T)
+    return 4.0 * (8 + 10) * H * (3 * L + 1)
+
+
+def loso_measure(args, world, rank, local, init_pg=True):
     """BASELINE.json configs[2]: full 15-subject LOSO-CV (main.py:91-156 semantics: 100 epochs, patience 20, batch 64,
     Adam 1e-3 / 1e-4) with the folds sharded over the ranks.  value = wall-clock seconds (max over ranks) from
-    raw synthetic recordings on the host to cv_summary.txt."""
+    raw synthetic recordings on the host to cv_summary.txt.  Returns (record on rank 0 / None elsewhere, streams, the synthetic subjects this rank generated)."""
     import tempfile
     import numpy as np
     import torch
     import torch.distributed as dist
     from multimodalsignal_b200 import _ext, main as mm, preprocess as pp
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
-    if world > 1:
+    if world > 1 and init_pg and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _ext.lib()
-    sids, subs = _synthetic_subjects(args)
+    sids, mine, protocol = _synthetic_subjects(args, rank, world)
     mm.ALL_SUBJECTS = list(sids)
     mm.CHANNELS_TO_USE = list(NORTH_STAR_CHANNELS)
     mm.EPOCHS = args.epochs
@@ -641,8 +703,8 @@ def run_loso(args):
     t0 = time.perf_counter()
     # every rank keeps all subjects resident (replicated, ~0.65 GB); the resampling itself is sharded over the ranks
     # and the streams are exchanged GPU-to-GPU (NCCL broadcast over NVLink)
-    streams = pp.preprocess_subjects_sharded([(s.sid, s.as_pickle_dict, pp.base_halving_quirk(s.sid, s.protocol)) for s in subs],
-                                             64, include_wrist=True)
+    items = [(sid, (mine[sid].as_pickle_dict if sid in mine else (lambda: None)), pp.base_halving_quirk(sid, protocol)) for sid in sids]
+    streams = pp.preprocess_subjects_sharded(items, 64, include_wrist=True)
     torch.cuda.synchronize()
     t_pre = time.perf_counter() - t0
     out_dir = Path(tempfile.mkdtemp(prefix="mms_loso_"))
@@ -667,59 +729,286 @@ def run_loso(args):
     if world > 1:
         dist.all_reduce(total, op=dist.ReduceOp.MAX)
     launches = int(lib.mms_launch_count() - l0)
+    if rank != 0:
+        return None, streams, mine
+    windows = sum(r["windows_trained"] for r in results)
+    secs = float(total.item())
+    pk = peaks()
+    wps = windows / max(1e-9, secs - t_pre)
+    gbs = wps * _gru_bytes_per_window(3840) / 1e9
+    line = {"metric": "15-fold LOSO wall-clock (preprocess + train + evaluate)", "value": secs, "unit": "s",
+            "n_gpus": world, "steps": len(results), "warmup": 0, "ms_per_step": 1e3 * secs / max(1, len(results)),
+            "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "cnn_gru_attention full LOSO-CV, folds sharded over ranks (BASELINE.json configs[2])",
+                       "subjects": len(sids), "channels": NORTH_STAR_CHANNELS, "epochs_max": args.epochs, "patience": mm.PATIENCE,
+                       "batch": mm.BATCH_SIZE, "minutes": args.minutes, "concurrent_folds_per_gpu": args.concurrent_folds},
+            "preprocess_s": t_pre, "windows_trained": windows, "train_windows_per_s": wps,
+            "accuracy_mean": float(np.mean([r["accuracy"] for r in results])),
+            "f1_mean": float(np.mean([r["f1_score"] for r in results])),
+            "roofline": {"kernel": "gru_fwd_v2_kernel + gru_bwd_ring_kernel (the recurrences of every co-resident fold)", "bound": "hbm",
+                         "unit": "GB/s", "achieved": gbs, "peak": pk["hbm_gbs"], "frac": gbs / pk["hbm_gbs"], "traffic": None,
+                         "algorithmic_bytes_per_window": _gru_bytes_per_window(3840),
+                         "note": "whole-job figure: windows trained per second of the train + evaluate phase x the recurrences' "
+                                 "algorithmic bytes per window, all GPUs together"},
+            "folds": [{k: r[k] for k in ("subject", "accuracy", "f1_score", "windows_trained", "seconds", "start_s", "end_s") if k in r} for r in results],
+            "host_seconds_by_phase": {k: round(sum(r.get("timing", {}).get(k, 0.0) for r in results), 3)
+                                      for k in ("train_enqueue", "train_wait", "evaluate", "bookkeeping")},
+            "gpu_launches_rank0_uncaptured": launches,
+            "summary_file": str(out_dir / "cv_summary.txt")}
+    line["roofline"]["peak"] = pk["hbm_gbs"] * world
+    line["roofline"]["frac"] = gbs / (pk["hbm_gbs"] * world)
+    return line, streams, mine
+
+
+def run_loso(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    line, streams, _ = loso_measure(args, world, rank, local)
     if rank == 0:
-        windows = sum(r["windows_trained"] for r in results)
-        line = {"metric": "15-fold LOSO wall-clock (preprocess + train + evaluate)", "value": float(total.item()), "unit": "s",
-                "n_gpus": world, "steps": len(results), "warmup": 0, "ms_per_step": 1e3 * float(total.item()) / max(1, len(results)),
-                "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "cnn_gru_attention full LOSO-CV, folds sharded over ranks (BASELINE.json configs[2])",
-                           "subjects": len(sids), "channels": NORTH_STAR_CHANNELS, "epochs_max": args.epochs, "patience": mm.PATIENCE,
-                           "batch": mm.BATCH_SIZE, "minutes": args.minutes, "concurrent_folds_per_gpu": args.concurrent_folds},
-                "preprocess_s": t_pre, "windows_trained": windows, "train_windows_per_s": windows / max(1e-9, float(total.item()) - t_pre),
-                "accuracy_mean": float(np.mean([r["accuracy"] for r in results])),
-                "f1_mean": float(np.mean([r["f1_score"] for r in results])),
-                "folds": [{k: r[k] for k in ("subject", "accuracy", "f1_score", "windows_trained", "seconds", "start_s", "end_s") if k in r} for r in results],
-                "host_seconds_by_phase": {k: round(sum(r.get("timing", {}).get(k, 0.0) for r in results), 3)
-                                          for k in ("train_enqueue", "train_wait", "evaluate", "bookkeeping")},
-                "gpu_launches_rank0_uncaptured": launches,
-                "summary_file": str(out_dir / "cv_summary.txt")}
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                line["fold_vs_reference"] = fold_parity_measure(args, streams)
+            except Exception as exc:
+                line["fold_vs_reference"] = {"unavailable": f"{type(exc).__name__}: {exc}"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_dp(args):
-    """BASELINE.json configs[4]: intra-fold data parallelism -- ONE fold, the global batch (--batch) split over
-    the ranks, SyncBN + one flat-gradient NCCL all-reduce per step (strong scaling)."""
+# ---- matched accuracy: one LOSO fold through the UNMODIFIED reference Trainer (CPU) and through ours (B200) --------------
+PARITY_FOLD = "S2"            # fold "test S2"
+PARITY_EPOCHS = 2
+
+
+def _write_reference_npy(streams, out_dir, channels):
+    """The .npy files reference dataset.py:25-36 loads, for the channels in use only: {sid}_X.npy float64 [N, W, C],
+    {sid}_y.npy, _channel_names.txt -- from the device-resident streams of our preprocessing (byte-identical to what the
+    reference's run_preprocessing writes: tests/test_gpu_preprocess.py)."""
+    import numpy as np
+    out_dir.mkdir(parents=True, exist_ok=True)
+    (out_dir / "_channel_names.txt").write_text("".join(f"{c}\n" for c in channels))
+    for sid, sub in streams.items():
+        if not len(sub.labels):
+            continue
+        idx = [sub.channel_names.index(c) for c in channels]
+        w = sub.windows_f64(idx)                    # [N, W, len(channels)] float64 on the device
+        np.save(out_dir / f"{sid}_X.npy", w.cpu().numpy())
+        np.save(out_dir / f"{sid}_y.npy", np.asarray(sub.labels))
+        del w
+
+
+def reference_fold_run(data_dir, channels, sids, epochs=PARITY_EPOCHS, fold=PARITY_FOLD, dropout=0.0, threads=None):
+    """Fold ``fold`` of reference main.py:98-125 -- the reference's own WesadDataset, DataLoader, CnnGruAttentionModel and
+    Trainer, unmodified, on the host cores -- for ``epochs`` epochs.  dropout = 0 makes the run deterministic, so that ours
+    (same initial weights, same batch order) must reproduce it to fp32 rounding.  Returns losses, accuracy, F1, seconds."""
+    import contextlib
+    import io
+    import tempfile
+    import warnings
+    import numpy as np
+    import torch
+    from torch.utils.data import DataLoader
+    from oracle import ref_harness
+    from multimodalsignal_b200 import main as mm
+    ds_mod, models, trainer_mod = ref_harness.load("dataset"), ref_harness.load("models"), ref_harness.load("trainer")
+    torch.set_num_threads(threads or os.cpu_count() or 1)
+    names = (Path(data_dir) / "_channel_names.txt").read_text().split()
+    train_s, val_s = mm.fold_split(fold, list(sids))                      # main.py:102-103 (sklearn, seed 42)
+    mk = lambda subs: ds_mod.WesadDataset(Path(data_dir), subs, channels, names, classification_mode="stress_binary")
+    torch.manual_seed(42)
+    np.random.seed(42)
+    t_load = time.perf_counter()
+    train_ds, val_ds, test_ds = mk(train_s), mk(val_s), mk([fold])
+    t_load = time.perf_counter() - t_load
+    tl = DataLoader(train_ds, batch_size=64, shuffle=True, num_workers=0)
+    vl = DataLoader(val_ds, batch_size=64, shuffle=False, num_workers=0)
+    te = DataLoader(test_ds, batch_size=64, shuffle=False, num_workers=0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model = models.CnnGruAttentionModel(in_channels=len(channels), num_classes=2, cnn_out_channels=32, gru_hidden_size=64,
+                                            gru_num_layers=2, dropout=dropout)
+    init = {k: v.clone() for k, v in model.state_dict().items()}
+    cfg = {'trainer': {'epochs': epochs, 'learning_rate': 1e-3, 'early_stopping': {'enabled': True, 'patience': 20, 'delta': 0},
+                       'weight_decay': 1e-4}}
+    tmp = Path(tempfile.mkdtemp(prefix="mms_ref_fold_"))
+    dev_was = torch.cuda.is_available
+    torch.cuda.is_available = lambda: False          # trainer.py:57 picks cuda when it can: this leg is the CPU path
+    try:
+        with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+            tr = trainer_mod.Trainer(model, tmp / "fold", cfg)
+            t0 = time.perf_counter()
+            tr.train(tl, vl)
+            t_train = time.perf_counter() - t0
+            test_loss, test_acc, test_f1 = tr.evaluate(te, is_test=True)
+    finally:
+        torch.cuda.is_available = dev_was
+    log = (tmp / "fold" / "training_log.txt").read_text(encoding="utf-8")
+    return {"fold": fold, "epochs": epochs, "dropout": dropout, "n_train": len(train_ds), "n_val": len(val_ds), "n_test": len(test_ds),
+            "train_seconds": t_train, "dataset_seconds": t_load, "windows_per_s": epochs * len(train_ds) / t_train,
+            "test_loss": float(test_loss), "test_accuracy": float(test_acc), "test_f1": float(test_f1), "log": log,
+            "init": init, "train_subjects": train_s, "val_subjects": val_s, "cores": torch.get_num_threads()}
+
+
+def reference_loso_leg(args, minutes=100.0):
+    """The reference arm's LOSO figure: fold "test S2" of the 15-subject protocol for PARITY_EPOCHS epochs
+    through the reference's own dataset.py / models.py / trainer.py on the host cores, on the same synthetic recordings as
+    our arm (windows by the numpy restatement of preprocess.py: no GPU code on this path), and the extrapolation to 15 folds."""
+    import copy
+    import shutil
+    import tempfile
+    from concurrent.futures import ThreadPoolExecutor
+    import numpy as np
+    from oracle import preprocess_oracle as po, ref_harness
+    if not ref_harness.available():
+        return {"unavailable": "reference modules not staged under baseline/_ref"}
+    largs = copy.copy(args)
+    largs.subjects, largs.minutes = 15, minutes
+    t0 = time.perf_counter()
+    sids, subs, protocol = _synthetic_subjects(largs)
+    root = Path(tempfile.mkdtemp(prefix="mms_ref_loso_"))
+    data_dir = root / "data" / "all_raw"
+    data_dir.mkdir(parents=True)
+    (data_dir / "_channel_names.txt").write_text("".join(f"{c}\n" for c in NORTH_STAR_CHANNELS))
+    wrist_fs = {"BVP": 64, "EDA": 4}
+
+    def prep(sid):
+        sub = subs[sid]
+        res = {}
+        for name in NORTH_STAR_CHANNELS:
+            where, ch = name.split("_")
+            if where == "chest":
+                res[name] = po.resample_signal(sub.chest[ch], 700, 64)
+        num = len(next(iter(res.values())))
+        for name in NORTH_STAR_CHANNELS:
+            where, ch = name.split("_")
+            if where == "wrist":
+                y = po.resample_signal(sub.wrist[ch], wrist_fs[ch], 64)
+                if len(y) < num:
+                    y = np.concatenate([y, np.repeat(y[-1:], num - len(y), axis=0)], axis=0)
+                res[name] = y[:num]
+        starts, labels, w = po.window_plan(po.apply_subject_quirk(sid, protocol), 64)
+        X = np.stack([np.stack([res[c][a:a + w, 0] for c in NORTH_STAR_CHANNELS], axis=1) for a in starts]) if len(starts) else np.zeros((0, w, 6))
+        np.save(data_dir / f"{sid}_X.npy", X)
+        np.save(data_dir / f"{sid}_y.npy", np.asarray(labels))
+        return len(labels)
+
+    try:
+        with ThreadPoolExecutor(max(1, min(8, os.cpu_count() or 1))) as ex:
+            nwin = sum(ex.map(prep, sids))
+        t_prep = time.perf_counter() - t0
+        ref = reference_fold_run(data_dir, NORTH_STAR_CHANNELS, sids)
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+    per_epoch = ref["train_seconds"] / PARITY_EPOCHS
+    return {"metric": "LOSO fold wall-clock, reference Trainer on the host cores", "fold": PARITY_FOLD, "epochs": PARITY_EPOCHS, "dropout": 0.0,
+            "cores": ref["cores"], "windows_total": nwin, "n_train": ref["n_train"], "n_val": ref["n_val"], "n_test": ref["n_test"],
+            "preprocess_and_generate_s": t_prep, "train_seconds": ref["train_seconds"], "seconds_per_epoch": per_epoch,
+            "windows_per_s": ref["windows_per_s"], "test_accuracy": ref["test_accuracy"], "test_f1": ref["test_f1"],
+            "test_loss": ref["test_loss"], "epoch_losses": _log_losses(ref["log"]),
+            "extrapolated_15_fold_s": 15 * 40 * per_epoch,
+            "extrapolation": "15 folds x ~40 epochs (where early stopping ends the synthetic folds in our GPU run) x the measured seconds per epoch"}
+
+
+def _log_losses(log):
+    """(train loss, validation loss) per epoch from a training_log.txt of reference trainer.py:171-176 (ours writes the same lines)."""
+    import re
+    return [(float(a), float(b)) for a, b in re.findall(r"训练损失: ([0-9.eE+-]+).*?验证损失: ([0-9.eE+-]+)", log)]
+
+
+def fold_parity_measure(args, streams):
+    """north_star "matched accuracy against the reference": fold S2, 2 epochs, dropout 0 (deterministic), the SAME .npy files,
+    initial weights and batch order through the reference Trainer on the host cores and through ours on the GPU."""
+    import contextlib
+    import io
+    import shutil
+    import tempfile
+    import torch
+    from torch.utils.data import DataLoader
+    from oracle import ref_harness
+    if not ref_harness.available():
+        return {"unavailable": "reference modules not staged under baseline/_ref"}
+    from multimodalsignal_b200 import main as mm
+    from multimodalsignal_b200.dataset import WesadDataset
+    from multimodalsignal_b200.models import CnnGruAttentionModel
+    from multimodalsignal_b200.trainer import Trainer
+    sids = list(streams.keys())
+    root = Path(tempfile.mkdtemp(prefix="mms_parity_"))
+    try:
+        data_dir = root / "data" / "all_raw"
+        _write_reference_npy(streams, data_dir, NORTH_STAR_CHANNELS)
+        ref = reference_fold_run(data_dir, NORTH_STAR_CHANNELS, sids)
+        # ours: the file path of run_fold_async (the reference's data flow), same seed -> same shuffle order, same initial weights
+        torch.manual_seed(42)
+        import numpy as np
+        np.random.seed(42)
+        names = (data_dir / "_channel_names.txt").read_text().split()
+        mk = lambda subs: WesadDataset(data_dir, subs, NORTH_STAR_CHANNELS, names, classification_mode="stress_binary")
+        train_ds, val_ds, test_ds = mk(ref["train_subjects"]), mk(ref["val_subjects"]), mk([PARITY_FOLD])
+        tl = DataLoader(train_ds, batch_size=64, shuffle=True, num_workers=0, pin_memory=True)
+        vl = DataLoader(val_ds, batch_size=64, shuffle=False, num_workers=0, pin_memory=True)
+        te = DataLoader(test_ds, batch_size=64, shuffle=False, num_workers=0, pin_memory=True)
+        model = CnnGruAttentionModel(in_channels=len(NORTH_STAR_CHANNELS), num_classes=2, cnn_out_channels=32, gru_hidden_size=64,
+                                     gru_num_layers=2, dropout=0.0)
+        same_init = all(torch.equal(v, ref["init"][k]) for k, v in model.state_dict().items())
+        if not same_init:
+            model.load_state_dict(ref["init"])
+        cfg = {'trainer': {'epochs': PARITY_EPOCHS, 'learning_rate': 1e-3, 'early_stopping': {'enabled': True, 'patience': 20, 'delta': 0},
+                           'weight_decay': 1e-4}}
+        with contextlib.redirect_stdout(io.StringIO()):
+            tr = Trainer(model, root / "fold_ours", cfg)
+            t0 = time.perf_counter()
+            tr.train(tl, vl)
+            torch.cuda.synchronize()
+            t_ours = time.perf_counter() - t0
+            test_loss, test_acc, test_f1 = tr.evaluate(te, is_test=True)
+        ours_losses = _log_losses((root / "fold_ours" / "training_log.txt").read_text(encoding="utf-8"))
+        ref_losses = _log_losses(ref["log"])
+        n = min(len(ours_losses), len(ref_losses))
+        return {"fold": PARITY_FOLD, "epochs": PARITY_EPOCHS, "dropout": 0.0, "n_train": ref["n_train"], "n_val": ref["n_val"], "n_test": ref["n_test"],
+                "same_initial_weights_from_seed": bool(same_init),
+                "reference": {"kind": "unmodified reference dataset.py / models.py / trainer.py on the host cores", "cores": ref["cores"],
+                              "train_seconds": ref["train_seconds"], "windows_per_s": ref["windows_per_s"], "test_loss": ref["test_loss"],
+                              "test_accuracy": ref["test_accuracy"], "test_f1": ref["test_f1"], "epoch_losses": ref_losses},
+                "ours": {"kind": "multimodalsignal_b200 Trainer + DataLoader on the same files (B200)", "train_seconds": t_ours,
+                         "windows_per_s": PARITY_EPOCHS * ref["n_train"] / t_ours, "test_loss": float(test_loss), "test_accuracy": float(test_acc),
+                         "test_f1": float(test_f1), "epoch_losses": ours_losses},
+                "accuracy_delta_vs_reference": float(test_acc) - ref["test_accuracy"],
+                "f1_delta_vs_reference": float(test_f1) - ref["test_f1"],
+                "max_epoch_loss_delta": max([max(abs(o[0] - r[0]), abs(o[1] - r[1])) for o, r in zip(ours_losses[:n], ref_losses[:n])], default=None),
+                "reference_extrapolation": {"fifteen_folds_s": 15 * ref["train_seconds"] / PARITY_EPOCHS * 40,
+                                            "how": "15 folds x ~40 epochs (where early stopping ends the synthetic folds on the GPU run) x the "
+                                                   "reference's measured seconds per epoch; BASELINE.md 4.3 allows the extrapolation to be stated"}}
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+
+
+def dp_measure(args, world, rank, dev, B, Cc, T, steps, exchange):
+    """BASELINE.json configs[4]: intra-fold data parallelism -- ONE fold, the global batch split over the ranks, SyncBN + one
+    flat-gradient exchange per step (strong scaling).  The process group must exist.  Returns the record on every rank."""
     import torch
     import torch.distributed as dist
     from multimodalsignal_b200.models import CnnGruAttentionModel
     from multimodalsignal_b200.parallel import DataParallelTrainStep
     from multimodalsignal_b200.trainer import FlatAdam
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
-    B, Cc, T = args.batch, args.channels, args.seq_len
     assert B % world == 0, "global batch must divide over the ranks"
     b = B // world
     torch.manual_seed(42)
     model = CnnGruAttentionModel(Cc, 2, dropout=0.5).to(dev).train()
-    peer = "symm" if args.dp_exchange == "peer" else None
+    peer = "symm" if exchange == "peer" else None
     step = DataParallelTrainStep(model, FlatAdam(model, lr=1e-3, weight_decay=1e-4), b, B, T, rank=rank, peer=peer)
     gen = torch.Generator(device=dev).manual_seed(7 + rank)
     NB = 16
     px = torch.randn(NB, b, Cc, T, device=dev, generator=gen)
     py = torch.randint(0, 2, (NB, b), device=dev, generator=gen)
-    for i in range(max(3, args.warmup)):
+    for i in range(max(3, args.warmup if args.warmup < 20 else 20)):
         step(px[i % NB], py[i % NB])
     dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(args.steps):
+    for i in range(steps):
         step(px[i % NB], py[i % NB])
     e1.record()
     dist.barrier()
@@ -727,16 +1016,30 @@ def run_dp(args):
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     loss = step.global_loss()
+    del step
+    return {"metric": "train windows/sec (fwd+bwd+Adam) CnnGruAttention, intra-fold data parallel", "value": B * steps / (ms.item() * 1e-3),
+            "unit": "windows/s", "n_gpus": world, "steps": steps, "warmup": max(3, args.warmup if args.warmup < 20 else 20),
+            "ms_per_step": ms.item() / steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "intra-fold data parallel (BASELINE.json configs[4])", "global_batch": B, "local_batch": b, "channels": Cc,
+                       "seq_len": T, "parallelism": (f"dp{world}: SyncBN (4 x <=1 KB) + flat gradient (0.5 MB) exchanged by peer-memory kernels over NVLink, "
+                                       "gradient all-reduce fused with Adam, one CUDA graph per rank") if peer else
+                                      f"dp{world}: SyncBN (4 x <=1 KB all-reduce) + 1 flat gradient all-reduce (0.5 MB) per step (NCCL)",
+                       "exchange": exchange, "cuda_graph": bool(peer)},
+            "final_loss": loss}
+
+
+def run_dp(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    line = dp_measure(args, world, rank, dev, args.batch, args.channels, args.seq_len, args.steps, args.dp_exchange)
     if rank == 0:
-        line = {"metric": "train windows/sec (fwd+bwd+Adam) CnnGruAttention, intra-fold data parallel", "value": B * args.steps / (ms.item() * 1e-3),
-                "unit": "windows/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms.item() / args.steps,
-                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "intra-fold data parallel (BASELINE.json configs[4])", "global_batch": B, "local_batch": b, "channels": Cc,
-                           "seq_len": T, "parallelism": (f"dp{world}: SyncBN (4 x <=1 KB) + flat gradient (0.5 MB) exchanged by peer-memory kernels over NVLink, "
-                                           "gradient all-reduce fused with Adam, one CUDA graph per rank") if peer else
-                                          f"dp{world}: SyncBN (4 x <=1 KB all-reduce) + 1 flat gradient all-reduce (0.5 MB) per step (NCCL)",
-                           "exchange": args.dp_exchange, "cuda_graph": bool(peer)},
-                "final_loss": loss}
         print(json.dumps(line), flush=True)
     dist.destroy_process_group()
 

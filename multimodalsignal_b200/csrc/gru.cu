@@ -753,7 +753,7 @@ static int gru_fwd_dispatch(const GruFwdParams& prm, int ndirs, cudaStream_t st)
         MMS_PROF_BEGIN(st);
         auto k2 = gru_fwd_v2_kernel<H>;
         MMS_LAUNCH(k2, grid, dim3(2 * H), 0, st, prm);
-        MMS_LAUNCH_CHECK("gru_fwd_kernel");
+        MMS_LAUNCH_CHECK("gru_fwd_v2_kernel");
         return MMS_OK;
     }
     MMS_PROF_BEGIN(st);
@@ -782,10 +782,10 @@ template <int H>
 static int gru_bwd_dispatch(const GruBwdParams& prm, int ndirs, cudaStream_t st) {
     const int R = rows_per_cta(prm.B, ndirs);
     dim3 grid(cdiv(prm.B, R), ndirs);
-    // MMS_GRU_BWD_RING / mms_set_option("GRU_BWD_RING", n): shared-memory ring of depth 4 (default) or 8; 0 = the register-ring
+    // MMS_GRU_BWD_RING / mms_set_option("GRU_BWD_RING", n): shared-memory ring of depth 8 (default) or 4; 0 = the register-ring
     // kernel (gru_bwd_kernel), which also serves R > 1 rows per CTA and operands that are not 16-byte aligned.
     // Measured on a B200 (profiles/r1_ab_gru_bwd_ring.json): 89.6 us (register ring) -> 69.3 us (depth 4) -> 66.7 us (depth 8)
-    // per launch; depth 4 is the default because the whole GPU suite was run with it.
+    // per launch; depth 8 is the default since round 2 (the whole GPU suite runs with it).
     const int ring = option_get("GRU_BWD_RING", 8);
     if (ring > 0 && R == 1 && bwd_ring_ok(prm, ndirs)) {
         // MMS_GRU_BWD_EXCLUSIVE_KB (experiment, default 0): reserve that much dynamic shared memory per CTA so that no
@@ -806,7 +806,7 @@ static int gru_bwd_dispatch(const GruBwdParams& prm, int ndirs, cudaStream_t st)
         auto r4 = gru_bwd_ring_kernel<H, 4>;
         if (ring >= 8) MMS_LAUNCH(r8, grid, dim3(2 * H), dyn, st, prm);
         else MMS_LAUNCH(r4, grid, dim3(2 * H), dyn, st, prm);
-        MMS_LAUNCH_CHECK("gru_bwd_kernel");
+        MMS_LAUNCH_CHECK("gru_bwd_ring_kernel");
         return MMS_OK;
     }
     MMS_PROF_BEGIN(st);

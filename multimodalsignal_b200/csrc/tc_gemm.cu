@@ -436,7 +436,7 @@ int launch_tc_gemm_tn_batch(const TnCall* calls, int n, cudaStream_t st) {
     if (ns == 1) tc_gemm_tn_batch_kernel<1><<<grid, TC_THREADS, smem, st>>>(maps, bp);
     else if (ns == 2) tc_gemm_tn_batch_kernel<2><<<grid, TC_THREADS, smem, st>>>(maps, bp);
     else tc_gemm_tn_batch_kernel<3><<<grid, TC_THREADS, smem, st>>>(maps, bp);
-    MMS_LAUNCH_CHECK("tc_gemm_tn_kernel");
+    MMS_LAUNCH_CHECK("tc_gemm_tn_batch_kernel");
     return MMS_OK;
 }
 
