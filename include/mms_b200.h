@@ -162,7 +162,13 @@ int mms_cross_entropy_partial(const float* logits, const int64_t* labels, int32_
  * vectors whose workspace offsets mms_cnngru_sync_offsets() reports.
  * mms_peer_allreduce_adam: flat gradient all-reduce FUSED with mms_adam_flat_step (trainer.py:148-149): the gradients of
  * all ranks are summed on the fly in rank order (bit-identical parameters on every rank) and consumed by the Adam update;
- * scratch2_dev: two zero-initialised local uint32. */
+ * scratch2_dev: two zero-initialised local uint32.
+ * Every wait inside these kernels is bounded (MMS_PEER_TIMEOUT_MS, default 2000): if a peer never signals -- a rank died,
+ * made a different number of steps, or raised between two phases -- the kernel gives up, finishes with a meaningless sum and
+ * counts the event.  mms_peer_status() returns that count for the current device and clears it (it synchronises the device);
+ * a caller checks it wherever it reads results back.  The reference has no counterpart (its training is single-device,
+ * trainer.py:57-58); this is the failure detection of the data-parallel extension (BASELINE.json configs[4]). */
+int mms_peer_status(uint32_t* timeouts_host);
 int mms_peer_allreduce_f64(const void* const* bufs_host, void* const* signals_host, int32_t world, int32_t rank,
                            int32_t signal_base, int32_t count, uint32_t* epoch_dev, mms_stream_t stream);
 int mms_peer_allreduce_adam(float* params, const void* const* grads_host, void* const* signals_host, int32_t world,

@@ -95,6 +95,7 @@ _SIGNATURES = {
     "mms_cnngru_backward_phase": (c_i32, [C.POINTER(CnnGruDesc), c_i32, P, P, P, P, P, P, P]),
     "mms_cnngru_sync_offsets": (c_i32, [C.POINTER(CnnGruDesc), C.POINTER(c_i64), C.POINTER(c_i64)]),
     "mms_peer_allreduce_f64": (c_i32, [P, P, c_i32, c_i32, c_i32, c_i32, P, P]),
+    "mms_peer_status": (c_i32, [P]),
     "mms_peer_allreduce_adam": (c_i32, [P, P, P, c_i32, c_i32, c_i32, P, P, c_i64, P, c_f32, c_f32, c_f32, c_f32, P, P, P, P]),
     "mms_adam_flat_step": (c_i32, [P, P, P, P, c_i64, P, c_f32, c_f32, c_f32, c_f32, P, P, P]),
     "mms_cnngru_train_step": (c_i32, [C.POINTER(CnnGruDesc), P, P, P, P, P, P, P, P, P, P, P, P, P,

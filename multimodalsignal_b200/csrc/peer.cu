@@ -11,6 +11,15 @@
 // (ld.acquire.sys).  Epochs only grow, so the words never need resetting; `epoch_dev` (local) holds the last epoch used.
 // Each call uses two barriers: "my data is ready" before the peers are read, and "I have finished reading" before the
 // kernel ends, so that whatever runs next on any rank may overwrite its buffer.
+//
+// Failure behaviour: every wait is BOUNDED (%globaltimer deadline, MMS_PEER_TIMEOUT_MS, default 2000 ms).  A rank that has
+// died, diverged in step count or raised on the host between two phases therefore cannot hang the other GPUs inside a
+// kernel that nothing short of a device reset could cancel: the waiting threads give up, count the event in a device
+// counter and the kernel finishes (with a meaningless sum); mms_peer_status() reads and clears the counter, and the Python
+// side checks it wherever it reads a loss back (parallel.DataParallelTrainStep.global_loss) and raises.
+// No kernel here depends on its own CTAs being co-resident: every CTA of the fused Adam kernel polls the rank's own signal
+// pad itself (CTA 0, which the hardware dispatches first, is the only one that signals the peers), and the closing barrier
+// is run by whichever CTA finishes last.
 #include "mms_common.cuh"
 
 namespace mms {
@@ -46,54 +55,78 @@ __device__ __forceinline__ double ld_relaxed_sys_d(const double* p) {
     return v;
 }
 
-// executed by threads 0 .. world-1 of ONE CTA; the caller synchronises the CTA afterwards
-__device__ __forceinline__ void peer_barrier(const PeerPtrs& pp, int world, int rank, int base, uint32_t e, int tid) {
+__device__ unsigned int g_peer_timeouts;      // waits that ran into their deadline since the last mms_peer_status()
+
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// spin until *word >= e (epochs wrap: signed difference) or `timeout_ns` has passed; false + one count on a timeout
+__device__ __forceinline__ bool spin_until(const uint32_t* word, uint32_t e, uint64_t timeout_ns) {
+    if ((int32_t)(ld_acquire_sys(word) - e) >= 0) return true;
+    const uint64_t t0 = globaltimer_ns();
+    for (;;) {
+#pragma unroll 1
+        for (int i = 0; i < 64; ++i)
+            if ((int32_t)(ld_acquire_sys(word) - e) >= 0) return true;
+        if (globaltimer_ns() - t0 > timeout_ns) {
+            atomicAdd(&g_peer_timeouts, 1u);
+            return false;
+        }
+    }
+}
+
+// "I have passed this point of epoch e": threads 0 .. world-1 of ONE CTA store e into every peer's pad
+__device__ __forceinline__ void peer_signal(const PeerPtrs& pp, int world, int rank, int base, uint32_t e, int tid) {
     if (tid < world) {
         __threadfence_system();
         st_release_sys(pp.sig[tid] + base + rank, e);
-        const uint32_t* mine = pp.sig[rank] + base + tid;
-        while ((int32_t)(ld_acquire_sys(mine) - e) < 0) { }
     }
+}
+// "every rank has passed it": threads 0 .. world-1 wait on the words of the rank's OWN pad; the caller synchronises the CTA
+__device__ __forceinline__ void peer_wait(const PeerPtrs& pp, int world, int rank, int base, uint32_t e, int tid, uint64_t timeout_ns) {
+    if (tid < world) spin_until(pp.sig[rank] + base + tid, e, timeout_ns);
+}
+__device__ __forceinline__ void peer_barrier(const PeerPtrs& pp, int world, int rank, int base, uint32_t e, int tid, uint64_t timeout_ns) {
+    peer_signal(pp, world, rank, base, e, tid);
+    peer_wait(pp, world, rank, base, e, tid, timeout_ns);
 }
 
 // v[i] = sum over the ranks (rank order) of buf[p][i], i < count <= blockDim.x, written back IN PLACE to the local buffer
 // after every peer has finished reading it.  One CTA.
 __global__ void __launch_bounds__(256) peer_allreduce_f64_kernel(const PeerPtrs pp, int world, int rank, int base, int count,
-                                                                 uint32_t* epoch_dev) {
+                                                                 uint32_t* epoch_dev, uint64_t timeout_ns) {
     const int tid = threadIdx.x;
     const uint32_t e = *epoch_dev + 1;
     __syncthreads();                               // everybody has read the epoch before thread 0 advances it
-    peer_barrier(pp, world, rank, base, e, tid);   // the peers' values are in place
+    peer_barrier(pp, world, rank, base, e, tid, timeout_ns);   // the peers' values are in place
     __syncthreads();
     double s = 0.0;
     if (tid < count)
         for (int p = 0; p < world; ++p) s += ld_relaxed_sys_d(reinterpret_cast<const double*>(pp.buf[p]) + tid);
     __syncthreads();
-    peer_barrier(pp, world, rank, base + world, e, tid);    // everybody has read everybody
+    peer_barrier(pp, world, rank, base + world, e, tid, timeout_ns);    // everybody has read everybody
     __syncthreads();
     if (tid < count) const_cast<double*>(reinterpret_cast<const double*>(pp.buf[rank]))[tid] = s;
     if (tid == 0) *epoch_dev = e;
 }
 
-// Fused gradient all-reduce + Adam (same update rule as adam_flat_kernel in head_opt.cu).  CTA 0 runs the cross-GPU
-// barriers; the other CTAs wait on / report through local flags (all CTAs are co-resident: grid <= number of SMs).
+// Fused gradient all-reduce + Adam (same update rule as adam_flat_kernel in head_opt.cu).  CTA 0 tells the peers that this
+// rank's gradient is complete; EVERY CTA waits for the peers' signals on the rank's own pad (no CTA waits for another CTA of
+// the same launch, so nothing depends on co-residency); the last CTA to finish runs the closing barrier.
 __global__ void __launch_bounds__(256) peer_allreduce_adam_kernel(float* __restrict__ p, const PeerPtrs pp, float* __restrict__ m,
                                                                   float* __restrict__ v, int64_t n, const float* __restrict__ lr_dev,
                                                                   float beta1, float beta2, float eps, float wd, int64_t* step_dev,
                                                                   int world, int rank, int base, uint32_t* epoch_dev,
-                                                                  uint32_t* gate_dev, uint32_t* done_dev) {
+                                                                  uint32_t* done_dev, uint64_t timeout_ns) {
     const int tid = threadIdx.x;
     const uint32_t e = *epoch_dev + 1;
     const double t = (double)(*step_dev + 1);
     const float lr = *lr_dev;
-    if (blockIdx.x == 0) {
-        peer_barrier(pp, world, rank, base, e, tid);          // every rank's gradient buffer is complete
-        __syncthreads();
-        if (tid == 0) { __threadfence(); atomicExch(gate_dev, e); }
-    } else if (tid == 0) {
-        while ((int32_t)(atomicAdd(gate_dev, 0u) - e) < 0) { }
-        __threadfence();
-    }
+    if (blockIdx.x == 0) peer_signal(pp, world, rank, base, e, tid);      // this rank's gradient buffer is complete (stream order)
+    peer_wait(pp, world, rank, base, e, tid, timeout_ns);                   // ... and so is every peer's
     __syncthreads();
     const float bc1 = (float)(1.0 - pow((double)beta1, t));
     const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, t));
@@ -138,7 +171,7 @@ __global__ void __launch_bounds__(256) peer_allreduce_adam_kernel(float* __restr
     }
     __syncthreads();
     if (s_last) {
-        peer_barrier(pp, world, rank, base + world, e, tid);
+        peer_barrier(pp, world, rank, base + world, e, tid, timeout_ns);
         __syncthreads();
         if (tid == 0) {
             *done_dev = 0u;
@@ -158,9 +191,25 @@ static int fill_peer(PeerPtrs* pp, const void* const* bufs_host, void* const* si
     return MMS_OK;
 }
 
+static uint64_t peer_timeout_ns() {
+    int ms = option_get("PEER_TIMEOUT_MS", 2000);
+    if (ms < 1) ms = 1;
+    return (uint64_t)ms * 1000000ull;
+}
+
 }  // namespace mms
 
 using namespace mms;
+
+// Number of peer waits that ran into their deadline on the current device since the last call (read and cleared; synchronises).
+extern "C" int mms_peer_status(uint32_t* timeouts_host) {
+    MMS_REQUIRE(timeouts_host, "peer_status: null pointer");
+    unsigned int v = 0, zero = 0;
+    MMS_CUDA(cudaMemcpyFromSymbol(&v, g_peer_timeouts, sizeof(v)));
+    if (v) MMS_CUDA(cudaMemcpyToSymbol(g_peer_timeouts, &zero, sizeof(zero)));
+    *timeouts_host = v;
+    return MMS_OK;
+}
 
 extern "C" int mms_peer_allreduce_f64(const void* const* bufs_host, void* const* signals_host, int32_t world, int32_t rank,
                                       int32_t signal_base, int32_t count, uint32_t* epoch_dev, mms_stream_t stream) {
@@ -171,7 +220,7 @@ extern "C" int mms_peer_allreduce_f64(const void* const* bufs_host, void* const*
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     MMS_PROF_BEGIN(st);
-    peer_allreduce_f64_kernel<<<1, 256, 0, st>>>(pp, world, rank, signal_base, count, epoch_dev);
+    peer_allreduce_f64_kernel<<<1, 256, 0, st>>>(pp, world, rank, signal_base, count, epoch_dev, peer_timeout_ns());
     MMS_LAUNCH_CHECK("peer_allreduce_f64_kernel");
     return MMS_OK;
 }
@@ -190,12 +239,12 @@ extern "C" int mms_peer_allreduce_adam(float* params, const void* const* grads_h
     if (rc) return rc;
     for (int i = 0; i < world; ++i) MMS_REQUIRE((reinterpret_cast<uintptr_t>(pp.buf[i]) & 15) == 0, "peer_allreduce_adam: gradient buffers must be 16-byte aligned");
     int blocks = (int)((n / 4 + 255) / 256);
-    if (blocks > 64) blocks = 64;               // co-resident by construction (64 CTAs of 256 threads on 148 SMs)
+    if (blocks > 64) blocks = 64;
     if (blocks < 1) blocks = 1;
     cudaStream_t st = (cudaStream_t)stream;
     MMS_PROF_BEGIN(st);
     peer_allreduce_adam_kernel<<<blocks, 256, 0, st>>>(params, pp, exp_avg, exp_avg_sq, n, lr_dev, beta1, beta2, eps, weight_decay,
-                                                       step_dev, world, rank, signal_base, epoch_dev, scratch2_dev, scratch2_dev + 1);
+                                                       step_dev, world, rank, signal_base, epoch_dev, scratch2_dev + 1, peer_timeout_ns());
     MMS_LAUNCH_CHECK("peer_allreduce_adam_kernel");
     return MMS_OK;
 }

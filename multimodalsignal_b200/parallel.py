@@ -197,13 +197,37 @@ class DataParallelTrainStep:
         for t in self.phases(x, y):
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
 
+    def check_peers(self):
+        """Failure detection of the peer-memory path, called wherever results are read back: raises if any bounded wait of the
+        peer kernels timed out on this device (a rank died, raised between two phases or made a different number of steps:
+        the sums of such a step are meaningless) or if the ranks disagree on the number of steps made."""
+        if self.peer is None:
+            return
+        n = C.c_uint32(0)
+        check(self.lib.mms_peer_status(C.byref(n)))
+        if n.value:
+            raise RuntimeError(f"data-parallel peer exchange: {n.value} wait(s) timed out on rank {self.rank} -- a peer did not reach "
+                               "the same exchange point (MMS_PEER_TIMEOUT_MS); the parameters of this fold are no longer valid")
+        import torch.distributed as dist
+        if self.peer == "symm" and dist.is_available() and dist.is_initialized():
+            steps = torch.tensor([self.calls], dtype=torch.int64, device=self.loss.device)
+            lo, hi = steps.clone(), steps.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=self.group)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=self.group)
+            if int(lo.item()) != int(hi.item()):
+                raise RuntimeError(f"data-parallel ranks made different numbers of steps ({int(lo.item())} .. {int(hi.item())}): "
+                                   "every rank must see the same number of batches (drop the ragged last batch or pad it)")
+
     def global_loss(self) -> float:
-        """Mean loss over the global batch of the last step (one extra scalar all-reduce; for logging)."""
+        """Mean loss over the global batch of the last step (one extra scalar all-reduce; for logging).  Also the point where
+        the peer-memory path reports a failed exchange (``check_peers``)."""
         import torch.distributed as dist
         t = self.loss.clone()
         if dist.is_available() and dist.is_initialized():
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
-        return float(t.item())
+        v = float(t.item())
+        self.check_peers()
+        return v
 
 
 class LocalPeers:

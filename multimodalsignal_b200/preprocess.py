@@ -349,6 +349,14 @@ def run_preprocessing(wesad_root=None, output_path=None, subject_ids=None, inclu
     with open(raw_path / '_channel_names.txt', 'w') as f:
         for name in names:
             f.write(f"{name}\n")
+    # RAW_FS defaults to 64 Hz here (north star) where the reference ships 128 (preprocess.py:21): say so at run time and leave
+    # a sidecar next to the windows, so that arrays of different rates in the same ./data tree can be told apart
+    window = int(RAW_WINDOW_SEC * RAW_FS)
+    print(f"Resampling to RAW_FS = {RAW_FS} Hz: windows of {window} samples x {len(names)} channels "
+          f"(the reference's default RAW_FS = 128 gives 7680)")
+    import json
+    (raw_path / '_preprocess_meta.json').write_text(json.dumps({"raw_fs": RAW_FS, "window_samples": window, "stride_samples": int(RAW_STRIDE_SEC * RAW_FS),
+                                                                 "channels": names, "producer": "multimodalsignal_b200.preprocess"}))
     done = []
     for sid in subject_ids:
         data = load_pkl(sid, wesad_root)

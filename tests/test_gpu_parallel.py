@@ -3,6 +3,7 @@ phase-split steps run in lockstep with their sync tensors summed by hand -- exac
 all-reduce does -- and must reproduce the single-device full-batch step (the reference computes BN
 statistics over the whole batch, models.py:47,51)."""
 import copy
+import time
 
 import numpy as np
 import pytest
@@ -190,3 +191,46 @@ def test_peer_memory_exchange_two_gpus():
                        capture_output=True, text=True, timeout=600, env=dict(os.environ))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "dp_check ok" in r.stdout
+
+
+@pytest.mark.timeout(60)
+def test_peer_wait_is_bounded_and_reported():
+    """csrc/peer.cu failure behaviour: a peer that never signals (a dead or diverged rank) must not hang the kernel.  World of
+    two ranks of which only rank 0 ever runs: its waits run into the deadline (MMS_PEER_TIMEOUT_MS), the kernels finish,
+    and mms_peer_status reports -- and clears -- the timeouts."""
+    import ctypes as C
+    from multimodalsignal_b200 import _ext
+    lib = _ext.lib()
+    dev = torch.device("cuda")
+    bufs = [torch.ones(8, dtype=torch.float64, device=dev), torch.full((8,), 2.0, dtype=torch.float64, device=dev)]
+    sigs = [torch.zeros(256, dtype=torch.int32, device=dev) for _ in range(2)]
+    epoch = torch.zeros(1, dtype=torch.int32, device=dev)
+    arr = lambda ts: (C.c_void_p * 2)(*[t.data_ptr() for t in ts])
+    n = C.c_uint32(7)
+    _ext.check(lib.mms_peer_status(C.byref(n)))          # clear whatever earlier tests left
+    prev = lib.mms_get_option(b"PEER_TIMEOUT_MS", -1)
+    _ext.check(lib.mms_set_option(b"PEER_TIMEOUT_MS", 20))
+    try:
+        t0 = time.perf_counter()
+        _ext.check(lib.mms_peer_allreduce_f64(arr(bufs), arr(sigs), 2, 0, 0, 8, epoch.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        assert time.perf_counter() - t0 < 5.0
+        _ext.check(lib.mms_peer_status(C.byref(n)))
+        assert n.value >= 1                                # both barriers of the call timed out on the silent peer's word
+        _ext.check(lib.mms_peer_status(C.byref(n)))
+        assert n.value == 0                                # read-and-clear
+        # the fused gradient all-reduce + Adam: every CTA waits for itself, none for another CTA of the launch
+        N = 4096
+        p, m, v = (torch.zeros(N, device=dev) for _ in range(3))
+        g = [torch.ones(N, device=dev), torch.ones(N, device=dev)]
+        lr = torch.full((1,), 1e-3, device=dev)
+        step = torch.zeros(1, dtype=torch.int64, device=dev)
+        scratch = torch.zeros(2, dtype=torch.int32, device=dev)
+        _ext.check(lib.mms_peer_allreduce_adam(p.data_ptr(), arr(g), arr(sigs), 2, 0, 8, m.data_ptr(), v.data_ptr(), N, lr.data_ptr(),
+                                               0.9, 0.999, 1e-8, 0.0, step.data_ptr(), epoch.data_ptr(), scratch.data_ptr(),
+                                               torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        _ext.check(lib.mms_peer_status(C.byref(n)))
+        assert n.value >= 1
+    finally:
+        _ext.check(lib.mms_set_option(b"PEER_TIMEOUT_MS", prev) if prev >= 0 else lib.mms_clear_option(b"PEER_TIMEOUT_MS"))
