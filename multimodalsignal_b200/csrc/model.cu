@@ -640,21 +640,31 @@ static int model_backward(const mms_cnngru_desc* d, const float* x, const float*
         }
         rc = launch_gru_bwd(dirs, 2, B, H, p, d->rng_seed, d->rng_offset, d->rng_offset_dev, st);
         if (rc) return rc;
-        if (defer_top_wgrad && l == top - 1) {
+        const bool tn_after = option_get("TN_AFTER_NT", 1) == 1;
+        if (defer_top_wgrad && l == top - 1 && !tn_after) {
             rc = top_wgrad();
             if (rc) return rc;
         }
-        cudaStream_t sw = fk.fork(1 - (l & 1));
-        TnCall four[4];
-        for (int dd = 0; dd < 2; ++dd) {
-            const float* Dd = w.D[l] + dd * 4 * H;
-            four[2 * dd] = {Dd, 8 * H, 3 * H, 0, in_l, I_l, 0, L, G + po.w_ih[l] + (int64_t)dd * 3 * H * I_l, I_l,
-                            G + po.b_ih[l] + dd * 3 * H, M, 3 * H, I_l};
-            four[2 * dd + 1] = {Dd, 8 * H, 2 * H, H, w.hs[l] + dd * H, 2 * H, dd ? 1 : -1, L,
-                                G + po.w_hh[l] + (int64_t)dd * 3 * H * H, H, G + po.b_hh[l] + dd * 3 * H, M, 3 * H, H};
+        // Weight gradients of this layer: side stream.  MMS_TN_AFTER_NT=1 (default) forks them AFTER the input-gradient product
+        // below has been enqueued: both stream the same D rows, and started together the 148-CTA weight-gradient kernels
+        // stretched the (critical-path) input-gradient product 2.4x (round-2 timeline); started behind it they overlap the
+        // encoder's backward kernels instead.
+        auto layer_wgrad = [&]() -> int {
+            cudaStream_t sw = fk.fork(1 - (l & 1));
+            TnCall four[4];
+            for (int dd = 0; dd < 2; ++dd) {
+                const float* Dd = w.D[l] + dd * 4 * H;
+                four[2 * dd] = {Dd, 8 * H, 3 * H, 0, in_l, I_l, 0, L, G + po.w_ih[l] + (int64_t)dd * 3 * H * I_l, I_l,
+                                G + po.b_ih[l] + dd * 3 * H, M, 3 * H, I_l};
+                four[2 * dd + 1] = {Dd, 8 * H, 2 * H, H, w.hs[l] + dd * H, 2 * H, dd ? 1 : -1, L,
+                                    G + po.w_hh[l] + (int64_t)dd * 3 * H * H, H, G + po.b_hh[l] + dd * 3 * H, M, 3 * H, H};
+            }
+            return gemm_tn_many(four, 4, sw);
+        };
+        if (!tn_after) {
+            rc = layer_wgrad();
+            if (rc) return rc;
         }
-        rc = gemm_tn_many(four, 4, sw);
-        if (rc) return rc;
         if (tc_bwd && tc_gemm_supported(w.D[l], 8 * H, w.wT[l], 8 * H, M, I_l, 8 * H)) {
             // both directions in one NT product: K = [fwd 3H | (dq) | rev 3H | (dq)], zero weights on the dq columns
             rc = launch_tc_gemm_nt(w.D[l], 8 * H, w.wT[l], 8 * H, nullptr, dxnext, I_l, M, I_l, 8 * H, 0, st);
@@ -665,6 +675,14 @@ static int model_backward(const mms_cnngru_desc* d, const float* x, const float*
                                     3 * H, dd, st);
                 if (rc) return rc;
             }
+        }
+        if (tn_after) {
+            if (defer_top_wgrad && l == top - 1) {
+                rc = top_wgrad();
+                if (rc) return rc;
+            }
+            rc = layer_wgrad();
+            if (rc) return rc;
         }
         float* t = dxcur; dxcur = dxnext; dxnext = t;
     }

@@ -12,6 +12,10 @@
 // that permutation, so no reordering pass exists: the point-wise product with the (identically
 // permuted) chirp-filter spectrum happens in the permuted domain.
 // HBM-bound: every pass streams the M complex values once (32*M bytes of traffic).
+// Two REAL signals share one COMPLEX stage-A transform (z = x1 + i x2, the textbook pairing): the chirp-z transform is asked
+// for the bins -(m2-1) .. m2-1 of z instead of 0 .. m2-1 (same convolution length for the decimating case N >> num), and
+// X1[k] = (Z[k] + conj Z[-k]) / 2, X2[k] = (Z[k] - conj Z[-k]) / 2i are separated while the spectrum is fixed up.  Stage A is
+// ~90 % of the traffic of a 700 Hz -> 64 Hz resampling, so the bytes moved per signal nearly halve.
 #include "mms_common.cuh"
 
 namespace mms {
@@ -26,6 +30,14 @@ __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
 // e^{sign * pi * i * (n^2 mod 2P) / P}
 __device__ __forceinline__ double2 chirp(int64_t n, int64_t P, int sign) {
     const uint64_t e = ((uint64_t)n * (uint64_t)n) % (uint64_t)(2 * P);
+    double s, c;
+    sincospi((double)e / (double)P, &s, &c);
+    return make_double2(c, sign > 0 ? s : -s);
+}
+
+// e^{sign * pi * i * ((n^2 + 2 n k) mod 2P) / P}: the chirp times the linear phase e^{sign * 2 pi i n k / P} (0 <= k < P)
+__device__ __forceinline__ double2 chirp_shift(int64_t n, int64_t k, int64_t P, int sign) {
+    const uint64_t e = ((uint64_t)n * (uint64_t)n + 2ull * (uint64_t)n * (uint64_t)k) % (uint64_t)(2 * P);
     double s, c;
     sincospi((double)e / (double)P, &s, &c);
     return make_double2(c, sign > 0 ? s : -s);
@@ -149,6 +161,25 @@ __global__ void __launch_bounds__(256) czt_pre_real_kernel(const double* __restr
     }
 }
 
+// Paired version: a[p][n] = (x[2p][n] + i x[2p+1][n]) * chirp(n, P, sign) * e^{sign 2 pi i n k0 / P}; the second signal of the last
+// pair may be missing (odd n_sig): zero imaginary part.
+__global__ void __launch_bounds__(256) czt_pre_pair_kernel(const double* __restrict__ x, int64_t n_in, int n_sig, int64_t P, int64_t k0,
+                                                           int sign, double2* __restrict__ a, int64_t M) {
+    const int p = blockIdx.y;
+    const double* x1 = x + (int64_t)(2 * p) * n_in;
+    const double* x2 = 2 * p + 1 < n_sig ? x + (int64_t)(2 * p + 1) * n_in : nullptr;
+    double2* as = a + (int64_t)p * M;
+    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < M; n += (int64_t)gridDim.x * blockDim.x) {
+        double2 v = make_double2(0.0, 0.0);
+        if (n < n_in) {
+            const double2 c = chirp_shift(n, k0, P, sign);
+            const double re = x1[n], im = x2 ? x2[n] : 0.0;
+            v = make_double2(re * c.x - im * c.y, re * c.y + im * c.x);
+        }
+        as[n] = v;
+    }
+}
+
 // Chirp filter b[j mod M] = conj(chirp(j, P, sign)) for j in (-n_in, n_out), zero elsewhere.
 __global__ void __launch_bounds__(256) czt_filter_kernel(double2* __restrict__ b, int64_t M, int64_t n_in, int64_t n_out,
                                                          int64_t P, int sign) {
@@ -192,6 +223,40 @@ __global__ void __launch_bounds__(256) spectrum_fix_kernel(const double2* __rest
             v = cmul(G, chirp(k, num, +1));
         }
         a2[k] = v;
+    }
+}
+
+// Paired version of spectrum_fix_kernel: conv holds the bins k = j - (m2 - 1), j < 2 m2 - 1, of z = x1 + i x2 (pair blockIdx.y at
+// conv + blockIdx.y * M); the two real signals' spectra are separated, fixed up as above and written to a2 + (2p) * M2 and
+// a2 + (2p + 1) * M2 (a different region of the workspace: nothing is read after it has been overwritten).
+__global__ void __launch_bounds__(256) spectrum_fix_pair_kernel(const double2* __restrict__ conv, double2* __restrict__ a2, int n_sig,
+                                                                int64_t M, int64_t M2, int64_t N, int64_t num, int64_t m2) {
+    const int p = blockIdx.y;
+    const double2* cv = conv + (int64_t)p * M;
+    double2* o1 = a2 + (int64_t)(2 * p) * M2;
+    double2* o2 = 2 * p + 1 < n_sig ? a2 + (int64_t)(2 * p + 1) * M2 : nullptr;
+    const int64_t m = N < num ? N : num;
+    const double scale = ((double)num / (double)N) / (double)M;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < M2; k += (int64_t)gridDim.x * blockDim.x) {
+        double2 v1 = make_double2(0.0, 0.0), v2 = v1;
+        if (k < m2) {
+            const int64_t jp = m2 - 1 + k, jn = m2 - 1 - k;
+            const double2 Zp = cmul(cv[jp], chirp(jp, N, -1));
+            const double2 Zn = cmul(cv[jn], chirp(jn, N, -1));
+            double2 X1 = make_double2(0.5 * (Zp.x + Zn.x) * scale, 0.5 * (Zp.y - Zn.y) * scale);
+            double2 X2 = make_double2(0.5 * (Zp.y + Zn.y) * scale, -0.5 * (Zp.x - Zn.x) * scale);
+            if ((m & 1) == 0 && num != N && k == m / 2) {
+                const double f = num < N ? 2.0 : 0.5;
+                X1.x *= f; X1.y *= f; X2.x *= f; X2.y *= f;
+            }
+            double2 G1 = make_double2(2.0 * X1.x, 2.0 * X1.y), G2 = make_double2(2.0 * X2.x, 2.0 * X2.y);
+            if (k == 0 || ((num & 1) == 0 && k == num / 2)) { G1 = make_double2(X1.x, 0.0); G2 = make_double2(X2.x, 0.0); }
+            const double2 c = chirp(k, num, +1);
+            v1 = cmul(G1, c);
+            v2 = cmul(G2, c);
+        }
+        o1[k] = v1;
+        if (o2) o2[k] = v2;
     }
 }
 
@@ -317,6 +382,43 @@ extern "C" int mms_resample_f64(const double* x, int64_t n_in, int64_t n_out, in
     double2* work = filt + d.Mmax;                       // [n_sig][Mmax]
 
     // ---- stage A: the m2 lowest bins of the length-N DFT ------------------------------------------
+    // Paired (two real signals per complex transform) when that needs no longer convolution and the stage-C operands of all
+    // signals fit in the part of the workspace the halved stage A leaves free; otherwise one transform per signal.
+    const int n_pairs = (n_sig + 1) / 2;
+    const int64_t J = 2 * d.m2 - 1;
+    const bool paired = n_sig >= 2 && option_get("RESAMPLE_PAIRED", 1) == 1 && pow2_at_least(n_in + J - 1) == d.M1 &&
+                        (int64_t)n_sig * d.M2 <= (int64_t)(n_sig - n_pairs) * d.Mmax;
+    double2* workC = work;                               // where stage C finds its n_sig operands (stride M2)
+    if (paired) {
+        workC = work + (int64_t)n_pairs * d.Mmax;
+        MMS_PROF_BEGIN(st);
+        czt_filter_kernel<<<grid_for(d.M1), 256, 0, st>>>(filt, d.M1, d.N, J, d.N, -1);
+        MMS_LAUNCH_CHECK("czt_filter_kernel");
+        rc = fft_inplace(filt, d.M1, d.M1, 1, 0, st);
+        if (rc) return rc;
+        {
+            dim3 grid(grid_for(d.M1), n_pairs);
+            MMS_PROF_BEGIN(st);
+            czt_pre_pair_kernel<<<grid, 256, 0, st>>>(x, d.N, n_sig, d.N, d.N - (d.m2 - 1), -1, work, d.M1);     // first bin: -(m2 - 1) mod N
+            MMS_LAUNCH_CHECK("czt_pre_pair_kernel");
+        }
+        rc = fft_inplace(work, d.M1, d.M1, n_pairs, 0, st);
+        if (rc) return rc;
+        {
+            dim3 grid(grid_for(d.M1), n_pairs);
+            MMS_PROF_BEGIN(st);
+            cmul_kernel<<<grid, 256, 0, st>>>(work, filt, d.M1);
+            MMS_LAUNCH_CHECK("cmul_kernel");
+        }
+        rc = fft_inplace(work, d.M1, d.M1, n_pairs, 1, st);
+        if (rc) return rc;
+        {
+            dim3 grid(grid_for(d.M2), n_pairs);
+            MMS_PROF_BEGIN(st);
+            spectrum_fix_pair_kernel<<<grid, 256, 0, st>>>(work, workC, n_sig, d.M1, d.M2, d.N, d.num, d.m2);
+            MMS_LAUNCH_CHECK("spectrum_fix_pair_kernel");
+        }
+    } else {
     MMS_PROF_BEGIN(st);
     czt_filter_kernel<<<grid_for(d.M1), 256, 0, st>>>(filt, d.M1, d.N, d.m2, d.N, -1);
     MMS_LAUNCH_CHECK("czt_filter_kernel");
@@ -349,6 +451,7 @@ extern "C" int mms_resample_f64(const double* x, int64_t n_in, int64_t n_out, in
                                                           d.num, d.m2);
         MMS_LAUNCH_CHECK("spectrum_fix_kernel");
     }
+    }
 
     // ---- stage C: one-sided inverse transform of length num ----------------------------------------
     MMS_PROF_BEGIN(st);
@@ -356,20 +459,20 @@ extern "C" int mms_resample_f64(const double* x, int64_t n_in, int64_t n_out, in
     MMS_LAUNCH_CHECK("czt_filter_kernel");
     rc = fft_inplace(filt, d.M2, d.M2, 1, 0, st);
     if (rc) return rc;
-    rc = fft_inplace(work, d.M2, d.M2, n_sig, 0, st);
+    rc = fft_inplace(workC, d.M2, d.M2, n_sig, 0, st);
     if (rc) return rc;
     {
         dim3 grid(grid_for(d.M2), n_sig);
         MMS_PROF_BEGIN(st);
-        cmul_kernel<<<grid, 256, 0, st>>>(work, filt, d.M2);
+        cmul_kernel<<<grid, 256, 0, st>>>(workC, filt, d.M2);
         MMS_LAUNCH_CHECK("cmul_kernel");
     }
-    rc = fft_inplace(work, d.M2, d.M2, n_sig, 1, st);
+    rc = fft_inplace(workC, d.M2, d.M2, n_sig, 1, st);
     if (rc) return rc;
     {
         dim3 grid(grid_for(d.num), n_sig);
         MMS_PROF_BEGIN(st);
-        czt_post_real_kernel<<<grid, 256, 0, st>>>(work, d.M2, d.num, y);
+        czt_post_real_kernel<<<grid, 256, 0, st>>>(workC, d.M2, d.num, y);
         MMS_LAUNCH_CHECK("czt_post_real_kernel");
     }
     return MMS_OK;

@@ -47,6 +47,30 @@ def test_resample_matches_scipy_semantics(n, num):
     err_ok(got, ref)
 
 
+@pytest.mark.parametrize("n_sig", [2, 5, 8])
+def test_resample_paired_transforms_equal_single_transforms(n_sig):
+    """csrc/resample.cu: two real signals per complex chirp-z transform (the default when it fits) against one transform per
+    signal (MMS_RESAMPLE_PAIRED=0) and against the numpy restatement of scipy.signal.resample; odd counts leave the last
+    signal alone in its pair."""
+    from multimodalsignal_b200 import _ext, preprocess as pp
+    lib = _ext.lib()
+    n, num = 70000 + 37, 6403
+    rng = np.random.default_rng(n_sig)
+    x = rng.standard_normal((n_sig, n)) * np.arange(1, n_sig + 1)[:, None] + np.arange(n_sig)[:, None]
+    xd = torch.from_numpy(x).cuda()
+    ref = np.stack([po.fft_resample(r, num) for r in x])
+    prev = lib.mms_get_option(b"RESAMPLE_PAIRED", -1)
+    try:
+        outs = {}
+        for mode in (1, 0):
+            _ext.check(lib.mms_set_option(b"RESAMPLE_PAIRED", mode))
+            outs[mode] = pp.resample_on_device(xd, num).cpu().numpy()
+            err_ok(outs[mode], ref)
+        assert np.abs(outs[1] - outs[0]).max() <= 1e-10 * max(1.0, np.abs(ref).max())
+    finally:
+        _ext.check(lib.mms_set_option(b"RESAMPLE_PAIRED", prev) if prev >= 0 else lib.mms_clear_option(b"RESAMPLE_PAIRED"))
+
+
 def test_resample_full_size_recording():
     """BASELINE-size stream: 700 Hz x 100 min + odd offset (N = 4 200 959 has a large prime factor)."""
     from multimodalsignal_b200 import preprocess as pp
