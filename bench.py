@@ -612,8 +612,10 @@ def preprocess_measure(args, subjects=None):
     # staged (pinned, threaded), copied up and resampled on the compute stream, the window array of subject i-1 travels back on
     # a copy stream into one of two pinned buffers (what run_preprocessing does with _NpyWriter, minus the file system)
     copy_stream = torch.cuda.Stream()
-    pinned = [None, None]
+    out_elems = int(max(n for _, n, _ in [process(*staged[i], protos[i], False) for i in range(len(subs))]) * window * 14 * 1.05)
+    pinned = [torch.empty(out_elems, dtype=torch.float64).pin_memory() for _ in range(2)]     # the caller's destination arrays
     pinned_free = [None, None]
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
     h2d = d2h = 0
     pending = None

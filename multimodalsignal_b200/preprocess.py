@@ -160,18 +160,21 @@ class _Uploader:
     """Host -> device staging for the raw recordings (4.2 M samples x 8 chest columns = 269 MB per subject).
 
     ``torch.from_numpy(rows).to(device)`` costs two pageable host copies plus a pageable H2D per subject -- more
-    than the resampling itself.  Here every sensor column is converted / de-interleaved ONCE, by a small thread pool
-    (numpy releases the GIL while copying), straight into one of two pinned staging buffers, and handed to ONE
-    asynchronous H2D copy per call; the second buffer lets the next subject's columns be staged while that copy runs.
-    ``groups`` stages several sensors of different lengths (chest + every wrist sensor of a subject) in one go: one
-    thread-pool barrier and one copy per subject instead of five.  The pinned buffers grow with 25 % headroom -- recordings
-    differ in length by a fraction of a percent, and re-pinning 270 MB costs ~100 ms."""
+    than the resampling itself.  Here every sensor column is converted / de-interleaved ONCE, in 8 MB pieces, by a small
+    thread pool (numpy releases the GIL while copying) into a ring of pinned chunks; each piece goes up with its own
+    asynchronous copy on a private upload stream as soon as it is staged, so the H2D copies of a subject overlap the staging
+    of its later pieces and the device work of the previous subject.  The ring is small (128 MB): page-locking a buffer for
+    a whole subject cost ~250 ms per buffer (measured), several times the staging itself.
+    ``groups`` stages several sensors of different lengths (chest + every wrist sensor of a subject) in one go."""
+
+    CHUNK = 1 << 20          # doubles per pinned chunk (8 MB)
+    RING = 16                # 128 MB of pinned memory in all
 
     def __init__(self):
-        self._buf = [None, None]
-        self._free = [None, None]        # event: the H2D that last read the buffer has finished
-        self._turn = 0
+        self._ring = None
+        self._events = [None] * self.RING
         self._pool = None
+        self._stream = {}
 
     @staticmethod
     def _columns(sensor_dict, names):
@@ -184,41 +187,50 @@ class _Uploader:
 
     def groups(self, column_groups, device):
         """``column_groups``: list of lists of equally long 1-D arrays.  Returns one float64 device tensor ``[len(group), n]``
-        per group (views of ONE device buffer filled by one asynchronous copy)."""
+        per group (views of ONE device buffer).  The caller's stream waits for the upload; the host does not."""
         import concurrent.futures as cf
-        offs, total = [], 0
+        offs, total, tasks = [], 0, []
         for cols in column_groups:
             n = len(cols[0])
             assert all(len(c) == n for c in cols), "the columns of a group must have the same length"
             offs.append(total)
+            for c, col in enumerate(cols):
+                for lo in range(0, n, self.CHUNK):
+                    tasks.append((total + c * n + lo, col[lo:lo + self.CHUNK]))
             total += len(cols) * n
             total += total & 1                       # keep every group 16-byte aligned
-        k = self._turn
-        self._turn ^= 1
-        if self._buf[k] is None or self._buf[k].numel() < total:
-            self._buf[k] = None
-            self._buf[k] = torch.empty(int(total * 1.25) + 1024, dtype=torch.float64).pin_memory()
-            self._free[k] = None
-        if self._free[k] is not None:
-            self._free[k].synchronize()
-        stage = self._buf[k][:total]
-        view = stage.numpy()
-        if self._pool is None:
+        if self._ring is None:
+            self._ring = torch.empty(self.RING * self.CHUNK, dtype=torch.float64).pin_memory()
             self._pool = cf.ThreadPoolExecutor(max_workers=min(12, max(4, (os.cpu_count() or 8) - 2)), thread_name_prefix="mms-upload")
-        jobs = []
-        for cols, off in zip(column_groups, offs):
-            n = len(cols[0])
-            step = max(1 << 16, -(-n // 4))          # quarter columns of the long recordings: 4 x n_ch independent copies
-            for c, col in enumerate(cols):
-                for lo in range(0, n, step):
-                    jobs.append(self._pool.submit(np.copyto, view[off + c * n + lo:off + c * n + min(n, lo + step)], col[lo:lo + step], "unsafe"))
-        for j in jobs:
-            j.result()
+        ring_np = self._ring.numpy()
         dev = torch.empty(total, dtype=torch.float64, device=device)
-        dev.copy_(stage, non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream())
-        self._free[k] = ev
+        key = (device.type, device.index)
+        if key not in self._stream:
+            self._stream[key] = torch.cuda.Stream(device=device)
+        up = self._stream[key]
+        up.wait_stream(torch.cuda.current_stream(device))           # `dev` may reuse memory the compute stream is still reading
+        futures = [None] * len(tasks)
+
+        def submit(t):
+            slot = t % self.RING
+            if self._events[slot] is not None:
+                self._events[slot].synchronize()                     # the copy that last read this chunk has finished
+            _, src = tasks[t]
+            futures[t] = self._pool.submit(np.copyto, ring_np[slot * self.CHUNK:slot * self.CHUNK + len(src)], src, "unsafe")
+
+        for t in range(min(self.RING, len(tasks))):
+            submit(t)
+        for t, (off, src) in enumerate(tasks):
+            futures[t].result()
+            slot = t % self.RING
+            with torch.cuda.stream(up):
+                dev[off:off + len(src)].copy_(self._ring[slot * self.CHUNK:slot * self.CHUNK + len(src)], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(up)
+            self._events[slot] = ev
+            if t + self.RING < len(tasks):
+                submit(t + self.RING)
+        torch.cuda.current_stream(device).wait_stream(up)
         return [dev[off:off + len(cols) * len(cols[0])].view(len(cols), len(cols[0])) for cols, off in zip(column_groups, offs)]
 
     def rows(self, sensor_dict, names, device):
@@ -239,7 +251,9 @@ class SubjectStreams:
     def __init__(self, sid, streams, starts, labels, window, channel_names):
         self.sid, self.streams, self.labels, self.window = sid, streams, labels, window
         self.starts_host = starts
-        self.starts = torch.from_numpy(starts).to(streams.device)
+        # pinned + non_blocking: a pageable copy would make the host wait for everything enqueued before it (the whole subject)
+        self.starts = torch.from_numpy(starts).pin_memory().to(streams.device, non_blocking=True) if streams.is_cuda and len(starts) \
+            else torch.from_numpy(starts).to(streams.device)
         self.channel_names = list(channel_names)
 
     def _ptr_array(self, idx):
