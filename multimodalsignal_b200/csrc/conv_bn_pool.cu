@@ -91,112 +91,6 @@ __global__ void __launch_bounds__(TL) conv1d_fwd_kernel(const float* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------
-// conv1d_fwd, second version (MMS_CONV_FWD_V2=1, experiment; written without GPU access at the end of round 1).
-// ncu on conv1d_fwd_kernel: 40 % of the stall samples are short_scoreboard (waiting for shared-memory loads) and 10 % mio:
-// per (input channel, tap) a thread issues 1 + CO/4 shared-memory loads for CO FFMAs.  Here a thread owns NP output
-// positions (tid + j * TL: the stores stay coalesced), so the CO/4 broadcast weight loads are shared by NP * CO FMAs, the
-// output channels are processed in pairs as packed fma.rn.f32x2 (FFMA2: weights (w[o], w[o+1]) against a broadcast x), and
-// the BatchNorm partial sums of a thread cover NP positions before the warp reduction (NP times fewer shuffles per output).
-// The (c, k) summation order per output is that of conv1d_fwd_kernel, so y is bit-identical; the statistics differ in
-// the last bits only (fp32 partial sums of NP values before the warp reduction).
-template <int CO, int KW, int S, int P, int TL, int NP>
-__global__ void __launch_bounds__(TL) conv1d_fwd_v2_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                           const float* __restrict__ gate, float* __restrict__ y,
-                                                           double* __restrict__ stats, int CI, int Lin, int Lout) {
-    MMS_PDL_PROLOGUE();
-    constexpr int TPOS = TL * NP;                 // output positions per CTA
-    constexpr int SPAN = (TPOS - 1) * S + KW;
-    static_assert(CO % 4 == 0 && TL % 32 == 0, "channel quads, whole warps");
-    extern __shared__ __align__(16) float smem[];
-    float* ws = smem;                             // [CI*KW][CO]
-    float* xs = smem + CI * KW * CO;              // [CI][SPAN]   (CI*KW*CO is a multiple of 4: ws rows stay 16-byte aligned)
-    __shared__ double red[TL / 32][2 * CO];
-
-    const int b = blockIdx.y, l0 = blockIdx.x * TPOS, tid = threadIdx.x;
-    const int in0 = l0 * S - P;
-    const float* xb = x + (size_t)b * CI * Lin;
-    for (int idx = tid; idx < CI * SPAN; idx += TL) {
-        const int c = idx / SPAN, i = idx - c * SPAN, gi = in0 + i;
-        const bool ok = gi >= 0 && gi < Lin;
-        cp_async4_zfill(xs + idx, xb + (size_t)c * Lin + (ok ? gi : 0), ok);
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-#pragma unroll 4
-    for (int idx = tid; idx < CO * CI * KW; idx += TL) {
-        const int o = idx / (CI * KW), ck = idx - o * (CI * KW), c = ck / KW;
-        const float g = gate ? gate[b * CI + c] : 1.f;
-        ws[ck * CO + o] = w[idx] * g;
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-
-    float2 acc[NP][CO / 2];
-#pragma unroll
-    for (int j = 0; j < NP; ++j)
-#pragma unroll
-        for (int o2 = 0; o2 < CO / 2; ++o2) acc[j][o2] = make_float2(0.f, 0.f);
-    const float* xr = xs + tid * S;
-    for (int c = 0; c < CI; ++c) {
-#pragma unroll
-        for (int k = 0; k < KW; ++k) {
-            float xv[NP];
-#pragma unroll
-            for (int j = 0; j < NP; ++j) xv[j] = xr[c * SPAN + j * (TL * S) + k];
-            const float4* wv = reinterpret_cast<const float4*>(ws + (c * KW + k) * CO);
-#pragma unroll
-            for (int o4 = 0; o4 < CO / 4; ++o4) {
-                const float4 wq = wv[o4];
-                const float2 wa = make_float2(wq.x, wq.y), wb = make_float2(wq.z, wq.w);
-#pragma unroll
-                for (int j = 0; j < NP; ++j) {
-                    const float2 xx = make_float2(xv[j], xv[j]);
-                    acc[j][2 * o4] = __ffma2_rn(wa, xx, acc[j][2 * o4]);
-                    acc[j][2 * o4 + 1] = __ffma2_rn(wb, xx, acc[j][2 * o4 + 1]);
-                }
-            }
-        }
-    }
-    bool valid[NP];
-#pragma unroll
-    for (int j = 0; j < NP; ++j) {
-        const int l = l0 + tid + j * TL;
-        valid[j] = l < Lout;
-        if (valid[j]) {
-            float* yb = y + (size_t)b * CO * Lout + l;
-#pragma unroll
-            for (int o2 = 0; o2 < CO / 2; ++o2) {
-                yb[(size_t)(2 * o2) * Lout] = acc[j][o2].x;
-                yb[(size_t)(2 * o2 + 1) * Lout] = acc[j][o2].y;
-            }
-        }
-    }
-    if (stats) {
-        const int warp = tid >> 5, lane = tid & 31;
-#pragma unroll
-        for (int o2 = 0; o2 < CO / 2; ++o2) {
-            float sx = 0.f, sy = 0.f, qx = 0.f, qy = 0.f;
-#pragma unroll
-            for (int j = 0; j < NP; ++j) {
-                const float vx = valid[j] ? acc[j][o2].x : 0.f, vy = valid[j] ? acc[j][o2].y : 0.f;
-                sx += vx; sy += vy;
-                qx = fmaf(vx, vx, qx); qy = fmaf(vy, vy, qy);
-            }
-            sx = warp_sum(sx); sy = warp_sum(sy); qx = warp_sum(qx); qy = warp_sum(qy);
-            if (lane == 0) {
-                red[warp][2 * o2] = (double)sx; red[warp][2 * o2 + 1] = (double)sy;
-                red[warp][CO + 2 * o2] = (double)qx; red[warp][CO + 2 * o2 + 1] = (double)qy;
-            }
-        }
-        __syncthreads();
-        if (tid < 2 * CO) {
-            double t = 0.0;
-#pragma unroll
-            for (int wq = 0; wq < TL / 32; ++wq) t += red[wq][tid];
-            atomicAdd(stats + tid, t);
-        }
-    }
-}
-
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ float pooled_value(const float* __restrict__ row, int j, int Lin, float a, float bsh) {
     float m = -INFINITY;
@@ -478,126 +372,6 @@ __global__ void __launch_bounds__(TI) conv1d_dgrad_kernel(const float* __restric
     }
 }
 
-// conv1d_dgrad, second version (MMS_CONV_DGRAD_V2=1, experiment; written without GPU access at the end of round 1).  As
-// conv1d_fwd_v2_kernel: a thread owns NP input positions (tid + j * TI, all of one parity because TI is even, hence the same
-// kernel taps), so the CPAD/4 broadcast weight loads of a (tap, output channel) pair serve NP * CPAD FMAs, and the input
-// channels are processed in pairs as packed fma.rn.f32x2.  The (k, o) summation order per element is that of
-// conv1d_dgrad_kernel: dx is bit-identical, dgate differs in the last bits (fp32 partial sums over NP positions).
-template <int CO, int KW, int S, int P, int TI, int CPAD, int NP>
-__global__ void __launch_bounds__(TI) conv1d_dgrad_v2_kernel(const float* __restrict__ dy, const float* __restrict__ w,
-                                                             float* __restrict__ dx, const float* __restrict__ xdot,
-                                                             float* __restrict__ dgate, int CI, int Lin, int Lout, const BnBwd bn) {
-    MMS_PDL_PROLOGUE();
-    static_assert(S == 2 && TI % 2 == 0, "stride-2 convolutions; the positions of a thread share their parity");
-    static_assert(CO <= TI && CPAD % 4 == 0, "one thread per output channel for the BN constants; channel quads");
-    constexpr int TPOS = TI * NP;
-    constexpr int NL = (TPOS - 1 + KW - 1) / S + 2;
-    extern __shared__ __align__(16) float smem[];
-    float* ws = smem;                    // [KW][CO][CPAD]
-    float* dys = smem + KW * CO * CPAD;  // [CO][NL]
-    float* ys = dys + CO * NL;           // [CO][NL], only with the folded BatchNorm backward
-    __shared__ float red[TI / 32][CPAD];
-    __shared__ float s_bn[CO][5];
-    if (bn.y) bn_bwd_constants<CO>(bn, Lout, s_bn);
-
-    const int b = blockIdx.y, i0 = blockIdx.x * TPOS, tid = threadIdx.x;
-    const int lbase = floor_div2(i0 + P - (KW - 1));
-    const float* dyb = dy + (size_t)b * CO * Lout;
-    for (int idx = tid; idx < CO * NL; idx += TI) {
-        const int o = idx / NL, ll = idx - o * NL, l = lbase + ll;
-        const bool ok = l >= 0 && l < Lout;
-        cp_async4_zfill(dys + idx, dyb + (size_t)o * Lout + (ok ? l : 0), ok);
-        if (bn.y) cp_async4_zfill(ys + idx, bn.y + (size_t)b * CO * Lout + (size_t)o * Lout + (ok ? l : 0), ok);
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-#pragma unroll 4
-    for (int idx = tid; idx < KW * CO * CPAD; idx += TI) {
-        const int c = idx % CPAD, ko = idx / CPAD, o = ko % CO, k = ko / CO;
-        ws[idx] = c < CI ? __ldg(w + ((size_t)o * CI + c) * KW + k) : 0.f;
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-    if (bn.y) {          // dyn -> dy in place (positions outside the tensor stay zero)
-        for (int idx = tid; idx < CO * NL; idx += TI) {
-            const int o = idx / NL, l = lbase + (idx - o * NL);
-            if (l >= 0 && l < Lout)
-                dys[idx] = s_bn[o][0] * (dys[idx] - s_bn[o][3] - (ys[idx] - s_bn[o][1]) * s_bn[o][2] * s_bn[o][4]);
-        }
-        __syncthreads();
-    }
-
-    const int ibase = i0 + tid;
-    float2 acc[NP][CPAD / 2];
-#pragma unroll
-    for (int j = 0; j < NP; ++j)
-#pragma unroll
-        for (int c2 = 0; c2 < CPAD / 2; ++c2) acc[j][c2] = make_float2(0.f, 0.f);
-    for (int k = (ibase + P) & 1; k < KW; k += S) {
-        // ibase + P - k is even (may be negative: staged as zero); position j sits TI / S tile entries further
-        const int ll0 = (ibase + P - k) / S - lbase;
-        int llc[NP];
-        float keep[NP];
-#pragma unroll
-        for (int j = 0; j < NP; ++j) {
-            const int ll = ll0 + j * (TI / S);
-            const bool ok = ll >= 0 && ll < NL;
-            llc[j] = ok ? ll : 0;
-            keep[j] = ok ? 1.f : 0.f;
-        }
-        for (int o = 0; o < CO; ++o) {
-            float d[NP];
-#pragma unroll
-            for (int j = 0; j < NP; ++j) d[j] = dys[o * NL + llc[j]] * keep[j];
-            const float4* wv = reinterpret_cast<const float4*>(ws + (k * CO + o) * CPAD);
-#pragma unroll
-            for (int c4 = 0; c4 < CPAD / 4; ++c4) {
-                const float4 wq = wv[c4];
-                const float2 wa = make_float2(wq.x, wq.y), wb = make_float2(wq.z, wq.w);
-#pragma unroll
-                for (int j = 0; j < NP; ++j) {
-                    const float2 dd = make_float2(d[j], d[j]);
-                    acc[j][2 * c4] = __ffma2_rn(wa, dd, acc[j][2 * c4]);
-                    acc[j][2 * c4 + 1] = __ffma2_rn(wb, dd, acc[j][2 * c4 + 1]);
-                }
-            }
-        }
-    }
-    bool valid[NP];
-#pragma unroll
-    for (int j = 0; j < NP; ++j) {
-        const int i = ibase + j * TI;
-        valid[j] = i < Lin;
-        if (dx && valid[j]) {
-#pragma unroll
-            for (int c2 = 0; c2 < CPAD / 2; ++c2) {
-                if (2 * c2 < CI) dx[((size_t)b * CI + 2 * c2) * Lin + i] = acc[j][c2].x;
-                if (2 * c2 + 1 < CI) dx[((size_t)b * CI + 2 * c2 + 1) * Lin + i] = acc[j][c2].y;
-            }
-        }
-    }
-    if (xdot) {
-        const int warp = tid >> 5, lane = tid & 31;
-#pragma unroll
-        for (int c = 0; c < CPAD; ++c) {
-            float v = 0.f;
-#pragma unroll
-            for (int j = 0; j < NP; ++j) {
-                const float a = (c & 1) ? acc[j][c / 2].y : acc[j][c / 2].x;
-                if (valid[j] && c < CI) v = fmaf(a, __ldg(xdot + ((size_t)b * CI + c) * Lin + ibase + j * TI), v);
-            }
-            v = warp_sum(v);
-            if (lane == 0) red[warp][c] = v;
-        }
-        __syncthreads();
-        if (tid < CI) {
-            float t = 0.f;
-#pragma unroll
-            for (int wq = 0; wq < TI / 32; ++wq) t += red[wq][tid];
-            atomicAdd(dgate + b * CI + tid, t);
-        }
-    }
-}
-
 // dw[o,c,k] += gate[b,c] * sum_l dy[b,o,l] * x[b,c,S*l+k-P]
 // One CTA = one batch row x TLW output positions, staged in shared memory.  A thread owns one input channel c, one group
 // of 16 output channels and every NPL-th position of the tile: its 16 x KW partial sums live in registers, so a position
@@ -716,24 +490,6 @@ static int conv_fwd_launch(const float* x, const float* w, const float* gate, in
     return MMS_OK;
 }
 
-template <int CO, int KW, int S, int P, int TL, int NP>
-static int conv_fwd_v2_launch(const float* x, const float* w, const float* gate, int B, int CI, int Lin, float* y,
-                              double* stats, cudaStream_t st) {
-    static_assert(2 * CO <= TL, "the statistics epilogue needs 2 * CO threads");
-    const int Lout = conv_out_len(Lin, KW, S, P);
-    constexpr int SPAN = (TL * NP - 1) * S + KW;
-    const size_t smem = (size_t)(CI * KW * CO + CI * SPAN) * sizeof(float);
-    auto kern = conv1d_fwd_v2_kernel<CO, KW, S, P, TL, NP>;
-    static PerDeviceOnce attr_once;
-    if (attr_once.need()) { MMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); }
-    MMS_REQUIRE(smem <= 96 * 1024, "conv1d_fwd_v2: shared memory %zu too large", smem);
-    dim3 grid(cdiv(Lout, TL * NP), B);
-    MMS_PROF_BEGIN(st);
-    MMS_LAUNCH(kern, grid, dim3(TL), smem, st, x, w, gate, y, stats, CI, Lin, Lout);
-    MMS_LAUNCH_CHECK("conv1d_fwd_kernel");
-    return MMS_OK;
-}
-
 template <int CO, int KW, int S, int P, int TI, int CPAD>
 static int conv_dgrad_launch_pad(const float* dy, const float* w, int B, int CI, int Lin, float* dx, const float* xdot,
                                  float* dgate, cudaStream_t st, const BnBwd& bn) {
@@ -744,23 +500,6 @@ static int conv_dgrad_launch_pad(const float* dy, const float* w, int B, int CI,
     static PerDeviceOnce attr_once;
     if (attr_once.need()) { MMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); }
     dim3 grid(cdiv(Lin, TI), B);
-    MMS_PROF_BEGIN(st);
-    MMS_LAUNCH(kern, grid, dim3(TI), smem, st, dy, w, dx, xdot, dgate, CI, Lin, Lout, bn);
-    MMS_LAUNCH_CHECK("conv1d_dgrad_kernel");
-    return MMS_OK;
-}
-
-template <int CO, int KW, int S, int P, int TI, int CPAD, int NP>
-static int conv_dgrad_v2_launch_pad(const float* dy, const float* w, int B, int CI, int Lin, float* dx, const float* xdot,
-                                    float* dgate, cudaStream_t st, const BnBwd& bn) {
-    const int Lout = conv_out_len(Lin, KW, S, P);
-    constexpr int NL = (TI * NP - 1 + KW - 1) / S + 2;
-    const size_t smem = (size_t)(KW * CO * CPAD + (bn.y ? 2 : 1) * CO * NL) * sizeof(float);
-    auto kern = conv1d_dgrad_v2_kernel<CO, KW, S, P, TI, CPAD, NP>;
-    static PerDeviceOnce attr_once;
-    if (attr_once.need()) { MMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); }
-    MMS_REQUIRE(smem <= 96 * 1024, "conv1d_dgrad_v2: shared memory %zu too large", smem);
-    dim3 grid(cdiv(Lin, TI * NP), B);
     MMS_PROF_BEGIN(st);
     MMS_LAUNCH(kern, grid, dim3(TI), smem, st, dy, w, dx, xdot, dgate, CI, Lin, Lout, bn);
     MMS_LAUNCH_CHECK("conv1d_dgrad_kernel");
@@ -823,10 +562,6 @@ int launch_conv_fwd(int which, const float* x, const float* w, const float* gate
     if (rc) return rc;
     if (conv_use_tc() && conv_fwd_tc_supported(which, x, c_in, c_out, l_in))     // implicit GEMM on tcgen05 (conv_tc.cu)
         return launch_conv_fwd_tc(which, x, w, gate, B, c_in, c_out, l_in, y, stats, st);
-    if (option_get("CONV_FWD_V2", 0) == 1) {      // experiment: NP = 2 positions per thread, FFMA2 channel pairs
-        if (which == 1) return conv_fwd_v2_launch<16, CONV1_K, CONV1_S, CONV1_P, 128, 2>(x, w, gate, B, c_in, l_in, y, stats, st);
-        if (c_out == 32) return conv_fwd_v2_launch<32, CONV2_K, CONV2_S, CONV2_P, 64, 2>(x, w, gate, B, c_in, l_in, y, stats, st);
-    }
     if (which == 1) return conv_fwd_launch<16, CONV1_K, CONV1_S, CONV1_P, 256>(x, w, gate, B, c_in, l_in, y, stats, st);
     if (c_out == 16) return conv_fwd_launch<16, CONV2_K, CONV2_S, CONV2_P, 128>(x, w, gate, B, c_in, l_in, y, stats, st);
     if (c_out == 32) return conv_fwd_launch<32, CONV2_K, CONV2_S, CONV2_P, 128>(x, w, gate, B, c_in, l_in, y, stats, st);
@@ -840,12 +575,6 @@ int launch_conv_dgrad(int which, const float* dy, const float* w, int B, int c_i
     int rc = check_conv(which, c_in, c_out);
     if (rc) return rc;
     const BnBwd& bn = bnp ? *bnp : NO_BN;
-    if (option_get("CONV_DGRAD_V2", 0) == 1) {     // experiment: NP = 2 positions per thread, FFMA2 channel pairs
-        if (which == 1 && c_in <= 8)
-            return conv_dgrad_v2_launch_pad<16, CONV1_K, CONV1_S, CONV1_P, 128, 8, 2>(dy, w, B, c_in, l_in, dx, xdot, dgate, st, bn);
-        if (which == 2 && c_out == 32)
-            return conv_dgrad_v2_launch_pad<32, CONV2_K, CONV2_S, CONV2_P, 64, 16, 2>(dy, w, B, c_in, l_in, dx, xdot, dgate, st, bn);
-    }
     if (which == 1) return conv_dgrad_launch<16, CONV1_K, CONV1_S, CONV1_P, 256>(dy, w, B, c_in, l_in, dx, xdot, dgate, st, bn);
     if (c_out == 16) return conv_dgrad_launch<16, CONV2_K, CONV2_S, CONV2_P, 128>(dy, w, B, c_in, l_in, dx, xdot, dgate, st, bn);
     if (c_out == 32) return conv_dgrad_launch<32, CONV2_K, CONV2_S, CONV2_P, 128>(dy, w, B, c_in, l_in, dx, xdot, dgate, st, bn);

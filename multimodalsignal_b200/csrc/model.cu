@@ -54,13 +54,6 @@ int launch_conv2_w_relayout(const float*, float*, cudaStream_t);
 int64_t conv2_w_relayout_floats();
 int launch_conv1_bwd(const float*, const float*, const float*, const float*, const float*, const float*, const float*, int, int, int,
                      float*, int*, float*, float*, float*, cudaStream_t, const BnBwd*);
-bool pool_bwd_tile_supported(int, int);
-int launch_pool_relu_bwd_tile(const float*, const double*, const float*, const float*, const float*, const float*, const float*, int, int,
-                              int, int, int, float*, double*, cudaStream_t, int);
-int launch_conv2_dgrad_v3(const float*, const float*, int, int, int, float*, cudaStream_t, const BnBwd*);
-bool conv1_wgrad_dgate_supported(const float*, int, int);
-int launch_conv1_wgrad_dgate(const float*, const float*, const float*, const float*, const float*, const float*, const float*, int, int,
-                             int, float*, float*, float*, cudaStream_t, const BnBwd*);
 int launch_attn_conv1_fwd(const float*, const float*, const float*, const float*, int, int, int, int, float*, float*, float*, double*,
                           cudaStream_t);
 int launch_bn_pool_conv2_fwd(const float*, const double*, const float*, const float*, float*, float*, int64_t*, int, int, const float*,
@@ -499,11 +492,8 @@ static int model_backward(const mms_cnngru_desc* d, const float* x, const float*
     const float p = m.p;
 
     const float gscale = (float)m.B / (float)m.Bg;       // share of the global BN affine gradient this rank adds
-    // tile / cluster kernels of conv_fused_bwd.cu: T % 8 == 0, BatchNorm backward folded, no input gradient requested
-    const bool fused_bwd = bn_fold() && !dx && option_get("CONV_BWD_FUSED", 0) == 1 && conv1_wgrad_dgate_supported(x, m.C, m.T) &&
-                           pool_bwd_tile_supported(m.O, 1);
     // conv_bwd.cu (the default when the shapes allow it): T % 32 == 0, C_out == 32, BatchNorm backward folded, no input gradient
-    const bool bwd2 = !fused_bwd && bn_fold() && !dx && option_get("CONV_BWD", 1) == 1 && conv_bwd_supported(x, m.C, m.T, m.O);
+    const bool bwd2 = bn_fold() && !dx && option_get("CONV_BWD", 1) == 1 && conv_bwd_supported(x, m.C, m.T, m.O);
     Forker fk(st);
     if (phases & 1) {
     MMS_CUDA(cudaMemsetAsync(w.bwd_zero, 0, w.bwd_zero_bytes, st));
@@ -690,9 +680,6 @@ static int model_backward(const mms_cnngru_desc* d, const float* x, const float*
     if (bwd2)
         rc = launch_pool_bwd_tm(w.y2, w.stats2, P + po.bn2_g, P + po.bn2_b, rm2, rv2, dxcur, B, m.O, m.L2c, m.training, w.dy2, w.red2, st,
                                 m.Bg);
-    else if (fused_bwd)
-        rc = launch_pool_relu_bwd_tile(w.y2, w.stats2, P + po.bn2_g, P + po.bn2_b, rm2, rv2, dxcur, B, m.O, m.L2c, m.training, 1, w.dy2,
-                                       w.red2, st, m.Bg);
     else
         rc = launch_bn_relu_pool_bwd(w.y2, w.stats2, P + po.bn2_g, P + po.bn2_b, rm2, rv2, dxcur, B, m.O, m.L2c, m.training, 1, w.dy2,
                                      G + po.bn2_g, G + po.bn2_b, w.red2, st, 1, m.Bg, gscale);
@@ -729,17 +716,10 @@ static int model_backward(const mms_cnngru_desc* d, const float* x, const float*
         } else {
         rc = launch_conv_wgrad(2, w.p1, w.dy2, nullptr, B, CONV2_CI, m.O, m.P1, G + po.conv2_w, fk.fork(0), &bn2w);
         if (rc) return rc;
-        if (fused_bwd) {
-            rc = launch_conv2_dgrad_v3(w.dy2, P + po.conv2_w, B, m.O, m.P1, w.dp1, st, &bn2d);
-            if (rc) return rc;
-            rc = launch_pool_relu_bwd_tile(w.y1, w.stats1, P + po.bn1_g, P + po.bn1_b, rm1, rv1, w.dp1, B, CONV1_CO, m.L1c, m.training, 0,
-                                           w.dy1, w.red1, st, m.Bg);
-        } else {
-            rc = launch_conv_dgrad(2, w.dy2, P + po.conv2_w, B, CONV2_CI, m.O, m.P1, w.dp1, nullptr, nullptr, st, &bn2d);
-            if (rc) return rc;
-            rc = launch_bn_relu_pool_bwd(w.y1, w.stats1, P + po.bn1_g, P + po.bn1_b, rm1, rv1, w.dp1, B, CONV1_CO, m.L1c, m.training, 0,
-                                         w.dy1, G + po.bn1_g, G + po.bn1_b, w.red1, st, 1, m.Bg, gscale);
-        }
+        rc = launch_conv_dgrad(2, w.dy2, P + po.conv2_w, B, CONV2_CI, m.O, m.P1, w.dp1, nullptr, nullptr, st, &bn2d);
+        if (rc) return rc;
+        rc = launch_bn_relu_pool_bwd(w.y1, w.stats1, P + po.bn1_g, P + po.bn1_b, rm1, rv1, w.dp1, B, CONV1_CO, m.L1c, m.training, 0,
+                                     w.dy1, G + po.bn1_g, G + po.bn1_b, w.red1, st, 1, m.Bg, gscale);
         if (rc) return rc;
         }
     }
@@ -749,14 +729,6 @@ static int model_backward(const mms_cnngru_desc* d, const float* x, const float*
         const BnBwd bn1f = {w.y1, w.stats1, P + po.bn1_g, P + po.bn1_b, rm1, rv1, w.red1, G + po.bn1_g, G + po.bn1_b, m.Bg, m.training, gscale};
         rc = launch_conv1_bwd(x, w.dy1, P + po.conv1_w, m.attention ? w.gate : nullptr, w.mean, P + po.ca_w1, P + po.ca_w2, B, m.C, m.T,
                               w.c1_part, w.row_counter, G + po.conv1_w, G + po.ca_w1, G + po.ca_w2, st, &bn1f);
-        if (rc) return rc;
-        return fk.join();
-    }
-    if (fused_bwd) {
-        // conv1 weight gradient, attention-gate gradient and the ChannelAttention parameter gradients in one cluster launch
-        const BnBwd bn1f = {w.y1, w.stats1, P + po.bn1_g, P + po.bn1_b, rm1, rv1, w.red1, G + po.bn1_g, G + po.bn1_b, m.Bg, m.training, gscale};
-        rc = launch_conv1_wgrad_dgate(x, w.dy1, P + po.conv1_w, m.attention ? w.gate : nullptr, w.mean, P + po.ca_w1, P + po.ca_w2, B, m.C,
-                                      m.T, G + po.conv1_w, G + po.ca_w1, G + po.ca_w2, st, &bn1f);
         if (rc) return rc;
         return fk.join();
     }
