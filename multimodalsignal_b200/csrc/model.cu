@@ -59,6 +59,9 @@ int launch_attn_conv1_fwd(const float*, const float*, const float*, const float*
 int launch_bn_pool_conv2_fwd(const float*, const double*, const float*, const float*, float*, float*, int64_t*, int, int, const float*,
                              int, int, int, float*, float*, double*, cudaStream_t);
 int launch_tc_gemm_nt(const float*, int64_t, const float*, int64_t, const float*, float*, int64_t, int, int, int, int, cudaStream_t);
+int launch_tc_gemm_nt_drop(const float*, int64_t, const float*, int64_t, const float*, float*, int64_t, int, int, int, int, cudaStream_t,
+                           float, uint64_t, uint64_t, const int64_t*, int64_t, int);
+bool tc_gemm_nt_drop_supported(const float*, int64_t, int);
 bool tc_gemm_supported(const float*, int64_t, const float*, int64_t, int, int, int);
 constexpr int TC_MIN_ROWS = 1024;      // below this a single tcgen05 CTA is pure latency: the SIMT kernels win
 int launch_transpose_pad(const float*, int, int, float*, int64_t, int, cudaStream_t);
@@ -412,6 +415,7 @@ static int model_forward(const mms_cnngru_desc* d, const float* x, const float* 
 
     const float* in = w.seq;
     int I = m.O;
+    bool drop_on_a = false;
     for (int l = 0; l < m.layers - 1; ++l) {
         rc = gemm_nt(in, I, P + po.w_ih[l], I, P + po.b_ih[l], w.gi[l], 6 * H, (int)M, 6 * H, I, st);
         if (rc) return rc;
@@ -429,7 +433,13 @@ static int model_forward(const mms_cnngru_desc* d, const float* x, const float* 
         }
         rc = launch_gru_fwd(dirs, 2, B, H, m.p, d->rng_seed, d->rng_offset, d->rng_offset_dev, st);
         if (rc) return rc;
-        if (m.drop_gru) {      // models.py:62: dropout on the outputs of every layer but the last
+        // models.py:62: dropout on the outputs of every layer but the last.  For the layer under the top one the multipliers
+        // can ride on the A operand of the top layer's input projection (tc_gemm_nt, drop_on_a): the streaming pass that
+        // materialises the dropped tensor for the other consumers (the single reverse step, the weight gradients) then runs
+        // on a side stream beside that product instead of in front of it (MMS_DROP_FUSED=0: the separate pass).
+        drop_on_a = m.drop_gru && l == m.layers - 2 && option_get("DROP_FUSED", 1) == 1 && use_tc() && M >= TC_MIN_ROWS &&
+                    tc_gemm_supported(w.hs[l], 2 * H, P + po.w_ih[l + 1], 2 * H, (int)M, 3 * H, 2 * H);
+        if (m.drop_gru && !drop_on_a) {
             rc = launch_dropout_apply(w.hs[l], w.outd[l], M * 2 * H, (int64_t)l * DROP_LAYER_STRIDE, m.p, d->rng_seed,
                                       d->rng_offset, d->rng_offset_dev, st);
             if (rc) return rc;
@@ -440,10 +450,20 @@ static int model_forward(const mms_cnngru_desc* d, const float* x, const float* 
     {   // top layer: forward direction over the whole sequence, reverse direction for its first step only
         const int l = m.layers - 1;
         Forker fkf(st);
+        cudaStream_t s_side = fkf.fork(0);
+        if (drop_on_a) {
+            rc = launch_dropout_apply(w.hs[l - 1], w.outd[l - 1], M * 2 * H, (int64_t)(l - 1) * DROP_LAYER_STRIDE, m.p, d->rng_seed,
+                                      d->rng_offset, d->rng_offset_dev, s_side);
+            if (rc) return rc;
+        }
         rc = gemm_nt(in + (int64_t)(L - 1) * I, (int64_t)L * I, P + po.w_ih[l] + (int64_t)3 * H * I, I,
-                     P + po.b_ih[l] + 3 * H, w.gi_tr, 3 * H, B, 3 * H, I, fkf.fork(0));     // B rows: beside the big one
+                     P + po.b_ih[l] + 3 * H, w.gi_tr, 3 * H, B, 3 * H, I, s_side);     // B rows: beside the big one
         if (rc) return rc;
-        rc = gemm_nt(in, I, P + po.w_ih[l], I, P + po.b_ih[l], w.gi_tf, 3 * H, (int)M, 3 * H, I, st);
+        if (drop_on_a)
+            rc = launch_tc_gemm_nt_drop(w.hs[l - 1], I, P + po.w_ih[l], I, P + po.b_ih[l], w.gi_tf, 3 * H, (int)M, 3 * H, I, 0, st, m.p,
+                                        d->rng_seed, d->rng_offset, d->rng_offset_dev, (int64_t)(l - 1) * DROP_LAYER_STRIDE, 1);
+        else
+            rc = gemm_nt(in, I, P + po.w_ih[l], I, P + po.b_ih[l], w.gi_tf, 3 * H, (int)M, 3 * H, I, st);
         if (rc) return rc;
         rc = fkf.join();
         if (rc) return rc;
@@ -532,6 +552,7 @@ static int model_backward(const mms_cnngru_desc* d, const float* x, const float*
     const int I_top = top == 0 ? m.O : 2 * H;
     float* dxcur = w.dxa;
     float* dxnext = w.dxb;
+    int drop_done_for = -1;        // layer whose output-dropout gradient has already been applied by a GEMM epilogue
     // Weight gradients of the top layer: side stream 0, forked from wherever this is called.  MMS_WGRAD_DEFER=1 (experiment)
     // forks them after the NEXT layer's recurrence has been enqueued instead of right after the top one, so that they overlap
     // the conv backward chain rather than the layer-0 recurrence (whose CTAs lose issue slots to co-resident GEMM CTAs).
@@ -588,7 +609,15 @@ static int model_backward(const mms_cnngru_desc* d, const float* x, const float*
             // tensor-core path: dx = D @ W_ih as an NT product against the transposed weights
             rc = fk.join_one(1);          // the transposed weights (side stream 1) are needed from here on
             if (rc) return rc;
-            rc = launch_tc_gemm_nt(w.D_tf, 4 * H, w.wT_top, 3 * H, nullptr, dxcur, I_top, M, I_top, 3 * H, 0, st);
+            // the gradient through the dropout between layer top-1 and top (same multipliers as the forward) rides on this
+            // product's epilogue instead of a separate pass over dxcur
+            if (top >= 1 && m.drop_gru && option_get("DROP_FUSED", 1) == 1 && tc_gemm_nt_drop_supported(dxcur, I_top, I_top)) {
+                rc = launch_tc_gemm_nt_drop(w.D_tf, 4 * H, w.wT_top, 3 * H, nullptr, dxcur, I_top, M, I_top, 3 * H, 0, st, p, d->rng_seed,
+                                            d->rng_offset, d->rng_offset_dev, (int64_t)(top - 1) * DROP_LAYER_STRIDE, 0);
+                drop_done_for = top - 1;
+            } else {
+                rc = launch_tc_gemm_nt(w.D_tf, 4 * H, w.wT_top, 3 * H, nullptr, dxcur, I_top, M, I_top, 3 * H, 0, st);
+            }
             if (rc) return rc;
         } else {
             rc = launch_gemm_nn(w.D_tf, 4 * H, P + po.w_ih[top], I_top, dxcur, I_top, M, I_top, 3 * H, 0, st);
@@ -604,7 +633,7 @@ static int model_backward(const mms_cnngru_desc* d, const float* x, const float*
     for (int l = top - 1; l >= 0; --l) {
         const float* in_l = l == 0 ? w.seq : w.outd[l - 1];
         const int I_l = l == 0 ? m.O : 2 * H;
-        if (m.drop_gru) {      // gradient through the dropout between layer l and l + 1 (same multipliers)
+        if (m.drop_gru && drop_done_for != l) {      // gradient through the dropout between layer l and l + 1 (same multipliers)
             rc = launch_dropout_apply(dxcur, dxcur, (int64_t)M * 2 * H, (int64_t)l * DROP_LAYER_STRIDE, p, d->rng_seed,
                                       d->rng_offset, d->rng_offset_dev, st);
             if (rc) return rc;

@@ -22,6 +22,16 @@ struct TcGemmParams {
     const float* bias;
     int64_t ldc;
     int M, N, K, BN, accumulate;
+    // optional dropout on the OUTPUT (the gradient through nn.GRU's inter-layer dropout, models.py:62): C[m][n] is multiplied by
+    // the multiplier of element drop_base + m * ldc + n of the counter-based stream (mms_common.cuh) -- what a separate
+    // dropout_apply pass over C would do, without the extra launch and the read + write of C.  drop_p == 0: off.
+    // drop_on_a: the multipliers go onto the A operand instead (element drop_base + m * drop_lda + k), while it is split for the
+    // tensor core: the product then reads the UN-dropped tensor and a separate dropout pass leaves the critical path.
+    float drop_p;
+    uint64_t drop_seed, drop_offset;
+    const int64_t* drop_offset_dev;
+    int64_t drop_base, drop_lda;
+    int drop_on_a;
 };
 
 // dynamic smem: [stage][A_hi | A_lo | B_hi | B_lo] (1024-byte aligned tiles)
@@ -101,6 +111,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const __grid_
     } else {
         // ===== operand splitters (warps 2..5), then epilogue =====
         const int t = threadIdx.x - 64;                // 0..127
+        DropRng rng_a;
+        const bool drop_a = p.drop_p > 0.f && p.drop_on_a;
+        if (drop_a) rng_a.init(p.drop_seed, resolve_offset(p.drop_offset, p.drop_offset_dev), p.drop_p);
         for (int kb = 0; kb < nkb; ++kb) {
             const int s = kb % TC_STAGES, round = kb / TC_STAGES;
             mbar_wait(&full_bar[s], round & 1);
@@ -110,7 +123,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const __grid_
                 float4* hi = reinterpret_cast<float4*>(st);
                 float4* lo = reinterpret_cast<float4*>(st + a_bytes);
                 for (int i = t; i < (int)(a_bytes / 16); i += 128) {
-                    const float4 v = hi[i];
+                    float4 v = hi[i];
+                    if (drop_a) {
+                        // 128-byte swizzle: row r of the tile holds its 16-byte chunk c at position c ^ (r & 7)
+                        const int r = i >> 3, c = (i & 7) ^ (r & 7);
+                        const uint64_t e = (uint64_t)(p.drop_base + (int64_t)(m0 + r) * p.drop_lda + kb * TC_BK + 4 * c);
+                        v.x *= rng_a.mult(e); v.y *= rng_a.mult(e + 1); v.z *= rng_a.mult(e + 2); v.w *= rng_a.mult(e + 3);
+                    }
                     float4 h, l;
                     h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
                     h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
@@ -152,6 +171,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const __grid_
             // start; fetching it here from global memory was the largest stall).
             float* tb = reinterpret_cast<float*>(base) + (warp - 2) * (32 * 36);
             const int rbase = m0 + quarter * 32;
+            DropRng rng;
+            const bool drop = p.drop_p > 0.f && !p.drop_on_a;
+            if (drop) rng.init(p.drop_seed, resolve_offset(p.drop_offset, p.drop_offset_dev), p.drop_p);
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 const int wcols = min(32, BN - c0);           // 32 or 16 (BN is a multiple of 16)
                 uint32_t r[32];
@@ -188,6 +210,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const __grid_
                         if (rbase + rr < p.M) {
                             float4 v = *reinterpret_cast<const float4*>(tb + rr * 36 + 4 * col4);
                             v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+                            if (drop) {
+                                const uint64_t e = (uint64_t)(p.drop_base + (int64_t)(rbase + rr) * p.ldc + n);
+                                v.x *= rng.mult(e); v.y *= rng.mult(e + 1); v.z *= rng.mult(e + 2); v.w *= rng.mult(e + 3);
+                            }
                             *reinterpret_cast<float4*>(p.C + (int64_t)(rbase + rr) * p.ldc + n) = v;
                         }
                     }
@@ -240,9 +266,27 @@ bool tc_gemm_supported(const float* A, int64_t lda, const float* W, int64_t ldw,
            lda % 4 == 0 && ldw % 4 == 0 && M >= 1 && N >= 1 && K >= 1;
 }
 
+// true when launch_tc_gemm_nt_drop can apply the output dropout itself (the coalesced epilogue)
+bool tc_gemm_nt_drop_supported(const float* C, int64_t ldc, int N) {
+    const int BN = pick_bn(N);
+    return (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0 && (N & 3) == 0 && (BN & 3) == 0;
+}
+
+int launch_tc_gemm_nt_drop(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, float* C, int64_t ldc, int M,
+                           int N, int K, int accumulate, cudaStream_t st, float drop_p, uint64_t seed, uint64_t offset,
+                           const int64_t* offset_dev, int64_t drop_base, int drop_on_a);
+
 int launch_tc_gemm_nt(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, float* C, int64_t ldc, int M,
                       int N, int K, int accumulate, cudaStream_t st) {
+    return launch_tc_gemm_nt_drop(A, lda, W, ldw, bias, C, ldc, M, N, K, accumulate, st, 0.f, 0, 0, nullptr, 0, 0);
+}
+
+int launch_tc_gemm_nt_drop(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, float* C, int64_t ldc, int M,
+                           int N, int K, int accumulate, cudaStream_t st, float drop_p, uint64_t seed, uint64_t offset,
+                           const int64_t* offset_dev, int64_t drop_base, int drop_on_a) {
     if (M <= 0 || N <= 0) return MMS_OK;
+    MMS_REQUIRE(drop_p == 0.f || drop_on_a || (!accumulate && tc_gemm_nt_drop_supported(C, ldc, N)),
+                "tc_gemm_nt: output dropout needs the aligned epilogue");
     const int BN = pick_bn(N);
     CUtensorMap mapA, mapB;
     int rc = make_map(&mapA, A, M, K, lda, TC_BM);
@@ -264,6 +308,8 @@ int launch_tc_gemm_nt(const float* A, int64_t lda, const float* W, int64_t ldw, 
     MMS_REQUIRE(smem <= 200 * 1024, "tc_gemm: shared memory %zu too large", smem);
     TcGemmParams p;
     p.C = C; p.bias = bias; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.BN = BN; p.accumulate = accumulate;
+    p.drop_p = drop_p; p.drop_seed = seed; p.drop_offset = offset; p.drop_offset_dev = offset_dev; p.drop_base = drop_base;
+    p.drop_lda = lda; p.drop_on_a = drop_on_a;
     dim3 grid(cdiv(M, TC_BM), cdiv(N, BN));
     MMS_PROF_BEGIN(st);
     MMS_LAUNCH(tc_gemm_nt_kernel, grid, dim3(TC_THREADS), smem, st, mapA, mapB, p);

@@ -269,3 +269,34 @@ def test_cpu_input_is_refused():
     m = CnnGruAttentionModel(6, 2)
     with pytest.raises(MmsError):
         m(torch.zeros(2, 6, 640))
+
+
+def test_dropout_gradient_fused_into_gemm_epilogue_equals_separate_pass():
+    """The gradient through nn.GRU's inter-layer dropout (models.py:62) is applied by the epilogue of the tensor-core product that
+    forms it (MMS_DROP_FUSED=1, default) -- the same multipliers as a separate dropout_apply pass over the result
+    (MMS_DROP_FUSED=0); in the forward the multipliers ride on the A operand of the top layer's input projection.  Same RNG
+    offset in both runs: equal logits and gradients up to rounding / atomic ordering."""
+    from multimodalsignal_b200 import _ext
+    from multimodalsignal_b200.models import CnnGruAttentionModel
+    lib = _ext.lib()
+    torch.manual_seed(11)
+    B, C, T = 8, 6, 3840                      # M = B * L = 1920 rows: the tcgen05 products
+    m = CnnGruAttentionModel(C, 2, dropout=0.5).cuda().train()
+    x = torch.randn(B, C, T, device="cuda")
+    y = torch.randint(0, 2, (B,), device="cuda")
+    prev = lib.mms_get_option(b"DROP_FUSED", -1)
+    grads = {}
+    try:
+        for mode in (1, 0):
+            _ext.check(lib.mms_set_option(b"DROP_FUSED", mode))
+            m.zero_grad()
+            m._rng_calls = 100                # the same dropout masks in both runs
+            out = m(x)
+            torch.nn.functional.cross_entropy(out, y).backward()
+            grads[mode] = {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.numel()}
+            grads[mode]["__logits__"] = out.detach().clone()
+    finally:
+        _ext.check(lib.mms_set_option(b"DROP_FUSED", prev) if prev >= 0 else lib.mms_clear_option(b"DROP_FUSED"))
+    for k in grads[1]:
+        scale = max(grads[0][k].abs().max().item(), 1e-8)
+        assert (grads[1][k] - grads[0][k]).abs().max().item() <= 2e-5 * scale, k
