@@ -34,12 +34,13 @@ struct TcGemmParams {
     int drop_on_a;
 };
 
-// dynamic smem: [stage][A_hi | A_lo | B_hi | B_lo] (1024-byte aligned tiles)
+// dynamic smem: [stage][A_hi | A_lo | B_hi | B_lo] (1024-byte aligned tiles); NS = pipeline stages (2, or 4 for long reductions)
+template <int NS>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                    const __grid_constant__ CUtensorMap mapB, const TcGemmParams p) {
     MMS_PDL_TRIGGER();
     extern __shared__ __align__(1024) uint8_t tc_smem[];
-    __shared__ __align__(8) uint64_t full_bar[TC_STAGES], split_bar[TC_STAGES], empty_bar[TC_STAGES], acc_bar;
+    __shared__ __align__(8) uint64_t full_bar[NS], split_bar[NS], empty_bar[NS], acc_bar;
     __shared__ uint32_t tmem_base_sh;
     __shared__ __align__(16) float s_bias[256];
 
@@ -55,7 +56,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const __grid_
     for (int i = threadIdx.x; i < 256; i += TC_THREADS) s_bias[i] = (p.bias && i < BN && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) {
+        for (int s = 0; s < NS; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&split_bar[s], 4);      // one arrival per splitter warp
             mbar_init(&empty_bar[s], 1);
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const __grid_
         // ===== TMA producer =====
         if (lane == 0) {
             for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % TC_STAGES, round = kb / TC_STAGES;
+                const int s = kb % NS, round = kb / NS;
                 if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);
                 uint8_t* st = base + (size_t)s * stage_bytes;
                 mbar_expect_tx(&full_bar[s], a_bytes + b_bytes);
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const __grid_
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_tf32(BN);
             for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % TC_STAGES, round = kb / TC_STAGES;
+                const int s = kb % NS, round = kb / NS;
                 mbar_wait(&split_bar[s], round & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t st = smem_u32(base + (size_t)s * stage_bytes);
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const __grid_
         const bool drop_a = p.drop_p > 0.f && p.drop_on_a;
         if (drop_a) rng_a.init(p.drop_seed, resolve_offset(p.drop_offset, p.drop_offset_dev), p.drop_p);
         for (int kb = 0; kb < nkb; ++kb) {
-            const int s = kb % TC_STAGES, round = kb / TC_STAGES;
+            const int s = kb % NS, round = kb / NS;
             mbar_wait(&full_bar[s], round & 1);
             uint8_t* st = base + (size_t)s * stage_bytes;
             // A: hi in place, lo to the second tile (same offsets, so the swizzle is irrelevant)
@@ -298,12 +299,18 @@ int launch_tc_gemm_nt_drop(const float* A, int64_t lda, const float* W, int64_t 
     // ever touches stage 0, so it can ask for one stage of shared memory and let two CTAs share an SM (81 KB, 2 x 256
     // TMEM columns), overlapping one CTA's epilogue with the other's TMA / split / MMA
     const int nkb = (K + TC_BK - 1) / TC_BK;
-    const int stages = (option_get("NT_TRIM_STAGES", 1) == 1 && nkb < TC_STAGES) ? nkb : TC_STAGES;
+    // pipeline depth: 4 stages when the reduction has at least 4 k-blocks and they fit (MMS_NT_STAGES=2 keeps two): with two, a
+    // CTA's TMA latency is exposed once per k-block pair -- its 16 k-blocks made the K = 512 input-gradient product the
+    // slowest of the four; 1 stage for a single k-block (two CTAs per SM)
+    int stages = TC_STAGES;
+    if (nkb >= 4 && option_get("NT_STAGES", 4) >= 4 && stage * 4 + 1024 <= 200 * 1024) stages = 4;
+    const bool four = stages == 4;
+    if (option_get("NT_TRIM_STAGES", 1) == 1 && nkb < TC_STAGES) stages = nkb;
     const size_t smem = stage * stages + 1024;
     static PerDeviceOnce attr_once;
     if (attr_once.need()) {
-        MMS_CUDA(cudaFuncSetAttribute(tc_gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-       
+        MMS_CUDA(cudaFuncSetAttribute(tc_gemm_nt_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        MMS_CUDA(cudaFuncSetAttribute(tc_gemm_nt_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     }
     MMS_REQUIRE(smem <= 200 * 1024, "tc_gemm: shared memory %zu too large", smem);
     TcGemmParams p;
@@ -312,7 +319,8 @@ int launch_tc_gemm_nt_drop(const float* A, int64_t lda, const float* W, int64_t 
     p.drop_lda = lda; p.drop_on_a = drop_on_a;
     dim3 grid(cdiv(M, TC_BM), cdiv(N, BN));
     MMS_PROF_BEGIN(st);
-    MMS_LAUNCH(tc_gemm_nt_kernel, grid, dim3(TC_THREADS), smem, st, mapA, mapB, p);
+    if (four) MMS_LAUNCH(tc_gemm_nt_kernel<4>, grid, dim3(TC_THREADS), smem, st, mapA, mapB, p);
+    else MMS_LAUNCH(tc_gemm_nt_kernel<2>, grid, dim3(TC_THREADS), smem, st, mapA, mapB, p);
     MMS_LAUNCH_CHECK("tc_gemm_nt_kernel");
     return MMS_OK;
 }

@@ -24,7 +24,7 @@ def facts():
 
 def test_tensor_core_kernels_use_tcgen05_tma_and_tmem(facts):
     k, _ = facts
-    for name in ("tc_gemm_nt_kernel", "tc_gemm_tn_kernel<2>", "tc_gemm_tn_batch_kernel<2>", "conv1d_fwd_tc_kernel<16, 7, 2, 3>"):
+    for name in ("tc_gemm_nt_kernel<2>", "tc_gemm_nt_kernel<4>", "tc_gemm_tn_kernel<2>", "tc_gemm_tn_batch_kernel<2>", "conv1d_fwd_tc_kernel<16, 7, 2, 3>"):
         f = k[name]
         assert f.get("UTMALDG (TMA load)", 0) > 0, name
         assert f.get("UTC*MMA (tcgen05.mma)", 0) > 0, name
@@ -39,6 +39,13 @@ def test_recurrence_kernels_use_packed_fma_and_async_copies(facts):
         assert f.get("LDGSTS (cp.async)", 0) >= 8, name                 # ring prologue + one refill per unrolled step
     # the shared-memory-ring backward has no global load inside its loop: every LDG belongs to the weight / head prologue
     assert "LDGSTS (cp.async)" not in k["gru_bwd_kernel<64, 1>"]        # the register-ring kernel it replaced
+
+
+def test_encoder_backward_kernels_stage_by_bulk_copy_and_compute_with_packed_fma(facts):
+    """conv_bwd.cu: tiles arrive by cp.async.bulk (UBLKCP) on an mbarrier, the products run on packed fma.rn.f32x2."""
+    k, _ = facts
+    assert k["conv2_bwd_kernel"].get("UBLKCP (cp.async.bulk)", 0) >= 3 and k["conv2_bwd_kernel"].get("FFMA2 (fma.rn.f32x2)", 0) >= 160
+    assert k["conv1_bwd_kernel"].get("UBLKCP (cp.async.bulk)", 0) >= 3 and k["conv1_bwd_kernel"].get("FFMA2 (fma.rn.f32x2)", 0) >= 56
 
 
 def test_peer_kernels_use_system_scope_accesses(facts):

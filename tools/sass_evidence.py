@@ -16,6 +16,7 @@ LOG = ROOT / "multimodalsignal_b200" / "csrc" / "build.log"
 
 PATTERNS = OrderedDict([
     ("UTMALDG (TMA load)", r"\bUTMALDG"),
+    ("UBLKCP (cp.async.bulk)", r"\bUBLKCP"),
     ("UTC*MMA (tcgen05.mma)", r"\bUTC[A-Z]*MMA"),
     ("UTCBAR/commit", r"\bUTCBAR"),
     ("LDTM (tcgen05.ld)", r"\bLDTM"),
