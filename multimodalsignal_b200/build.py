@@ -72,7 +72,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 def build_pdl(force: bool = False) -> Path:
     """The programmatic-dependent-launch variant (-DMMS_PDL, see csrc/mms_common.cuh) as a SECOND library,
     ``libmms_b200_pdl.so``, beside the default one; select it with ``MMS_B200_LIB=<path>``.  Round-2 experiment:
-    compiled and checked for the griddepcontrol instructions (ACQBULK / PREEXIT in the SASS), not yet run on a GPU."""
+    compiled and checked for the griddepcontrol instructions (ACQBULK / PREEXIT in the SASS), parity-green on a B200 in round 2 but slower than the default library there."""
     lib = PKG / "libmms_b200_pdl.so"
     stamp = CSRC / ".build_stamp_pdl"
     digest = _digest() + ":pdl"

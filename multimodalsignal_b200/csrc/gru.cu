@@ -593,8 +593,8 @@ __global__ void __launch_bounds__(2 * H) gru_bwd_ring_kernel(const GruBwdParams 
 #undef MMS_RING_LOAD
 }
 
-// Forward recurrence, second version (MMS_GRU_FWD_V2=1, experiment; written without GPU access at the end of round 1; one
-// batch row per CTA).  Same algorithm and data movement as gru_fwd_kernel, three changes aimed at the dependent chain of a
+// Forward recurrence, second version (the default since round 2: 68 -> 57 us per launch on a B200; MMS_GRU_FWD_V2=0 restores the
+// first; one batch row per CTA).  Same algorithm and data movement as gru_fwd_kernel, three changes aimed at the dependent chain of a
 // step (ncu: 36 % fixed-latency waits, 21 % short scoreboard, 4 % branch resolving on one warp per scheduler):
 //   * thread (j, q) = (tid >> 1, tid & 1) owns ONE hidden unit and half of the reduction index, so the partial sums meet in
 //     ONE shuffle stage instead of two.  FFMA2 packing: (r, z) gate weights of the unit against a broadcast h_k, and the n

@@ -110,7 +110,7 @@ struct BnBwd {
 // MMS_LAUNCH only if it executes MMS_PDL_WAIT() on every path before its first such access.  The first kernel of the
 // forward and of the backward pass follows a memset node (full dependency) and chan_gate is a plain launch, so every kernel
 // of a step starts after the previous step's Adam has completed: reading parameters ahead of the wait is safe.
-// Build: MMS_NVCC_EXTRA="-DMMS_PDL" python -m multimodalsignal_b200.build --force   (unverified on a GPU, round-2 experiment)
+// Build: MMS_NVCC_EXTRA="-DMMS_PDL" python -m multimodalsignal_b200.build --force   (parity-green on a B200 but slower than the default build in round 2: not the default)
 #ifdef MMS_PDL
 #define MMS_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
 #define MMS_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")

@@ -118,7 +118,7 @@ static int gemm_tn_many(const TnCall* c, int n, cudaStream_t st) {
 // capture (the side streams become branches of the captured graph).  MMS_DISABLE_STREAMS=1 serialises.
 struct SideStreams {
     cudaStream_t s[3] = {nullptr, nullptr, nullptr};
-    cudaEvent_t fork_ev[8] = {}, join_ev[3] = {}, aux_ev = nullptr;
+    cudaEvent_t fork_ev[16] = {}, join_ev[3] = {}, aux_ev = nullptr;
     bool ok = false;
 };
 static int g_streams_disabled = -1;
@@ -132,7 +132,7 @@ static SideStreams* side_streams() {
     if (!ss.ok) {
         for (int i = 0; i < 3; ++i)
             if (cudaStreamCreateWithFlags(&ss.s[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < 16; ++i)
             if (cudaEventCreateWithFlags(&ss.fork_ev[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
         for (int i = 0; i < 3; ++i)
             if (cudaEventCreateWithFlags(&ss.join_ev[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
@@ -149,7 +149,7 @@ struct Forker {
     Forker(cudaStream_t m) : ss(side_streams()), main(m) {}
     // stream on which work that only depends on what `main` has enqueued so far may run
     cudaStream_t fork(int which) {
-        if (!ss || n_forks >= 8) return main;
+        if (!ss || n_forks >= 16) return main;
         if (cudaEventRecord(ss->fork_ev[n_forks], main) != cudaSuccess) return main;
         if (cudaStreamWaitEvent(ss->s[which], ss->fork_ev[n_forks], 0) != cudaSuccess) return main;
         ++n_forks;
@@ -563,11 +563,13 @@ static int model_backward(const mms_cnngru_desc* d, const float* x, const float*
             {w.D_tf, 4 * H, 2 * H, H, w.hs_tf, H, -1, L, G + po.w_hh[top], H, G + po.b_hh[top], M, 3 * H, H}};
         int r = gemm_tn_many(big, 2, sw);
         if (r) return r;
+        // the B-row products of the single reverse step: their own side stream, beside the big products instead of behind them
+        cudaStream_t ss = fk.fork(2);
         r = gemm_tn(w.D_tr, 4 * H, 3 * H, 0, in_top + (int64_t)(L - 1) * I_top, (int64_t)L * I_top, 0, 1,
-                    G + po.w_ih[top] + (int64_t)3 * H * I_top, I_top, G + po.b_ih[top] + 3 * H, B, 3 * H, I_top, sw);
+                    G + po.w_ih[top] + (int64_t)3 * H * I_top, I_top, G + po.b_ih[top] + 3 * H, B, 3 * H, I_top, ss);
         if (r) return r;
         // h_prev = 0 for the single reverse step: dW_hh(reverse) = 0, only the bias gradient remains
-        return gemm_tn(w.D_tr, 4 * H, 2 * H, H, nullptr, 0, 0, 1, nullptr, 0, G + po.b_hh[top] + 3 * H, B, 3 * H, 0, sw);
+        return gemm_tn(w.D_tr, 4 * H, 2 * H, H, nullptr, 0, 0, 1, nullptr, 0, G + po.b_hh[top] + 3 * H, B, 3 * H, 0, ss);
     };
     const bool defer_top_wgrad = top >= 1 && option_get("WGRAD_DEFER", 1) == 1;
     {
