@@ -1,5 +1,5 @@
 // Backward pass of the CNN encoder (reverse of reference models.py:45-53 and 24-31), the default path of a training step
-// when the shapes allow it (T % 32 == 0, cnn_out_channels == 32, no input gradient requested):
+// when the shapes allow it (T % 64 == 0, cnn_out_channels == 32, no input gradient requested):
 //
 //   pool_bwd_tm_kernel    MaxPool1d(3,2,1) + ReLU backward of stage 2 and the two BatchNorm reductions (sum dyn, sum dyn*xhat).
 //                         The upstream gradient is time-major [B, L, C] (the GRU's layout): a thread owns ONE channel
@@ -28,12 +28,6 @@
 #include "tc_common.cuh"
 
 namespace mms {
-
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
-                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
 
 // Columns [g0, g0 + n) of a row of `len` floats -> dst[0, n): the part inside the row by ONE bulk copy, the rest zeros (plain
 // stores of the calling lane).  g0, n, len multiples of 4 and both pointers 16-byte aligned.  Arrives once on `bar`.
@@ -469,7 +463,9 @@ __global__ void __launch_bounds__(256) conv1_bwd_kernel(const float* __restrict_
         if (lane < C) row_load(xs + lane * XS, x + ((size_t)b * C + lane) * T, 2 * l0 - 4, XS, T, &bar);
         if (lane < 16) row_load(dys + lane * CH, dyn + ((size_t)b * 16 + lane) * Lout, l0, CH, Lout, &bar);
         else if (fold) row_load(ys + (lane - 16) * CH, bn.y + ((size_t)b * 16 + lane - 16) * Lout, l0, CH, Lout, &bar);
-    } else if (warp == 1 && fold && lane < 16) {
+    }
+    // constants of the folded BatchNorm backward: the second warp beside the copies (the only warp of a one-channel model after them)
+    if (warp == (NW > 1 ? 1 : 0) && fold && lane < 16) {
         const int o = lane;
         const double n = (double)bn.Bstat * (double)Lout;
         const BnAffine af = bn_affine(bn.training, bn.stats, bn.gamma, bn.beta, bn.rm, bn.rv, o, 16, n);
@@ -636,7 +632,8 @@ static bool conv1_bwd_plan(int C, int L1, int* CH, int* NCH) {
 }
 
 bool conv_bwd_supported(const float* x, int C, int T, int O) {
-    if ((reinterpret_cast<uintptr_t>(x) & 15) || T % 32 != 0 || T < 64 || C < 1 || C > 16 || O != C2B_CO) return false;
+    // T % 64 == 0: the conv2 output rows (T / 8 floats) are handled in groups of 8 elements / 16-byte pieces everywhere
+    if ((reinterpret_cast<uintptr_t>(x) & 15) || T % 64 != 0 || T < 64 || C < 1 || C > 16 || O != C2B_CO) return false;
     int ch, nch;
     return conv1_bwd_plan(C, T / 2, &ch, &nch);
 }

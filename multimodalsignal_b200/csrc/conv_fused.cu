@@ -257,7 +257,8 @@ template <int CO2, int TM, int P>
 __global__ void __launch_bounds__((TM / P) * (CO2 / 16)) bn_pool_conv2_fwd_kernel(
     const __grid_constant__ CUtensorMap map_panel, const __grid_constant__ CUtensorMap map_tail, const double* __restrict__ stats1,
     const float* __restrict__ gamma, const float* __restrict__ beta, float* rm, float* rv, int64_t* nbt, int Bstat, int training,
-    const float* __restrict__ w, int L1, int P1, int L2, float* __restrict__ p1_out, float* __restrict__ y2, double* __restrict__ stats2) {
+    const float* __restrict__ w, int w_arranged, int L1, int P1, int L2, float* __restrict__ p1_out, float* __restrict__ y2,
+    double* __restrict__ stats2) {
     constexpr int NPG = TM / P, NCG = CO2 / 16, NT = NPG * NCG;
     constexpr int NI = 4 * TM + 12, NFULL = NI / CF_PANEL, TAILW = NI % CF_PANEL;
     constexpr int NJ = 2 * TM + 3, NJP = 2 * TM + 4;
@@ -280,11 +281,12 @@ __global__ void __launch_bounds__((TM / P) * (CO2 / 16)) bn_pool_conv2_fwd_kerne
     }
     __syncthreads();
     if (tid == 0) {
-        mbar_expect_tx(&load_bar, (uint32_t)(16 * NI * 4));
+        mbar_expect_tx(&load_bar, (uint32_t)(16 * NI * 4) + (w_arranged ? (uint32_t)(CO2 * 80 * 4) : 0u));
         const int col0 = 4 * m0 - 8;
 #pragma unroll
         for (int p = 0; p < NFULL; ++p) tma_load_2d(&map_panel, &load_bar, ys + p * 16 * CF_PANEL, col0 + p * CF_PANEL, b * 16);
         tma_load_2d(&map_tail, &load_bar, ys + NFULL * 16 * CF_PANEL, col0 + NFULL * CF_PANEL, b * 16);
+        if (w_arranged) bulk_g2s(w2s, w, (uint32_t)(CO2 * 80 * 4), &load_bar);     // already [ci*5 + k][o] (conv2_w_relayout_fwd_kernel)
     }
     const double n1 = (double)Bstat * (double)L1;
     if (tid < 16) {
@@ -293,32 +295,58 @@ __global__ void __launch_bounds__((TM / P) * (CO2 / 16)) bn_pool_conv2_fwd_kerne
         s_b[tid] = af.b;
     }
     // w2s[(ci*5 + k)*CO2 + o] = w[o][ci][k]
-    for (int idx = tid; idx < CO2 * 80; idx += NT) {
-        const int o = idx / 80, ck = idx - o * 80;
-        w2s[ck * CO2 + o] = __ldg(w + idx);
+    if (!w_arranged) {
+        for (int idx = tid; idx < CO2 * 80; idx += NT) {
+            const int o = idx / 80, ck = idx - o * 80;
+            w2s[ck * CO2 + o] = __ldg(w + idx);
+        }
     }
     mbar_wait(&load_bar, 0);
     __syncthreads();
 
-    // BatchNorm + ReLU + MaxPool(3,2,1) of the tile; positions outside [0, P1) are the convolution's zero padding
-    for (int idx = tid; idx < 16 * NJ; idx += NT) {
-        const int c = idx / NJ, jj = idx - c * NJ;
-        const int j = 2 * m0 - 2 + jj;
-        float v = 0.f;
-        if (j >= 0 && j < P1) {
-            const float a = s_a[c], bsh = s_b[c];
-            float m = -INFINITY;
+    // BatchNorm + ReLU + MaxPool(3,2,1) of the tile; positions outside [0, P1) are the convolution's zero padding.
+    // NT / 16 threads per channel, four pooled values per visit: three 128-bit loads of conv1 outputs (a quad of pooled
+    // values jj .. jj+3 needs the local columns 2 jj + 3 .. 2 jj + 11), one 128-bit store of the tile, 64-bit stores of p1.
+    {
+        constexpr int TPC = NT / 16, NQ = NJP / 4;
+        const int c = tid / TPC;
+        const float a = s_a[c], bsh = s_b[c];
+        float* p1row = p1_out + ((size_t)b * 16 + c) * P1;
+        auto ycol = [&](int ii) -> const float* {
+            return ii < NFULL * CF_PANEL ? ys + ((((ii >> 8) * 16 + c) << 8) + (ii & 255))
+                                         : ys + (NFULL * 16 * CF_PANEL + c * TAILW + (ii - NFULL * CF_PANEL));
+        };
+        for (int q = tid - c * TPC; q < NQ; q += TPC) {
+            const int jj = 4 * q, ii0 = 2 * jj;
+            float yv[12];
 #pragma unroll
-            for (int e = 0; e < 3; ++e) {
-                const int i = 2 * j - 1 + e, ii = 2 * jj + 3 + e;
-                const float yv = ii < NFULL * CF_PANEL ? ys[(((ii >> 8) * 16 + c) << 8) + (ii & 255)]
-                                                       : ys[NFULL * 16 * CF_PANEL + c * TAILW + (ii - NFULL * CF_PANEL)];
-                if (i >= 0 && i < L1) m = fmaxf(m, fmaxf(fmaf(a, yv, bsh), 0.f));
+            for (int t = 0; t < 3; ++t) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ii0 + 4 * t < NI) v = *reinterpret_cast<const float4*>(ycol(ii0 + 4 * t));
+                yv[4 * t] = v.x; yv[4 * t + 1] = v.y; yv[4 * t + 2] = v.z; yv[4 * t + 3] = v.w;
             }
-            v = m;
-            if (jj >= 2 && jj < 2 + 2 * TM) p1_out[((size_t)b * 16 + c) * P1 + j] = v;
+            float z[9];           // relu(bn(y)) at the local columns ii0 + 3 .. ii0 + 11; -inf outside the row
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const int i = 4 * m0 - 8 + ii0 + 3 + t;
+                z[t] = (i >= 0 && i < L1) ? fmaxf(fmaf(a, yv[t + 3], bsh), 0.f) : -INFINITY;
+            }
+            float pv[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int j = 2 * m0 - 2 + jj + e;
+                pv[e] = (j >= 0 && j < P1) ? fmaxf(fmaxf(z[2 * e], z[2 * e + 1]), z[2 * e + 2]) : 0.f;
+            }
+            *reinterpret_cast<float4*>(p1s + c * NJP + jj) = make_float4(pv[0], pv[1], pv[2], pv[3]);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int je = jj + 2 * h, j = 2 * m0 - 2 + je;       // the pair (je, je + 1): j is even
+                if (je >= 2 && je < 2 + 2 * TM && j >= 0 && j + 1 < P1)
+                    *reinterpret_cast<float2*>(p1row + j) = make_float2(pv[2 * h], pv[2 * h + 1]);
+                else if (je >= 2 && je < 2 + 2 * TM && j >= 0 && j < P1)
+                    p1row[j] = pv[2 * h];
+            }
         }
-        p1s[c * NJP + jj] = v;
     }
     __syncthreads();
 
@@ -359,13 +387,21 @@ __global__ void __launch_bounds__((TM / P) * (CO2 / 16)) bn_pool_conv2_fwd_kerne
     // epilogue
     const int m = m0 + P * pg;
     float* yb = y2 + ((size_t)b * CO2 + cg * 16) * L2 + m;
+    if (P == 2 && (L2 & 1) == 0 && m + 1 < L2 && (reinterpret_cast<uintptr_t>(y2) & 7) == 0) {
 #pragma unroll
-    for (int pp = 0; pp < P; ++pp) {
-        if (m + pp < L2) {
+        for (int i = 0; i < 8; ++i) {
+            *reinterpret_cast<float2*>(yb + (size_t)(2 * i) * L2) = make_float2(acc[0][i].x, acc[P - 1][i].x);
+            *reinterpret_cast<float2*>(yb + (size_t)(2 * i + 1) * L2) = make_float2(acc[0][i].y, acc[P - 1][i].y);
+        }
+    } else {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                yb[(size_t)(2 * i) * L2 + pp] = acc[pp][i].x;
-                yb[(size_t)(2 * i + 1) * L2 + pp] = acc[pp][i].y;
+        for (int pp = 0; pp < P; ++pp) {
+            if (m + pp < L2) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    yb[(size_t)(2 * i) * L2 + pp] = acc[pp][i].x;
+                    yb[(size_t)(2 * i + 1) * L2 + pp] = acc[pp][i].y;
+                }
             }
         }
     }
@@ -397,7 +433,22 @@ __global__ void __launch_bounds__((TM / P) * (CO2 / 16)) bn_pool_conv2_fwd_kerne
     if (training && blockIdx.x == 0 && blockIdx.y == 0) bn_running_update(stats1, rm, rv, nbt, 16, n1, tid);
 }
 
+// wt[(ci*5 + k) * O + o] = w[o][ci][k]: conv2's weights in the order bn_pool_conv2_fwd_kernel keeps them in shared memory
+__global__ void __launch_bounds__(256) conv2_w_relayout_fwd_kernel(const float* __restrict__ w, int O, float* __restrict__ wt) {
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= O * 80) return;
+    const int o = idx / 80, ck = idx - o * 80;
+    wt[ck * O + o] = __ldg(w + idx);
+}
+
 // ---- host side -------------------------------------------------------------------------------------------------------
+int launch_conv2_w_relayout_fwd(const float* w, int O, float* wt, cudaStream_t st) {
+    MMS_PROF_BEGIN(st);
+    conv2_w_relayout_fwd_kernel<<<cdiv(O * 80, 256), 256, 0, st>>>(w, O, wt);
+    MMS_LAUNCH_CHECK("conv2_w_relayout_fwd_kernel");
+    return MMS_OK;
+}
+
 bool conv_fused_supported(const float* x, int C, int T, int O) {
     if (!encode_tiled_fn() || (reinterpret_cast<uintptr_t>(x) & 15) || T % 8 != 0 || T < 16 || C < 1 || C > 16) return false;
     if (!(O == 16 || O == 32 || O == 64)) return false;
@@ -441,7 +492,7 @@ int launch_attn_conv1_fwd(const float* x, const float* w, const float* ca_w1, co
 
 template <int CO2, int TM, int P>
 static int bn_pool_conv2_launch(const float* y1, const double* stats1, const float* gamma, const float* beta, float* rm, float* rv,
-                                int64_t* nbt, int Bstat, int training, const float* w, int B, int L1, float* p1, float* y2,
+                                int64_t* nbt, int Bstat, int training, const float* w, int w_arranged, int B, int L1, float* p1, float* y2,
                                 double* stats2, cudaStream_t st) {
     constexpr int NI = 4 * TM + 12, TAILW = NI % CF_PANEL, NJP = 2 * TM + 4, NT = (TM / P) * (CO2 / 16);
     const int P1 = pool_out_len(L1), L2 = conv_out_len(P1, CONV2_K, CONV2_S, CONV2_P);
@@ -457,21 +508,23 @@ static int bn_pool_conv2_launch(const float* y1, const double* stats1, const flo
     MMS_REQUIRE(smem <= 100 * 1024, "bn_pool_conv2_fwd: shared memory %zu too large", smem);
     dim3 grid(cdiv(L2, TM), B);
     MMS_PROF_BEGIN(st);
-    kern<<<grid, NT, smem, st>>>(mp, mt, stats1, gamma, beta, rm, rv, nbt, Bstat, training, w, L1, P1, L2, p1, y2, stats2);
+    MMS_REQUIRE(!w_arranged || (reinterpret_cast<uintptr_t>(w) & 15) == 0, "bn_pool_conv2_fwd: re-arranged weights must be 16-byte aligned");
+    kern<<<grid, NT, smem, st>>>(mp, mt, stats1, gamma, beta, rm, rv, nbt, Bstat, training, w, w_arranged, L1, P1, L2, p1, y2, stats2);
     MMS_LAUNCH_CHECK("bn_pool_conv2_fwd_kernel");
     return MMS_OK;
 }
 
 // BN1 + ReLU + MaxPool + conv2 (+ BN2 batch sums, BN1 running statistics).  L1 = T / 2 (multiple of 4).
+// w_arranged != 0: `w` is the [ci*5 + k][o] copy made by launch_conv2_w_relayout_fwd (one bulk copy per CTA instead of a gather)
 int launch_bn_pool_conv2_fwd(const float* y1, const double* stats1, const float* gamma, const float* beta, float* rm, float* rv,
-                             int64_t* nbt, int Bstat, int training, const float* w, int B, int O, int L1, float* p1, float* y2,
-                             double* stats2, cudaStream_t st) {
+                             int64_t* nbt, int Bstat, int training, const float* w, int w_arranged, int B, int O, int L1, float* p1,
+                             float* y2, double* stats2, cudaStream_t st) {
     MMS_REQUIRE(L1 % 4 == 0 && (reinterpret_cast<uintptr_t>(y1) & 15) == 0, "bn_pool_conv2_fwd: unsupported shape / alignment");
     MMS_REQUIRE(!training || stats1, "bn_pool_conv2_fwd: training mode needs batch statistics");
     if (Bstat <= 0) Bstat = B;
-    if (O == 16) return bn_pool_conv2_launch<16, 128, 4>(y1, stats1, gamma, beta, rm, rv, nbt, Bstat, training, w, B, L1, p1, y2, stats2, st);
-    if (O == 32) return bn_pool_conv2_launch<32, 128, 2>(y1, stats1, gamma, beta, rm, rv, nbt, Bstat, training, w, B, L1, p1, y2, stats2, st);
-    return bn_pool_conv2_launch<64, 128, 4>(y1, stats1, gamma, beta, rm, rv, nbt, Bstat, training, w, B, L1, p1, y2, stats2, st);
+    if (O == 16) return bn_pool_conv2_launch<16, 128, 4>(y1, stats1, gamma, beta, rm, rv, nbt, Bstat, training, w, w_arranged, B, L1, p1, y2, stats2, st);
+    if (O == 32) return bn_pool_conv2_launch<32, 128, 2>(y1, stats1, gamma, beta, rm, rv, nbt, Bstat, training, w, w_arranged, B, L1, p1, y2, stats2, st);
+    return bn_pool_conv2_launch<64, 128, 4>(y1, stats1, gamma, beta, rm, rv, nbt, Bstat, training, w, w_arranged, B, L1, p1, y2, stats2, st);
 }
 
 }  // namespace mms

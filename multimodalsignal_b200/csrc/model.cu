@@ -57,7 +57,8 @@ int launch_conv1_bwd(const float*, const float*, const float*, const float*, con
 int launch_attn_conv1_fwd(const float*, const float*, const float*, const float*, int, int, int, int, float*, float*, float*, double*,
                           cudaStream_t);
 int launch_bn_pool_conv2_fwd(const float*, const double*, const float*, const float*, float*, float*, int64_t*, int, int, const float*,
-                             int, int, int, float*, float*, double*, cudaStream_t);
+                             int, int, int, int, float*, float*, double*, cudaStream_t);
+int launch_conv2_w_relayout_fwd(const float*, int, float*, cudaStream_t);
 int launch_tc_gemm_nt(const float*, int64_t, const float*, int64_t, const float*, float*, int64_t, int, int, int, int, cudaStream_t);
 int launch_tc_gemm_nt_drop(const float*, int64_t, const float*, int64_t, const float*, float*, int64_t, int, int, int, int, cudaStream_t,
                            float, uint64_t, uint64_t, const int64_t*, int64_t, int);
@@ -277,7 +278,7 @@ struct Workspace {
     double* red1; double* red2; float* dgate; int* row_counter;
     size_t fwd_zero_bytes, bwd_zero_bytes;
     char* fwd_zero; char* bwd_zero;
-    float *mean, *gate, *y1, *p1, *y2, *seq;
+    float *mean, *gate, *y1, *p1, *y2, *seq, *c2_wt;
     float *gi[MAX_LAYERS], *hs[MAX_LAYERS], *outd[MAX_LAYERS], *stash[MAX_LAYERS];   // bottom layers
     float *gi_tf, *gi_tr, *hs_tf, *h_tr, *stash_tf, *stash_tr, *last, *hid;
     float *wT_top, *wT[MAX_LAYERS], *dx_extra;
@@ -313,6 +314,7 @@ static void carve(const Dims& m, char* base, Workspace* w) {
     w->p1 = (float*)take(B * CONV1_CO * m.P1 * f);
     w->y2 = (float*)take(B * m.O * m.L2c * f);
     w->seq = (float*)take(M * m.O * f);
+    w->c2_wt = (float*)take((int64_t)m.O * CONV2_CI * CONV2_K * f);     // conv2 weights as [ci*5 + k][o] for the fused forward
     for (int l = 0; l < m.layers - 1; ++l) {
         w->gi[l] = (float*)take(M * 6 * H * f);
         w->hs[l] = (float*)take(M * 2 * H * f);
@@ -381,6 +383,13 @@ static int model_forward(const mms_cnngru_desc* d, const float* x, const float* 
     // fused encoder kernels (conv_fused.cu): attention + conv1 in one cluster launch, BN1/ReLU/pool + conv2 in one launch
     const bool fused = option_get("CONV_FUSED", 1) == 1 && conv_fused_supported(x, m.C, m.T, m.O);
     if (fused) {
+        Forker fkw(st);
+        if (phases == 7) {       // conv2's weights in the kernel's shared-memory order: side stream, beside attention + conv1
+            rc = launch_conv2_w_relayout_fwd(P + po.conv2_w, m.O, w.c2_wt, fkw.fork(1));
+            if (rc) return rc;
+            rc = fkw.mark(1);
+            if (rc) return rc;
+        }
         if (phases & 1) {
             MMS_CUDA(cudaMemsetAsync(w.fwd_zero, 0, w.fwd_zero_bytes, st));
             rc = launch_attn_conv1_fwd(x, P + po.conv1_w, P + po.ca_w1, P + po.ca_w2, m.attention ? 1 : 0, B, m.C, m.T, w.mean, w.gate,
@@ -388,8 +397,16 @@ static int model_forward(const mms_cnngru_desc* d, const float* x, const float* 
             if (rc) return rc;
         }
         if (phases & 2) {
-            rc = launch_bn_pool_conv2_fwd(w.y1, w.stats1, P + po.bn1_g, P + po.bn1_b, rm1, rv1, nbt, m.Bg, m.training, P + po.conv2_w, B,
+            if (phases != 7) {   // phase-split call: make the re-arranged weights here
+                rc = launch_conv2_w_relayout_fwd(P + po.conv2_w, m.O, w.c2_wt, st);
+                if (rc) return rc;
+            }
+            rc = fkw.wait_mark();
+            if (rc) return rc;
+            rc = launch_bn_pool_conv2_fwd(w.y1, w.stats1, P + po.bn1_g, P + po.bn1_b, rm1, rv1, nbt, m.Bg, m.training, w.c2_wt, 1, B,
                                           m.O, m.L1c, w.p1, w.y2, m.training ? w.stats2 : nullptr, st);
+            if (rc) return rc;
+            rc = fkw.join();
             if (rc) return rc;
         }
     }

@@ -190,6 +190,20 @@ def _model_from(p, bufs, C):
 # the GRU runs on the tcgen05 kernels here, which the small golden cases never reach.
 @pytest.mark.parametrize("B,C,T", [(64, 6, 3840), (64, 3, 7680), (64, 14, 3840)])
 def test_whole_step_at_quoted_configs_vs_float64_oracle(B, C, T):
+    _whole_step_case(B, C, T)
+
+
+# Edge shapes of the fused encoder kernels (conv_fused.cu takes T % 8 == 0, conv_bwd.cu T % 64 == 0): the shortest sequence (one
+# partial tile everywhere, L = 4), one and sixteen channels, tile counts that do not divide (T = 4032: L2 = 504 = 3.9 tiles of
+# 128, L1 = 2016 = 4.2 chunks of 480), a single batch row -- and lengths that take the per-layer backward kernels (T % 64 != 0)
+# or the per-layer kernels throughout (T % 8 != 0).
+@pytest.mark.parametrize("B,C,T", [(1, 1, 64), (3, 5, 128), (2, 16, 1088), (5, 6, 4032), (4, 8, 320), (3, 5, 96), (4, 8, 352),
+                                   (2, 6, 100), (3, 4, 1004)])
+def test_whole_step_edge_shapes_vs_float64_oracle(B, C, T):
+    _whole_step_case(B, C, T)
+
+
+def _whole_step_case(B, C, T):
     from multimodalsignal_b200.synth import synthetic_windows
     p, bufs = _random_state(C, seed=11 + C)
     x, y = synthetic_windows(B, C, T, seed=5 + C)
