@@ -300,6 +300,17 @@ int mms_gemm_nt_bias(const float* A, int64_t lda, const float* W, int64_t ldw, c
                      float* C, int64_t ldc, int32_t M, int32_t N, int32_t K, mms_stream_t stream);
 int mms_gemm_nn(const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc,
                 int32_t M, int32_t N, int32_t K, int32_t accumulate, mms_stream_t stream);
+/* Few-row products (M <= 256, K <= 256, K % 4 == 0, 16-byte aligned operands with strides that are multiples of 4): the B
+ * rows of the top GRU layer's single reverse step (models.py:79 keeps only outputs[:, -1, :]) -- its input
+ * projection in the forward pass and the input gradient of that step in the backward pass.
+ *   C[m,n] = sum_k a(m,k) W(n,k) (+ bias[n]);  W(n,k) = W[n*ldw + k] (w_kmajor != 0) or W[k*ldw + n]
+ *   drop_mode 1: a(m,k) = A[m,k] * m(drop_base + m*drop_row_stride + k)  (models.py:62 inter-layer dropout on the operand)
+ *   drop_mode 2: C[m,n] *= m(drop_base + m*drop_row_stride + n)          (the same multipliers on the gradient)
+ * with the multipliers of mms_dropout_apply. */
+int mms_gemm_skinny(const float* A, int64_t lda, const float* W, int64_t ldw, int32_t w_kmajor, const float* bias,
+                    float* C, int64_t ldc, int32_t M, int32_t N, int32_t K, int32_t drop_mode, int64_t drop_base,
+                    int64_t drop_row_stride, float dropout_p, uint64_t rng_seed, uint64_t rng_offset,
+                    const int64_t* rng_offset_dev, mms_stream_t stream);
 int mms_gemm_tn_acc(const float* A, int64_t lda, int32_t a_split, int32_t a_skip, const float* Bm, int64_t ldb,
                     int32_t shift, int32_t seq, float* C, int64_t ldc, float* bias_grad,
                     int32_t M, int32_t N1, int32_t N2, mms_stream_t stream);

@@ -114,6 +114,7 @@ _SIGNATURES = {
     "mms_tc_gemm_tn_batch": (c_i32, [C.POINTER(TnCall), c_i32, P]),
     "mms_tc_gemm_tn": (c_i32, [P, c_i64, c_i32, c_i32, P, c_i64, c_i32, c_i32, P, c_i64, P, c_i32, c_i32, c_i32, P]),
     "mms_gemm_nt_bias": (c_i32, [P, c_i64, P, c_i64, P, P, c_i64, c_i32, c_i32, c_i32, P]),
+    "mms_gemm_skinny": (c_i32, [P, c_i64, P, c_i64, c_i32, P, P, c_i64, c_i32, c_i32, c_i32, c_i32, c_i64, c_i64, c_f32, c_u64, c_u64, P, P]),
     "mms_gemm_nn": (c_i32, [P, c_i64, P, c_i64, P, c_i64, c_i32, c_i32, c_i32, c_i32, P]),
     "mms_gemm_tn_acc": (c_i32, [P, c_i64, c_i32, c_i32, P, c_i64, c_i32, c_i32, P, c_i64, P, c_i32, c_i32, c_i32, P]),
     "mms_dropout_apply": (c_i32, [P, P, c_i64, c_i64, c_f32, c_u64, c_u64, P, P]),

@@ -71,7 +71,8 @@ __global__ void __launch_bounds__(A1_NT) attn_conv1_fwd_kernel(const __grid_cons
                                                                const float* __restrict__ ca_w2, int use_gate, int C, int A, int T,
                                                                int Lout, int tpc, float* __restrict__ mean_out,
                                                                float* __restrict__ gate_out, float* __restrict__ y,
-                                                               double* __restrict__ stats) {
+                                                               double* __restrict__ stats, const float* __restrict__ w2, int O2,
+                                                               float* __restrict__ w2_fwd, float* __restrict__ w2_bwd) {
     extern __shared__ __align__(128) float a1_smem[];
     __shared__ __align__(8) uint64_t load_bar;
     __shared__ float s_wsum[2][16], s_part[16], s_all[8 * 16], s_mean[16], s_gate[16];
@@ -110,6 +111,17 @@ __global__ void __launch_bounds__(A1_NT) attn_conv1_fwd_kernel(const __grid_cons
         w1s[ck * 16 + o] = __ldg(w + idx);
     }
     if (tid < 16) { s_part[tid] = 0.f; s_gate[tid] = 1.f; }
+    // conv2's weights w2[o][ci][k] in the orders the NEXT kernels stage them with one bulk copy per CTA (they follow this
+    // launch on the stream): [ci*5 + k][o] for bn_pool_conv2_fwd_kernel, [o*5 + k][ci] for conv2_bwd_kernel.  Rank 0 of every
+    // cluster takes a 64-element slice while its tiles are in flight.
+    if (w2_fwd && rank == 0) {
+        for (int idx = b * A1_NT + tid; idx < O2 * 80; idx += (int)gridDim.y * A1_NT) {
+            const float v = __ldg(w2 + idx);
+            const int o = idx / 80, r = idx - o * 80, ci = r / 5, k = r - ci * 5;
+            w2_fwd[r * O2 + o] = v;
+            if (w2_bwd) w2_bwd[(o * 5 + k) * 16 + ci] = v;
+        }
+    }
     if (mine > 0) mbar_wait(&load_bar, 0);
     __syncthreads();
 
@@ -457,8 +469,12 @@ bool conv_fused_supported(const float* x, int C, int T, int O) {
 }
 
 // ChannelAttention + conv1 (+ BN batch sums).  use_gate == 0: plain convolution (cnn_gru baseline).
+// w2 / w2_fwd / w2_bwd (optional): conv2's weights [O2][16][5] and where to leave their re-arranged copies (w2_bwd: O2 == 32 only)
 int launch_attn_conv1_fwd(const float* x, const float* w, const float* ca_w1, const float* ca_w2, int use_gate, int B, int C, int T,
-                          float* mean_out, float* gate_out, float* y1, double* stats, cudaStream_t st) {
+                          float* mean_out, float* gate_out, float* y1, double* stats, const float* w2, int O2, float* w2_fwd,
+                          float* w2_bwd, cudaStream_t st) {
+    MMS_REQUIRE(!w2_fwd || (w2 && O2 > 0), "attn_conv1_fwd: re-layout requested without weights");
+    MMS_REQUIRE(!w2_bwd || (w2_fwd && O2 == 32), "attn_conv1_fwd: the backward order of conv2's weights needs C_out = 32");
     MMS_REQUIRE(conv_fused_supported(x, C, T, 16), "attn_conv1_fwd: unsupported shape / alignment");
     MMS_REQUIRE((reinterpret_cast<uintptr_t>(y1) & 15) == 0, "attn_conv1_fwd: y1 must be 16-byte aligned");
     const int L1 = T / 2, ntiles = (L1 + A1_TL - 1) / A1_TL, tpc = (ntiles + 7) / 8, CS = (ntiles + tpc - 1) / tpc;
@@ -485,7 +501,7 @@ int launch_attn_conv1_fwd(const float* x, const float* w, const float* ca_w1, co
     cfg.numAttrs = 1;
     MMS_PROF_BEGIN(st);
     MMS_CUDA(cudaLaunchKernelEx(&cfg, attn_conv1_fwd_kernel, mp, mt, w, ca_w1, ca_w2, use_gate, C, C / 4, T, L1, tpc, mean_out, gate_out,
-                                y1, stats));
+                                y1, stats, w2, O2, w2_fwd, w2_bwd));
     MMS_LAUNCH_CHECK("attn_conv1_fwd_kernel");
     return MMS_OK;
 }

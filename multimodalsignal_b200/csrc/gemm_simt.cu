@@ -186,6 +186,107 @@ __global__ void __launch_bounds__(256) gemm_tn_acc_kernel(const float* __restric
     if (bias_grad && blockIdx.x == 0 && t < BM && i0 + t < N1) atomicAdd(bias_grad + i0 + t, bsum);
 }
 
+// Products with few rows (M <= a few dozen: the B rows of the top layer's single reverse step, forward and backward).  The
+// 64 x 64-tile kernels above run them on N / 64 = 2-3 CTAs with a serial load -> barrier -> FMA loop per 16 reduction
+// elements (14-18 us for 1.5 MFLOP, and the recurrence that follows waits for them); here a CTA owns ALL reduction elements
+// of 32 rows x 8 columns, stages both operands with every load in flight at once, and N / 8 CTAs run side by side.
+//   C[m,n] = sum_k a(m,k) W(n,k) (+ bias[n]),   W(n,k) = W[n*ldw + k] (w_kmajor) or W[k*ldw + n]
+//   drop_mode 1: a(m,k) = A[m,k] * mult(drop_base + m*drop_row_stride + k)   (inter-layer dropout on the operand)
+//   drop_mode 2: C[m,n] *= mult(drop_base + m*drop_row_stride + n)            (its gradient, on the result)
+constexpr int SK_ROWS = 32, SK_COLS = 8, SK_MAXK = 256;
+
+__global__ void __launch_bounds__(256) gemm_skinny_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ W,
+                                                          int64_t ldw, int w_kmajor, const float* __restrict__ bias,
+                                                          float* __restrict__ C, int64_t ldc, int M, int N, int K, int drop_mode,
+                                                          int64_t drop_base, int64_t drop_row_stride, float p, uint64_t seed,
+                                                          uint64_t offset, const int64_t* offset_dev) {
+    extern __shared__ __align__(16) float sk_smem[];
+    const int KP = K + 4;                                  // row pitch: rows 4 banks apart -> conflict-free 128-bit reads
+    float* As = sk_smem;                                   // [SK_ROWS][KP]
+    float* Ws = sk_smem + SK_ROWS * KP;                    // [SK_COLS][KP]
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.y * SK_ROWS, n0 = blockIdx.x * SK_COLS;
+    const int K4 = K >> 2;
+    DropRng rng;
+    if (drop_mode) rng.init(seed, resolve_offset(offset, offset_dev), p);
+
+    for (int i = tid; i < SK_ROWS * K4; i += 256) {
+        const int r = i / K4, k = (i - r * K4) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m0 + r < M) {
+            v = __ldg(reinterpret_cast<const float4*>(A + (int64_t)(m0 + r) * lda + k));
+            if (drop_mode == 1) {
+                const uint64_t e = (uint64_t)(drop_base + (int64_t)(m0 + r) * drop_row_stride + k);
+                v.x *= rng.mult(e); v.y *= rng.mult(e + 1); v.z *= rng.mult(e + 2); v.w *= rng.mult(e + 3);
+            }
+        }
+        *reinterpret_cast<float4*>(As + r * KP + k) = v;
+    }
+    if (w_kmajor) {
+        for (int i = tid; i < SK_COLS * K4; i += 256) {
+            const int c = i / K4, k = (i - c * K4) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n0 + c < N) v = __ldg(reinterpret_cast<const float4*>(W + (int64_t)(n0 + c) * ldw + k));
+            *reinterpret_cast<float4*>(Ws + c * KP + k) = v;
+        }
+    } else {
+        for (int i = tid; i < K * 2; i += 256) {           // two 16-byte pieces of the 8 columns per reduction index
+            const int k = i >> 1, c = (i & 1) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n0 + c + 3 < N) v = __ldg(reinterpret_cast<const float4*>(W + (int64_t)k * ldw + n0 + c));
+            else {
+                if (n0 + c + 0 < N) v.x = __ldg(W + (int64_t)k * ldw + n0 + c + 0);
+                if (n0 + c + 1 < N) v.y = __ldg(W + (int64_t)k * ldw + n0 + c + 1);
+                if (n0 + c + 2 < N) v.z = __ldg(W + (int64_t)k * ldw + n0 + c + 2);
+            }
+            Ws[(c + 0) * KP + k] = v.x; Ws[(c + 1) * KP + k] = v.y; Ws[(c + 2) * KP + k] = v.z; Ws[(c + 3) * KP + k] = v.w;
+        }
+    }
+    __syncthreads();
+
+    // thread (c, r) = (tid & 7, tid >> 3) owns one output: a warp reads 4 rows of A and 8 rows of W, 128 bits per lane
+    const int c = tid & 7, r = tid >> 3;                   // r in 0..31
+    const float4* ap = reinterpret_cast<const float4*>(As + r * KP);
+    const float4* wp = reinterpret_cast<const float4*>(Ws + c * KP);
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+#pragma unroll 4
+    for (int k4 = 0; k4 < K4; ++k4) {
+        const float4 a = ap[k4], w = wp[k4];
+        acc0 = fmaf(a.x, w.x, acc0);
+        acc1 = fmaf(a.y, w.y, acc1);
+        acc2 = fmaf(a.z, w.z, acc2);
+        acc3 = fmaf(a.w, w.w, acc3);
+    }
+    const int m = m0 + r, n = n0 + c;
+    if (m < M && n < N) {
+        float v = (acc0 + acc1) + (acc2 + acc3);
+        if (bias) v += __ldg(bias + n);
+        if (drop_mode == 2) v *= rng.mult((uint64_t)(drop_base + (int64_t)m * drop_row_stride + n));
+        C[(int64_t)m * ldc + n] = v;
+    }
+}
+
+bool gemm_skinny_supported(const float* A, int64_t lda, const float* W, int64_t ldw, int w_kmajor, int M, int N, int K) {
+    if (option_get("GEMM_SKINNY", 1) != 1) return false;
+    if (M < 1 || M > 256 || N < 1 || K < 4 || K > SK_MAXK || K % 4 != 0) return false;
+    if (!aligned16(A) || lda % 4 != 0 || !aligned16(W) || ldw % 4 != 0) return false;
+    return true;
+}
+
+int launch_gemm_skinny(const float* A, int64_t lda, const float* W, int64_t ldw, int w_kmajor, const float* bias, float* C, int64_t ldc,
+                       int M, int N, int K, int drop_mode, int64_t drop_base, int64_t drop_row_stride, float p, uint64_t seed,
+                       uint64_t offset, const int64_t* offset_dev, cudaStream_t st) {
+    MMS_REQUIRE(gemm_skinny_supported(A, lda, W, ldw, w_kmajor, M, N, K), "gemm_skinny: unsupported shape / alignment");
+    if (p <= 0.f) drop_mode = 0;
+    const size_t smem = (size_t)(SK_ROWS + SK_COLS) * (K + 4) * sizeof(float);      // <= 41.6 KB
+    dim3 grid(cdiv(N, SK_COLS), cdiv(M, SK_ROWS));
+    MMS_PROF_BEGIN(st);
+    gemm_skinny_kernel<<<grid, 256, smem, st>>>(A, lda, W, ldw, w_kmajor, bias, C, ldc, M, N, K, drop_mode, drop_base, drop_row_stride,
+                                                p, seed, offset, offset_dev);
+    MMS_LAUNCH_CHECK("gemm_skinny_kernel");
+    return MMS_OK;
+}
+
 int launch_gemm_nt_bias(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, float* C, int64_t ldc,
                         int M, int N, int K, cudaStream_t st) {
     if (M <= 0 || N <= 0) return MMS_OK;
@@ -229,6 +330,14 @@ extern "C" int mms_gemm_nt_bias(const float* A, int64_t lda, const float* W, int
                                 int64_t ldc, int32_t M, int32_t N, int32_t K, mms_stream_t stream) {
     MMS_REQUIRE(A && W && C && K > 0, "gemm_nt_bias: bad arguments");
     return launch_gemm_nt_bias(A, lda, W, ldw, bias, C, ldc, M, N, K, (cudaStream_t)stream);
+}
+extern "C" int mms_gemm_skinny(const float* A, int64_t lda, const float* W, int64_t ldw, int32_t w_kmajor, const float* bias, float* C,
+                               int64_t ldc, int32_t M, int32_t N, int32_t K, int32_t drop_mode, int64_t drop_base,
+                               int64_t drop_row_stride, float dropout_p, uint64_t rng_seed, uint64_t rng_offset,
+                               const int64_t* rng_offset_dev, mms_stream_t stream) {
+    MMS_REQUIRE(A && W && C && drop_mode >= 0 && drop_mode <= 2 && dropout_p >= 0.f && dropout_p < 1.f, "gemm_skinny: bad arguments");
+    return launch_gemm_skinny(A, lda, W, ldw, w_kmajor, bias, C, ldc, M, N, K, drop_mode, drop_base, drop_row_stride, dropout_p, rng_seed,
+                              rng_offset, rng_offset_dev, (cudaStream_t)stream);
 }
 extern "C" int mms_gemm_nn(const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc, int32_t M,
                            int32_t N, int32_t K, int32_t accumulate, mms_stream_t stream) {

@@ -21,6 +21,9 @@ int launch_bn_relu_pool_bwd(const float*, const double*, const float*, const flo
                             int, int, int, int, float*, float*, float*, double*, cudaStream_t, int which, int Bstat, float grad_scale);
 int launch_gemm_nt_bias(const float*, int64_t, const float*, int64_t, const float*, float*, int64_t, int, int, int, cudaStream_t);
 int launch_gemm_nn(const float*, int64_t, const float*, int64_t, float*, int64_t, int, int, int, int, cudaStream_t);
+bool gemm_skinny_supported(const float*, int64_t, const float*, int64_t, int, int, int, int);
+int launch_gemm_skinny(const float*, int64_t, const float*, int64_t, int, const float*, float*, int64_t, int, int, int, int, int64_t, int64_t,
+                       float, uint64_t, uint64_t, const int64_t*, cudaStream_t);
 int launch_gemm_tn_acc(const float*, int64_t, int, int, const float*, int64_t, int, int, float*, int64_t, float*, int, int, int,
                        cudaStream_t);
 bool tc_gemm_tn_supported(const float*, int64_t, int, int, const float*, int64_t, float*, int64_t, int, int, int);
@@ -55,6 +58,7 @@ int64_t conv2_w_relayout_floats();
 int launch_conv1_bwd(const float*, const float*, const float*, const float*, const float*, const float*, const float*, int, int, int,
                      float*, int*, float*, float*, float*, cudaStream_t, const BnBwd*);
 int launch_attn_conv1_fwd(const float*, const float*, const float*, const float*, int, int, int, int, float*, float*, float*, double*,
+                          const float*, int, float*, float*,
                           cudaStream_t);
 int launch_bn_pool_conv2_fwd(const float*, const double*, const float*, const float*, float*, float*, int64_t*, int, int, const float*,
                              int, int, int, int, float*, float*, double*, cudaStream_t);
@@ -362,7 +366,15 @@ struct FusedLoss {
     const int64_t* labels;
     float* loss_out;
     double* loss_sum_accum;
+    float* grads;            // zero_grad of the fused step: cleared on a side stream of the forward (nullptr: the caller did it)
+    size_t grads_bytes;
+    bool zero_bwd;           // the backward follows in the same call chain: clear its reductions with the forward's
 };
+
+// the fused forward encoder kernels run (and attn_conv1_fwd_kernel leaves the re-arranged conv2 weights in the workspace)
+static bool fwd_is_fused(const Dims& m, const float* x) {
+    return option_get("CONV_FUSED", 1) == 1 && conv_fused_supported(x, m.C, m.T, m.O);
+}
 
 static int model_forward(const mms_cnngru_desc* d, const float* x, const float* P, float* bn, int64_t* nbt, void* ws,
                          float* logits, cudaStream_t st, int phases = 7, const FusedLoss* fl = nullptr) {
@@ -381,32 +393,25 @@ static int model_forward(const mms_cnngru_desc* d, const float* x, const float* 
 
     const float* gate = m.attention ? w.gate : nullptr;
     // fused encoder kernels (conv_fused.cu): attention + conv1 in one cluster launch, BN1/ReLU/pool + conv2 in one launch
-    const bool fused = option_get("CONV_FUSED", 1) == 1 && conv_fused_supported(x, m.C, m.T, m.O);
+    const bool fused = fwd_is_fused(m, x);
     if (fused) {
-        Forker fkw(st);
-        if (phases == 7) {       // conv2's weights in the kernel's shared-memory order: side stream, beside attention + conv1
-            rc = launch_conv2_w_relayout_fwd(P + po.conv2_w, m.O, w.c2_wt, fkw.fork(1));
-            if (rc) return rc;
-            rc = fkw.mark(1);
-            if (rc) return rc;
-        }
         if (phases & 1) {
-            MMS_CUDA(cudaMemsetAsync(w.fwd_zero, 0, w.fwd_zero_bytes, st));
+            // one memset for the sums of this forward AND (training step in one call) the reductions / counters of the backward
+            // that follows: the two regions are adjacent, and a memset node on the chain between the loss and the first
+            // recurrence of the backward costs ~4 us
+            size_t zb = w.fwd_zero_bytes;
+            if (fl && fl->zero_bwd && m.need_grad) zb = (size_t)((w.bwd_zero + w.bwd_zero_bytes) - w.fwd_zero);
+            MMS_CUDA(cudaMemsetAsync(w.fwd_zero, 0, zb, st));
+            // conv2's weights in the orders bn_pool_conv2_fwd_kernel / conv2_bwd_kernel stage them are written by this launch
+            // too (a few CTAs, while their tiles are in flight): no re-layout launches, no cross-stream edges on the chain
             rc = launch_attn_conv1_fwd(x, P + po.conv1_w, P + po.ca_w1, P + po.ca_w2, m.attention ? 1 : 0, B, m.C, m.T, w.mean, w.gate,
-                                       w.y1, m.training ? w.stats1 : nullptr, st);
+                                       w.y1, m.training ? w.stats1 : nullptr, P + po.conv2_w, m.O, w.c2_wt,
+                                       m.need_grad && m.O == 32 ? w.c2_wd : nullptr, st);
             if (rc) return rc;
         }
         if (phases & 2) {
-            if (phases != 7) {   // phase-split call: make the re-arranged weights here
-                rc = launch_conv2_w_relayout_fwd(P + po.conv2_w, m.O, w.c2_wt, st);
-                if (rc) return rc;
-            }
-            rc = fkw.wait_mark();
-            if (rc) return rc;
             rc = launch_bn_pool_conv2_fwd(w.y1, w.stats1, P + po.bn1_g, P + po.bn1_b, rm1, rv1, nbt, m.Bg, m.training, w.c2_wt, 1, B,
                                           m.O, m.L1c, w.p1, w.y2, m.training ? w.stats2 : nullptr, st);
-            if (rc) return rc;
-            rc = fkw.join();
             if (rc) return rc;
         }
     }
@@ -426,6 +431,30 @@ static int model_forward(const mms_cnngru_desc* d, const float* x, const float* 
         if (rc) return rc;
     }
     if (!(phases & 4)) return MMS_OK;
+    // Side work that only reads parameters (or clears what the backward writes): forked here, joined in front of the top
+    // layer's recurrence, ~80 us later -- zero_grad (trainer.py:144) of the fused training step and the transposed W_ih copies
+    // of the backward's tensor-core dx products.
+    Forker fka(st);
+    {
+        const bool tc_bwd = m.need_grad && use_tc() && M >= TC_MIN_ROWS;
+        if ((fl && fl->grads) || tc_bwd) {
+            cudaStream_t s1 = fka.fork(1);
+            if (fl && fl->grads) MMS_CUDA(cudaMemsetAsync(fl->grads, 0, fl->grads_bytes, s1));
+            if (tc_bwd) {
+                const int I_t = m.layers == 1 ? m.O : 2 * H;
+                rc = launch_transpose_pad(P + po.w_ih[m.layers - 1], 3 * H, I_t, w.wT_top, 3 * H, 0, s1);
+                if (rc) return rc;
+                for (int l = 0; l < m.layers - 1; ++l) {
+                    const int I_l = l == 0 ? m.O : 2 * H;
+                    MMS_CUDA(cudaMemsetAsync(w.wT[l], 0, (size_t)I_l * 8 * H * sizeof(float), s1));
+                    for (int dd = 0; dd < 2; ++dd) {
+                        rc = launch_transpose_pad(P + po.w_ih[l] + (int64_t)dd * 3 * H * I_l, 3 * H, I_l, w.wT[l], 8 * H, dd * 4 * H, s1);
+                        if (rc) return rc;
+                    }
+                }
+            }
+        }
+    }
     rc = launch_bn_relu_pool_fwd(w.y2, w.stats2, P + po.bn2_g, P + po.bn2_b, rm2, rv2, nbt ? nbt + 1 : nullptr, B, m.O, m.L2c,
                                  m.training, 1, w.seq, st, m.Bg);
     if (rc) return rc;
@@ -466,23 +495,35 @@ static int model_forward(const mms_cnngru_desc* d, const float* x, const float* 
     }
     {   // top layer: forward direction over the whole sequence, reverse direction for its first step only
         const int l = m.layers - 1;
-        Forker fkf(st);
-        cudaStream_t s_side = fkf.fork(0);
+        cudaStream_t s_side = fka.fork(0);
+        // the B rows of the single reverse step: ahead of everything else on the side stream (the recurrence waits for them).
+        // With the dropout riding on the big product's A operand the dropped tensor does not exist yet: the few-row kernel
+        // applies the multipliers to its own operand rows.
+        const float* w_rev = P + po.w_ih[l] + (int64_t)3 * H * I;
+        const float* rows = (drop_on_a ? w.hs[l - 1] : in) + (int64_t)(L - 1) * I;
+        if (gemm_skinny_supported(rows, (int64_t)L * I, w_rev, I, 1, B, 3 * H, I)) {
+            rc = launch_gemm_skinny(rows, (int64_t)L * I, w_rev, I, 1, P + po.b_ih[l] + 3 * H, w.gi_tr, 3 * H, B, 3 * H, I, drop_on_a ? 1 : 0,
+                                    (int64_t)(l - 1) * DROP_LAYER_STRIDE + (int64_t)(L - 1) * I, (int64_t)L * I, m.p, d->rng_seed,
+                                    d->rng_offset, d->rng_offset_dev, s_side);
+            if (rc) return rc;
+            rows = nullptr;
+        }
         if (drop_on_a) {
             rc = launch_dropout_apply(w.hs[l - 1], w.outd[l - 1], M * 2 * H, (int64_t)(l - 1) * DROP_LAYER_STRIDE, m.p, d->rng_seed,
                                       d->rng_offset, d->rng_offset_dev, s_side);
             if (rc) return rc;
         }
-        rc = gemm_nt(in + (int64_t)(L - 1) * I, (int64_t)L * I, P + po.w_ih[l] + (int64_t)3 * H * I, I,
-                     P + po.b_ih[l] + 3 * H, w.gi_tr, 3 * H, B, 3 * H, I, s_side);     // B rows: beside the big one
-        if (rc) return rc;
+        if (rows) {
+            rc = gemm_nt(in + (int64_t)(L - 1) * I, (int64_t)L * I, w_rev, I, P + po.b_ih[l] + 3 * H, w.gi_tr, 3 * H, B, 3 * H, I, s_side);
+            if (rc) return rc;
+        }
         if (drop_on_a)
             rc = launch_tc_gemm_nt_drop(w.hs[l - 1], I, P + po.w_ih[l], I, P + po.b_ih[l], w.gi_tf, 3 * H, (int)M, 3 * H, I, 0, st, m.p,
                                         d->rng_seed, d->rng_offset, d->rng_offset_dev, (int64_t)(l - 1) * DROP_LAYER_STRIDE, 1);
         else
             rc = gemm_nt(in, I, P + po.w_ih[l], I, P + po.b_ih[l], w.gi_tf, 3 * H, (int)M, 3 * H, I, st);
         if (rc) return rc;
-        rc = fkf.join();
+        rc = fka.join();
         if (rc) return rc;
         mms_gru_dir_fwd dirs[2];
         memset(dirs, 0, sizeof(dirs));
@@ -513,7 +554,8 @@ static int model_forward(const mms_cnngru_desc* d, const float* x, const float* 
 // conv2 gradients, pool/ReLU backward of stage 1 (+ reductions), bit 2 = the rest.  A data-parallel caller
 // all-reduces the float64 reductions between the phases; 7 = everything.
 static int model_backward(const mms_cnngru_desc* d, const float* x, const float* P, const float* bn, void* ws,
-                          const float* dlogits, float* G, float* dx, cudaStream_t st, int phases = 7, bool head_done = false) {
+                          const float* dlogits, float* G, float* dx, cudaStream_t st, int phases = 7, bool head_done = false,
+                          bool bwd_zeroed = false) {
     Dims m;
     int rc = make_dims(d, &m);
     if (rc) return rc;
@@ -533,29 +575,15 @@ static int model_backward(const mms_cnngru_desc* d, const float* x, const float*
     const bool bwd2 = bn_fold() && !dx && option_get("CONV_BWD", 1) == 1 && conv_bwd_supported(x, m.C, m.T, m.O);
     Forker fk(st);
     if (phases & 1) {
-    MMS_CUDA(cudaMemsetAsync(w.bwd_zero, 0, w.bwd_zero_bytes, st));
-    const bool tc_bwd = use_tc() && M >= TC_MIN_ROWS;
-    if (bwd2 && phases == 7) {       // conv2 weights in the order conv2_bwd_kernel stages them: side stream, long before they are needed
+    if (!bwd_zeroed) MMS_CUDA(cudaMemsetAsync(w.bwd_zero, 0, w.bwd_zero_bytes, st));
+    const bool tc_bwd = use_tc() && M >= TC_MIN_ROWS;      // W_ih^T for the tensor-core dx products: made by the forward pass
+    // conv2's weights in conv2_bwd_kernel's order: left in the workspace by the fused forward (attn_conv1_fwd_kernel); after a
+    // per-layer forward they are made here, on a side stream, long before they are needed
+    if (bwd2 && phases == 7 && !fwd_is_fused(m, x)) {
         rc = launch_conv2_w_relayout(P + po.conv2_w, w.c2_wd, fk.fork(1));
         if (rc) return rc;
         rc = fk.mark(1);
         if (rc) return rc;
-    }
-    if (tc_bwd) {
-        // W_ih^T (zero-padded over the dq columns for the bottom layers) for the tensor-core dx products:
-        // side stream, hidden behind the head backward and the top-layer recurrence
-        cudaStream_t sw = fk.fork(1);
-        const int I_t = m.layers == 1 ? m.O : 2 * H;
-        rc = launch_transpose_pad(P + po.w_ih[m.layers - 1], 3 * H, I_t, w.wT_top, 3 * H, 0, sw);
-        if (rc) return rc;
-        for (int l = 0; l < m.layers - 1; ++l) {
-            const int I_l = l == 0 ? m.O : 2 * H;
-            MMS_CUDA(cudaMemsetAsync(w.wT[l], 0, (size_t)I_l * 8 * H * sizeof(float), sw));
-            for (int dd = 0; dd < 2; ++dd) {
-                rc = launch_transpose_pad(P + po.w_ih[l] + (int64_t)dd * 3 * H * I_l, 3 * H, I_l, w.wT[l], 8 * H, dd * 4 * H, sw);
-                if (rc) return rc;
-            }
-        }
     }
     // head: dhid feeds the top recurrence; with the fused forward it already exists and only the weight gradients remain,
     // which nothing on the chain needs -> side stream
@@ -588,7 +616,10 @@ static int model_backward(const mms_cnngru_desc* d, const float* x, const float*
         // h_prev = 0 for the single reverse step: dW_hh(reverse) = 0, only the bias gradient remains
         return gemm_tn(w.D_tr, 4 * H, 2 * H, H, nullptr, 0, 0, 1, nullptr, 0, G + po.b_hh[top] + 3 * H, B, 3 * H, 0, ss);
     };
-    const bool defer_top_wgrad = top >= 1 && option_get("WGRAD_DEFER", 1) == 1;
+    // MMS_WGRAD_DEFER: 0 = right behind the top recurrence (beside the dx product), 1 (default) = behind the next recurrence,
+    // 2 (experiment) = behind the dx product, i.e. beside the next recurrence only
+    const int defer_mode = top >= 1 ? option_get("WGRAD_DEFER", 1) : 0;
+    const bool defer_top_wgrad = defer_mode >= 1;
     {
         mms_gru_dir_bwd dirs[2];
         memset(dirs, 0, sizeof(dirs));
@@ -615,19 +646,26 @@ static int model_backward(const mms_cnngru_desc* d, const float* x, const float*
             // the single reverse step only touches the rows t = L-1: its B-row product goes to dx_extra on a side
             // stream, beside the big product below; the layer underneath adds it at t = L-1
             cudaStream_t sx = fk.fork(2);
-            rc = launch_gemm_nn(w.D_tr, 4 * H, P + po.w_ih[top] + (int64_t)3 * H * I_top, I_top, w.dx_extra, I_top, B, I_top, 3 * H, 0, sx);
-            if (rc) return rc;
-            if (m.drop_gru) {
-                rc = launch_dropout_rows(w.dx_extra, w.dx_extra, B, I_top, (int64_t)(top - 1) * DROP_LAYER_STRIDE + (int64_t)(L - 1) * I_top,
-                                         (int64_t)L * I_top, p, d->rng_seed, d->rng_offset, d->rng_offset_dev, sx);
+            const float* w_rev = P + po.w_ih[top] + (int64_t)3 * H * I_top;
+            if (gemm_skinny_supported(w.D_tr, 4 * H, w_rev, I_top, 0, B, I_top, 3 * H)) {
+                // few-row kernel, the dropout gradient on its result: the next recurrence waits for these rows
+                rc = launch_gemm_skinny(w.D_tr, 4 * H, w_rev, I_top, 0, nullptr, w.dx_extra, I_top, B, I_top, 3 * H, m.drop_gru ? 2 : 0,
+                                        (int64_t)(top - 1) * DROP_LAYER_STRIDE + (int64_t)(L - 1) * I_top, (int64_t)L * I_top, p,
+                                        d->rng_seed, d->rng_offset, d->rng_offset_dev, sx);
                 if (rc) return rc;
+            } else {
+                rc = launch_gemm_nn(w.D_tr, 4 * H, w_rev, I_top, w.dx_extra, I_top, B, I_top, 3 * H, 0, sx);
+                if (rc) return rc;
+                if (m.drop_gru) {
+                    rc = launch_dropout_rows(w.dx_extra, w.dx_extra, B, I_top, (int64_t)(top - 1) * DROP_LAYER_STRIDE + (int64_t)(L - 1) * I_top,
+                                             (int64_t)L * I_top, p, d->rng_seed, d->rng_offset, d->rng_offset_dev, sx);
+                    if (rc) return rc;
+                }
             }
         }
         // gradient w.r.t. the top layer's input
         if (tc_bwd && tc_gemm_supported(w.D_tf, 4 * H, w.wT_top, 3 * H, M, I_top, 3 * H)) {
             // tensor-core path: dx = D @ W_ih as an NT product against the transposed weights
-            rc = fk.join_one(1);          // the transposed weights (side stream 1) are needed from here on
-            if (rc) return rc;
             // the gradient through the dropout between layer top-1 and top (same multipliers as the forward) rides on this
             // product's epilogue instead of a separate pass over dxcur
             if (top >= 1 && m.drop_gru && option_get("DROP_FUSED", 1) == 1 && tc_gemm_nt_drop_supported(dxcur, I_top, I_top)) {
@@ -676,10 +714,14 @@ static int model_backward(const mms_cnngru_desc* d, const float* x, const float*
             g.D = w.D[l] + dd * 4 * H; g.d_bs = (int64_t)L * 8 * H; g.d_ts = 8 * H;
             g.t0 = dd ? L - 1 : 0; g.dt = dd ? -1 : 1; g.nsteps = L;
         }
+        if (defer_mode == 2 && l == top - 1) {
+            rc = top_wgrad();
+            if (rc) return rc;
+        }
         rc = launch_gru_bwd(dirs, 2, B, H, p, d->rng_seed, d->rng_offset, d->rng_offset_dev, st);
         if (rc) return rc;
         const bool tn_after = option_get("TN_AFTER_NT", 0) == 1;
-        if (defer_top_wgrad && l == top - 1 && !tn_after) {
+        if (defer_mode == 1 && l == top - 1 && !tn_after) {
             rc = top_wgrad();
             if (rc) return rc;
         }
@@ -715,7 +757,7 @@ static int model_backward(const mms_cnngru_desc* d, const float* x, const float*
             }
         }
         if (tn_after) {
-            if (defer_top_wgrad && l == top - 1) {
+            if (defer_mode == 1 && l == top - 1) {
                 rc = top_wgrad();
                 if (rc) return rc;
             }
@@ -898,16 +940,19 @@ extern "C" int mms_cnngru_train_step(const mms_cnngru_desc* d, const float* x, c
     make_params(m, &po);
     Workspace w;
     carve(m, (char*)workspace, &w);
-    MMS_CUDA(cudaMemsetAsync(grads, 0, po.total * sizeof(float), st));                      // trainer.py:144
     const bool fuse_head = option_get("HEAD_FUSED", 1) == 1;
-    const FusedLoss fl = {labels, loss_out, loss_sum_accum};
+    // zero_grad (trainer.py:144): nothing writes a gradient before the backward pass, so with the fused head the memset runs on
+    // a side stream of the forward instead of in front of its first kernel
+    if (!fuse_head) MMS_CUDA(cudaMemsetAsync(grads, 0, po.total * sizeof(float), st));
+    const bool zero_bwd = fuse_head && fwd_is_fused(m, x);
+    const FusedLoss fl = {labels, loss_out, loss_sum_accum, grads, po.total * sizeof(float), zero_bwd};
     rc = model_forward(d, x, params, bn_buffers, num_batches_tracked, workspace, logits, st, 7, fuse_head ? &fl : nullptr);  // trainer.py:146-147
     if (rc) return rc;
     if (!fuse_head) {
         rc = launch_cross_entropy(logits, labels, m.B, m.nc, loss_out, w.dlogits, loss_sum_accum, st, m.Bg);  // trainer.py:147
         if (rc) return rc;
     }
-    rc = model_backward(d, x, params, bn_buffers, workspace, w.dlogits, grads, nullptr, st, 7, fuse_head);        // trainer.py:148
+    rc = model_backward(d, x, params, bn_buffers, workspace, w.dlogits, grads, nullptr, st, 7, fuse_head, zero_bwd);        // trainer.py:148
     if (rc) return rc;
     return launch_adam(params, grads, exp_avg, exp_avg_sq, po.total, lr_dev, beta1, beta2, eps, weight_decay, step_dev,
                        scratch_dev, st);                                                          // trainer.py:149

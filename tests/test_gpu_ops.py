@@ -223,6 +223,41 @@ def test_gemms(lib):
     ok(lib.mms_gemm_tn_acc(P(Dd), 4 * H, 2 * H, H, None, 0, 0, 1, None, 0, P(bgd), M, 3 * H, 0, ST()))
     close(bgd, torch.cat([D[:, :2 * H], D[:, 3 * H:]], dim=1).sum(dim=0), 2e-5, "tn bias only")
 
+@pytest.mark.parametrize("M,N,K", [(64, 192, 128), (64, 128, 192), (5, 50, 32), (70, 9, 256)])
+def test_gemm_skinny(lib, M, N, K):
+    """Few-row products of the single reverse step: both operand orders against float64, and the two dropout
+    variants against the multipliers mms_dropout_apply draws for the same element ids."""
+    torch.manual_seed(M + K)
+    Lrows = 3                                              # the rows are a strided slice [m*Lrows + 2] of a taller operand
+    Afull = torch.randn(M * Lrows, K, dtype=torch.float64)
+    A = Afull.view(M, Lrows, K)[:, 2]
+    Wnt = torch.randn(N, K, dtype=torch.float64)
+    Wnn = torch.randn(K, (N + 3) // 4 * 4, dtype=torch.float64)        # row stride a multiple of 4 floats
+    bias = torch.randn(N, dtype=torch.float64)
+    Afd, Wntd, Wnnd, bd = dev(Afull), dev(Wnt), dev(Wnn), dev(bias)
+    a_ptr = Afd.data_ptr() + 2 * K * 4
+    Cd = torch.full((M, N), 7.0, device="cuda")
+    ok(lib.mms_gemm_skinny(a_ptr, Lrows * K, P(Wntd), K, 1, P(bd), P(Cd), N, M, N, K, 0, 0, 0, 0.0, 0, 0, None, ST()))
+    close(Cd, A @ Wnt.t() + bias, 1e-5, "skinny nt")
+    ldw = Wnn.shape[1]
+    ok(lib.mms_gemm_skinny(a_ptr, Lrows * K, P(Wnnd), ldw, 0, None, P(Cd), N, M, N, K, 0, 0, 0, 0.0, 0, 0, None, ST()))
+    close(Cd, A @ Wnn[:, :N], 1e-5, "skinny nn")
+
+    # dropout on the operand: ids base + m*row_stride + k, the multipliers of mms_dropout_apply over the whole tall operand
+    p, seed, off, base = 0.5, 11, 5, 1 << 40
+    mult = torch.ones(M * Lrows * K, device="cuda")
+    ok(lib.mms_dropout_apply(P(mult), P(mult), M * Lrows * K, base, p, seed, off, None, ST()))
+    mA = mult.view(M, Lrows, K)[:, 2].double().cpu()
+    ok(lib.mms_gemm_skinny(a_ptr, Lrows * K, P(Wntd), K, 1, P(bd), P(Cd), N, M, N, K, 1, base + 2 * K, Lrows * K, p, seed, off, None, ST()))
+    close(Cd, (A * mA) @ Wnt.t() + bias, 1e-5, "skinny nt, dropout on A")
+    assert 0.3 < (mA == 0).double().mean().item() < 0.7
+    # dropout on the result: ids base + m*row_stride + n
+    multC = torch.ones(M * Lrows * N, device="cuda")
+    ok(lib.mms_dropout_apply(P(multC), P(multC), M * Lrows * N, base, p, seed, off, None, ST()))
+    mC = multC.view(M, Lrows, N)[:, 2].double().cpu()
+    ok(lib.mms_gemm_skinny(a_ptr, Lrows * K, P(Wnnd), ldw, 0, None, P(Cd), N, M, N, K, 2, base + 2 * N, Lrows * N, p, seed, off, None, ST()))
+    close(Cd, (A @ Wnn[:, :N]) * mC, 1e-5, "skinny nn, dropout on C")
+
 
 def _gru_case(lib, B, L, H, I, reverse, steps=None, with_dout=True):
     from multimodalsignal_b200._ext import GruDirFwd, GruDirBwd
