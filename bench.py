@@ -588,14 +588,7 @@ def preprocess_measure(args, subjects=None):
         return staged[0], dict(zip(pp.WRIST_CHANNELS, staged[1:]))
 
     def process(rows, wr, proto, want_windows):
-        num = pp.resampled_length(rows.shape[1], 700, 64)
-        parts = [pp.resample_on_device(rows, num)]
-        for n, fs in pp.WRIST_CHANNELS.items():
-            y = pp.resample_on_device(wr[n], pp.resampled_length(wr[n].shape[1], fs, 64))
-            if y.shape[1] < num:
-                y = torch.cat([y, y[:, -1:].expand(-1, num - y.shape[1])], dim=1)
-            parts.append(y[:, :num])
-        streams = torch.cat(parts, dim=0).contiguous()
+        streams = pp.resample_subject_rows(rows, wr, 64)                # what preprocess_subject does with the staged rows
         starts, labels, window = pp.window_plan(proto, 64)
         sub = pp.SubjectStreams("S", streams, starts, labels, window, pp.CHEST_CHANNEL_NAMES + pp.WRIST_CHANNEL_NAMES)
         return sub.windows_f64() if want_windows else sub, len(labels), window

@@ -1,0 +1,446 @@
+// Register-resident FFT passes for the chirp-z resampler (resample.cu; reference preprocess.py:70-75 through
+// scipy.signal.resample), float64.
+//
+// A transform of length M = R_0 * R_1 * ... is a sequence of in-place passes.  Pass i works on blocks of Mc = R_i * S
+// consecutive elements (S = the product of the later radices): the R_i elements q * S + r of a block form one column,
+// which is transformed by an R_i-point DFT and (forward) multiplied by the inter-pass twiddle w_Mc^{r k}.  The previous
+// kernel ran the column DFT as log2(R) radix-2 stages through shared memory (8 round trips of 16-byte elements per pass,
+// a sincospi per element); here R = N1 * N2 and a thread holds a whole N1- or N2-point sub-transform in REGISTERS:
+//     stage 1   thread (column c, q0):  v[q1] = x[N2 q1 + q0],  DFT_N1 over q1,  v[k1] *= w_R^{q0 k1},  -> smem row N2 k1 + q0
+//     stage 2   thread (column c, k1):  v[q0] = smem row N2 k1 + q0,  DFT_N2 over q0,  v[k0] *= w_Mc^{r (k1 + N1 k0)},
+//                                       -> global row N2 k1 + k0  (which therefore holds frequency k1 + N1 k0)
+// so a pass moves every element global -> registers -> shared -> registers -> global: ONE shared-memory round trip, all
+// global loads of a thread in flight at once, twiddles as running products (one sincospi per thread for the intra-pass
+// factors w_R^{q0 k1}, two for the inter-pass ones) instead of a sincospi per element.  The inverse pass is the exact reverse (conjugate twiddles, DFTs with the
+// opposite sign, stages in the opposite order); the frequency order a forward transform leaves (digit-reversed in the
+// mixed radix N1, N2 of every pass) is what the inverse expects, and point-wise products are formed in that order.
+// N1 in {16, 12, 9, 8}, N2 in {16, 8}: radices 256, 192, 144, 128, 64 -- lengths 2^a, 3 * 2^a and 9 * 2^a.
+// Fused into the passes: the chirp pre-multiplication of (pairs of) real signals and the chirp filter (loads of the first
+// forward pass; the zero-padded part is not read), the point-wise product with the filter spectrum (stores of the last
+// forward pass), pruning of the outputs that are never used (stores of the last inverse pass).
+//
+// Everything here is __host__ __device__ so that tests/test_fft_fast_host.py can run the same pass bodies on the CPU
+// (threads emulated by loops) against a direct DFT.
+#pragma once
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define FF_HD __host__ __device__ __forceinline__
+#else
+#include <math.h>
+#define FF_HD inline
+struct double2 { double x, y; };
+static inline double2 make_double2(double x, double y) { double2 v; v.x = x; v.y = y; return v; }
+static inline void sincospi(double x, double* s, double* c) {
+    const long double a = 3.14159265358979323846264338327950288L * (long double)x;
+    *s = (double)sinl(a); *c = (double)cosl(a);
+}
+#endif
+
+namespace ff {
+
+FF_HD double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+FF_HD double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+FF_HD double2 cmulf(double2 a, double2 b) { return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x)); }
+FF_HD double2 cmulc(double2 a, double2 b) { return make_double2(fma(a.x, b.x, a.y * b.y), fma(a.y, b.x, -a.x * b.y)); }   // a * conj(b)
+
+// w_N^j = (cos, sin)(2 pi j / N), j < N, for the composite register DFTs
+// (local constant arrays: indexed by unrolled loop counters they fold into immediates, on the host and in device code)
+#define FF_SQ 0.70710678118654752440
+#define FF_C16 0.92387953251128675613
+#define FF_S16 0.38268343236508977173
+#define FF_H3 0.86602540378443864676
+#define FF_C91 0.76604444311897803520
+#define FF_S91 0.64278760968653932632
+#define FF_C92 0.17364817766693034885
+#define FF_S92 0.98480775301220805937
+#define FF_C94 0.93969262078590838405
+#define FF_S94 0.34202014332566873304
+template <int N>
+FF_HD double tw_cos(int j) {
+    if (N == 8) { const double t[8] = {1.0, FF_SQ, 0.0, -FF_SQ, -1.0, -FF_SQ, 0.0, FF_SQ}; return t[j & 7]; }
+    if (N == 9) { const double t[9] = {1.0, FF_C91, FF_C92, -0.5, -FF_C94, -FF_C94, -0.5, FF_C92, FF_C91}; return t[j % 9]; }
+    if (N == 12) { const double t[12] = {1.0, FF_H3, 0.5, 0.0, -0.5, -FF_H3, -1.0, -FF_H3, -0.5, 0.0, 0.5, FF_H3}; return t[j % 12]; }
+    const double t[16] = {1.0, FF_C16, FF_SQ, FF_S16, 0.0, -FF_S16, -FF_SQ, -FF_C16, -1.0, -FF_C16, -FF_SQ, -FF_S16, 0.0, FF_S16, FF_SQ, FF_C16};
+    return t[j & 15];
+}
+template <int N>
+FF_HD double tw_sin(int j) {
+    if (N == 8) { const double t[8] = {0.0, FF_SQ, 1.0, FF_SQ, 0.0, -FF_SQ, -1.0, -FF_SQ}; return t[j & 7]; }
+    if (N == 9) { const double t[9] = {0.0, FF_S91, FF_S92, FF_H3, FF_S94, -FF_S94, -FF_H3, -FF_S92, -FF_S91}; return t[j % 9]; }
+    if (N == 12) { const double t[12] = {0.0, 0.5, FF_H3, 1.0, FF_H3, 0.5, 0.0, -0.5, -FF_H3, -1.0, -FF_H3, -0.5}; return t[j % 12]; }
+    const double t[16] = {0.0, FF_S16, FF_SQ, FF_C16, 1.0, FF_C16, FF_SQ, FF_S16, 0.0, -FF_S16, -FF_SQ, -FF_C16, -1.0, -FF_C16, -FF_SQ, -FF_S16};
+    return t[j & 15];
+}
+
+// v *= (c + i SIGN s): SIGN = -1 forward (e^{-2 pi i jk/N}), +1 inverse; the trivial factors cost nothing once unrolled
+template <int SIGN>
+FF_HD double2 mul_const(double2 v, double c, double s) {
+    if (c == 1.0 && s == 0.0) return v;
+    if (c == -1.0 && s == 0.0) return make_double2(-v.x, -v.y);
+    const double ss = SIGN > 0 ? s : -s;
+    if (c == 0.0 && ss == 1.0) return make_double2(-v.y, v.x);
+    if (c == 0.0 && ss == -1.0) return make_double2(v.y, -v.x);
+    return make_double2(fma(v.x, c, -v.y * ss), fma(v.x, ss, v.y * c));
+}
+
+// natural order in, natural order out
+template <int N, int SIGN> struct Dft;
+template <int SIGN> struct Dft<2, SIGN> {
+    static FF_HD void run(double2* v) {
+        const double2 a = v[0], b = v[1];
+        v[0] = cadd(a, b);
+        v[1] = csub(a, b);
+    }
+};
+template <int SIGN> struct Dft<3, SIGN> {
+    static FF_HD void run(double2* v) {
+        const double2 s = cadd(v[1], v[2]), d = csub(v[1], v[2]);
+        const double2 m = make_double2(fma(-0.5, s.x, v[0].x), fma(-0.5, s.y, v[0].y));
+        const double h = SIGN > 0 ? FF_H3 : -FF_H3;           // X1 = m + i h d (inverse), m - i |h| d (forward)
+        v[0] = cadd(v[0], s);
+        v[1] = make_double2(fma(-h, d.y, m.x), fma(h, d.x, m.y));
+        v[2] = make_double2(fma(h, d.y, m.x), fma(-h, d.x, m.y));
+    }
+};
+template <int SIGN> struct Dft<4, SIGN> {
+    static FF_HD void run(double2* v) {
+        const double2 t0 = cadd(v[0], v[2]), t1 = csub(v[0], v[2]), t2 = cadd(v[1], v[3]), d = csub(v[1], v[3]);
+        const double2 t3 = SIGN > 0 ? make_double2(-d.y, d.x) : make_double2(d.y, -d.x);       // (+-i) d
+        v[0] = cadd(t0, t2);
+        v[2] = csub(t0, t2);
+        v[1] = cadd(t1, t3);
+        v[3] = csub(t1, t3);
+    }
+};
+// N = A * B:  n = B n1 + n0,  k = k1 + A k0:  X[k1 + A k0] = sum_n0 w_B^{n0 k0} ( w_N^{n0 k1} sum_n1 x[B n1 + n0] w_A^{n1 k1} )
+template <int A, int B, int SIGN>
+FF_HD void dft_comp(double2* v) {
+    constexpr int N = A * B;
+    double2 t[N];
+#pragma unroll
+    for (int n0 = 0; n0 < B; ++n0) {
+        double2 u[A];
+#pragma unroll
+        for (int n1 = 0; n1 < A; ++n1) u[n1] = v[B * n1 + n0];
+        Dft<A, SIGN>::run(u);
+#pragma unroll
+        for (int k1 = 0; k1 < A; ++k1) t[n0 * A + k1] = mul_const<SIGN>(u[k1], tw_cos<N>(n0 * k1), tw_sin<N>(n0 * k1));
+    }
+#pragma unroll
+    for (int k1 = 0; k1 < A; ++k1) {
+        double2 u[B];
+#pragma unroll
+        for (int n0 = 0; n0 < B; ++n0) u[n0] = t[n0 * A + k1];
+        Dft<B, SIGN>::run(u);
+#pragma unroll
+        for (int k0 = 0; k0 < B; ++k0) v[k1 + A * k0] = u[k0];
+    }
+}
+template <int SIGN> struct Dft<8, SIGN> { static FF_HD void run(double2* v) { dft_comp<4, 2, SIGN>(v); } };
+template <int SIGN> struct Dft<9, SIGN> { static FF_HD void run(double2* v) { dft_comp<3, 3, SIGN>(v); } };
+template <int SIGN> struct Dft<12, SIGN> { static FF_HD void run(double2* v) { dft_comp<4, 3, SIGN>(v); } };
+template <int SIGN> struct Dft<16, SIGN> { static FF_HD void run(double2* v) { dft_comp<4, 4, SIGN>(v); } };
+
+// e^{sign * 2 pi i e / Mc} for an integer exponent already reduced mod Mc
+FF_HD double2 cis_frac(uint64_t e, int64_t Mc, double sign) {
+    double s, c;
+    sincospi(2.0 * (double)e / (double)Mc, &s, &c);
+    return make_double2(c, sign * s);
+}
+// e^{sign * pi * i * ((n * b) mod 2P) / P} for integers with n * b < 2^53: the product is exact in float64, the quotient by
+// 2P is estimated with a reciprocal, and one fused multiply-add leaves the exact remainder (corrected by at most one period) --
+// a dozen float64 instructions where a 64-bit integer modulo by a run-time divisor costs over a hundred.
+FF_HD double2 chirp_prod(int64_t n, int64_t b, int64_t P, int sign) {
+    const double two_p = (double)(2 * P), inv_p = 1.0 / (double)P;
+    const double prod = (double)n * (double)b;
+    const double q = floor(prod * (0.5 * inv_p));
+    double r = fma(-q, two_p, prod);
+    if (r < 0.0) r += two_p;
+    if (r >= two_p) r -= two_p;
+    double s, c;
+    sincospi(r * inv_p, &s, &c);
+    return make_double2(c, sign > 0 ? s : -s);
+}
+// the chirp e^{sign pi i n^2 / P} (0 <= n <= 2^26) and the chirp times the linear phase e^{sign 2 pi i n k / P} (0 <= n, k < P <= 2^26)
+FF_HD double2 chirp_at(int64_t n, int64_t P, int sign) { return chirp_prod(n, n, P, sign); }
+FF_HD double2 chirp_shift_at(int64_t n, int64_t k, int64_t P, int sign) {
+    int64_t b = n + 2 * k;                                  // < 3P: one subtraction brings it below 2P, so n * b < 2 P^2 <= 2^53
+    if (b >= 2 * P) b -= 2 * P;
+    return chirp_prod(n, b, P, sign);
+}
+
+// 32-byte global accesses (two complex doubles of one thread): Blackwell's 256-bit ld / st.  The contiguous-tile side of a pass
+// has every thread own 16 consecutive elements; 16-byte accesses there would touch half a sector per lane and instruction.
+FF_HD void load2(const double2* p, double2* a, double2* b) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a->x), "=d"(a->y), "=d"(b->x), "=d"(b->y) : "l"(p) : "memory");
+#else
+    *a = p[0]; *b = p[1];
+#endif
+}
+FF_HD void store2(double2* p, double2 a, double2 b) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a.x), "d"(a.y), "d"(b.x), "d"(b.y) : "memory");
+#else
+    p[0] = a; p[1] = b;
+#endif
+}
+
+enum { LD_PLAIN = 0, LD_PAIR = 1, LD_FILTER = 2 };
+
+struct PassArgs {
+    double2* a;             // [n_sig][sig_stride] complex work buffer, transformed in place
+    int64_t sig_stride;
+    int64_t M;              // transform length
+    int64_t Mc;             // block size of this pass (= R * S)
+    int contig;             // S == 1 (the last forward / first inverse pass): a tile is TC consecutive blocks
+    int64_t ncols;          // columns in all: M / R (strided: (block, r) pairs; contiguous: blocks)
+    // loads of the first forward pass
+    int load_op;
+    const double* x;        // LD_PAIR: real signals [n_x][n_in]; paired: transform p = blockIdx.y takes rows 2p (real part) and
+                            // 2p + 1 (imaginary part, zero if absent); not paired: row p alone
+    int paired;
+    int64_t n_in;           // LD_PAIR: signal length; LD_FILTER: the filter covers lags (-n_in, n_out)
+    int n_x;
+    int64_t P, k0;          // chirp period and first bin
+    int sign;
+    int64_t n_out;
+    // stores
+    const double2* mul;     // forward: multiply by mul[i] (filter spectrum in the same order) before the store
+    int64_t n_keep;         // inverse: elements i >= n_keep of a signal are not stored
+};
+
+// position of tile row `row`, column `c`: strided tiles are [row][c] (lanes run over c), contiguous tiles are [c][row + row / N2]
+// (lanes run over q0 in stage 1 and over k1 in stage 2: the pad makes the stride-N2 accesses of stage 2 conflict-free)
+template <int R, int N2, int TC>
+FF_HD int tile_pos(int row, int c, int contig) {
+    return contig ? c * (R + R / N2) + row + row / N2 : row * TC + c;
+}
+template <int R, int N2, int TC>
+constexpr int tile_elems() { return TC * (R + R / N2); }
+
+template <int N1, int N2, int TC>
+FF_HD double2 pass_load(const PassArgs& p, int sig, const double2* base, int64_t idx) {
+    if (p.load_op == LD_PLAIN) return base[idx];
+    if (p.load_op == LD_PAIR) {
+        if (idx >= p.n_in) return make_double2(0.0, 0.0);
+        const double re = p.x[(int64_t)(p.paired ? 2 * sig : sig) * p.n_in + idx];
+        const double im = p.paired && 2 * sig + 1 < p.n_x ? p.x[(int64_t)(2 * sig + 1) * p.n_in + idx] : 0.0;
+        return cmulf(make_double2(re, im), chirp_shift_at(idx, p.k0, p.P, p.sign));
+    }
+    // LD_FILTER: b[i mod M] = conj(chirp(i)) for lags i in (-n_in, n_out)
+    if (idx < p.n_out) return chirp_at(idx, p.P, -p.sign);
+    if (p.M - idx < p.n_in) return chirp_at(p.M - idx, p.P, -p.sign);
+    return make_double2(0.0, 0.0);
+}
+
+// ---- forward pass -----------------------------------------------------------------------------------------------------
+// One CTA = one tile of TC columns; `tile` holds tile_elems() values.  tile_x = blockIdx.x, sig = blockIdx.y; the two stage
+// bodies are called once per thread with a block barrier in between.
+template <int N1, int N2, int TC>
+FF_HD void tile_origin(const PassArgs& p, int tile_x, int64_t* origin, int64_t* S, int64_t* r0, int* tc_eff) {
+    constexpr int R = N1 * N2;
+    *S = p.Mc / R;
+    const int64_t left = p.ncols - (int64_t)tile_x * TC;
+    *tc_eff = left < TC ? (int)left : TC;
+    if (p.contig) { *origin = (int64_t)tile_x * TC * R; *r0 = 0; }
+    else {
+        const int64_t g0 = (int64_t)tile_x * TC, blk0 = g0 / *S;
+        *r0 = g0 - blk0 * *S;
+        *origin = blk0 * p.Mc + *r0;
+    }
+}
+
+template <int N1, int N2, int TC, int NT>
+FF_HD void fwd_stage1(const PassArgs& p, int tid, int tile_x, int sig, double2* tile) {
+    constexpr int R = N1 * N2;
+    int64_t origin, S, r0;
+    int tc_eff;
+    tile_origin<N1, N2, TC>(p, tile_x, &origin, &S, &r0, &tc_eff);
+    const double2* base = p.a + (int64_t)sig * p.sig_stride;
+    for (int it = tid; it < TC * N2; it += NT) {
+        const int c = p.contig ? it / N2 : it % TC, q0 = p.contig ? it % N2 : it / TC;
+        if (c >= tc_eff) continue;
+        double2 v[N1];
+#pragma unroll
+        for (int q1 = 0; q1 < N1; ++q1) {
+            const int q = N2 * q1 + q0;
+            const int64_t idx = p.contig ? origin + (int64_t)c * R + q : origin + (int64_t)q * S + c;
+            v[q1] = pass_load<N1, N2, TC>(p, sig, base, idx);
+        }
+        Dft<N1, -1>::run(v);
+        const double2 wq = cis_frac((uint64_t)q0, R, -1.0);       // w_R^{q0 k1} as a running product over k1
+        double2 w = wq;
+        tile[tile_pos<R, N2, TC>(q0, c, p.contig)] = v[0];
+#pragma unroll
+        for (int k1 = 1; k1 < N1; ++k1) {
+            tile[tile_pos<R, N2, TC>(N2 * k1 + q0, c, p.contig)] = cmulf(v[k1], w);
+            w = cmulf(w, wq);
+        }
+    }
+}
+
+template <int N1, int N2, int TC, int NT>
+FF_HD void fwd_stage2(const PassArgs& p, int tid, int tile_x, int sig, const double2* tile) {
+    constexpr int R = N1 * N2;
+    int64_t origin, S, r0;
+    int tc_eff;
+    tile_origin<N1, N2, TC>(p, tile_x, &origin, &S, &r0, &tc_eff);
+    double2* base = p.a + (int64_t)sig * p.sig_stride;
+    for (int it = tid; it < TC * N1; it += NT) {
+        const int c = p.contig ? it / N1 : it % TC, k1 = p.contig ? it % N1 : it / TC;
+        if (c >= tc_eff) continue;
+        double2 v[N2];
+#pragma unroll
+        for (int q0 = 0; q0 < N2; ++q0) v[q0] = tile[tile_pos<R, N2, TC>(N2 * k1 + q0, c, p.contig)];
+        Dft<N2, -1>::run(v);
+        if (S > 1) {        // inter-pass twiddle w_Mc^{r (k1 + N1 k0)} = w^{r k1} (w^{r N1})^{k0}
+            const uint64_t r = (uint64_t)(r0 + c);
+            double2 w = cis_frac((r * (uint64_t)k1) % (uint64_t)p.Mc, p.Mc, -1.0);
+            const double2 step = cis_frac((r * (uint64_t)N1) % (uint64_t)p.Mc, p.Mc, -1.0);
+#pragma unroll
+            for (int k0 = 0; k0 < N2; ++k0) {
+                v[k0] = cmulf(v[k0], w);
+                w = cmulf(w, step);
+            }
+        }
+        if (p.contig) {         // 16 consecutive elements per thread: 32-byte accesses
+            const int64_t i0 = origin + (int64_t)c * R + N2 * k1;
+#pragma unroll
+            for (int k0 = 0; k0 < N2; k0 += 2) {
+                double2 o0 = v[k0], o1 = v[k0 + 1];
+                if (p.mul) {
+                    double2 m0, m1;
+                    load2(p.mul + i0 + k0, &m0, &m1);
+                    o0 = cmulf(o0, m0);
+                    o1 = cmulf(o1, m1);
+                }
+                store2(base + i0 + k0, o0, o1);
+            }
+        } else {
+#pragma unroll
+            for (int k0 = 0; k0 < N2; ++k0) {
+                const int64_t idx = origin + (int64_t)(N2 * k1 + k0) * S + c;
+                double2 o = v[k0];
+                if (p.mul) o = cmulf(o, p.mul[idx]);
+                base[idx] = o;
+            }
+        }
+    }
+}
+
+// ---- inverse pass (exact reverse of the forward pass, unnormalised: a forward + inverse transform multiplies by M) ------
+template <int N1, int N2, int TC, int NT>
+FF_HD void inv_stage2(const PassArgs& p, int tid, int tile_x, int sig, double2* tile) {
+    constexpr int R = N1 * N2;
+    int64_t origin, S, r0;
+    int tc_eff;
+    tile_origin<N1, N2, TC>(p, tile_x, &origin, &S, &r0, &tc_eff);
+    const double2* base = p.a + (int64_t)sig * p.sig_stride;
+    for (int it = tid; it < TC * N1; it += NT) {
+        const int c = p.contig ? it / N1 : it % TC, k1 = p.contig ? it % N1 : it / TC;
+        if (c >= tc_eff) continue;
+        double2 v[N2];
+        if (p.contig) {
+            const int64_t i0 = origin + (int64_t)c * R + N2 * k1;
+#pragma unroll
+            for (int k0 = 0; k0 < N2; k0 += 2) load2(base + i0 + k0, &v[k0], &v[k0 + 1]);
+        } else {
+#pragma unroll
+            for (int k0 = 0; k0 < N2; ++k0) v[k0] = base[origin + (int64_t)(N2 * k1 + k0) * S + c];
+        }
+        if (S > 1) {
+            const uint64_t r = (uint64_t)(r0 + c);
+            double2 w = cis_frac((r * (uint64_t)k1) % (uint64_t)p.Mc, p.Mc, 1.0);
+            const double2 step = cis_frac((r * (uint64_t)N1) % (uint64_t)p.Mc, p.Mc, 1.0);
+#pragma unroll
+            for (int k0 = 0; k0 < N2; ++k0) {
+                v[k0] = cmulf(v[k0], w);
+                w = cmulf(w, step);
+            }
+        }
+        Dft<N2, +1>::run(v);
+        const double2 wk = cis_frac((uint64_t)k1, R, -1.0);       // conj(w_R^{q0 k1}) as a running product over q0
+        double2 wi = wk;
+        tile[tile_pos<R, N2, TC>(N2 * k1, c, p.contig)] = v[0];
+#pragma unroll
+        for (int q0 = 1; q0 < N2; ++q0) {
+            tile[tile_pos<R, N2, TC>(N2 * k1 + q0, c, p.contig)] = cmulc(v[q0], wi);
+            wi = cmulf(wi, wk);
+        }
+    }
+}
+
+template <int N1, int N2, int TC, int NT>
+FF_HD void inv_stage1(const PassArgs& p, int tid, int tile_x, int sig, const double2* tile) {
+    constexpr int R = N1 * N2;
+    int64_t origin, S, r0;
+    int tc_eff;
+    tile_origin<N1, N2, TC>(p, tile_x, &origin, &S, &r0, &tc_eff);
+    double2* base = p.a + (int64_t)sig * p.sig_stride;
+    for (int it = tid; it < TC * N2; it += NT) {
+        const int c = p.contig ? it / N2 : it % TC, q0 = p.contig ? it % N2 : it / TC;
+        if (c >= tc_eff) continue;
+        // pruned outputs: the smallest index this item stores is that of row q0 (q1 = 0)
+        if ((p.contig ? origin + (int64_t)c * R + q0 : origin + (int64_t)q0 * S + c) >= p.n_keep) continue;
+        double2 v[N1];
+#pragma unroll
+        for (int k1 = 0; k1 < N1; ++k1) v[k1] = tile[tile_pos<R, N2, TC>(N2 * k1 + q0, c, p.contig)];
+        Dft<N1, +1>::run(v);
+#pragma unroll
+        for (int q1 = 0; q1 < N1; ++q1) {
+            const int q = N2 * q1 + q0;
+            const int64_t idx = p.contig ? origin + (int64_t)c * R + q : origin + (int64_t)q * S + c;
+            if (idx < p.n_keep) base[idx] = v[q1];
+        }
+    }
+}
+
+// ---- plan ------------------------------------------------------------------------------------------------------------
+// M = f * 2^b with f in {1, 3, 9}: an optional first pass of radix 192 = 12 x 16 or 144 = 9 x 16, then power-of-two passes of
+// 6..8 bits (64 = 8 x 8, 128 = 16 x 8, 256 = 16 x 16).  ok == false: not such a length (the caller keeps the generic kernels).
+struct FastPass { int n1, n2, tc; int64_t mc; };
+struct FastPlan { int n; FastPass p[8]; bool ok; };
+
+inline FastPlan make_fast_plan(int64_t M) {
+    FastPlan pl;
+    pl.n = 0; pl.ok = false;
+    int64_t rest = M, mc = M;
+    if (M >= 144 && M % 144 == 0 && ((M / 144) & (M / 144 - 1)) == 0) {
+        pl.p[pl.n++] = {9, 16, 16, mc}; rest = M / 144; mc = rest;
+    } else if (M >= 192 && M % 192 == 0 && ((M / 192) & (M / 192 - 1)) == 0) {
+        pl.p[pl.n++] = {12, 16, 16, mc}; rest = M / 192; mc = rest;
+    }
+    if (rest < 1 || (rest & (rest - 1)) != 0) return pl;
+    int bits = 0;
+    while (((int64_t)1 << bits) < rest) ++bits;
+    if (bits == 0) { pl.ok = pl.n > 0; return pl; }
+    const int np = (bits + 7) / 8;
+    if (bits < 6 * np || pl.n + np > 8) return pl;
+    int left = bits;
+    for (int i = 0; i < np; ++i) {
+        const int b = (left + (np - i) - 1) / (np - i);       // spread the bits evenly, larger radices first
+        left -= b;
+        if (b == 8) pl.p[pl.n++] = {16, 16, 16, mc};
+        else if (b == 7) pl.p[pl.n++] = {16, 8, 32, mc};
+        else pl.p[pl.n++] = {8, 8, 64, mc};
+        mc >>= b;
+    }
+    pl.ok = true;
+    return pl;
+}
+
+// smallest length >= need among 2^a, 9 * 2^(a-3) and 3 * 2^(a-1) that make_fast_plan accepts; 0 if none below 2^30
+inline int64_t fast_length_at_least(int64_t need) {
+    int64_t best = 0;
+    for (int a = 6; a <= 30; ++a) {
+        const int64_t cand[3] = {(int64_t)1 << a, a >= 7 ? (int64_t)9 << (a - 3) : 0, a >= 7 ? (int64_t)3 << (a - 1) : 0};
+        for (int j = 0; j < 3; ++j)
+            if (cand[j] >= need && (best == 0 || cand[j] < best) && make_fast_plan(cand[j]).ok) best = cand[j];
+        if (best && ((int64_t)1 << a) >= best) break;
+    }
+    return best;
+}
+
+}  // namespace ff

@@ -17,6 +17,8 @@
 // X1[k] = (Z[k] + conj Z[-k]) / 2, X2[k] = (Z[k] - conj Z[-k]) / 2i are separated while the spectrum is fixed up.  Stage A is
 // ~90 % of the traffic of a 700 Hz -> 64 Hz resampling, so the bytes moved per signal nearly halve.
 #include "mms_common.cuh"
+#include "fft_fast.cuh"
+#include <string.h>
 
 namespace mms {
 
@@ -27,21 +29,9 @@ __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
     return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
 }
 
-// e^{sign * pi * i * (n^2 mod 2P) / P}
-__device__ __forceinline__ double2 chirp(int64_t n, int64_t P, int sign) {
-    const uint64_t e = ((uint64_t)n * (uint64_t)n) % (uint64_t)(2 * P);
-    double s, c;
-    sincospi((double)e / (double)P, &s, &c);
-    return make_double2(c, sign > 0 ? s : -s);
-}
-
-// e^{sign * pi * i * ((n^2 + 2 n k) mod 2P) / P}: the chirp times the linear phase e^{sign * 2 pi i n k / P} (0 <= k < P)
-__device__ __forceinline__ double2 chirp_shift(int64_t n, int64_t k, int64_t P, int sign) {
-    const uint64_t e = ((uint64_t)n * (uint64_t)n + 2ull * (uint64_t)n * (uint64_t)k) % (uint64_t)(2 * P);
-    double s, c;
-    sincospi((double)e / (double)P, &s, &c);
-    return make_double2(c, sign > 0 ? s : -s);
-}
+// e^{sign * pi * i * (n^2 mod 2P) / P} and the chirp times the linear phase e^{sign * 2 pi i n k / P} (0 <= k < P): fft_fast.cuh
+__device__ __forceinline__ double2 chirp(int64_t n, int64_t P, int sign) { return ff::chirp_at(n, P, sign); }
+__device__ __forceinline__ double2 chirp_shift(int64_t n, int64_t k, int64_t P, int sign) { return ff::chirp_shift_at(n, k, P, sign); }
 
 __device__ __forceinline__ int bitrev(int v, int bits) { return bits ? (int)(__brev((unsigned)v) >> (32 - bits)) : 0; }
 
@@ -273,6 +263,87 @@ __global__ void __launch_bounds__(256) czt_post_real_kernel(const double2* __res
     }
 }
 
+
+// ---- register-resident passes (fft_fast.cuh) ---------------------------------------------------------------------------
+// One CTA = one tile of TC columns, 256 threads, one block barrier; two CTAs per SM (a thread holds 16 complex doubles).
+// grid = (signals, tiles): the CTAs of one tile position run next to each other, so the filter spectrum tile they all multiply
+// by (last forward pass) is read from DRAM once.
+template <int N1, int N2, int TC>
+__global__ void __launch_bounds__(256, 2) fft_fast_fwd_kernel(const ff::PassArgs p) {
+    extern __shared__ __align__(16) double2 ffs[];
+    ff::fwd_stage1<N1, N2, TC, 256>(p, threadIdx.x, blockIdx.y, blockIdx.x, ffs);
+    __syncthreads();
+    ff::fwd_stage2<N1, N2, TC, 256>(p, threadIdx.x, blockIdx.y, blockIdx.x, ffs);
+}
+template <int N1, int N2, int TC>
+__global__ void __launch_bounds__(256, 2) fft_fast_inv_kernel(const ff::PassArgs p) {
+    extern __shared__ __align__(16) double2 ffs[];
+    ff::inv_stage2<N1, N2, TC, 256>(p, threadIdx.x, blockIdx.y, blockIdx.x, ffs);
+    __syncthreads();
+    ff::inv_stage1<N1, N2, TC, 256>(p, threadIdx.x, blockIdx.y, blockIdx.x, ffs);
+}
+
+template <int N1, int N2, int TC>
+static int launch_fast_pass(const ff::PassArgs& p, int n_sig, int inverse, cudaStream_t st) {
+    constexpr int R = N1 * N2;
+    const size_t smem = (size_t)ff::tile_elems<R, N2, TC>() * sizeof(double2);
+    auto kf = fft_fast_fwd_kernel<N1, N2, TC>;
+    auto ki = fft_fast_inv_kernel<N1, N2, TC>;
+    static PerDeviceOnce attr_once;
+    if (attr_once.need()) {
+        MMS_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MMS_CUDA(cudaFuncSetAttribute(ki, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    const int64_t tiles = (p.ncols + TC - 1) / TC;
+    MMS_REQUIRE(tiles <= 65535, "fft_fast: %lld tiles exceed the grid limit", (long long)tiles);
+    dim3 grid(n_sig, (unsigned)tiles);
+    MMS_PROF_BEGIN(st);
+    if (inverse) ki<<<grid, 256, smem, st>>>(p);
+    else kf<<<grid, 256, smem, st>>>(p);
+    MMS_LAUNCH_CHECK(inverse ? "fft_fast_inv_kernel" : "fft_fast_fwd_kernel");
+    return MMS_OK;
+}
+
+// Hooks of a fast transform: loads of the first forward pass, multiplier of the last forward pass, outputs kept by the last
+// inverse pass (0 = all).  Only the fields named here are read.
+struct FastHooks {
+    int load_op = ff::LD_PLAIN;
+    const double* x = nullptr;
+    int paired = 0, n_x = 0, sign = 0;
+    int64_t n_in = 0, n_out = 0, P = 0, k0 = 0;
+    const double2* mul = nullptr;
+    int64_t n_keep = 0;
+};
+
+static int fft_fast(double2* a, int64_t sig_stride, int64_t M, int n_sig, int inverse, const FastHooks& h, cudaStream_t st) {
+    const ff::FastPlan pl = ff::make_fast_plan(M);
+    MMS_REQUIRE(pl.ok, "fft_fast: no plan for length %lld", (long long)M);
+    for (int ii = 0; ii < pl.n; ++ii) {
+        const int i = inverse ? pl.n - 1 - ii : ii;
+        const ff::FastPass& fp = pl.p[i];
+        ff::PassArgs p;
+        memset(&p, 0, sizeof(p));
+        p.a = a; p.sig_stride = sig_stride; p.M = M; p.Mc = fp.mc; p.contig = i == pl.n - 1 ? 1 : 0;
+        p.ncols = M / (fp.n1 * fp.n2);
+        p.n_keep = M;
+        if (!inverse && i == 0) {
+            p.load_op = h.load_op; p.x = h.x; p.paired = h.paired; p.n_in = h.n_in; p.n_x = h.n_x; p.P = h.P; p.k0 = h.k0; p.sign = h.sign;
+            p.n_out = h.n_out;
+        }
+        if (!inverse && i == pl.n - 1) p.mul = h.mul;
+        if (inverse && i == 0 && h.n_keep > 0) p.n_keep = h.n_keep;
+        int rc;
+        if (fp.n1 == 16 && fp.n2 == 16) rc = launch_fast_pass<16, 16, 16>(p, n_sig, inverse, st);
+        else if (fp.n1 == 16 && fp.n2 == 8) rc = launch_fast_pass<16, 8, 32>(p, n_sig, inverse, st);
+        else if (fp.n1 == 8 && fp.n2 == 8) rc = launch_fast_pass<8, 8, 64>(p, n_sig, inverse, st);
+        else if (fp.n1 == 9 && fp.n2 == 16) rc = launch_fast_pass<9, 16, 16>(p, n_sig, inverse, st);
+        else if (fp.n1 == 12 && fp.n2 == 16) rc = launch_fast_pass<12, 16, 16>(p, n_sig, inverse, st);
+        else { set_error("fft_fast: no kernel for radix %d x %d", fp.n1, fp.n2); return MMS_E_INVALID; }
+        if (rc) return rc;
+    }
+    return MMS_OK;
+}
+
 // ---- host side -----------------------------------------------------------------------------------
 static int64_t pow2_at_least(int64_t v) { int64_t m = 1; while (m < v) m <<= 1; return m; }
 
@@ -344,6 +415,26 @@ static inline unsigned grid_for(int64_t n) {
 
 struct ResampleDims { int64_t N, num, m2, M1, M2, Mmax; };
 
+// The fast path (MMS_RESAMPLE_FAST, default 1): smooth convolution lengths 2^a / 3 * 2^a / 9 * 2^a just above what the
+// chirp-z transforms need (the power of two above N + J - 1 = 4.58 M is 8.39 M; 9 * 2^19 = 4.72 M), register-resident
+// passes with the chirp multiplications, the filter product and the output pruning fused in.  Workspace layout:
+// filter [Mmax] | stage-A transforms [nA][M1] | stage-C transforms [n_sig][M2].
+struct FastDims { bool ok; bool paired; int nA; int64_t J, M1, M2, Mmax; };
+
+static FastDims fast_dims(const ResampleDims& d, int n_sig) {
+    FastDims f;
+    memset(&f, 0, sizeof(f));
+    if (option_get("RESAMPLE_FAST", 1) != 1) return f;
+    f.paired = n_sig >= 2 && option_get("RESAMPLE_PAIRED", 1) == 1;
+    f.J = f.paired ? 2 * d.m2 - 1 : d.m2;
+    f.nA = f.paired ? (n_sig + 1) / 2 : n_sig;
+    f.M1 = ff::fast_length_at_least(d.N + f.J - 1);
+    f.M2 = ff::fast_length_at_least(d.m2 + d.num - 1);
+    f.Mmax = f.M1 > f.M2 ? f.M1 : f.M2;
+    f.ok = f.M1 > 0 && f.M2 > 0;
+    return f;
+}
+
 static int resample_dims(int64_t n_in, int64_t n_out, ResampleDims* d) {
     MMS_REQUIRE(n_in >= 1 && n_out >= 1 && n_in < ((int64_t)1 << 26) && n_out < ((int64_t)1 << 26),
                 "resample: lengths must be in [1, 2^26) (got %lld -> %lld)", (long long)n_in, (long long)n_out);
@@ -363,6 +454,8 @@ using namespace mms;
 extern "C" int64_t mms_resample_workspace_bytes(int64_t n_in, int64_t n_out, int32_t n_sig) {
     ResampleDims d;
     if (resample_dims(n_in, n_out, &d) || n_sig < 1) return -1;
+    const FastDims f = fast_dims(d, n_sig);
+    if (f.ok) return (int64_t)sizeof(double2) * (f.Mmax + (int64_t)f.nA * f.M1 + (int64_t)n_sig * f.M2);
     return (int64_t)sizeof(double2) * d.Mmax * ((int64_t)n_sig + 1);
 }
 
@@ -373,6 +466,65 @@ extern "C" int mms_resample_f64(const double* x, int64_t n_in, int64_t n_out, in
     int rc = resample_dims(n_in, n_out, &d);
     if (rc) return rc;
     MMS_REQUIRE(x && y && workspace && n_sig >= 1, "resample_f64: bad arguments");
+    const FastDims f = fast_dims(d, n_sig);
+    if (f.ok) {
+        const int64_t need_f = (int64_t)sizeof(double2) * (f.Mmax + (int64_t)f.nA * f.M1 + (int64_t)n_sig * f.M2);
+        if (workspace_bytes < need_f) {
+            set_error("resample_f64: workspace %lld bytes < %lld", (long long)workspace_bytes, (long long)need_f);
+            return MMS_E_WORKSPACE;
+        }
+        double2* filt = (double2*)workspace;
+        double2* workA = filt + f.Mmax;
+        double2* workC = workA + (int64_t)f.nA * f.M1;
+        // stage A: chirp filter spectrum (generated by the first pass's loads), then the transforms of the (paired) signals
+        // with the chirp pre-multiplication on the loads and the filter product on the last pass's stores; the inverse keeps
+        // the J outputs that are used
+        FastHooks hf;
+        hf.load_op = ff::LD_FILTER; hf.n_in = d.N; hf.n_out = f.J; hf.P = d.N; hf.sign = -1;
+        rc = fft_fast(filt, f.M1, f.M1, 1, 0, hf, st);
+        if (rc) return rc;
+        FastHooks ha;
+        ha.load_op = ff::LD_PAIR; ha.x = x; ha.paired = f.paired ? 1 : 0; ha.n_x = n_sig; ha.n_in = d.N; ha.P = d.N; ha.sign = -1;
+        ha.k0 = f.paired ? d.N - (d.m2 - 1) : 0;           // first bin: -(m2 - 1) mod N
+        ha.mul = filt;
+        rc = fft_fast(workA, f.M1, f.M1, f.nA, 0, ha, st);
+        if (rc) return rc;
+        FastHooks hi;
+        hi.n_keep = f.J;
+        rc = fft_fast(workA, f.M1, f.M1, f.nA, 1, hi, st);
+        if (rc) return rc;
+        if (f.paired) {
+            dim3 grid(grid_for(f.M2), f.nA);
+            MMS_PROF_BEGIN(st);
+            spectrum_fix_pair_kernel<<<grid, 256, 0, st>>>(workA, workC, n_sig, f.M1, f.M2, d.N, d.num, d.m2);
+            MMS_LAUNCH_CHECK("spectrum_fix_pair_kernel");
+        } else {
+            for (int s = 0; s < n_sig; ++s) {
+                MMS_PROF_BEGIN(st);
+                spectrum_fix_kernel<<<grid_for(f.M2), 256, 0, st>>>(workA + (int64_t)s * f.M1, workC + (int64_t)s * f.M2, f.M1, f.M2, d.N, d.num,
+                                                                  d.m2);
+                MMS_LAUNCH_CHECK("spectrum_fix_kernel");
+            }
+        }
+        // stage C
+        FastHooks hg;
+        hg.load_op = ff::LD_FILTER; hg.n_in = d.m2; hg.n_out = d.num; hg.P = d.num; hg.sign = +1;
+        rc = fft_fast(filt, f.M2, f.M2, 1, 0, hg, st);
+        if (rc) return rc;
+        FastHooks hc;
+        hc.mul = filt;
+        rc = fft_fast(workC, f.M2, f.M2, n_sig, 0, hc, st);
+        if (rc) return rc;
+        FastHooks hj;
+        hj.n_keep = d.num;
+        rc = fft_fast(workC, f.M2, f.M2, n_sig, 1, hj, st);
+        if (rc) return rc;
+        dim3 grid(grid_for(d.num), n_sig);
+        MMS_PROF_BEGIN(st);
+        czt_post_real_kernel<<<grid, 256, 0, st>>>(workC, f.M2, d.num, y);
+        MMS_LAUNCH_CHECK("czt_post_real_kernel");
+        return MMS_OK;
+    }
     const int64_t need = (int64_t)sizeof(double2) * d.Mmax * ((int64_t)n_sig + 1);
     if (workspace_bytes < need) {
         set_error("resample_f64: workspace %lld bytes < %lld", (long long)workspace_bytes, (long long)need);

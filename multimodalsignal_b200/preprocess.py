@@ -20,6 +20,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import pickle
+import threading
 from pathlib import Path
 
 import numpy as np
@@ -67,6 +68,53 @@ def resample_on_device(x: torch.Tensor, num: int) -> torch.Tensor:
         ws = torch.empty(int(nbytes), dtype=torch.uint8, device=x.device)
         check(lib.mms_resample_f64(ptr(x[s0:s0 + k]), n, num, k, ptr(y[s0:s0 + k]), ptr(ws), int(nbytes), stream()))
     return y
+
+
+_SIDE_STREAM = {}
+
+
+def resample_many(items):
+    """``items``: list of ``(x [k, N] float64 CUDA, num)``.  The first one runs on the current stream, the others behind each
+    other on a side stream BESIDE it: the wrist channels of a subject are four calls of ~20 launches on a few hundred
+    thousand samples each -- launch-latency-bound, about as long as the chest call when run in sequence, hidden next to it."""
+    if len(items) == 1:
+        return [resample_on_device(*items[0])]
+    dev = items[0][0].device
+    key = (dev.index, threading.get_ident())
+    if key not in _SIDE_STREAM:
+        _SIDE_STREAM[key] = torch.cuda.Stream(device=dev)
+    cur, side = torch.cuda.current_stream(dev), _SIDE_STREAM[key]
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        rest = [resample_on_device(x, n) for x, n in items[1:]]
+    first = resample_on_device(*items[0])
+    cur.wait_stream(side)
+    for y in rest:
+        y.record_stream(cur)
+    return [first] + rest
+
+
+def resample_subject_rows(chest_rows, wrist_rows=None, target_fs=None):
+    """Chest rows ``[8, N]`` at 700 Hz (+ the wrist rows of ``WRIST_CHANNELS``, each at its own rate) -> float64
+    ``[n_channels, num]`` at ``target_fs``; wrist streams that end a few samples early are padded with their last value
+    (the wrist clock is not the chest clock), longer ones cut."""
+    target_fs = RAW_FS if target_fs is None else target_fs
+    num = resampled_length(chest_rows.shape[1], ORIGINAL_CHEST_FS, target_fs)
+    items = [(chest_rows, num)]
+    if wrist_rows:
+        items += [(wrist_rows[name], resampled_length(wrist_rows[name].shape[1], fs, target_fs)) for name, fs in WRIST_CHANNELS.items()]
+    ys = resample_many(items)
+    if len(ys) == 1:
+        return ys[0]
+    out = torch.empty(sum(y.shape[0] for y in ys), num, dtype=torch.float64, device=chest_rows.device)
+    r0 = 0
+    for y in ys:
+        k, nw = y.shape
+        out[r0:r0 + k, :min(nw, num)] = y[:, :num]
+        if nw < num:
+            out[r0:r0 + k, nw:] = y[:, -1:]
+        r0 += k
+    return out
 
 
 def resample_signal(signal_data, original_fs, target_fs):
@@ -285,18 +333,8 @@ def preprocess_subject(sid, data, protocol, target_fs=None, include_wrist=False,
     staged = _UPLOADER.groups(groups, device)          # the whole subject: one staging pass, one H2D copy
     rows = staged[0]
     num = resampled_length(rows.shape[1], ORIGINAL_CHEST_FS, target_fs)
-    streams = resample_on_device(rows, num)
-    names = list(CHEST_CHANNEL_NAMES)
-    if include_wrist:
-        parts = []
-        for (name, fs), r in zip(WRIST_CHANNELS.items(), staged[1:]):
-            nw = resampled_length(r.shape[1], fs, target_fs)
-            y = resample_on_device(r, nw)
-            if nw < num:                                   # wrist clock ends a few samples early: pad with the last value
-                y = torch.cat([y, y[:, -1:].expand(-1, num - nw)], dim=1)
-            parts.append(y[:, :num])
-        streams = torch.cat([streams] + parts, dim=0).contiguous()
-        names += WRIST_CHANNEL_NAMES
+    streams = resample_subject_rows(rows, dict(zip(WRIST_CHANNELS, staged[1:])) if include_wrist else None, target_fs)
+    names = list(CHEST_CHANNEL_NAMES) + (list(WRIST_CHANNEL_NAMES) if include_wrist else [])
     starts, labels, window = window_plan(protocol, target_fs)
     if len(starts) and starts.max() + window > num:
         raise ValueError(f"{sid}: a window runs past the end of the resampled stream")
