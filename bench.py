@@ -595,8 +595,8 @@ def preprocess_measure(args, subjects=None):
 
     staged = [on_device(i) for i in range(len(subs))]
     torch.cuda.synchronize()
-    for i in range(min(2, len(subs))):                                  # warm-up
-        process(*staged[i], protos[i], True)
+    for i in range(len(subs)):                                          # warm-up: every subject once (each has its own lengths -> its own
+        process(*staged[i], protos[i], True)                            # workspace sizes in the caching allocator)
     torch.cuda.synchronize()
     sampler = ClockSampler(torch.cuda.current_device())
     sampler.start()
@@ -674,11 +674,11 @@ def preprocess_measure(args, subjects=None):
                                             "subjects": len(subs), "minutes": args.minutes, "windows_per_pass": nwin // reps},
             "e2e": {"value": len(subs) / e2e_s, "unit": "subjects/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "clocks": clocks,
-            "roofline": {"kernel": "resample + window pipeline (fft_pass_kernel dominates)", "bound": "hbm", "unit": "GB/s",
+            "roofline": {"kernel": "resample + window pipeline (fft_fast_fwd_kernel / fft_fast_inv_kernel dominate)", "bound": "hbm", "unit": "GB/s",
                          "achieved": algo * reps / dev_s / 1e9, "peak": pk["hbm_gbs"], "frac": algo * reps / dev_s / 1e9 / pk["hbm_gbs"],
                          "traffic": None, "algorithmic_bytes_per_pass": algo,
-                         "note": "chirp-z FFT makes ~30 passes over 2^23 complex doubles per signal; algorithmic bytes count the "
-                                 "source once and the windows once"},
+                         "note": "chirp-z: 12 register-resident passes over 9 * 2^19 complex doubles per PAIR of chest signals + 6 over 9 * 2^16 "
+                                 "per signal (DESIGN section 5); algorithmic bytes count the source once and the windows once"},
             "cpu_baseline": {"value": 1.0 / cpu_s, "unit": "subjects/s", "cores": os.cpu_count(), "kind": "port",
                              "sample": "oracle/preprocess_oracle.py on 1 synthetic subject, chest channels only (8 FFT round trips "
                                        "of N = 4.2 M + window stacking); the reference's scipy path measured the same arithmetic"}}

@@ -162,6 +162,19 @@ FF_HD double2 chirp_prod(int64_t n, int64_t b, int64_t P, int sign) {
     sincospi(r * inv_p, &s, &c);
     return make_double2(c, sign > 0 ? s : -s);
 }
+// v mod m for non-negative integers held exactly in float64 (v < 2^53), inv_m = 1 / m
+FF_HD double mod_exact(double v, double m, double inv_m) {
+    const double q = floor(v * inv_m);
+    double r = fma(-q, m, v);
+    if (r < 0.0) r += m;
+    if (r >= m) r -= m;
+    return r;
+}
+FF_HD double2 cis_pi(double x, int sign) {
+    double s, c;
+    sincospi(x, &s, &c);
+    return make_double2(c, sign > 0 ? s : -s);
+}
 // the chirp e^{sign pi i n^2 / P} (0 <= n <= 2^26) and the chirp times the linear phase e^{sign 2 pi i n k / P} (0 <= n, k < P <= 2^26)
 FF_HD double2 chirp_at(int64_t n, int64_t P, int sign) { return chirp_prod(n, n, P, sign); }
 FF_HD double2 chirp_shift_at(int64_t n, int64_t k, int64_t P, int sign) {
@@ -263,11 +276,37 @@ FF_HD void fwd_stage1(const PassArgs& p, int tid, int tile_x, int sig, double2* 
         const int c = p.contig ? it / N2 : it % TC, q0 = p.contig ? it % N2 : it / TC;
         if (c >= tc_eff) continue;
         double2 v[N1];
+        if (p.load_op == LD_PAIR && !p.contig && p.P <= ((int64_t)1 << 25)) {
+            // chirp of the N1 elements of this thread (stride D = N2 S) from ONE exact evaluation and a second-order recurrence:
+            //   phi(n + D) - phi(n) = pi D (2n + D + 2 k0) / P,   and that difference grows by 2 pi D^2 / P per step
+            // (three sincospi per thread instead of one per element; every product below stays under 2^53)
+            const int64_t n0 = origin + (int64_t)q0 * S + c, D = (int64_t)N2 * S;
 #pragma unroll
-        for (int q1 = 0; q1 < N1; ++q1) {
-            const int q = N2 * q1 + q0;
-            const int64_t idx = p.contig ? origin + (int64_t)c * R + q : origin + (int64_t)q * S + c;
-            v[q1] = pass_load<N1, N2, TC>(p, sig, base, idx);
+            for (int q1 = 0; q1 < N1; ++q1) v[q1] = make_double2(0.0, 0.0);
+            if (n0 < p.n_in) {
+                const double two_p = (double)(2 * p.P), inv_p = 1.0 / (double)p.P, inv_2p = 0.5 * inv_p;
+                const double dm = mod_exact((double)D, two_p, inv_2p);
+                const double bm = mod_exact((double)(2 * n0 + D + 2 * p.k0), two_p, inv_2p);
+                double2 ch = chirp_shift_at(n0, p.k0, p.P, p.sign);
+                double2 ratio = cis_pi(mod_exact(bm * dm, two_p, inv_2p) * inv_p, p.sign);
+                const double2 grow = cis_pi(mod_exact(2.0 * dm * dm, two_p, inv_2p) * inv_p, p.sign);
+                const double* xr = p.x + (int64_t)(p.paired ? 2 * sig : sig) * p.n_in;
+                const double* xi = p.paired && 2 * sig + 1 < p.n_x ? p.x + (int64_t)(2 * sig + 1) * p.n_in : nullptr;
+#pragma unroll
+                for (int q1 = 0; q1 < N1; ++q1) {
+                    const int64_t idx = n0 + (int64_t)q1 * D;
+                    if (idx < p.n_in) v[q1] = cmulf(make_double2(xr[idx], xi ? xi[idx] : 0.0), ch);
+                    ch = cmulf(ch, ratio);
+                    ratio = cmulf(ratio, grow);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int q1 = 0; q1 < N1; ++q1) {
+                const int q = N2 * q1 + q0;
+                const int64_t idx = p.contig ? origin + (int64_t)c * R + q : origin + (int64_t)q * S + c;
+                v[q1] = pass_load<N1, N2, TC>(p, sig, base, idx);
+            }
         }
         Dft<N1, -1>::run(v);
         const double2 wq = cis_frac((uint64_t)q0, R, -1.0);       // w_R^{q0 k1} as a running product over k1

@@ -70,26 +70,35 @@ def resample_on_device(x: torch.Tensor, num: int) -> torch.Tensor:
     return y
 
 
-_SIDE_STREAM = {}
+_SIDE_STREAMS = {}
+_MANY_ORDER = int(os.environ.get("MMS_RESAMPLE_MANY_ORDER", "1"))     # 0 = everything on the current stream (A/B)
 
 
 def resample_many(items):
-    """``items``: list of ``(x [k, N] float64 CUDA, num)``.  The first one runs on the current stream, the others behind each
-    other on a side stream BESIDE it: the wrist channels of a subject are four calls of ~20 launches on a few hundred
-    thousand samples each -- launch-latency-bound, about as long as the chest call when run in sequence, hidden next to it."""
-    if len(items) == 1:
-        return [resample_on_device(*items[0])]
+    """``items``: list of ``(x [k, N] float64 CUDA, num)``.  The first (large) one runs on the current stream, every other one
+    on its own HIGH-PRIORITY side stream beside it.  The wrist channels of a subject are short transforms of ~20 launches
+    each whose grids do not fill the GPU: a launch lasts as long as one CTA (10-25 us), so run one after the other they cost
+    about as much device time as the 30x larger chest call.  Beside each other their latencies overlap, and with priority
+    their few CTAs get the slots the chest kernels' CTAs free every couple of microseconds instead of waiting for a kernel
+    boundary."""
+    if len(items) == 1 or _MANY_ORDER == 0:
+        return [resample_on_device(x, n) for x, n in items]
     dev = items[0][0].device
     key = (dev.index, threading.get_ident())
-    if key not in _SIDE_STREAM:
-        _SIDE_STREAM[key] = torch.cuda.Stream(device=dev)
-    cur, side = torch.cuda.current_stream(dev), _SIDE_STREAM[key]
-    side.wait_stream(cur)
-    with torch.cuda.stream(side):
-        rest = [resample_on_device(x, n) for x, n in items[1:]]
+    pool = _SIDE_STREAMS.setdefault(key, [])
+    while len(pool) < len(items) - 1:
+        pool.append(torch.cuda.Stream(device=dev, priority=-1))
+    cur = torch.cuda.current_stream(dev)
+    ready = torch.cuda.Event()
+    ready.record(cur)                       # the inputs exist here
+    rest = []
+    for (x, n), side in zip(items[1:], pool):
+        side.wait_event(ready)
+        with torch.cuda.stream(side):
+            rest.append(resample_on_device(x, n))
     first = resample_on_device(*items[0])
-    cur.wait_stream(side)
-    for y in rest:
+    for y, side in zip(rest, pool):
+        cur.wait_stream(side)
         y.record_stream(cur)
     return [first] + rest
 
@@ -97,12 +106,20 @@ def resample_many(items):
 def resample_subject_rows(chest_rows, wrist_rows=None, target_fs=None):
     """Chest rows ``[8, N]`` at 700 Hz (+ the wrist rows of ``WRIST_CHANNELS``, each at its own rate) -> float64
     ``[n_channels, num]`` at ``target_fs``; wrist streams that end a few samples early are padded with their last value
-    (the wrist clock is not the chest clock), longer ones cut."""
+    (the wrist clock is not the chest clock), longer ones cut.  Wrist channels of equal rate and length share a call."""
     target_fs = RAW_FS if target_fs is None else target_fs
     num = resampled_length(chest_rows.shape[1], ORIGINAL_CHEST_FS, target_fs)
     items = [(chest_rows, num)]
     if wrist_rows:
-        items += [(wrist_rows[name], resampled_length(wrist_rows[name].shape[1], fs, target_fs)) for name, fs in WRIST_CHANNELS.items()]
+        groups = []                                     # [fs, n, [rows...]] of consecutive channels (the output keeps their order)
+        for name, fs in WRIST_CHANNELS.items():
+            r = wrist_rows[name]
+            if groups and groups[-1][0] == fs and groups[-1][1] == r.shape[1]:
+                groups[-1][2].append(r)
+            else:
+                groups.append([fs, r.shape[1], [r]])
+        for fs, n, rs in groups:
+            items.append((rs[0] if len(rs) == 1 else torch.cat(rs, dim=0), resampled_length(n, fs, target_fs)))
     ys = resample_many(items)
     if len(ys) == 1:
         return ys[0]

@@ -143,7 +143,7 @@ static int check_length(int64_t M) {
         transform(got.data(), M, M, 2, false, &hooks);
     }
     const double e_ld = maxdiff(ref.data(), got.data(), 2 * M);
-    if (e_ld > 0) { printf("  paired chirp loads differ by %.3e\n", e_ld); ++bad; }
+    if (e_ld > 1e-13 * 64) { printf("  paired chirp loads differ by %.3e\n", e_ld); ++bad; }       // chirp by recurrence: not bit-equal
 
     for (int64_t i = 0; i < M; ++i) {
         double2 v = make_double2(0, 0);

@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-T=r2c26
+T=r2c28
 timeout 600 python -m pytest tests/test_gpu_preprocess.py -m gpu -q -x > gpurun_out/${T}_pp.log 2>&1; echo "preprocess tests rc=$?"; tail -5 gpurun_out/${T}_pp.log
 for fast in 1 0; do
 MMS_RESAMPLE_FAST=$fast timeout 300 python - <<'PY'
@@ -31,6 +31,7 @@ PY
 done
 timeout 300 python bench.py --workload preprocess > gpurun_out/${T}_preprocess.json 2>gpurun_out/${T}_preprocess.err; echo "bench preprocess rc=$?"; python - <<'PY'
 import json
-p=json.load(open('gpurun_out/r2c26_preprocess.json'))
+p=json.load(open('gpurun_out/r2c28_preprocess.json'))
 print({k:p[k] for k in ('value','unit','e2e') if k in p}); print(p.get('roofline'))
 PY
+timeout 300 python tools/subject_probe.py 2>&1 | tail -3
