@@ -152,15 +152,50 @@ __global__ void __launch_bounds__(256) bn_relu_pool_fwd_tm_kernel(const float* _
     const int b = blockIdx.y, j0 = blockIdx.x * 32;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const double n = (double)Bn * (double)Lin;
+    // even rows, 8-byte aligned: the raw values of every (channel, window) of this thread are requested BEFORE the float64
+    // BatchNorm constants are formed (they do not depend on them): one 64-bit load per window, the left neighbour by shuffle
+    const bool fast = (C & 7) == 0 && (Lin & 1) == 0 && (reinterpret_cast<uintptr_t>(y) & 7) == 0;
+    float2 raw[8];
+    float left[8];
+    if (fast) {
+        const int j = j0 + lane;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            raw[i] = make_float2(0.f, 0.f);
+            left[i] = 0.f;
+            if (8 * i < C && j < Lout) {
+                const float* row = y + ((size_t)b * C + warp + 8 * i) * Lin;
+                raw[i] = __ldg(reinterpret_cast<const float2*>(row + 2 * j));
+                if (lane == 0 && j > 0) left[i] = __ldg(row + 2 * j - 1);
+            }
+        }
+    }
     if (threadIdx.x < C) {
         const BnAffine af = bn_affine(training, stats, gamma, beta, rm, rv, threadIdx.x, C, n);
         sa[threadIdx.x] = af.a;
         sb[threadIdx.x] = af.b;
     }
     __syncthreads();
-    for (int c = warp; c < C; c += 8) {
+    if (fast) {
         const int j = j0 + lane;
-        if (j < Lout) tile[lane][c] = pooled_value(y + ((size_t)b * C + c) * Lin, j, Lin, sa[c], sb[c]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (8 * i < C) {
+                const int c = warp + 8 * i;
+                const float a = sa[c], bs = sb[c];
+                const float z0 = fmaxf(fmaf(a, raw[i].x, bs), 0.f), z1 = fmaxf(fmaf(a, raw[i].y, bs), 0.f);
+                float zl = __shfl_up_sync(0xffffffffu, z1, 1);
+                // first window of the tile: its left element comes from the previous tile (none for j = 0: the pool pads with
+                // -inf, and 0 is as good since every candidate is >= 0 after the ReLU)
+                if (lane == 0) zl = j > 0 ? fmaxf(fmaf(a, left[i], bs), 0.f) : 0.f;
+                if (j < Lout) tile[lane][c] = fmaxf(zl, fmaxf(z0, z1));
+            }
+        }
+    } else {
+        for (int c = warp; c < C; c += 8) {
+            const int j = j0 + lane;
+            if (j < Lout) tile[lane][c] = pooled_value(y + ((size_t)b * C + c) * Lin, j, Lin, sa[c], sb[c]);
+        }
     }
     __syncthreads();
     for (int jj = warp; jj < 32; jj += 8) {

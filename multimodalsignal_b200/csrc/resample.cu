@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(256) spectrum_fix_kernel(const double2* __rest
 // Paired version of spectrum_fix_kernel: conv holds the bins k = j - (m2 - 1), j < 2 m2 - 1, of z = x1 + i x2 (pair blockIdx.y at
 // conv + blockIdx.y * M); the two real signals' spectra are separated, fixed up as above and written to a2 + (2p) * M2 and
 // a2 + (2p + 1) * M2 (a different region of the workspace: nothing is read after it has been overwritten).
-__global__ void __launch_bounds__(256) spectrum_fix_pair_kernel(const double2* __restrict__ conv, double2* __restrict__ a2, int n_sig,
+__global__ void __launch_bounds__(256, 2) spectrum_fix_pair_kernel(const double2* __restrict__ conv, double2* __restrict__ a2, int n_sig,
                                                                 int64_t M, int64_t M2, int64_t N, int64_t num, int64_t m2) {
     const int p = blockIdx.y;
     const double2* cv = conv + (int64_t)p * M;
