@@ -70,6 +70,13 @@ bool tc_gemm_nt_drop_supported(const float*, int64_t, int);
 bool tc_gemm_supported(const float*, int64_t, const float*, int64_t, int, int, int);
 constexpr int TC_MIN_ROWS = 1024;      // below this a single tcgen05 CTA is pure latency: the SIMT kernels win
 int launch_transpose_pad(const float*, int, int, float*, int64_t, int, cudaStream_t);
+struct TransposeJobs {
+    const float* W[4];
+    float* out[4];
+    int64_t ldo[4];
+    int rows[4], cols[4], col_off[4], pad[4];
+};
+int launch_transpose_pad_multi(const TransposeJobs&, int, cudaStream_t);
 int launch_dropout_apply(const float*, float*, int64_t, int64_t, float, uint64_t, uint64_t, const int64_t*, cudaStream_t);
 int launch_dropout_rows(const float*, float*, int, int, int64_t, int64_t, float, uint64_t, uint64_t, const int64_t*, cudaStream_t);
 
@@ -441,16 +448,31 @@ static int model_forward(const mms_cnngru_desc* d, const float* x, const float* 
             cudaStream_t s1 = fka.fork(1);
             if (fl && fl->grads) MMS_CUDA(cudaMemsetAsync(fl->grads, 0, fl->grads_bytes, s1));
             if (tc_bwd) {
+                // W_ih^T of every layer, up to four matrices per launch; the bottom layers' copies carry zero columns where the
+                // D rows hold dq
+                TransposeJobs jobs;
+                int nj = 0;
+                auto add = [&](const float* Wm, int cols, float* out, int64_t ldo, int off, int pad) -> int {
+                    jobs.W[nj] = Wm; jobs.out[nj] = out; jobs.ldo[nj] = ldo; jobs.rows[nj] = 3 * H; jobs.cols[nj] = cols;
+                    jobs.col_off[nj] = off; jobs.pad[nj] = pad;
+                    if (++nj < 4) return MMS_OK;
+                    const int r = launch_transpose_pad_multi(jobs, nj, s1);
+                    nj = 0;
+                    return r;
+                };
                 const int I_t = m.layers == 1 ? m.O : 2 * H;
-                rc = launch_transpose_pad(P + po.w_ih[m.layers - 1], 3 * H, I_t, w.wT_top, 3 * H, 0, s1);
+                rc = add(P + po.w_ih[m.layers - 1], I_t, w.wT_top, 3 * H, 0, 0);
                 if (rc) return rc;
                 for (int l = 0; l < m.layers - 1; ++l) {
                     const int I_l = l == 0 ? m.O : 2 * H;
-                    MMS_CUDA(cudaMemsetAsync(w.wT[l], 0, (size_t)I_l * 8 * H * sizeof(float), s1));
                     for (int dd = 0; dd < 2; ++dd) {
-                        rc = launch_transpose_pad(P + po.w_ih[l] + (int64_t)dd * 3 * H * I_l, 3 * H, I_l, w.wT[l], 8 * H, dd * 4 * H, s1);
+                        rc = add(P + po.w_ih[l] + (int64_t)dd * 3 * H * I_l, I_l, w.wT[l], 8 * H, dd * 4 * H, H);
                         if (rc) return rc;
                     }
+                }
+                if (nj) {
+                    rc = launch_transpose_pad_multi(jobs, nj, s1);
+                    if (rc) return rc;
                 }
             }
         }

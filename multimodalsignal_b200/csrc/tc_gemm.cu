@@ -515,6 +515,45 @@ int launch_transpose_pad(const float* W, int rows, int cols, float* out, int64_t
     return MMS_OK;
 }
 
+// Up to 4 transposes in one launch (the W_ih^T copies of every GRU layer for the backward's dx products are three 4 us launches
+// of a few dozen CTAs otherwise); `pad` further columns behind each transposed block are zero-filled (the dq columns of the
+// bottom layers' D rows meet zero weights), which replaces the memset of the destination.
+struct TransposeJobs {
+    const float* W[4];
+    float* out[4];
+    int64_t ldo[4];
+    int rows[4], cols[4], col_off[4], pad[4];
+};
+__global__ void __launch_bounds__(256) transpose_pad_multi_kernel(const TransposeJobs jobs) {
+    __shared__ float tile[32][33];
+    const int j = blockIdx.z;
+    const int rows = jobs.rows[j], cols = jobs.cols[j], pad = jobs.pad[j];
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    if (r0 >= rows + pad || c0 >= cols) return;
+    const float* __restrict__ W = jobs.W[j];
+    float* __restrict__ out = jobs.out[j] + jobs.col_off[j];
+    const int64_t ldo = jobs.ldo[j];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int i = ty; i < 32; i += 8)
+        tile[i][tx] = (r0 + i < rows && c0 + tx < cols) ? __ldg(W + (int64_t)(r0 + i) * cols + c0 + tx) : 0.f;     // rows beyond the matrix: the pad
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8)
+        if (c0 + i < cols && r0 + tx < rows + pad) out[(int64_t)(c0 + i) * ldo + r0 + tx] = tile[tx][i];
+}
+
+int launch_transpose_pad_multi(const TransposeJobs& jobs, int n, cudaStream_t st) {
+    MMS_REQUIRE(n >= 1 && n <= 4, "transpose_pad_multi: 1..4 jobs");
+    int gx = 1, gy = 1;
+    for (int j = 0; j < n; ++j) {
+        gx = max(gx, cdiv(jobs.cols[j], 32));
+        gy = max(gy, cdiv(jobs.rows[j] + jobs.pad[j], 32));
+    }
+    MMS_PROF_BEGIN(st);
+    transpose_pad_multi_kernel<<<dim3(gx, gy, n), 256, 0, st>>>(jobs);
+    MMS_LAUNCH_CHECK("transpose_pad_multi_kernel");
+    return MMS_OK;
+}
+
 }  // namespace mms
 
 using namespace mms;

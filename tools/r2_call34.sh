@@ -1,0 +1,20 @@
+#!/bin/bash
+mkdir -p gpurun_out
+T=r2c34
+timeout 900 python -m pytest tests/test_gpu_ops.py tests/test_gpu_model.py tests/test_gpu_trainer.py -m gpu -q -x > gpurun_out/${T}_suite.log 2>&1; echo "suite rc=$?"; tail -2 gpurun_out/${T}_suite.log
+timeout 200 python tools/graph_timeline.py --out gpurun_out/${T}_timeline.json > gpurun_out/${T}_timeline.log 2>&1; echo "timeline rc=$?"
+cat gpurun_out/${T}_timeline.log
+for i in 1 2; do timeout 200 python bench.py --steps 1500 --warmup 30 --no-subrecords --no-cpu-baseline --no-library-baseline > gpurun_out/${T}_b.json 2>/dev/null
+python - <<PY
+import json
+p=json.load(open('gpurun_out/${T}_b.json'))
+print('ms', round(p['ms_per_step'],5), 'e2e', round(p['e2e']['ms_per_step'],5))
+PY
+done
+for i in 1 2; do timeout 300 python bench.py --workload loso > gpurun_out/${T}_loso_$i.json 2>/dev/null
+python - <<PY
+import json
+p=json.load(open('gpurun_out/${T}_loso_$i.json'))
+print('loso', round(p['value'],2), 's pre', round(p.get('preprocess_s',0),2), 'windows', p.get('windows_trained'), 'w/s', round(p.get('train_windows_per_s',0)), 'acc', round(p.get('accuracy_mean',0),4))
+PY
+done
