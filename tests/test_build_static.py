@@ -48,6 +48,20 @@ def test_encoder_backward_kernels_stage_by_bulk_copy_and_compute_with_packed_fma
     assert k["conv1_bwd_kernel"].get("UBLKCP (cp.async.bulk)", 0) >= 3 and k["conv1_bwd_kernel"].get("FFMA2 (fma.rn.f32x2)", 0) >= 56
 
 
+def test_resampler_passes_keep_their_transforms_in_registers(facts):
+    """fft_fast.cuh: float64 butterflies in registers (no spills, <= 128 registers for two CTAs per SM), 256-bit global accesses
+    on the contiguous side of a pass."""
+    k, px = facts
+    for name in ("fft_fast_fwd_kernel<16, 16, 16>", "fft_fast_inv_kernel<16, 16, 16>", "fft_fast_fwd_kernel<9, 16, 16>",
+                 "fft_fast_inv_kernel<16, 8, 32>"):
+        f = k[name]
+        assert f.get("DFMA/DMUL/DADD (float64)", 0) > 200, name
+        assert f.get("LDG/STG .256 (256-bit global access)", 0) >= 4, name
+    fast = {n: v for n, v in px.items() if "fft_fast_" in n}
+    assert len(fast) == 10
+    assert all(v["registers"] <= 128 and not v.get("spill_stores") for v in fast.values()), fast
+
+
 def test_peer_kernels_use_system_scope_accesses(facts):
     k, _ = facts
     assert k["peer_allreduce_adam_kernel"].get("*.SYS loads/stores (peer memory)", 0) > 0

@@ -25,6 +25,8 @@ PATTERNS = OrderedDict([
     ("*.SYS loads/stores (peer memory)", r"\.SYS\b"),
     ("RED (red.global.add)", r"\bRED\b|\bREDG"),
     ("MUFU.EX2/RCP", r"\bMUFU\.(EX2|RCP)\b"),
+    ("LDG/STG .256 (256-bit global access)", r"\b(LDG|STG)\.[A-Z0-9.]*256"),
+    ("DFMA/DMUL/DADD (float64)", r"\b(DFMA|DMUL|DADD)\b"),
 ])
 
 
