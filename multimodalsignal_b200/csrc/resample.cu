@@ -312,8 +312,32 @@ struct FastHooks {
     int paired = 0, n_x = 0, sign = 0;
     int64_t n_in = 0, n_out = 0, P = 0, k0 = 0;
     const double2* mul = nullptr;
+    cudaEvent_t mul_ready = nullptr;       // recorded on another stream once `mul` is complete: waited for in front of the last forward pass
     int64_t n_keep = 0;
 };
+
+// Side stream of the filter transforms.  The two chirp-filter spectra of a call depend on the lengths only, are needed by the
+// LAST forward pass of their stage, and are transforms of ONE signal whose grids leave most of the GPU idle: for long signals
+// they run beside the first passes of the signal transforms instead of in front of them.
+struct FilterStream {
+    cudaStream_t s = nullptr;
+    cudaEvent_t fork = nullptr, ready_a = nullptr, ready_c = nullptr;
+    bool ok = false;
+};
+static FilterStream* filter_stream() {
+    static FilterStream per_dev[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    FilterStream& f = per_dev[dev];
+    if (!f.ok) {
+        if (cudaStreamCreateWithFlags(&f.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;    // default priority: highest measured slower (1.435 vs 1.403 ms)
+        if (cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&f.ready_a, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&f.ready_c, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        f.ok = true;
+    }
+    return &f;
+}
 
 static int fft_fast(double2* a, int64_t sig_stride, int64_t M, int n_sig, int inverse, const FastHooks& h, cudaStream_t st) {
     const ff::FastPlan pl = ff::make_fast_plan(M);
@@ -330,7 +354,10 @@ static int fft_fast(double2* a, int64_t sig_stride, int64_t M, int n_sig, int in
             p.load_op = h.load_op; p.x = h.x; p.paired = h.paired; p.n_in = h.n_in; p.n_x = h.n_x; p.P = h.P; p.k0 = h.k0; p.sign = h.sign;
             p.n_out = h.n_out;
         }
-        if (!inverse && i == pl.n - 1) p.mul = h.mul;
+        if (!inverse && i == pl.n - 1) {
+            p.mul = h.mul;
+            if (h.mul && h.mul_ready) MMS_CUDA(cudaStreamWaitEvent(st, h.mul_ready, 0));
+        }
         if (inverse && i == 0 && h.n_keep > 0) p.n_keep = h.n_keep;
         int rc;
         if (fp.n1 == 16 && fp.n2 == 16) rc = launch_fast_pass<16, 16, 16>(p, n_sig, inverse, st);
@@ -418,7 +445,7 @@ struct ResampleDims { int64_t N, num, m2, M1, M2, Mmax; };
 // The fast path (MMS_RESAMPLE_FAST, default 1): smooth convolution lengths 2^a / 3 * 2^a / 9 * 2^a just above what the
 // chirp-z transforms need (the power of two above N + J - 1 = 4.58 M is 8.39 M; 9 * 2^19 = 4.72 M), register-resident
 // passes with the chirp multiplications, the filter product and the output pruning fused in.  Workspace layout:
-// filter [Mmax] | stage-A transforms [nA][M1] | stage-C transforms [n_sig][M2].
+// filter A [M1] | filter C [M2] | stage-A transforms [nA][M1] | stage-C transforms [n_sig][M2].
 struct FastDims { bool ok; bool paired; int nA; int64_t J, M1, M2, Mmax; };
 
 static FastDims fast_dims(const ResampleDims& d, int n_sig) {
@@ -455,7 +482,7 @@ extern "C" int64_t mms_resample_workspace_bytes(int64_t n_in, int64_t n_out, int
     ResampleDims d;
     if (resample_dims(n_in, n_out, &d) || n_sig < 1) return -1;
     const FastDims f = fast_dims(d, n_sig);
-    if (f.ok) return (int64_t)sizeof(double2) * (f.Mmax + (int64_t)f.nA * f.M1 + (int64_t)n_sig * f.M2);
+    if (f.ok) return (int64_t)sizeof(double2) * (f.M1 + f.M2 + (int64_t)f.nA * f.M1 + (int64_t)n_sig * f.M2);
     return (int64_t)sizeof(double2) * d.Mmax * ((int64_t)n_sig + 1);
 }
 
@@ -468,25 +495,39 @@ extern "C" int mms_resample_f64(const double* x, int64_t n_in, int64_t n_out, in
     MMS_REQUIRE(x && y && workspace && n_sig >= 1, "resample_f64: bad arguments");
     const FastDims f = fast_dims(d, n_sig);
     if (f.ok) {
-        const int64_t need_f = (int64_t)sizeof(double2) * (f.Mmax + (int64_t)f.nA * f.M1 + (int64_t)n_sig * f.M2);
+        const int64_t need_f = (int64_t)sizeof(double2) * (f.M1 + f.M2 + (int64_t)f.nA * f.M1 + (int64_t)n_sig * f.M2);
         if (workspace_bytes < need_f) {
             set_error("resample_f64: workspace %lld bytes < %lld", (long long)workspace_bytes, (long long)need_f);
             return MMS_E_WORKSPACE;
         }
-        double2* filt = (double2*)workspace;
-        double2* workA = filt + f.Mmax;
+        double2* filtA = (double2*)workspace;
+        double2* filtC = filtA + f.M1;
+        double2* workA = filtC + f.M2;
         double2* workC = workA + (int64_t)f.nA * f.M1;
-        // stage A: chirp filter spectrum (generated by the first pass's loads), then the transforms of the (paired) signals
-        // with the chirp pre-multiplication on the loads and the filter product on the last pass's stores; the inverse keeps
-        // the J outputs that are used
-        FastHooks hf;
+        // The two chirp filter spectra (generated by the loads of their first pass): beside the signal transforms on the filter
+        // stream for long signals (MMS_RESAMPLE_FILTER_STREAM, default 1), in front of them otherwise
+        FastHooks hf, hg;
         hf.load_op = ff::LD_FILTER; hf.n_in = d.N; hf.n_out = f.J; hf.P = d.N; hf.sign = -1;
-        rc = fft_fast(filt, f.M1, f.M1, 1, 0, hf, st);
+        hg.load_op = ff::LD_FILTER; hg.n_in = d.m2; hg.n_out = d.num; hg.P = d.num; hg.sign = +1;
+        FilterStream* fs = f.M1 >= ((int64_t)1 << 20) && option_get("RESAMPLE_FILTER_STREAM", 1) == 1 ? filter_stream() : nullptr;
+        cudaStream_t sf = fs ? fs->s : st;
+        if (fs) {
+            MMS_CUDA(cudaEventRecord(fs->fork, st));            // everything the caller enqueued before (and the previous call's reads of this workspace)
+            MMS_CUDA(cudaStreamWaitEvent(sf, fs->fork, 0));
+        }
+        rc = fft_fast(filtA, f.M1, f.M1, 1, 0, hf, sf);
         if (rc) return rc;
+        if (fs) MMS_CUDA(cudaEventRecord(fs->ready_a, sf));
+        rc = fft_fast(filtC, f.M2, f.M2, 1, 0, hg, sf);
+        if (rc) return rc;
+        if (fs) MMS_CUDA(cudaEventRecord(fs->ready_c, sf));
+        // stage A: the transforms of the (paired) signals with the chirp pre-multiplication on the loads and the filter product
+        // on the last pass's stores; the inverse keeps the J outputs that are used
         FastHooks ha;
         ha.load_op = ff::LD_PAIR; ha.x = x; ha.paired = f.paired ? 1 : 0; ha.n_x = n_sig; ha.n_in = d.N; ha.P = d.N; ha.sign = -1;
         ha.k0 = f.paired ? d.N - (d.m2 - 1) : 0;           // first bin: -(m2 - 1) mod N
-        ha.mul = filt;
+        ha.mul = filtA;
+        ha.mul_ready = fs ? fs->ready_a : nullptr;
         rc = fft_fast(workA, f.M1, f.M1, f.nA, 0, ha, st);
         if (rc) return rc;
         FastHooks hi;
@@ -507,12 +548,9 @@ extern "C" int mms_resample_f64(const double* x, int64_t n_in, int64_t n_out, in
             }
         }
         // stage C
-        FastHooks hg;
-        hg.load_op = ff::LD_FILTER; hg.n_in = d.m2; hg.n_out = d.num; hg.P = d.num; hg.sign = +1;
-        rc = fft_fast(filt, f.M2, f.M2, 1, 0, hg, st);
-        if (rc) return rc;
         FastHooks hc;
-        hc.mul = filt;
+        hc.mul = filtC;
+        hc.mul_ready = fs ? fs->ready_c : nullptr;
         rc = fft_fast(workC, f.M2, f.M2, n_sig, 0, hc, st);
         if (rc) return rc;
         FastHooks hj;
