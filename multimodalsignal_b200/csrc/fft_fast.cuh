@@ -335,9 +335,10 @@ FF_HD void fwd_stage2(const PassArgs& p, int tid, int tile_x, int sig, const dou
         for (int q0 = 0; q0 < N2; ++q0) v[q0] = tile[tile_pos<R, N2, TC>(N2 * k1 + q0, c, p.contig)];
         Dft<N2, -1>::run(v);
         if (S > 1) {        // inter-pass twiddle w_Mc^{r (k1 + N1 k0)} = w^{r k1} (w^{r N1})^{k0}
-            const uint64_t r = (uint64_t)(r0 + c);
-            double2 w = cis_frac((r * (uint64_t)k1) % (uint64_t)p.Mc, p.Mc, -1.0);
-            const double2 step = cis_frac((r * (uint64_t)N1) % (uint64_t)p.Mc, p.Mc, -1.0);
+            // exponents r k1 and r N1 (< 2^31) reduced mod Mc in float64: a 64-bit integer modulo by a run-time divisor is > 100 instructions
+            const double r = (double)(r0 + c), mc = (double)p.Mc, inv_mc = 1.0 / mc;
+            double2 w = cis_pi(2.0 * mod_exact(r * (double)k1, mc, inv_mc) * inv_mc, -1);
+            const double2 step = cis_pi(2.0 * mod_exact(r * (double)N1, mc, inv_mc) * inv_mc, -1);
 #pragma unroll
             for (int k0 = 0; k0 < N2; ++k0) {
                 v[k0] = cmulf(v[k0], w);
@@ -390,9 +391,9 @@ FF_HD void inv_stage2(const PassArgs& p, int tid, int tile_x, int sig, double2* 
             for (int k0 = 0; k0 < N2; ++k0) v[k0] = base[origin + (int64_t)(N2 * k1 + k0) * S + c];
         }
         if (S > 1) {
-            const uint64_t r = (uint64_t)(r0 + c);
-            double2 w = cis_frac((r * (uint64_t)k1) % (uint64_t)p.Mc, p.Mc, 1.0);
-            const double2 step = cis_frac((r * (uint64_t)N1) % (uint64_t)p.Mc, p.Mc, 1.0);
+            const double r = (double)(r0 + c), mc = (double)p.Mc, inv_mc = 1.0 / mc;
+            double2 w = cis_pi(2.0 * mod_exact(r * (double)k1, mc, inv_mc) * inv_mc, +1);
+            const double2 step = cis_pi(2.0 * mod_exact(r * (double)N1, mc, inv_mc) * inv_mc, +1);
 #pragma unroll
             for (int k0 = 0; k0 < N2; ++k0) {
                 v[k0] = cmulf(v[k0], w);
