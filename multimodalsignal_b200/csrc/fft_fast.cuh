@@ -73,6 +73,50 @@ FF_HD double tw_sin(int j) {
     return t[j & 15];
 }
 
+// w_R^{q} = (cos, sin)(2 pi q / R), q < 16, for the five radices (rows: R = 64, 128, 256, 144, 192): the base of the
+// intra-pass twiddles of a stage-1 thread, from constant memory instead of a sincospi
+#ifdef __CUDACC__
+#define FF_CONSTANT static __constant__
+#else
+#define FF_CONSTANT static const
+#endif
+FF_CONSTANT double TW_BASE_C[5][16] = {
+    {1.0, 0.9951847266721969, 0.9807852804032304, 0.9569403357322088, 0.9238795325112867, 0.881921264348355, 0.8314696123025452, 0.773010453362737, 0.7071067811865476, 0.6343932841636455, 0.5555702330196023, 0.4713967368259978, 0.38268343236508984, 0.29028467725446233, 0.19509032201612833, 0.09801714032956077},
+    {1.0, 0.9987954562051724, 0.9951847266721969, 0.989176509964781, 0.9807852804032304, 0.970031253194544, 0.9569403357322088, 0.9415440651830208, 0.9238795325112867, 0.9039892931234433, 0.881921264348355, 0.8577286100002721, 0.8314696123025452, 0.8032075314806449, 0.773010453362737, 0.7409511253549591},
+    {1.0, 0.9996988186962042, 0.9987954562051724, 0.9972904566786902, 0.9951847266721969, 0.99247953459871, 0.989176509964781, 0.9852776423889412, 0.9807852804032304, 0.9757021300385286, 0.970031253194544, 0.9637760657954398, 0.9569403357322088, 0.9495281805930367, 0.9415440651830208, 0.932992798834739},
+    {1.0, 0.9990482215818578, 0.9961946980917455, 0.9914448613738104, 0.984807753012208, 0.9762960071199334, 0.9659258262890683, 0.9537169507482269, 0.9396926207859084, 0.9238795325112867, 0.9063077870366499, 0.8870108331782217, 0.8660254037844387, 0.8433914458128857, 0.8191520442889918, 0.7933533402912353},
+    {1.0, 0.9994645874763657, 0.9978589232386035, 0.9951847266721969, 0.9914448613738104, 0.986643332084879, 0.9807852804032304, 0.9738769792773336, 0.9659258262890683, 0.9569403357322088, 0.9469301294951057, 0.9359059267573258, 0.9238795325112867, 0.9108638249211758, 0.8968727415326884, 0.881921264348355}};
+FF_CONSTANT double TW_BASE_S[5][16] = {
+    {0.0, 0.0980171403295606, 0.19509032201612825, 0.29028467725446233, 0.3826834323650898, 0.47139673682599764, 0.5555702330196022, 0.6343932841636455, 0.7071067811865475, 0.773010453362737, 0.8314696123025452, 0.8819212643483549, 0.9238795325112867, 0.9569403357322089, 0.9807852804032304, 0.9951847266721968},
+    {0.0, 0.049067674327418015, 0.0980171403295606, 0.14673047445536175, 0.19509032201612825, 0.24298017990326387, 0.29028467725446233, 0.33688985339222005, 0.3826834323650898, 0.4275550934302821, 0.47139673682599764, 0.5141027441932217, 0.5555702330196022, 0.5956993044924334, 0.6343932841636455, 0.6715589548470183},
+    {0.0, 0.024541228522912288, 0.049067674327418015, 0.07356456359966743, 0.0980171403295606, 0.1224106751992162, 0.14673047445536175, 0.17096188876030122, 0.19509032201612825, 0.2191012401568698, 0.24298017990326387, 0.26671275747489837, 0.29028467725446233, 0.3136817403988915, 0.33688985339222005, 0.3598950365349881},
+    {0.0, 0.043619387365336, 0.08715574274765817, 0.13052619222005157, 0.17364817766693033, 0.21643961393810288, 0.25881904510252074, 0.3007057995042731, 0.3420201433256687, 0.3826834323650898, 0.42261826174069944, 0.46174861323503386, 0.49999999999999994, 0.5372996083468239, 0.573576436351046, 0.6087614290087205},
+    {0.0, 0.03271908282177614, 0.06540312923014306, 0.0980171403295606, 0.13052619222005157, 0.16289547339458874, 0.19509032201612825, 0.2270762630343732, 0.25881904510252074, 0.29028467725446233, 0.3214394653031616, 0.3522500479212335, 0.3826834323650898, 0.4127070298043947, 0.44228869021900125, 0.4713967368259976}};
+template <int R>
+FF_HD double2 tw_base(int q0) {      // e^{-2 pi i q0 / R}
+#if defined(__CUDA_ARCH__) || !defined(__CUDACC__)
+    constexpr int row = R == 64 ? 0 : R == 128 ? 1 : R == 256 ? 2 : R == 144 ? 3 : 4;
+    static_assert(R == 64 || R == 128 || R == 256 || R == 144 || R == 192, "radix without a table");
+    return make_double2(TW_BASE_C[row][q0], -TW_BASE_S[row][q0]);
+#else
+    double sn, cs;
+    sincospi(2.0 * (double)q0 / (double)R, &sn, &cs);
+    return make_double2(cs, -sn);
+#endif
+}
+// b^k for 0 <= k < 16 by squaring (three squarings, at most three products)
+FF_HD double2 cpow16(double2 b, int k, double2* b8_out) {
+    const double2 b2 = make_double2(fma(b.x, b.x, -b.y * b.y), 2.0 * b.x * b.y);
+    const double2 b4 = make_double2(fma(b2.x, b2.x, -b2.y * b2.y), 2.0 * b2.x * b2.y);
+    const double2 b8 = make_double2(fma(b4.x, b4.x, -b4.y * b4.y), 2.0 * b4.x * b4.y);
+    double2 w = (k & 1) ? b : make_double2(1.0, 0.0);
+    if (k & 2) w = make_double2(fma(w.x, b2.x, -w.y * b2.y), fma(w.x, b2.y, w.y * b2.x));
+    if (k & 4) w = make_double2(fma(w.x, b4.x, -w.y * b4.y), fma(w.x, b4.y, w.y * b4.x));
+    if (k & 8) w = make_double2(fma(w.x, b8.x, -w.y * b8.y), fma(w.x, b8.y, w.y * b8.x));
+    *b8_out = b8;
+    return w;
+}
+
 // v *= (c + i SIGN s): SIGN = -1 forward (e^{-2 pi i jk/N}), +1 inverse; the trivial factors cost nothing once unrolled
 template <int SIGN>
 FF_HD double2 mul_const(double2 v, double c, double s) {
@@ -230,8 +274,13 @@ template <int R, int N2, int TC>
 FF_HD int tile_pos(int row, int c, int contig) {
     return contig ? c * (R + R / N2) + row + row / N2 : row * TC + c;
 }
+// + 2 TC entries behind the tile: b_c = w_Mc^{r0 + c} and its N1-th power (each from its own exactly reduced sincospi), the bases of
+// column c's inter-pass twiddles w_Mc^{r (k1 + N1 k0)} = b^{k1} (b^{N1})^{k0}: written by TC threads (stage 1 of the forward,
+// col_bases() + a barrier in front of the inverse), so the other threads need neither a sincospi nor a modulo for them
 template <int R, int N2, int TC>
-constexpr int tile_elems() { return TC * (R + R / N2); }
+constexpr int tile_elems() { return TC * (R + R / N2) + 2 * TC; }
+template <int R, int N2, int TC>
+constexpr int colbase_offset() { return TC * (R + R / N2); }
 
 template <int N1, int N2, int TC>
 FF_HD double2 pass_load(const PassArgs& p, int sig, const double2* base, int64_t idx) {
@@ -246,6 +295,15 @@ FF_HD double2 pass_load(const PassArgs& p, int sig, const double2* base, int64_t
     if (idx < p.n_out) return chirp_at(idx, p.P, -p.sign);
     if (p.M - idx < p.n_in) return chirp_at(p.M - idx, p.P, -p.sign);
     return make_double2(0.0, 0.0);
+}
+
+// bases of column c's inter-pass twiddles (sign -1 forward, +1 inverse)
+template <int N1, int N2, int TC>
+FF_HD void write_col_bases(const PassArgs& p, int64_t r0, int c, int sign, double2* tile) {
+    constexpr int R = N1 * N2;
+    const double r = (double)(r0 + c), mc = (double)p.Mc, inv_mc = 1.0 / mc;
+    tile[colbase_offset<R, N2, TC>() + c] = cis_pi(2.0 * r * inv_mc, sign);                                  // r < Mc / R: no reduction needed
+    tile[colbase_offset<R, N2, TC>() + TC + c] = cis_pi(2.0 * mod_exact(r * (double)N1, mc, inv_mc) * inv_mc, sign);
 }
 
 // ---- forward pass -----------------------------------------------------------------------------------------------------
@@ -309,7 +367,8 @@ FF_HD void fwd_stage1(const PassArgs& p, int tid, int tile_x, int sig, double2* 
             }
         }
         Dft<N1, -1>::run(v);
-        const double2 wq = cis_frac((uint64_t)q0, R, -1.0);       // w_R^{q0 k1} as a running product over k1
+        if (!p.contig && q0 == 0) write_col_bases<N1, N2, TC>(p, r0, c, -1, tile);
+        const double2 wq = tw_base<R>(q0);                        // w_R^{q0 k1} as a running product over k1
         double2 w = wq;
         tile[tile_pos<R, N2, TC>(q0, c, p.contig)] = v[0];
 #pragma unroll
@@ -334,11 +393,10 @@ FF_HD void fwd_stage2(const PassArgs& p, int tid, int tile_x, int sig, const dou
 #pragma unroll
         for (int q0 = 0; q0 < N2; ++q0) v[q0] = tile[tile_pos<R, N2, TC>(N2 * k1 + q0, c, p.contig)];
         Dft<N2, -1>::run(v);
-        if (S > 1) {        // inter-pass twiddle w_Mc^{r (k1 + N1 k0)} = w^{r k1} (w^{r N1})^{k0}
-            // exponents r k1 and r N1 (< 2^31) reduced mod Mc in float64: a 64-bit integer modulo by a run-time divisor is > 100 instructions
-            const double r = (double)(r0 + c), mc = (double)p.Mc, inv_mc = 1.0 / mc;
-            double2 w = cis_pi(2.0 * mod_exact(r * (double)k1, mc, inv_mc) * inv_mc, -1);
-            const double2 step = cis_pi(2.0 * mod_exact(r * (double)N1, mc, inv_mc) * inv_mc, -1);
+        if (S > 1) {        // inter-pass twiddle w_Mc^{r (k1 + N1 k0)} = b^{k1} (b^{N1})^{k0}, b = w_Mc^r from stage 1 (no sincospi, no modulo)
+            const double2 b = tile[colbase_offset<R, N2, TC>() + c], step = tile[colbase_offset<R, N2, TC>() + TC + c];
+            double2 b8;
+            double2 w = cpow16(b, k1, &b8);
 #pragma unroll
             for (int k0 = 0; k0 < N2; ++k0) {
                 v[k0] = cmulf(v[k0], w);
@@ -371,6 +429,15 @@ FF_HD void fwd_stage2(const PassArgs& p, int tid, int tile_x, int sig, const dou
 }
 
 // ---- inverse pass (exact reverse of the forward pass, unnormalised: a forward + inverse transform multiplies by M) ------
+// inv_stage0 (TC threads) + barrier, inv_stage2, barrier, inv_stage1
+template <int N1, int N2, int TC, int NT>
+FF_HD void inv_stage0(const PassArgs& p, int tid, int tile_x, double2* tile) {
+    int64_t origin, S, r0;
+    int tc_eff;
+    tile_origin<N1, N2, TC>(p, tile_x, &origin, &S, &r0, &tc_eff);
+    if (!p.contig && tid < tc_eff) write_col_bases<N1, N2, TC>(p, r0, tid, +1, tile);
+}
+
 template <int N1, int N2, int TC, int NT>
 FF_HD void inv_stage2(const PassArgs& p, int tid, int tile_x, int sig, double2* tile) {
     constexpr int R = N1 * N2;
@@ -390,10 +457,10 @@ FF_HD void inv_stage2(const PassArgs& p, int tid, int tile_x, int sig, double2* 
 #pragma unroll
             for (int k0 = 0; k0 < N2; ++k0) v[k0] = base[origin + (int64_t)(N2 * k1 + k0) * S + c];
         }
-        if (S > 1) {
-            const double r = (double)(r0 + c), mc = (double)p.Mc, inv_mc = 1.0 / mc;
-            double2 w = cis_pi(2.0 * mod_exact(r * (double)k1, mc, inv_mc) * inv_mc, +1);
-            const double2 step = cis_pi(2.0 * mod_exact(r * (double)N1, mc, inv_mc) * inv_mc, +1);
+        if (S > 1) {        // conjugate inter-pass twiddles from the column bases (inv_stage0)
+            const double2 b = tile[colbase_offset<R, N2, TC>() + c], step = tile[colbase_offset<R, N2, TC>() + TC + c];
+            double2 b8;
+            double2 w = cpow16(b, k1, &b8);
 #pragma unroll
             for (int k0 = 0; k0 < N2; ++k0) {
                 v[k0] = cmulf(v[k0], w);
@@ -401,7 +468,7 @@ FF_HD void inv_stage2(const PassArgs& p, int tid, int tile_x, int sig, double2* 
             }
         }
         Dft<N2, +1>::run(v);
-        const double2 wk = cis_frac((uint64_t)k1, R, -1.0);       // conj(w_R^{q0 k1}) as a running product over q0
+        const double2 wk = tw_base<R>(k1);                        // conj(w_R^{q0 k1}) as a running product over q0
         double2 wi = wk;
         tile[tile_pos<R, N2, TC>(N2 * k1, c, p.contig)] = v[0];
 #pragma unroll

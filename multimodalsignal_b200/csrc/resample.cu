@@ -278,6 +278,8 @@ __global__ void __launch_bounds__(256, 2) fft_fast_fwd_kernel(const ff::PassArgs
 template <int N1, int N2, int TC>
 __global__ void __launch_bounds__(256, 2) fft_fast_inv_kernel(const ff::PassArgs p) {
     extern __shared__ __align__(16) double2 ffs[];
+    ff::inv_stage0<N1, N2, TC, 256>(p, threadIdx.x, blockIdx.y, ffs);
+    __syncthreads();
     ff::inv_stage2<N1, N2, TC, 256>(p, threadIdx.x, blockIdx.y, blockIdx.x, ffs);
     __syncthreads();
     ff::inv_stage1<N1, N2, TC, 256>(p, threadIdx.x, blockIdx.y, blockIdx.x, ffs);

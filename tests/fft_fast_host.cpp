@@ -26,6 +26,7 @@ static void run_pass(const PassArgs& p, int n_sig, bool inverse) {
                 for (int tid = 0; tid < NT; ++tid) fwd_stage1<N1, N2, TC, NT>(p, tid, (int)tx, sig, tile.data());
                 for (int tid = 0; tid < NT; ++tid) fwd_stage2<N1, N2, TC, NT>(p, tid, (int)tx, sig, tile.data());
             } else {
+                for (int tid = 0; tid < NT; ++tid) inv_stage0<N1, N2, TC, NT>(p, tid, (int)tx, tile.data());
                 for (int tid = 0; tid < NT; ++tid) inv_stage2<N1, N2, TC, NT>(p, tid, (int)tx, sig, tile.data());
                 for (int tid = 0; tid < NT; ++tid) inv_stage1<N1, N2, TC, NT>(p, tid, (int)tx, sig, tile.data());
             }
