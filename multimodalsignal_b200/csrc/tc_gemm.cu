@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const __grid_
     const int BN = p.BN;
     const uint32_t a_bytes = TC_BM * TC_BK * 4, b_bytes = (uint32_t)BN * TC_BK * 4;
     const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
-    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem) + 1023) & ~(uintptr_t)1023);
+    uint8_t* base = tc_smem + ((1024u - (smem_u32(tc_smem) & 1023u)) & 1023u);      // pointer arithmetic keeps the address space: LDS / STS, not generic LD / ST
     const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN;
     const int nkb = (p.K + TC_BK - 1) / TC_BK;
     uint32_t tmem_cols = 32;

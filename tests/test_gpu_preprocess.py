@@ -71,6 +71,28 @@ def test_resample_paired_transforms_equal_single_transforms(n_sig):
         _ext.check(lib.mms_set_option(b"RESAMPLE_PAIRED", prev) if prev >= 0 else lib.mms_clear_option(b"RESAMPLE_PAIRED"))
 
 
+@pytest.mark.parametrize("n,num,n_sig", [(70037, 6403, 3), (24000, 384000, 2), (1000, 500, 1), (190001, 17371, 2), (131, 977, 1)])
+def test_resample_fast_passes_equal_generic_passes(n, num, n_sig):
+    """csrc/fft_fast.cuh (register-resident mixed-radix passes, smooth lengths, fused chirp / filter / pruning: the default) against
+    the round-1 power-of-two radix-2 passes through shared memory (MMS_RESAMPLE_FAST=0) and against the numpy restatement."""
+    from multimodalsignal_b200 import _ext, preprocess as pp
+    lib = _ext.lib()
+    rng = np.random.default_rng(n + num)
+    x = rng.standard_normal((n_sig, n)) * 3.0 + 1.5
+    xd = torch.from_numpy(x).cuda()
+    ref = np.stack([po.fft_resample(r, num) for r in x])
+    prev = lib.mms_get_option(b"RESAMPLE_FAST", -1)
+    try:
+        outs = {}
+        for mode in (1, 0):
+            _ext.check(lib.mms_set_option(b"RESAMPLE_FAST", mode))
+            outs[mode] = pp.resample_on_device(xd, num).cpu().numpy()
+            err_ok(outs[mode], ref)
+        assert np.abs(outs[1] - outs[0]).max() <= 1e-10 * max(1.0, np.abs(ref).max())
+    finally:
+        _ext.check(lib.mms_set_option(b"RESAMPLE_FAST", prev) if prev >= 0 else lib.mms_clear_option(b"RESAMPLE_FAST"))
+
+
 def test_resample_full_size_recording():
     """BASELINE-size stream: 700 Hz x 100 min + odd offset (N = 4 200 959 has a large prime factor)."""
     from multimodalsignal_b200 import preprocess as pp
