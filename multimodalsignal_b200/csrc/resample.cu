@@ -264,6 +264,61 @@ __global__ void __launch_bounds__(256) czt_post_real_kernel(const double2* __res
 }
 
 
+// Paired stage A -> PAIRED stage C (MMS_RESAMPLE_PAIRED_C): the two real OUTPUT signals of a pair come out of ONE complex inverse
+// chirp-z transform.  A real y_s[j] = Re sum_{k=0..K} G_s[k] e^{i theta jk} is the two-sided sum over k = -K .. K of c_s[k] = G_s[k] / 2
+// (k > 0), conj(G_s[-k]) / 2 (k < 0), G_s[0] (k = 0), so y_1 + i y_2 = sum_k (c_1[k] + i c_2[k]) e^{i theta jk}: a transform with
+// 2K + 1 = 2 m2 - 1 inputs (index n = k + K; the shift by K is the linear phase e^{-i theta jK} of the post kernel) instead of two
+// with m2 inputs each -- for the 700 -> 64 Hz case 4 transforms of 3 * 2^18 points instead of 8 of 9 * 2^16.
+__global__ void __launch_bounds__(256, 2) spectrum_fix_pair2_kernel(const double2* __restrict__ conv, double2* __restrict__ a2, int n_sig,
+                                                                    int64_t M, int64_t M2, int64_t N, int64_t num, int64_t m2) {
+    const int p = blockIdx.y;
+    const double2* cv = conv + (int64_t)p * M;
+    double2* out = a2 + (int64_t)p * M2;
+    const bool has2 = 2 * p + 1 < n_sig;
+    const int64_t m = N < num ? N : num, K = m2 - 1;
+    const double scale = ((double)num / (double)N) / (double)M;
+    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < M2; n += (int64_t)gridDim.x * blockDim.x) {
+        double2 v = make_double2(0.0, 0.0);
+        if (n <= 2 * K) {
+            const int64_t k = n - K, kk = k < 0 ? -k : k;
+            const int64_t jp = K + kk, jn = K - kk;
+            const double2 Zp = cmul(cv[jp], chirp(jp, N, -1));
+            const double2 Zn = cmul(cv[jn], chirp(jn, N, -1));
+            double2 X1 = make_double2(0.5 * (Zp.x + Zn.x) * scale, 0.5 * (Zp.y - Zn.y) * scale);
+            double2 X2 = make_double2(0.5 * (Zp.y + Zn.y) * scale, -0.5 * (Zp.x - Zn.x) * scale);
+            if ((m & 1) == 0 && num != N && kk == m / 2) {
+                const double f = num < N ? 2.0 : 0.5;
+                X1.x *= f; X1.y *= f; X2.x *= f; X2.y *= f;
+            }
+            double2 G1 = make_double2(2.0 * X1.x, 2.0 * X1.y), G2 = make_double2(2.0 * X2.x, 2.0 * X2.y);
+            if (kk == 0 || ((num & 1) == 0 && kk == num / 2)) { G1 = make_double2(X1.x, 0.0); G2 = make_double2(X2.x, 0.0); }
+            if (!has2) G2 = make_double2(0.0, 0.0);
+            double2 d;
+            if (k > 0) d = make_double2(0.5 * (G1.x - G2.y), 0.5 * (G1.y + G2.x));
+            else if (k < 0) d = make_double2(0.5 * (G1.x + G2.y), 0.5 * (G2.x - G1.y));
+            else d = make_double2(G1.x, G2.x);
+            v = cmul(d, chirp(n, num, +1));
+        }
+        out[n] = v;
+    }
+}
+
+// (y_1 + i y_2)[j] = conv[j] * chirp(j) * e^{-2 pi i jK / num} / (M2 * num)
+__global__ void __launch_bounds__(256) czt_post_pair_kernel(const double2* __restrict__ a, int64_t M2, int64_t num, int64_t K, int n_sig,
+                                                            double* __restrict__ y) {
+    const int p = blockIdx.y;
+    const double2* as = a + (int64_t)p * M2;
+    double* y1 = y + (int64_t)(2 * p) * num;
+    double* y2 = 2 * p + 1 < n_sig ? y + (int64_t)(2 * p + 1) * num : nullptr;
+    const double scale = 1.0 / ((double)M2 * (double)num);
+    const int64_t ks = (num - K % num) % num;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < num; j += (int64_t)gridDim.x * blockDim.x) {
+        const double2 z = cmul(as[j], chirp_shift(j, ks, num, +1));
+        y1[j] = z.x * scale;
+        if (y2) y2[j] = z.y * scale;
+    }
+}
+
 // ---- register-resident passes (fft_fast.cuh) ---------------------------------------------------------------------------
 // One CTA = one tile of TC columns, 256 threads, one block barrier; two CTAs per SM (a thread holds 16 complex doubles).
 // grid = (signals, tiles): the CTAs of one tile position run next to each other, so the filter spectrum tile they all multiply
@@ -447,8 +502,8 @@ struct ResampleDims { int64_t N, num, m2, M1, M2, Mmax; };
 // The fast path (MMS_RESAMPLE_FAST, default 1): smooth convolution lengths 2^a / 3 * 2^a / 9 * 2^a just above what the
 // chirp-z transforms need (the power of two above N + J - 1 = 4.58 M is 8.39 M; 9 * 2^19 = 4.72 M), register-resident
 // passes with the chirp multiplications, the filter product and the output pruning fused in.  Workspace layout:
-// filter A [M1] | filter C [M2] | stage-A transforms [nA][M1] | stage-C transforms [n_sig][M2].
-struct FastDims { bool ok; bool paired; int nA; int64_t J, M1, M2, Mmax; };
+// filter A [M1] | filter C [M2] | stage-A transforms [nA][M1] | stage-C transforms [nC][M2].
+struct FastDims { bool ok; bool paired, paired_c; int nA, nC; int64_t J, JC, M1, M2, Mmax; };
 
 static FastDims fast_dims(const ResampleDims& d, int n_sig) {
     FastDims f;
@@ -457,8 +512,11 @@ static FastDims fast_dims(const ResampleDims& d, int n_sig) {
     f.paired = n_sig >= 2 && option_get("RESAMPLE_PAIRED", 1) == 1;
     f.J = f.paired ? 2 * d.m2 - 1 : d.m2;
     f.nA = f.paired ? (n_sig + 1) / 2 : n_sig;
+    f.paired_c = f.paired && option_get("RESAMPLE_PAIRED_C", 1) == 1;
+    f.JC = f.paired_c ? 2 * d.m2 - 1 : d.m2;
+    f.nC = f.paired_c ? f.nA : n_sig;
     f.M1 = ff::fast_length_at_least(d.N + f.J - 1);
-    f.M2 = ff::fast_length_at_least(d.m2 + d.num - 1);
+    f.M2 = ff::fast_length_at_least(f.JC + d.num - 1);
     f.Mmax = f.M1 > f.M2 ? f.M1 : f.M2;
     f.ok = f.M1 > 0 && f.M2 > 0;
     return f;
@@ -484,7 +542,7 @@ extern "C" int64_t mms_resample_workspace_bytes(int64_t n_in, int64_t n_out, int
     ResampleDims d;
     if (resample_dims(n_in, n_out, &d) || n_sig < 1) return -1;
     const FastDims f = fast_dims(d, n_sig);
-    if (f.ok) return (int64_t)sizeof(double2) * (f.M1 + f.M2 + (int64_t)f.nA * f.M1 + (int64_t)n_sig * f.M2);
+    if (f.ok) return (int64_t)sizeof(double2) * (f.M1 + f.M2 + (int64_t)f.nA * f.M1 + (int64_t)f.nC * f.M2);
     return (int64_t)sizeof(double2) * d.Mmax * ((int64_t)n_sig + 1);
 }
 
@@ -497,7 +555,7 @@ extern "C" int mms_resample_f64(const double* x, int64_t n_in, int64_t n_out, in
     MMS_REQUIRE(x && y && workspace && n_sig >= 1, "resample_f64: bad arguments");
     const FastDims f = fast_dims(d, n_sig);
     if (f.ok) {
-        const int64_t need_f = (int64_t)sizeof(double2) * (f.M1 + f.M2 + (int64_t)f.nA * f.M1 + (int64_t)n_sig * f.M2);
+        const int64_t need_f = (int64_t)sizeof(double2) * (f.M1 + f.M2 + (int64_t)f.nA * f.M1 + (int64_t)f.nC * f.M2);
         if (workspace_bytes < need_f) {
             set_error("resample_f64: workspace %lld bytes < %lld", (long long)workspace_bytes, (long long)need_f);
             return MMS_E_WORKSPACE;
@@ -510,7 +568,7 @@ extern "C" int mms_resample_f64(const double* x, int64_t n_in, int64_t n_out, in
         // stream for long signals (MMS_RESAMPLE_FILTER_STREAM, default 1), in front of them otherwise
         FastHooks hf, hg;
         hf.load_op = ff::LD_FILTER; hf.n_in = d.N; hf.n_out = f.J; hf.P = d.N; hf.sign = -1;
-        hg.load_op = ff::LD_FILTER; hg.n_in = d.m2; hg.n_out = d.num; hg.P = d.num; hg.sign = +1;
+        hg.load_op = ff::LD_FILTER; hg.n_in = f.JC; hg.n_out = d.num; hg.P = d.num; hg.sign = +1;
         FilterStream* fs = f.M1 >= ((int64_t)1 << 20) && option_get("RESAMPLE_FILTER_STREAM", 1) == 1 ? filter_stream() : nullptr;
         cudaStream_t sf = fs ? fs->s : st;
         if (fs) {
@@ -536,7 +594,12 @@ extern "C" int mms_resample_f64(const double* x, int64_t n_in, int64_t n_out, in
         hi.n_keep = f.J;
         rc = fft_fast(workA, f.M1, f.M1, f.nA, 1, hi, st);
         if (rc) return rc;
-        if (f.paired) {
+        if (f.paired_c) {
+            dim3 grid(grid_for(f.M2), f.nA);
+            MMS_PROF_BEGIN(st);
+            spectrum_fix_pair2_kernel<<<grid, 256, 0, st>>>(workA, workC, n_sig, f.M1, f.M2, d.N, d.num, d.m2);
+            MMS_LAUNCH_CHECK("spectrum_fix_pair2_kernel");
+        } else if (f.paired) {
             dim3 grid(grid_for(f.M2), f.nA);
             MMS_PROF_BEGIN(st);
             spectrum_fix_pair_kernel<<<grid, 256, 0, st>>>(workA, workC, n_sig, f.M1, f.M2, d.N, d.num, d.m2);
@@ -553,16 +616,22 @@ extern "C" int mms_resample_f64(const double* x, int64_t n_in, int64_t n_out, in
         FastHooks hc;
         hc.mul = filtC;
         hc.mul_ready = fs ? fs->ready_c : nullptr;
-        rc = fft_fast(workC, f.M2, f.M2, n_sig, 0, hc, st);
+        rc = fft_fast(workC, f.M2, f.M2, f.nC, 0, hc, st);
         if (rc) return rc;
         FastHooks hj;
         hj.n_keep = d.num;
-        rc = fft_fast(workC, f.M2, f.M2, n_sig, 1, hj, st);
+        rc = fft_fast(workC, f.M2, f.M2, f.nC, 1, hj, st);
         if (rc) return rc;
-        dim3 grid(grid_for(d.num), n_sig);
         MMS_PROF_BEGIN(st);
-        czt_post_real_kernel<<<grid, 256, 0, st>>>(workC, f.M2, d.num, y);
-        MMS_LAUNCH_CHECK("czt_post_real_kernel");
+        if (f.paired_c) {
+            dim3 grid(grid_for(d.num), f.nC);
+            czt_post_pair_kernel<<<grid, 256, 0, st>>>(workC, f.M2, d.num, d.m2 - 1, n_sig, y);
+            MMS_LAUNCH_CHECK("czt_post_pair_kernel");
+        } else {
+            dim3 grid(grid_for(d.num), n_sig);
+            czt_post_real_kernel<<<grid, 256, 0, st>>>(workC, f.M2, d.num, y);
+            MMS_LAUNCH_CHECK("czt_post_real_kernel");
+        }
         return MMS_OK;
     }
     const int64_t need = (int64_t)sizeof(double2) * d.Mmax * ((int64_t)n_sig + 1);

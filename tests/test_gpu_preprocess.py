@@ -67,6 +67,15 @@ def test_resample_paired_transforms_equal_single_transforms(n_sig):
             outs[mode] = pp.resample_on_device(xd, num).cpu().numpy()
             err_ok(outs[mode], ref)
         assert np.abs(outs[1] - outs[0]).max() <= 1e-10 * max(1.0, np.abs(ref).max())
+        # paired stage A with one inverse transform per signal (MMS_RESAMPLE_PAIRED_C=0) against the paired inverse (default)
+        _ext.check(lib.mms_set_option(b"RESAMPLE_PAIRED", 1))
+        _ext.check(lib.mms_set_option(b"RESAMPLE_PAIRED_C", 0))
+        try:
+            single_c = pp.resample_on_device(xd, num).cpu().numpy()
+        finally:
+            _ext.check(lib.mms_clear_option(b"RESAMPLE_PAIRED_C"))
+        err_ok(single_c, ref)
+        assert np.abs(outs[1] - single_c).max() <= 1e-10 * max(1.0, np.abs(ref).max())
     finally:
         _ext.check(lib.mms_set_option(b"RESAMPLE_PAIRED", prev) if prev >= 0 else lib.mms_clear_option(b"RESAMPLE_PAIRED"))
 

@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-T=r2c43
+T=r2c48
 timeout 600 python -m pytest tests/test_gpu_preprocess.py -m gpu -q -x > gpurun_out/${T}_pp.log 2>&1; echo "preprocess tests rc=$?"; tail -2 gpurun_out/${T}_pp.log
 for fs in 1 0; do
 MMS_RESAMPLE_FILTER_STREAM=$fs timeout 300 python - <<'PY'
@@ -21,6 +21,6 @@ done
 timeout 600 python tools/preprocess_order_probe.py 2>&1 | tail -9
 timeout 300 python bench.py --workload preprocess > gpurun_out/${T}_preprocess.json 2>gpurun_out/${T}_preprocess.err; echo "bench preprocess rc=$?"; python - <<'PY'
 import json
-p=json.load(open('gpurun_out/r2c43_preprocess.json'))
+p=json.load(open('gpurun_out/r2c48_preprocess.json'))
 print({k:p[k] for k in ('value','unit','e2e') if k in p}); print(p.get('roofline')['frac'])
 PY
