@@ -228,6 +228,9 @@ static int make_dims(const mms_cnngru_desc* d, Dims* o) {
     MMS_REQUIRE(o->layers >= 1 && o->layers <= MAX_LAYERS, "gru_num_layers %d outside [1,%d]", o->layers, MAX_LAYERS);
     o->L1c = conv_out_len(o->T, CONV1_K, CONV1_S, CONV1_P);
     MMS_REQUIRE(o->T >= 1 && o->L1c >= 1, "seq_len %d too short", o->T);
+    // the BatchNorm / pool kernels stage whole rows (T / 2 floats) in shared memory and the fused encoder kernels take at most
+    // 32 position tiles per row: windows beyond 16384 samples (60 s at > 273 Hz) are refused here, not at some launch
+    MMS_REQUIRE(o->T <= 16384, "seq_len %d: windows longer than 16384 samples are not supported", o->T);
     o->P1 = pool_out_len(o->L1c);
     o->L2c = conv_out_len(o->P1, CONV2_K, CONV2_S, CONV2_P);
     MMS_REQUIRE(o->L2c >= 1, "seq_len %d too short", o->T);

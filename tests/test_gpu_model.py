@@ -285,6 +285,17 @@ def test_cpu_input_is_refused():
         m(torch.zeros(2, 6, 640))
 
 
+def test_overlong_window_is_refused_up_front():
+    """seq_len > 16384 (the BatchNorm / pool kernels stage whole rows in shared memory): a clear error from the descriptor check,
+    not a failed launch somewhere inside the chain."""
+    from multimodalsignal_b200.models import CnnGruAttentionModel
+    from multimodalsignal_b200._ext import MmsError
+    m = CnnGruAttentionModel(3, 2).cuda().eval()
+    with pytest.raises(MmsError, match="16384"):
+        with torch.no_grad():
+            m(torch.zeros(1, 3, 16400, device="cuda"))
+
+
 def test_dropout_gradient_fused_into_gemm_epilogue_equals_separate_pass():
     """The gradient through nn.GRU's inter-layer dropout (models.py:62) is applied by the epilogue of the tensor-core product that
     forms it (MMS_DROP_FUSED=1, default) -- the same multipliers as a separate dropout_apply pass over the result
