@@ -35,8 +35,12 @@ struct TcGemmParams {
 };
 
 // dynamic smem: [stage][A_hi | A_lo | B_hi | B_lo] (1024-byte aligned tiles); NS = pipeline stages (2, or 4 for long reductions)
+// 256 threads: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = splitters; ALL EIGHT warps run the epilogue -- a warp reads
+// the TMEM lane quarter (warp % 4), so every quarter has two warps (2-5 and 0, 1, 6, 7) that take half of the columns each: the
+// epilogue (tcgen05.ld, shared-memory transpose, bias / dropout, 128-byte stores) was 0.7-5.5 us of a CTA's 12 us with four warps.
+constexpr int NT_THREADS = 256;
 template <int NS>
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA,
+__global__ void __launch_bounds__(NT_THREADS, 1) tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                    const __grid_constant__ CUtensorMap mapB, const TcGemmParams p) {
     MMS_PDL_TRIGGER();
     extern __shared__ __align__(1024) uint8_t tc_smem[];
@@ -53,7 +57,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const __grid_
     const int nkb = (p.K + TC_BK - 1) / TC_BK;
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < BN) tmem_cols <<= 1;
-    for (int i = threadIdx.x; i < 256; i += TC_THREADS) s_bias[i] = (p.bias && i < BN && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
+    for (int i = threadIdx.x; i < 256; i += NT_THREADS) s_bias[i] = (p.bias && i < BN && n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.f;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NS; ++s) {
@@ -109,8 +113,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const __grid_
             }
             umma_commit(&acc_bar);                     // accumulator complete
         }
-    } else {
-        // ===== operand splitters (warps 2..5), then epilogue =====
+    } else if (warp < 6) {
+        // ===== operand splitters (warps 2..5) =====
         const int t = threadIdx.x - 64;                // 0..127
         DropRng rng_a;
         const bool drop_a = p.drop_p > 0.f && p.drop_on_a;
@@ -158,10 +162,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const __grid_
             __syncwarp();
             if (lane == 0) mbar_arrive(&split_bar[s]);
         }
-        // ===== epilogue: TMEM lane quarter (warp % 4) -> registers -> global =====
+    }
+    __syncwarp();             // lanes 1..31 of the producer / issuer warps wait here (no spinning beside lane 0's loop)
+    {
+        // ===== epilogue (all warps): TMEM lane quarter (warp % 4) -> registers -> global; warps 2-5 take the first half of the
+        // column blocks, warps 0, 1, 6, 7 the second =====
         mbar_wait(&acc_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int quarter = warp & 3;
+        const int second = (warp >= 2 && warp < 6) ? 0 : 1;
         const bool aligned = !p.accumulate && (p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && (n0 & 3) == 0 &&
                              (p.N & 3) == 0;
         if (aligned) {
@@ -170,12 +179,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const __grid_
             // 32 x 32 block through a private shared-memory tile (the operand stages are free once acc_bar has fired) and
             // writes 4 rows x 128 contiguous bytes per instruction.  The bias comes from shared memory (loaded at kernel
             // start; fetching it here from global memory was the largest stall).
-            float* tb = reinterpret_cast<float*>(base) + (warp - 2) * (32 * 36);
+            float* tb = reinterpret_cast<float*>(base) + warp * (32 * 36);
             const int rbase = m0 + quarter * 32;
             DropRng rng;
             const bool drop = p.drop_p > 0.f && !p.drop_on_a;
             if (drop) rng.init(p.drop_seed, resolve_offset(p.drop_offset, p.drop_offset_dev), p.drop_p);
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            const int nblk = (BN + 31) / 32, blk_mid = (nblk + 1) / 2;      // column blocks of 32: [0, blk_mid) first group, the rest second
+            for (int c0 = (second ? blk_mid : 0) * 32; c0 < (second ? nblk : blk_mid) * 32 && c0 < BN; c0 += 32) {
                 const int wcols = min(32, BN - c0);           // 32 or 16 (BN is a multiple of 16)
                 uint32_t r[32];
                 const uint32_t taddr = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
@@ -224,7 +234,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_nt_kernel(const __grid_
         } else {
             const int row = m0 + quarter * 32 + lane;
             float* crow = p.C + (int64_t)row * p.ldc + n0;
-            for (int c0 = 0; c0 < BN; c0 += 16) {
+            const int nblk16 = (BN + 15) / 16, mid16 = (nblk16 + 1) / 2;
+            for (int c0 = (second ? mid16 : 0) * 16; c0 < (second ? nblk16 : mid16) * 16; c0 += 16) {
                 uint32_t r[16];
                 const uint32_t taddr = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
                 asm volatile(
@@ -319,8 +330,8 @@ int launch_tc_gemm_nt_drop(const float* A, int64_t lda, const float* W, int64_t 
     p.drop_lda = lda; p.drop_on_a = drop_on_a;
     dim3 grid(cdiv(M, TC_BM), cdiv(N, BN));
     MMS_PROF_BEGIN(st);
-    if (four) MMS_LAUNCH(tc_gemm_nt_kernel<4>, grid, dim3(TC_THREADS), smem, st, mapA, mapB, p);
-    else MMS_LAUNCH(tc_gemm_nt_kernel<2>, grid, dim3(TC_THREADS), smem, st, mapA, mapB, p);
+    if (four) MMS_LAUNCH(tc_gemm_nt_kernel<4>, grid, dim3(NT_THREADS), smem, st, mapA, mapB, p);
+    else MMS_LAUNCH(tc_gemm_nt_kernel<2>, grid, dim3(NT_THREADS), smem, st, mapA, mapB, p);
     MMS_LAUNCH_CHECK("tc_gemm_nt_kernel");
     return MMS_OK;
 }
