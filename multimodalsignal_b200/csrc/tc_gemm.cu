@@ -35,10 +35,12 @@ struct TcGemmParams {
 };
 
 // dynamic smem: [stage][A_hi | A_lo | B_hi | B_lo] (1024-byte aligned tiles); NS = pipeline stages (2, or 4 for long reductions)
-// 256 threads: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = splitters; ALL EIGHT warps run the epilogue -- a warp reads
-// the TMEM lane quarter (warp % 4), so every quarter has two warps (2-5 and 0, 1, 6, 7) that take half of the columns each: the
-// epilogue (tcgen05.ld, shared-memory transpose, bias / dropout, 128-byte stores) was 0.7-5.5 us of a CTA's 12 us with four warps.
-constexpr int NT_THREADS = 256;
+// 384 threads = 12 warps: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-11 = operand splitters (clock stamps inside a CTA
+// showed the splitters setting the pace of a k-block with FOUR warps -- one per scheduler, every latency exposed; ten warps
+// overlap each other's).  ALL warps run the epilogue: a warp reads the TMEM lane quarter (warp % 4), so every quarter has three
+// warps that take every third block of 32 columns each (tcgen05.ld, shared-memory transpose, bias / dropout, 128-byte stores:
+// 0.7-5.5 us of a CTA's 12 us with four warps).  68 registers: two such CTAs still share an SM for the single-k-block product.
+constexpr int NT_THREADS = 384, NT_WARPS = NT_THREADS / 32, NT_SPLIT_THREADS = NT_THREADS - 64, NT_GROUPS = NT_WARPS / 4;
 template <int NS>
 __global__ void __launch_bounds__(NT_THREADS, 1) tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                    const __grid_constant__ CUtensorMap mapB, const TcGemmParams p) {
@@ -62,7 +64,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1) tc_gemm_nt_kernel(const __grid_
     if (threadIdx.x == 0) {
         for (int s = 0; s < NS; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&split_bar[s], 4);      // one arrival per splitter warp
+            mbar_init(&split_bar[s], NT_WARPS - 2);      // one arrival per splitter warp
             mbar_init(&empty_bar[s], 1);
         }
         mbar_init(&acc_bar, 1);
@@ -113,9 +115,9 @@ __global__ void __launch_bounds__(NT_THREADS, 1) tc_gemm_nt_kernel(const __grid_
             }
             umma_commit(&acc_bar);                     // accumulator complete
         }
-    } else if (warp < 6) {
-        // ===== operand splitters (warps 2..5) =====
-        const int t = threadIdx.x - 64;                // 0..127
+    } else {
+        // ===== operand splitters (warps 2 .. NT_WARPS - 1) =====
+        const int t = threadIdx.x - 64;                // 0 .. NT_SPLIT_THREADS - 1
         DropRng rng_a;
         const bool drop_a = p.drop_p > 0.f && p.drop_on_a;
         if (drop_a) rng_a.init(p.drop_seed, resolve_offset(p.drop_offset, p.drop_offset_dev), p.drop_p);
@@ -127,7 +129,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1) tc_gemm_nt_kernel(const __grid_
             {
                 float4* hi = reinterpret_cast<float4*>(st);
                 float4* lo = reinterpret_cast<float4*>(st + a_bytes);
-                for (int i = t; i < (int)(a_bytes / 16); i += 128) {
+                for (int i = t; i < (int)(a_bytes / 16); i += NT_SPLIT_THREADS) {
                     float4 v = hi[i];
                     if (drop_a) {
                         // 128-byte swizzle: row r of the tile holds its 16-byte chunk c at position c ^ (r & 7)
@@ -147,7 +149,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1) tc_gemm_nt_kernel(const __grid_
             {
                 float4* hi = reinterpret_cast<float4*>(st + 2 * a_bytes);
                 float4* lo = reinterpret_cast<float4*>(st + 2 * a_bytes + b_bytes);
-                for (int i = t; i < (int)(b_bytes / 16); i += 128) {
+                for (int i = t; i < (int)(b_bytes / 16); i += NT_SPLIT_THREADS) {
                     const float4 v = hi[i];
                     float4 h, l;
                     h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
@@ -165,12 +167,12 @@ __global__ void __launch_bounds__(NT_THREADS, 1) tc_gemm_nt_kernel(const __grid_
     }
     __syncwarp();             // lanes 1..31 of the producer / issuer warps wait here (no spinning beside lane 0's loop)
     {
-        // ===== epilogue (all warps): TMEM lane quarter (warp % 4) -> registers -> global; warps 2-5 take the first half of the
-        // column blocks, warps 0, 1, 6, 7 the second =====
+        // ===== epilogue (all warps): TMEM lane quarter (warp % 4) -> registers -> global; warp group (warp / 4) takes the column
+        // blocks group, group + NT_GROUPS, ... =====
         mbar_wait(&acc_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int quarter = warp & 3;
-        const int second = (warp >= 2 && warp < 6) ? 0 : 1;
+        const int group = warp >> 2;
         const bool aligned = !p.accumulate && (p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && (n0 & 3) == 0 &&
                              (p.N & 3) == 0;
         if (aligned) {
@@ -184,8 +186,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1) tc_gemm_nt_kernel(const __grid_
             DropRng rng;
             const bool drop = p.drop_p > 0.f && !p.drop_on_a;
             if (drop) rng.init(p.drop_seed, resolve_offset(p.drop_offset, p.drop_offset_dev), p.drop_p);
-            const int nblk = (BN + 31) / 32, blk_mid = (nblk + 1) / 2;      // column blocks of 32: [0, blk_mid) first group, the rest second
-            for (int c0 = (second ? blk_mid : 0) * 32; c0 < (second ? nblk : blk_mid) * 32 && c0 < BN; c0 += 32) {
+            for (int c0 = group * 32; c0 < BN; c0 += NT_GROUPS * 32) {
                 const int wcols = min(32, BN - c0);           // 32 or 16 (BN is a multiple of 16)
                 uint32_t r[32];
                 const uint32_t taddr = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
@@ -234,8 +235,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1) tc_gemm_nt_kernel(const __grid_
         } else {
             const int row = m0 + quarter * 32 + lane;
             float* crow = p.C + (int64_t)row * p.ldc + n0;
-            const int nblk16 = (BN + 15) / 16, mid16 = (nblk16 + 1) / 2;
-            for (int c0 = (second ? mid16 : 0) * 16; c0 < (second ? nblk16 : mid16) * 16; c0 += 16) {
+            for (int c0 = group * 16; c0 < BN; c0 += NT_GROUPS * 16) {
                 uint32_t r[16];
                 const uint32_t taddr = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
                 asm volatile(
@@ -317,7 +317,8 @@ int launch_tc_gemm_nt_drop(const float* A, int64_t lda, const float* W, int64_t 
     if (nkb >= 4 && option_get("NT_STAGES", 4) >= 4 && stage * 4 + 1024 <= 200 * 1024) stages = 4;
     const bool four = stages == 4;
     if (option_get("NT_TRIM_STAGES", 1) == 1 && nkb < TC_STAGES) stages = nkb;
-    const size_t smem = stage * stages + 1024;
+    // the epilogue's per-warp transpose tiles (NT_WARPS x 4.5 KB) reuse the operand stages
+    const size_t smem = (stage * stages > (size_t)NT_WARPS * 32 * 36 * 4 ? stage * stages : (size_t)NT_WARPS * 32 * 36 * 4) + 1024;
     static PerDeviceOnce attr_once;
     if (attr_once.need()) {
         MMS_CUDA(cudaFuncSetAttribute(tc_gemm_nt_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
