@@ -353,6 +353,8 @@ int launch_tc_gemm_nt_drop(const float* A, int64_t lda, const float* W, int64_t 
 constexpr int TN_KB = 32;           // reduction rows per k-block
 constexpr int TN_STAGES = 2;        // pipeline depth of the default instantiation (NS below)
 constexpr int TN_BLK = TN_KB * 128; // bytes of one [KB x 32 floats] column block
+// 384 threads as in the NT kernel: warp 0 = TMA, warp 1 = MMA, warps 2-11 split the operands, all twelve run the epilogue
+constexpr int TN_THREADS = 384, TN_WARPS = TN_THREADS / 32, TN_SPLIT_THREADS = TN_THREADS - 64, TN_GROUPS = TN_WARPS / 4;
 
 struct TcGemmTnParams {
     float* C;
@@ -369,7 +371,7 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 // NS = pipeline stages: 2 by default; 1 (MMS_TN_STAGES=1, experiment) halves the shared-memory footprint (<= 88 KB), so
 // that a weight-gradient CTA on a side stream no longer blocks its SM for the conv / pool kernels of the main chain.
 template <int NS>
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap mapA,
+__global__ void __launch_bounds__(TN_THREADS, 1) tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                    const __grid_constant__ CUtensorMap mapB, const TcGemmTnParams p) {
 #define TN_MAPA (&mapA)
 #define TN_MAPB (&mapB)
@@ -389,7 +391,7 @@ struct TnBatchMaps { CUtensorMap a[TN_MAX_BATCH], b[TN_MAX_BATCH]; };
 struct TnBatchParams { TcGemmTnParams p[TN_MAX_BATCH]; int nchunks[TN_MAX_BATCH]; };
 
 template <int NS>
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_tn_batch_kernel(const __grid_constant__ TnBatchMaps maps, const TnBatchParams bp) {
+__global__ void __launch_bounds__(TN_THREADS, 1) tc_gemm_tn_batch_kernel(const __grid_constant__ TnBatchMaps maps, const TnBatchParams bp) {
     const int j = blockIdx.y;
     if ((int)blockIdx.x >= bp.nchunks[j]) return;      // whole CTA leaves before any barrier / TMEM allocation
     const TcGemmTnParams p = bp.p[j];
@@ -444,8 +446,8 @@ int launch_tc_gemm_tn(const float* A, int64_t lda, int a_split, int a_skip, cons
     }
     MMS_REQUIRE(smem <= 220 * 1024, "tc_gemm_tn: shared memory %zu too large", smem);
     MMS_PROF_BEGIN(st);
-    if (ns == 1) tc_gemm_tn_kernel<1><<<cdiv(M, chunk), TC_THREADS, smem, st>>>(mapA, mapB, p);
-    else tc_gemm_tn_kernel<TN_STAGES><<<cdiv(M, chunk), TC_THREADS, smem, st>>>(mapA, mapB, p);
+    if (ns == 1) tc_gemm_tn_kernel<1><<<cdiv(M, chunk), TN_THREADS, smem, st>>>(mapA, mapB, p);
+    else tc_gemm_tn_kernel<TN_STAGES><<<cdiv(M, chunk), TN_THREADS, smem, st>>>(mapA, mapB, p);
     MMS_LAUNCH_CHECK("tc_gemm_tn_kernel");
     return MMS_OK;
 }
@@ -499,9 +501,9 @@ int launch_tc_gemm_tn_batch(const TnCall* calls, int n, cudaStream_t st) {
     MMS_REQUIRE(smem <= 220 * 1024, "tc_gemm_tn_batch: shared memory %zu too large", smem);
     dim3 grid(max_chunks, n);
     MMS_PROF_BEGIN(st);
-    if (ns == 1) tc_gemm_tn_batch_kernel<1><<<grid, TC_THREADS, smem, st>>>(maps, bp);
-    else if (ns == 2) tc_gemm_tn_batch_kernel<2><<<grid, TC_THREADS, smem, st>>>(maps, bp);
-    else tc_gemm_tn_batch_kernel<3><<<grid, TC_THREADS, smem, st>>>(maps, bp);
+    if (ns == 1) tc_gemm_tn_batch_kernel<1><<<grid, TN_THREADS, smem, st>>>(maps, bp);
+    else if (ns == 2) tc_gemm_tn_batch_kernel<2><<<grid, TN_THREADS, smem, st>>>(maps, bp);
+    else tc_gemm_tn_batch_kernel<3><<<grid, TN_THREADS, smem, st>>>(maps, bp);
     MMS_LAUNCH_CHECK("tc_gemm_tn_batch_kernel");
     return MMS_OK;
 }
