@@ -350,8 +350,11 @@ int launch_tc_gemm_nt_drop(const float* A, int64_t lda, const float* W, int64_t 
 //     to C with vector red.global.add.f32 (C is the zero-initialised flat gradient buffer);
 //   * 3xTF32 operand split and warp roles as in the NT kernel; the splitter warps also zero the B rows that the
 //     shift moves across a sequence boundary.
-constexpr int TN_KB = 32;           // reduction rows per k-block
-constexpr int TN_STAGES = 2;        // pipeline depth of the default instantiation (NS below)
+// 16 rows per k-block and 4 stages (round 2, after clock stamps inside a CTA): with 32-row k-blocks a stage is 88 KB, only two fit,
+// and a k-block then cost one exposed TMA latency (~2000 cycles) + its split + its MMAs = 3300 cycles; half-size k-blocks four deep
+// keep the loads ahead of the splitters.
+constexpr int TN_KB = 16;           // reduction rows per k-block
+constexpr int TN_STAGES = 4;        // pipeline depth of the default instantiation (NS below)
 constexpr int TN_BLK = TN_KB * 128; // bytes of one [KB x 32 floats] column block
 // 384 threads as in the NT kernel: warp 0 = TMA, warp 1 = MMA, warps 2-11 split the operands, all twelve run the epilogue
 constexpr int TN_THREADS = 384, TN_WARPS = TN_THREADS / 32, TN_SPLIT_THREADS = TN_THREADS - 64, TN_GROUPS = TN_WARPS / 4;
@@ -436,7 +439,7 @@ int launch_tc_gemm_tn(const float* A, int64_t lda, int a_split, int a_skip, cons
     if (chunk < 2 * TN_KB) chunk = 2 * TN_KB;
     p.chunk = chunk;
     const size_t stage = (size_t)2 * p.nblkA * TN_BLK + (size_t)2 * (p.nblkB + 1) * TN_BLK;
-    const int ns = option_get("TN_STAGES", 2) == 1 ? 1 : TN_STAGES;
+    const int ns = option_get("TN_STAGES", TN_STAGES) == 1 ? 1 : TN_STAGES;
     const size_t smem = stage * ns + 1024;
     static PerDeviceOnce attr_once;
     if (attr_once.need()) {
@@ -462,8 +465,8 @@ int launch_tc_gemm_tn_batch(const TnCall* calls, int n, cudaStream_t st) {
     memset(&bp, 0, sizeof(bp));
     int budget = option_get("TN_BATCH_CTAS", 148);
     if (budget < n) budget = n;
-    int ns = option_get("TN_STAGES", 2);           // 1, 2 or 3 pipeline stages; reduced until the largest problem's stages fit
-    ns = ns < 1 ? 1 : (ns > 3 ? 3 : ns);
+    int ns = option_get("TN_STAGES", TN_STAGES);           // 1 .. 4 pipeline stages; reduced until the largest problem's stages fit
+    ns = ns < 1 ? 1 : (ns > 4 ? 4 : ns);
     size_t stage_max = 0;
     int max_chunks = 0;
     for (int j = 0; j < n; ++j) {
@@ -494,6 +497,7 @@ int launch_tc_gemm_tn_batch(const TnCall* calls, int n, cudaStream_t st) {
     for (int j = n; j < TN_MAX_BATCH; ++j) { maps.a[j] = maps.a[0]; maps.b[j] = maps.b[0]; }     // unused slots: valid bytes, never read
     static PerDeviceOnce attr_once;
     if (attr_once.need()) {
+        MMS_CUDA(cudaFuncSetAttribute(tc_gemm_tn_batch_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         MMS_CUDA(cudaFuncSetAttribute(tc_gemm_tn_batch_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         MMS_CUDA(cudaFuncSetAttribute(tc_gemm_tn_batch_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         MMS_CUDA(cudaFuncSetAttribute(tc_gemm_tn_batch_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
@@ -503,7 +507,8 @@ int launch_tc_gemm_tn_batch(const TnCall* calls, int n, cudaStream_t st) {
     MMS_PROF_BEGIN(st);
     if (ns == 1) tc_gemm_tn_batch_kernel<1><<<grid, TN_THREADS, smem, st>>>(maps, bp);
     else if (ns == 2) tc_gemm_tn_batch_kernel<2><<<grid, TN_THREADS, smem, st>>>(maps, bp);
-    else tc_gemm_tn_batch_kernel<3><<<grid, TN_THREADS, smem, st>>>(maps, bp);
+    else if (ns == 3) tc_gemm_tn_batch_kernel<3><<<grid, TN_THREADS, smem, st>>>(maps, bp);
+    else tc_gemm_tn_batch_kernel<4><<<grid, TN_THREADS, smem, st>>>(maps, bp);
     MMS_LAUNCH_CHECK("tc_gemm_tn_batch_kernel");
     return MMS_OK;
 }

@@ -92,7 +92,7 @@ def test_tc_gemm_tn_3xtf32(B, L, H, N2, lda_mul, ldb_mul, mode, shift):
 
 @pytest.mark.skipif(os.environ.get("MMS_TEST_EXPERIMENTAL") != "1",
                     reason="batched TN kernel: written without GPU access at the end of round 1, opt-in until it has run once")
-@pytest.mark.parametrize("stages", [2, 1, 3])
+@pytest.mark.parametrize("stages", [4, 2, 1, 3])
 def test_tc_gemm_tn_batch_equals_single_launches(stages):
     """mms_tc_gemm_tn_batch on the four weight-gradient products of a bidirectional GRU layer (both directions' dW_ih and
     dW_hh out of one D [M, 8H]) against float64 and against four single launches."""

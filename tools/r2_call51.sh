@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-T=r2c53
+T=r2c55
 timeout 900 python -m pytest tests/test_gpu_tc_gemm.py tests/test_gpu_model.py tests/test_gpu_ops.py -m gpu -q -x > gpurun_out/${T}_suite.log 2>&1; echo "suite rc=$?"; tail -2 gpurun_out/${T}_suite.log
 timeout 200 python tools/graph_timeline.py --out gpurun_out/${T}_timeline.json > gpurun_out/${T}_timeline.log 2>&1; echo "timeline rc=$?"
 grep -E "span|tc_gemm" gpurun_out/${T}_timeline.log
