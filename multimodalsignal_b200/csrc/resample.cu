@@ -277,29 +277,30 @@ __global__ void __launch_bounds__(256, 2) spectrum_fix_pair2_kernel(const double
     const bool has2 = 2 * p + 1 < n_sig;
     const int64_t m = N < num ? N : num, K = m2 - 1;
     const double scale = ((double)num / (double)N) / (double)M;
-    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < M2; n += (int64_t)gridDim.x * blockDim.x) {
-        double2 v = make_double2(0.0, 0.0);
-        if (n <= 2 * K) {
-            const int64_t k = n - K, kk = k < 0 ? -k : k;
-            const int64_t jp = K + kk, jn = K - kk;
-            const double2 Zp = cmul(cv[jp], chirp(jp, N, -1));
-            const double2 Zn = cmul(cv[jn], chirp(jn, N, -1));
-            double2 X1 = make_double2(0.5 * (Zp.x + Zn.x) * scale, 0.5 * (Zp.y - Zn.y) * scale);
-            double2 X2 = make_double2(0.5 * (Zp.y + Zn.y) * scale, -0.5 * (Zp.x - Zn.x) * scale);
-            if ((m & 1) == 0 && num != N && kk == m / 2) {
-                const double f = num < N ? 2.0 : 0.5;
-                X1.x *= f; X1.y *= f; X2.x *= f; X2.y *= f;
-            }
-            double2 G1 = make_double2(2.0 * X1.x, 2.0 * X1.y), G2 = make_double2(2.0 * X2.x, 2.0 * X2.y);
-            if (kk == 0 || ((num & 1) == 0 && kk == num / 2)) { G1 = make_double2(X1.x, 0.0); G2 = make_double2(X2.x, 0.0); }
-            if (!has2) G2 = make_double2(0.0, 0.0);
-            double2 d;
-            if (k > 0) d = make_double2(0.5 * (G1.x - G2.y), 0.5 * (G1.y + G2.x));
-            else if (k < 0) d = make_double2(0.5 * (G1.x + G2.y), 0.5 * (G2.x - G1.y));
-            else d = make_double2(G1.x, G2.x);
-            v = cmul(d, chirp(n, num, +1));
+    // one thread per |k|: X1, X2 of bin |k| give both d[+k] (index K + k) and d[-k] (index K - k); the tail beyond 2K is zeroed
+    for (int64_t kk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; kk < M2 - K; kk += (int64_t)gridDim.x * blockDim.x) {
+        if (kk > K) {
+            out[K + kk] = make_double2(0.0, 0.0);
+            continue;
         }
-        out[n] = v;
+        const int64_t jp = K + kk, jn = K - kk;
+        const double2 Zp = cmul(cv[jp], chirp(jp, N, -1));
+        const double2 Zn = cmul(cv[jn], chirp(jn, N, -1));
+        double2 X1 = make_double2(0.5 * (Zp.x + Zn.x) * scale, 0.5 * (Zp.y - Zn.y) * scale);
+        double2 X2 = make_double2(0.5 * (Zp.y + Zn.y) * scale, -0.5 * (Zp.x - Zn.x) * scale);
+        if ((m & 1) == 0 && num != N && kk == m / 2) {
+            const double f = num < N ? 2.0 : 0.5;
+            X1.x *= f; X1.y *= f; X2.x *= f; X2.y *= f;
+        }
+        double2 G1 = make_double2(2.0 * X1.x, 2.0 * X1.y), G2 = make_double2(2.0 * X2.x, 2.0 * X2.y);
+        if (kk == 0 || ((num & 1) == 0 && kk == num / 2)) { G1 = make_double2(X1.x, 0.0); G2 = make_double2(X2.x, 0.0); }
+        if (!has2) G2 = make_double2(0.0, 0.0);
+        if (kk == 0) {
+            out[K] = cmul(make_double2(G1.x, G2.x), chirp(K, num, +1));
+        } else {
+            out[K + kk] = cmul(make_double2(0.5 * (G1.x - G2.y), 0.5 * (G1.y + G2.x)), chirp(K + kk, num, +1));
+            out[K - kk] = cmul(make_double2(0.5 * (G1.x + G2.y), 0.5 * (G2.x - G1.y)), chirp(K - kk, num, +1));
+        }
     }
 }
 
