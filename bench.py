@@ -602,7 +602,7 @@ def preprocess_measure(args, subjects=None):
     sampler.start()
     l0 = lib.mms_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = max(1, args.steps if args.steps < 50 else 3)
+    reps = max(1, args.steps if args.steps < 50 else 10)      # 15 subjects per pass, ~26 ms: ten passes average out the first pass's ramp
     e0.record()
     nwin = 0
     for _ in range(reps):
