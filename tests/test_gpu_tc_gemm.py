@@ -1,6 +1,5 @@
 """tcgen05 / TMA GEMM (3xTF32) against a float64 matmul.  Stated tolerance: 1e-5 of max|C| -- two
 orders of magnitude tighter than a plain tf32 GEMM would pass (5e-4), i.e. fp32-class accuracy."""
-import os
 
 import pytest
 import torch
@@ -90,8 +89,6 @@ def test_tc_gemm_tn_3xtf32(B, L, H, N2, lda_mul, ldb_mul, mode, shift):
     assert (b2 - bd).abs().max().item() <= 4e-5 * refb.abs().max().item()
 
 
-@pytest.mark.skipif(os.environ.get("MMS_TEST_EXPERIMENTAL") != "1",
-                    reason="batched TN kernel: written without GPU access at the end of round 1, opt-in until it has run once")
 @pytest.mark.parametrize("stages", [4, 2, 1, 3])
 def test_tc_gemm_tn_batch_equals_single_launches(stages):
     """mms_tc_gemm_tn_batch on the four weight-gradient products of a bidirectional GRU layer (both directions' dW_ih and
