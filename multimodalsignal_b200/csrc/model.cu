@@ -745,12 +745,12 @@ static int model_backward(const mms_cnngru_desc* d, const float* x, const float*
         }
         rc = launch_gru_bwd(dirs, 2, B, H, p, d->rng_seed, d->rng_offset, d->rng_offset_dev, st);
         if (rc) return rc;
-        const bool tn_after = option_get("TN_AFTER_NT", 0) == 1;
+        const bool tn_after = option_get("TN_AFTER_NT", 1) == 1;
         if (defer_mode == 1 && l == top - 1 && !tn_after) {
             rc = top_wgrad();
             if (rc) return rc;
         }
-        // Weight gradients of this layer: side stream.  MMS_TN_AFTER_NT=1 (experiment; measured 3 % slower than forking first, so off) forks them AFTER the input-gradient product
+        // Weight gradients of this layer: side stream.  MMS_TN_AFTER_NT=1 (default since the GEMM CTAs were re-staffed: 1.7 % faster; it was 3 % slower with the earlier kernels) forks them AFTER the input-gradient product
         // below has been enqueued: both stream the same D rows, and started together the 148-CTA weight-gradient kernels
         // stretched the (critical-path) input-gradient product 2.4x (round-2 timeline); started behind it they overlap the
         // encoder's backward kernels instead.

@@ -350,11 +350,12 @@ int launch_tc_gemm_nt_drop(const float* A, int64_t lda, const float* W, int64_t 
 //     to C with vector red.global.add.f32 (C is the zero-initialised flat gradient buffer);
 //   * 3xTF32 operand split and warp roles as in the NT kernel; the splitter warps also zero the B rows that the
 //     shift moves across a sequence boundary.
-// 16 rows per k-block and 4 stages (round 2, after clock stamps inside a CTA): with 32-row k-blocks a stage is 88 KB, only two fit,
+// 16 rows per k-block and 3 stages (round 2, after clock stamps inside a CTA): with 32-row k-blocks a stage is 88 KB, only two fit,
 // and a k-block then cost one exposed TMA latency (~2000 cycles) + its split + its MMAs = 3300 cycles; half-size k-blocks four deep
-// keep the loads ahead of the splitters.
+// keep the loads ahead of the splitters (four deep measured 1.7 % slower in the step than three: the fourth stage's
+// 44 KB of shared memory keep the chain's CTAs off the SM).
 constexpr int TN_KB = 16;           // reduction rows per k-block
-constexpr int TN_STAGES = 4;        // pipeline depth of the default instantiation (NS below)
+constexpr int TN_STAGES = 3;        // pipeline depth of the default instantiation (NS below): 3 x 44 KB leave room for a co-resident CTA of the chain
 constexpr int TN_BLK = TN_KB * 128; // bytes of one [KB x 32 floats] column block
 // 384 threads as in the NT kernel: warp 0 = TMA, warp 1 = MMA, warps 2-11 split the operands, all twelve run the epilogue
 constexpr int TN_THREADS = 384, TN_WARPS = TN_THREADS / 32, TN_SPLIT_THREADS = TN_THREADS - 64, TN_GROUPS = TN_WARPS / 4;
@@ -463,7 +464,9 @@ int launch_tc_gemm_tn_batch(const TnCall* calls, int n, cudaStream_t st) {
     TnBatchMaps maps;
     TnBatchParams bp;
     memset(&bp, 0, sizeof(bp));
-    int budget = option_get("TN_BATCH_CTAS", 148);
+    // 80 CTAs, not one per SM: the products run beside the critical chain (the dseq product, pool / conv backward), and 68 free SMs
+    // serve it better than a 1.9x shorter weight-gradient launch (A/B r2c60: 148 -> 0.451, 120 -> 0.448, 100 -> 0.443, 80 -> 0.440, 64 -> 0.442 ms)
+    int budget = option_get("TN_BATCH_CTAS", 80);
     if (budget < n) budget = n;
     int ns = option_get("TN_STAGES", TN_STAGES);           // 1 .. 4 pipeline stages; reduced until the largest problem's stages fit
     ns = ns < 1 ? 1 : (ns > 4 ? 4 : ns);

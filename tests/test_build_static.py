@@ -24,7 +24,7 @@ def facts():
 
 def test_tensor_core_kernels_use_tcgen05_tma_and_tmem(facts):
     k, _ = facts
-    for name in ("tc_gemm_nt_kernel<2>", "tc_gemm_nt_kernel<4>", "tc_gemm_tn_kernel<4>", "tc_gemm_tn_batch_kernel<4>", "conv1d_fwd_tc_kernel<16, 7, 2, 3>"):
+    for name in ("tc_gemm_nt_kernel<2>", "tc_gemm_nt_kernel<4>", "tc_gemm_tn_kernel<3>", "tc_gemm_tn_batch_kernel<3>", "conv1d_fwd_tc_kernel<16, 7, 2, 3>"):
         f = k[name]
         assert f.get("UTMALDG (TMA load)", 0) > 0, name
         assert f.get("UTC*MMA (tcgen05.mma)", 0) > 0, name
