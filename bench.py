@@ -600,9 +600,10 @@ def preprocess_measure(args, subjects=None):
     torch.cuda.synchronize()
     sampler = ClockSampler(torch.cuda.current_device())
     sampler.start()
-    l0 = lib.mms_launch_count()
+    time.sleep(0.4)                                                     # nvidia-smi's start-up (NVML initialisation) stalls launches: keep it out of
+    l0 = lib.mms_launch_count()                                         # a region that is ~100 host-enqueued launches per subject
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = max(1, args.steps if args.steps < 50 else 10)      # 15 subjects per pass, ~26 ms: ten passes average out the first pass's ramp
+    reps = max(1, args.steps if args.steps < 50 else 20)      # 15 subjects per pass, ~26 ms per pass
     e0.record()
     nwin = 0
     for _ in range(reps):

@@ -65,9 +65,24 @@ def resample_on_device(x: torch.Tensor, num: int) -> torch.Tensor:
         nbytes = lib.mms_resample_workspace_bytes(n, num, k)
         if nbytes < 0:
             raise _ext.MmsError(f"resample: unsupported lengths {n} -> {num}")
-        ws = torch.empty(int(nbytes), dtype=torch.uint8, device=x.device)
+        ws = _workspace(x.device, int(nbytes))
         check(lib.mms_resample_f64(ptr(x[s0:s0 + k]), n, num, k, ptr(y[s0:s0 + k]), ptr(ws), int(nbytes), stream()))
     return y
+
+
+_WORKSPACES = {}
+
+
+def _workspace(device, nbytes):
+    """One grow-only resample workspace per (device, stream): calls on a stream run in order, so they can share it, and the
+    caching allocator is not asked for a fresh 0.1-0.5 GB block per call and stream (every recording has its own length, so
+    those requests rarely hit a cached block of the right size; an occasional pass over the subjects ran 2.5x slower)."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _WORKSPACES.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(int(nbytes * 1.05) + 4096, dtype=torch.uint8, device=device)
+        _WORKSPACES[key] = ws
+    return ws
 
 
 _SIDE_STREAMS = {}
