@@ -534,6 +534,7 @@ static int conv_dgrad_launch_pad(const float* dy, const float* w, int B, int CI,
     auto kern = conv1d_dgrad_kernel<CO, KW, S, P, TI, CPAD>;
     static PerDeviceOnce attr_once;
     if (attr_once.need()) { MMS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); }
+    MMS_REQUIRE(smem <= 96 * 1024, "conv1d_dgrad: shared memory %zu too large", smem);
     dim3 grid(cdiv(Lin, TI), B);
     MMS_PROF_BEGIN(st);
     MMS_LAUNCH(kern, grid, dim3(TI), smem, st, dy, w, dx, xdot, dgate, CI, Lin, Lout, bn);
